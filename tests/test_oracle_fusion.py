@@ -1,0 +1,82 @@
+"""Oracle (oracle/fusion_oracle.py) vs golden vectors produced by the REAL reference src/fusion.py."""
+import gzip
+import hashlib
+import json
+import os
+
+import pytest
+
+from oracle import fusion_oracle as fo
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "fusion_weighted.json.gz")
+
+
+def load_gold():
+    with gzip.open(GOLD, "rt") as f:
+        return json.load(f)
+
+
+def rows_to_runs(case, rankers):
+    runs = {}
+    for ranker in rankers:
+        per_q = {}
+        for (qid, _it, docno, rank, score, _tag) in case["rows"][ranker]:
+            per_q.setdefault(qid, []).append((docno, float(score), int(rank)))
+        runs[ranker] = per_q
+    return runs
+
+
+METHODS = {"wcombsum": (fo.SUM, 60), "wcombmnz": (fo.MNZ, 60), "wrrf": (fo.RRF, 60), "wrrf_k10": (fo.RRF, 10)}
+
+
+@pytest.mark.parametrize("case_idx", [0, 1, 2])
+def test_weighted_matches_reference_bit_exact(case_idx):
+    gold = load_gold()
+    case = gold["cases"][case_idx]
+    runs = rows_to_runs(case, gold["rankers"])
+    for key, res in case["results"].items():
+        mname, idx = key.split("@")
+        method, k = METHODS[mname]
+        fused = fo.weighted_fusion(runs, case["qpp"], method, int(idx), k)
+        ref = {q: [(d, float(s)) for d, s in lst] for q, lst in res["fused"].items()}
+        assert list(fused.keys()) == list(ref.keys()), key
+        for q in ref:
+            assert fused[q] == ref[q], (case["name"], key, q)   # order, doc ids and float64 bits
+        lines = fo.runfile_lines(fused, tag=f"{mname}-x")
+        assert len(lines) == res["runfile_n"]
+        assert lines[:25] == res["runfile_head"]
+        assert hashlib.sha256("\n".join(lines).encode()).hexdigest() == res["runfile_sha256"]
+
+
+def test_missing_weight_raises_keyerror_even_without_rows():
+    runs = {"A": {"1": [("d1", 0.5, 1)]}, "B": {}}
+    qpp = {"1": {"A": [0.1] * 13}}
+    with pytest.raises(KeyError):
+        fo.weighted_fusion(runs, qpp, fo.SUM, 5)
+    with pytest.raises(IndexError):
+        fo.weighted_fusion({"A": runs["A"]}, {"1": {"A": [0.1] * 3}}, fo.SUM, 5)
+
+
+def test_ranx_restatement_formulas():
+    # hand-computed: two runs, min-max per run, CombSUM / CombMNZ / RRF
+    a = [("x", 3.0, 1), ("y", 2.0, 2), ("z", 1.0, 3)]
+    b = [("y", 10.0, 1), ("w", 5.0, 2)]
+    docs, s, c = fo.fuse_ranx_query([a, b], fo.SUM)
+    assert docs == ["x", "y", "z", "w"]
+    assert s == [1.0, 1.5, 0.0, 0.0] and c == [1, 2, 1, 1]
+    docs, s, c = fo.fuse_ranx_query([a, b], fo.MNZ)
+    assert s == [1.0, 3.0, 0.0, 0.0]
+    docs, s, c = fo.fuse_ranx_query([a, b], fo.MNZ, mnz_skip_zero=True)
+    assert c == [1, 2, 0, 0] and s == [1.0, 3.0, 0.0, 0.0]
+    docs, s, c = fo.fuse_ranx_query([a, b], fo.RRF, rrf_k=60)
+    assert s == [1 / 61, 1 / 62 + 1 / 61, 1 / 63, 1 / 62]
+    # duplicate docno: first position, last score (python dict semantics of _df_runs_to_ranx)
+    docs, s, c = fo.fuse_ranx_query([[("x", 1.0, 1), ("y", 0.5, 2), ("x", 0.0, 3)]], fo.SUM)
+    assert docs == ["y", "x"] and s == [1.0, 0.0]
+    # constant list: denominator guard 1e-9 -> all zeros
+    docs, s, c = fo.fuse_ranx_query([[("x", 0.7, 1), ("y", 0.7, 2)]], fo.SUM)
+    assert s == [0.0, 0.0]
+
+
+def test_rank_order_is_stable_descending():
+    assert fo.rank_order([0.5, 1.0, 0.5, 1.0, -0.0, 0.0]) == [1, 3, 0, 2, 4, 5]
