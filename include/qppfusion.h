@@ -1,0 +1,156 @@
+/*
+ * qppfusion.h -- C ABI of libqppfusion.so: the B200 (sm_100a) implementation of QPP-Fusion-RAG's
+ * retrieval-scoring -> QPP -> rank-fusion hot path.
+ *
+ * The reference (PoisedDok/QPP-Fusion-RAG) has no FFI / plugin registry for this path: its boundary is
+ * a set of Python functions (src/fusion.py, src/qpp.py, src/retrievers/bge.py) over three foreign
+ * engines (ranx/numba, a JVM subprocess, FAISS).  Each entry point below replaces the arithmetic
+ * inside one of those call sites; the reference-side binding is a ctypes stub.
+ *
+ * Conventions
+ *   - every function returns 0 (QF_OK) or a negative QF_E_* code; qf_last_error() gives the message
+ *     for the calling thread.  No C++ exception crosses this boundary.
+ *   - all buffers are CALLER-OWNED DEVICE pointers (PyTorch allocates them); functions never allocate
+ *     device memory, never synchronise the device, and enqueue all work on `stream`
+ *     (a cudaStream_t passed as void*).
+ *   - there is no CPU fallback: without an sm_100 device every compute entry point fails with
+ *     QF_E_NO_DEVICE.
+ *   - row-major, innermost dimension last.  Q = queries, R = retrievers (runs), K = list capacity.
+ */
+#ifndef QPPFUSION_H_
+#define QPPFUSION_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QF_ABI_VERSION 1
+
+/* status codes */
+#define QF_OK               0
+#define QF_E_INVALID       -1   /* bad argument (null pointer, negative size, unknown enum) */
+#define QF_E_UNSUPPORTED   -2   /* valid request outside the implemented envelope (e.g. R*K too large) */
+#define QF_E_CUDA          -3   /* a CUDA runtime call failed; message has cudaGetErrorString */
+#define QF_E_NO_DEVICE     -4   /* no CUDA device, or device is not compute capability 10.x */
+#define QF_E_WORKSPACE     -5   /* workspace too small; call the matching *_workspace_bytes first */
+
+const char* qf_last_error(void);
+int         qf_abi_version(void);
+/* 0 if `device` is a compute-capability-10.x GPU this library can run on. */
+int         qf_device_check(int device);
+
+/* ------------------------------------------------------------------------------------------------
+ * Rank fusion  --  replaces ranx.fuse (src/fusion.py:182,201,226) and the weighted_* Python loops
+ *                  (src/fusion.py:266-278, 309-327, 361-377)
+ * ---------------------------------------------------------------------------------------------- */
+#define QF_METHOD_SUM 0    /* CombSUM  / W-CombSUM : sum_r w_r * s_r(d)                               */
+#define QF_METHOD_MNZ 1    /* CombMNZ  / W-CombMNZ : count(d) * sum_r w_r * s_r(d)                    */
+#define QF_METHOD_RRF 2    /* RRF      / W-RRF     : sum_r w_r / (rrf_k + rank_r(d))                  */
+
+#define QF_NORM_NONE   0   /* weighted_* path: scores used as given (src/fusion.py:275)               */
+#define QF_NORM_MINMAX 1   /* ranx default norm="min-max": (s-min)/max(max-min,1e-9) per (q, r) list  */
+
+#define QF_SCORE_F64   0   /* double scores[Q][R][K]                                                  */
+#define QF_SCORE_F32   1   /* float  scores[Q][R][K]  (widened exactly to double)                     */
+#define QF_SCORE_MICRO 2   /* int32  scores[Q][R][K] = round(score * 1e6): the ".6f" text value;      */
+                           /* the kernel reconstructs exactly the double float("x.xxxxxx") parses to */
+
+/* flags */
+#define QF_FLAG_MNZ_SKIP_ZERO     1u  /* MNZ count ignores postings whose (normalised) score == 0.0   */
+#define QF_FLAG_REQUIRE_SORTED    2u  /* ranx semantics: each list must be sorted by score descending */
+                                      /* and duplicate-free (the packer guarantees it); violations    */
+                                      /* are reported in out_status, never silently repaired          */
+#define QF_FLAG_UNRANKED_OUTPUT   4u  /* skip the final ranking: outputs stay in first-seen order     */
+
+/* per-query status bits written to out_status[Q] */
+#define QF_QSTAT_DUPLICATES   1   /* a doc id occurs twice inside one list (handled exactly; info)    */
+#define QF_QSTAT_UNSORTED     2   /* QF_FLAG_REQUIRE_SORTED violated, or RRF ranks not ascending      */
+#define QF_QSTAT_BAD_LEN      4   /* lens[q][r] < 0 or > K; the query produced no output              */
+
+/*
+ * One launch fuses Q queries.  For query q, list r holds lens[q][r] postings (doc id, score[, rank])
+ * in visiting order; rank defaults to position+1 when `ranks` is NULL (RRF with explicit ranks requires
+ * them ascending within each list, as pandas sort_values("rank") would leave them, src/fusion.py:371).
+ * weights == NULL means unweighted (w = 1).
+ *
+ * Semantics (bit-exact with the reference's float64 arithmetic):
+ *   visiting order  = r ascending, then row order; union kept in FIRST-SEEN order;
+ *   accumulation    = acc <- fl(acc + fl(w * s))      (SUM/MNZ, no FMA contraction)
+ *                     acc <- fl(acc + fl(w / (rrf_k + rank)))  (RRF)
+ *   MNZ             = fl(acc * count), count = postings of the doc (all rows, duplicates included)
+ *   ranking         = score descending, ties by first-seen order (Python's stable sort,
+ *                     src/fusion.py:488); -0.0 == +0.0.
+ *
+ * Outputs, per query q (row stride = R*K):
+ *   out_ids[q][j], out_scores[q][j] : j-th ranked doc and its fused float64 score, j < out_lens[q]
+ *   out_counts[q][j] (nullable)     : number of postings merged into that doc
+ *   out_pos[q][j]    (nullable)     : the doc's index in first-seen order (to rebuild the reference's
+ *                                     unsorted return value)
+ *   out_status[q]    (nullable)     : QF_QSTAT_* bits
+ *
+ * Envelope: R*K <= qf_fuse_max_postings() (shared-memory resident per query), R <= 32.
+ */
+int qf_fuse_max_postings(void);
+int qf_fuse(const int32_t* doc_ids, const void* scores, int score_type, const int32_t* ranks,
+            const int32_t* lens, const double* weights,
+            int Q, int R, int K, int method, int norm, double rrf_k, uint32_t flags,
+            int32_t* out_ids, double* out_scores, uint16_t* out_counts, uint16_t* out_pos,
+            int32_t* out_lens, int32_t* out_status, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * QPP statistics  --  replaces the JVM round trip QPPBridge.compute_batch -> qpp.QPPBridge
+ *                     (src/qpp.py:117-171; src/qpp/java/qpp/QPPBridge.java:134-453)
+ * ---------------------------------------------------------------------------------------------- */
+#define QF_QPP_BRIDGE_COLS   13  /* nqc smv wig SigmaMax SigmaX RSD UEF MaxIDF avgidf cumnqc snqc dense-qpp dense-qpp-m */
+#define QF_QPP_RESEARCH_COLS  5  /* rsd_bootstrap smv_research wig_research sigmax_research scnqc_research */
+#define QF_QPP_COLS          (QF_QPP_BRIDGE_COLS + QF_QPP_RESEARCH_COLS)
+
+/*
+ * For each of the Q*R lists: scores[q][r][0..len) must be sorted descending (what
+ * compute_qpp_for_res_file's sorted(reverse=True), src/qpp.py:304-305, produces; violations set
+ * out_status).  The 13 bridge columns use the first min(k_cut, len, top_k) scores rounded to float32
+ * (Gson getAsFloat, QPPBridge.java:69) and widened to double; out[q][r][0..13) is in
+ * config.qpp.methods order (config/defaults.yaml:164-177).
+ *
+ * text_feats[q] = {n_terms, n_unique, max_len, sum_len} of queryText.toLowerCase().split("\\s+")
+ * (Java semantics; computed on the host, QPPBridge.java:250,272,369,386).
+ *
+ * Research columns out[q][r][13..18) (RSDSpecificity.java:22-52 bootstrap over NQCSpecificity,
+ * SMVSpecificity, WIGSpecificity, SigmaXSpecificity, NQCCalibratedSpecificity) are computed when
+ * `perms` != NULL: perms[s][0..perm_len) are caller-supplied permutations of range(perm_len)
+ * (perm_len >= K), one per bootstrap sample (n_samples, reference uses 10); query_idf[q] (nullable,
+ * default 1.0) stands in for maxIDF(q), which needs a Lucene index.  Without perms the 5 columns are 0.
+ */
+int qf_qpp_stats(const void* scores, int score_type, const int32_t* lens, const int32_t* text_feats,
+                 const double* query_idf, const int32_t* perms, int n_samples, int perm_len,
+                 int Q, int R, int K, int top_k, int k_cut, int wig_k,
+                 double* out, int32_t* out_status, void* stream);
+
+/*
+ * Cross-query column normalisation of one retriever's [Q][ncols] block, _normalize_qpp
+ * (src/qpp.py:340-374): mode 1 = minmax ((v-min)/(max-min if max>min else 1)), 2 = zscore
+ * ((v-mean)/(std_pop or 1)).  `vals` is [Q][R][ncols]; each (r, col) is normalised over q, in place.
+ * When `round6` != 0 the result is additionally passed through the "%.6f" text round trip
+ * (src/qpp.py:333 -> src/data_utils.py:290) so it equals the value fusion reads back from the .qpp file.
+ * ws: qf_qpp_colnorm_workspace_bytes(R, ncols) bytes of device scratch.
+ */
+#define QF_COLNORM_MINMAX 1
+#define QF_COLNORM_ZSCORE 2
+size_t qf_qpp_colnorm_workspace_bytes(int R, int ncols);
+int qf_qpp_colnorm(double* vals, int Q, int R, int ncols, int mode, int round6,
+                   void* ws, size_t ws_bytes, void* stream);
+
+/*
+ * weights[q][r] = vals[q][r][col]  (col >= 0)  or  mean over the first `ncols_mean` columns
+ * (col == -1, get_qpp_weight's fusion mode, src/fusion.py:152-153: sum(scores)/len(scores)).
+ */
+int qf_qpp_select_weight(const double* vals, int Q, int R, int ncols, int col, int ncols_mean,
+                         double* weights, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QPPFUSION_H_ */

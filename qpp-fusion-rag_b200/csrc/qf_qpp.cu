@@ -1,0 +1,510 @@
+// qf_qpp_stats / qf_qpp_colnorm / qf_qpp_select_weight
+//
+// Batched score-distribution QPP predictors: one warp per (query, retriever) list, float64 arithmetic,
+// coalesced loads of the list prefix, warp-shuffle reductions.  Restates
+//   qpp.QPPBridge.computeQPPScores            reference src/qpp/java/qpp/QPPBridge.java:134-453
+//   the research predictors behind the names  NQC/SMV/WIG/SigmaX/NQCCalibrated/RSD Specificity.java
+//   OverlapStats.computeRBO                   src/qpp/java/correlation/OverlapStats.java:77-99
+//   _normalize_qpp + "%.6f" round trip        src/qpp.py:329-374
+//   get_qpp_weight                            src/fusion.py:116-158
+#include "qf_common.cuh"
+
+namespace {
+
+constexpr int MAXK = 128;        // k_cut envelope (reference uses 50)
+constexpr int MAXLIST = 1024;    // list length envelope for the bootstrap columns
+constexpr int WARPS = 4;
+constexpr int NT = WARPS * 32;
+
+struct QppParams {
+  const void* scores;
+  const int32_t* lens;
+  const int32_t* text_feats;
+  const double* query_idf;
+  const int32_t* perms;
+  int n_samples, perm_len;
+  int Q, R, K, top_k, k_cut, wig_k;
+  double* out;
+  int32_t* out_status;
+};
+
+// decimal micro-units -> nearest float32 of the DECIMAL value (Float.parseFloat semantics): the
+// double quotient is correctly rounded; if it sits exactly on a float32 rounding boundary the sign of
+// the exact residual decides.
+__device__ __forceinline__ float micro_to_f32(int v) {
+  const double d = __ddiv_rn((double)v, 1.0e6);
+  const float fu = __double2float_ru(d), fd = __double2float_rd(d);
+  if (fu == fd) return fu;
+  const double mid = 0.5 * ((double)fu + (double)fd);
+  if (d > mid) return fu;
+  if (d < mid) return fd;
+  const double res = fma(d, 1.0e6, -(double)v);   // sign(d - v/1e6)
+  if (res > 0) return fd;
+  if (res < 0) return fu;
+  return __double2float_rn(d);
+}
+
+template <int ST> struct Raw;
+template <> struct Raw<QF_SCORE_F64> { using type = double; static __device__ float f32(double v) { return __double2float_rn(v); } };
+template <> struct Raw<QF_SCORE_F32> { using type = float;  static __device__ float f32(float v) { return v; } };
+template <> struct Raw<QF_SCORE_MICRO> { using type = int;  static __device__ float f32(int v) { return micro_to_f32(v); } };
+
+// population variance of x[idx(j)], j < cnt, by the two-pass formula; all lanes get the result
+template <typename F>
+__device__ __forceinline__ double warp_var(F get, int cnt, int lane, double* mean_out) {
+  double s = 0.0;
+  for (int j = lane; j < cnt; j += 32) s += get(j);
+  s = qf::warp_sum(s);
+  const double mean = s / (double)cnt;
+  double v = 0.0;
+  for (int j = lane; j < cnt; j += 32) {
+    const double d = get(j) - mean;
+    v += d * d;
+  }
+  v = qf::warp_sum(v);
+  if (mean_out) *mean_out = mean;
+  return v / (double)cnt;
+}
+
+template <int ST>
+__global__ void __launch_bounds__(NT) qpp_kernel(const QppParams p) {
+  using raw_t = typename Raw<ST>::type;
+  __shared__ double s_x[WARPS][MAXK];          // first k scores (float32-rounded, widened)
+  __shared__ double s_win[WARPS][MAXK];        // var of x[0:i]
+  __shared__ float s_all[WARPS][MAXLIST];      // whole list as float32 (bootstrap)
+  __shared__ unsigned s_cnt[WARPS][MAXLIST / 4 + 1];   // RBO depth histogram, 4 x 8-bit counters per word
+                                                        // (a depth bucket holds at most 2 sample entries)
+  __shared__ unsigned short s_samp[WARPS][MAXK];
+  __shared__ double s_pw[MAXLIST];             // p^(d-1)
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool research = p.perms != nullptr;
+  const double p09 = (double)0.9f;              // RBO p is a Java float
+  if (research) {
+    for (int d = tid; d < p.K && d < MAXLIST; d += NT) s_pw[d] = pow(p09, (double)d);
+  }
+  __syncthreads();
+
+  const long long n_lists = (long long)p.Q * p.R;
+  for (long long li = (long long)blockIdx.x * WARPS + warp; li < n_lists; li += (long long)gridDim.x * WARPS) {
+    const int q = (int)(li / p.R);
+    const raw_t* g = reinterpret_cast<const raw_t*>(p.scores) + li * p.K;
+    double* out = p.out + li * QF_QPP_COLS;
+    int len = p.lens[li];
+    int status = 0;
+    if (len < 0 || len > p.K) { status |= QF_QSTAT_BAD_LEN; len = 0; }
+    const int n_top = min(len, p.top_k);
+    const int k = min(p.k_cut, n_top);
+    double* x = s_x[warp];
+
+    // ---- load prefix, validate order
+    int unsorted = 0;
+    for (int j = lane; j < k; j += 32) x[j] = (double)Raw<ST>::f32(__ldg(g + j));
+    if (research) {
+      for (int j = lane; j < len; j += 32) s_all[warp][j] = Raw<ST>::f32(__ldg(g + j));
+    }
+    __syncwarp();
+    if (research) {
+      for (int j = lane + 1; j < len; j += 32) unsorted |= (s_all[warp][j - 1] < s_all[warp][j]);
+    } else {
+      for (int j = lane + 1; j < k; j += 32) unsorted |= (x[j - 1] < x[j]);
+    }
+    unsorted = __any_sync(0xffffffffu, unsorted);
+    if (unsorted) status |= QF_QSTAT_UNSORTED;
+
+    const int* tf = p.text_feats + (size_t)q * 4;
+    const int n_terms = tf[0], n_unique = tf[1], max_len = tf[2], sum_len = tf[3];
+    const int nT = max(1, n_terms);
+
+    double col[QF_QPP_COLS];
+#pragma unroll
+    for (int c = 0; c < QF_QPP_COLS; ++c) col[c] = 0.0;
+
+    if (k > 0) {
+      auto getx = [&](int j) { return x[j]; };
+      double mean;
+      const double var = warp_var(getx, k, lane, &mean);
+      const double kk = (double)k;
+      col[0] = var;                                                      // nqc          :202-216
+      {                                                                  // smv          :223-239
+        const double mu = mean <= 0 ? 1.0 : mean;
+        double a = 0.0, ar = 0.0;
+        for (int j = lane; j < k; j += 32) {
+          const double s = x[j];
+          if (s > 0) {
+            a += s * fabs(log(s / mu));
+            if (mean > 0) ar += s * fabs(log(s / mean));
+          }
+        }
+        col[1] = qf::warp_sum(a) / kk;
+        col[14] = (qf::warp_sum(ar) / kk) * 1.0;                         // smv_research SMVSpecificity.java:22-45
+      }
+      {                                                                  // wig          :247-262
+        const double base = 1.0 / fmax(0.01, mean);
+        double a = 0.0;
+        for (int j = lane; j < k; j += 32) a += x[j] - base;
+        col[2] = qf::warp_sum(a) / ((double)nT * kk);
+      }
+      {                                                                  // SigmaMax :269-293, cumnqc :400-410
+        double* win = s_win[warp];
+        for (int i = 2 + lane; i <= k; i += 32) {
+          double s = 0.0;
+          for (int j = 0; j < i; ++j) s += x[j];
+          const double mu = s / (double)i;
+          double v = 0.0;
+          for (int j = 0; j < i; ++j) {
+            const double d = x[j] - mu;
+            v += d * d;
+          }
+          win[i - 2] = v / (double)i;
+        }
+        __syncwarp();
+        double mx = 0.0, sm = 0.0;
+        for (int i = lane; i < k - 1; i += 32) {
+          mx = fmax(mx, win[i]);
+          sm += win[i];
+        }
+        mx = qf::warp_max(mx);
+        sm = qf::warp_sum(sm);
+        if (k >= 2) {
+          col[3] = sqrt(mx) / sqrt((double)max(1, nT));
+          col[9] = sm / (double)(k - 1);
+        }
+      }
+      {                                                                  // SigmaX       :299-319
+        const double thr = x[0] * 0.5;
+        int c = 0;
+        double s = 0.0;
+        for (int j = lane; j < k; j += 32)
+          if (x[j] >= thr) { ++c; s += x[j]; }
+        c = __reduce_add_sync(0xffffffffu, c);
+        s = qf::warp_sum(s);
+        double sig = 0.0;
+        if (c >= 1) {
+          const double mu = s / (double)c;
+          double v = 0.0;
+          for (int j = lane; j < k; j += 32)
+            if (x[j] >= thr) { const double d = x[j] - mu; v += d * d; }
+          sig = sqrt(qf::warp_sum(v) / (double)c);
+        }
+        col[4] = (k >= 2 && c >= 2) ? sig : 0.0;
+        col[16] = sig / sqrt((double)n_unique);                          // sigmax_research SigmaXSpecificity.java:19-52
+      }
+      {                                                                  // RSD skew     :324-342
+        const double sd = sqrt(var);
+        double a = 0.0;
+        if (k >= 3 && !(sd < 1e-10)) {
+          for (int j = lane; j < k; j += 32) {
+            const double z = (x[j] - mean) / sd;
+            a += z * z * z;
+          }
+          col[5] = qf::warp_sum(a) / kk;
+        }
+      }
+      {                                                                  // UEF          :349-363
+        const int kk20 = min(20, k);
+        double u = 0.0, ws = 0.0;
+        for (int i = lane; i < kk20; i += 32) {
+          const double w = 1.0 / (log((double)(i + 2)) / log(2.0));
+          u += x[i] * w;
+          ws += w;
+        }
+        col[6] = qf::warp_sum(u) / qf::warp_sum(ws);
+      }
+      {                                                                  // snqc         :417-438
+        double a = 0.0;
+        if (mean > 0) {
+          for (int j = lane; j < k; j += 32) {
+            const double r = x[j];
+            if (r > 0) {
+              const double f2 = ((r - mean) * (r - mean)) / r;
+              a += pow(pow(1.0, 0.33) * pow(f2, 0.33), 0.33);
+            }
+          }
+          col[10] = qf::warp_sum(a) / kk;
+        }
+      }
+      {                                                                  // dense-qpp(-m) :444-453
+        double mn = INFINITY, mx = -INFINITY;
+        for (int j = lane; j < k; j += 32) { mn = fmin(mn, x[j]); mx = fmax(mx, x[j]); }
+        mn = qf::warp_min(mn);
+        mx = qf::warp_max(mx);
+        const double range = mx - mn;
+        col[11] = col[12] = (k >= 2 && range > 0) ? log(1.0 + 1.0 / range) : 0.0;
+      }
+      // text-only proxies                                                :368-393
+      col[7] = log(1.0 + (double)n_unique) + log(1.0 + (double)max_len) * 0.5;
+      {
+        const double avg_len = n_terms > 0 ? (double)sum_len / (double)n_terms : 3.0;
+        const double diversity = n_terms > 0 ? (double)n_unique / (double)n_terms : __longlong_as_double(0x7ff8000000000000ll);
+        col[8] = log(1.0 + avg_len) * diversity;
+      }
+
+      if (research) {
+        const double max_idf = p.query_idf ? p.query_idf[q] : 1.0;
+        const float* all = s_all[warp];
+        {                                                                // wig_research  WIGSpecificity.java:18-51
+          const int cutoff = min(p.wig_k, len);
+          const double base = 1.0 / max_idf;
+          double a = 0.0;
+          for (int i = 0; i < cutoff; ++i) a += (double)all[i] - base;   // tiny, sequential like the reference
+          col[15] = a / (double)(n_unique * cutoff);
+        }
+        {                                                                // scnqc_research NQCCalibratedSpecificity.java:31-57
+          const double e = (double)0.33f;
+          double a = 0.0;
+          for (int j = lane; j < k; j += 32) {
+            const double r = x[j];
+            const double f2 = (r - mean) * (r - mean) / r;
+            a += pow(pow(max_idf, e) * pow(f2, e), e);
+          }
+          col[17] = (qf::warp_sum(a) / kk) * max_idf;
+        }
+        {                                                                // rsd_bootstrap  RSDSpecificity.java:22-52
+          const int mS = min(len, p.k_cut);
+          unsigned* cnt = s_cnt[warp];
+          unsigned short* samp = s_samp[warp];
+          double acc = 0.0;
+          for (int s = 0; s < p.n_samples; ++s) {
+            const int32_t* perm = p.perms + (size_t)s * p.perm_len;
+            // first mS entries of the permutation that are < len
+            int got = 0;
+            for (int base = 0; base < p.perm_len && got < mS; base += 32) {
+              const int e = base + lane < p.perm_len ? __ldg(perm + base + lane) : 0x7fffffff;
+              const bool ok = e >= 0 && e < len;
+              const unsigned bal = __ballot_sync(0xffffffffu, ok);
+              const int pos = got + __popc(bal & ((1u << lane) - 1u));
+              if (ok && pos < mS) samp[pos] = (unsigned short)e;
+              got += __popc(bal);
+            }
+            __syncwarp();
+            auto gets = [&](int j) { return (double)all[samp[j]]; };
+            const double est = warp_var(gets, mS, lane, nullptr);       // NQC of the sample
+            // RBO(original, sample; depth len, p = 0.9f): overlap(d) = #{j < mS : max(j, b_j) < d}
+            for (int d = lane; d <= (len >> 2); d += 32) cnt[d] = 0u;
+            __syncwarp();
+            for (int j = lane; j < mS; j += 32) {
+              const int t = max(j, (int)samp[j]);
+              atomicAdd(&cnt[t >> 2], 1u << (8 * (t & 3)));
+            }
+            __syncwarp();
+            double aggr = 0.0;
+            int carry = 0;
+            for (int base = 0; base < len; base += 32) {
+              const int t = base + lane;                                  // depth d = t + 1 uses cnt[0..t]
+              int c = t < len ? (int)((cnt[t >> 2] >> (8 * (t & 3))) & 0xffu) : 0;
+#pragma unroll
+              for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, c, o);
+                if (lane >= o) c += v;
+              }
+              if (t < len) aggr += ((double)(carry + c) / (double)(t + 1)) * s_pw[t];
+              carry += __shfl_sync(0xffffffffu, c, 31);
+            }
+            aggr = qf::warp_sum(aggr);
+            const double one_minus_p = (double)(1.0f - 0.9f);
+            acc += (one_minus_p * aggr) * est;
+            __syncwarp();
+          }
+          col[13] = p.n_samples > 0 ? acc / (double)p.n_samples : 0.0;
+        }
+      }
+    }
+    // every lane holds identical col[]: spread the stores over lanes
+#pragma unroll
+    for (int c = 0; c < QF_QPP_COLS; ++c)
+      if (lane == c) out[c] = col[c];
+    if (p.out_status && lane == 31) p.out_status[li] = status;
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// column normalisation
+// ------------------------------------------------------------------------------------------------
+struct ColStat {
+  unsigned long long omin, omax;
+  double sum, sumsq;
+};
+
+__global__ void colnorm_init(ColStat* st, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { st[i].omin = ~0ull; st[i].omax = 0ull; st[i].sum = 0.0; st[i].sumsq = 0.0; }
+}
+
+// pass 1: min / max / sum per (r, col); pass 2: sum of squared deviations
+template <int PASS>
+__global__ void __launch_bounds__(256) colnorm_reduce(const double* vals, long long Q, int RC, ColStat* st) {
+  extern __shared__ unsigned char sm_raw[];
+  ColStat* loc = reinterpret_cast<ColStat*>(sm_raw);
+  for (int i = threadIdx.x; i < RC; i += blockDim.x) { loc[i].omin = ~0ull; loc[i].omax = 0ull; loc[i].sum = 0.0; loc[i].sumsq = 0.0; }
+  __syncthreads();
+  const long long total = Q * RC;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(e % RC);
+    const double v = vals[e];
+    if (PASS == 1) {
+      const unsigned long long o = qf::ord_f64(v + 0.0);
+      atomicMin(&loc[c].omin, o);
+      atomicMax(&loc[c].omax, o);
+      atomicAdd(&loc[c].sum, v);
+    } else {
+      const double d = v - st[c].sum / (double)Q;
+      atomicAdd(&loc[c].sumsq, d * d);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < RC; i += blockDim.x) {
+    if (PASS == 1) {
+      atomicMin(&st[i].omin, loc[i].omin);
+      atomicMax(&st[i].omax, loc[i].omax);
+      atomicAdd(&st[i].sum, loc[i].sum);
+    } else {
+      atomicAdd(&st[i].sumsq, loc[i].sumsq);
+    }
+  }
+}
+
+__device__ __forceinline__ double unord_f64(unsigned long long o) {
+  const unsigned long long b = (o >> 63) ? (o & 0x7fffffffffffffffull) : ~o;
+  return __longlong_as_double((long long)b);
+}
+
+// float(f"{v:.6f}"): exact round-half-even of the binary value to 6 decimals, then the nearest double.
+__device__ __forceinline__ double round6(double v) {
+  if (!(fabs(v) < 1.0e9)) return v;
+  const double pr = __dmul_rn(v, 1.0e6);
+  const double err = fma(v, 1.0e6, -pr);       // v*1e6 == pr + err exactly
+  double r = rint(pr);
+  const double a = pr - r;                      // exact, in [-0.5, 0.5]
+  if (a > 0) {
+    const double c = 0.5 - a;                   // distance to the upper tie (exact)
+    if (err > c) r += 1.0;
+    else if (err == c && fmod(r, 2.0) != 0.0) r += 1.0;
+  } else if (a < 0) {
+    const double c = 0.5 + a;                   // distance to the lower tie (exact)
+    if (-err > c) r -= 1.0;
+    else if (-err == c && fmod(r, 2.0) != 0.0) r -= 1.0;
+  }
+  // a == 0: pr is an integer; |err| < 0.5 so r stands.  a == +-0.5 is covered above (c == 0).
+  return __ddiv_rn(r + 0.0, 1.0e6);
+}
+
+__global__ void __launch_bounds__(256) colnorm_apply(double* vals, long long Q, int RC, const ColStat* st, int mode, int do_round6) {
+  const long long total = Q * RC;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(e % RC);
+    double v = vals[e];
+    if (mode == QF_COLNORM_MINMAX) {
+      const double vmin = unord_f64(st[c].omin), vmax = unord_f64(st[c].omax);
+      const double scale = vmax > vmin ? __dsub_rn(vmax, vmin) : 1.0;
+      v = __ddiv_rn(__dsub_rn(v, vmin), scale);
+    } else if (mode == QF_COLNORM_ZSCORE) {
+      const double mean = st[c].sum / (double)Q;
+      const double sd = sqrt(st[c].sumsq / (double)Q);
+      v = (v - mean) / (sd > 0 ? sd : 1.0);
+    }
+    if (do_round6) v = round6(v);
+    vals[e] = v;
+  }
+}
+
+__global__ void __launch_bounds__(256) select_weight_kernel(const double* vals, long long n_lists, int ncols, int col,
+                                                            int ncols_mean, double* weights) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_lists) return;
+  const double* v = vals + i * ncols;
+  if (col >= 0) {
+    weights[i] = v[col];
+  } else {
+    double s = 0.0;                                  // Python sum(): left to right from 0
+    for (int c = 0; c < ncols_mean; ++c) s = __dadd_rn(s, v[c]);
+    weights[i] = __ddiv_rn(s, (double)ncols_mean);
+  }
+}
+
+}  // namespace
+
+extern "C" int qf_qpp_stats(const void* scores, int score_type, const int32_t* lens, const int32_t* text_feats,
+                            const double* query_idf, const int32_t* perms, int n_samples, int perm_len, int Q, int R,
+                            int K, int top_k, int k_cut, int wig_k, double* out, int32_t* out_status, void* stream) {
+  QF_REQUIRE(Q >= 0 && R >= 1 && K >= 1, QF_E_INVALID, "qf_qpp_stats: bad sizes Q=%d R=%d K=%d", Q, R, K);
+  QF_REQUIRE(k_cut >= 1 && k_cut <= MAXK, QF_E_UNSUPPORTED, "qf_qpp_stats: k_cut=%d outside [1,%d]", k_cut, MAXK);
+  QF_REQUIRE(top_k >= 1 && wig_k >= 1, QF_E_INVALID, "qf_qpp_stats: top_k and wig_k must be >= 1");
+  QF_REQUIRE(score_type >= QF_SCORE_F64 && score_type <= QF_SCORE_MICRO, QF_E_INVALID,
+             "qf_qpp_stats: unknown score_type %d", score_type);
+  if (perms) {
+    QF_REQUIRE(K <= MAXLIST, QF_E_UNSUPPORTED, "qf_qpp_stats: bootstrap columns need K <= %d (got %d)", MAXLIST, K);
+    QF_REQUIRE(n_samples >= 1 && perm_len >= K, QF_E_INVALID,
+               "qf_qpp_stats: perms need n_samples >= 1 and perm_len >= K (got %d, %d)", n_samples, perm_len);
+  }
+  if (Q == 0) return QF_OK;
+  QF_REQUIRE(scores && lens && text_feats && out, QF_E_INVALID, "qf_qpp_stats: null pointer argument");
+  int rc = qf::check_device();
+  if (rc != QF_OK) return rc;
+  QppParams p{scores, lens, text_feats, query_idf, perms, n_samples, perm_len, Q, R, K, top_k, k_cut, wig_k, out, out_status};
+  const long long n_lists = (long long)Q * R;
+  long long blocks = (n_lists + WARPS - 1) / WARPS;
+  const long long cap = (long long)qf::sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  switch (score_type) {
+    case QF_SCORE_F64: qpp_kernel<QF_SCORE_F64><<<(unsigned)blocks, NT, 0, st>>>(p); break;
+    case QF_SCORE_F32: qpp_kernel<QF_SCORE_F32><<<(unsigned)blocks, NT, 0, st>>>(p); break;
+    default: qpp_kernel<QF_SCORE_MICRO><<<(unsigned)blocks, NT, 0, st>>>(p); break;
+  }
+  QF_CUDA_TRY(cudaGetLastError());
+  return QF_OK;
+}
+
+extern "C" size_t qf_qpp_colnorm_workspace_bytes(int R, int ncols) {
+  if (R < 1 || ncols < 1) return 0;
+  return sizeof(ColStat) * (size_t)R * (size_t)ncols;
+}
+
+extern "C" int qf_qpp_colnorm(double* vals, int Q, int R, int ncols, int mode, int round6_flag, void* ws,
+                              size_t ws_bytes, void* stream) {
+  QF_REQUIRE(Q >= 0 && R >= 1 && ncols >= 1, QF_E_INVALID, "qf_qpp_colnorm: bad sizes");
+  QF_REQUIRE(mode >= 0 && mode <= QF_COLNORM_ZSCORE, QF_E_INVALID, "qf_qpp_colnorm: unknown mode %d", mode);
+  const int RC = R * ncols;
+  QF_REQUIRE(RC <= 1024, QF_E_UNSUPPORTED, "qf_qpp_colnorm: R*ncols=%d exceeds 1024", RC);
+  if (Q == 0) return QF_OK;
+  QF_REQUIRE(vals && ws, QF_E_INVALID, "qf_qpp_colnorm: null pointer argument");
+  QF_REQUIRE(ws_bytes >= qf_qpp_colnorm_workspace_bytes(R, ncols), QF_E_WORKSPACE,
+             "qf_qpp_colnorm: workspace %zu < %zu bytes", ws_bytes, qf_qpp_colnorm_workspace_bytes(R, ncols));
+  int rc = qf::check_device();
+  if (rc != QF_OK) return rc;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  ColStat* cs = reinterpret_cast<ColStat*>(ws);
+  const long long total = (long long)Q * RC;
+  long long blocks = (total + 255) / 256;
+  const long long cap = (long long)qf::sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  if (mode != 0) {
+    colnorm_init<<<(RC + 255) / 256, 256, 0, st>>>(cs, RC);
+    colnorm_reduce<1><<<(unsigned)blocks, 256, sizeof(ColStat) * RC, st>>>(vals, Q, RC, cs);
+    if (mode == QF_COLNORM_ZSCORE)
+      colnorm_reduce<2><<<(unsigned)blocks, 256, sizeof(ColStat) * RC, st>>>(vals, Q, RC, cs);
+  }
+  if (mode != 0 || round6_flag)
+    colnorm_apply<<<(unsigned)blocks, 256, 0, st>>>(vals, Q, RC, cs, mode, round6_flag);
+  QF_CUDA_TRY(cudaGetLastError());
+  return QF_OK;
+}
+
+extern "C" int qf_qpp_select_weight(const double* vals, int Q, int R, int ncols, int col, int ncols_mean,
+                                    double* weights, void* stream) {
+  QF_REQUIRE(Q >= 0 && R >= 1 && ncols >= 1, QF_E_INVALID, "qf_qpp_select_weight: bad sizes");
+  QF_REQUIRE(col >= -1 && col < ncols, QF_E_INVALID, "qf_qpp_select_weight: column %d out of range [-1,%d)", col, ncols);
+  QF_REQUIRE(col >= 0 || (ncols_mean >= 1 && ncols_mean <= ncols), QF_E_INVALID,
+             "qf_qpp_select_weight: ncols_mean=%d out of range", ncols_mean);
+  if (Q == 0) return QF_OK;
+  QF_REQUIRE(vals && weights, QF_E_INVALID, "qf_qpp_select_weight: null pointer argument");
+  int rc = qf::check_device();
+  if (rc != QF_OK) return rc;
+  const long long n = (long long)Q * R;
+  select_weight_kernel<<<(unsigned)((n + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      vals, n, ncols, col, ncols_mean, weights);
+  QF_CUDA_TRY(cudaGetLastError());
+  return QF_OK;
+}

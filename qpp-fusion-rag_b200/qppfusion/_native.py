@@ -1,0 +1,105 @@
+"""
+ctypes binding of libqppfusion.so (include/qppfusion.h) + registration of its entry points as PyTorch
+custom ops (torch.ops.qppfusion.*).
+
+STRICT, like the reference ("No fallbacks", src/fusion.py:24, src/qpp.py:25): if the shared library is
+missing, or there is no sm_100 CUDA device, every compute call raises -- nothing here falls back to a CPU
+or eager-PyTorch implementation.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional
+
+import torch
+
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_PKG_DIR), "lib", "libqppfusion.so")
+
+QF_OK = 0
+_ERR_NAMES = {-1: "QF_E_INVALID", -2: "QF_E_UNSUPPORTED", -3: "QF_E_CUDA", -4: "QF_E_NO_DEVICE", -5: "QF_E_WORKSPACE"}
+
+METHOD_SUM, METHOD_MNZ, METHOD_RRF = 0, 1, 2
+NORM_NONE, NORM_MINMAX = 0, 1
+SCORE_F64, SCORE_F32, SCORE_MICRO = 0, 1, 2
+FLAG_MNZ_SKIP_ZERO, FLAG_REQUIRE_SORTED, FLAG_UNRANKED_OUTPUT = 1, 2, 4
+FLAG_DEBUG_FULLSORT = 0x100
+QSTAT_DUPLICATES, QSTAT_UNSORTED, QSTAT_BAD_LEN = 1, 2, 4
+QPP_BRIDGE_COLS, QPP_RESEARCH_COLS = 13, 5
+QPP_COLS = QPP_BRIDGE_COLS + QPP_RESEARCH_COLS
+COLNORM_MINMAX, COLNORM_ZSCORE = 1, 2
+
+
+class NativeError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libqppfusion: {_ERR_NAMES.get(code, code)}: {msg}")
+        self.code = code
+
+
+_lib: Optional[ctypes.CDLL] = None
+
+_vp, _i, _d, _u32, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_uint32, ctypes.c_size_t
+
+# name -> (restype, argtypes); must list every symbol include/qppfusion.h declares
+PROTOTYPES = {
+    "qf_last_error": (ctypes.c_char_p, []),
+    "qf_abi_version": (_i, []),
+    "qf_device_check": (_i, [_i]),
+    "qf_fuse_max_postings": (_i, []),
+    "qf_fuse": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _d, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "qf_qpp_stats": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "qf_qpp_colnorm_workspace_bytes": (_sz, [_i, _i]),
+    "qf_qpp_colnorm": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
+    "qf_qpp_select_weight": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp]),
+}
+
+
+def lib() -> ctypes.CDLL:
+    """Load libqppfusion.so (once).  Raises if it has not been built -- there is no fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise RuntimeError(
+                f"libqppfusion.so not found at {LIB_PATH}. Build it with "
+                f"`python qpp-fusion-rag_b200/build_native.py` (or __graft_entry__.build()). "
+                f"There is no CPU / PyTorch fallback for this path.")
+        l = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(l, name)      # AttributeError if the library is stale
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc != QF_OK:
+        raise NativeError(rc, lib().qf_last_error().decode("utf-8", "replace"))
+
+
+def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def stream_ptr(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def require_cuda(*tensors: Optional[torch.Tensor]) -> torch.device:
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("qppfusion ops take CUDA tensors only (no CPU fallback); got a "
+                               f"{t.device} tensor")
+        if not t.is_contiguous():
+            raise RuntimeError("qppfusion ops need contiguous tensors")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise RuntimeError("qppfusion ops need all tensors on one device")
+    if dev is None:
+        raise RuntimeError("no tensor arguments")
+    return dev

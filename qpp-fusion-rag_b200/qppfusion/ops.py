@@ -1,0 +1,164 @@
+"""
+PyTorch custom ops over the C ABI (torch.ops.qppfusion.*).
+
+Each op allocates its outputs with torch (device memory + current stream are PyTorch's; the arithmetic is
+libqppfusion's hand-written sm_100a kernels) and calls the matching qf_* entry point through ctypes.
+"""
+from __future__ import annotations
+
+from typing import NamedTuple, Optional, Tuple
+
+import torch
+
+from . import _native as N
+
+_SCORE_DTYPES = {N.SCORE_F64: torch.float64, N.SCORE_F32: torch.float32, N.SCORE_MICRO: torch.int32}
+
+
+def _score_type_of(t: torch.Tensor) -> int:
+    for k, v in _SCORE_DTYPES.items():
+        if t.dtype == v:
+            return k
+    raise TypeError(f"scores must be float64, float32 or int32 (micro-units), got {t.dtype}")
+
+
+# ---------------------------------------------------------------------------------------------- fuse
+@torch.library.custom_op("qppfusion::fuse", mutates_args=())
+def _fuse_op(doc_ids: torch.Tensor, scores: torch.Tensor, lens: torch.Tensor,
+             weights: Optional[torch.Tensor], ranks: Optional[torch.Tensor],
+             method: int, norm: int, rrf_k: float, flags: int
+             ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    dev = N.require_cuda(doc_ids, scores, lens, weights, ranks)
+    if doc_ids.dim() != 3 or doc_ids.dtype != torch.int32:
+        raise TypeError("doc_ids must be int32 [Q, R, K]")
+    Q, R, K = doc_ids.shape
+    if scores.shape != doc_ids.shape:
+        raise ValueError("scores must have the shape of doc_ids")
+    if lens.shape != (Q, R) or lens.dtype != torch.int32:
+        raise TypeError("lens must be int32 [Q, R]")
+    if weights is not None and (weights.shape != (Q, R) or weights.dtype != torch.float64):
+        raise TypeError("weights must be float64 [Q, R]")
+    if ranks is not None and (ranks.shape != doc_ids.shape or ranks.dtype != torch.int32):
+        raise TypeError("ranks must be int32 [Q, R, K]")
+    st = _score_type_of(scores)
+    n = R * K
+    out_ids = torch.empty((Q, n), dtype=torch.int32, device=dev)
+    out_scores = torch.empty((Q, n), dtype=torch.float64, device=dev)
+    out_counts = torch.empty((Q, n), dtype=torch.uint16, device=dev)
+    out_pos = torch.empty((Q, n), dtype=torch.uint16, device=dev)
+    out_lens = torch.empty((Q,), dtype=torch.int32, device=dev)
+    out_status = torch.empty((Q,), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        N.check(N.lib().qf_fuse(N.ptr(doc_ids), N.ptr(scores), st, N.ptr(ranks), N.ptr(lens), N.ptr(weights),
+                                Q, R, K, method, norm, float(rrf_k), flags,
+                                N.ptr(out_ids), N.ptr(out_scores), N.ptr(out_counts), N.ptr(out_pos),
+                                N.ptr(out_lens), N.ptr(out_status), N.stream_ptr(dev)))
+    return out_ids, out_scores, out_counts, out_pos, out_lens, out_status
+
+
+@_fuse_op.register_fake
+def _(doc_ids, scores, lens, weights, ranks, method, norm, rrf_k, flags):
+    Q, R, K = doc_ids.shape
+    n = R * K
+    e = lambda shape, dt: torch.empty(shape, dtype=dt, device=doc_ids.device)
+    return (e((Q, n), torch.int32), e((Q, n), torch.float64), e((Q, n), torch.uint16), e((Q, n), torch.uint16),
+            e((Q,), torch.int32), e((Q,), torch.int32))
+
+
+class FuseOut(NamedTuple):
+    ids: torch.Tensor       # int32  [Q, R*K]  ranked doc ids
+    scores: torch.Tensor    # float64[Q, R*K]  fused scores
+    counts: torch.Tensor    # uint16 [Q, R*K]  postings merged per doc (CombMNZ count)
+    pos: torch.Tensor       # uint16 [Q, R*K]  first-seen index of the doc
+    lens: torch.Tensor      # int32  [Q]       union size
+    status: torch.Tensor    # int32  [Q]       QSTAT_* bits
+
+
+def fuse(doc_ids, scores, lens, weights=None, ranks=None, method=N.METHOD_SUM, norm=N.NORM_NONE,
+         rrf_k=60.0, flags=0) -> FuseOut:
+    return FuseOut(*torch.ops.qppfusion.fuse(doc_ids, scores, lens, weights, ranks, int(method), int(norm),
+                                             float(rrf_k), int(flags)))
+
+
+# ---------------------------------------------------------------------------------------------- qpp
+@torch.library.custom_op("qppfusion::qpp_stats", mutates_args=())
+def _qpp_stats_op(scores: torch.Tensor, lens: torch.Tensor, text_feats: torch.Tensor,
+                  query_idf: Optional[torch.Tensor], perms: Optional[torch.Tensor],
+                  top_k: int, k_cut: int, wig_k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    dev = N.require_cuda(scores, lens, text_feats, query_idf, perms)
+    if scores.dim() != 3:
+        raise TypeError("scores must be [Q, R, K]")
+    Q, R, K = scores.shape
+    if lens.shape != (Q, R) or lens.dtype != torch.int32:
+        raise TypeError("lens must be int32 [Q, R]")
+    if text_feats.shape != (Q, 4) or text_feats.dtype != torch.int32:
+        raise TypeError("text_feats must be int32 [Q, 4]")
+    if query_idf is not None and (query_idf.shape != (Q,) or query_idf.dtype != torch.float64):
+        raise TypeError("query_idf must be float64 [Q]")
+    n_samples = perm_len = 0
+    if perms is not None:
+        if perms.dim() != 2 or perms.dtype != torch.int32:
+            raise TypeError("perms must be int32 [n_samples, perm_len]")
+        n_samples, perm_len = perms.shape
+    st = _score_type_of(scores)
+    out = torch.empty((Q, R, N.QPP_COLS), dtype=torch.float64, device=dev)
+    status = torch.empty((Q, R), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        N.check(N.lib().qf_qpp_stats(N.ptr(scores), st, N.ptr(lens), N.ptr(text_feats), N.ptr(query_idf),
+                                     N.ptr(perms), n_samples, perm_len, Q, R, K, top_k, k_cut, wig_k,
+                                     N.ptr(out), N.ptr(status), N.stream_ptr(dev)))
+    return out, status
+
+
+@_qpp_stats_op.register_fake
+def _(scores, lens, text_feats, query_idf, perms, top_k, k_cut, wig_k):
+    Q, R, K = scores.shape
+    return (torch.empty((Q, R, N.QPP_COLS), dtype=torch.float64, device=scores.device),
+            torch.empty((Q, R), dtype=torch.int32, device=scores.device))
+
+
+def qpp_stats(scores, lens, text_feats, query_idf=None, perms=None, top_k=100, k_cut=50, wig_k=5):
+    """-> (out float64 [Q, R, 18], status int32 [Q, R]).  Columns 0..12 = config.qpp.methods order."""
+    return torch.ops.qppfusion.qpp_stats(scores, lens, text_feats, query_idf, perms, int(top_k), int(k_cut), int(wig_k))
+
+
+@torch.library.custom_op("qppfusion::qpp_colnorm", mutates_args=("vals",))
+def _colnorm_op(vals: torch.Tensor, mode: int, round6: bool) -> None:
+    dev = N.require_cuda(vals)
+    if vals.dim() != 3 or vals.dtype != torch.float64:
+        raise TypeError("vals must be float64 [Q, R, ncols]")
+    Q, R, C = vals.shape
+    nbytes = N.lib().qf_qpp_colnorm_workspace_bytes(R, C)
+    ws = torch.empty((max(nbytes, 8),), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        N.check(N.lib().qf_qpp_colnorm(N.ptr(vals), Q, R, C, mode, 1 if round6 else 0, N.ptr(ws), nbytes,
+                                       N.stream_ptr(dev)))
+
+
+def qpp_colnorm_(vals: torch.Tensor, mode: str = "minmax", round6: bool = False) -> torch.Tensor:
+    """In-place _normalize_qpp over the query axis of vals [Q, R, ncols] (+ optional "%.6f" round trip)."""
+    m = {"none": 0, "minmax": N.COLNORM_MINMAX, "zscore": N.COLNORM_ZSCORE}[mode]
+    torch.ops.qppfusion.qpp_colnorm(vals, m, bool(round6))
+    return vals
+
+
+@torch.library.custom_op("qppfusion::qpp_select_weight", mutates_args=())
+def _select_weight_op(vals: torch.Tensor, col: int, ncols_mean: int) -> torch.Tensor:
+    dev = N.require_cuda(vals)
+    if vals.dim() != 3 or vals.dtype != torch.float64:
+        raise TypeError("vals must be float64 [Q, R, ncols]")
+    Q, R, C = vals.shape
+    w = torch.empty((Q, R), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        N.check(N.lib().qf_qpp_select_weight(N.ptr(vals), Q, R, C, col, ncols_mean, N.ptr(w), N.stream_ptr(dev)))
+    return w
+
+
+@_select_weight_op.register_fake
+def _(vals, col, ncols_mean):
+    return torch.empty(vals.shape[:2], dtype=torch.float64, device=vals.device)
+
+
+def qpp_select_weight(vals: torch.Tensor, col: int, ncols_mean: int = N.QPP_BRIDGE_COLS) -> torch.Tensor:
+    """weights[q, r] = vals[q, r, col], or the mean of the first ncols_mean columns when col == -1."""
+    return torch.ops.qppfusion.qpp_select_weight(vals, int(col), int(ncols_mean))

@@ -1,0 +1,165 @@
+"""GPU parity: qf_qpp_stats / qf_qpp_colnorm / qf_qpp_select_weight vs oracle/qpp_oracle.py.
+
+Tolerance: the north star asks for 1e-5 relative (fp32); the kernels compute in float64 and the test
+holds them to 1e-9 relative (+1e-12 absolute) -- summation order is the only difference."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import qpp_oracle as qo
+
+pytestmark = pytest.mark.gpu
+RTOL, ATOL = 1e-9, 1e-12
+
+TEXTS = ["what is machine learning", "  leading space query", "", "single", "a a a b",
+         "0-dimensional biomaterials show inductive properties.", "who wrote\tthe  origin of species ?"]
+
+
+def make_lists(seed, Q, R, K, kind="mixed"):
+    rng = np.random.default_rng(seed)
+    sc = np.zeros((Q, R, K), dtype=np.float64)
+    lens = np.zeros((Q, R), dtype=np.int32)
+    for q in range(Q):
+        for r in range(R):
+            n = K if rng.random() < 0.7 else int(rng.integers(0, K + 1))
+            scale = [1.0, 30.0, 1.0, 1.0, 12.0][r % 5]
+            v = np.sort(rng.beta(2, 5, size=n) * scale)[::-1]
+            if r == 2:
+                v = np.sort(-rng.exponential(3.0, size=n))[::-1]
+            if q % 7 == 3 and n > 4:
+                v[:] = v[0]                     # constant list
+            if q % 7 == 5 and n > 6:
+                v[2:6] = v[2]                   # ties
+            sc[q, r, :n] = np.round(v, 6)
+            lens[q, r] = n
+    return sc, lens
+
+
+def oracle_table(sc, lens, texts, perms, idf, top_k=100, k_cut=50, wig_k=5):
+    Q, R, K = sc.shape
+    out = np.zeros((Q, R, 18))
+    for q in range(Q):
+        feats = qo.text_features(texts[q])
+        for r in range(R):
+            lst = [float(v) for v in sc[q, r, :lens[q, r]]]
+            out[q, r, :13] = qo.bridge_scores(texts[q], lst[:top_k], k_cut)
+            if perms is not None and lst:
+                out[q, r, 13:] = qo.research_scores(lst, feats[1], idf[q], perms, k_cut, wig_k)
+    return out
+
+
+def close(a, b):
+    both_nan = np.isnan(a) & np.isnan(b)
+    both_inf = np.isinf(a) & np.isinf(b) & (np.sign(a) == np.sign(b))
+    ok = both_nan | both_inf | (np.abs(a - b) <= ATOL + RTOL * np.abs(b))
+    return ok
+
+
+@pytest.mark.parametrize("score_type", ["f64", "micro", "f32"])
+def test_bridge_and_research_columns(score_type):
+    from qppfusion import ops
+    Q, R, K = 21, 5, 120
+    sc, lens = make_lists(21, Q, R, K)
+    texts = [TEXTS[q % len(TEXTS)] for q in range(Q)]
+    feats = np.array([qo.text_features(t) for t in texts], dtype=np.int32)
+    rng = np.random.default_rng(22)
+    perms = np.stack([rng.permutation(K) for _ in range(10)]).astype(np.int32)
+    idf = np.round(rng.random(Q) * 8 + 1, 3)
+    if score_type == "micro":
+        dev_sc = np.round(sc * 1e6).astype(np.int32)
+    elif score_type == "f32":
+        dev_sc = sc.astype(np.float32)
+        sc = dev_sc.astype(np.float64)
+    else:
+        dev_sc = sc
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    out, status = ops.qpp_stats(t(dev_sc), t(lens), t(feats), t(idf), t(perms), top_k=100, k_cut=50, wig_k=5)
+    out = out.cpu().numpy()
+    assert (status.cpu().numpy() == 0).all()
+    exp = oracle_table(sc, lens, texts, [p.tolist() for p in perms], idf)
+    ok = close(out, exp)
+    assert ok.all(), (np.argwhere(~ok)[:10], out[~ok][:10], exp[~ok][:10])
+    assert np.array_equal(out[..., 11], out[..., 12])
+    # without permutations the research columns are zero and the bridge columns unchanged
+    out2, _ = ops.qpp_stats(t(dev_sc), t(lens), t(feats), None, None)
+    out2 = out2.cpu().numpy()
+    assert np.array_equal(out2[..., :13], out[..., :13]) and (out2[..., 13:] == 0).all()
+
+
+def test_reference_smoke_vector_and_k1000():
+    from qppfusion import ops
+    dev = torch.device("cuda:0")
+    sc = np.zeros((2, 1, 1000))
+    lens = np.array([[10], [1000]], dtype=np.int32)
+    sc[0, 0, :10] = [0.95, 0.82, 0.71, 0.65, 0.58, 0.52, 0.48, 0.41, 0.35, 0.28]   # src/qpp.py:397-398
+    sc[1, 0] = np.round(np.sort(np.random.default_rng(3).random(1000) * 25)[::-1], 6)
+    texts = ["what is machine learning", "deep list"]
+    feats = np.array([qo.text_features(t) for t in texts], dtype=np.int32)
+    perms = np.stack([np.random.default_rng(4 + i).permutation(1000) for i in range(10)]).astype(np.int32)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    out, status = ops.qpp_stats(t(sc), t(lens), t(feats), None, t(perms))
+    out = out.cpu().numpy()
+    exp = oracle_table(sc, lens, texts, [p.tolist() for p in perms], [1.0, 1.0])
+    ok = close(out, exp)
+    assert ok.all(), (np.argwhere(~ok), out[~ok], exp[~ok])
+
+
+def test_unsorted_input_is_flagged():
+    from qppfusion import ops
+    dev = torch.device("cuda:0")
+    sc = np.array([[[0.1, 0.9, 0.5, 0.0]]])
+    out, status = ops.qpp_stats(torch.from_numpy(sc).to(dev), torch.tensor([[3]], dtype=torch.int32, device=dev),
+                                torch.tensor([[1, 1, 1, 1]], dtype=torch.int32, device=dev))
+    assert int(status.cpu()[0, 0]) & 2
+
+
+@pytest.mark.parametrize("mode", ["minmax", "zscore", "none"])
+def test_colnorm_round6_and_select_weight(mode):
+    from qppfusion import ops
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(31)
+    Q, R, C = 257, 5, 18
+    vals = rng.normal(size=(Q, R, C)) * np.array([1e-3, 1, 50] * 6)
+    vals[:, 1, 4] = 0.25                      # constant column -> scale 1.0
+    vals[3, 0, 0] = 0.1234565                 # decimal ties / near ties for the %.6f round trip
+    vals[4, 0, 0] = 2.5e-7
+    exp = np.empty_like(vals)
+    for r in range(R):
+        res = {str(q): list(vals[q, r]) for q in range(Q)}
+        nrm = qo.normalize_qpp(res, mode) if mode != "none" else res
+        for q in range(Q):
+            exp[q, r] = nrm[str(q)]
+    g = torch.from_numpy(vals.copy()).to(dev)
+    ops.qpp_colnorm_(g, mode, round6=False)
+    got = g.cpu().numpy()
+    if mode == "zscore":
+        assert np.allclose(got, exp, rtol=1e-10, atol=1e-12)
+    else:
+        assert np.array_equal(got, exp)          # min-max is two exact float64 ops
+    # "%.6f" round trip is exact
+    g6 = torch.from_numpy(exp.copy()).to(dev)
+    ops.qpp_colnorm_(g6, "none", round6=True)
+    exp6 = np.vectorize(qo.fmt6)(exp)
+    assert np.array_equal(g6.cpu().numpy(), exp6)
+    w5 = ops.qpp_select_weight(g6, 5).cpu().numpy()
+    assert np.array_equal(w5, exp6[:, :, 5])
+    wm = ops.qpp_select_weight(g6, -1, 13).cpu().numpy()
+    expm = np.array([[sum(list(exp6[q, r, :13])) / 13 for r in range(R)] for q in range(Q)])
+    assert np.array_equal(wm, expm)
+
+
+def test_round6_hard_cases():
+    from qppfusion import ops
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(41)
+    k = rng.integers(-10**7, 10**7, size=20000)
+    v = (k + 0.5) / 1e6                       # as close to decimal ties as doubles get
+    v = np.concatenate([v, np.nextafter(v, np.inf), np.nextafter(v, -np.inf), rng.random(20000), [0.0, -0.0, 1.0, 0.9999995]])
+    n = v.size
+    g = torch.from_numpy(v.reshape(n, 1, 1).copy()).to(dev)
+    ops.qpp_colnorm_(g, "none", round6=True)
+    exp = np.array([qo.fmt6(float(x)) for x in v])
+    assert np.array_equal(g.cpu().numpy().reshape(-1), exp)
