@@ -29,6 +29,12 @@ extern "C" {
 
 #define QF_ABI_VERSION 1
 
+#if defined(__GNUC__)
+#define QF_API __attribute__((visibility("default")))
+#else
+#define QF_API
+#endif
+
 /* status codes */
 #define QF_OK               0
 #define QF_E_INVALID       -1   /* bad argument (null pointer, negative size, unknown enum) */
@@ -37,10 +43,10 @@ extern "C" {
 #define QF_E_NO_DEVICE     -4   /* no CUDA device, or device is not compute capability 10.x */
 #define QF_E_WORKSPACE     -5   /* workspace too small; call the matching *_workspace_bytes first */
 
-const char* qf_last_error(void);
-int         qf_abi_version(void);
+QF_API const char* qf_last_error(void);
+QF_API int         qf_abi_version(void);
 /* 0 if `device` is a compute-capability-10.x GPU this library can run on. */
-int         qf_device_check(int device);
+QF_API int         qf_device_check(int device);
 
 /* ------------------------------------------------------------------------------------------------
  * Rank fusion  --  replaces ranx.fuse (src/fusion.py:182,201,226) and the weighted_* Python loops
@@ -93,8 +99,8 @@ int         qf_device_check(int device);
  *
  * Envelope: R*K <= qf_fuse_max_postings() (shared-memory resident per query), R <= 32.
  */
-int qf_fuse_max_postings(void);
-int qf_fuse(const int32_t* doc_ids, const void* scores, int score_type, const int32_t* ranks,
+QF_API int qf_fuse_max_postings(void);
+QF_API int qf_fuse(const int32_t* doc_ids, const void* scores, int score_type, const int32_t* ranks,
             const int32_t* lens, const double* weights,
             int Q, int R, int K, int method, int norm, double rrf_k, uint32_t flags,
             int32_t* out_ids, double* out_scores, uint16_t* out_counts, uint16_t* out_pos,
@@ -124,7 +130,7 @@ int qf_fuse(const int32_t* doc_ids, const void* scores, int score_type, const in
  * (perm_len >= K), one per bootstrap sample (n_samples, reference uses 10); query_idf[q] (nullable,
  * default 1.0) stands in for maxIDF(q), which needs a Lucene index.  Without perms the 5 columns are 0.
  */
-int qf_qpp_stats(const void* scores, int score_type, const int32_t* lens, const int32_t* text_feats,
+QF_API int qf_qpp_stats(const void* scores, int score_type, const int32_t* lens, const int32_t* text_feats,
                  const double* query_idf, const int32_t* perms, int n_samples, int perm_len,
                  int Q, int R, int K, int top_k, int k_cut, int wig_k,
                  double* out, int32_t* out_status, void* stream);
@@ -139,15 +145,15 @@ int qf_qpp_stats(const void* scores, int score_type, const int32_t* lens, const 
  */
 #define QF_COLNORM_MINMAX 1
 #define QF_COLNORM_ZSCORE 2
-size_t qf_qpp_colnorm_workspace_bytes(int R, int ncols);
-int qf_qpp_colnorm(double* vals, int Q, int R, int ncols, int mode, int round6,
+QF_API size_t qf_qpp_colnorm_workspace_bytes(int R, int ncols);
+QF_API int qf_qpp_colnorm(double* vals, int Q, int R, int ncols, int mode, int round6,
                    void* ws, size_t ws_bytes, void* stream);
 
 /*
  * weights[q][r] = vals[q][r][col]  (col >= 0)  or  mean over the first `ncols_mean` columns
  * (col == -1, get_qpp_weight's fusion mode, src/fusion.py:152-153: sum(scores)/len(scores)).
  */
-int qf_qpp_select_weight(const double* vals, int Q, int R, int ncols, int col, int ncols_mean,
+QF_API int qf_qpp_select_weight(const double* vals, int Q, int R, int ncols, int col, int ncols_mean,
                          double* weights, void* stream);
 
 #ifdef __cplusplus

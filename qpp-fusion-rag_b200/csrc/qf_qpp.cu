@@ -310,6 +310,10 @@ __global__ void __launch_bounds__(NT) qpp_kernel(const QppParams p) {
         }
       }
     }
+    if (!research) {
+#pragma unroll
+      for (int c = QF_QPP_BRIDGE_COLS; c < QF_QPP_COLS; ++c) col[c] = 0.0;
+    }
     // every lane holds identical col[]: spread the stores over lanes
 #pragma unroll
     for (int c = 0; c < QF_QPP_COLS; ++c)
