@@ -1,0 +1,367 @@
+#!/usr/bin/env python3
+"""
+bench.py -- headline benchmark of the B200-native QPP-Fusion-RAG hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one pass of the hot path over one NQ-shaped batch (BASELINE.json configs[1]):
+    3,452 queries x 5 retrievers x top-1000 run lists ->
+      qf_qpp_stats (13 QPPBridge predictors per list) -> qf_qpp_colnorm (cross-query min-max + "%.6f")
+      -> qf_qpp_select_weight (RSD column, method id 5) -> qf_fuse (W-CombSUM, ranked)
+metric = fused queries/s.  `value` has the inputs resident in HBM; `e2e` goes through host (pinned)
+buffers with the H2D / D2H copies inside the timed region.  Synthetic data (no network): seeded, generated
+on the device in the BEIR/NQ shape described in SURVEY.md section 8(d).
+
+N > 1 (torchrun, one rank per GPU, NCCL): queries are sharded across ranks (weak scaling: every rank
+fuses its own 3,452-query shard); QPP/fusion need no data-path collective.
+
+--impl reference times the reference's CPU implementation of the same step (oracle port of
+src/fusion.py weighted_combsum + QPPBridge.java; see oracle/) on a bounded query sample per step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "qpp-fusion-rag_b200"), os.path.join(ROOT, "tests")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+Q_NQ, R_NQ, K_NQ, N_DOCS = 3452, 5, 1000, 2_681_468
+POOL = 2200                      # per-query candidate pool -> union ratio ~0.45
+METRIC = "fused queries/s (5x top-1000) + BGE top-1000 QPS @2.68M docs; % of roofline"
+
+
+# ------------------------------------------------------------------------------------------------ data
+def synth_device(Q, R, K, seed, device):
+    """Seeded synthetic NQ-shaped runs, generated on the device.
+    doc_ids int32 [Q,R,K] (distinct inside a list), scores int32 micro-units [Q,R,K] sorted descending
+    (6-decimal values as .res files carry them), lens int32 [Q,R], text_feats int32 [Q,4]."""
+    import torch
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    stride = N_DOCS // POOL
+    pool = (torch.arange(POOL, device=device, dtype=torch.int64)[None, :] * stride
+            + torch.randint(0, stride, (Q, POOL), generator=g, device=device))            # distinct per query
+    ids = torch.empty((Q, R, K), dtype=torch.int32, device=device)
+    micro = torch.empty((Q, R, K), dtype=torch.int32, device=device)
+    scale = [1.0, 30.0, 1.0, 1.0, 12.0]
+    for r in range(R):
+        pick = torch.rand((Q, POOL), generator=g, device=device).argsort(dim=1)[:, :K]
+        ids[:, r] = torch.gather(pool, 1, pick).to(torch.int32)
+        u1 = torch.rand((Q, K), generator=g, device=device, dtype=torch.float64)
+        u2 = torch.rand((Q, K), generator=g, device=device, dtype=torch.float64)
+        s = (1.0 - u1.sqrt()) * (0.35 + 0.65 * u2)          # right-skewed in (0,1), Beta(2,5)-like
+        s = s * scale[r % 5]
+        if r % 5 == 2:
+            s = -3.0 * (-torch.log1p(-u2))                   # MonoT5-style negative log-probs
+        s = torch.sort(s, dim=1, descending=True).values
+        micro[:, r] = torch.round(s * 1e6).to(torch.int32)
+    lens = torch.full((Q, R), K, dtype=torch.int32, device=device)
+    n_tok = (torch.poisson(torch.full((Q,), 9.0, device=device), generator=g) + 1).to(torch.int32)
+    n_unique = torch.clamp(n_tok - (torch.rand((Q,), generator=g, device=device) < 0.2).to(torch.int32), min=1)
+    max_len = torch.randint(4, 14, (Q,), generator=g, device=device, dtype=torch.int32)
+    sum_len = (n_tok.to(torch.float32) * (3.5 + 2.0 * torch.rand((Q,), generator=g, device=device))).to(torch.int32)
+    feats = torch.stack([n_tok, n_unique, max_len, sum_len], dim=1).contiguous()
+    return ids.contiguous(), micro.contiguous(), lens, feats
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled every 200 ms while the timed region runs."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for row in self.rows:
+            try:
+                sm.append(float(row[0]))
+                mx.append(float(row[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, row[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------ ours
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops", 1590.0), "measured"
+    return 6650.0, 1590.0, "fallback"
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from qppfusion import ops
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    Q, R, K = Q_NQ, R_NQ, K_NQ
+    NSETS = 3     # rotating input sets: 138 MB each, so no step finds its inputs in the 126 MB L2
+    sets = [synth_device(Q, R, K, 20250101 + 2 + 17 * rank + 1000 * i, dev) for i in range(NSETS)]
+    stream = torch.cuda.current_stream(dev)
+
+    def step(i, ev=None):
+        ids, micro, lens, feats = sets[i % NSETS]
+        if ev: ev[0].record(stream)
+        qpp, _st = ops.qpp_stats(micro, lens, feats, None, None, top_k=100, k_cut=50)
+        if ev: ev[1].record(stream)
+        ops.qpp_colnorm_(qpp, "minmax", round6=True)
+        w = ops.qpp_select_weight(qpp, 5)
+        if ev: ev[2].record(stream)
+        out = ops.fuse(ids, micro, lens, w, None, 0, 0, 60.0, 0, want_counts=False, want_pos=False)
+        if ev: ev[3].record(stream)
+        return out
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for i in range(args.warmup):
+        out = step(i)
+    barrier()
+    union_total = int(out.lens.sum().item())
+    assert int(out.status.max().item()) == 0
+
+    # ---- timed region: K steps, device-timed, max over ranks
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    t0.record(stream)
+    for i in range(args.steps):
+        out = step(i, evs[i])
+    t1.record(stream)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = t0.elapsed_time(t1)
+    fuse_ms = sum(e[2].elapsed_time(e[3]) for e in evs) / args.steps
+    qpp_ms = sum(e[0].elapsed_time(e[1]) for e in evs) / args.steps
+    norm_ms = sum(e[1].elapsed_time(e[2]) for e in evs) / args.steps
+
+    # ---- end to end: pinned host buffers -> H2D -> step -> D2H of the fused run
+    ids, micro, lens, feats = sets[0]
+    h_in = [x.cpu().pin_memory() for x in (ids, micro, lens, feats)]
+    h_out = None
+    e2e_steps = max(3, min(args.steps, 10))
+
+    def e2e_step():
+        nonlocal h_out
+        d = [x.to(dev, non_blocking=True) for x in h_in]
+        qpp, _ = ops.qpp_stats(d[1], d[2], d[3], None, None, top_k=100, k_cut=50)
+        ops.qpp_colnorm_(qpp, "minmax", round6=True)
+        w = ops.qpp_select_weight(qpp, 5)
+        o = ops.fuse(d[0], d[1], d[2], w, None, 0, 0, 60.0, 0, want_counts=False, want_pos=False)
+        if h_out is None:
+            h_out = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in (o.ids, o.scores, o.lens)]
+        for dst, src in zip(h_out, (o.ids, o.scores, o.lens)):
+            dst.copy_(src, non_blocking=True)
+
+    e2e_step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(e2e_steps):
+        e2e_step()
+    e1.record(stream)
+    barrier()
+    e2e_ms = e0.elapsed_time(e1) / e2e_steps
+    h2d = sum(x.numel() * x.element_size() for x in h_in)
+    d2h = sum(x.numel() * x.element_size() for x in h_out)
+
+    times = torch.tensor([ms_total, e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    ms_total, e2e_ms = times.tolist()
+
+    if rank == 0:
+        hbm_peak, tf_peak, which = load_peaks()
+        n_post = Q * R * K
+        alg_bytes = 8 * n_post + Q * R * 12 + 12 * union_total + 8 * Q   # ids+micro in, lens+weights, ids+f64 out
+        achieved = alg_bytes / (fuse_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": world * Q * args.steps / (ms_total * 1e-3), "unit": "fused queries/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "NQ-shaped 3452 queries x 5 retrievers x top-1000: 13 QPP predictors + "
+                                   "cross-query min-max + W-CombSUM(RSD) per step (BASELINE configs[1])",
+                       "queries_per_gpu": Q, "retrievers": R, "depth": K, "score_format": "int32 micro-units",
+                       "union_ratio": union_total / n_post, "sharding": f"query-sharded x{world}, no collective",
+                       "l2": "3 rotating input sets of 138 MB (> 126 MB L2)"},
+            "kernel_ms": {"qpp_stats": qpp_ms, "colnorm+select": norm_ms, "fuse": fuse_ms},
+            "roofline": {"kernel": "fuse_kernel<5120,13,512,micro>", "bound": "hbm", "achieved": achieved,
+                         "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "peak_source": which,
+                         "algorithmic_bytes": alg_bytes, "traffic": None},
+            "e2e": {"value": world * Q / (e2e_ms * 1e-3), "unit": "fused queries/s", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": 6 * args.steps,
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(seconds=12.0)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def _cpu_sample(nq, seed):
+    """Host-side sample of the same synthetic shape as lists of rows for the oracle."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    lists, texts = [], []
+    stride = N_DOCS // POOL
+    scale = [1.0, 30.0, 1.0, 1.0, 12.0]
+    for q in range(nq):
+        pool = np.arange(POOL) * stride + rng.integers(0, stride, POOL)
+        per_r = []
+        for r in range(R_NQ):
+            docs = rng.choice(pool, size=K_NQ, replace=False)
+            u1, u2 = rng.random(K_NQ), rng.random(K_NQ)
+            s = (1.0 - np.sqrt(u1)) * (0.35 + 0.65 * u2) * scale[r]
+            if r == 2:
+                s = -3.0 * (-np.log1p(-u2))
+            s = np.round(np.sort(s)[::-1], 6)
+            per_r.append([(int(d), float(v), i + 1) for i, (d, v) in enumerate(zip(docs, s))])
+        lists.append(per_r)
+        texts.append(" ".join("tok%d" % t for t in rng.integers(0, 50, int(rng.poisson(9)) + 1)))
+    return lists, texts
+
+
+def _cpu_step(lists, texts):
+    """The reference's step restated on the CPU: QPPBridge columns -> min-max -> %.6f -> W-CombSUM -> rank."""
+    from oracle import fusion_oracle as fo
+    from oracle import qpp_oracle as qo
+    nq = len(lists)
+    w = [[0.0] * R_NQ for _ in range(nq)]
+    for r in range(R_NQ):
+        raw = {str(q): qo.bridge_scores(texts[q], [s for (_, s, _) in lists[q][r]][:100], inputs_are_f32=False)
+               for q in range(nq)}
+        nrm = qo.normalize_qpp(raw, "minmax")
+        for q in range(nq):
+            w[q][r] = qo.fmt6(nrm[str(q)][5])
+    n_docs = 0
+    for q in range(nq):
+        docs, scores, _ = fo.fuse_weighted_query(lists[q], w[q], fo.SUM)
+        order = fo.rank_order(scores)
+        n_docs += len(order)
+    return n_docs
+
+
+def cpu_baseline(seconds=12.0):
+    lists, texts = _cpu_sample(8, 7)
+    t = time.perf_counter()
+    _cpu_step(lists, texts)
+    per_q = (time.perf_counter() - t) / 8
+    nq = max(8, min(512, int(seconds / per_q)))
+    lists, texts = _cpu_sample(nq, 8)
+    t = time.perf_counter()
+    _cpu_step(lists, texts)
+    dt = time.perf_counter() - t
+    return {"value": nq / dt, "unit": "fused queries/s", "cores": 1, "kind": "port",
+            "sample": f"{nq} queries of the same NQ shape (5 x top-1000), oracle port of QPPBridge.java + "
+                      f"src/fusion.py weighted_combsum dict loops, 1 Python thread as the reference; "
+                      f"host has {os.cpu_count()} cores"}
+
+
+def _ref_worker(args):
+    nq, seed = args
+    lists, texts = _cpu_sample(nq, seed)
+    t = time.perf_counter()
+    _cpu_step(lists, texts)
+    return time.perf_counter() - t
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    per_worker = 4
+    nq_step = cores * per_worker
+    # each step: every host core fuses `per_worker` queries; step time = slowest worker's compute time
+    # (sample generation is outside the workers' timers)
+    with mp.get_context("fork").Pool(cores) as pool:
+        for i in range(args.warmup):
+            pool.map(_ref_worker, [(1, 100 + i * cores + c) for c in range(cores)])
+        comp = []
+        for i in range(args.steps):
+            comp.append(max(pool.map(_ref_worker, [(per_worker, 5000 + i * cores + c) for c in range(cores)])))
+    value = nq_step * args.steps / sum(comp)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "fused queries/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(comp) / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "NQ-shaped 5 retrievers x top-1000: 13 QPP predictors + cross-query min-max + "
+                                   "W-CombSUM(RSD) (BASELINE configs[1]); bounded sample per step",
+                       "queries_per_step": nq_step},
+            "cpu_baseline": {"value": value, "unit": "fused queries/s", "cores": cores, "kind": "port",
+                             "sample": f"{nq_step} queries/step ({per_worker} per process x {cores} processes), "
+                                       "oracle port of QPPBridge.java + src/fusion.py weighted_combsum"},
+            "e2e": {"value": value, "unit": "fused queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

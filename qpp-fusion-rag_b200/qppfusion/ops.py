@@ -26,7 +26,7 @@ def _score_type_of(t: torch.Tensor) -> int:
 @torch.library.custom_op("qppfusion::fuse", mutates_args=())
 def _fuse_op(doc_ids: torch.Tensor, scores: torch.Tensor, lens: torch.Tensor,
              weights: Optional[torch.Tensor], ranks: Optional[torch.Tensor],
-             method: int, norm: int, rrf_k: float, flags: int
+             method: int, norm: int, rrf_k: float, flags: int, want_counts: bool, want_pos: bool
              ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
     dev = N.require_cuda(doc_ids, scores, lens, weights, ranks)
     if doc_ids.dim() != 3 or doc_ids.dtype != torch.int32:
@@ -44,40 +44,42 @@ def _fuse_op(doc_ids: torch.Tensor, scores: torch.Tensor, lens: torch.Tensor,
     n = R * K
     out_ids = torch.empty((Q, n), dtype=torch.int32, device=dev)
     out_scores = torch.empty((Q, n), dtype=torch.float64, device=dev)
-    out_counts = torch.empty((Q, n), dtype=torch.uint16, device=dev)
-    out_pos = torch.empty((Q, n), dtype=torch.uint16, device=dev)
+    out_counts = torch.empty((Q, n) if want_counts else (0, n), dtype=torch.uint16, device=dev)
+    out_pos = torch.empty((Q, n) if want_pos else (0, n), dtype=torch.uint16, device=dev)
     out_lens = torch.empty((Q,), dtype=torch.int32, device=dev)
     out_status = torch.empty((Q,), dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
         N.check(N.lib().qf_fuse(N.ptr(doc_ids), N.ptr(scores), st, N.ptr(ranks), N.ptr(lens), N.ptr(weights),
                                 Q, R, K, method, norm, float(rrf_k), flags,
-                                N.ptr(out_ids), N.ptr(out_scores), N.ptr(out_counts), N.ptr(out_pos),
+                                N.ptr(out_ids), N.ptr(out_scores),
+                                N.ptr(out_counts) if want_counts else None, N.ptr(out_pos) if want_pos else None,
                                 N.ptr(out_lens), N.ptr(out_status), N.stream_ptr(dev)))
     return out_ids, out_scores, out_counts, out_pos, out_lens, out_status
 
 
 @_fuse_op.register_fake
-def _(doc_ids, scores, lens, weights, ranks, method, norm, rrf_k, flags):
+def _(doc_ids, scores, lens, weights, ranks, method, norm, rrf_k, flags, want_counts, want_pos):
     Q, R, K = doc_ids.shape
     n = R * K
     e = lambda shape, dt: torch.empty(shape, dtype=dt, device=doc_ids.device)
-    return (e((Q, n), torch.int32), e((Q, n), torch.float64), e((Q, n), torch.uint16), e((Q, n), torch.uint16),
+    return (e((Q, n), torch.int32), e((Q, n), torch.float64), e((Q, n) if want_counts else (0, n), torch.uint16),
+            e((Q, n) if want_pos else (0, n), torch.uint16),
             e((Q,), torch.int32), e((Q,), torch.int32))
 
 
 class FuseOut(NamedTuple):
     ids: torch.Tensor       # int32  [Q, R*K]  ranked doc ids
     scores: torch.Tensor    # float64[Q, R*K]  fused scores
-    counts: torch.Tensor    # uint16 [Q, R*K]  postings merged per doc (CombMNZ count)
-    pos: torch.Tensor       # uint16 [Q, R*K]  first-seen index of the doc
+    counts: torch.Tensor    # uint16 [Q, R*K]  postings merged per doc (CombMNZ count); [0, R*K] if not requested
+    pos: torch.Tensor       # uint16 [Q, R*K]  first-seen index of the doc;              [0, R*K] if not requested
     lens: torch.Tensor      # int32  [Q]       union size
     status: torch.Tensor    # int32  [Q]       QSTAT_* bits
 
 
 def fuse(doc_ids, scores, lens, weights=None, ranks=None, method=N.METHOD_SUM, norm=N.NORM_NONE,
-         rrf_k=60.0, flags=0) -> FuseOut:
+         rrf_k=60.0, flags=0, want_counts=True, want_pos=True) -> FuseOut:
     return FuseOut(*torch.ops.qppfusion.fuse(doc_ids, scores, lens, weights, ranks, int(method), int(norm),
-                                             float(rrf_k), int(flags)))
+                                             float(rrf_k), int(flags), bool(want_counts), bool(want_pos)))
 
 
 # ---------------------------------------------------------------------------------------------- qpp
