@@ -156,6 +156,37 @@ QF_API int qf_qpp_colnorm(double* vals, int Q, int R, int ncols, int mode, int r
 QF_API int qf_qpp_select_weight(const double* vals, int Q, int R, int ncols, int col, int ncols_mean,
                          double* weights, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Dense retrieval  --  replaces faiss.IndexFlatIP.search behind BGERetriever._search_batch /
+ *                      _search_faiss_batch (src/retrievers/bge.py:179-194; also the flat-IP search of
+ *                      TCTColBERTRetriever, src/retrievers/tct_colbert.py:139-151)
+ * ---------------------------------------------------------------------------------------------- */
+/*
+ * Exact inner-product top-k of queries[Q][D] against corpus[N][D], both bf16 row-major, fp32 accumulate
+ * on the tcgen05 tensor cores (the reference scores in fp32; see DESIGN.md for the bf16 tolerance).
+ * Output rows are sorted by (score descending, id ascending); ids are corpus row + id_offset (the
+ * shard offset under corpus sharding); rows with fewer than k hits are padded with id -1 / score -inf,
+ * as FAISS does.  out_status[q] (nullable): 0 ok, bit 0 = the candidate threshold admitted fewer than
+ * k documents, bit 1 = more than the candidate capacity (results for that query are then NOT exact and
+ * the host wrapper re-runs it; never silently accepted).
+ * Envelope: D multiple of 64 and <= 768 (the query tile is held in tensor memory), k <= qf_dense_max_k().
+ * ws: qf_dense_workspace_bytes(Q, N, k) bytes of device scratch.
+ */
+QF_API size_t qf_dense_workspace_bytes(int Q, int N, int k);
+QF_API int    qf_dense_max_k(void);
+QF_API int    qf_dense_topk(const void* queries_bf16, const void* corpus_bf16, int Q, int N, int D, int k,
+                            long long id_offset, float* out_scores, int32_t* out_ids, int32_t* out_status,
+                            void* ws, size_t ws_bytes, void* stream);
+
+/*
+ * k-way merge after the all-gather of per-shard results (multi-GPU dense retrieval; precedent: the
+ * reference's HNSW segment merge, src/retrievers/bge.py:216-237): scores/ids are [G][Q][k] as
+ * ncclAllGather leaves them, ids global, -1 = padding.  Output [Q][k], (score desc, id asc).
+ * Envelope: G*k <= 8192.
+ */
+QF_API int    qf_topk_merge(const float* scores, const int32_t* ids, int G, int Q, int k,
+                            float* out_scores, int32_t* out_ids, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,668 @@
+// qf_dense_topk: exact inner-product top-k of a bf16 query batch against a bf16 corpus matrix
+// (reference: BGERetriever._search_faiss_batch -> faiss.IndexFlatIP.search, src/retrievers/bge.py:179-194).
+//
+// B200 design: the GEMM  S[Q,N] = Qm[Q,D] . C[N,D]^T  runs on the 5th-gen tensor cores and the score
+// matrix never reaches HBM:
+//   * a persistent CTA keeps ONE 128-query tile resident in TENSOR MEMORY as the A operand
+//     (128 lanes x D/2 columns, D <= 768 -> 384 of the 512 TMEM columns); the remaining 128 columns are
+//     two 64-column fp32 accumulator stages
+//   * the corpus streams through shared memory exactly once per query tile: TMA (cp.async.bulk.tensor,
+//     SWIZZLE_128B) fills a ring of 24 x 8 KB boxes (64 docs x 64 k), an mbarrier pipeline feeds
+//     tcgen05.mma.cta_group::1.kind::f16 (A from TMEM, B from smem descriptors, M=128 N=64 K=16)
+//   * four epilogue warps read each finished accumulator stage with tcgen05.ld (TMEM lane == query row,
+//     so every thread owns one query's threshold in a register), and either
+//        FILTER  : append (score, doc) pairs with score >= tau[q] to the query's candidate list, or
+//        STORE   : write the raw scores (threshold-estimation sample / exact fallback)
+//   * tau[q] comes from an exact order statistic of a strided corpus sample; a per-query select kernel
+//     then ranks the few thousand candidates (score desc, id asc) and emits the top k.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "qf_common.cuh"
+#include "qf_radix.cuh"
+
+namespace {
+
+using qf::u16;
+using qf::u32;
+using qf::u64;
+
+constexpr int BM = 128;                 // queries per tile (TMEM lanes)
+constexpr int BN = 64;                  // docs per accumulator stage
+constexpr int BK = 64;                  // k elements per TMA box (128 B rows, SWIZZLE_128B)
+constexpr int MAX_D = 768;
+constexpr int SLOT_BYTES = BN * BK * 2; // 8 KB
+constexpr int NSLOT = 24;
+constexpr int A_COLS = MAX_D / 2;       // 384 TMEM columns hold the query tile
+constexpr int TMEM_COLS = 512;
+constexpr int NT = 256;                 // warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc, warps 4-7 epilogue
+constexpr int EPI_THREADS = 128;
+
+constexpr int MODE_FILTER = 0;
+constexpr int MODE_STORE = 1;
+
+struct DenseParams {
+  const __nv_bfloat16* queries;   // [Q, D]
+  int Q, N, D;
+  int n_mtiles;                   // ceil(Q / 128)
+  int n_vtiles;                   // virtual doc tiles processed by this launch
+  int tile_step;                  // real tile = vtile * tile_step (1 = whole corpus, >1 = strided sample)
+  int chunk_tiles;                // vtiles per work unit
+  int mode;
+  const float* tau;               // [Q]            (FILTER)
+  float* cand_score;              // [Q, cand_cap]  (FILTER)
+  int* cand_id;                   // [Q, cand_cap]
+  int* cand_cnt;                  // [Q]
+  int cand_cap;
+  float* store;                   // [n_mtiles*128, store_ld]  (STORE): column = vtile*64 + j
+  long long store_ld;
+};
+
+// ------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ u32 smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(u64* bar, u32 count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(u64* bar, u32 bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(u64* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64* bar, u32 parity) {
+  u32 done;
+  const u32 addr = smem_u32(bar);
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tmap, u64* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<u64>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(u32* smem_dst, u32 ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(u32 taddr, u32 ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+// D[tmem_d] (+)= A[tmem_a] * B[smem desc]   (A from tensor memory, kind::f16 = bf16/f16 inputs, fp32 accumulate)
+__device__ __forceinline__ void umma_ts(u32 tmem_d, u32 tmem_a, u64 desc_b, u32 idesc, u32 accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(u64* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_st8(u32 taddr, const u32 (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld32(u32 taddr, u32 (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (rows of 128 B, 8-row groups 1024 B apart)
+__device__ __forceinline__ u64 make_desc_sw128(u32 saddr) {
+  u64 d = 0;
+  d |= (u64)((saddr >> 4) & 0x3FFFu);   // start address
+  d |= (u64)1 << 16;                    // leading byte offset (ignored for swizzled K-major)
+  d |= (u64)(1024 >> 4) << 32;          // stride byte offset between 8-row groups
+  d |= (u64)1 << 46;                    // descriptor version (Blackwell)
+  d |= (u64)2 << 61;                    // SWIZZLE_128B
+  return d;
+}
+
+// instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=64
+constexpr u32 IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((u32)(BN >> 3) << 17) | ((u32)(BM >> 4) << 24);
+
+struct __align__(8) DenseSmemCtl {
+  u64 full[NSLOT];
+  u64 empty[NSLOT];
+  u64 tmem_full[2];
+  u64 tmem_empty[2];
+  u64 a_ready;
+  u32 tmem_base;
+};
+
+__global__ void __launch_bounds__(NT, 1) dense_kernel(const __grid_constant__ CUtensorMap tmap, const DenseParams p) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* slots = smem;
+  DenseSmemCtl* ctl = reinterpret_cast<DenseSmemCtl*>(smem + NSLOT * SLOT_BYTES);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int KB = p.D / BK;
+  const int n_chunks = (p.n_vtiles + p.chunk_tiles - 1) / p.chunk_tiles;
+  const int n_units = n_chunks * p.n_mtiles;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < NSLOT; ++i) {
+      mbar_init(&ctl->full[i], 1);
+      mbar_init(&ctl->empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&ctl->tmem_full[i], 1);
+      mbar_init(&ctl->tmem_empty[i], EPI_THREADS);
+    }
+    mbar_init(&ctl->a_ready, EPI_THREADS);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(&ctl->tmem_base, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const u32 tmem_base = ctl->tmem_base;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    if (lane == 0) {
+      int slot = 0;
+      u32 phase = 0;
+      for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+        const int c = u / p.n_mtiles;
+        const int t0 = c * p.chunk_tiles, t1 = min(p.n_vtiles, t0 + p.chunk_tiles);
+        for (int t = t0; t < t1; ++t) {
+          const int row0 = t * p.tile_step * BN;
+          for (int kb = 0; kb < KB; ++kb) {
+            mbar_wait(&ctl->empty[slot], phase ^ 1);
+            mbar_expect_tx(&ctl->full[slot], SLOT_BYTES);
+            tma_load_2d(slots + slot * SLOT_BYTES, &tmap, &ctl->full[slot], kb * BK, row0);
+            if (++slot == NSLOT) { slot = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    if (lane == 0) {
+      int slot = 0, acc = 0, cur_m = -1;
+      u32 phase = 0, acc_phase = 0, a_phase = 0;
+      for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+        const int c = u / p.n_mtiles, m = u % p.n_mtiles;
+        const int t0 = c * p.chunk_tiles, t1 = min(p.n_vtiles, t0 + p.chunk_tiles);
+        if (m != cur_m) {
+          mbar_wait(&ctl->a_ready, a_phase);
+          a_phase ^= 1;
+          cur_m = m;
+          tc_fence_after();
+        }
+        for (int t = t0; t < t1; ++t) {
+          mbar_wait(&ctl->tmem_empty[acc], acc_phase ^ 1);
+          tc_fence_after();
+          const u32 tmem_d = tmem_base + A_COLS + acc * BN;
+          for (int kb = 0; kb < KB; ++kb) {
+            mbar_wait(&ctl->full[slot], phase);
+            tc_fence_after();
+            const u64 desc = make_desc_sw128(smem_u32(slots + slot * SLOT_BYTES));
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) {
+              // advance 16 k-elements: +32 B in the B descriptor, +8 columns in the TMEM A operand
+              umma_ts(tmem_d, tmem_base + kb * (BK / 2) + k * 8, desc + (u64)(k * 2), IDESC, (kb | k) != 0);
+            }
+            umma_commit(&ctl->empty[slot]);
+            if (++slot == NSLOT) { slot = 0; phase ^= 1; }
+          }
+          umma_commit(&ctl->tmem_full[acc]);
+          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================================================================== epilogue (128 threads = 128 query rows)
+    const int row = tid - 128;
+    const u32 lane_base = (u32)((warp & 3) * 32) << 16;
+    int acc = 0, cur_m = -1;
+    u32 acc_phase = 0;
+    float tau = INFINITY;
+    int q = 0;
+    for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+      const int c = u / p.n_mtiles, m = u % p.n_mtiles;
+      const int t0 = c * p.chunk_tiles, t1 = min(p.n_vtiles, t0 + p.chunk_tiles);
+      if (m != cur_m) {
+        // every MMA that read the previous query tile has completed (its last tmem_full was consumed)
+        q = m * BM + row;
+        const uint4* src = reinterpret_cast<const uint4*>(p.queries + (size_t)min(q, p.Q - 1) * p.D);
+        const bool valid = q < p.Q;
+        for (int j = 0; j < p.D / 16; ++j) {
+          uint4 a = __ldg(src + 2 * j), b = __ldg(src + 2 * j + 1);
+          u32 r[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+          if (!valid) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) r[i] = 0u;
+          }
+          tmem_st8(tmem_base + lane_base + j * 8, r);
+        }
+        tmem_wait_st();
+        tc_fence_before();
+        mbar_arrive(&ctl->a_ready);
+        cur_m = m;
+        tau = (valid && p.mode == MODE_FILTER) ? __ldg(p.tau + q) : INFINITY;
+      }
+      for (int t = t0; t < t1; ++t) {
+        mbar_wait(&ctl->tmem_full[acc], acc_phase);
+        tc_fence_after();
+        u32 v0[32], v1[32];
+        const u32 taddr = tmem_base + lane_base + A_COLS + acc * BN;
+        tmem_ld32(taddr, v0);
+        tmem_ld32(taddr + 32, v1);
+        tmem_wait_ld();
+        tc_fence_before();
+        mbar_arrive(&ctl->tmem_empty[acc]);        // accumulator stage is free again
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+
+        const int doc0 = t * p.tile_step * BN;
+        if (p.mode == MODE_FILTER) {
+          if (q < p.Q) {
+            const int nvalid = min(BN, p.N - doc0);
+#pragma unroll
+            for (int j = 0; j < 64; ++j) {
+              const float s = __uint_as_float(j < 32 ? v0[j & 31] : v1[j & 31]);
+              if (s >= tau && j < nvalid) {
+                const int pos = atomicAdd(p.cand_cnt + q, 1);
+                if (pos < p.cand_cap) {
+                  p.cand_score[(size_t)q * p.cand_cap + pos] = s;
+                  p.cand_id[(size_t)q * p.cand_cap + pos] = doc0 + j;
+                }
+              }
+            }
+          }
+        } else {
+          float4* dst = reinterpret_cast<float4*>(p.store + (size_t)(m * BM + row) * p.store_ld + (size_t)t * BN);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            dst[j] = make_float4(__uint_as_float(v0[4 * j]), __uint_as_float(v0[4 * j + 1]), __uint_as_float(v0[4 * j + 2]),
+                                 __uint_as_float(v0[4 * j + 3]));
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            dst[8 + j] = make_float4(__uint_as_float(v1[4 * j]), __uint_as_float(v1[4 * j + 1]), __uint_as_float(v1[4 * j + 2]),
+                                     __uint_as_float(v1[4 * j + 3]));
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ threshold
+// tau[q] = the j-th largest of the valid sample scores of row q (exact, MSB-first radix select on the
+// order-preserving integer image of the floats).  One CTA per query row.
+__device__ __forceinline__ u32 ord_f32(float x) {
+  const u32 b = __float_as_uint(x);
+  return (b >> 31) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float unord_f32(u32 o) {
+  return __uint_as_float((o >> 31) ? (o & 0x7fffffffu) : ~o);
+}
+
+__global__ void __launch_bounds__(512) tau_kernel(const float* sample, long long ld, int n_vtiles, int tile_step, int N, int Q,
+                                                  int target, float* tau) {
+  __shared__ u32 hist[256];
+  __shared__ u32 s_prefix, s_remaining;
+  const int q = blockIdx.x;
+  if (q >= Q) return;
+  const float* row = sample + (size_t)q * ld;
+  const int n_cols = n_vtiles * BN;
+  // number of valid sample docs (real doc index < N)
+  long long s_valid = 0;
+  for (int t = 0; t < n_vtiles; ++t) {   // cheap: <= 512 iterations, same on every thread
+    const long long d0 = (long long)t * tile_step * BN;
+    s_valid += max(0ll, min((long long)BN, (long long)N - d0));
+  }
+  long long jj = ((long long)target * s_valid + N - 1) / N;
+  if (jj < 1) jj = 1;
+  if (jj > s_valid) jj = s_valid;
+  u32 prefix = 0, remaining = (u32)jj;
+  for (int pass = 0; pass < 4; ++pass) {
+    const int shift = 24 - 8 * pass;
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    const u32 mask_hi = pass == 0 ? 0u : (0xFFFFFFFFu << (shift + 8));
+    for (int cidx = threadIdx.x; cidx < n_cols; cidx += blockDim.x) {
+      const long long doc = (long long)(cidx / BN) * tile_step * BN + (cidx % BN);
+      if (doc < N) {
+        const u32 o = ord_f32(row[cidx]);
+        if ((o & mask_hi) == prefix) atomicAdd(&hist[(o >> shift) & 255u], 1u);
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      u32 rem = remaining;
+      int d = 255;
+      for (; d > 0; --d) {
+        if (hist[d] >= rem) break;
+        rem -= hist[d];
+      }
+      s_prefix = prefix | ((u32)d << shift);
+      s_remaining = rem;
+    }
+    __syncthreads();
+    prefix = s_prefix;
+    remaining = s_remaining;
+  }
+  if (threadIdx.x == 0) tau[q] = unord_f32(prefix);
+}
+
+__global__ void fill_kernel(float* p, int n, float v) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+// ------------------------------------------------------------------------------------------ select
+// Rank one query's candidates by (score desc, id asc) and emit the top k.  Candidates come either from
+// the FILTER pass (n = cand_cnt[q], arbitrary order) or from `nseg` already-ranked segments
+// (multi-GPU merge).  Stable LSD radix on the 32-bit score image, exact fix-up of equal-score runs by id.
+constexpr int SEL_CAP = 8192;
+constexpr int SEL_NT = 512;
+constexpr int SEL_ROUNDS = (SEL_CAP / 32 + SEL_NT / 32 - 1) / (SEL_NT / 32);
+
+struct SelectParams {
+  const float* cand_score;
+  const int* cand_id;
+  const int* cand_cnt;     // nullable: n = nseg * seg_len
+  long long q_stride;      // element stride between queries
+  long long seg_stride;    // element stride between segments
+  int nseg, seg_len;
+  int Q, k, N_total;
+  long long id_offset;
+  float* out_scores;       // [Q, k]
+  int* out_ids;            // [Q, k]  (-1 padded)
+  int* out_status;         // [Q] nullable: 1 = candidate underflow, 2 = overflow
+};
+
+__global__ void __launch_bounds__(SEL_NT, 1) select_kernel(const SelectParams p) {
+  extern __shared__ __align__(16) unsigned char sm[];
+  float* s_score = reinterpret_cast<float*>(sm);
+  int* s_id = reinterpret_cast<int*>(sm + 4 * SEL_CAP);
+  u32* keyA = reinterpret_cast<u32*>(sm + 8 * SEL_CAP);
+  u32* keyB = reinterpret_cast<u32*>(sm + 12 * SEL_CAP);
+  u16* idxA = reinterpret_cast<u16*>(sm + 16 * SEL_CAP);
+  u16* idxB = reinterpret_cast<u16*>(sm + 18 * SEL_CAP);
+  u16* whist = reinterpret_cast<u16*>(sm + 20 * SEL_CAP);
+  __shared__ int warp_tot[32];
+  __shared__ int flag_single, flag_long;
+  const int tid = threadIdx.x;
+
+  for (int q = blockIdx.x; q < p.Q; q += gridDim.x) {
+    int n_raw = p.cand_cnt ? p.cand_cnt[q] : p.nseg * p.seg_len;
+    int status = 0;
+    const int want = min(p.k, p.N_total);
+    if (n_raw > SEL_CAP) { status |= 2; n_raw = SEL_CAP; }
+    const int n = n_raw;
+    if (n < want) status |= 1;
+    const int n_pad = (n + 31) & ~31;
+    if (tid == 0) flag_long = 0;
+    for (int i = tid; i < n_pad; i += SEL_NT) {
+      float s = -INFINITY;
+      int id = 0x7fffffff;
+      if (i < n) {
+        const int seg = p.cand_cnt ? 0 : i / p.seg_len;
+        const int off = p.cand_cnt ? i : i % p.seg_len;
+        const size_t a = (size_t)q * p.q_stride + (size_t)seg * p.seg_stride + off;
+        s = p.cand_score[a];
+        id = p.cand_id[a];
+        if (id < 0) s = -INFINITY;          // padding of a short segment
+      }
+      s_score[i] = s;
+      s_id[i] = id;
+      keyA[i] = i < n ? ~ord_f32(s + 0.0f) : 0xFFFFFFFFu;     // ascending key = descending score
+      idxA[i] = (u16)i;
+    }
+    __syncthreads();
+    u32* kin = keyA; u32* kout = keyB;
+    u16* iin = idxA; u16* iout = idxB;
+#pragma unroll 1
+    for (int pass = 0; pass < 4; ++pass) {
+      const int shift = 8 * pass;
+      const u32* kk = kin;
+      auto dig = [&](int e) -> u32 { return (kk[e] >> shift) & 255u; };
+      if (qf::radix_pass<SEL_NT, SEL_ROUNDS, true>(dig, n_pad, kin, kout, iin, iout, whist, warp_tot, &flag_single)) {
+        u32* t = kin; kin = kout; kout = t;
+        u16* ti = iin; iin = iout; iout = ti;
+      }
+    }
+    // equal-score runs: order by id ascending (exact)
+    for (int j = tid; j < n; j += SEL_NT) {
+      const u32 kj = kin[j];
+      const bool head = (j == 0 || kin[j - 1] != kj) && (j + 1 < n && kin[j + 1] == kj);
+      if (head) {
+        int e = j + 2;
+        while (e < n && kin[e] == kj) ++e;
+        for (int a = j + 1; a < e; ++a) {
+          const u16 ia = iin[a];
+          const int ida = s_id[ia];
+          int b = a - 1;
+          while (b >= j && s_id[iin[b]] > ida) { iin[b + 1] = iin[b]; --b; }
+          iin[b + 1] = ia;
+        }
+      }
+    }
+    __syncthreads();
+    for (int j = tid; j < p.k; j += SEL_NT) {
+      float s = -INFINITY;
+      int id = -1;
+      if (j < n) {
+        const int e = iin[j];
+        if (s_id[e] != 0x7fffffff && s_score[e] != -INFINITY) {
+          s = s_score[e];
+          id = (int)(s_id[e] + p.id_offset);
+        }
+      }
+      p.out_scores[(size_t)q * p.k + j] = s;
+      p.out_ids[(size_t)q * p.k + j] = id;
+    }
+    if (p.out_status && tid == 0) p.out_status[q] = status;
+    __syncthreads();
+  }
+}
+
+constexpr size_t SEL_SMEM = 20 * SEL_CAP + 2 * (SEL_NT / 32) * 256;
+
+// ------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int get_encode_fn(EncodeTiledFn* out) {
+  static EncodeTiledFn cached = nullptr;
+  if (!cached) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    QF_CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    QF_REQUIRE(fn != nullptr && qres == cudaDriverEntryPointSuccess, QF_E_CUDA, "cuTensorMapEncodeTiled not available");
+    cached = reinterpret_cast<EncodeTiledFn>(fn);
+  }
+  *out = cached;
+  return QF_OK;
+}
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+struct DenseWs {
+  size_t off_cnt, off_tau, off_cscore, off_cid, off_sample, total;
+  int n_sample_tiles;
+  long long sample_ld;
+};
+
+DenseWs plan_ws(int Q, int N) {
+  DenseWs w{};
+  const int n_mtiles = (Q + BM - 1) / BM;
+  const long long T = ((long long)N + BN - 1) / BN;
+  w.n_sample_tiles = N > SEL_CAP ? (int)(T < 512 ? T : 512) : 0;
+  w.sample_ld = (long long)w.n_sample_tiles * BN;
+  size_t o = 0;
+  w.off_cnt = o;    o = align_up(o + sizeof(int) * (size_t)Q, 256);
+  w.off_tau = o;    o = align_up(o + sizeof(float) * (size_t)Q, 256);
+  w.off_cscore = o; o = align_up(o + sizeof(float) * (size_t)Q * SEL_CAP, 256);
+  w.off_cid = o;    o = align_up(o + sizeof(int) * (size_t)Q * SEL_CAP, 256);
+  w.off_sample = o; o = align_up(o + sizeof(float) * (size_t)n_mtiles * BM * (size_t)w.sample_ld, 256);
+  w.total = o;
+  return w;
+}
+
+constexpr size_t DENSE_SMEM = (size_t)NSLOT * SLOT_BYTES + sizeof(DenseSmemCtl) + 1024;
+
+}  // namespace
+
+extern "C" size_t qf_dense_workspace_bytes(int Q, int N, int k) {
+  if (Q < 1 || N < 1 || k < 1) return 0;
+  return plan_ws(Q, N).total;
+}
+
+extern "C" int qf_dense_max_k(void) { return 1024; }
+
+extern "C" int qf_dense_topk(const void* queries_bf16, const void* corpus_bf16, int Q, int N, int D, int k,
+                             long long id_offset, float* out_scores, int32_t* out_ids, int32_t* out_status, void* ws,
+                             size_t ws_bytes, void* stream) {
+  QF_REQUIRE(Q >= 0 && N >= 1 && k >= 1, QF_E_INVALID, "qf_dense_topk: bad sizes Q=%d N=%d k=%d", Q, N, k);
+  QF_REQUIRE(D >= BK && D % BK == 0 && D <= MAX_D, QF_E_UNSUPPORTED,
+             "qf_dense_topk: D=%d must be a multiple of %d and <= %d (query tile lives in tensor memory)", D, BK, MAX_D);
+  QF_REQUIRE(k <= qf_dense_max_k(), QF_E_UNSUPPORTED, "qf_dense_topk: k=%d exceeds %d", k, qf_dense_max_k());
+  if (Q == 0) return QF_OK;
+  QF_REQUIRE(queries_bf16 && corpus_bf16 && out_scores && out_ids && ws, QF_E_INVALID, "qf_dense_topk: null pointer argument");
+  QF_REQUIRE((reinterpret_cast<uintptr_t>(corpus_bf16) & 15) == 0 && (reinterpret_cast<uintptr_t>(queries_bf16) & 15) == 0,
+             QF_E_INVALID, "qf_dense_topk: queries/corpus must be 16-byte aligned");
+  int rc = qf::check_device();
+  if (rc != QF_OK) return rc;
+  const DenseWs w = plan_ws(Q, N);
+  QF_REQUIRE(ws_bytes >= w.total, QF_E_WORKSPACE, "qf_dense_topk: workspace %zu < %zu bytes", ws_bytes, w.total);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  unsigned char* base = reinterpret_cast<unsigned char*>(ws);
+
+  EncodeTiledFn encode;
+  rc = get_encode_fn(&encode);
+  if (rc != QF_OK) return rc;
+  CUtensorMap tmap;
+  {
+    cuuint64_t gdim[2] = {(cuuint64_t)D, (cuuint64_t)N};
+    cuuint64_t gstride[1] = {(cuuint64_t)D * 2};
+    cuuint32_t box[2] = {BK, BN};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(corpus_bf16), gdim, gstride, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    QF_REQUIRE(r == CUDA_SUCCESS, QF_E_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  }
+  static bool configured = false;
+  if (!configured) {
+    QF_CUDA_TRY(cudaFuncSetAttribute(dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DENSE_SMEM));
+    QF_CUDA_TRY(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SEL_SMEM));
+    configured = true;
+  }
+  const int sms = qf::sm_count();
+  const int n_mtiles = (Q + BM - 1) / BM;
+  const int T = (int)(((long long)N + BN - 1) / BN);
+  int* cnt = reinterpret_cast<int*>(base + w.off_cnt);
+  float* tau = reinterpret_cast<float*>(base + w.off_tau);
+
+  DenseParams p{};
+  p.queries = reinterpret_cast<const __nv_bfloat16*>(queries_bf16);
+  p.Q = Q; p.N = N; p.D = D; p.n_mtiles = n_mtiles;
+  p.tau = tau;
+  p.cand_score = reinterpret_cast<float*>(base + w.off_cscore);
+  p.cand_id = reinterpret_cast<int*>(base + w.off_cid);
+  p.cand_cnt = cnt;
+  p.cand_cap = SEL_CAP;
+  p.store = reinterpret_cast<float*>(base + w.off_sample);
+  p.store_ld = w.sample_ld;
+
+  QF_CUDA_TRY(cudaMemsetAsync(cnt, 0, sizeof(int) * (size_t)Q, st));
+  auto grid_for = [&](int n_units) { return n_units < sms ? n_units : sms; };
+  if (w.n_sample_tiles > 0) {
+    // threshold estimation: score a strided sample of doc tiles, take an exact order statistic per query
+    p.mode = MODE_STORE;
+    p.n_vtiles = w.n_sample_tiles;
+    p.tile_step = T / w.n_sample_tiles;
+    p.chunk_tiles = 16;
+    const int units = ((p.n_vtiles + p.chunk_tiles - 1) / p.chunk_tiles) * n_mtiles;
+    dense_kernel<<<grid_for(units), NT, DENSE_SMEM, st>>>(tmap, p);
+    QF_CUDA_TRY(cudaGetLastError());
+    const int target = k * 3 + 1000;
+    tau_kernel<<<Q, 512, 0, st>>>(p.store, p.store_ld, p.n_vtiles, p.tile_step, N, Q, target, tau);
+    QF_CUDA_TRY(cudaGetLastError());
+  } else {
+    fill_kernel<<<(Q + 255) / 256, 256, 0, st>>>(tau, Q, -INFINITY);
+    QF_CUDA_TRY(cudaGetLastError());
+  }
+  p.mode = MODE_FILTER;
+  p.n_vtiles = T;
+  p.tile_step = 1;
+  p.chunk_tiles = T >= 4096 ? 256 : (T >= 256 ? 32 : 4);
+  {
+    const int units = ((p.n_vtiles + p.chunk_tiles - 1) / p.chunk_tiles) * n_mtiles;
+    dense_kernel<<<grid_for(units), NT, DENSE_SMEM, st>>>(tmap, p);
+    QF_CUDA_TRY(cudaGetLastError());
+  }
+  SelectParams sp{};
+  sp.cand_score = p.cand_score; sp.cand_id = p.cand_id; sp.cand_cnt = cnt;
+  sp.q_stride = SEL_CAP; sp.seg_stride = 0; sp.nseg = 1; sp.seg_len = SEL_CAP;
+  sp.Q = Q; sp.k = k; sp.N_total = N; sp.id_offset = id_offset;
+  sp.out_scores = out_scores; sp.out_ids = out_ids; sp.out_status = out_status;
+  select_kernel<<<Q < sms ? Q : sms, SEL_NT, SEL_SMEM, st>>>(sp);
+  QF_CUDA_TRY(cudaGetLastError());
+  return QF_OK;
+}
+
+extern "C" int qf_topk_merge(const float* scores, const int32_t* ids, int G, int Q, int k, float* out_scores,
+                             int32_t* out_ids, void* stream) {
+  QF_REQUIRE(G >= 1 && Q >= 0 && k >= 1, QF_E_INVALID, "qf_topk_merge: bad sizes G=%d Q=%d k=%d", G, Q, k);
+  QF_REQUIRE((long long)G * k <= SEL_CAP, QF_E_UNSUPPORTED, "qf_topk_merge: G*k=%lld exceeds %d", (long long)G * k, SEL_CAP);
+  if (Q == 0) return QF_OK;
+  QF_REQUIRE(scores && ids && out_scores && out_ids, QF_E_INVALID, "qf_topk_merge: null pointer argument");
+  int rc = qf::check_device();
+  if (rc != QF_OK) return rc;
+  static bool configured = false;
+  if (!configured) {
+    QF_CUDA_TRY(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SEL_SMEM));
+    configured = true;
+  }
+  SelectParams sp{};
+  sp.cand_score = scores; sp.cand_id = ids; sp.cand_cnt = nullptr;
+  sp.q_stride = k; sp.seg_stride = (long long)Q * k; sp.nseg = G; sp.seg_len = k;
+  sp.Q = Q; sp.k = k; sp.N_total = 0x7fffffff; sp.id_offset = 0;
+  sp.out_scores = out_scores; sp.out_ids = out_ids; sp.out_status = nullptr;
+  const int sms = qf::sm_count();
+  select_kernel<<<Q < sms ? Q : sms, SEL_NT, SEL_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(sp);
+  QF_CUDA_TRY(cudaGetLastError());
+  return QF_OK;
+}

@@ -16,6 +16,7 @@
 //       32 bits of a range-normalised descending key, then an exact fix-up of equal-prefix runs by
 //       full float64 comparison (long runs fall back to a full 64-bit sort)
 #include "qf_common.cuh"
+#include "qf_radix.cuh"
 
 namespace {
 
@@ -106,109 +107,6 @@ __device__ __forceinline__ int list_of(const int* start, int R, int seq) {
   int r = 0;
   while (r + 1 < R && seq >= start[r + 1]) ++r;
   return r;
-}
-
-// One stable LSD radix pass over `n_pad` (multiple of 32) elements.
-// digit(e) is supplied by `dig`; payload = (optional key32, idx16).  Ranking inside a warp uses
-// __match_any_sync, per-warp digit counters live in shared memory (only the lowest lane of each
-// digit group updates a counter, so no atomics), a digit-major scan turns them into scatter bases.
-template <int NT, int MAXROUNDS, bool CARRY_KEY, typename DigitFn>
-__device__ __forceinline__ bool radix_pass(DigitFn dig, int n_pad, const u32* keyIn, u32* keyOut, const u16* idxIn,
-                                           u16* idxOut, u16* whist, int* warp_tot, int* single_flag) {
-  constexpr int NW = NT / 32;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int rounds_total = n_pad >> 5;
-  const int rounds_per_warp = (rounds_total + NW - 1) / NW;
-  const int r0 = warp * rounds_per_warp;
-  const int r1 = min(rounds_total, r0 + rounds_per_warp);
-
-  for (int i = tid; i < NW * 256; i += NT) whist[i] = 0;
-  if (tid == 0) *single_flag = 0;
-  __syncthreads();
-
-  u16 lrank[MAXROUNDS];
-  u16 ldig[MAXROUNDS];
-  u16* myhist = whist + warp * 256;
-#pragma unroll
-  for (int k = 0; k < MAXROUNDS; ++k) {
-    const int rd = r0 + k;
-    if (rd < r1) {
-      const int e = (rd << 5) + lane;
-      const u32 d = dig(e);
-      const u32 peers = __match_any_sync(0xffffffffu, d);
-      const u32 lt = peers & ((1u << lane) - 1u);
-      u32 base = 0;
-      if (lt == 0) {
-        base = myhist[d];
-        myhist[d] = (u16)(base + __popc(peers));
-      }
-      __syncwarp();
-      base = __shfl_sync(0xffffffffu, base, __ffs(peers) - 1);
-      lrank[k] = (u16)(base + __popc(lt));
-      ldig[k] = (u16)d;
-    }
-  }
-  __syncthreads();
-
-  // digit-major exclusive scan: thread t < SCAN_T owns digits [t*DPT, (t+1)*DPT)
-  constexpr int DPT = NT >= 256 ? 1 : 256 / NT;
-  constexpr int SCAN_T = 256 / DPT;
-  {
-    int dtot[DPT];
-    int tot = 0;
-    if (tid < SCAN_T) {
-#pragma unroll
-      for (int j = 0; j < DPT; ++j) {
-        const int d = tid * DPT + j;
-        int run = 0;
-#pragma unroll 4
-        for (int w = 0; w < NW; ++w) {
-          const int c = whist[w * 256 + d];
-          whist[w * 256 + d] = (u16)run;
-          run += c;
-        }
-        dtot[j] = run;
-        tot += run;
-        if (run == n_pad) *single_flag = 1;   // every element has this digit: the pass is the identity
-      }
-    }
-    int incl = tot;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int t = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += t;
-    }
-    if (tid < SCAN_T && lane == 31) warp_tot[warp] = incl;
-    __syncthreads();
-    if (tid < SCAN_T) {
-      int excl = incl - tot;
-      for (int w = 0; w < warp; ++w) excl += warp_tot[w];
-#pragma unroll
-      for (int j = 0; j < DPT; ++j) {
-        const int d = tid * DPT + j;
-#pragma unroll 4
-        for (int w = 0; w < NW; ++w) whist[w * 256 + d] = (u16)(whist[w * 256 + d] + excl);
-        excl += dtot[j];
-      }
-    }
-    __syncthreads();
-  }
-  if (*single_flag) {
-    __syncthreads();
-    return false;   // nothing moves; caller keeps the current buffers
-  }
-#pragma unroll
-  for (int k = 0; k < MAXROUNDS; ++k) {
-    const int rd = r0 + k;
-    if (rd < r1) {
-      const int e = (rd << 5) + lane;
-      const int pos = myhist[ldig[k]] + lrank[k];
-      if (CARRY_KEY) keyOut[pos] = keyIn[e];
-      idxOut[pos] = idxIn[e];
-    }
-  }
-  __syncthreads();
-  return true;
 }
 
 template <int CAP, int HBITS, int NT, int ST>
@@ -510,7 +408,7 @@ __global__ void __launch_bounds__(NT) fuse_kernel(const FuseParams p) {
           const int shift = pass * 8;
           const u32* kin = keyIn;
           auto dig = [&](int e) -> u32 { return (kin[e] >> shift) & 255u; };
-          if (radix_pass<NT, MAXROUNDS, true>(dig, n_pad, keyIn, keyOut, idxIn, idxOut, s_whist, m.warp_tot, &m.flag_single)) {
+          if (qf::radix_pass<NT, MAXROUNDS, true>(dig, n_pad, keyIn, keyOut, idxIn, idxOut, s_whist, m.warp_tot, &m.flag_single)) {
             u32* tk = keyIn; keyIn = keyOut; keyOut = tk;
             u16* ti = idxIn; idxIn = idxOut; idxOut = ti;
           }
@@ -559,7 +457,7 @@ __global__ void __launch_bounds__(NT) fuse_kernel(const FuseParams p) {
           };
           // padding elements (u >= n_u) carry digit 255 in every pass and start at the tail, so the
           // stable passes keep them behind every real element
-          if (radix_pass<NT, MAXROUNDS, false>(dig, n_pad, nullptr, nullptr, idxIn, idxOut, s_whist, m.warp_tot, &m.flag_single)) {
+          if (qf::radix_pass<NT, MAXROUNDS, false>(dig, n_pad, nullptr, nullptr, idxIn, idxOut, s_whist, m.warp_tot, &m.flag_single)) {
             u16* ti = idxIn; idxIn = idxOut; idxOut = ti;
           }
         }

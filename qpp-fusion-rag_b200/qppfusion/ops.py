@@ -164,3 +164,63 @@ def _(vals, col, ncols_mean):
 def qpp_select_weight(vals: torch.Tensor, col: int, ncols_mean: int = N.QPP_BRIDGE_COLS) -> torch.Tensor:
     """weights[q, r] = vals[q, r, col], or the mean of the first ncols_mean columns when col == -1."""
     return torch.ops.qppfusion.qpp_select_weight(vals, int(col), int(ncols_mean))
+
+
+# ---------------------------------------------------------------------------------------------- dense
+@torch.library.custom_op("qppfusion::dense_topk", mutates_args=())
+def _dense_topk_op(queries: torch.Tensor, corpus: torch.Tensor, k: int, id_offset: int
+                   ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    dev = N.require_cuda(queries, corpus)
+    if queries.dtype != torch.bfloat16 or corpus.dtype != torch.bfloat16:
+        raise TypeError("queries and corpus must be bfloat16 (convert the fp32 index once with corpus_to_device)")
+    if queries.dim() != 2 or corpus.dim() != 2 or queries.shape[1] != corpus.shape[1]:
+        raise ValueError("queries [Q, D] and corpus [N, D] must share D")
+    Q, D = queries.shape
+    Nn = corpus.shape[0]
+    scores = torch.empty((Q, k), dtype=torch.float32, device=dev)
+    ids = torch.empty((Q, k), dtype=torch.int32, device=dev)
+    status = torch.zeros((Q,), dtype=torch.int32, device=dev)
+    nbytes = N.lib().qf_dense_workspace_bytes(Q, Nn, k)
+    ws = torch.empty((max(nbytes, 16),), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        N.check(N.lib().qf_dense_topk(N.ptr(queries), N.ptr(corpus), Q, Nn, D, k, id_offset, N.ptr(scores), N.ptr(ids),
+                                      N.ptr(status), N.ptr(ws), nbytes, N.stream_ptr(dev)))
+    return scores, ids, status
+
+
+@_dense_topk_op.register_fake
+def _(queries, corpus, k, id_offset):
+    Q = queries.shape[0]
+    return (torch.empty((Q, k), dtype=torch.float32, device=queries.device),
+            torch.empty((Q, k), dtype=torch.int32, device=queries.device),
+            torch.empty((Q,), dtype=torch.int32, device=queries.device))
+
+
+def dense_topk(queries: torch.Tensor, corpus: torch.Tensor, k: int, id_offset: int = 0):
+    """-> (scores f32 [Q,k] desc, ids int32 [Q,k] (-1 padded), status int32 [Q])."""
+    return torch.ops.qppfusion.dense_topk(queries, corpus, int(k), int(id_offset))
+
+
+@torch.library.custom_op("qppfusion::topk_merge", mutates_args=())
+def _topk_merge_op(scores: torch.Tensor, ids: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    dev = N.require_cuda(scores, ids)
+    if scores.dim() != 3 or scores.dtype != torch.float32 or ids.shape != scores.shape or ids.dtype != torch.int32:
+        raise TypeError("scores f32 [G, Q, k] and ids int32 [G, Q, k] expected")
+    G, Q, k = scores.shape
+    out_s = torch.empty((Q, k), dtype=torch.float32, device=dev)
+    out_i = torch.empty((Q, k), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        N.check(N.lib().qf_topk_merge(N.ptr(scores), N.ptr(ids), G, Q, k, N.ptr(out_s), N.ptr(out_i), N.stream_ptr(dev)))
+    return out_s, out_i
+
+
+@_topk_merge_op.register_fake
+def _(scores, ids):
+    G, Q, k = scores.shape
+    return (torch.empty((Q, k), dtype=torch.float32, device=scores.device),
+            torch.empty((Q, k), dtype=torch.int32, device=scores.device))
+
+
+def topk_merge(scores: torch.Tensor, ids: torch.Tensor):
+    """k-way merge of per-shard results [G, Q, k] (as all_gather leaves them) -> ([Q, k], [Q, k])."""
+    return torch.ops.qppfusion.topk_merge(scores, ids)
