@@ -31,12 +31,13 @@ constexpr int BM = 128;                 // queries per tile (TMEM lanes)
 constexpr int BN = 64;                  // docs per accumulator stage
 constexpr int BK = 64;                  // k elements per TMA box (128 B rows, SWIZZLE_128B)
 constexpr int MAX_D = 768;
-constexpr int SLOT_BYTES = BN * BK * 2; // 8 KB
-constexpr int NSLOT = 24;
+constexpr int BOX_BYTES = BN * BK * 2;  // 8 KB: one TMA box = 64 docs x 64 k
+constexpr int SLOT_BYTES = 2 * BOX_BYTES;   // a pipeline slot = two boxes (128 k) behind one mbarrier
+constexpr int NSLOT = 12;
 constexpr int A_COLS = MAX_D / 2;       // 384 TMEM columns hold the query tile
 constexpr int TMEM_COLS = 512;
-constexpr int NT = 256;                 // warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc, warps 4-7 epilogue
-constexpr int EPI_THREADS = 128;
+constexpr int NT = 384;                 // warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc, warps 4-11 epilogue
+constexpr int EPI_THREADS = 256;        // 2 threads per query row (32 accumulator columns each)
 
 constexpr int MODE_FILTER = 0;
 constexpr int MODE_STORE = 1;
@@ -64,15 +65,14 @@ __device__ __forceinline__ u32 smem_u32(const void* p) { return (u32)__cvta_gene
 __device__ __forceinline__ void mbar_init(u64* bar, u32 count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
-__device__ __forceinline__ void mbar_expect_tx(u64* bar, u32 bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+__device__ __forceinline__ void mbar_expect_tx(u32 bar, u32 bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(u64* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+__device__ __forceinline__ void mbar_arrive(u32 bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(u64* bar, u32 parity) {
+__device__ __forceinline__ void mbar_wait(u32 addr, u32 parity) {
   u32 done;
-  const u32 addr = smem_u32(bar);
   do {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -87,10 +87,10 @@ __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarr
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tmap, u64* bar, int c0, int c1) {
+__device__ __forceinline__ void tma_load_2d(u32 smem_dst, const CUtensorMap* tmap, u32 bar, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<u64>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      ::"r"(smem_dst), "l"(reinterpret_cast<u64>(tmap)), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
 
@@ -111,8 +111,8 @@ __device__ __forceinline__ void umma_ts(u32 tmem_d, u32 tmem_a, u64 desc_b, u32 
       ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-__device__ __forceinline__ void umma_commit(u64* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+__device__ __forceinline__ void umma_commit(u32 bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
 __device__ __forceinline__ void tmem_st8(u32 taddr, const u32 (&r)[8]) {
@@ -150,6 +150,8 @@ __device__ __forceinline__ u64 make_desc_sw128(u32 saddr) {
 // instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=64
 constexpr u32 IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((u32)(BN >> 3) << 17) | ((u32)(BM >> 4) << 24);
 
+constexpr int STAGE_N = 8;                // staged candidates per epilogue thread before a flush
+
 struct __align__(8) DenseSmemCtl {
   u64 full[NSLOT];
   u64 empty[NSLOT];
@@ -157,18 +159,44 @@ struct __align__(8) DenseSmemCtl {
   u64 tmem_empty[2];
   u64 a_ready;
   u32 tmem_base;
+  u32 pad;
+  uint2 stage[EPI_THREADS * STAGE_N];     // (score bits, doc id), [slot][thread] so a warp's stores hit 32 banks
 };
+
+__device__ __forceinline__ u32 elect_one() {
+  u32 pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred;
+}
+
+// Move a thread's staged candidates to its query's global candidate list: one returning atomic per
+// STAGE_N survivors.  (Out of line: it sits inside an unrolled loop and would blow the instruction cache.)
+__device__ __noinline__ void flush_stage(float* cand_score, int* cand_id, int* cand_cnt, int cand_cap,
+                                         const uint2* stage, int et, int q, int n_staged) {
+  const int pos = atomicAdd(cand_cnt + q, n_staged);
+  for (int i = 0; i < n_staged; ++i) {
+    if (pos + i < cand_cap) {
+      const uint2 e = stage[i * EPI_THREADS + et];
+      cand_score[(size_t)q * cand_cap + pos + i] = __uint_as_float(e.x);
+      cand_id[(size_t)q * cand_cap + pos + i] = (int)e.y;
+    }
+  }
+}
 
 __global__ void __launch_bounds__(NT, 1) dense_kernel(const __grid_constant__ CUtensorMap tmap, const DenseParams p) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  unsigned char* slots = smem;
   DenseSmemCtl* ctl = reinterpret_cast<DenseSmemCtl*>(smem + NSLOT * SLOT_BYTES);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int KB = p.D / BK;
+  const int KB2 = (p.D + 2 * BK - 1) / (2 * BK);     // pipeline steps per doc tile (128 k each; last may be 64)
   const int n_chunks = (p.n_vtiles + p.chunk_tiles - 1) / p.chunk_tiles;
   const int n_units = n_chunks * p.n_mtiles;
+  // shared-window addresses (computed once; barriers are 8 bytes apart)
+  const u32 a_slots = smem_u32(smem);
+  const u32 a_full = smem_u32(&ctl->full[0]), a_empty = smem_u32(&ctl->empty[0]);
+  const u32 a_tfull = smem_u32(&ctl->tmem_full[0]), a_tempty = smem_u32(&ctl->tmem_empty[0]);
+  const u32 a_aready = smem_u32(&ctl->a_ready);
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < NSLOT; ++i) {
@@ -189,64 +217,77 @@ __global__ void __launch_bounds__(NT, 1) dense_kernel(const __grid_constant__ CU
   const u32 tmem_base = ctl->tmem_base;
 
   if (warp == 0) {
-    // ===================================================================== TMA producer
-    if (lane == 0) {
-      int slot = 0;
-      u32 phase = 0;
-      for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-        const int c = u / p.n_mtiles;
-        const int t0 = c * p.chunk_tiles, t1 = min(p.n_vtiles, t0 + p.chunk_tiles);
-        for (int t = t0; t < t1; ++t) {
-          const int row0 = t * p.tile_step * BN;
-          for (int kb = 0; kb < KB; ++kb) {
-            mbar_wait(&ctl->empty[slot], phase ^ 1);
-            mbar_expect_tx(&ctl->full[slot], SLOT_BYTES);
-            tma_load_2d(slots + slot * SLOT_BYTES, &tmap, &ctl->full[slot], kb * BK, row0);
-            if (++slot == NSLOT) { slot = 0; phase ^= 1; }
+    // ===================================================================== TMA producer (warp-uniform, one elected lane issues)
+    int slot = 0;
+    u32 phase = 0;
+    for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+      const int c = u / p.n_mtiles;
+      const int t0 = c * p.chunk_tiles, t1 = min(p.n_vtiles, t0 + p.chunk_tiles);
+      for (int t = t0; t < t1; ++t) {
+        const int row0 = t * p.tile_step * BN;
+        for (int kb = 0; kb < KB2; ++kb) {
+          mbar_wait(a_empty + 8 * slot, phase ^ 1);
+          if (elect_one()) {
+            const bool two = (kb * 2 + 1) * BK < p.D;
+            mbar_expect_tx(a_full + 8 * slot, two ? SLOT_BYTES : BOX_BYTES);
+            tma_load_2d(a_slots + slot * SLOT_BYTES, &tmap, a_full + 8 * slot, kb * 2 * BK, row0);
+            if (two) tma_load_2d(a_slots + slot * SLOT_BYTES + BOX_BYTES, &tmap, a_full + 8 * slot, (kb * 2 + 1) * BK, row0);
           }
+          __syncwarp();
+          if (++slot == NSLOT) { slot = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================================================================== MMA issuer
-    if (lane == 0) {
-      int slot = 0, acc = 0, cur_m = -1;
-      u32 phase = 0, acc_phase = 0, a_phase = 0;
-      for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-        const int c = u / p.n_mtiles, m = u % p.n_mtiles;
-        const int t0 = c * p.chunk_tiles, t1 = min(p.n_vtiles, t0 + p.chunk_tiles);
-        if (m != cur_m) {
-          mbar_wait(&ctl->a_ready, a_phase);
-          a_phase ^= 1;
-          cur_m = m;
+    // ===================================================================== MMA issuer (warp-uniform, one elected lane issues)
+    int slot = 0, acc = 0, cur_m = -1;
+    u32 phase = 0, acc_phase = 0, a_phase = 0;
+    const u64 desc0 = make_desc_sw128(a_slots);
+    for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+      const int c = u / p.n_mtiles, m = u % p.n_mtiles;
+      const int t0 = c * p.chunk_tiles, t1 = min(p.n_vtiles, t0 + p.chunk_tiles);
+      if (m != cur_m) {
+        mbar_wait(a_aready, a_phase);
+        a_phase ^= 1;
+        cur_m = m;
+        tc_fence_after();
+      }
+      for (int t = t0; t < t1; ++t) {
+        mbar_wait(a_tempty + 8 * acc, acc_phase ^ 1);
+        tc_fence_after();
+        const u32 tmem_d = tmem_base + A_COLS + acc * BN;
+        for (int kb = 0; kb < KB2; ++kb) {
+          mbar_wait(a_full + 8 * slot, phase);
           tc_fence_after();
-        }
-        for (int t = t0; t < t1; ++t) {
-          mbar_wait(&ctl->tmem_empty[acc], acc_phase ^ 1);
-          tc_fence_after();
-          const u32 tmem_d = tmem_base + A_COLS + acc * BN;
-          for (int kb = 0; kb < KB; ++kb) {
-            mbar_wait(&ctl->full[slot], phase);
-            tc_fence_after();
-            const u64 desc = make_desc_sw128(smem_u32(slots + slot * SLOT_BYTES));
+          if (elect_one()) {
+            const u64 desc = desc0 + (u64)(slot * (SLOT_BYTES >> 4));
+            const u32 ta = tmem_base + kb * BK;      // 128 k-elements = 64 TMEM columns per step
+            const bool two = (kb * 2 + 1) * BK < p.D;
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k) {
-              // advance 16 k-elements: +32 B in the B descriptor, +8 columns in the TMEM A operand
-              umma_ts(tmem_d, tmem_base + kb * (BK / 2) + k * 8, desc + (u64)(k * 2), IDESC, (kb | k) != 0);
+            for (int k = 0; k < 4; ++k)              // +32 B in the B descriptor, +8 columns in the TMEM A operand
+              umma_ts(tmem_d, ta + k * 8, desc + (u64)(k * 2), IDESC, (kb | k) != 0);
+            if (two) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_ts(tmem_d, ta + 32 + k * 8, desc + (u64)((BOX_BYTES >> 4) + k * 2), IDESC, 1u);
             }
-            umma_commit(&ctl->empty[slot]);
-            if (++slot == NSLOT) { slot = 0; phase ^= 1; }
+            umma_commit(a_empty + 8 * slot);
+            if (kb == KB2 - 1) umma_commit(a_tfull + 8 * acc);
           }
-          umma_commit(&ctl->tmem_full[acc]);
-          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+          __syncwarp();
+          if (++slot == NSLOT) { slot = 0; phase ^= 1; }
         }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else if (warp >= 4) {
-    // ===================================================================== epilogue (128 threads = 128 query rows)
-    const int row = tid - 128;
+    // ===================================================================== epilogue: 256 threads, 2 per query row
+    const int et = tid - 128;                          // 0..255
+    const int row = ((warp & 3) << 5) | lane;          // TMEM lane == query row of the tile
+    const int half = (warp - 4) >> 2;                  // accumulator columns [32*half, 32*half+32)
     const u32 lane_base = (u32)((warp & 3) * 32) << 16;
-    int acc = 0, cur_m = -1;
+    uint2* stage = ctl->stage;
+    int acc = 0, cur_m = -1, n_staged = 0;
     u32 acc_phase = 0;
     float tau = INFINITY;
     int q = 0;
@@ -255,10 +296,13 @@ __global__ void __launch_bounds__(NT, 1) dense_kernel(const __grid_constant__ CU
       const int t0 = c * p.chunk_tiles, t1 = min(p.n_vtiles, t0 + p.chunk_tiles);
       if (m != cur_m) {
         // every MMA that read the previous query tile has completed (its last tmem_full was consumed)
+        if (n_staged > 0) { flush_stage(p.cand_score, p.cand_id, p.cand_cnt, p.cand_cap, stage, et, q, n_staged); n_staged = 0; }
         q = m * BM + row;
-        const uint4* src = reinterpret_cast<const uint4*>(p.queries + (size_t)min(q, p.Q - 1) * p.D);
         const bool valid = q < p.Q;
-        for (int j = 0; j < p.D / 16; ++j) {
+        // this thread loads half of the row's k range: 16-element groups [jb, je)
+        const int groups = p.D / 16, jb = half * (groups / 2), je = half ? groups : groups / 2;
+        const uint4* src = reinterpret_cast<const uint4*>(p.queries + (size_t)min(q, p.Q - 1) * p.D);
+        for (int j = jb; j < je; ++j) {
           uint4 a = __ldg(src + 2 * j), b = __ldg(src + 2 * j + 1);
           u32 r[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
           if (!valid) {
@@ -269,51 +313,43 @@ __global__ void __launch_bounds__(NT, 1) dense_kernel(const __grid_constant__ CU
         }
         tmem_wait_st();
         tc_fence_before();
-        mbar_arrive(&ctl->a_ready);
+        mbar_arrive(a_aready);
         cur_m = m;
         tau = (valid && p.mode == MODE_FILTER) ? __ldg(p.tau + q) : INFINITY;
       }
       for (int t = t0; t < t1; ++t) {
-        mbar_wait(&ctl->tmem_full[acc], acc_phase);
+        mbar_wait(a_tfull + 8 * acc, acc_phase);
         tc_fence_after();
-        u32 v0[32], v1[32];
-        const u32 taddr = tmem_base + lane_base + A_COLS + acc * BN;
-        tmem_ld32(taddr, v0);
-        tmem_ld32(taddr + 32, v1);
+        u32 v[32];
+        tmem_ld32(tmem_base + lane_base + A_COLS + acc * BN + half * 32, v);
         tmem_wait_ld();
         tc_fence_before();
-        mbar_arrive(&ctl->tmem_empty[acc]);        // accumulator stage is free again
+        mbar_arrive(a_tempty + 8 * acc);        // accumulator stage is free again
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
 
-        const int doc0 = t * p.tile_step * BN;
+        const int doc0 = t * p.tile_step * BN + half * 32;
         if (p.mode == MODE_FILTER) {
-          if (q < p.Q) {
-            const int nvalid = min(BN, p.N - doc0);
+          const int nvalid = p.N - doc0;        // >= 32 except in the last tile
 #pragma unroll
-            for (int j = 0; j < 64; ++j) {
-              const float s = __uint_as_float(j < 32 ? v0[j & 31] : v1[j & 31]);
-              if (s >= tau && j < nvalid) {
-                const int pos = atomicAdd(p.cand_cnt + q, 1);
-                if (pos < p.cand_cap) {
-                  p.cand_score[(size_t)q * p.cand_cap + pos] = s;
-                  p.cand_id[(size_t)q * p.cand_cap + pos] = doc0 + j;
-                }
+          for (int j = 0; j < 32; ++j) {
+            if (__uint_as_float(v[j]) >= tau && j < nvalid) {
+              stage[n_staged * EPI_THREADS + et] = make_uint2(v[j], (u32)(doc0 + j));
+              if (++n_staged == STAGE_N) {
+                flush_stage(p.cand_score, p.cand_id, p.cand_cnt, p.cand_cap, stage, et, q, STAGE_N);
+                n_staged = 0;
               }
             }
           }
         } else {
-          float4* dst = reinterpret_cast<float4*>(p.store + (size_t)(m * BM + row) * p.store_ld + (size_t)t * BN);
+          float4* dst = reinterpret_cast<float4*>(p.store + (size_t)(m * BM + row) * p.store_ld + (size_t)t * BN + half * 32);
 #pragma unroll
           for (int j = 0; j < 8; ++j)
-            dst[j] = make_float4(__uint_as_float(v0[4 * j]), __uint_as_float(v0[4 * j + 1]), __uint_as_float(v0[4 * j + 2]),
-                                 __uint_as_float(v0[4 * j + 3]));
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            dst[8 + j] = make_float4(__uint_as_float(v1[4 * j]), __uint_as_float(v1[4 * j + 1]), __uint_as_float(v1[4 * j + 2]),
-                                     __uint_as_float(v1[4 * j + 3]));
+            dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                                 __uint_as_float(v[4 * j + 3]));
         }
       }
     }
+    if (n_staged > 0) flush_stage(p.cand_score, p.cand_id, p.cand_cnt, p.cand_cap, stage, et, q, n_staged);
   }
 
   tc_fence_before();
@@ -336,11 +372,12 @@ __device__ __forceinline__ float unord_f32(u32 o) {
 }
 
 __global__ void __launch_bounds__(512) tau_kernel(const float* sample, long long ld, int n_vtiles, int tile_step, int N, int Q,
-                                                  int target, float* tau) {
+                                                  int target, float* tau, int only_nan) {
   __shared__ u32 hist[256];
   __shared__ u32 s_prefix, s_remaining;
   const int q = blockIdx.x;
   if (q >= Q) return;
+  if (only_nan && !isnan(tau[q])) return;
   const float* row = sample + (size_t)q * ld;
   const int n_cols = n_vtiles * BN;
   // number of valid sample docs (real doc index < N)
@@ -381,6 +418,74 @@ __global__ void __launch_bounds__(512) tau_kernel(const float* sample, long long
     remaining = s_remaining;
   }
   if (threadIdx.x == 0) tau[q] = unord_f32(prefix);
+}
+
+// descending bitonic sort of 512 floats in shared memory by 512 threads
+__device__ __forceinline__ void bitonic512_desc(float* v, int tid) {
+  for (int k = 2; k <= 512; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      const int ixj = tid ^ j;
+      if (ixj > tid) {
+        const float a = v[tid], b = v[ixj];
+        const bool desc = (tid & k) == 0;
+        if (desc ? (a < b) : (a > b)) { v[tid] = b; v[ixj] = a; }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// Fast path for small order statistics (jj <= 128): the jj-th largest of the per-thread maxima is a lower
+// bound L of the answer; the handful of elements >= L are collected and sorted exactly.  Falls back to
+// the radix select (tau_kernel) by writing NaN when the collection overflows (host never sees it: the
+// caller launches the radix kernel for rows still NaN).
+__global__ void __launch_bounds__(512) tau_kernel_small(const float* sample, long long ld, int n_vtiles, int tile_step, int N,
+                                                        int Q, int target, float* tau) {
+  __shared__ float buf[512];
+  __shared__ int s_cnt;
+  const int q = blockIdx.x, tid = threadIdx.x;
+  if (q >= Q) return;
+  const float* row = sample + (size_t)q * ld;
+  const int n_cols = n_vtiles * BN;
+  long long s_valid = 0;
+  for (int t = 0; t < n_vtiles; ++t) {
+    const long long d0 = (long long)t * tile_step * BN;
+    s_valid += max(0ll, min((long long)BN, (long long)N - d0));
+  }
+  long long jj = ((long long)target * s_valid + N - 1) / N;
+  if (jj < 1) jj = 1;
+  if (jj > s_valid) jj = s_valid;
+  float mx = -INFINITY;
+  for (int cidx = tid; cidx < n_cols; cidx += 512) {
+    const long long doc = (long long)(cidx / BN) * tile_step * BN + (cidx % BN);
+    if (doc < N) mx = fmaxf(mx, row[cidx]);
+  }
+  buf[tid] = mx;
+  if (tid == 0) s_cnt = 0;
+  __syncthreads();
+  bitonic512_desc(buf, tid);
+  const float L = buf[jj - 1];          // at least jj elements are >= L
+  __syncthreads();
+  for (int cidx = tid; cidx < n_cols; cidx += 512) {
+    const long long doc = (long long)(cidx / BN) * tile_step * BN + (cidx % BN);
+    if (doc < N) {
+      const float v = row[cidx];
+      if (v >= L) {
+        const int pos = atomicAdd(&s_cnt, 1);
+        if (pos < 512) buf[pos] = v;
+      }
+    }
+  }
+  __syncthreads();
+  const int c = s_cnt;
+  if (c > 512) {                        // heavy ties: let the radix kernel handle this row
+    if (tid == 0) tau[q] = __int_as_float(0x7fc00000);
+    return;
+  }
+  if (tid >= c) buf[tid] = -INFINITY;
+  __syncthreads();
+  bitonic512_desc(buf, tid);
+  if (tid == 0) tau[q] = buf[jj - 1];
 }
 
 __global__ void fill_kernel(float* p, int n, float v) {
@@ -618,7 +723,10 @@ extern "C" int qf_dense_topk(const void* queries_bf16, const void* corpus_bf16, 
     dense_kernel<<<grid_for(units), NT, DENSE_SMEM, st>>>(tmap, p);
     QF_CUDA_TRY(cudaGetLastError());
     const int target = k * 3 + 1000;
-    tau_kernel<<<Q, 512, 0, st>>>(p.store, p.store_ld, p.n_vtiles, p.tile_step, N, Q, target, tau);
+    const long long s_cols = (long long)p.n_vtiles * BN;
+    const bool small_j = ((long long)target * s_cols + N - 1) / N <= 128;
+    if (small_j) tau_kernel_small<<<Q, 512, 0, st>>>(p.store, p.store_ld, p.n_vtiles, p.tile_step, N, Q, target, tau);
+    tau_kernel<<<Q, 512, 0, st>>>(p.store, p.store_ld, p.n_vtiles, p.tile_step, N, Q, target, tau, small_j ? 1 : 0);
     QF_CUDA_TRY(cudaGetLastError());
   } else {
     fill_kernel<<<(Q + 255) / 256, 256, 0, st>>>(tau, Q, -INFINITY);
