@@ -123,6 +123,131 @@ def load_peaks():
     return 6650.0, 1590.0, "fallback"
 
 
+
+N_DENSE, D_DENSE, K_DENSE = 2_681_468, 768, 1000
+
+
+def synth_dense(Q, N, D, seed, device):
+    """Unit-normalised N(0,1) rows -> bf16, generated on the device in blocks."""
+    import torch
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    corpus = torch.empty((N, D), dtype=torch.bfloat16, device=device)
+    for s in range(0, N, 262144):
+        x = torch.randn((min(262144, N - s), D), generator=g, device=device)
+        corpus[s:s + x.shape[0]] = (x / x.norm(dim=1, keepdim=True)).to(torch.bfloat16)
+    x = torch.randn((Q, D), generator=g, device=device)
+    q32 = (x / x.norm(dim=1, keepdim=True)).contiguous()
+    return q32, corpus
+
+
+def dense_leg(args, dev, world, rank):
+    """BGE-shaped flat inner-product top-1000 (BASELINE configs[2]); corpus row-sharded when world > 1."""
+    import torch
+    import torch.distributed as dist
+    from qppfusion import _native as N_, ops
+    Q, D, k = Q_NQ, D_DENSE, K_DENSE
+    n_local = (N_DENSE + world - 1) // world
+    lo = rank * n_local
+    n_local = max(0, min(n_local, N_DENSE - lo))
+    q32, corpus = synth_dense(Q, n_local, D, 20250103 + rank, dev)
+    if world > 1:
+        dist.broadcast(q32, src=0)
+    qb = q32.to(torch.bfloat16)
+    stream = torch.cuda.current_stream(dev)
+    steps = max(3, min(args.steps, 10))
+
+    def step():
+        sc, ids, st = ops.dense_topk(qb, corpus, k, lo)
+        if world > 1:
+            gs = torch.empty((world, Q, k), dtype=torch.float32, device=dev)
+            gi = torch.empty((world, Q, k), dtype=torch.int32, device=dev)
+            dist.all_gather_into_tensor(gs, sc)
+            dist.all_gather_into_tensor(gi, ids)
+            sc, ids = ops.topk_merge(gs, gi)
+        return sc, ids, st
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    N_.profile_enable(True)
+    for _ in range(3):
+        sc, ids, st = step()
+    barrier()
+    status_bad = int((st != 0).sum().item())
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    main_ms = 0.0
+    e0.record(stream)
+    for _ in range(steps):
+        sc, ids, st = step()
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1) / steps
+    phases = {n: N_.profile_read(i) for i, n in enumerate(["sample", "tau", "main", "select"])}
+    N_.profile_enable(False)
+    main_ms = phases["main"]
+
+    # end to end: pinned fp32 queries -> H2D -> bf16 -> search -> D2H (ids, scores); the index stays resident
+    h_q = q32.cpu().pin_memory()
+    h_s = torch.empty((Q, k), dtype=torch.float32).pin_memory()
+    h_i = torch.empty((Q, k), dtype=torch.int32).pin_memory()
+
+    def e2e_step():
+        dq = h_q.to(dev, non_blocking=True).to(torch.bfloat16)
+        s_, i_, _ = ops.dense_topk(dq, corpus, k, lo)
+        if world > 1:
+            gs = torch.empty((world, Q, k), dtype=torch.float32, device=dev)
+            gi = torch.empty((world, Q, k), dtype=torch.int32, device=dev)
+            dist.all_gather_into_tensor(gs, s_)
+            dist.all_gather_into_tensor(gi, i_)
+            s_, i_ = ops.topk_merge(gs, gi)
+        h_s.copy_(s_, non_blocking=True)
+        h_i.copy_(i_, non_blocking=True)
+
+    e2e_step()
+    barrier()
+    e0.record(stream)
+    for _ in range(steps):
+        e2e_step()
+    e1.record(stream)
+    barrier()
+    e2e_ms = e0.elapsed_time(e1) / steps
+
+    # parity spot check on the device copy (torch fp32 matmul as an independent reference; world == 1 only)
+    parity = None
+    if world == 1:
+        nq = 8
+        ref = q32[:nq] @ corpus.float().T if n_local <= 3_000_000 else None
+        if ref is not None:
+            rs, ri = torch.topk(ref, k, dim=1)
+            overlap = sum(len(set(ri[i].tolist()) & set(ids[i].tolist())) for i in range(nq)) / (nq * k)
+            parity = {"queries_checked": nq, "top1000_overlap_vs_fp32": overlap,
+                      "max_abs_score_diff_vs_fp32": float((rs - sc[:nq]).abs().max().item())}
+    t = torch.tensor([ms, e2e_ms, main_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, e2e_ms, main_ms = t.tolist()
+    _hbm, tf_peak, which = load_peaks()
+    flops_main = 2.0 * Q * n_local * D           # per GPU, main pass
+    ach = flops_main / (main_ms * 1e-3) / 1e12
+    return {"metric": "BGE top-1000 QPS", "value": Q / (ms * 1e-3), "unit": "queries/s", "ms_per_step": ms,
+            "scaling": "strong" if world > 1 else "n/a",
+            "config": {"workload": "BGE-base-shaped flat IP top-1000 (BASELINE configs[2])", "queries": Q,
+                       "docs": N_DENSE, "docs_per_gpu": n_local, "dim": D, "k": k, "dtype": "bf16 in, fp32 accumulate",
+                       "sharding": f"corpus rows x{world}" + (", all_gather + qf_topk_merge" if world > 1 else "")},
+            "kernel_ms": phases,
+            "roofline": {"kernel": "dense_kernel (tcgen05 main pass)", "bound": "tensor", "achieved": ach, "peak": tf_peak,
+                         "unit": "TFLOP/s", "frac": ach / tf_peak, "peak_source": which,
+                         "algorithmic_flops": flops_main, "traffic": None},
+            "whole_call_tflops": 2.0 * Q * N_DENSE * D / (ms * 1e-3) / 1e12,
+            "e2e": {"value": Q / (e2e_ms * 1e-3), "unit": "queries/s", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": Q * D * 4, "d2h_bytes_per_step": Q * k * 8},
+            "threshold_failures": status_bad, "parity": parity, "gpu_launches": 5 * steps}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -214,6 +339,10 @@ def run_ours(args):
     h2d = sum(x.numel() * x.element_size() for x in h_in)
     d2h = sum(x.numel() * x.element_size() for x in h_out)
 
+    del sets, h_in, h_out
+    torch.cuda.empty_cache()
+    dense = None if args.no_dense else dense_leg(args, dev, world, rank)
+
     times = torch.tensor([ms_total, e2e_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
@@ -239,8 +368,9 @@ def run_ours(args):
                          "algorithmic_bytes": alg_bytes, "traffic": None},
             "e2e": {"value": world * Q / (e2e_ms * 1e-3), "unit": "fused queries/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": 6 * args.steps,
+            "gpu_launches": 6 * args.steps + (dense["gpu_launches"] if dense else 0),
             "clocks": clocks,
+            "dense": dense,
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(seconds=12.0)
@@ -355,6 +485,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-dense", action="store_true", help="skip the BGE dense-retrieval leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

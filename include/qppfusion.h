@@ -48,6 +48,20 @@ QF_API int         qf_abi_version(void);
 /* 0 if `device` is a compute-capability-10.x GPU this library can run on. */
 QF_API int         qf_device_check(int device);
 
+/*
+ * Optional device-side timing of the kernels a multi-kernel entry point launches (used by bench.py for
+ * the per-kernel roofline): when enabled, CUDA events are recorded on the caller's stream around the
+ * named phase; qf_profile_read synchronises on the closing event and returns the elapsed milliseconds
+ * of the most recent call.
+ */
+#define QF_PROF_DENSE_SAMPLE 0   /* strided-sample scoring pass of qf_dense_topk            */
+#define QF_PROF_DENSE_TAU    1   /* per-query threshold selection                           */
+#define QF_PROF_DENSE_MAIN   2   /* tcgen05 GEMM + fused threshold filter over the corpus   */
+#define QF_PROF_DENSE_SELECT 3   /* per-query candidate ranking                             */
+#define QF_PROF_PHASES       4
+QF_API int qf_profile_enable(int on);
+QF_API int qf_profile_read(int phase, float* ms);
+
 /* ------------------------------------------------------------------------------------------------
  * Rank fusion  --  replaces ranx.fuse (src/fusion.py:182,201,226) and the weighted_* Python loops
  *                  (src/fusion.py:266-278, 309-327, 361-377)

@@ -25,6 +25,24 @@ int check_device() {
   return qf_device_check(dev);
 }
 
+static bool g_prof_on = false;
+static cudaEvent_t g_prof_ev[QF_PROF_PHASES][2];
+static bool g_prof_init = false, g_prof_rec[QF_PROF_PHASES];
+
+void prof_mark(int phase, int which, cudaStream_t st) {
+  if (!g_prof_on || phase < 0 || phase >= QF_PROF_PHASES) return;
+  if (!g_prof_init) {
+    for (int i = 0; i < QF_PROF_PHASES; ++i) {
+      cudaEventCreate(&g_prof_ev[i][0]);
+      cudaEventCreate(&g_prof_ev[i][1]);
+      g_prof_rec[i] = false;
+    }
+    g_prof_init = true;
+  }
+  cudaEventRecord(g_prof_ev[phase][which], st);
+  if (which == 1) g_prof_rec[phase] = true;
+}
+
 int sm_count() {
   int dev = 0, n = 148;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
@@ -55,5 +73,18 @@ extern "C" int qf_device_check(int device) {
                   major, minor);
     return QF_E_NO_DEVICE;
   }
+  return QF_OK;
+}
+
+extern "C" int qf_profile_enable(int on) {
+  qf::g_prof_on = on != 0;
+  return QF_OK;
+}
+
+extern "C" int qf_profile_read(int phase, float* ms) {
+  QF_REQUIRE(ms != nullptr && phase >= 0 && phase < QF_PROF_PHASES, QF_E_INVALID, "qf_profile_read: bad argument");
+  QF_REQUIRE(qf::g_prof_init && qf::g_prof_rec[phase], QF_E_INVALID, "qf_profile_read: phase %d was not recorded", phase);
+  QF_CUDA_TRY(cudaEventSynchronize(qf::g_prof_ev[phase][1]));
+  QF_CUDA_TRY(cudaEventElapsedTime(ms, qf::g_prof_ev[phase][0], qf::g_prof_ev[phase][1]));
   return QF_OK;
 }

@@ -720,13 +720,17 @@ extern "C" int qf_dense_topk(const void* queries_bf16, const void* corpus_bf16, 
     p.tile_step = T / w.n_sample_tiles;
     p.chunk_tiles = 16;
     const int units = ((p.n_vtiles + p.chunk_tiles - 1) / p.chunk_tiles) * n_mtiles;
+    qf::prof_mark(QF_PROF_DENSE_SAMPLE, 0, st);
     dense_kernel<<<grid_for(units), NT, DENSE_SMEM, st>>>(tmap, p);
+    qf::prof_mark(QF_PROF_DENSE_SAMPLE, 1, st);
     QF_CUDA_TRY(cudaGetLastError());
     const int target = k * 3 + 1000;
     const long long s_cols = (long long)p.n_vtiles * BN;
     const bool small_j = ((long long)target * s_cols + N - 1) / N <= 128;
+    qf::prof_mark(QF_PROF_DENSE_TAU, 0, st);
     if (small_j) tau_kernel_small<<<Q, 512, 0, st>>>(p.store, p.store_ld, p.n_vtiles, p.tile_step, N, Q, target, tau);
     tau_kernel<<<Q, 512, 0, st>>>(p.store, p.store_ld, p.n_vtiles, p.tile_step, N, Q, target, tau, small_j ? 1 : 0);
+    qf::prof_mark(QF_PROF_DENSE_TAU, 1, st);
     QF_CUDA_TRY(cudaGetLastError());
   } else {
     fill_kernel<<<(Q + 255) / 256, 256, 0, st>>>(tau, Q, -INFINITY);
@@ -738,7 +742,9 @@ extern "C" int qf_dense_topk(const void* queries_bf16, const void* corpus_bf16, 
   p.chunk_tiles = T >= 4096 ? 256 : (T >= 256 ? 32 : 4);
   {
     const int units = ((p.n_vtiles + p.chunk_tiles - 1) / p.chunk_tiles) * n_mtiles;
+    qf::prof_mark(QF_PROF_DENSE_MAIN, 0, st);
     dense_kernel<<<grid_for(units), NT, DENSE_SMEM, st>>>(tmap, p);
+    qf::prof_mark(QF_PROF_DENSE_MAIN, 1, st);
     QF_CUDA_TRY(cudaGetLastError());
   }
   SelectParams sp{};
@@ -746,7 +752,9 @@ extern "C" int qf_dense_topk(const void* queries_bf16, const void* corpus_bf16, 
   sp.q_stride = SEL_CAP; sp.seg_stride = 0; sp.nseg = 1; sp.seg_len = SEL_CAP;
   sp.Q = Q; sp.k = k; sp.N_total = N; sp.id_offset = id_offset;
   sp.out_scores = out_scores; sp.out_ids = out_ids; sp.out_status = out_status;
+  qf::prof_mark(QF_PROF_DENSE_SELECT, 0, st);
   select_kernel<<<Q < sms ? Q : sms, SEL_NT, SEL_SMEM, st>>>(sp);
+  qf::prof_mark(QF_PROF_DENSE_SELECT, 1, st);
   QF_CUDA_TRY(cudaGetLastError());
   return QF_OK;
 }

@@ -46,6 +46,8 @@ PROTOTYPES = {
     "qf_last_error": (ctypes.c_char_p, []),
     "qf_abi_version": (_i, []),
     "qf_device_check": (_i, [_i]),
+    "qf_profile_enable": (_i, [_i]),
+    "qf_profile_read": (_i, [_i, ctypes.POINTER(ctypes.c_float)]),
     "qf_fuse_max_postings": (_i, []),
     "qf_fuse": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _d, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "qf_qpp_stats": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
@@ -107,3 +109,16 @@ def require_cuda(*tensors: Optional[torch.Tensor]) -> torch.device:
     if dev is None:
         raise RuntimeError("no tensor arguments")
     return dev
+
+
+PROF_DENSE_SAMPLE, PROF_DENSE_TAU, PROF_DENSE_MAIN, PROF_DENSE_SELECT = 0, 1, 2, 3
+
+
+def profile_enable(on: bool) -> None:
+    check(lib().qf_profile_enable(1 if on else 0))
+
+
+def profile_read(phase: int) -> float:
+    ms = ctypes.c_float(0.0)
+    check(lib().qf_profile_read(phase, ctypes.byref(ms)))
+    return float(ms.value)
