@@ -179,12 +179,16 @@ def dense_leg(args, dev, world, rank):
     barrier()
     status_bad = int((st != 0).sum().item())
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    main_ms = 0.0
+    sampler = ClockSampler(dev.index)
+    if rank == 0:
+        sampler.start()
+    barrier()
     e0.record(stream)
     for _ in range(steps):
         sc, ids, st = step()
     e1.record(stream)
     barrier()
+    clocks = sampler.stop() if rank == 0 else None
     ms = e0.elapsed_time(e1) / steps
     phases = {n: N_.profile_read(i) for i, n in enumerate(["sample", "tau", "main", "select"])}
     N_.profile_enable(False)
@@ -245,7 +249,7 @@ def dense_leg(args, dev, world, rank):
             "whole_call_tflops": 2.0 * Q * N_DENSE * D / (ms * 1e-3) / 1e12,
             "e2e": {"value": Q / (e2e_ms * 1e-3), "unit": "queries/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": Q * D * 4, "d2h_bytes_per_step": Q * k * 8},
-            "threshold_failures": status_bad, "parity": parity, "gpu_launches": 5 * steps}
+            "threshold_failures": status_bad, "parity": parity, "gpu_launches": 5 * steps, "clocks": clocks}
 
 
 def run_ours(args):
