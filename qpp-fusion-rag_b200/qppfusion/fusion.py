@@ -1,0 +1,339 @@
+#!/usr/bin/env python3
+"""
+Rank fusion for multi-retriever RAG -- B200-native drop-in for the reference's src/fusion.py.
+
+Same entry points, argument meaning, return types, printed tags and error behaviour as the reference
+(PoisedDok/QPP-Fusion-RAG src/fusion.py), with the arithmetic moved from ranx/numba and Python dict loops
+into one CUDA kernel (qf_fuse, csrc/qf_fuse.cu):
+
+    Unweighted (reference: via ranx)        CombSUM   sum_i S_i(d,q)            combsum(runs)
+                                            CombMNZ   |{i: d in R_i}| x sum     combmnz(runs)
+                                            RRF       sum_i 1/(k + rank_i)      rrf(runs, k)
+    QPP-weighted (reference: Python loops)  W-CombSUM / W-CombMNZ / W-RRF       weighted_*(runs, qpp_data, qpp_index)
+    Learned                                 W-CombSUM with model-predicted weights   learned_fusion(...)
+
+STRICT, like the reference ("No fallbacks", src/fusion.py:24): no CUDA library or no sm_100 GPU -> the call
+raises; there is no CPU path in this package.
+"""
+from __future__ import annotations
+
+import os
+import pickle
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+import pandas as pd
+import torch
+
+from . import _native as N
+from . import ops
+from .config import config
+from .packing import PackedRuns, pack_runs, unpack_fused
+
+Fused = Dict[str, List[Tuple[str, float]]]
+
+
+# =============================================================================
+# Data loading
+# =============================================================================
+
+def _run_files(res_path: str, use_normalized: bool):
+    suffix = ".norm.res" if use_normalized else ".res"
+    files = [f for f in os.listdir(res_path) if f.endswith(suffix)]
+    if not use_normalized:
+        files = [f for f in files if not f.endswith(".norm.res")]
+    if not files:
+        raise FileNotFoundError(f"No {suffix} files found in {res_path}")
+    # The reference keeps os.listdir order (src/fusion.py:60), i.e. filesystem dependent.  Ranker order
+    # decides float64 accumulation order and the tie-break, so this build fixes it: sorted by name.
+    return sorted(files), suffix
+
+
+def load_runs(res_path: str, use_normalized: bool = True) -> Dict[str, pd.DataFrame]:
+    """{retriever_name: DataFrame[qid, iter, docno, rank, score, runid]} (reference src/fusion.py:46-76)."""
+    files, suffix = _run_files(res_path, use_normalized)
+    runs = {}
+    for f in files:
+        ranker = f.replace(suffix, "")
+        df = pd.read_csv(os.path.join(res_path, f), sep=r"\s+", names=["qid", "iter", "docno", "rank", "score", "runid"],
+                         dtype={"qid": str, "docno": str})
+        df["qid"] = df["qid"].astype(str)
+        runs[ranker] = df
+    return runs
+
+
+def load_runs_as_ranx(res_path: str, use_normalized: bool = True) -> Dict[str, pd.DataFrame]:
+    """The reference returns ranx.Run objects (src/fusion.py:79-103); ranx is not part of this build, the
+    same data is returned as DataFrames sorted the way ranx.Run sorts (score descending per query)."""
+    runs = load_runs(res_path, use_normalized)
+    return {k: df.sort_values(["qid", "score"], ascending=[True, False], kind="stable").reset_index(drop=True)
+            for k, df in runs.items()}
+
+
+def load_qpp_scores(qpp_path: str) -> Dict[str, Dict[str, List[float]]]:
+    """{qid: {retriever: [13 qpp scores]}} (reference src/fusion.py:106-113)."""
+    from .data_utils import load_qpp_scores as _load
+    return _load(qpp_path)
+
+
+def get_qpp_weight(qid: str, ranker: str, qpp_data: Dict[str, Dict[str, List[float]]], qpp_index: int = None,
+                   fusion_mode: bool = False) -> float:
+    """Weight of one (query, ranker) pair; KeyError / IndexError exactly as the reference (src/fusion.py:116-158)."""
+    if qpp_index is None:
+        qpp_index = config.qpp.default_index
+    if qid not in qpp_data:
+        raise KeyError(f"QPP data missing for query '{qid}'. Run QPP computation first.")
+    if ranker not in qpp_data[qid]:
+        raise KeyError(f"QPP data missing for ranker '{ranker}' on query '{qid}'. Available: {list(qpp_data[qid].keys())}")
+    scores = qpp_data[qid][ranker]
+    if fusion_mode or qpp_index == -1:
+        return sum(scores) / len(scores)
+    if qpp_index >= len(scores):
+        raise IndexError(f"QPP index {qpp_index} out of range. Available: 0-{len(scores)-1}")
+    return scores[qpp_index]
+
+
+def get_qpp_index(model_name: str) -> int:
+    """Resolve QPP model name to index; -1 for 'fusion' (reference src/fusion.py:161-163)."""
+    return config.get_qpp_index(model_name)
+
+
+# =============================================================================
+# Device plumbing
+# =============================================================================
+
+def _device() -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError("qppfusion.fusion needs a CUDA (sm_100) device: there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _weights_matrix(packed: PackedRuns, qpp_data, qpp_index: int) -> np.ndarray:
+    """float64 [Q, R]; the weight is looked up for EVERY (qid, ranker), also when that ranker has no rows for
+    the qid, so a missing entry raises KeyError exactly as the reference does (src/fusion.py:270-272)."""
+    fusion_mode = (qpp_index == -1)
+    w = np.empty((len(packed.qids), len(packed.rankers)), dtype=np.float64)
+    for qi, qid in enumerate(packed.qids):
+        for ri, ranker in enumerate(packed.rankers):
+            w[qi, ri] = get_qpp_weight(qid, ranker, qpp_data, qpp_index, fusion_mode)
+    return w
+
+
+def fuse_packed(packed: PackedRuns, method: int, weights: Optional[np.ndarray] = None, norm: int = N.NORM_NONE,
+                rrf_k: float = 60.0, flags: int = 0, want_counts: bool = False, want_pos: bool = False) -> ops.FuseOut:
+    """Array-level entry point: PackedRuns -> kernel outputs on the device (no Python objects built)."""
+    dev = _device()
+    t = lambda a: None if a is None else torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    out = ops.fuse(t(packed.doc_ids), t(packed.scores), t(packed.lens), t(weights), t(packed.ranks), method, norm,
+                   rrf_k, flags, want_counts, want_pos)
+    status = out.status.cpu().numpy()
+    if (status & N.QSTAT_BAD_LEN).any():
+        raise ValueError("qf_fuse: invalid list length")
+    if (status & N.QSTAT_UNSORTED).any():
+        bad = [packed.qids[i] for i in np.flatnonzero(status & N.QSTAT_UNSORTED)[:5]]
+        raise ValueError(f"qf_fuse: run lists violate the ordering contract for queries {bad}")
+    return out
+
+
+def _to_dict(packed: PackedRuns, out: ops.FuseOut) -> Fused:
+    return unpack_fused(packed, out.ids.cpu().numpy(), out.scores.cpu().numpy(), out.lens.cpu().numpy())
+
+
+# =============================================================================
+# Unweighted fusion (reference: ranx.fuse with its default norm="min-max")
+# =============================================================================
+
+def _ranx_fuse(runs: Dict[str, pd.DataFrame], method: int, rrf_k: float = 60.0) -> Fused:
+    packed = pack_runs(runs, mode="ranx")
+    flags = N.FLAG_REQUIRE_SORTED
+    if method == N.METHOD_MNZ and not config.fusion.ranx_mnz_counts_zero_scores:
+        flags |= N.FLAG_MNZ_SKIP_ZERO
+    norm = N.NORM_NONE if method == N.METHOD_RRF else N.NORM_MINMAX
+    out = fuse_packed(packed, method, None, norm, rrf_k, flags)
+    return _to_dict(packed, out)      # ranked: score descending (as _ranx_to_dict, src/fusion.py:469-477)
+
+
+def combsum(runs: Dict[str, pd.DataFrame]) -> Fused:
+    """CombSUM(d,q) = sum_i S_i(d,q) over min-max normalised runs (reference src/fusion.py:170-186)."""
+    print("[fusion] Running CombSUM (qf_fuse)...")
+    result = _ranx_fuse(runs, N.METHOD_SUM)
+    print(f"[fusion] CombSUM done: {len(result)} queries")
+    return result
+
+
+def combmnz(runs: Dict[str, pd.DataFrame]) -> Fused:
+    """CombMNZ(d,q) = |{i: d in R_i}| x sum_i S_i(d,q) (reference src/fusion.py:189-205)."""
+    print("[fusion] Running CombMNZ (qf_fuse)...")
+    result = _ranx_fuse(runs, N.METHOD_MNZ)
+    print(f"[fusion] CombMNZ done: {len(result)} queries")
+    return result
+
+
+def rrf(runs: Dict[str, pd.DataFrame], k: int = None) -> Fused:
+    """RRF(d,q) = sum_i 1/(k + rank_i(d,q)), rank = position in the score-sorted run (reference src/fusion.py:208-230)."""
+    k = k if k is not None else config.fusion.rrf_k
+    print("[fusion] Running RRF (qf_fuse)...")
+    result = _ranx_fuse(runs, N.METHOD_RRF, float(k))
+    print(f"[fusion] RRF done: {len(result)} queries")
+    return result
+
+
+# =============================================================================
+# QPP-weighted fusion (reference: Python dict loops over iterrows)
+# =============================================================================
+
+def _weighted(runs, qpp_data, qpp_index, method: int, rrf_k: float = 60.0) -> Fused:
+    packed = pack_runs(runs, mode="weighted_rrf" if method == N.METHOD_RRF else "weighted",
+                       need_ranks=(method == N.METHOD_RRF))
+    w = _weights_matrix(packed, qpp_data, qpp_index)
+    # the reference returns each query's list in dict-insertion (first-seen) order, UNSORTED
+    # (src/fusion.py:277-278); ranking happens in write_runfile
+    out = fuse_packed(packed, method, w, N.NORM_NONE, rrf_k, N.FLAG_UNRANKED_OUTPUT)
+    return _to_dict(packed, out)
+
+
+def weighted_combsum(runs: Dict[str, pd.DataFrame], qpp_data, qpp_index: int = None) -> Fused:
+    """W-CombSUM(d,q) = sum_i w_i(q) x S_i(d,q) (reference src/fusion.py:237-281)."""
+    qpp_index = qpp_index if qpp_index is not None else config.qpp.default_index
+    print(f"[fusion] Running W-CombSUM (QPP index={qpp_index})...")
+    fused = _weighted(runs, qpp_data, qpp_index, N.METHOD_SUM)
+    print(f"[fusion] W-CombSUM done: {len(fused)} queries")
+    return fused
+
+
+def weighted_combmnz(runs: Dict[str, pd.DataFrame], qpp_data, qpp_index: int = None) -> Fused:
+    """W-CombMNZ(d,q) = |{i}| x sum_i w_i(q) x S_i(d,q) (reference src/fusion.py:284-330)."""
+    qpp_index = qpp_index if qpp_index is not None else config.qpp.default_index
+    print(f"[fusion] Running W-CombMNZ (QPP index={qpp_index})...")
+    fused = _weighted(runs, qpp_data, qpp_index, N.METHOD_MNZ)
+    print(f"[fusion] W-CombMNZ done: {len(fused)} queries")
+    return fused
+
+
+def weighted_rrf(runs: Dict[str, pd.DataFrame], qpp_data, qpp_index: int = None, k: int = None) -> Fused:
+    """W-RRF(d,q) = sum_i w_i(q) / (k + rank_i(d,q)) with the FILE's rank column (reference src/fusion.py:333-380)."""
+    qpp_index = qpp_index if qpp_index is not None else config.qpp.default_index
+    k = k if k is not None else config.fusion.rrf_k
+    print(f"[fusion] Running W-RRF (QPP index={qpp_index})...")
+    fused = _weighted(runs, qpp_data, qpp_index, N.METHOD_RRF, float(k))
+    print(f"[fusion] W-RRF done: {len(fused)} queries")
+    return fused
+
+
+# =============================================================================
+# Learned fusion (model-predicted weights)
+# =============================================================================
+
+def learned_fusion(runs: Dict[str, pd.DataFrame], qpp_data, model_path: str,
+                   retrievers: Optional[List[str]] = None) -> Fused:
+    """W-CombSUM with per-query weights predicted by a pickled model (reference src/fusion.py:387-448).
+
+    The weight matrix build follows the reference (feature vector = the first n_qpp QPP values of each
+    retriever in model order, zeros when missing; weight 1/R for a ranker the model does not know, :435);
+    the accumulation runs in qf_fuse.  The reference sums with pandas groupby(["qid","docno"]).sum() and
+    returns documents in docno order; this returns the same (docno, score) sets -- scores equal within
+    float64 summation-order error (<= 1e-15 relative), list order = docno ascending like the reference.
+    """
+    print(f"[fusion] Running learned fusion from {model_path}...")
+    with open(model_path, "rb") as f:
+        model_data = pickle.load(f)
+    model = model_data.get("model")
+    retrievers = retrievers or model_data.get("retrievers", sorted(runs.keys()))
+    n_qpp = model_data.get("n_qpp", config.qpp.n_methods)
+
+    packed = pack_runs(runs, mode="weighted")
+    n_ret = len(retrievers)
+    X = np.zeros((len(packed.qids), n_qpp * n_ret))
+    for i, qid in enumerate(packed.qids):
+        for j, retriever in enumerate(retrievers):
+            if qid in qpp_data and retriever in qpp_data[qid]:
+                X[i, j * n_qpp:(j + 1) * n_qpp] = qpp_data[qid][retriever][:n_qpp]
+    pred = np.asarray(model.predict(X), dtype=np.float64)
+    w = np.full((len(packed.qids), len(packed.rankers)), 1.0 / n_ret, dtype=np.float64)
+    for ri, ranker in enumerate(packed.rankers):
+        if ranker in retrievers:
+            w[:, ri] = pred[:, retrievers.index(ranker)]
+    out = fuse_packed(packed, N.METHOD_SUM, w, N.NORM_NONE, 60.0, N.FLAG_UNRANKED_OUTPUT)
+    fused = _to_dict(packed, out)
+    fused = {qid: sorted(lst, key=lambda x: x[0]) for qid, lst in fused.items()}
+    print(f"[fusion] Learned fusion done: {len(fused)} queries")
+    return fused
+
+
+# =============================================================================
+# Output
+# =============================================================================
+
+def _qid_sort_key(x: str):
+    return int(x.replace("test", "")) if x.startswith("test") else x     # reference src/fusion.py:487
+
+
+def write_runfile(fused: Fused, output_path: str, tag: str = "fusion"):
+    """TREC run file: queries in the reference's order, documents by score descending with ties in list
+    order (Python's stable sort, reference src/fusion.py:480-492), "{qid} Q0 {docid} {rank} {score:.6f} {tag}"."""
+    with open(output_path, "w") as fout:
+        for qid in sorted(fused.keys(), key=_qid_sort_key):
+            lst = fused[qid]
+            if not lst:
+                continue
+            scores = np.fromiter((s for _, s in lst), dtype=np.float64, count=len(lst))
+            order = np.argsort(-scores, kind="stable")      # == sorted(key=score, reverse=True): stable
+            fout.write("".join(f"{qid} Q0 {lst[i][0]} {rank} {lst[i][1]:.6f} {tag}\n"
+                               for rank, i in enumerate(order.tolist(), start=1)))
+    print(f"Wrote fused run to {output_path}")
+
+
+def run_fusion(method: str, runs_dir: str, qpp_dir: Optional[str] = None, qpp_model: str = None,
+               model_path: Optional[str] = None, output_path: Optional[str] = None, rrf_k: int = None) -> Fused:
+    """Dispatcher with the reference's method names, aliases, tags and errors (src/fusion.py:495-579)."""
+    qpp_model = qpp_model or config.qpp.default_method
+    rrf_k = rrf_k if rrf_k is not None else config.fusion.rrf_k
+    runs = load_runs(runs_dir, use_normalized=True)
+    print(f"Loaded {len(runs)} rankers: {list(runs.keys())}")
+    method = method.lower()
+    if method == "combsum":
+        fused, tag = combsum(runs), "combsum"
+    elif method == "combmnz":
+        fused, tag = combmnz(runs), "combmnz"
+    elif method == "rrf":
+        fused, tag = rrf(runs, k=rrf_k), f"rrf-k{rrf_k}"
+    elif method in ["wcombsum", "w-combsum", "wcombmnz", "w-combmnz", "wrrf", "w-rrf"]:
+        if not qpp_dir:
+            raise ValueError("--qpp_dir required for weighted methods")
+        qpp_data = load_qpp_scores(qpp_dir)
+        qpp_index = get_qpp_index(qpp_model)
+        base = method.replace("-", "")
+        if base == "wcombsum":
+            fused = weighted_combsum(runs, qpp_data, qpp_index)
+        elif base == "wcombmnz":
+            fused = weighted_combmnz(runs, qpp_data, qpp_index)
+        else:
+            fused = weighted_rrf(runs, qpp_data, qpp_index, k=rrf_k)
+        tag = f"{base}-{qpp_model.lower()}"
+    elif method == "learned":
+        if not model_path:
+            raise ValueError("--model_path required for learned fusion")
+        if not qpp_dir:
+            raise ValueError("--qpp_dir required for learned fusion")
+        fused, tag = learned_fusion(runs, load_qpp_scores(qpp_dir), model_path), "learned"
+    else:
+        raise ValueError(f"Unknown method '{method}'. Valid: {config.fusion.methods}")
+    if output_path:
+        write_runfile(fused, output_path, tag)
+    return fused
+
+
+if __name__ == "__main__":
+    import argparse
+
+    parser = argparse.ArgumentParser(description="Fusion Methods for Multi-Retriever RAG (B200-native)")
+    parser.add_argument("--method", required=True, choices=config.fusion.methods, help="Fusion method")
+    parser.add_argument("--runs_dir", required=True, help="Directory with .norm.res files")
+    parser.add_argument("--qpp_dir", default=None, help="Directory with .qpp files")
+    parser.add_argument("--qpp_model", default=config.qpp.default_method, help="QPP model for weighting")
+    parser.add_argument("--model_path", default=None, help="Path to learned model")
+    parser.add_argument("--output", required=True, help="Output TREC run file")
+    parser.add_argument("--rrf_k", type=int, default=config.fusion.rrf_k, help="RRF k constant")
+    a = parser.parse_args()
+    run_fusion(method=a.method, runs_dir=a.runs_dir, qpp_dir=a.qpp_dir, qpp_model=a.qpp_model,
+               model_path=a.model_path, output_path=a.output, rrf_k=a.rrf_k)

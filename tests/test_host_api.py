@@ -1,0 +1,134 @@
+"""CPU-side tests of the host mirror of the reference API: packing, loaders, writers, error behaviour."""
+import gzip
+import hashlib
+import json
+import os
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from oracle import fusion_oracle as fo
+from qppfusion import fusion
+from qppfusion.config import ConfigError, config
+from qppfusion.data_utils import load_qpp_scores, load_run_as_dict, load_run_file
+from qppfusion.packing import pack_runs
+from qppfusion.retrievers.base import BaseRetriever, RetrieverResult
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "fusion_weighted.json.gz")
+
+
+def gold_frames(case, rankers):
+    frames = {}
+    for rk in rankers:
+        df = pd.DataFrame(case["rows"][rk], columns=["qid", "iter", "docno", "rank", "score", "runid"])
+        frames[rk] = df.astype({"qid": str, "docno": str, "rank": "int64", "score": "float64"})
+    return frames
+
+
+def packed_to_lists(p):
+    Q, R, K = p.shape
+    lists = []
+    for q in range(Q):
+        per_r = []
+        for r in range(R):
+            n = p.lens[q, r]
+            sc = p.scores[q, r, :n]
+            sc = sc / 1e6 if sc.dtype == np.int32 else sc
+            rk = p.ranks[q, r, :n] if p.ranks is not None else np.arange(1, n + 1)
+            per_r.append([(p.docnos[p.doc_ids[q, r, i]], float(sc[i]), int(rk[i])) for i in range(n)])
+        lists.append(per_r)
+    return lists
+
+
+def test_pack_runs_reproduces_reference_visiting_order():
+    with gzip.open(GOLD, "rt") as f:
+        gold = json.load(f)
+    case = gold["cases"][0]                      # adversarial: ragged, missing ranker, duplicate docno, shuffled rows
+    frames = gold_frames(case, gold["rankers"])
+    for mode, method in (("weighted", fo.SUM), ("weighted", fo.MNZ), ("weighted_rrf", fo.RRF)):
+        p = pack_runs(frames, mode=mode, need_ranks=True)
+        assert p.scores.dtype == np.int32          # 6-decimal scores -> micro-units
+        assert p.qids == sorted(p.qids)
+        lists = packed_to_lists(p)
+        key = {fo.SUM: "wcombsum@5", fo.MNZ: "wcombmnz@5", fo.RRF: "wrrf@5"}[method]
+        for qi, qid in enumerate(p.qids):
+            w = [case["qpp"][qid][rk][5] for rk in p.rankers]
+            docs, scores, _ = fo.fuse_weighted_query(lists[qi], w, method, 60)
+            ref = [(d, float(s)) for d, s in case["results"][key]["fused"].get(qid, [])]
+            assert list(zip(docs, scores)) == ref, (mode, qid)
+
+
+def test_pack_runs_ranx_mode_dict_semantics_and_f64_fallback():
+    df = pd.DataFrame({"qid": ["1"] * 4 + ["2"], "iter": "Q0", "docno": ["a", "b", "a", "c", "z"],
+                       "rank": [1, 2, 3, 4, 1], "score": [0.2, 0.9, 0.5, 0.9, 1.0 / 3.0], "runid": "x"})
+    p = pack_runs({"A": df}, mode="ranx")
+    assert p.scores.dtype == np.float64            # 1/3 is not a 6-decimal value
+    l = packed_to_lists(p)
+    # "a" keeps first dict position but last score (0.5); sorted by score desc, ties keep dict order (b before c)
+    assert [(d, s) for d, s, _ in l[0][0]] == [("b", 0.9), ("c", 0.9), ("a", 0.5)]
+    assert l[1][0][0][0] == "z"
+
+
+def test_write_runfile_matches_reference_bytes(tmp_path):
+    with gzip.open(GOLD, "rt") as f:
+        gold = json.load(f)
+    for case in gold["cases"]:
+        for key, res in case["results"].items():
+            fused = {q: [(d, float(s)) for d, s in lst] for q, lst in res["fused"].items()}
+            out = tmp_path / "o.res"
+            fusion.write_runfile(fused, str(out), tag=f"{key.split('@')[0]}-x")
+            lines = out.read_text().splitlines()
+            assert len(lines) == res["runfile_n"] and lines[:25] == res["runfile_head"]
+            assert hashlib.sha256("\n".join(lines).encode()).hexdigest() == res["runfile_sha256"]
+
+
+def test_loaders_and_errors(tmp_path):
+    runs = tmp_path / "runs"
+    runs.mkdir()
+    with pytest.raises(FileNotFoundError):
+        fusion.load_runs(str(runs))
+    (runs / "B.norm.res").write_text("q1 Q0 d1 1 1.000000 B\nq1 Q0 d2 2 0.000000 B\n")
+    (runs / "A.norm.res").write_text("q1 Q0 d2 1 0.750000 A\n007 Q0 d9 1 0.5 A\n")
+    (runs / "A.res").write_text("q1 Q0 d2 1 12.5 A\nshort line\n")
+    r = fusion.load_runs(str(runs))
+    assert list(r.keys()) == ["A", "B"]                      # fixed, documented order
+    assert r["A"]["qid"].tolist() == ["q1", "007"] and r["A"]["score"].dtype == np.float64
+    assert list(fusion.load_runs(str(runs), use_normalized=False).keys()) == ["A"]
+    assert load_run_file(runs / "A.res") == {"q1": [("d2", 12.5, 1)]}
+    assert load_run_as_dict(runs / "B.norm.res") == {"q1": {"d1": 1.0, "d2": 0.0}}
+    qdir = tmp_path / "qpp"
+    qdir.mkdir()
+    with pytest.raises(FileNotFoundError):
+        load_qpp_scores(qdir)
+    (qdir / "A.res.mmnorm.qpp").write_text("q1\t" + "\t".join(["0.500000"] * 13) + "\n\n")
+    q = fusion.load_qpp_scores(str(qdir))
+    assert q == {"q1": {"A": [0.5] * 13}}
+    assert fusion.get_qpp_weight("q1", "A", q, 5) == 0.5 and fusion.get_qpp_weight("q1", "A", q, -1) == 0.5
+    with pytest.raises(KeyError):
+        fusion.get_qpp_weight("q2", "A", q)
+    with pytest.raises(KeyError):
+        fusion.get_qpp_weight("q1", "B", q)
+    with pytest.raises(IndexError):
+        fusion.get_qpp_weight("q1", "A", q, 13)
+    with pytest.raises(ValueError, match="qpp_dir required"):
+        fusion.run_fusion("wcombsum", str(runs))
+    with pytest.raises(ValueError, match="Unknown method"):
+        fusion.run_fusion("borda", str(runs))
+    with pytest.raises(ConfigError):
+        fusion.get_qpp_index("nope")
+
+
+def test_method_id_tables_are_the_reference_quirk():
+    assert [fusion.get_qpp_index(n) for n in ("SMV", "Sigma_max", "Sigma(%)", "NQC", "RSD", "WIG", "SCNQC")] == [0, 1, 2, 3, 5, 7, 8]
+    assert fusion.get_qpp_index("rsd") == 5 and fusion.get_qpp_index("fusion") == -1
+    assert config.qpp.methods[3] == "SigmaMax" and config.qpp.methods[0] == "nqc"     # id 3 ("NQC") selects SigmaMax
+    assert config.qpp.default_index == 5 and config.fusion.rrf_k == 60 and config.processing.retrieval.top_k == 100
+
+
+def test_retriever_result_and_normalize_scores():
+    r = RetrieverResult("q1", [("d1", 3.0, 1), ("d2", 1.0, 2)], "BGE")
+    assert r.to_trec_lines() == ["q1 Q0 d1 1 3.000000 BGE", "q1 Q0 d2 2 1.000000 BGE"]
+    assert BaseRetriever.normalize_scores(r.results) == [("d1", 1.0, 1), ("d2", 0.0, 2)]
+    assert BaseRetriever.normalize_scores([("d", 2.0, 1)]) == [("d", 0.0, 1)]
+    assert BaseRetriever.normalize_scores([]) == []
