@@ -164,6 +164,18 @@ QF_API int qf_qpp_colnorm(double* vals, int Q, int R, int ncols, int mode, int r
                    void* ws, size_t ws_bytes, void* stream);
 
 /*
+ * The same normalisation split in two for query-sharded multi-GPU runs (the ONE cross-query dependency of
+ * the QPP/fusion path): qf_qpp_colstats writes stats[r*ncols+c] = {min, max, sum, sum of squared deviations
+ * from mean[] (0 when mean == NULL)} of this rank's rows; the host all-reduces (MIN, MAX, SUM) over ranks,
+ * derives (base, scale) exactly as _normalize_qpp does and calls qf_qpp_colnorm_apply on every rank.
+ * base == scale == NULL applies only the "%.6f" round trip.
+ */
+QF_API int qf_qpp_colstats(const double* vals, int Q, int R, int ncols, const double* mean, double* stats,
+                           void* ws, size_t ws_bytes, void* stream);
+QF_API int qf_qpp_colnorm_apply(double* vals, int Q, int R, int ncols, const double* base, const double* scale,
+                                int round6, void* stream);
+
+/*
  * weights[q][r] = vals[q][r][col]  (col >= 0)  or  mean over the first `ncols_mean` columns
  * (col == -1, get_qpp_weight's fusion mode, src/fusion.py:152-153: sum(scores)/len(scores)).
  */

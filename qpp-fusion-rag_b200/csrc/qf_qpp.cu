@@ -413,6 +413,44 @@ __global__ void __launch_bounds__(256) colnorm_apply(double* vals, long long Q, 
   }
 }
 
+__global__ void colstats_export(const ColStat* st, int RC, double* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < RC) {
+    out[4 * i + 0] = unord_f64(st[i].omin);
+    out[4 * i + 1] = unord_f64(st[i].omax);
+    out[4 * i + 2] = st[i].sum;
+    out[4 * i + 3] = st[i].sumsq;
+  }
+}
+
+template <int PASS2>
+__global__ void __launch_bounds__(256) colstats_sumsq(const double* vals, long long Q, int RC, const double* mean, ColStat* st) {
+  extern __shared__ unsigned char sm_raw[];
+  double* loc = reinterpret_cast<double*>(sm_raw);
+  for (int i = threadIdx.x; i < RC; i += blockDim.x) loc[i] = 0.0;
+  __syncthreads();
+  const long long total = Q * RC;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(e % RC);
+    const double d = vals[e] - mean[c];
+    atomicAdd(&loc[c], d * d);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < RC; i += blockDim.x) atomicAdd(&st[i].sumsq, loc[i]);
+}
+
+__global__ void __launch_bounds__(256) colnorm_apply_params(double* vals, long long Q, int RC, const double* base,
+                                                            const double* scale, int do_round6) {
+  const long long total = Q * RC;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(e % RC);
+    double v = vals[e];
+    if (base) v = __ddiv_rn(__dsub_rn(v, base[c]), scale[c]);
+    if (do_round6) v = round6(v);
+    vals[e] = v;
+  }
+}
+
 __global__ void __launch_bounds__(256) select_weight_kernel(const double* vals, long long n_lists, int ncols, int col,
                                                             int ncols_mean, double* weights) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -509,6 +547,50 @@ extern "C" int qf_qpp_select_weight(const double* vals, int Q, int R, int ncols,
   const long long n = (long long)Q * R;
   select_weight_kernel<<<(unsigned)((n + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       vals, n, ncols, col, ncols_mean, weights);
+  QF_CUDA_TRY(cudaGetLastError());
+  return QF_OK;
+}
+
+extern "C" int qf_qpp_colstats(const double* vals, int Q, int R, int ncols, const double* mean, double* stats, void* ws,
+                               size_t ws_bytes, void* stream) {
+  QF_REQUIRE(Q >= 0 && R >= 1 && ncols >= 1, QF_E_INVALID, "qf_qpp_colstats: bad sizes");
+  const int RC = R * ncols;
+  QF_REQUIRE(RC <= 1024, QF_E_UNSUPPORTED, "qf_qpp_colstats: R*ncols=%d exceeds 1024", RC);
+  QF_REQUIRE(stats && ws && (vals || Q == 0), QF_E_INVALID, "qf_qpp_colstats: null pointer argument");
+  QF_REQUIRE(ws_bytes >= qf_qpp_colnorm_workspace_bytes(R, ncols), QF_E_WORKSPACE, "qf_qpp_colstats: workspace too small");
+  int rc = qf::check_device();
+  if (rc != QF_OK) return rc;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  ColStat* cs = reinterpret_cast<ColStat*>(ws);
+  const long long total = (long long)Q * RC;
+  long long blocks = (total + 255) / 256;
+  const long long cap = (long long)qf::sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  colnorm_init<<<(RC + 255) / 256, 256, 0, st>>>(cs, RC);
+  if (Q > 0) {
+    colnorm_reduce<1><<<(unsigned)blocks, 256, sizeof(ColStat) * RC, st>>>(vals, Q, RC, cs);
+    if (mean) colstats_sumsq<1><<<(unsigned)blocks, 256, sizeof(double) * RC, st>>>(vals, Q, RC, mean, cs);
+  }
+  colstats_export<<<(RC + 255) / 256, 256, 0, st>>>(cs, RC, stats);
+  QF_CUDA_TRY(cudaGetLastError());
+  return QF_OK;
+}
+
+extern "C" int qf_qpp_colnorm_apply(double* vals, int Q, int R, int ncols, const double* base, const double* scale,
+                                    int round6_flag, void* stream) {
+  QF_REQUIRE(Q >= 0 && R >= 1 && ncols >= 1, QF_E_INVALID, "qf_qpp_colnorm_apply: bad sizes");
+  QF_REQUIRE((base == nullptr) == (scale == nullptr), QF_E_INVALID, "qf_qpp_colnorm_apply: base and scale go together");
+  if (Q == 0) return QF_OK;
+  QF_REQUIRE(vals, QF_E_INVALID, "qf_qpp_colnorm_apply: null pointer argument");
+  int rc = qf::check_device();
+  if (rc != QF_OK) return rc;
+  const int RC = R * ncols;
+  const long long total = (long long)Q * RC;
+  long long blocks = (total + 255) / 256;
+  const long long cap = (long long)qf::sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  colnorm_apply_params<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(vals, Q, RC, base, scale, round6_flag);
   QF_CUDA_TRY(cudaGetLastError());
   return QF_OK;
 }

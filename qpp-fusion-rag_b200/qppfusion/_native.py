@@ -53,6 +53,8 @@ PROTOTYPES = {
     "qf_qpp_stats": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "qf_qpp_colnorm_workspace_bytes": (_sz, [_i, _i]),
     "qf_qpp_colnorm": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
+    "qf_qpp_colstats": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    "qf_qpp_colnorm_apply": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _vp]),
     "qf_qpp_select_weight": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "qf_dense_workspace_bytes": (_sz, [_i, _i, _i]),
     "qf_dense_max_k": (_i, []),

@@ -1,0 +1,83 @@
+"""
+Multi-GPU host logic (one process per GPU, torch.distributed; NCCL on the B200 box, gloo in CPU tests).
+
+  * dense retrieval : corpus rows sharded contiguously; every rank scores all queries against its shard
+                      (global ids via id_offset), one all-gather of the [Q, k] (score, id) pairs, k-way merge
+                      (qf_topk_merge).  Precedent in the reference: the HNSW segment merge,
+                      src/retrievers/bge.py:216-237.
+  * QPP + fusion    : queries sharded contiguously, no data-path collective.  The only cross-query dependency
+                      is _normalize_qpp's per-column min/max (or mean/std) over ALL queries of a run file
+                      (src/qpp.py:340-374): three tiny all-reduces (MIN, MAX, SUM) of R*13 doubles.
+
+The collective plumbing is separated from the kernel calls so it can be exercised on CPU tensors with gloo.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous shard [lo, hi) of n items for `rank` (ceil-sized shards, the last ones may be short/empty)."""
+    per = (n + world - 1) // world
+    lo = min(n, rank * per)
+    return lo, min(n, lo + per)
+
+
+def gather_topk(scores: torch.Tensor, ids: torch.Tensor, group=None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """All-gather per-shard results [Q, k] -> [G, Q, k] (the layout qf_topk_merge consumes)."""
+    world = dist.get_world_size(group)
+    gs = torch.empty((world,) + tuple(scores.shape), dtype=scores.dtype, device=scores.device)
+    gi = torch.empty((world,) + tuple(ids.shape), dtype=ids.dtype, device=ids.device)
+    # views of the [G, Q, k] buffers: NCCL gathers in place, gloo (CPU tests) copies into them
+    dist.all_gather(list(gs.unbind(0)), scores.contiguous(), group=group)
+    dist.all_gather(list(gi.unbind(0)), ids.contiguous(), group=group)
+    return gs, gi
+
+
+def reduce_colstats(stats: torch.Tensor, group=None) -> torch.Tensor:
+    """Combine per-rank [R, C, 4] = {min, max, sum, sumsq} tables across ranks (in place)."""
+    mn, mx, sm = stats[..., 0].contiguous(), stats[..., 1].contiguous(), stats[..., 2:].contiguous()
+    dist.all_reduce(mn, op=dist.ReduceOp.MIN, group=group)
+    dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=group)
+    dist.all_reduce(sm, op=dist.ReduceOp.SUM, group=group)
+    stats[..., 0], stats[..., 1], stats[..., 2:] = mn, mx, sm
+    return stats
+
+
+def colnorm_params(stats: torch.Tensor, q_total: int, mode: str) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(base, scale) per (retriever, column) exactly as _normalize_qpp derives them (src/qpp.py:355-361):
+    minmax -> (min, max-min if max>min else 1.0); zscore -> (mean, std_pop if std_pop>0 else 1.0)."""
+    if mode == "minmax":
+        mn, mx = stats[..., 0], stats[..., 1]
+        return mn.clone(), torch.where(mx > mn, mx - mn, torch.ones_like(mx))
+    mean = stats[..., 2] / q_total
+    std = torch.sqrt(stats[..., 3] / q_total)
+    return mean, torch.where(std > 0, std, torch.ones_like(std))
+
+
+def qpp_colnorm_sharded_(vals: torch.Tensor, mode: str, round6: bool, group=None) -> torch.Tensor:
+    """_normalize_qpp over a query-sharded [Q_local, R, C] table (in place, on the GPU)."""
+    from . import ops
+    if mode == "none":
+        return ops.qpp_colnorm_apply_(vals, None, None, round6) if round6 else vals
+    q_total = torch.tensor([vals.shape[0]], dtype=torch.int64, device=vals.device)
+    dist.all_reduce(q_total, group=group)
+    q_total = int(q_total.item())
+    stats = reduce_colstats(ops.qpp_colstats(vals), group)
+    if mode == "zscore":
+        mean = (stats[..., 2] / q_total).contiguous()
+        stats = reduce_colstats(ops.qpp_colstats(vals, mean), group)
+    base, scale = colnorm_params(stats, q_total, mode)
+    return ops.qpp_colnorm_apply_(vals, base.contiguous(), scale.contiguous(), round6)
+
+
+def dense_search_sharded(queries_bf16: torch.Tensor, corpus_shard_bf16: torch.Tensor, k: int, id_offset: int, group=None):
+    """Every rank: local top-k over its corpus rows, all-gather, merge -> identical [Q, k] on all ranks."""
+    from . import ops
+    scores, ids, status = ops.dense_topk(queries_bf16, corpus_shard_bf16, k, id_offset)
+    gs, gi = gather_topk(scores, ids, group)
+    ms, mi = ops.topk_merge(gs, gi)
+    return ms, mi, status

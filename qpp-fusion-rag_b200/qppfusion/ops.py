@@ -224,3 +224,30 @@ def _(scores, ids):
 def topk_merge(scores: torch.Tensor, ids: torch.Tensor):
     """k-way merge of per-shard results [G, Q, k] (as all_gather leaves them) -> ([Q, k], [Q, k])."""
     return torch.ops.qppfusion.topk_merge(scores, ids)
+
+
+# ---------------------------------------------------------------------------------------------- colstats (multi-GPU)
+def qpp_colstats(vals: torch.Tensor, mean: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Per (retriever, column) {min, max, sum, sumsq-about-mean} of this rank's rows: float64 [R, ncols, 4]."""
+    dev = N.require_cuda(vals, mean)
+    if vals.dim() != 3 or vals.dtype != torch.float64:
+        raise TypeError("vals must be float64 [Q, R, ncols]")
+    Q, R, C = vals.shape
+    stats = torch.empty((R, C, 4), dtype=torch.float64, device=dev)
+    nbytes = N.lib().qf_qpp_colnorm_workspace_bytes(R, C)
+    ws = torch.empty((max(nbytes, 8),), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        N.check(N.lib().qf_qpp_colstats(N.ptr(vals), Q, R, C, N.ptr(mean), N.ptr(stats), N.ptr(ws), nbytes,
+                                        N.stream_ptr(dev)))
+    return stats
+
+
+def qpp_colnorm_apply_(vals: torch.Tensor, base: Optional[torch.Tensor], scale: Optional[torch.Tensor],
+                       round6: bool = False) -> torch.Tensor:
+    """In place (v - base[r,c]) / scale[r,c] (+ optional "%.6f" round trip)."""
+    dev = N.require_cuda(vals, base, scale)
+    Q, R, C = vals.shape
+    with torch.cuda.device(dev):
+        N.check(N.lib().qf_qpp_colnorm_apply(N.ptr(vals), Q, R, C, N.ptr(base), N.ptr(scale), 1 if round6 else 0,
+                                             N.stream_ptr(dev)))
+    return vals

@@ -111,3 +111,27 @@ def test_topk_merge_matches_oracle():
     es, ei = do.merge_topk(s, i, k)
     assert np.array_equal(os_.cpu().numpy(), es)
     assert np.array_equal(oi.cpu().numpy().astype(np.int64), ei)
+
+
+def test_row_sharded_search_plus_merge_equals_single_shard():
+    """Multi-GPU dense path emulated on one device: 3 corpus shards -> per-shard top-k with global ids ->
+    [G, Q, k] (all-gather layout) -> qf_topk_merge == searching the whole corpus at once."""
+    from qppfusion import distributed as qd
+    from qppfusion import ops
+    rng = np.random.default_rng(21)
+    Q, N, D, k = 40, 30_000, 768, 200
+    dev = torch.device("cuda:0")
+    qb = to_bf16(unit_rows(rng, Q, D)).to(dev)
+    cb = to_bf16(unit_rows(rng, N, D)).to(dev)
+    fs, fi, st = ops.dense_topk(qb, cb, k, 0)
+    assert int(st.max()) == 0
+    G = 3
+    parts_s, parts_i = [], []
+    for g in range(G):
+        lo, hi = qd.shard_range(N, G, g)
+        s, i, st = ops.dense_topk(qb, cb[lo:hi].contiguous(), k, lo)
+        assert int(st.max()) == 0
+        parts_s.append(s)
+        parts_i.append(i)
+    ms, mi = ops.topk_merge(torch.stack(parts_s), torch.stack(parts_i))
+    assert torch.equal(ms, fs) and torch.equal(mi, fi)

@@ -163,3 +163,36 @@ def test_round6_hard_cases():
     ops.qpp_colnorm_(g, "none", round6=True)
     exp = np.array([qo.fmt6(float(x)) for x in v])
     assert np.array_equal(g.cpu().numpy().reshape(-1), exp)
+
+
+@pytest.mark.parametrize("mode", ["minmax", "zscore"])
+def test_query_sharded_colnorm_equals_single_launch(mode):
+    """The multi-GPU normalisation path (per-shard qf_qpp_colstats, host combine, qf_qpp_colnorm_apply) emulated
+    on one device equals the fused single-GPU qf_qpp_colnorm."""
+    from qppfusion import distributed as qd
+    from qppfusion import ops
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(51)
+    Q, R, C = 301, 5, 13
+    vals = rng.normal(size=(Q, R, C)) * 3
+    full = torch.from_numpy(vals.copy()).to(dev)
+    ops.qpp_colnorm_(full, mode, round6=True)
+    shards = [torch.from_numpy(vals[lo:hi].copy()).to(dev) for lo, hi in (qd.shard_range(Q, 3, g) for g in range(3))]
+
+    def combined(mean=None):
+        st = torch.stack([ops.qpp_colstats(s, mean) for s in shards])
+        out = torch.empty_like(st[0])
+        out[..., 0] = st[..., 0].amin(dim=0)
+        out[..., 1] = st[..., 1].amax(dim=0)
+        out[..., 2:] = st[..., 2:].sum(dim=0)
+        return out
+
+    st = combined()
+    if mode == "zscore":
+        st = combined((st[..., 2] / Q).contiguous())
+    base, scale = qd.colnorm_params(st, Q, mode)
+    got = torch.cat([ops.qpp_colnorm_apply_(s, base.contiguous(), scale.contiguous(), round6=True) for s in shards])
+    if mode == "minmax":
+        assert torch.equal(got, full)
+    else:
+        assert torch.allclose(got, full, rtol=0, atol=1.1e-6)     # %.6f of values that differ in the last ulps

@@ -1,0 +1,36 @@
+#!/usr/bin/env python3
+"""torchrun --nproc-per-node N tools/dist_gpu_check.py -- NCCL multi-GPU check of the sharded dense search and
+the sharded QPP normalisation against single-GPU results computed on rank 0."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "qpp-fusion-rag_b200"))
+import numpy as np
+import torch
+import torch.distributed as dist
+from qppfusion import distributed as qd, ops
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+g = torch.Generator(device="cpu"); g.manual_seed(5)
+Q, N, D, k = 300, 200_000, 768, 1000
+c = torch.randn((N, D), generator=g); c = (c / c.norm(dim=1, keepdim=True)).to(torch.bfloat16)
+q = torch.randn((Q, D), generator=g); q = (q / q.norm(dim=1, keepdim=True)).to(torch.bfloat16).to(dev)
+lo, hi = qd.shard_range(N, world, rank)
+ms, mi, st = qd.dense_search_sharded(q, c[lo:hi].to(dev).contiguous(), k, lo)
+assert int(st.max()) == 0
+if rank == 0:
+    fs, fi, st0 = ops.dense_topk(q, c.to(dev), k, 0)
+    assert torch.equal(fs, ms) and torch.equal(fi, mi), "sharded dense search differs from single-GPU search"
+vals = torch.randn((1000, 5, 13), generator=g, dtype=torch.float64)
+qlo, qhi = qd.shard_range(1000, world, rank)
+loc = vals[qlo:qhi].to(dev).contiguous()
+qd.qpp_colnorm_sharded_(loc, "minmax", True)
+if rank == 0:
+    full = vals.to(dev).contiguous(); ops.qpp_colnorm_(full, "minmax", round6=True)
+    assert torch.equal(full[qlo:qhi], loc), "sharded colnorm differs"
+dist.barrier()
+if rank == 0:
+    print(f"dist_gpu_check OK on {world} GPUs")
+dist.destroy_process_group()
