@@ -246,3 +246,21 @@ int qfo_qpp_bridge_batch(const int32_t* micro, const int32_t* lens, const int32_
   }
   return 0;
 }
+
+/* ------------------------------------------------------------------------------------------ arithmetic proofs */
+/* The CUDA kernels rebuild the double of a 6-decimal score from its integer micro-units without a division:
+ *     q0 = a * 1e-6;  r = fma(-1e6, q0, a);  q = fma(r, 1e-6, q0)
+ * (Markstein's correction step).  This exhaustive check counts the integers a in [lo, hi) for which q differs
+ * from the correctly rounded a / 1e6 (the value strtod("x.xxxxxx") returns).  Expected result: 0. */
+long long qfo_check_micro_division(long long lo, long long hi, int n_threads) {
+  long long bad = 0;
+#pragma omp parallel for reduction(+ : bad) num_threads(n_threads > 0 ? n_threads : 1) schedule(static)
+  for (long long a = lo; a < hi; ++a) {
+    const double x = (double)a;
+    const double q0 = x * 1.0e-6;
+    const double r = fma(-1.0e6, q0, x);
+    const double q = fma(r, 1.0e-6, q0);
+    if (q != x / 1.0e6) ++bad;
+  }
+  return bad;
+}

@@ -42,7 +42,15 @@ __device__ __forceinline__ unsigned long long ord_f64(double x) {
 // The double that Python's float("d.dddddd") parses to, from the integer number of micro-units.
 // i / 1e6 is an IEEE division of two exactly representable values, hence the correctly rounded
 // double nearest to the decimal -- exactly what strtod returns.
-__device__ __forceinline__ double micro_to_f64(int v) { return __ddiv_rn((double)v, 1.0e6); }
+// Division-free (Markstein correction): q0 = a*1e-6; r = fma(-1e6, q0, a); q = fma(r, 1e-6, q0).  Verified
+// EXHAUSTIVELY equal to a/1e6 for every int32 a (oracle/qf_oracle.c qfo_check_micro_division,
+// tests/test_oracle_c.py).
+__device__ __forceinline__ double micro_to_f64(int v) {
+  const double a = (double)v;
+  const double q0 = __dmul_rn(a, 1.0e-6);
+  const double r = __fma_rn(-1.0e6, q0, a);
+  return __fma_rn(r, 1.0e-6, q0);
+}
 
 template <typename T>
 __device__ __forceinline__ T warp_min(T v) {

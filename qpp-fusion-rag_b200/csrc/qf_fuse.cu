@@ -81,6 +81,10 @@ struct Layout {
   static constexpr size_t off_first = end_x;
   static constexpr size_t off_cnt = align16(off_first + sizeof(u16) * H);
   static constexpr size_t off_acc = align16(off_cnt + sizeof(u16) * H);
+  // the hash-join work lists (P1) live in the accumulator region, which is only initialised after P1
+  static constexpr size_t off_wlA = off_acc;
+  static constexpr size_t off_wlB = align16(off_wlA + sizeof(u32) * CAP);
+  static_assert(2 * sizeof(u32) * CAP + 32 <= sizeof(double) * H, "work lists must fit in the accumulator region");
   static constexpr size_t off_uslot = align16(off_acc + sizeof(double) * H);
   static constexpr size_t off_whist = align16(off_uslot + sizeof(u16) * CAP);
   static constexpr size_t off_misc = align16(off_whist + sizeof(u16) * NW * 256);
@@ -96,6 +100,7 @@ struct Misc {
   int flag_status;
   int flag_long;
   int flag_single;
+  int wl_cnt;
   int n_u;
   int warp_tot[32];
   u64 red_min[32];
@@ -135,6 +140,8 @@ __global__ void __launch_bounds__(NT) fuse_kernel(const FuseParams p) {
   double* s_acc = reinterpret_cast<double*>(smem + L::off_acc);
   u16* s_uslot = reinterpret_cast<u16*>(smem + L::off_uslot);
   u16* s_whist = reinterpret_cast<u16*>(smem + L::off_whist);
+  u32* s_wlA = reinterpret_cast<u32*>(smem + L::off_wlA);
+  u32* s_wlB = reinterpret_cast<u32*>(smem + L::off_wlB);
   Misc& m = *reinterpret_cast<Misc*>(smem + L::off_misc);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -155,13 +162,12 @@ __global__ void __launch_bounds__(NT) fuse_kernel(const FuseParams p) {
       m.start[R] = acc;
       m.flag_dup = 0;
       m.flag_long = 0;
+      m.wl_cnt = 0;
       m.flag_status = bad ? QF_QSTAT_BAD_LEN : 0;
     }
-    for (int i = tid; i < H; i += NT) {
-      s_table[i] = EMPTY16;
-      s_first[i] = EMPTY16;
-      s_cnt[i] = 0;
-      s_acc[i] = 0.0;
+    {
+      u32* t32 = reinterpret_cast<u32*>(s_table);
+      for (int i = tid; i < H / 2; i += NT) t32[i] = 0xFFFFFFFFu;
     }
     __syncthreads();
     const int n = m.start[R];
@@ -224,40 +230,75 @@ __global__ void __launch_bounds__(NT) fuse_kernel(const FuseParams p) {
       if (bad) m.flag_status = QF_QSTAT_UNSORTED;   // benign race: all writers store the same value
     }
 
-    // ---------------------------------------------------------------- P1: atomics-free hash join
+    // ---------------------------------------------------------------- P1: hash join (no atomics on the table)
+    // Round 0 visits every posting; postings that lose their slot to a DIFFERENT doc id go to a work list
+    // (seq | next probe position << 16) and only those are revisited in later rounds.  All postings of one
+    // doc id probe the same sequence in lock-step, so they settle in the same slot.
     {
+      u32* wl_out = s_wlA;
+      u32* wl_in = s_wlB;
       u16 hpos[PPT];
-      u32 active = 0;
 #pragma unroll
       for (int k = 0; k < PPT; ++k) {
         const int seq = tid + k * NT;
         if (seq < n) {
           hpos[k] = (u16)(((u32)s_ids[seq] * 2654435761u) >> (32 - HBITS));
-          active |= 1u << k;
+          if (s_table[hpos[k]] == EMPTY16) s_table[hpos[k]] = (u16)seq;
         }
       }
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < PPT; ++k) {
+        const int seq = tid + k * NT;
+        if (seq < n) {
+          const u16 owner = s_table[hpos[k]];
+          if (s_ids[owner] == s_ids[seq]) {
+            s_slotof[seq] = hpos[k];
+          } else {
+            const int pos = atomicAdd(&m.wl_cnt, 1);
+            wl_out[pos] = (u32)seq | ((u32)((hpos[k] + 1) & (H - 1)) << 16);
+          }
+        }
+      }
+      __syncthreads();
       while (true) {
-#pragma unroll
-        for (int k = 0; k < PPT; ++k)
-          if (active & (1u << k)) {
-            if (s_table[hpos[k]] == EMPTY16) s_table[hpos[k]] = (u16)(tid + k * NT);
-          }
+        const int cnt = m.wl_cnt;
+        if (cnt == 0) break;
+        { u32* t = wl_in; wl_in = wl_out; wl_out = t; }
+        __syncthreads();                       // everyone has read wl_cnt
+        if (tid == 0) m.wl_cnt = 0;
+        for (int e = tid; e < cnt; e += NT) {
+          const u32 ent = wl_in[e];
+          const u32 h = ent >> 16;
+          if (s_table[h] == EMPTY16) s_table[h] = (u16)(ent & 0xFFFFu);
+        }
         __syncthreads();
-#pragma unroll
-        for (int k = 0; k < PPT; ++k)
-          if (active & (1u << k)) {
-            const int seq = tid + k * NT;
-            const u16 owner = s_table[hpos[k]];
-            if (s_ids[owner] == s_ids[seq]) {
-              s_slotof[seq] = hpos[k];
-              active &= ~(1u << k);
-            } else {
-              hpos[k] = (u16)((hpos[k] + 1) & (H - 1));
-            }
+        for (int e = tid; e < cnt; e += NT) {
+          const u32 ent = wl_in[e];
+          const u32 h = ent >> 16, seq = ent & 0xFFFFu;
+          const u16 owner = s_table[h];
+          if (s_ids[owner] == s_ids[seq]) {
+            s_slotof[seq] = (u16)h;
+          } else {
+            const int pos = atomicAdd(&m.wl_cnt, 1);
+            wl_out[pos] = seq | (((h + 1) & (H - 1)) << 16);
           }
-        if (!__syncthreads_or(active != 0)) break;
+        }
+        __syncthreads();
       }
     }
+    // per-slot accumulators (their region held the work lists until now)
+    {
+      u32* f32 = reinterpret_cast<u32*>(s_first);
+      u32* c32 = reinterpret_cast<u32*>(s_cnt);
+      for (int i = tid; i < H / 2; i += NT) {
+        f32[i] = 0xFFFFFFFFu;
+        c32[i] = 0u;
+      }
+      double2* a2 = reinterpret_cast<double2*>(s_acc);
+      for (int i = tid; i < H / 2; i += NT) a2[i] = make_double2(0.0, 0.0);
+    }
+    __syncthreads();
 
     // ---------------------------------------------------------------- P3: ordered accumulation
     const bool is_rrf = (p.method == QF_METHOD_RRF);
@@ -321,36 +362,18 @@ __global__ void __launch_bounds__(NT) fuse_kernel(const FuseParams p) {
       __syncthreads();
     }
 
-    // ---------------------------------------------------------------- P4: final scores, key range
-    {
-      u64 omin = ~0ull, omax = 0ull;
-      for (int slot = tid; slot < H; slot += NT) {
-        if (s_first[slot] != EMPTY16) {
-          double fs = s_acc[slot];
-          if (p.method == QF_METHOD_MNZ) fs = __dmul_rn(fs, (double)s_cnt[slot]);
-          fs = fs + 0.0;                       // -0.0 -> +0.0 (Python: -0.0 == 0.0 is a tie)
-          s_acc[slot] = fs;
-          const u64 o = qf::ord_f64(fs);
-          omin = o < omin ? o : omin;
-          omax = o > omax ? o : omax;
-        }
-      }
-      omin = qf::warp_min(omin);
-      omax = qf::warp_max(omax);
-      if (lane == 0) {
-        m.red_min[warp] = omin;
-        m.red_max[warp] = omax;
-      }
-    }
-
     // ---------------------------------------------------------------- P2: first-seen order
     {
       const int base_seq = tid * PPT;
       int cnt = 0;
+      u32 firstmask = 0;
 #pragma unroll
       for (int k = 0; k < PPT; ++k) {
         const int seq = base_seq + k;
-        if (seq < n && s_first[s_slotof[seq]] == (u16)seq) ++cnt;
+        if (seq < n && s_first[s_slotof[seq]] == (u16)seq) {
+          ++cnt;
+          firstmask |= 1u << k;
+        }
       }
       int incl = cnt;
 #pragma unroll
@@ -364,21 +387,39 @@ __global__ void __launch_bounds__(NT) fuse_kernel(const FuseParams p) {
       for (int w = 0; w < warp; ++w) wbase += m.warp_tot[w];
       int u = wbase + incl - cnt;
 #pragma unroll
-      for (int k = 0; k < PPT; ++k) {
-        const int seq = base_seq + k;
-        if (seq < n) {
-          const int slot = s_slotof[seq];
-          if (s_first[slot] == (u16)seq) s_uslot[u++] = (u16)slot;
-        }
-      }
+      for (int k = 0; k < PPT; ++k)
+        if (firstmask & (1u << k)) s_uslot[u++] = s_slotof[base_seq + k];
       if (tid == NT - 1) m.n_u = u;
     }
     __syncthreads();   // region X (scores/table/slot_of/tag) is dead from here on
     const int n_u = m.n_u;
+
+    // ---------------------------------------------------------------- P4: final scores, key range (over the union)
     u64 omin = ~0ull, omax = 0ull;
-    for (int w = 0; w < NW; ++w) {
-      omin = m.red_min[w] < omin ? m.red_min[w] : omin;
-      omax = m.red_max[w] > omax ? m.red_max[w] : omax;
+    {
+      for (int u = tid; u < n_u; u += NT) {
+        const int slot = s_uslot[u];
+        double fs = s_acc[slot];
+        if (p.method == QF_METHOD_MNZ) fs = __dmul_rn(fs, (double)s_cnt[slot]);
+        fs = fs + 0.0;                       // -0.0 -> +0.0 (Python: -0.0 == 0.0 is a tie)
+        s_acc[slot] = fs;
+        const u64 o = qf::ord_f64(fs);
+        omin = o < omin ? o : omin;
+        omax = o > omax ? o : omax;
+      }
+      omin = qf::warp_min(omin);
+      omax = qf::warp_max(omax);
+      if (lane == 0) {
+        m.red_min[warp] = omin;
+        m.red_max[warp] = omax;
+      }
+      __syncthreads();
+      omin = ~0ull;
+      omax = 0ull;
+      for (int w = 0; w < NW; ++w) {
+        omin = m.red_min[w] < omin ? m.red_min[w] : omin;
+        omax = m.red_max[w] > omax ? m.red_max[w] : omax;
+      }
     }
 
     // ---------------------------------------------------------------- P5: ranking
@@ -404,7 +445,7 @@ __global__ void __launch_bounds__(NT) fuse_kernel(const FuseParams p) {
         u32* keyIn = s_keyA;
         u32* keyOut = s_keyB;
 #pragma unroll 1
-        for (int pass = 0; pass < 4; ++pass) {
+        for (int pass = 1; pass < 4; ++pass) {       // top 24 bits of the key: 3 passes, the fix-up is exact
           const int shift = pass * 8;
           const u32* kin = keyIn;
           auto dig = [&](int e) -> u32 { return (kin[e] >> shift) & 255u; };
@@ -413,13 +454,13 @@ __global__ void __launch_bounds__(NT) fuse_kernel(const FuseParams p) {
             u16* ti = idxIn; idxIn = idxOut; idxOut = ti;
           }
         }
-        // exact fix-up of runs with equal 32-bit prefix
+        // exact fix-up of runs whose sorted 24-bit prefix is equal
         for (int j = tid; j < n_u; j += NT) {
-          const u32 kj = keyIn[j];
-          const bool head = (j == 0 || keyIn[j - 1] != kj) && (j + 1 < n_u && keyIn[j + 1] == kj);
+          const u32 kj = keyIn[j] >> 8;
+          const bool head = (j == 0 || (keyIn[j - 1] >> 8) != kj) && (j + 1 < n_u && (keyIn[j + 1] >> 8) == kj);
           if (head) {
             int e = j + 2;
-            while (e < n_u && keyIn[e] == kj) ++e;
+            while (e < n_u && (keyIn[e] >> 8) == kj) ++e;
             if (e - j > 48) {
               m.flag_long = 1;
             } else {

@@ -50,3 +50,16 @@ def test_c_qpp_bridge_equals_python_oracle():
             exp = np.array(qo.bridge_scores(texts[q], lst[:100]))
             ok = (np.isnan(exp) & np.isnan(got[q, r])) | (np.abs(got[q, r] - exp) <= 1e-12 + 1e-10 * np.abs(exp))
             assert ok.all(), (q, r, got[q, r], exp)
+
+
+def test_division_free_micro_to_double_is_exact_for_every_int32():
+    """The CUDA kernels turn micro-units into the double float("x.xxxxxx") parses to with a multiply and two FMAs;
+    exhaustive proof over the whole int32 range (about 6 s on 8 cores)."""
+    import ctypes
+    import os
+    l = co.lib()
+    l.qfo_check_micro_division.restype = ctypes.c_longlong
+    l.qfo_check_micro_division.argtypes = [ctypes.c_longlong, ctypes.c_longlong, ctypes.c_int]
+    assert l.qfo_check_micro_division(-2 ** 31, 2 ** 31, os.cpu_count() or 1) == 0
+    for v in (0, 1, -1, 123456, 999999, -2147483648, 2147483647):
+        assert float(f"{v / 1e6:.6f}") == v / 1e6
