@@ -205,6 +205,18 @@ QF_API int    qf_dense_topk(const void* queries_bf16, const void* corpus_bf16, i
                             void* ws, size_t ws_bytes, void* stream);
 
 /*
+ * Exact fallback for queries whose out_status is non-zero (and a building block for tests):
+ * qf_dense_scores writes the full fp32 score rows out[q][d] (rows padded to a multiple of 128, row stride ld >=
+ * 64*ceil(N/64)) with the same tcgen05 kernel; qf_dense_row_topk streams stored rows and writes the exact top-k
+ * (score desc, id asc; exact under arbitrary ties) of stored row r into output row rows[r], clearing its status.
+ */
+QF_API int    qf_dense_scores(const void* queries_bf16, const void* corpus_bf16, int Q, int N, int D, float* out,
+                              long long ld, void* stream);
+QF_API int    qf_dense_row_topk(const float* scores, long long ld, const int32_t* rows, int n_rows, int N, int k,
+                                long long id_offset, float* out_scores, int32_t* out_ids, int32_t* out_status,
+                                void* stream);
+
+/*
  * k-way merge after the all-gather of per-shard results (multi-GPU dense retrieval; precedent: the
  * reference's HNSW segment merge, src/retrievers/bge.py:216-237): scores/ids are [G][Q][k] as
  * ncclAllGather leaves them, ids global, -1 = padding.  Output [Q][k], (score desc, id asc).

@@ -23,7 +23,7 @@ INCLUDE = os.path.join(ROOT, "include")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 CFLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
-          "--expt-relaxed-constexpr", "-I", INCLUDE, "-I", CSRC]
+          "--expt-relaxed-constexpr", "-I", INCLUDE, "-I", CSRC] + os.environ.get("QF_EXTRA_CFLAGS", "").split()
 
 
 def sources():

@@ -515,15 +515,95 @@ struct SelectParams {
   int* out_status;         // [Q] nullable: 1 = candidate underflow, 2 = overflow
 };
 
+struct SelSmem {
+  float* score;
+  int* id;
+  u32 *keyA, *keyB;
+  u16 *idxA, *idxB, *whist;
+};
+
+__device__ __forceinline__ SelSmem carve_sel(unsigned char* sm) {
+  SelSmem s;
+  s.score = reinterpret_cast<float*>(sm);
+  s.id = reinterpret_cast<int*>(sm + 4 * SEL_CAP);
+  s.keyA = reinterpret_cast<u32*>(sm + 8 * SEL_CAP);
+  s.keyB = reinterpret_cast<u32*>(sm + 12 * SEL_CAP);
+  s.idxA = reinterpret_cast<u16*>(sm + 16 * SEL_CAP);
+  s.idxB = reinterpret_cast<u16*>(sm + 18 * SEL_CAP);
+  s.whist = reinterpret_cast<u16*>(sm + 20 * SEL_CAP);
+  return s;
+}
+
+// Rank the n candidates held in (S.score, S.id) by (score desc, id asc).  Block-wide; returns the index
+// array holding the order.  Entries [n, n_pad) must have been filled with score -inf / id INT_MAX.
+__device__ const u16* rank_candidates(const SelSmem& S, int n, int* warp_tot, int* flag_single, int* flag_long) {
+  const int tid = threadIdx.x;
+  const int n_pad = (n + 31) & ~31;
+  if (tid == 0) *flag_long = 0;
+  for (int i = tid; i < n_pad; i += SEL_NT) {
+    S.keyA[i] = i < n ? ~ord_f32(S.score[i] + 0.0f) : 0xFFFFFFFFu;     // ascending key = descending score
+    S.idxA[i] = (u16)i;
+  }
+  __syncthreads();
+  u32* kin = S.keyA; u32* kout = S.keyB;
+  u16* iin = S.idxA; u16* iout = S.idxB;
+#pragma unroll 1
+  for (int pass = 0; pass < 4; ++pass) {
+    const int shift = 8 * pass;
+    const u32* kk = kin;
+    auto dig = [&](int e) -> u32 { return (kk[e] >> shift) & 255u; };
+    if (qf::radix_pass<SEL_NT, SEL_ROUNDS, true>(dig, n_pad, kin, kout, iin, iout, S.whist, warp_tot, flag_single)) {
+      u32* t = kin; kin = kout; kout = t;
+      u16* ti = iin; iin = iout; iout = ti;
+    }
+  }
+  // equal-score runs: order by id ascending (exact); long runs take the two-key radix path below
+  for (int j = tid; j < n; j += SEL_NT) {
+    const u32 kj = kin[j];
+    const bool head = (j == 0 || kin[j - 1] != kj) && (j + 1 < n && kin[j + 1] == kj);
+    if (head) {
+      int e = j + 2;
+      while (e < n && kin[e] == kj) ++e;
+      if (e - j > 48) {
+        *flag_long = 1;
+      } else {
+        for (int a = j + 1; a < e; ++a) {
+          const u16 ia = iin[a];
+          const int ida = S.id[ia];
+          int b = a - 1;
+          while (b >= j && S.id[iin[b]] > ida) { iin[b + 1] = iin[b]; --b; }
+          iin[b + 1] = ia;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (*flag_long) {
+    // many equal scores: LSD radix over (id, then score) = full (score desc, id asc) order, no fix-up needed
+    for (int i = tid; i < n_pad; i += SEL_NT) S.idxA[i] = (u16)i;
+    __syncthreads();
+    iin = S.idxA; iout = S.idxB;
+#pragma unroll 1
+    for (int pass = 0; pass < 8; ++pass) {
+      const int shift = 8 * (pass & 3);
+      const u16* ii = iin;
+      const bool by_id = pass < 4;
+      auto dig = [&](int e) -> u32 {
+        const int c = ii[e];
+        const u32 key = by_id ? (u32)S.id[c] : (c < n ? ~ord_f32(S.score[c] + 0.0f) : 0xFFFFFFFFu);
+        return (key >> shift) & 255u;
+      };
+      if (qf::radix_pass<SEL_NT, SEL_ROUNDS, false>(dig, n_pad, nullptr, nullptr, iin, iout, S.whist, warp_tot, flag_single)) {
+        u16* ti = iin; iin = iout; iout = ti;
+      }
+    }
+  }
+  return iin;
+}
+
 __global__ void __launch_bounds__(SEL_NT, 1) select_kernel(const SelectParams p) {
   extern __shared__ __align__(16) unsigned char sm[];
-  float* s_score = reinterpret_cast<float*>(sm);
-  int* s_id = reinterpret_cast<int*>(sm + 4 * SEL_CAP);
-  u32* keyA = reinterpret_cast<u32*>(sm + 8 * SEL_CAP);
-  u32* keyB = reinterpret_cast<u32*>(sm + 12 * SEL_CAP);
-  u16* idxA = reinterpret_cast<u16*>(sm + 16 * SEL_CAP);
-  u16* idxB = reinterpret_cast<u16*>(sm + 18 * SEL_CAP);
-  u16* whist = reinterpret_cast<u16*>(sm + 20 * SEL_CAP);
+  const SelSmem S = carve_sel(sm);
   __shared__ int warp_tot[32];
   __shared__ int flag_single, flag_long;
   const int tid = threadIdx.x;
@@ -536,7 +616,6 @@ __global__ void __launch_bounds__(SEL_NT, 1) select_kernel(const SelectParams p)
     const int n = n_raw;
     if (n < want) status |= 1;
     const int n_pad = (n + 31) & ~31;
-    if (tid == 0) flag_long = 0;
     for (int i = tid; i < n_pad; i += SEL_NT) {
       float s = -INFINITY;
       int id = 0x7fffffff;
@@ -546,57 +625,116 @@ __global__ void __launch_bounds__(SEL_NT, 1) select_kernel(const SelectParams p)
         const size_t a = (size_t)q * p.q_stride + (size_t)seg * p.seg_stride + off;
         s = p.cand_score[a];
         id = p.cand_id[a];
-        if (id < 0) s = -INFINITY;          // padding of a short segment
+        if (id < 0) { s = -INFINITY; id = 0x7fffffff; }         // padding of a short segment
       }
-      s_score[i] = s;
-      s_id[i] = id;
-      keyA[i] = i < n ? ~ord_f32(s + 0.0f) : 0xFFFFFFFFu;     // ascending key = descending score
-      idxA[i] = (u16)i;
+      S.score[i] = s;
+      S.id[i] = id;
     }
     __syncthreads();
-    u32* kin = keyA; u32* kout = keyB;
-    u16* iin = idxA; u16* iout = idxB;
-#pragma unroll 1
-    for (int pass = 0; pass < 4; ++pass) {
-      const int shift = 8 * pass;
-      const u32* kk = kin;
-      auto dig = [&](int e) -> u32 { return (kk[e] >> shift) & 255u; };
-      if (qf::radix_pass<SEL_NT, SEL_ROUNDS, true>(dig, n_pad, kin, kout, iin, iout, whist, warp_tot, &flag_single)) {
-        u32* t = kin; kin = kout; kout = t;
-        u16* ti = iin; iin = iout; iout = ti;
-      }
-    }
-    // equal-score runs: order by id ascending (exact)
-    for (int j = tid; j < n; j += SEL_NT) {
-      const u32 kj = kin[j];
-      const bool head = (j == 0 || kin[j - 1] != kj) && (j + 1 < n && kin[j + 1] == kj);
-      if (head) {
-        int e = j + 2;
-        while (e < n && kin[e] == kj) ++e;
-        for (int a = j + 1; a < e; ++a) {
-          const u16 ia = iin[a];
-          const int ida = s_id[ia];
-          int b = a - 1;
-          while (b >= j && s_id[iin[b]] > ida) { iin[b + 1] = iin[b]; --b; }
-          iin[b + 1] = ia;
-        }
-      }
-    }
-    __syncthreads();
+    const u16* order = rank_candidates(S, n, warp_tot, &flag_single, &flag_long);
     for (int j = tid; j < p.k; j += SEL_NT) {
       float s = -INFINITY;
       int id = -1;
       if (j < n) {
-        const int e = iin[j];
-        if (s_id[e] != 0x7fffffff && s_score[e] != -INFINITY) {
-          s = s_score[e];
-          id = (int)(s_id[e] + p.id_offset);
+        const int e = order[j];
+        if (S.id[e] != 0x7fffffff && S.score[e] != -INFINITY) {
+          s = S.score[e];
+          id = (int)(S.id[e] + p.id_offset);
         }
       }
       p.out_scores[(size_t)q * p.k + j] = s;
       p.out_ids[(size_t)q * p.k + j] = id;
     }
     if (p.out_status && tid == 0) p.out_status[q] = status;
+    __syncthreads();
+  }
+}
+
+// Exact streaming top-k of stored score rows (the fallback when the sampled threshold admitted too few or too
+// many candidates for a query).  One CTA per row: candidates >= the running k-th score are appended to the
+// shared-memory buffer; when it fills up it is ranked and cut back to k.  Documents are scanned in increasing
+// id order, so once k candidates are held a later document with score == k-th can never enter (its id is
+// larger): strict '>' keeps the result exact under arbitrary ties.
+struct RowTopkParams {
+  const float* scores;     // [n_rows, ld]
+  long long ld;
+  const int* rows;         // [n_rows] output row (query index) of each stored row
+  int n_rows, N, k;
+  long long id_offset;
+  float* out_scores;       // [Q, k]
+  int* out_ids;
+  int* out_status;         // nullable; cleared to 0 for repaired rows
+};
+
+__global__ void __launch_bounds__(SEL_NT, 1) row_topk_kernel(const RowTopkParams p) {
+  extern __shared__ __align__(16) unsigned char sm[];
+  const SelSmem S = carve_sel(sm);
+  __shared__ int warp_tot[32];
+  __shared__ int flag_single, flag_long, s_cnt;
+  const int tid = threadIdx.x;
+  constexpr int BATCH = SEL_NT * 4;
+  for (int r = blockIdx.x; r < p.n_rows; r += gridDim.x) {
+    const float* row = p.scores + (size_t)r * p.ld;
+    const int q = p.rows[r];
+    float thr = -INFINITY;
+    bool have_k = false;
+    if (tid == 0) s_cnt = 0;
+    __syncthreads();
+    for (int base = 0; base < p.N; base += BATCH) {
+      if (s_cnt + BATCH > SEL_CAP) {           // make room: rank, keep the best k
+        const int n = s_cnt;
+        const int n_pad = (n + 31) & ~31;
+        for (int i = n + tid; i < n_pad; i += SEL_NT) { S.score[i] = -INFINITY; S.id[i] = 0x7fffffff; }
+        __syncthreads();
+        const u16* order = rank_candidates(S, n, warp_tot, &flag_single, &flag_long);
+        const int keep = min(n, p.k);
+        float ks[(SEL_CAP / SEL_NT) > 2 ? 2 : 2];
+        int ki[2];
+        // k <= 1024 = 2 * SEL_NT: each thread carries at most two kept entries through the compaction
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          const int j = tid + t * SEL_NT;
+          if (j < keep) { ks[t] = S.score[order[j]]; ki[t] = S.id[order[j]]; }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          const int j = tid + t * SEL_NT;
+          if (j < keep) { S.score[j] = ks[t]; S.id[j] = ki[t]; }
+        }
+        if (tid == 0) s_cnt = keep;
+        __syncthreads();
+        have_k = keep >= p.k;
+        thr = have_k ? S.score[keep - 1] : -INFINITY;
+        __syncthreads();
+      }
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int d = base + t * SEL_NT + tid;
+        if (d < p.N) {
+          const float s = row[d];
+          if (have_k ? (s > thr) : (s >= thr)) {
+            const int pos = atomicAdd(&s_cnt, 1);
+            S.score[pos] = s;
+            S.id[pos] = d;
+          }
+        }
+      }
+      __syncthreads();
+    }
+    const int n = s_cnt;
+    const int n_pad = (n + 31) & ~31;
+    for (int i = n + tid; i < n_pad; i += SEL_NT) { S.score[i] = -INFINITY; S.id[i] = 0x7fffffff; }
+    __syncthreads();
+    const u16* order = rank_candidates(S, n, warp_tot, &flag_single, &flag_long);
+    for (int j = tid; j < p.k; j += SEL_NT) {
+      float s = -INFINITY;
+      int id = -1;
+      if (j < n) { s = S.score[order[j]]; id = (int)(S.id[order[j]] + p.id_offset); }
+      p.out_scores[(size_t)q * p.k + j] = s;
+      p.out_ids[(size_t)q * p.k + j] = id;
+    }
+    if (p.out_status && tid == 0) p.out_status[q] = 0;
     __syncthreads();
   }
 }
@@ -755,6 +893,65 @@ extern "C" int qf_dense_topk(const void* queries_bf16, const void* corpus_bf16, 
   qf::prof_mark(QF_PROF_DENSE_SELECT, 0, st);
   select_kernel<<<Q < sms ? Q : sms, SEL_NT, SEL_SMEM, st>>>(sp);
   qf::prof_mark(QF_PROF_DENSE_SELECT, 1, st);
+  QF_CUDA_TRY(cudaGetLastError());
+  return QF_OK;
+}
+
+// Full score matrix for a (small) query batch: out[q][d] = <queries[q], corpus[d]>, rows padded to a multiple of
+// 128 and columns to a multiple of 64 (ld).  Same tcgen05 kernel, STORE epilogue.
+extern "C" int qf_dense_scores(const void* queries_bf16, const void* corpus_bf16, int Q, int N, int D, float* out,
+                               long long ld, void* stream) {
+  QF_REQUIRE(Q >= 1 && N >= 1, QF_E_INVALID, "qf_dense_scores: bad sizes Q=%d N=%d", Q, N);
+  QF_REQUIRE(D >= BK && D % BK == 0 && D <= MAX_D, QF_E_UNSUPPORTED, "qf_dense_scores: D=%d unsupported", D);
+  const long long T = ((long long)N + BN - 1) / BN;
+  QF_REQUIRE(ld >= T * BN && ld % 4 == 0, QF_E_INVALID, "qf_dense_scores: ld=%lld must be >= %lld and a multiple of 4", ld, T * BN);
+  QF_REQUIRE(queries_bf16 && corpus_bf16 && out, QF_E_INVALID, "qf_dense_scores: null pointer argument");
+  int rc = qf::check_device();
+  if (rc != QF_OK) return rc;
+  EncodeTiledFn encode;
+  rc = get_encode_fn(&encode);
+  if (rc != QF_OK) return rc;
+  CUtensorMap tmap;
+  {
+    cuuint64_t gdim[2] = {(cuuint64_t)D, (cuuint64_t)N};
+    cuuint64_t gstride[1] = {(cuuint64_t)D * 2};
+    cuuint32_t box[2] = {BK, BN};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(corpus_bf16), gdim, gstride, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    QF_REQUIRE(r == CUDA_SUCCESS, QF_E_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  }
+  QF_CUDA_TRY(cudaFuncSetAttribute(dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DENSE_SMEM));
+  DenseParams p{};
+  p.queries = reinterpret_cast<const __nv_bfloat16*>(queries_bf16);
+  p.Q = Q; p.N = N; p.D = D;
+  p.n_mtiles = (Q + BM - 1) / BM;
+  p.mode = MODE_STORE;
+  p.n_vtiles = (int)T;
+  p.tile_step = 1;
+  p.chunk_tiles = T >= 4096 ? 256 : (T >= 256 ? 32 : 4);
+  p.store = out;
+  p.store_ld = ld;
+  const int units = ((p.n_vtiles + p.chunk_tiles - 1) / p.chunk_tiles) * p.n_mtiles;
+  const int sms = qf::sm_count();
+  dense_kernel<<<units < sms ? units : sms, NT, DENSE_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(tmap, p);
+  QF_CUDA_TRY(cudaGetLastError());
+  return QF_OK;
+}
+
+extern "C" int qf_dense_row_topk(const float* scores, long long ld, const int32_t* rows, int n_rows, int N, int k,
+                                 long long id_offset, float* out_scores, int32_t* out_ids, int32_t* out_status,
+                                 void* stream) {
+  QF_REQUIRE(n_rows >= 0 && N >= 1 && k >= 1 && k <= qf_dense_max_k(), QF_E_INVALID, "qf_dense_row_topk: bad sizes");
+  if (n_rows == 0) return QF_OK;
+  QF_REQUIRE(scores && rows && out_scores && out_ids && ld >= N, QF_E_INVALID, "qf_dense_row_topk: bad argument");
+  int rc = qf::check_device();
+  if (rc != QF_OK) return rc;
+  QF_CUDA_TRY(cudaFuncSetAttribute(row_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SEL_SMEM));
+  RowTopkParams rp{scores, ld, rows, n_rows, N, k, id_offset, out_scores, out_ids, out_status};
+  const int sms = qf::sm_count();
+  row_topk_kernel<<<n_rows < sms ? n_rows : sms, SEL_NT, SEL_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(rp);
   QF_CUDA_TRY(cudaGetLastError());
   return QF_OK;
 }

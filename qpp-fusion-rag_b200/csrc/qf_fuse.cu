@@ -26,6 +26,9 @@ using u64 = unsigned long long;
 
 constexpr u16 EMPTY16 = 0xFFFFu;
 constexpr int MAX_R = 32;
+#ifndef QF_FUSE_NT
+#define QF_FUSE_NT 512
+#endif
 constexpr u32 QF_FLAG_DEBUG_FULLSORT = 0x100u;   // test hook: force the 64-bit sort path
 
 struct FuseParams {
@@ -551,7 +554,7 @@ template <int ST>
 int dispatch_cap(const FuseParams& p, cudaStream_t stream) {
   const long long n_max = (long long)p.R * p.K;
   if (n_max <= 1024) return launch<1024, 11, 128, ST>(p, stream);
-  return launch<5120, 13, 512, ST>(p, stream);
+  return launch<5120, 13, QF_FUSE_NT, ST>(p, stream);
 }
 
 }  // namespace

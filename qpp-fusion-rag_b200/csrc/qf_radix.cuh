@@ -18,7 +18,7 @@ template <int NT, int MAXROUNDS, bool CARRY_KEY, typename DigitFn>
 __device__ __forceinline__ bool radix_pass(DigitFn dig, int n_pad, const u32* keyIn, u32* keyOut, const u16* idxIn,
                                            u16* idxOut, u16* whist, int* warp_tot, int* single_flag) {
   constexpr int NW = NT / 32;
-  static_assert(NW % 2 == 0 && NW <= 16, "NW must be even and <= 16");
+  static_assert(NW % 2 == 0 && NW <= 32, "NW must be even and <= 32");
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int rounds_total = n_pad >> 5;
   const int rounds_per_warp = (rounds_total + NW - 1) / NW;

@@ -59,6 +59,8 @@ PROTOTYPES = {
     "qf_dense_workspace_bytes": (_sz, [_i, _i, _i]),
     "qf_dense_max_k": (_i, []),
     "qf_dense_topk": (_i, [_vp, _vp, _i, _i, _i, _i, ctypes.c_longlong, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "qf_dense_scores": (_i, [_vp, _vp, _i, _i, _i, _vp, ctypes.c_longlong, _vp]),
+    "qf_dense_row_topk": (_i, [_vp, ctypes.c_longlong, _vp, _i, _i, _i, ctypes.c_longlong, _vp, _vp, _vp, _vp]),
     "qf_topk_merge": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
 }
 

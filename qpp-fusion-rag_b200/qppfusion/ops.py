@@ -196,9 +196,43 @@ def _(queries, corpus, k, id_offset):
             torch.empty((Q,), dtype=torch.int32, device=queries.device))
 
 
-def dense_topk(queries: torch.Tensor, corpus: torch.Tensor, k: int, id_offset: int = 0):
-    """-> (scores f32 [Q,k] desc, ids int32 [Q,k] (-1 padded), status int32 [Q])."""
-    return torch.ops.qppfusion.dense_topk(queries, corpus, int(k), int(id_offset))
+def dense_scores(queries: torch.Tensor, corpus: torch.Tensor) -> torch.Tensor:
+    """Full fp32 score rows [ceil128(Q), 64*ceil(N/64)] (tcgen05 kernel, STORE epilogue); for small Q."""
+    dev = N.require_cuda(queries, corpus)
+    Q, D = queries.shape
+    Nn = corpus.shape[0]
+    ld = (Nn + 63) // 64 * 64
+    out = torch.empty(((Q + 127) // 128 * 128, ld), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        N.check(N.lib().qf_dense_scores(N.ptr(queries), N.ptr(corpus), Q, Nn, D, N.ptr(out), ld, N.stream_ptr(dev)))
+    return out
+
+
+def dense_repair_(queries, corpus, k, id_offset, scores, ids, status, max_rows: int = 512) -> int:
+    """Exact fallback: recompute every query whose status != 0 by streaming its full score row
+    (qf_dense_scores + qf_dense_row_topk), in place.  Returns the number of repaired queries."""
+    bad = torch.nonzero(status).flatten()
+    n_bad = int(bad.numel())
+    dev = queries.device
+    for s0 in range(0, n_bad, max_rows):
+        rows = bad[s0:s0 + max_rows].to(torch.int32).contiguous()
+        qb = queries[rows.long()].contiguous()
+        full = dense_scores(qb, corpus)
+        with torch.cuda.device(dev):
+            N.check(N.lib().qf_dense_row_topk(N.ptr(full), full.shape[1], N.ptr(rows), int(rows.numel()), corpus.shape[0],
+                                              k, id_offset, N.ptr(scores), N.ptr(ids), N.ptr(status), N.stream_ptr(dev)))
+        del full
+    return n_bad
+
+
+def dense_topk(queries: torch.Tensor, corpus: torch.Tensor, k: int, id_offset: int = 0, exact_fallback: bool = True):
+    """-> (scores f32 [Q,k] desc, ids int32 [Q,k] (-1 padded), status int32 [Q]).
+    With exact_fallback (default) queries whose sampled threshold failed are recomputed exactly, so status is 0
+    on return; this reads the status vector back (one small D2H sync)."""
+    scores, ids, status = torch.ops.qppfusion.dense_topk(queries, corpus, int(k), int(id_offset))
+    if exact_fallback and bool(status.any().item()):
+        dense_repair_(queries, corpus, int(k), int(id_offset), scores, ids, status)
+    return scores, ids, status
 
 
 @torch.library.custom_op("qppfusion::topk_merge", mutates_args=())

@@ -135,3 +135,47 @@ def test_row_sharded_search_plus_merge_equals_single_shard():
         parts_i.append(i)
     ms, mi = ops.topk_merge(torch.stack(parts_s), torch.stack(parts_i))
     assert torch.equal(ms, fs) and torch.equal(mi, fi)
+
+
+def test_exact_fallback_under_heavy_ties_and_clusters():
+    """Adversarial corpora for the sampled threshold: (a) thousands of identical documents (more ties than the
+    candidate capacity), (b) the relevant documents clustered in one region the strided sample never sees.
+    The status-driven exact fallback (full score rows + streaming top-k) must return the exact answer."""
+    from qppfusion import ops
+    rng = np.random.default_rng(31)
+    Q, N, D, k = 6, 120_000, 768, 1000
+    c = unit_rows(rng, N, D)
+    q = unit_rows(rng, Q, D)
+    c[20_000:32_000] = c[20_000]                       # 12k identical docs -> identical scores
+    q[0] = c[20_000]                                   # query 0 ties on all of them
+    for j in range(1, 3):                              # queries 1,2: 3000 near-duplicates of the query in one block
+        noise = rng.standard_normal((3000, D)).astype(np.float32) * 0.02
+        blk = q[j][None, :] + noise
+        c[60_000 + j * 4000: 60_000 + j * 4000 + 3000] = blk / np.linalg.norm(blk, axis=1, keepdims=True)
+    dev = torch.device("cuda:0")
+    qb, cb = to_bf16(q).to(dev), to_bf16(c).to(dev)
+    raw_s, raw_i, raw_st = torch.ops.qppfusion.dense_topk(qb, cb, k, 0)
+    assert int(raw_st[0]) != 0, "the tie-heavy query should trip the candidate capacity"
+    s, i, st = ops.dense_topk(qb, cb, k, 0)
+    assert int(st.max()) == 0
+    oi, os_ = do.flat_ip_topk(qb.float().cpu().numpy(), cb.float().cpu().numpy(), k)
+    s, i = s.cpu().numpy(), i.cpu().numpy().astype(np.int64)
+    assert np.abs(s - os_).max() <= TOL_SAME_INPUT
+    # query 0: all top-1000 scores tie exactly -> ids must be the 1000 smallest ids of the tied block
+    assert np.array_equal(i[0], np.arange(20_000, 21_000))
+    for qq in range(1, Q):
+        diff = set(i[qq].tolist()) ^ set(oi[qq].tolist())
+        for d in diff:
+            assert abs(float(qb[qq].float().cpu().numpy() @ cb[d].float().cpu().numpy()) - os_[qq, -1]) <= 2 * TOL_SAME_INPUT
+
+
+def test_dense_scores_matches_fp32_matmul():
+    from qppfusion import ops
+    rng = np.random.default_rng(33)
+    Q, N, D = 9, 1000, 768
+    dev = torch.device("cuda:0")
+    qb, cb = to_bf16(unit_rows(rng, Q, D)).to(dev), to_bf16(unit_rows(rng, N, D)).to(dev)
+    full = ops.dense_scores(qb, cb)
+    ref = qb.float() @ cb.float().T
+    assert full.shape == (128, 1024)
+    assert float((full[:Q, :N] - ref).abs().max()) <= TOL_SAME_INPUT
