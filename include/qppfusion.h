@@ -120,6 +120,17 @@ QF_API int qf_fuse(const int32_t* doc_ids, const void* scores, int score_type, c
             int32_t* out_ids, double* out_scores, uint16_t* out_counts, uint16_t* out_pos,
             int32_t* out_lens, int32_t* out_status, void* stream);
 
+/*
+ * Padded fusion outputs -> CSR: offsets[Q+1] (exclusive scan of out_lens, offsets[Q] = total), then the first
+ * out_lens[q] entries of every row copied to out_ids/out_scores[offsets[q] ...).  Used before the device->host
+ * copy / the .res writer so that |union| instead of R*K entries per query move.  out_* need capacity
+ * sum(out_lens) (<= Q*stride).  ws: qf_compact_workspace_bytes(Q).
+ */
+QF_API size_t qf_compact_workspace_bytes(int Q);
+QF_API int    qf_compact_fused(const int32_t* ids, const double* scores, const int32_t* lens, int Q, long long stride,
+                               long long* offsets, int32_t* out_ids, double* out_scores, void* ws, size_t ws_bytes,
+                               void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * QPP statistics  --  replaces the JVM round trip QPPBridge.compute_batch -> qpp.QPPBridge
  *                     (src/qpp.py:117-171; src/qpp/java/qpp/QPPBridge.java:134-453)

@@ -50,6 +50,8 @@ PROTOTYPES = {
     "qf_profile_read": (_i, [_i, ctypes.POINTER(ctypes.c_float)]),
     "qf_fuse_max_postings": (_i, []),
     "qf_fuse": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _d, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "qf_compact_workspace_bytes": (_sz, [_i]),
+    "qf_compact_fused": (_i, [_vp, _vp, _vp, _i, ctypes.c_longlong, _vp, _vp, _vp, _vp, _sz, _vp]),
     "qf_qpp_stats": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "qf_qpp_colnorm_workspace_bytes": (_sz, [_i, _i]),
     "qf_qpp_colnorm": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _sz, _vp]),

@@ -82,6 +82,23 @@ def fuse(doc_ids, scores, lens, weights=None, ranks=None, method=N.METHOD_SUM, n
                                              float(rrf_k), int(flags), bool(want_counts), bool(want_pos)))
 
 
+def compact_fused(out: "FuseOut", cap: Optional[int] = None):
+    """FuseOut (padded [Q, R*K]) -> CSR on the device: (offsets int64 [Q+1], ids int32 [cap], scores f64 [cap]).
+    cap defaults to the padded size; entries beyond offsets[Q] are unspecified."""
+    dev = N.require_cuda(out.ids, out.scores, out.lens)
+    Q, stride = out.ids.shape
+    cap = int(cap) if cap is not None else Q * stride
+    offsets = torch.empty((Q + 1,), dtype=torch.int64, device=dev)
+    cids = torch.empty((cap,), dtype=torch.int32, device=dev)
+    csc = torch.empty((cap,), dtype=torch.float64, device=dev)
+    nbytes = N.lib().qf_compact_workspace_bytes(Q)
+    ws = torch.empty((max(nbytes, 8),), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        N.check(N.lib().qf_compact_fused(N.ptr(out.ids), N.ptr(out.scores), N.ptr(out.lens), Q, stride, N.ptr(offsets),
+                                         N.ptr(cids), N.ptr(csc), N.ptr(ws), nbytes, N.stream_ptr(dev)))
+    return offsets, cids, csc
+
+
 # ---------------------------------------------------------------------------------------------- qpp
 @torch.library.custom_op("qppfusion::qpp_stats", mutates_args=())
 def _qpp_stats_op(scores: torch.Tensor, lens: torch.Tensor, text_feats: torch.Tensor,

@@ -183,3 +183,22 @@ def test_golden_reference_vectors_through_cuda():
                     got[opos[qi, j]] = (inv[int(oid[qi, j])], float(osc[qi, j]))
                 exp = [(d, float(s) + 0.0) for d, s in ref]
                 assert got == exp, (case["name"], key, qid)
+
+
+def test_compact_fused_csr():
+    from qppfusion import ops
+    lists = synth_lists(41, n_q=300, n_r=5, k=40, pool=90, ragged=True)
+    lists[7] = [[], [], [], [], []]
+    ids, sc, ranks, lens = pack_lists(lists, k=40, score_type="micro")
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.from_numpy(a).to(dev)
+    w = torch.ones((300, 5), dtype=torch.float64, device=dev)
+    out = ops.fuse(t(ids), t(sc), t(lens), w, None, 0, 0, 60.0, 0)
+    off, cids, csc = ops.compact_fused(out)
+    off = off.cpu().numpy()
+    n = out.lens.cpu().numpy()
+    assert off[0] == 0 and np.array_equal(np.diff(off), n)
+    oi, os_ = out.ids.cpu().numpy(), out.scores.cpu().numpy()
+    ci, cs = cids.cpu().numpy(), csc.cpu().numpy()
+    for q in range(300):
+        assert np.array_equal(ci[off[q]:off[q + 1]], oi[q, :n[q]]) and np.array_equal(cs[off[q]:off[q + 1]], os_[q, :n[q]])
