@@ -51,10 +51,12 @@ struct DenseParams {
   int chunk_tiles;                // vtiles per work unit
   int mode;
   const float* tau;               // [Q]            (FILTER)
-  float* cand_score;              // [Q, cand_cap]  (FILTER)
-  int* cand_id;                   // [Q, cand_cap]
-  int* cand_cnt;                  // [Q]
-  int cand_cap;
+  // FILTER output: every epilogue thread owns a private segment per work unit, so survivors are written with
+  // plain stores (no atomics, no round trips): segment s = (chunk*2 + half)*q_pad + q holds seg_cnt[s]
+  // (score bits, doc id) pairs, capacity SEG_T; a count > SEG_T flags the query for the exact fallback.
+  uint2* seg_pairs;               // [n_chunks*2*q_pad, SEG_T]
+  int* seg_cnt;                   // [n_chunks*2*q_pad]
+  int q_pad;                      // n_mtiles * 128
   float* store;                   // [n_mtiles*128, store_ld]  (STORE): column = vtile*64 + j
   long long store_ld;
 };
@@ -150,7 +152,7 @@ __device__ __forceinline__ u64 make_desc_sw128(u32 saddr) {
 // instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=64
 constexpr u32 IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((u32)(BN >> 3) << 17) | ((u32)(BM >> 4) << 24);
 
-constexpr int STAGE_N = 8;                // staged candidates per epilogue thread before a flush
+constexpr int SEG_T = 48;                 // private candidate segment per (work unit, epilogue thread)
 
 struct __align__(8) DenseSmemCtl {
   u64 full[NSLOT];
@@ -160,27 +162,12 @@ struct __align__(8) DenseSmemCtl {
   u64 a_ready;
   u32 tmem_base;
   u32 pad;
-  uint2 stage[EPI_THREADS * STAGE_N];     // (score bits, doc id), [slot][thread] so a warp's stores hit 32 banks
 };
 
 __device__ __forceinline__ u32 elect_one() {
   u32 pred;
   asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
   return pred;
-}
-
-// Move a thread's staged candidates to its query's global candidate list: one returning atomic per
-// STAGE_N survivors.  (Out of line: it sits inside an unrolled loop and would blow the instruction cache.)
-__device__ __noinline__ void flush_stage(float* cand_score, int* cand_id, int* cand_cnt, int cand_cap,
-                                         const uint2* stage, int et, int q, int n_staged) {
-  const int pos = atomicAdd(cand_cnt + q, n_staged);
-  for (int i = 0; i < n_staged; ++i) {
-    if (pos + i < cand_cap) {
-      const uint2 e = stage[i * EPI_THREADS + et];
-      cand_score[(size_t)q * cand_cap + pos + i] = __uint_as_float(e.x);
-      cand_id[(size_t)q * cand_cap + pos + i] = (int)e.y;
-    }
-  }
 }
 
 __global__ void __launch_bounds__(NT, 1) dense_kernel(const __grid_constant__ CUtensorMap tmap, const DenseParams p) {
@@ -263,6 +250,21 @@ __global__ void __launch_bounds__(NT, 1) dense_kernel(const __grid_constant__ CU
             const u64 desc = desc0 + (u64)(slot * (SLOT_BYTES >> 4));
             const u32 ta = tmem_base + kb * BK;      // 128 k-elements = 64 TMEM columns per step
             const bool two = (kb * 2 + 1) * BK < p.D;
+#ifdef QF_EXPERIMENT_SPLIT_N
+            constexpr u32 IDESC32 = (1u << 4) | (1u << 7) | (1u << 10) | ((u32)(32 >> 3) << 17) | ((u32)(BM >> 4) << 24);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              umma_ts(tmem_d, ta + k * 8, desc + (u64)(k * 2), IDESC32, (kb | k) != 0);
+              umma_ts(tmem_d + 32, ta + k * 8, desc + (u64)(k * 2 + 256), IDESC32, (kb | k) != 0);
+            }
+            if (two) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                umma_ts(tmem_d, ta + 32 + k * 8, desc + (u64)((BOX_BYTES >> 4) + k * 2), IDESC32, 1u);
+                umma_ts(tmem_d + 32, ta + 32 + k * 8, desc + (u64)((BOX_BYTES >> 4) + k * 2 + 256), IDESC32, 1u);
+              }
+            }
+#else
 #pragma unroll
             for (int k = 0; k < 4; ++k)              // +32 B in the B descriptor, +8 columns in the TMEM A operand
               umma_ts(tmem_d, ta + k * 8, desc + (u64)(k * 2), IDESC, (kb | k) != 0);
@@ -271,6 +273,7 @@ __global__ void __launch_bounds__(NT, 1) dense_kernel(const __grid_constant__ CU
               for (int k = 0; k < 4; ++k)
                 umma_ts(tmem_d, ta + 32 + k * 8, desc + (u64)((BOX_BYTES >> 4) + k * 2), IDESC, 1u);
             }
+#endif
             umma_commit(a_empty + 8 * slot);
             if (kb == KB2 - 1) umma_commit(a_tfull + 8 * acc);
           }
@@ -282,12 +285,10 @@ __global__ void __launch_bounds__(NT, 1) dense_kernel(const __grid_constant__ CU
     }
   } else if (warp >= 4) {
     // ===================================================================== epilogue: 256 threads, 2 per query row
-    const int et = tid - 128;                          // 0..255
     const int row = ((warp & 3) << 5) | lane;          // TMEM lane == query row of the tile
     const int half = (warp - 4) >> 2;                  // accumulator columns [32*half, 32*half+32)
     const u32 lane_base = (u32)((warp & 3) * 32) << 16;
-    uint2* stage = ctl->stage;
-    int acc = 0, cur_m = -1, n_staged = 0;
+    int acc = 0, cur_m = -1;
     u32 acc_phase = 0;
     float tau = INFINITY;
     int q = 0;
@@ -296,7 +297,6 @@ __global__ void __launch_bounds__(NT, 1) dense_kernel(const __grid_constant__ CU
       const int t0 = c * p.chunk_tiles, t1 = min(p.n_vtiles, t0 + p.chunk_tiles);
       if (m != cur_m) {
         // every MMA that read the previous query tile has completed (its last tmem_full was consumed)
-        if (n_staged > 0) { flush_stage(p.cand_score, p.cand_id, p.cand_cnt, p.cand_cap, stage, et, q, n_staged); n_staged = 0; }
         q = m * BM + row;
         const bool valid = q < p.Q;
         // this thread loads half of the row's k range: 16-element groups [jb, je)
@@ -317,6 +317,9 @@ __global__ void __launch_bounds__(NT, 1) dense_kernel(const __grid_constant__ CU
         cur_m = m;
         tau = (valid && p.mode == MODE_FILTER) ? __ldg(p.tau + q) : INFINITY;
       }
+      const size_t seg = ((size_t)c * 2 + half) * p.q_pad + q;
+      uint2* seg_out = p.mode == MODE_FILTER ? p.seg_pairs + seg * SEG_T : nullptr;
+      int n_mine = 0;
       for (int t = t0; t < t1; ++t) {
         mbar_wait(a_tfull + 8 * acc, acc_phase);
         tc_fence_after();
@@ -333,11 +336,8 @@ __global__ void __launch_bounds__(NT, 1) dense_kernel(const __grid_constant__ CU
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             if (__uint_as_float(v[j]) >= tau && j < nvalid) {
-              stage[n_staged * EPI_THREADS + et] = make_uint2(v[j], (u32)(doc0 + j));
-              if (++n_staged == STAGE_N) {
-                flush_stage(p.cand_score, p.cand_id, p.cand_cnt, p.cand_cap, stage, et, q, STAGE_N);
-                n_staged = 0;
-              }
+              if (n_mine < SEG_T) seg_out[n_mine] = make_uint2(v[j], (u32)(doc0 + j));
+              ++n_mine;
             }
           }
         } else {
@@ -348,8 +348,8 @@ __global__ void __launch_bounds__(NT, 1) dense_kernel(const __grid_constant__ CU
                                  __uint_as_float(v[4 * j + 3]));
         }
       }
+      if (p.mode == MODE_FILTER) p.seg_cnt[seg] = n_mine;      // > SEG_T flags an overflowed segment
     }
-    if (n_staged > 0) flush_stage(p.cand_score, p.cand_id, p.cand_cnt, p.cand_cap, stage, et, q, n_staged);
   }
 
   tc_fence_before();
@@ -502,9 +502,13 @@ constexpr int SEL_NT = 512;
 constexpr int SEL_ROUNDS = (SEL_CAP / 32 + SEL_NT / 32 - 1) / (SEL_NT / 32);
 
 struct SelectParams {
+  // source A (FILTER pass): per-(unit, thread) private segments, see DenseParams
+  const uint2* seg_pairs;
+  const int* seg_cnt;
+  int n_segs, q_pad;
+  // source B (multi-GPU merge): nseg already-ranked segments of seg_len entries
   const float* cand_score;
   const int* cand_id;
-  const int* cand_cnt;     // nullable: n = nseg * seg_len
   long long q_stride;      // element stride between queries
   long long seg_stride;    // element stride between segments
   int nseg, seg_len;
@@ -608,27 +612,54 @@ __global__ void __launch_bounds__(SEL_NT, 1) select_kernel(const SelectParams p)
   __shared__ int flag_single, flag_long;
   const int tid = threadIdx.x;
 
+  __shared__ int s_n, s_flag;
   for (int q = blockIdx.x; q < p.Q; q += gridDim.x) {
-    int n_raw = p.cand_cnt ? p.cand_cnt[q] : p.nseg * p.seg_len;
     int status = 0;
+    int n = 0;
     const int want = min(p.k, p.N_total);
-    if (n_raw > SEL_CAP) { status |= 2; n_raw = SEL_CAP; }
-    const int n = n_raw;
-    if (n < want) status |= 1;
-    const int n_pad = (n + 31) & ~31;
-    for (int i = tid; i < n_pad; i += SEL_NT) {
-      float s = -INFINITY;
-      int id = 0x7fffffff;
-      if (i < n) {
-        const int seg = p.cand_cnt ? 0 : i / p.seg_len;
-        const int off = p.cand_cnt ? i : i % p.seg_len;
-        const size_t a = (size_t)q * p.q_stride + (size_t)seg * p.seg_stride + off;
-        s = p.cand_score[a];
-        id = p.cand_id[a];
-        if (id < 0) { s = -INFINITY; id = 0x7fffffff; }         // padding of a short segment
+    if (p.seg_pairs) {
+      // gather the query's private segments: one warp per segment, offsets from a shared counter
+      if (tid == 0) { s_n = 0; s_flag = 0; }
+      __syncthreads();
+      const int warp = tid >> 5, lane = tid & 31;
+      for (int sg = warp; sg < p.n_segs; sg += SEL_NT / 32) {
+        const size_t seg = (size_t)sg * p.q_pad + q;
+        int c = p.seg_cnt[seg];
+        if (c > SEG_T) { c = SEG_T; if (lane == 0) s_flag = 2; }     // a unit overflowed its private segment
+        int base = 0;
+        if (lane == 0 && c > 0) base = atomicAdd(&s_n, c);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        for (int i = lane; i < c; i += 32) {
+          if (base + i < SEL_CAP) {
+            const uint2 e = p.seg_pairs[seg * SEG_T + i];
+            S.score[base + i] = __uint_as_float(e.x);
+            S.id[base + i] = (int)e.y;
+          }
+        }
       }
-      S.score[i] = s;
-      S.id[i] = id;
+      __syncthreads();
+      n = s_n;
+      status |= s_flag;
+      if (n > SEL_CAP) { status |= 2; n = SEL_CAP; }
+      if (n < want) status |= 1;
+      const int n_pad = (n + 31) & ~31;
+      for (int i = n + tid; i < n_pad; i += SEL_NT) { S.score[i] = -INFINITY; S.id[i] = 0x7fffffff; }
+    } else {
+      n = p.nseg * p.seg_len;
+      if (n > SEL_CAP) { status |= 2; n = SEL_CAP; }
+      const int n_pad = (n + 31) & ~31;
+      for (int i = tid; i < n_pad; i += SEL_NT) {
+        float s = -INFINITY;
+        int id = 0x7fffffff;
+        if (i < n) {
+          const size_t a = (size_t)q * p.q_stride + (size_t)(i / p.seg_len) * p.seg_stride + (i % p.seg_len);
+          s = p.cand_score[a];
+          id = p.cand_id[a];
+          if (id < 0) { s = -INFINITY; id = 0x7fffffff; }         // padding of a short segment
+        }
+        S.score[i] = s;
+        S.id[i] = id;
+      }
     }
     __syncthreads();
     const u16* order = rank_candidates(S, n, warp_tot, &flag_single, &flag_long);
@@ -762,23 +793,39 @@ int get_encode_fn(EncodeTiledFn* out) {
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 struct DenseWs {
-  size_t off_cnt, off_tau, off_cscore, off_cid, off_sample, total;
-  int n_sample_tiles;
+  size_t off_tau, off_segcnt, off_segpairs, off_sample, total;
+  int n_sample_tiles, chunk_tiles, n_chunks;
   long long sample_ld;
 };
 
-DenseWs plan_ws(int Q, int N) {
+// main-pass chunking: with a sampled threshold a thread sees ~12 survivors per 256-tile unit (SEG_T = 48 leaves
+// 4x head-room; overflow is flagged and repaired exactly); without a threshold (tiny corpora, tau = -inf) every
+// document survives, so units are single tiles (32 documents per epilogue thread <= SEG_T).
+int cand_target(int k) { return 3 * k + 1000; }   // candidates the sampled threshold aims to admit per query
+
+int main_chunk_tiles(int N, int k) {
+  if (N <= SEL_CAP) return 1;
+  // expected survivors per epilogue thread and unit = chunk_tiles * 32 docs * target / N  <=  SEG_T / 4
+  long long c = (long long)(SEG_T / 4) * N / (32LL * cand_target(k));
+  if (c < 1) c = 1;
+  if (c > 256) c = 256;
+  return (int)c;
+}
+
+DenseWs plan_ws(int Q, int N, int k) {
   DenseWs w{};
   const int n_mtiles = (Q + BM - 1) / BM;
   const long long T = ((long long)N + BN - 1) / BN;
   w.n_sample_tiles = N > SEL_CAP ? (int)(T < 512 ? T : 512) : 0;
   w.sample_ld = (long long)w.n_sample_tiles * BN;
+  w.chunk_tiles = main_chunk_tiles(N, k);
+  w.n_chunks = (int)((T + w.chunk_tiles - 1) / w.chunk_tiles);
+  const size_t n_seg = (size_t)w.n_chunks * 2 * n_mtiles * BM;
   size_t o = 0;
-  w.off_cnt = o;    o = align_up(o + sizeof(int) * (size_t)Q, 256);
-  w.off_tau = o;    o = align_up(o + sizeof(float) * (size_t)Q, 256);
-  w.off_cscore = o; o = align_up(o + sizeof(float) * (size_t)Q * SEL_CAP, 256);
-  w.off_cid = o;    o = align_up(o + sizeof(int) * (size_t)Q * SEL_CAP, 256);
-  w.off_sample = o; o = align_up(o + sizeof(float) * (size_t)n_mtiles * BM * (size_t)w.sample_ld, 256);
+  w.off_tau = o;      o = align_up(o + sizeof(float) * (size_t)Q, 256);
+  w.off_segcnt = o;   o = align_up(o + sizeof(int) * n_seg, 256);
+  w.off_segpairs = o; o = align_up(o + sizeof(uint2) * n_seg * SEG_T, 256);
+  w.off_sample = o;   o = align_up(o + sizeof(float) * (size_t)n_mtiles * BM * (size_t)w.sample_ld, 256);
   w.total = o;
   return w;
 }
@@ -789,7 +836,7 @@ constexpr size_t DENSE_SMEM = (size_t)NSLOT * SLOT_BYTES + sizeof(DenseSmemCtl) 
 
 extern "C" size_t qf_dense_workspace_bytes(int Q, int N, int k) {
   if (Q < 1 || N < 1 || k < 1) return 0;
-  return plan_ws(Q, N).total;
+  return plan_ws(Q, N, k).total;
 }
 
 extern "C" int qf_dense_max_k(void) { return 1024; }
@@ -807,7 +854,7 @@ extern "C" int qf_dense_topk(const void* queries_bf16, const void* corpus_bf16, 
              QF_E_INVALID, "qf_dense_topk: queries/corpus must be 16-byte aligned");
   int rc = qf::check_device();
   if (rc != QF_OK) return rc;
-  const DenseWs w = plan_ws(Q, N);
+  const DenseWs w = plan_ws(Q, N, k);
   QF_REQUIRE(ws_bytes >= w.total, QF_E_WORKSPACE, "qf_dense_topk: workspace %zu < %zu bytes", ws_bytes, w.total);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   unsigned char* base = reinterpret_cast<unsigned char*>(ws);
@@ -835,21 +882,18 @@ extern "C" int qf_dense_topk(const void* queries_bf16, const void* corpus_bf16, 
   const int sms = qf::sm_count();
   const int n_mtiles = (Q + BM - 1) / BM;
   const int T = (int)(((long long)N + BN - 1) / BN);
-  int* cnt = reinterpret_cast<int*>(base + w.off_cnt);
   float* tau = reinterpret_cast<float*>(base + w.off_tau);
 
   DenseParams p{};
   p.queries = reinterpret_cast<const __nv_bfloat16*>(queries_bf16);
   p.Q = Q; p.N = N; p.D = D; p.n_mtiles = n_mtiles;
   p.tau = tau;
-  p.cand_score = reinterpret_cast<float*>(base + w.off_cscore);
-  p.cand_id = reinterpret_cast<int*>(base + w.off_cid);
-  p.cand_cnt = cnt;
-  p.cand_cap = SEL_CAP;
+  p.seg_pairs = reinterpret_cast<uint2*>(base + w.off_segpairs);
+  p.seg_cnt = reinterpret_cast<int*>(base + w.off_segcnt);
+  p.q_pad = n_mtiles * BM;
   p.store = reinterpret_cast<float*>(base + w.off_sample);
   p.store_ld = w.sample_ld;
 
-  QF_CUDA_TRY(cudaMemsetAsync(cnt, 0, sizeof(int) * (size_t)Q, st));
   auto grid_for = [&](int n_units) { return n_units < sms ? n_units : sms; };
   if (w.n_sample_tiles > 0) {
     // threshold estimation: score a strided sample of doc tiles, take an exact order statistic per query
@@ -862,7 +906,7 @@ extern "C" int qf_dense_topk(const void* queries_bf16, const void* corpus_bf16, 
     dense_kernel<<<grid_for(units), NT, DENSE_SMEM, st>>>(tmap, p);
     qf::prof_mark(QF_PROF_DENSE_SAMPLE, 1, st);
     QF_CUDA_TRY(cudaGetLastError());
-    const int target = k * 3 + 1000;
+    const int target = cand_target(k);
     const long long s_cols = (long long)p.n_vtiles * BN;
     const bool small_j = ((long long)target * s_cols + N - 1) / N <= 128;
     qf::prof_mark(QF_PROF_DENSE_TAU, 0, st);
@@ -877,7 +921,7 @@ extern "C" int qf_dense_topk(const void* queries_bf16, const void* corpus_bf16, 
   p.mode = MODE_FILTER;
   p.n_vtiles = T;
   p.tile_step = 1;
-  p.chunk_tiles = T >= 4096 ? 256 : (T >= 256 ? 32 : 4);
+  p.chunk_tiles = w.chunk_tiles;
   {
     const int units = ((p.n_vtiles + p.chunk_tiles - 1) / p.chunk_tiles) * n_mtiles;
     qf::prof_mark(QF_PROF_DENSE_MAIN, 0, st);
@@ -886,8 +930,7 @@ extern "C" int qf_dense_topk(const void* queries_bf16, const void* corpus_bf16, 
     QF_CUDA_TRY(cudaGetLastError());
   }
   SelectParams sp{};
-  sp.cand_score = p.cand_score; sp.cand_id = p.cand_id; sp.cand_cnt = cnt;
-  sp.q_stride = SEL_CAP; sp.seg_stride = 0; sp.nseg = 1; sp.seg_len = SEL_CAP;
+  sp.seg_pairs = p.seg_pairs; sp.seg_cnt = p.seg_cnt; sp.n_segs = w.n_chunks * 2; sp.q_pad = p.q_pad;
   sp.Q = Q; sp.k = k; sp.N_total = N; sp.id_offset = id_offset;
   sp.out_scores = out_scores; sp.out_ids = out_ids; sp.out_status = out_status;
   qf::prof_mark(QF_PROF_DENSE_SELECT, 0, st);
@@ -970,7 +1013,7 @@ extern "C" int qf_topk_merge(const float* scores, const int32_t* ids, int G, int
     configured = true;
   }
   SelectParams sp{};
-  sp.cand_score = scores; sp.cand_id = ids; sp.cand_cnt = nullptr;
+  sp.seg_pairs = nullptr; sp.seg_cnt = nullptr; sp.cand_score = scores; sp.cand_id = ids;
   sp.q_stride = k; sp.seg_stride = (long long)Q * k; sp.nseg = G; sp.seg_len = k;
   sp.Q = Q; sp.k = k; sp.N_total = 0x7fffffff; sp.id_offset = 0;
   sp.out_scores = out_scores; sp.out_ids = out_ids; sp.out_status = nullptr;

@@ -33,7 +33,8 @@ def check(Q, N, D, k, seed, id_offset=0):
     qf32, cf32 = unit_rows(rng, Q, D), unit_rows(rng, N, D)
     qb, cb = to_bf16(qf32), to_bf16(cf32)
     dev = torch.device("cuda:0")
-    scores, ids, status = ops.dense_topk(qb.to(dev), cb.to(dev), k, id_offset)
+    # raw op: the fused threshold-filter path itself must succeed on ordinary data (no exact-fallback repair)
+    scores, ids, status = torch.ops.qppfusion.dense_topk(qb.to(dev), cb.to(dev), k, id_offset)
     torch.cuda.synchronize()
     scores, ids, status = scores.cpu().numpy(), ids.cpu().numpy().astype(np.int64), status.cpu().numpy()
     assert (status == 0).all(), f"threshold failures: {np.flatnonzero(status)[:10]} {status[status != 0][:10]}"
