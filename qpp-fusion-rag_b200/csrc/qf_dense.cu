@@ -57,6 +57,7 @@ struct DenseParams {
   uint2* seg_pairs;               // [n_chunks*2*q_pad, SEG_T]
   int* seg_cnt;                   // [n_chunks*2*q_pad]
   int q_pad;                      // n_mtiles * 128
+  long long* dbg;                 // optional [gridDim][8] cycle counters of the MMA issuer (profiling builds)
   float* store;                   // [n_mtiles*128, store_ld]  (STORE): column = vtile*64 + j
   long long store_ld;
 };
@@ -149,14 +150,19 @@ __device__ __forceinline__ u64 make_desc_sw128(u32 saddr) {
   return d;
 }
 
-// instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=64
-constexpr u32 IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((u32)(BN >> 3) << 17) | ((u32)(BM >> 4) << 24);
+// instruction descriptor: D=f32, A=B=bf16, both K-major, N=64, M=128 (one CTA) or 256 (CTA pair)
+template <int CG>
+struct Idesc {
+  static constexpr u32 value = (1u << 4) | (1u << 7) | (1u << 10) | ((u32)(BN >> 3) << 17) | ((u32)((BM * CG) >> 4) << 24);
+};
 
 constexpr int SEG_T = 48;                 // private candidate segment per (work unit, epilogue thread)
+constexpr int MAX_SLOTS = 24;
+constexpr u32 PEER_BIT_MASK = 0xFEFFFFFFu;   // clears the CTA-pair peer bit of a shared::cluster address -> CTA rank 0
 
 struct __align__(8) DenseSmemCtl {
-  u64 full[NSLOT];
-  u64 empty[NSLOT];
+  u64 full[MAX_SLOTS];
+  u64 empty[MAX_SLOTS];
   u64 tmem_full[2];
   u64 tmem_empty[2];
   u64 a_ready;
@@ -169,16 +175,68 @@ __device__ __forceinline__ u32 elect_one() {
   asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
   return pred;
 }
+__device__ __forceinline__ u32 cluster_ctarank() {
+  u32 r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(u32 bar, u32 rank) {
+  asm volatile("{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\tmbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
+               ::"r"(bar), "r"(rank) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(u32 smem_dst, const CUtensorMap* tmap, u32 bar, int c0, int c1) {
+  // issued by both CTAs of a pair; the transaction bytes are credited to the barrier of CTA rank 0
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_dst), "l"(reinterpret_cast<u64>(tmap)), "r"(bar & PEER_BIT_MASK), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_ts_pair(u32 tmem_d, u32 tmem_a, u64 desc_b, u32 idesc, u32 accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(u32 bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((unsigned short)3) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(u32* smem_dst, u32 ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(u32 taddr, u32 ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
 
+// CG = 1: one CTA per 128-query tile.  CG = 2: a CTA PAIR (cluster of 2, tcgen05 cta_group::2) works on two query
+// tiles against the same document tiles: each CTA TMA-loads half of every B tile (32 of the 64 documents), the
+// leader CTA issues M=256 MMAs that read both halves, so the L2->SM traffic per FLOP halves.
+template <int CG>
 __global__ void __launch_bounds__(NT, 1) dense_kernel(const __grid_constant__ CUtensorMap tmap, const DenseParams p) {
+  constexpr int BOX_ROWS = BN / CG;                 // documents this CTA loads per tile
+  constexpr int BOX_B = BOX_ROWS * BK * 2;          // bytes per TMA box
+  constexpr int SLOT_B = 2 * BOX_B;                 // pipeline slot = two boxes (128 k) behind one mbarrier
+  constexpr int NSL = 12 * CG;                      // 192 KB ring either way
+  constexpr u32 IDESC = Idesc<CG>::value;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  DenseSmemCtl* ctl = reinterpret_cast<DenseSmemCtl*>(smem + NSLOT * SLOT_BYTES);
+  DenseSmemCtl* ctl = reinterpret_cast<DenseSmemCtl*>(smem + NSL * SLOT_B);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const u32 rank = CG == 2 ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
   const int KB2 = (p.D + 2 * BK - 1) / (2 * BK);     // pipeline steps per doc tile (128 k each; last may be 64)
   const int n_chunks = (p.n_vtiles + p.chunk_tiles - 1) / p.chunk_tiles;
-  const int n_units = n_chunks * p.n_mtiles;
+  const int n_mgroups = (p.n_mtiles + CG - 1) / CG;
+  const int n_units = n_chunks * n_mgroups;
+  const int u_first = blockIdx.x / CG, u_step = gridDim.x / CG;
   // shared-window addresses (computed once; barriers are 8 bytes apart)
   const u32 a_slots = smem_u32(smem);
   const u32 a_full = smem_u32(&ctl->full[0]), a_empty = smem_u32(&ctl->empty[0]);
@@ -186,20 +244,24 @@ __global__ void __launch_bounds__(NT, 1) dense_kernel(const __grid_constant__ CU
   const u32 a_aready = smem_u32(&ctl->a_ready);
 
   if (warp == 0 && lane == 0) {
-    for (int i = 0; i < NSLOT; ++i) {
+    for (int i = 0; i < NSL; ++i) {
       mbar_init(&ctl->full[i], 1);
       mbar_init(&ctl->empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&ctl->tmem_full[i], 1);
-      mbar_init(&ctl->tmem_empty[i], EPI_THREADS);
+      mbar_init(&ctl->tmem_empty[i], EPI_THREADS * CG);
     }
-    mbar_init(&ctl->a_ready, EPI_THREADS);
+    mbar_init(&ctl->a_ready, EPI_THREADS * CG);
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(&ctl->tmem_base, TMEM_COLS);
+  if (warp == 2) {
+    if (CG == 2) tmem_alloc_pair(&ctl->tmem_base, TMEM_COLS);
+    else tmem_alloc(&ctl->tmem_base, TMEM_COLS);
+  }
   tc_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync_all();
   tc_fence_after();
   const u32 tmem_base = ctl->tmem_base;
 
@@ -207,82 +269,112 @@ __global__ void __launch_bounds__(NT, 1) dense_kernel(const __grid_constant__ CU
     // ===================================================================== TMA producer (warp-uniform, one elected lane issues)
     int slot = 0;
     u32 phase = 0;
-    for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-      const int c = u / p.n_mtiles;
+    for (int u = u_first; u < n_units; u += u_step) {
+      const int c = u / n_mgroups;
       const int t0 = c * p.chunk_tiles, t1 = min(p.n_vtiles, t0 + p.chunk_tiles);
       for (int t = t0; t < t1; ++t) {
-        const int row0 = t * p.tile_step * BN;
+        const int row0 = t * p.tile_step * BN + (int)rank * BOX_ROWS;
         for (int kb = 0; kb < KB2; ++kb) {
           mbar_wait(a_empty + 8 * slot, phase ^ 1);
           if (elect_one()) {
             const bool two = (kb * 2 + 1) * BK < p.D;
-            mbar_expect_tx(a_full + 8 * slot, two ? SLOT_BYTES : BOX_BYTES);
-            tma_load_2d(a_slots + slot * SLOT_BYTES, &tmap, a_full + 8 * slot, kb * 2 * BK, row0);
-            if (two) tma_load_2d(a_slots + slot * SLOT_BYTES + BOX_BYTES, &tmap, a_full + 8 * slot, (kb * 2 + 1) * BK, row0);
+            if (leader) mbar_expect_tx(a_full + 8 * slot, (two ? SLOT_B : BOX_B) * CG);
+            const u32 dst = a_slots + slot * SLOT_B;
+            if (CG == 2) {
+              tma_load_2d_pair(dst, &tmap, a_full + 8 * slot, kb * 2 * BK, row0);
+              if (two) tma_load_2d_pair(dst + BOX_B, &tmap, a_full + 8 * slot, (kb * 2 + 1) * BK, row0);
+            } else {
+              tma_load_2d(dst, &tmap, a_full + 8 * slot, kb * 2 * BK, row0);
+              if (two) tma_load_2d(dst + BOX_B, &tmap, a_full + 8 * slot, (kb * 2 + 1) * BK, row0);
+            }
           }
           __syncwarp();
-          if (++slot == NSLOT) { slot = 0; phase ^= 1; }
+          if (++slot == NSL) { slot = 0; phase ^= 1; }
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================================================================== MMA issuer (warp-uniform, one elected lane issues)
-    int slot = 0, acc = 0, cur_m = -1;
-    u32 phase = 0, acc_phase = 0, a_phase = 0;
+  } else if ((warp == 1 || warp == 3) && leader) {
+    // ===================================================================== MMA issuers (leader CTA)
+    // Issuing one M x 64 x 16 MMA costs the issuing thread ~25 cycles but only 32 tensor-pipe cycles, and every
+    // slot adds a barrier wait, so ONE issuer cannot keep the pipe busy (measured: 428 cycles per 256-cycle slot).
+    // Two issuer warps alternate document tiles; each owns one accumulator stage (stage == tile parity), its
+    // own accumulate chain and its own tcgen05.commit stream, and the tensor pipe interleaves the two chains.
+    const int mw = warp == 3 ? 1 : 0;
+    int cur_mg = -1;
+    u32 a_phase = 0, acc_phase = 0;
+    long long n_tile = 0;                        // tiles seen by this CTA so far (all issuers count alike)
     const u64 desc0 = make_desc_sw128(a_slots);
-    for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-      const int c = u / p.n_mtiles, m = u % p.n_mtiles;
+#ifdef QF_DENSE_TIMING
+    long long t_full = 0, t_tempty = 0, t_issue = 0, t_aready = 0, n_slots = 0;
+    const long long t_begin = clock64();
+#define QF_T0 const long long _t0 = clock64();
+#define QF_T1(var) var += clock64() - _t0;
+#else
+#define QF_T0
+#define QF_T1(var)
+#endif
+    for (int u = u_first; u < n_units; u += u_step) {
+      const int c = u / n_mgroups, mg = u % n_mgroups;
       const int t0 = c * p.chunk_tiles, t1 = min(p.n_vtiles, t0 + p.chunk_tiles);
-      if (m != cur_m) {
-        mbar_wait(a_aready, a_phase);
+      if (mg != cur_mg) {
+        { QF_T0 mbar_wait(a_aready, a_phase); QF_T1(t_aready) }
         a_phase ^= 1;
-        cur_m = m;
+        cur_mg = mg;
         tc_fence_after();
       }
-      for (int t = t0; t < t1; ++t) {
-        mbar_wait(a_tempty + 8 * acc, acc_phase ^ 1);
+      for (int t = t0; t < t1; ++t, ++n_tile) {
+        if ((int)(n_tile & 1) != mw) continue;
+        const int acc = mw;
+        { QF_T0 mbar_wait(a_tempty + 8 * acc, acc_phase ^ 1); QF_T1(t_tempty) }
         tc_fence_after();
         const u32 tmem_d = tmem_base + A_COLS + acc * BN;
+        const long long seq0 = n_tile * KB2;
         for (int kb = 0; kb < KB2; ++kb) {
-          mbar_wait(a_full + 8 * slot, phase);
+          const long long seq = seq0 + kb;
+          const int slot = (int)(seq % NSL);
+          const u32 phase = (u32)((seq / NSL) & 1);
+          { QF_T0 mbar_wait(a_full + 8 * slot, phase); QF_T1(t_full) }
           tc_fence_after();
+          QF_T0
           if (elect_one()) {
-            const u64 desc = desc0 + (u64)(slot * (SLOT_BYTES >> 4));
+            const u64 desc = desc0 + (u64)(slot * (SLOT_B >> 4));
             const u32 ta = tmem_base + kb * BK;      // 128 k-elements = 64 TMEM columns per step
             const bool two = (kb * 2 + 1) * BK < p.D;
-#ifdef QF_EXPERIMENT_SPLIT_N
-            constexpr u32 IDESC32 = (1u << 4) | (1u << 7) | (1u << 10) | ((u32)(32 >> 3) << 17) | ((u32)(BM >> 4) << 24);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              umma_ts(tmem_d, ta + k * 8, desc + (u64)(k * 2), IDESC32, (kb | k) != 0);
-              umma_ts(tmem_d + 32, ta + k * 8, desc + (u64)(k * 2 + 256), IDESC32, (kb | k) != 0);
+            for (int k = 0; k < 4; ++k) {            // +32 B in the B descriptor, +8 columns in the TMEM A operand
+              if (CG == 2) umma_ts_pair(tmem_d, ta + k * 8, desc + (u64)(k * 2), IDESC, (kb | k) != 0);
+              else umma_ts(tmem_d, ta + k * 8, desc + (u64)(k * 2), IDESC, (kb | k) != 0);
             }
             if (two) {
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
-                umma_ts(tmem_d, ta + 32 + k * 8, desc + (u64)((BOX_BYTES >> 4) + k * 2), IDESC32, 1u);
-                umma_ts(tmem_d + 32, ta + 32 + k * 8, desc + (u64)((BOX_BYTES >> 4) + k * 2 + 256), IDESC32, 1u);
+                if (CG == 2) umma_ts_pair(tmem_d, ta + 32 + k * 8, desc + (u64)((BOX_B >> 4) + k * 2), IDESC, 1u);
+                else umma_ts(tmem_d, ta + 32 + k * 8, desc + (u64)((BOX_B >> 4) + k * 2), IDESC, 1u);
               }
             }
-#else
-#pragma unroll
-            for (int k = 0; k < 4; ++k)              // +32 B in the B descriptor, +8 columns in the TMEM A operand
-              umma_ts(tmem_d, ta + k * 8, desc + (u64)(k * 2), IDESC, (kb | k) != 0);
-            if (two) {
-#pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma_ts(tmem_d, ta + 32 + k * 8, desc + (u64)((BOX_BYTES >> 4) + k * 2), IDESC, 1u);
+            if (CG == 2) {
+              umma_commit_pair(a_empty + 8 * slot);
+              if (kb == KB2 - 1) umma_commit_pair(a_tfull + 8 * acc);
+            } else {
+              umma_commit(a_empty + 8 * slot);
+              if (kb == KB2 - 1) umma_commit(a_tfull + 8 * acc);
             }
-#endif
-            umma_commit(a_empty + 8 * slot);
-            if (kb == KB2 - 1) umma_commit(a_tfull + 8 * acc);
           }
           __syncwarp();
-          if (++slot == NSLOT) { slot = 0; phase ^= 1; }
+          QF_T1(t_issue)
+#ifdef QF_DENSE_TIMING
+          ++n_slots;
+#endif
         }
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        acc_phase ^= 1;
       }
     }
+#ifdef QF_DENSE_TIMING
+    if (p.dbg && lane == 0 && mw == 0) {
+      long long* d = p.dbg + (size_t)blockIdx.x * 8;
+      d[0] = clock64() - t_begin; d[1] = t_full; d[2] = t_tempty; d[3] = t_issue; d[4] = t_aready; d[5] = n_slots;
+    }
+#endif
   } else if (warp >= 4) {
     // ===================================================================== epilogue: 256 threads, 2 per query row
     const int row = ((warp & 3) << 5) | lane;          // TMEM lane == query row of the tile
@@ -292,8 +384,8 @@ __global__ void __launch_bounds__(NT, 1) dense_kernel(const __grid_constant__ CU
     u32 acc_phase = 0;
     float tau = INFINITY;
     int q = 0;
-    for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-      const int c = u / p.n_mtiles, m = u % p.n_mtiles;
+    for (int u = u_first; u < n_units; u += u_step) {
+      const int c = u / n_mgroups, m = (u % n_mgroups) * CG + (int)rank;
       const int t0 = c * p.chunk_tiles, t1 = min(p.n_vtiles, t0 + p.chunk_tiles);
       if (m != cur_m) {
         // every MMA that read the previous query tile has completed (its last tmem_full was consumed)
@@ -313,7 +405,8 @@ __global__ void __launch_bounds__(NT, 1) dense_kernel(const __grid_constant__ CU
         }
         tmem_wait_st();
         tc_fence_before();
-        mbar_arrive(a_aready);
+        if (leader) mbar_arrive(a_aready);
+        else mbar_arrive_remote(a_aready, 0);
         cur_m = m;
         tau = (valid && p.mode == MODE_FILTER) ? __ldg(p.tau + q) : INFINITY;
       }
@@ -327,7 +420,8 @@ __global__ void __launch_bounds__(NT, 1) dense_kernel(const __grid_constant__ CU
         tmem_ld32(tmem_base + lane_base + A_COLS + acc * BN + half * 32, v);
         tmem_wait_ld();
         tc_fence_before();
-        mbar_arrive(a_tempty + 8 * acc);        // accumulator stage is free again
+        if (leader) mbar_arrive(a_tempty + 8 * acc);        // accumulator stage is free again
+        else mbar_arrive_remote(a_tempty + 8 * acc, 0);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
 
         const int doc0 = t * p.tile_step * BN + half * 32;
@@ -340,7 +434,7 @@ __global__ void __launch_bounds__(NT, 1) dense_kernel(const __grid_constant__ CU
               ++n_mine;
             }
           }
-        } else {
+        } else if (m < p.n_mtiles) {
           float4* dst = reinterpret_cast<float4*>(p.store + (size_t)(m * BM + row) * p.store_ld + (size_t)t * BN + half * 32);
 #pragma unroll
           for (int j = 0; j < 8; ++j)
@@ -348,15 +442,17 @@ __global__ void __launch_bounds__(NT, 1) dense_kernel(const __grid_constant__ CU
                                  __uint_as_float(v[4 * j + 3]));
         }
       }
-      if (p.mode == MODE_FILTER) p.seg_cnt[seg] = n_mine;      // > SEG_T flags an overflowed segment
+      if (p.mode == MODE_FILTER && m < p.n_mtiles) p.seg_cnt[seg] = n_mine;      // > SEG_T flags an overflowed segment
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync_all();       // neither CTA may exit (or free TMEM) while its peer still uses it
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if (CG == 2) tmem_dealloc_pair(tmem_base, TMEM_COLS);
+    else tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
@@ -790,6 +886,80 @@ int get_encode_fn(EncodeTiledFn* out) {
   return QF_OK;
 }
 
+int make_corpus_tmap(const void* corpus, int N, int D, int box_rows, CUtensorMap* tmap) {
+  EncodeTiledFn encode;
+  int rc = get_encode_fn(&encode);
+  if (rc != QF_OK) return rc;
+  cuuint64_t gdim[2] = {(cuuint64_t)D, (cuuint64_t)N};
+  cuuint64_t gstride[1] = {(cuuint64_t)D * 2};
+  cuuint32_t box[2] = {BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = encode(tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(corpus), gdim, gstride, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  QF_REQUIRE(r == CUDA_SUCCESS, QF_E_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return QF_OK;
+}
+
+struct DenseMaps {
+  CUtensorMap one;    // 64-document boxes (single CTA)
+  CUtensorMap pair;   // 32-document boxes (each CTA of a pair loads half a tile)
+};
+
+constexpr size_t DENSE_SMEM_BYTES = (size_t)12 * 16384 + 512 + 1024;
+
+// Launch the scoring kernel: CTA pairs (cta_group::2) when there are at least two query tiles, else single CTAs.
+int launch_dense(const DenseMaps& maps, const DenseParams& p_in, cudaStream_t st) {
+  DenseParams p = p_in;
+#ifdef QF_DENSE_TIMING
+  static long long* dbg = nullptr;
+  if (!dbg) cudaMalloc(&dbg, sizeof(long long) * 8 * 256);
+  p.dbg = dbg;
+#endif
+  static bool configured = false;
+  if (!configured) {
+    QF_CUDA_TRY(cudaFuncSetAttribute(dense_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DENSE_SMEM_BYTES));
+    QF_CUDA_TRY(cudaFuncSetAttribute(dense_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DENSE_SMEM_BYTES));
+    configured = true;
+  }
+  const int sms = qf::sm_count();
+  const int n_chunks = (p.n_vtiles + p.chunk_tiles - 1) / p.chunk_tiles;
+  const bool force1 = getenv("QF_DENSE_SINGLE_CTA") != nullptr;
+  if (p.n_mtiles >= 2 && !force1) {
+    const int units = n_chunks * ((p.n_mtiles + 1) / 2);
+    int clusters = sms / 2;
+    if (clusters > units) clusters = units;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * clusters);
+    cfg.blockDim = dim3(NT);
+    cfg.dynamicSmemBytes = DENSE_SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    QF_CUDA_TRY(cudaLaunchKernelEx(&cfg, dense_kernel<2>, maps.pair, p));
+  } else {
+    const int units = n_chunks * p.n_mtiles;
+    dense_kernel<1><<<units < sms ? units : sms, NT, DENSE_SMEM_BYTES, st>>>(maps.one, p);
+  }
+  QF_CUDA_TRY(cudaGetLastError());
+#ifdef QF_DENSE_TIMING
+  if (p.mode == MODE_FILTER && p.n_vtiles > 10000) {
+    static long long h[8 * 256];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost);
+    for (int b = 0; b < 4; ++b)
+      fprintf(stderr, "[dense timing] cta %d: total %lld  wait_full %lld  wait_tmem_empty %lld  issue %lld  wait_a %lld  slots %lld\n",
+              b * 2, h[b * 16], h[b * 16 + 1], h[b * 16 + 2], h[b * 16 + 3], h[b * 16 + 4], h[b * 16 + 5]);
+  }
+#endif
+  return QF_OK;
+}
+
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 struct DenseWs {
@@ -830,7 +1000,7 @@ DenseWs plan_ws(int Q, int N, int k) {
   return w;
 }
 
-constexpr size_t DENSE_SMEM = (size_t)NSLOT * SLOT_BYTES + sizeof(DenseSmemCtl) + 1024;
+constexpr size_t DENSE_SMEM = (size_t)12 * 16384 + sizeof(DenseSmemCtl) + 1024;
 
 }  // namespace
 
@@ -859,23 +1029,13 @@ extern "C" int qf_dense_topk(const void* queries_bf16, const void* corpus_bf16, 
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   unsigned char* base = reinterpret_cast<unsigned char*>(ws);
 
-  EncodeTiledFn encode;
-  rc = get_encode_fn(&encode);
+  DenseMaps maps;
+  rc = make_corpus_tmap(corpus_bf16, N, D, BN, &maps.one);
   if (rc != QF_OK) return rc;
-  CUtensorMap tmap;
-  {
-    cuuint64_t gdim[2] = {(cuuint64_t)D, (cuuint64_t)N};
-    cuuint64_t gstride[1] = {(cuuint64_t)D * 2};
-    cuuint32_t box[2] = {BK, BN};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(corpus_bf16), gdim, gstride, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    QF_REQUIRE(r == CUDA_SUCCESS, QF_E_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
-  }
+  rc = make_corpus_tmap(corpus_bf16, N, D, BN / 2, &maps.pair);
+  if (rc != QF_OK) return rc;
   static bool configured = false;
   if (!configured) {
-    QF_CUDA_TRY(cudaFuncSetAttribute(dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DENSE_SMEM));
     QF_CUDA_TRY(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SEL_SMEM));
     configured = true;
   }
@@ -903,9 +1063,9 @@ extern "C" int qf_dense_topk(const void* queries_bf16, const void* corpus_bf16, 
     p.chunk_tiles = 16;
     const int units = ((p.n_vtiles + p.chunk_tiles - 1) / p.chunk_tiles) * n_mtiles;
     qf::prof_mark(QF_PROF_DENSE_SAMPLE, 0, st);
-    dense_kernel<<<grid_for(units), NT, DENSE_SMEM, st>>>(tmap, p);
+    rc = launch_dense(maps, p, st);
     qf::prof_mark(QF_PROF_DENSE_SAMPLE, 1, st);
-    QF_CUDA_TRY(cudaGetLastError());
+    if (rc != QF_OK) return rc;
     const int target = cand_target(k);
     const long long s_cols = (long long)p.n_vtiles * BN;
     const bool small_j = ((long long)target * s_cols + N - 1) / N <= 128;
@@ -925,9 +1085,9 @@ extern "C" int qf_dense_topk(const void* queries_bf16, const void* corpus_bf16, 
   {
     const int units = ((p.n_vtiles + p.chunk_tiles - 1) / p.chunk_tiles) * n_mtiles;
     qf::prof_mark(QF_PROF_DENSE_MAIN, 0, st);
-    dense_kernel<<<grid_for(units), NT, DENSE_SMEM, st>>>(tmap, p);
+    rc = launch_dense(maps, p, st);
     qf::prof_mark(QF_PROF_DENSE_MAIN, 1, st);
-    QF_CUDA_TRY(cudaGetLastError());
+    if (rc != QF_OK) return rc;
   }
   SelectParams sp{};
   sp.seg_pairs = p.seg_pairs; sp.seg_cnt = p.seg_cnt; sp.n_segs = w.n_chunks * 2; sp.q_pad = p.q_pad;
@@ -951,21 +1111,11 @@ extern "C" int qf_dense_scores(const void* queries_bf16, const void* corpus_bf16
   QF_REQUIRE(queries_bf16 && corpus_bf16 && out, QF_E_INVALID, "qf_dense_scores: null pointer argument");
   int rc = qf::check_device();
   if (rc != QF_OK) return rc;
-  EncodeTiledFn encode;
-  rc = get_encode_fn(&encode);
+  DenseMaps maps;
+  rc = make_corpus_tmap(corpus_bf16, N, D, BN, &maps.one);
   if (rc != QF_OK) return rc;
-  CUtensorMap tmap;
-  {
-    cuuint64_t gdim[2] = {(cuuint64_t)D, (cuuint64_t)N};
-    cuuint64_t gstride[1] = {(cuuint64_t)D * 2};
-    cuuint32_t box[2] = {BK, BN};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(corpus_bf16), gdim, gstride, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    QF_REQUIRE(r == CUDA_SUCCESS, QF_E_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
-  }
-  QF_CUDA_TRY(cudaFuncSetAttribute(dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DENSE_SMEM));
+  rc = make_corpus_tmap(corpus_bf16, N, D, BN / 2, &maps.pair);
+  if (rc != QF_OK) return rc;
   DenseParams p{};
   p.queries = reinterpret_cast<const __nv_bfloat16*>(queries_bf16);
   p.Q = Q; p.N = N; p.D = D;
@@ -976,11 +1126,7 @@ extern "C" int qf_dense_scores(const void* queries_bf16, const void* corpus_bf16
   p.chunk_tiles = T >= 4096 ? 256 : (T >= 256 ? 32 : 4);
   p.store = out;
   p.store_ld = ld;
-  const int units = ((p.n_vtiles + p.chunk_tiles - 1) / p.chunk_tiles) * p.n_mtiles;
-  const int sms = qf::sm_count();
-  dense_kernel<<<units < sms ? units : sms, NT, DENSE_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(tmap, p);
-  QF_CUDA_TRY(cudaGetLastError());
-  return QF_OK;
+  return launch_dense(maps, p, reinterpret_cast<cudaStream_t>(stream));
 }
 
 extern "C" int qf_dense_row_topk(const float* scores, long long ld, const int32_t* rows, int n_rows, int N, int k,
