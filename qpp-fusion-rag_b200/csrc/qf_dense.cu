@@ -18,6 +18,8 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 
+#include <algorithm>
+
 #include "qf_common.cuh"
 #include "qf_radix.cuh"
 
@@ -41,6 +43,7 @@ constexpr int EPI_THREADS = 256;        // 2 threads per query row (32 accumulat
 
 constexpr int MODE_FILTER = 0;
 constexpr int MODE_STORE = 1;
+constexpr int MODE_TILEMAX = 2;   // store only max over each thread's 32 columns: store[row][vtile*2 + half]
 
 struct DenseParams {
   const __nv_bfloat16* queries;   // [Q, D]
@@ -52,11 +55,13 @@ struct DenseParams {
   int mode;
   const float* tau;               // [Q]            (FILTER)
   // FILTER output: every epilogue thread owns a private segment per work unit, so survivors are written with
-  // plain stores (no atomics, no round trips): segment s = (chunk*2 + half)*q_pad + q holds seg_cnt[s]
+  // plain stores (no atomics, no round trips): segment s = q*n_segs + chunk*2 + half holds seg_cnt[s]
   // (score bits, doc id) pairs, capacity SEG_T; a count > SEG_T flags the query for the exact fallback.
-  uint2* seg_pairs;               // [n_chunks*2*q_pad, SEG_T]
-  int* seg_cnt;                   // [n_chunks*2*q_pad]
+  // Query-major, so the select kernel reads one query's counts and candidates from one contiguous region.
+  uint2* seg_pairs;               // [q_pad*n_segs, SEG_T]
+  int* seg_cnt;                   // [q_pad*n_segs]
   int q_pad;                      // n_mtiles * 128
+  int n_segs;                     // n_chunks * 2
   long long* dbg;                 // optional [gridDim][8] cycle counters of the MMA issuer (profiling builds)
   float* store;                   // [n_mtiles*128, store_ld]  (STORE): column = vtile*64 + j
   long long store_ld;
@@ -410,7 +415,7 @@ __global__ void __launch_bounds__(NT, 1) dense_kernel(const __grid_constant__ CU
         cur_m = m;
         tau = (valid && p.mode == MODE_FILTER) ? __ldg(p.tau + q) : INFINITY;
       }
-      const size_t seg = ((size_t)c * 2 + half) * p.q_pad + q;
+      const size_t seg = (size_t)q * p.n_segs + (size_t)c * 2 + half;
       uint2* seg_out = p.mode == MODE_FILTER ? p.seg_pairs + seg * SEG_T : nullptr;
       int n_mine = 0;
       for (int t = t0; t < t1; ++t) {
@@ -434,6 +439,12 @@ __global__ void __launch_bounds__(NT, 1) dense_kernel(const __grid_constant__ CU
               ++n_mine;
             }
           }
+        } else if (p.mode == MODE_TILEMAX) {
+          const int nvalid = p.N - doc0;
+          float mx = -INFINITY;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) mx = (j < nvalid) ? fmaxf(mx, __uint_as_float(v[j])) : mx;
+          if (m < p.n_mtiles) p.store[(size_t)(m * BM + row) * p.store_ld + (size_t)t * 2 + half] = mx;
         } else if (m < p.n_mtiles) {
           float4* dst = reinterpret_cast<float4*>(p.store + (size_t)(m * BM + row) * p.store_ld + (size_t)t * BN + half * 32);
 #pragma unroll
@@ -584,6 +595,35 @@ __global__ void __launch_bounds__(512) tau_kernel_small(const float* sample, lon
   if (tid == 0) tau[q] = buf[jj - 1];
 }
 
+// descending bitonic sort of 1024 floats in shared memory by 512 threads
+__device__ __forceinline__ void bitonic1024_desc(float* v, int tid) {
+  for (int k = 2; k <= 1024; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      // thread t handles the pair (i, i ^ j) with i = the t-th index whose bit j is clear
+      const int i = ((tid & ~(j - 1)) << 1) | (tid & (j - 1));
+      const int ixj = i | j;
+      const float a = v[i], b = v[ixj];
+      const bool desc = (i & k) == 0;
+      if (desc ? (a < b) : (a > b)) { v[i] = b; v[ixj] = a; }
+      __syncthreads();
+    }
+  }
+}
+
+// tau[q] = the jj-th largest of the per-(sample tile, column half) maxima written by MODE_TILEMAX: a lower bound
+// of the jj-th largest sample score (equal unless two of the top jj fall into the same 32-document bucket), so
+// the threshold errs towards admitting a few more candidates.  n_vals = 2 * n_sample_tiles <= 1024.
+__global__ void __launch_bounds__(512) tau_kernel_tilemax(const float* vals, long long ld, int n_vals, int jj, int Q, float* tau) {
+  __shared__ float buf[1024];
+  const int q = blockIdx.x, tid = threadIdx.x;
+  if (q >= Q) return;
+  const float* row = vals + (size_t)q * ld;
+  for (int i = tid; i < 1024; i += 512) buf[i] = i < n_vals ? row[i] : -INFINITY;
+  __syncthreads();
+  bitonic1024_desc(buf, tid);
+  if (tid == 0) tau[q] = buf[jj - 1];
+}
+
 __global__ void fill_kernel(float* p, int n, float v) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
@@ -601,7 +641,7 @@ struct SelectParams {
   // source A (FILTER pass): per-(unit, thread) private segments, see DenseParams
   const uint2* seg_pairs;
   const int* seg_cnt;
-  int n_segs, q_pad;
+  int n_segs;
   // source B (multi-GPU merge): nseg already-ranked segments of seg_len entries
   const float* cand_score;
   const int* cand_id;
@@ -632,6 +672,71 @@ __device__ __forceinline__ SelSmem carve_sel(unsigned char* sm) {
   s.idxB = reinterpret_cast<u16*>(sm + 18 * SEL_CAP);
   s.whist = reinterpret_cast<u16*>(sm + 20 * SEL_CAP);
   return s;
+}
+
+// Keep only candidates that can be among the `keep` best (score desc): MSB-first radix select of the keep-th
+// largest score on the order-preserving integer image, then an in-smem compaction of everything >= it
+// (all ties of the boundary score are kept, so exactness is untouched).  Returns the new count.
+__device__ int prefilter_topk(const SelSmem& S, int n, int keep, int* s_scratch /* >= 260 ints */) {
+  const int tid = threadIdx.x;
+  if (n <= keep + keep / 2) return n;
+  int* hist = s_scratch;            // [256]
+  int* ctl = s_scratch + 256;       // [0] prefix, [1] remaining, [2] out count
+  u32 prefix = 0;
+  int remaining = keep;
+  for (int pass = 0; pass < 4; ++pass) {
+    const int shift = 24 - 8 * pass;
+    const u32 mask_hi = pass == 0 ? 0u : (0xFFFFFFFFu << (shift + 8));
+    for (int i = tid; i < 256; i += SEL_NT) hist[i] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += SEL_NT) {
+      const u32 key = ~ord_f32(S.score[i] + 0.0f);            // ascending key = descending score
+      if ((key & mask_hi) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1);
+    }
+    __syncthreads();
+    if (tid < 32) {
+      // warp 0: find the digit whose cumulative count reaches `remaining`
+      int c[8], tot = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { c[j] = hist[tid * 8 + j]; tot += c[j]; }
+      int incl = tot;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t_ = __shfl_up_sync(0xffffffffu, incl, o);
+        if (tid >= o) incl += t_;
+      }
+      int run = incl - tot;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (run < remaining && run + c[j] >= remaining) { ctl[0] = (int)(prefix | ((u32)(tid * 8 + j) << shift)); ctl[1] = remaining - run; }
+        run += c[j];
+      }
+    }
+    __syncthreads();
+    prefix = (u32)ctl[0];
+    remaining = ctl[1];
+    __syncthreads();
+  }
+  // compaction into (keyA: score bits, keyB: id), then back
+  if (tid == 0) ctl[2] = 0;
+  __syncthreads();
+  for (int i = tid; i < n; i += SEL_NT) {
+    const float sc = S.score[i];
+    if (~ord_f32(sc + 0.0f) <= prefix) {
+      const int pos = atomicAdd(&ctl[2], 1);
+      S.keyA[pos] = __float_as_uint(sc);
+      S.keyB[pos] = (u32)S.id[i];
+    }
+  }
+  __syncthreads();
+  const int m = ctl[2];
+  const int m_pad = (m + 31) & ~31;
+  for (int i = tid; i < m_pad; i += SEL_NT) {
+    S.score[i] = i < m ? __uint_as_float(S.keyA[i]) : -INFINITY;
+    S.id[i] = i < m ? (int)S.keyB[i] : 0x7fffffff;
+  }
+  __syncthreads();
+  return m;
 }
 
 // Rank the n candidates held in (S.score, S.id) by (score desc, id asc).  Block-wide; returns the index
@@ -709,28 +814,56 @@ __global__ void __launch_bounds__(SEL_NT, 1) select_kernel(const SelectParams p)
   const int tid = threadIdx.x;
 
   __shared__ int s_n, s_flag;
+  __shared__ int s_pref[260];
   for (int q = blockIdx.x; q < p.Q; q += gridDim.x) {
     int status = 0;
     int n = 0;
     const int want = min(p.k, p.N_total);
     if (p.seg_pairs) {
-      // gather the query's private segments: one warp per segment, offsets from a shared counter
+      // gather the query's private segments: counts first (contiguous), block scan -> offsets, then all
+      // segments are copied with independent loads
       if (tid == 0) { s_n = 0; s_flag = 0; }
+      int* s_off = reinterpret_cast<int*>(S.keyA);                 // [n_segs + 1] scratch (sort buffers are idle)
+      const size_t seg0 = (size_t)q * p.n_segs;
       __syncthreads();
-      const int warp = tid >> 5, lane = tid & 31;
-      for (int sg = warp; sg < p.n_segs; sg += SEL_NT / 32) {
-        const size_t seg = (size_t)sg * p.q_pad + q;
-        int c = p.seg_cnt[seg];
-        if (c > SEG_T) { c = SEG_T; if (lane == 0) s_flag = 2; }     // a unit overflowed its private segment
-        int base = 0;
-        if (lane == 0 && c > 0) base = atomicAdd(&s_n, c);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        for (int i = lane; i < c; i += 32) {
-          if (base + i < SEL_CAP) {
-            const uint2 e = p.seg_pairs[seg * SEG_T + i];
-            S.score[base + i] = __uint_as_float(e.x);
-            S.id[base + i] = (int)e.y;
+      {
+        // exclusive scan of min(cnt, SEG_T) over the n_segs segments, SEL_NT at a time
+        int carry = 0;
+        for (int base = 0; base < p.n_segs; base += SEL_NT) {
+          const int sg = base + tid;
+          int c = sg < p.n_segs ? p.seg_cnt[seg0 + sg] : 0;
+          if (c > SEG_T) { c = SEG_T; s_flag = 2; }                 // a unit overflowed its private segment
+          int incl = c;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const int t_ = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((tid & 31) >= o) incl += t_;
           }
+          if ((tid & 31) == 31) warp_tot[tid >> 5] = incl;
+          __syncthreads();
+          int wb = 0;
+          for (int w = 0; w < (tid >> 5); ++w) wb += warp_tot[w];
+          if (sg < p.n_segs) s_off[sg] = carry + wb + incl - c;
+          int tot = 0;
+          for (int w = 0; w < SEL_NT / 32; ++w) tot += warp_tot[w];
+          carry += tot;
+          __syncthreads();
+        }
+        if (tid == 0) { s_off[p.n_segs] = carry; s_n = carry; }
+      }
+      __syncthreads();
+      {
+        // flat gather: entry e -> its segment by binary search over the offsets, all loads independent
+        const int total = min(s_off[p.n_segs], SEL_CAP);
+        for (int e = tid; e < total; e += SEL_NT) {
+          int lo = 0, hi = p.n_segs;                    // largest sg with s_off[sg] <= e
+          while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (s_off[mid] <= e) lo = mid; else hi = mid;
+          }
+          const uint2 pr = p.seg_pairs[(seg0 + lo) * SEG_T + (e - s_off[lo])];
+          S.score[e] = __uint_as_float(pr.x);
+          S.id[e] = (int)pr.y;
         }
       }
       __syncthreads();
@@ -758,6 +891,7 @@ __global__ void __launch_bounds__(SEL_NT, 1) select_kernel(const SelectParams p)
       }
     }
     __syncthreads();
+    n = prefilter_topk(S, n, p.k, s_pref);
     const u16* order = rank_candidates(S, n, warp_tot, &flag_single, &flag_long);
     for (int j = tid; j < p.k; j += SEL_NT) {
       float s = -INFINITY;
@@ -1025,6 +1159,7 @@ extern "C" int qf_dense_topk(const void* queries_bf16, const void* corpus_bf16, 
   int rc = qf::check_device();
   if (rc != QF_OK) return rc;
   const DenseWs w = plan_ws(Q, N, k);
+  QF_REQUIRE(w.n_chunks * 2 < SEL_CAP, QF_E_UNSUPPORTED, "qf_dense_topk: corpus too large for one launch (%d chunks)", w.n_chunks);
   QF_REQUIRE(ws_bytes >= w.total, QF_E_WORKSPACE, "qf_dense_topk: workspace %zu < %zu bytes", ws_bytes, w.total);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   unsigned char* base = reinterpret_cast<unsigned char*>(ws);
@@ -1051,28 +1186,45 @@ extern "C" int qf_dense_topk(const void* queries_bf16, const void* corpus_bf16, 
   p.seg_pairs = reinterpret_cast<uint2*>(base + w.off_segpairs);
   p.seg_cnt = reinterpret_cast<int*>(base + w.off_segcnt);
   p.q_pad = n_mtiles * BM;
+  p.n_segs = w.n_chunks * 2;
   p.store = reinterpret_cast<float*>(base + w.off_sample);
   p.store_ld = w.sample_ld;
 
   auto grid_for = [&](int n_units) { return n_units < sms ? n_units : sms; };
   if (w.n_sample_tiles > 0) {
     // threshold estimation: score a strided sample of doc tiles, take an exact order statistic per query
-    p.mode = MODE_STORE;
+    const int target = cand_target(k);
     p.n_vtiles = w.n_sample_tiles;
     p.tile_step = T / w.n_sample_tiles;
     p.chunk_tiles = 16;
+    // valid sample documents and the order statistic that should admit ~target candidates
+    long long s_valid = 0;
+    for (int t = 0; t < p.n_vtiles; ++t) {
+      const long long d0 = (long long)t * p.tile_step * BN;
+      s_valid += std::max(0ll, std::min((long long)BN, (long long)N - d0));
+    }
+    long long jj = ((long long)target * s_valid + N - 1) / N;
+    if (jj < 1) jj = 1;
+    if (jj > s_valid) jj = s_valid;
+    const bool tilemax = jj <= 64 && p.n_vtiles * 2 <= 1024 && p.n_vtiles * 2 >= 4 * jj;
+    p.mode = tilemax ? MODE_TILEMAX : MODE_STORE;
+    if (tilemax) p.store_ld = (long long)p.n_vtiles * 2;
     const int units = ((p.n_vtiles + p.chunk_tiles - 1) / p.chunk_tiles) * n_mtiles;
     qf::prof_mark(QF_PROF_DENSE_SAMPLE, 0, st);
     rc = launch_dense(maps, p, st);
     qf::prof_mark(QF_PROF_DENSE_SAMPLE, 1, st);
     if (rc != QF_OK) return rc;
-    const int target = cand_target(k);
     const long long s_cols = (long long)p.n_vtiles * BN;
     const bool small_j = ((long long)target * s_cols + N - 1) / N <= 128;
     qf::prof_mark(QF_PROF_DENSE_TAU, 0, st);
-    if (small_j) tau_kernel_small<<<Q, 512, 0, st>>>(p.store, p.store_ld, p.n_vtiles, p.tile_step, N, Q, target, tau);
-    tau_kernel<<<Q, 512, 0, st>>>(p.store, p.store_ld, p.n_vtiles, p.tile_step, N, Q, target, tau, small_j ? 1 : 0);
+    if (tilemax) {
+      tau_kernel_tilemax<<<Q, 512, 0, st>>>(p.store, p.store_ld, p.n_vtiles * 2, (int)jj, Q, tau);
+    } else {
+      if (small_j) tau_kernel_small<<<Q, 512, 0, st>>>(p.store, p.store_ld, p.n_vtiles, p.tile_step, N, Q, target, tau);
+      tau_kernel<<<Q, 512, 0, st>>>(p.store, p.store_ld, p.n_vtiles, p.tile_step, N, Q, target, tau, small_j ? 1 : 0);
+    }
     qf::prof_mark(QF_PROF_DENSE_TAU, 1, st);
+    p.store_ld = w.sample_ld;
     QF_CUDA_TRY(cudaGetLastError());
   } else {
     fill_kernel<<<(Q + 255) / 256, 256, 0, st>>>(tau, Q, -INFINITY);
@@ -1090,7 +1242,7 @@ extern "C" int qf_dense_topk(const void* queries_bf16, const void* corpus_bf16, 
     if (rc != QF_OK) return rc;
   }
   SelectParams sp{};
-  sp.seg_pairs = p.seg_pairs; sp.seg_cnt = p.seg_cnt; sp.n_segs = w.n_chunks * 2; sp.q_pad = p.q_pad;
+  sp.seg_pairs = p.seg_pairs; sp.seg_cnt = p.seg_cnt; sp.n_segs = w.n_chunks * 2;
   sp.Q = Q; sp.k = k; sp.N_total = N; sp.id_offset = id_offset;
   sp.out_scores = out_scores; sp.out_ids = out_ids; sp.out_status = out_status;
   qf::prof_mark(QF_PROF_DENSE_SELECT, 0, st);
