@@ -157,15 +157,12 @@ def dense_leg(args, dev, world, rank):
     stream = torch.cuda.current_stream(dev)
     steps = max(3, min(args.steps, 10))
 
+    from qppfusion import distributed as qd
+
     def step():
-        sc, ids, st = ops.dense_topk(qb, corpus, k, lo)
-        if world > 1:
-            gs = torch.empty((world, Q, k), dtype=torch.float32, device=dev)
-            gi = torch.empty((world, Q, k), dtype=torch.int32, device=dev)
-            dist.all_gather_into_tensor(gs, sc)
-            dist.all_gather_into_tensor(gi, ids)
-            sc, ids = ops.topk_merge(gs, gi)
-        return sc, ids, st
+        if world > 1:        # local top-k -> all-to-all -> merge Q/G queries per rank -> all-gather
+            return qd.dense_search_sharded(qb, corpus, k, lo)
+        return ops.dense_topk(qb, corpus, k, lo)
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -201,13 +198,10 @@ def dense_leg(args, dev, world, rank):
 
     def e2e_step():
         dq = h_q.to(dev, non_blocking=True).to(torch.bfloat16)
-        s_, i_, _ = ops.dense_topk(dq, corpus, k, lo)
         if world > 1:
-            gs = torch.empty((world, Q, k), dtype=torch.float32, device=dev)
-            gi = torch.empty((world, Q, k), dtype=torch.int32, device=dev)
-            dist.all_gather_into_tensor(gs, s_)
-            dist.all_gather_into_tensor(gi, i_)
-            s_, i_ = ops.topk_merge(gs, gi)
+            s_, i_, _ = qd.dense_search_sharded(dq, corpus, k, lo)
+        else:
+            s_, i_, _ = ops.dense_topk(dq, corpus, k, lo)
         h_s.copy_(s_, non_blocking=True)
         h_i.copy_(i_, non_blocking=True)
 
@@ -241,7 +235,7 @@ def dense_leg(args, dev, world, rank):
             "scaling": "strong" if world > 1 else "n/a",
             "config": {"workload": "BGE-base-shaped flat IP top-1000 (BASELINE configs[2])", "queries": Q,
                        "docs": N_DENSE, "docs_per_gpu": n_local, "dim": D, "k": k, "dtype": "bf16 in, fp32 accumulate",
-                       "sharding": f"corpus rows x{world}" + (", all_gather + qf_topk_merge" if world > 1 else "")},
+                       "sharding": f"corpus rows x{world}" + (", all_to_all + qf_topk_merge(Q/G) + all_gather" if world > 1 else "")},
             "kernel_ms": phases,
             "roofline": {"kernel": "dense_kernel (tcgen05 main pass)", "bound": "tensor", "achieved": ach, "peak": tf_peak,
                          "unit": "TFLOP/s", "frac": ach / tf_peak, "peak_source": which,

@@ -74,10 +74,40 @@ def qpp_colnorm_sharded_(vals: torch.Tensor, mode: str, round6: bool, group=None
     return ops.qpp_colnorm_apply_(vals, base.contiguous(), scale.contiguous(), round6)
 
 
-def dense_search_sharded(queries_bf16: torch.Tensor, corpus_shard_bf16: torch.Tensor, k: int, id_offset: int, group=None):
-    """Every rank: local top-k over its corpus rows, all-gather, merge -> identical [Q, k] on all ranks."""
+def exchange_topk(scores: torch.Tensor, ids: torch.Tensor, group=None):
+    """All-to-all of per-shard results so that every rank holds ALL shards' lists for ITS slice of the queries:
+    [Q, k] on each rank -> ([G, Qs, k], [G, Qs, k], Qs) with Qs = ceil(Q / G) (the query axis is padded with
+    -inf / -1 rows).  The k-way merge then costs Q/G queries per rank instead of Q (all-gather + merge everywhere)."""
+    world = dist.get_world_size(group)
+    Q, k = scores.shape
+    qs = (Q + world - 1) // world
+    pad = qs * world - Q
+    if pad:
+        scores = torch.cat([scores, torch.full((pad, k), float("-inf"), dtype=scores.dtype, device=scores.device)])
+        ids = torch.cat([ids, torch.full((pad, k), -1, dtype=ids.dtype, device=ids.device)])
+    rs, ri = torch.empty_like(scores), torch.empty_like(ids)
+    dist.all_to_all_single(rs, scores.contiguous(), group=group)     # chunk g of the send buffer goes to rank g
+    dist.all_to_all_single(ri, ids.contiguous(), group=group)
+    return rs.view(world, qs, k), ri.view(world, qs, k), qs
+
+
+def dense_search_sharded(queries_bf16: torch.Tensor, corpus_shard_bf16: torch.Tensor, k: int, id_offset: int, group=None,
+                         merge: str = "all_to_all"):
+    """Every rank: local top-k over its corpus rows (global ids), exchange, k-way merge -> identical [Q, k] on all
+    ranks.  merge="all_to_all" (default): each rank merges Q/G queries and the merged slices are all-gathered;
+    merge="all_gather": every rank gathers all [G, Q, k] lists and merges all Q queries itself."""
     from . import ops
     scores, ids, status = ops.dense_topk(queries_bf16, corpus_shard_bf16, k, id_offset)
-    gs, gi = gather_topk(scores, ids, group)
-    ms, mi = ops.topk_merge(gs, gi)
-    return ms, mi, status
+    world = dist.get_world_size(group)
+    Q = scores.shape[0]
+    if merge == "all_gather" or world == 1:
+        gs, gi = gather_topk(scores, ids, group)
+        ms, mi = ops.topk_merge(gs, gi)
+        return ms, mi, status
+    rs, ri, qs = exchange_topk(scores, ids, group)
+    ms, mi = ops.topk_merge(rs.contiguous(), ri.contiguous())                       # [qs, k] for this rank's query slice
+    fs = torch.empty((world * qs, k), dtype=ms.dtype, device=ms.device)
+    fi = torch.empty((world * qs, k), dtype=mi.dtype, device=mi.device)
+    dist.all_gather_into_tensor(fs, ms.contiguous(), group=group)
+    dist.all_gather_into_tensor(fi, mi.contiguous(), group=group)
+    return fs[:Q], fi[:Q], status

@@ -119,19 +119,14 @@ class BGERetriever(BaseRetriever):
         return np.asarray(self.encoder(queries), dtype=np.float32)
 
     def _search_device(self, query_embs: torch.Tensor, top_k: int):
-        scores, ids, status = ops.dense_topk(query_embs, self.corpus, top_k, self.id_offset)
-        if int(status.max().item()) != 0:
-            bad = torch.nonzero(status).flatten()[:5].tolist()
-            raise RuntimeError(f"qf_dense_topk: candidate threshold failed for queries {bad} (status "
-                               f"{status[bad].tolist()}); results would not be exact")
         if self.process_group is not None:
-            import torch.distributed as dist
-            world = dist.get_world_size(self.process_group)
-            gs = torch.empty((world,) + tuple(scores.shape), dtype=scores.dtype, device=scores.device)
-            gi = torch.empty((world,) + tuple(ids.shape), dtype=ids.dtype, device=ids.device)
-            dist.all_gather_into_tensor(gs, scores, group=self.process_group)
-            dist.all_gather_into_tensor(gi, ids, group=self.process_group)
-            scores, ids = ops.topk_merge(gs, gi)
+            from .. import distributed as qd
+            scores, ids, status = qd.dense_search_sharded(query_embs, self.corpus, top_k, self.id_offset, self.process_group)
+        else:
+            scores, ids, status = ops.dense_topk(query_embs, self.corpus, top_k, self.id_offset)
+        if int(status.max().item()) != 0:      # cannot happen with the exact fallback enabled; never silently accept
+            bad = torch.nonzero(status).flatten()[:5].tolist()
+            raise RuntimeError(f"qf_dense_topk: candidate threshold failed for queries {bad}; results would not be exact")
         return scores, ids
 
     def _search_batch(self, query_embs: np.ndarray, top_k: int) -> Tuple[np.ndarray, np.ndarray]:

@@ -38,6 +38,13 @@ def _worker(rank, world, port, ret):
         ms, mi = do.merge_topk(gs.numpy(), gi.numpy(), k)
         fi, fs = do.flat_ip_topk(queries, corpus, k)
         assert np.array_equal(mi, fi) and np.array_equal(ms, fs)
+        # all-to-all variant: this rank ends up with every shard's lists for its own slice of the queries
+        rs, ri, qs = qd.exchange_topk(torch.from_numpy(sc), torch.from_numpy(ids.astype(np.int32)))
+        assert rs.shape == (world, qs, k)
+        ms2, mi2 = do.merge_topk(rs.numpy(), ri.numpy(), k)
+        q0 = rank * qs
+        n_mine = max(0, min(qs, Q - q0))
+        assert np.array_equal(mi2[:n_mine], fi[q0:q0 + n_mine]) and np.array_equal(ms2[:n_mine], fs[q0:q0 + n_mine])
         # ---- QPP colnorm: query-sharded table, stats all-reduced, params as _normalize_qpp
         Qq, R, C = 53, 3, 13
         table = rng.normal(size=(Qq, R, C))

@@ -18,8 +18,11 @@ Q, N, D, k = 300, 200_000, 768, 1000
 c = torch.randn((N, D), generator=g); c = (c / c.norm(dim=1, keepdim=True)).to(torch.bfloat16)
 q = torch.randn((Q, D), generator=g); q = (q / q.norm(dim=1, keepdim=True)).to(torch.bfloat16).to(dev)
 lo, hi = qd.shard_range(N, world, rank)
-ms, mi, st = qd.dense_search_sharded(q, c[lo:hi].to(dev).contiguous(), k, lo)
+shard = c[lo:hi].to(dev).contiguous()
+ms, mi, st = qd.dense_search_sharded(q, shard, k, lo)
 assert int(st.max()) == 0
+ms2, mi2, _ = qd.dense_search_sharded(q, shard, k, lo, merge="all_gather")
+assert torch.equal(ms, ms2) and torch.equal(mi, mi2), "all_to_all and all_gather merges differ"
 if rank == 0:
     fs, fi, st0 = ops.dense_topk(q, c.to(dev), k, 0)
     assert torch.equal(fs, ms) and torch.equal(fi, mi), "sharded dense search differs from single-GPU search"
