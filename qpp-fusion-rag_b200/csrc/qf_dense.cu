@@ -1120,7 +1120,13 @@ DenseWs plan_ws(int Q, int N, int k) {
   DenseWs w{};
   const int n_mtiles = (Q + BM - 1) / BM;
   const long long T = ((long long)N + BN - 1) / BN;
-  w.n_sample_tiles = N > SEL_CAP ? (int)(T < 512 ? T : 512) : 0;
+  // sample size: at most 512 tiles, and small enough that the order statistic jj = target * S / N stays <= 64 so
+  // the cheap tile-max estimator applies (S <= 64 N / target documents, i.e. N / target tiles)
+  long long ns = (long long)N / cand_target(k);
+  if (ns < 8) ns = 8;
+  if (ns > 512) ns = 512;
+  if (ns > T) ns = T;
+  w.n_sample_tiles = N > SEL_CAP ? (int)ns : 0;
   w.sample_ld = (long long)w.n_sample_tiles * BN;
   w.chunk_tiles = main_chunk_tiles(N, k);
   w.n_chunks = (int)((T + w.chunk_tiles - 1) / w.chunk_tiles);
