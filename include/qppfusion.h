@@ -132,6 +132,28 @@ QF_API int    qf_compact_fused(const int32_t* ids, const double* scores, const i
                                void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Run-file wire format (host side, multi-threaded, no CUDA)  --  replaces pd.read_csv(sep=r"\s+") in
+ * load_runs (src/fusion.py:67-72), the row loop of _df_runs_to_ranx (:455-466) and the per-line formatting of
+ * write_runfile (:480-492)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct qf_runs qf_runs;
+/* Parse TREC run files ("{qid} Q0 {docno} {rank} {score} {tag}", whitespace separated) into dictionary-encoded
+ * columns; one shared qid dictionary and one shared docno dictionary (first-seen order) for all files.  Scores are
+ * kept as strtod doubles and, when every score has <= 6 decimals and fits, as exact int32 micro-units. */
+QF_API int  qf_runs_parse(const char* const* paths, int n_files, int n_threads, qf_runs** out);
+QF_API void qf_runs_free(qf_runs* runs);
+QF_API int  qf_runs_info(const qf_runs* runs, int64_t* rows_per_file, int32_t* n_qids, int32_t* n_docs, int32_t* all_micro,
+                         int64_t* qid_arena_bytes, int64_t* doc_arena_bytes);
+QF_API int  qf_runs_rows(const qf_runs* runs, int file, int32_t* qid_idx, int32_t* doc_idx, int32_t* rank, int32_t* micro,
+                         double* score);
+QF_API int  qf_runs_dict(const qf_runs* runs, int which /*0 qid, 1 docno*/, char* arena, int64_t* offsets);
+/* Write "{qid} Q0 {docno} {rank} {score:.6f} {tag}" lines from CSR results (query j of the file = CSR row qsel[j],
+ * already ranked); strings come from the dictionaries (arena + offsets). */
+QF_API int  qf_runfile_write(const char* path, const char* qid_arena, const int64_t* qid_off, const int32_t* qsel,
+                             int n_queries, const char* doc_arena, const int64_t* doc_off, const int64_t* offsets,
+                             const int32_t* ids, const double* scores, const char* tag, int n_threads);
+
+/* ------------------------------------------------------------------------------------------------
  * QPP statistics  --  replaces the JVM round trip QPPBridge.compute_batch -> qpp.QPPBridge
  *                     (src/qpp.py:117-171; src/qpp/java/qpp/QPPBridge.java:134-453)
  * ---------------------------------------------------------------------------------------------- */

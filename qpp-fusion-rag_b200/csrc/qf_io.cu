@@ -1,0 +1,327 @@
+// qf_io: native (host, multi-threaded) TREC run-file parser and writer -- the wire formats either side of the
+// fusion kernel (reference: pd.read_csv(sep=r"\s+") in load_runs, src/fusion.py:67-72; the row loop of
+// _df_runs_to_ranx, :455-466; write_runfile, :480-492).  Once qf_fuse runs at millions of queries per second the
+// regex CSV reader, the docno string factorisation and the per-line Python formatting dominate a file-to-file run
+// by four orders of magnitude; this module parses "{qid} Q0 {docno} {rank} {score} {tag}" lines straight into
+// dictionary-encoded integer arrays (scores as exact int32 micro-units when the text has <= 6 decimals, and as
+// strtod doubles always) and writes "{qid} Q0 {docid} {rank} {score:.6f} {tag}" lines from CSR results.
+// Pure host code: no CUDA calls, usable on a CPU-only box.
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "qf_common.cuh"
+
+namespace {
+
+struct Tok {
+  const char* p;
+  int len;
+};
+
+struct Row {
+  Tok qid, doc;
+  uint64_t doc_hash;
+  int32_t rank;
+  int32_t micro;
+  double score;
+  bool micro_ok;
+};
+
+inline bool is_ws(char c) { return c == ' ' || c == '\t' || c == '\r' || c == '\f' || c == '\v'; }
+
+// exact decimal -> micro-units: [+-]digits[.digits{0,6}] with |value| < 2147.483647, else false
+inline bool parse_micro(const char* s, int len, int32_t* out) {
+  int i = 0;
+  bool neg = false;
+  if (i < len && (s[i] == '-' || s[i] == '+')) neg = s[i++] == '-';
+  long long ip = 0;
+  int nd = 0;
+  while (i < len && s[i] >= '0' && s[i] <= '9') {
+    ip = ip * 10 + (s[i++] - '0');
+    if (++nd > 6) return false;
+  }
+  long long fp = 0;
+  int nf = 0;
+  if (i < len && s[i] == '.') {
+    ++i;
+    while (i < len && s[i] >= '0' && s[i] <= '9') {
+      if (nf == 6) return false;
+      fp = fp * 10 + (s[i++] - '0');
+      ++nf;
+    }
+  }
+  if (i != len || (nd == 0 && nf == 0)) return false;
+  for (int k = nf; k < 6; ++k) fp *= 10;
+  const long long v = ip * 1000000LL + fp;
+  if (v > 2147483647LL) return false;
+  *out = (int32_t)(neg ? -v : v);
+  return true;
+}
+
+struct Dict {
+  // open addressing over (hash, arena offset, length); arena stores the strings back to back
+  std::vector<uint64_t> hashes;
+  std::vector<int32_t> slots;   // index into entries or -1
+  std::vector<int64_t> off;     // entry -> arena offset (off.size() == n+1)
+  std::string arena;
+  size_t mask = 0;
+  Dict() { rehash(1 << 16); off.push_back(0); }
+  static uint64_t hash(const char* p, int len) {
+    uint64_t h = 1469598103934665603ull;
+    for (int i = 0; i < len; ++i) { h ^= (unsigned char)p[i]; h *= 1099511628211ull; }
+    return h ^ (h >> 29);
+  }
+  void rehash(size_t cap) {
+    std::vector<int32_t> ns(cap, -1);
+    const size_t nm = cap - 1;
+    for (size_t e = 0; e < hashes.size(); ++e) {
+      size_t i = hashes[e] & nm;
+      while (ns[i] >= 0) i = (i + 1) & nm;
+      ns[i] = (int32_t)e;
+    }
+    slots.swap(ns);
+    mask = nm;
+  }
+  void prefetch(uint64_t h) const { __builtin_prefetch(&slots[h & mask]); }
+  int32_t get(const char* p, int len) { return get_hashed(p, len, hash(p, len)); }
+  int32_t get_hashed(const char* p, int len, uint64_t h) {
+    size_t i = h & mask;
+    while (true) {
+      const int32_t e = slots[i];
+      if (e < 0) break;
+      if (hashes[e] == h && off[e + 1] - off[e] == len && memcmp(arena.data() + off[e], p, (size_t)len) == 0) return e;
+      i = (i + 1) & mask;
+    }
+    const int32_t e = (int32_t)hashes.size();
+    hashes.push_back(h);
+    arena.append(p, (size_t)len);
+    off.push_back((int64_t)arena.size());
+    slots[i] = e;
+    if (hashes.size() * 2 > slots.size()) rehash(slots.size() * 2);
+    return e;
+  }
+  int32_t size() const { return (int32_t)hashes.size(); }
+};
+
+struct FileRows {
+  std::vector<int32_t> qid, doc, rank, micro;
+  std::vector<double> score;
+};
+
+}  // namespace
+
+struct qf_runs {
+  std::vector<FileRows> files;
+  Dict qids, docs;
+  bool all_micro = true;
+  std::string error;
+};
+
+namespace {
+
+bool parse_chunk(const char* b, const char* e, std::vector<Row>& rows, std::string& err) {
+  const char* p = b;
+  while (p < e) {
+    const char* eol = (const char*)memchr(p, '\n', (size_t)(e - p));
+    if (!eol) eol = e;
+    Tok f[6];
+    int nf = 0;
+    const char* c = p;
+    while (c < eol && nf < 6) {
+      while (c < eol && is_ws(*c)) ++c;
+      if (c >= eol) break;
+      const char* s = c;
+      while (c < eol && !is_ws(*c)) ++c;
+      f[nf].p = s;
+      f[nf].len = (int)(c - s);
+      ++nf;
+    }
+    if (nf >= 5) {
+      Row r;
+      r.qid = f[0];
+      r.doc = f[2];
+      r.doc_hash = Dict::hash(f[2].p, f[2].len);
+      char buf[64];
+      const int rl = f[3].len < 63 ? f[3].len : 63;
+      memcpy(buf, f[3].p, (size_t)rl);
+      buf[rl] = 0;
+      char* endp = nullptr;
+      const long rk = strtol(buf, &endp, 10);
+      if (*endp != 0 || rk < -2147483647L || rk > 2147483647L) { err = "bad rank field '" + std::string(buf) + "'"; return false; }
+      r.rank = (int32_t)rk;
+      const int sl = f[4].len < 63 ? f[4].len : 63;
+      memcpy(buf, f[4].p, (size_t)sl);
+      buf[sl] = 0;
+      r.score = strtod(buf, &endp);
+      if (*endp != 0) { err = "bad score field '" + std::string(buf) + "'"; return false; }
+      r.micro_ok = parse_micro(f[4].p, f[4].len, &r.micro);
+      if (!r.micro_ok) r.micro = 0;
+      rows.push_back(r);
+    } else if (nf != 0) {
+      err = "line with " + std::to_string(nf) + " fields (need >= 5)";
+      return false;
+    }
+    p = eol + 1;
+  }
+  return true;
+}
+
+}  // namespace
+
+extern "C" int qf_runs_parse(const char* const* paths, int n_files, int n_threads, qf_runs** out) {
+  QF_REQUIRE(paths && out && n_files >= 1, QF_E_INVALID, "qf_runs_parse: bad arguments");
+  if (n_threads < 1) n_threads = 1;
+  qf_runs* R = new qf_runs();
+  R->files.resize((size_t)n_files);
+  for (int fi = 0; fi < n_files; ++fi) {
+    const int fd = open(paths[fi], O_RDONLY);
+    if (fd < 0) { qf::set_error("qf_runs_parse: cannot open %s", paths[fi]); delete R; return QF_E_INVALID; }
+    struct stat st;
+    fstat(fd, &st);
+    const size_t sz = (size_t)st.st_size;
+    const char* base = sz ? (const char*)mmap(nullptr, sz, PROT_READ, MAP_PRIVATE, fd, 0) : nullptr;
+    if (sz && base == MAP_FAILED) { close(fd); qf::set_error("qf_runs_parse: mmap failed for %s", paths[fi]); delete R; return QF_E_INVALID; }
+    // split at newline boundaries, parse chunks in parallel
+    const int nt = sz < (1u << 20) ? 1 : n_threads;
+    std::vector<const char*> cut((size_t)nt + 1);
+    cut[0] = base;
+    cut[(size_t)nt] = base + sz;
+    for (int t = 1; t < nt; ++t) {
+      const char* p = base + sz * (size_t)t / (size_t)nt;
+      const char* nl = (const char*)memchr(p, '\n', (size_t)(base + sz - p));
+      cut[(size_t)t] = nl ? nl + 1 : base + sz;
+    }
+    std::vector<std::vector<Row>> parts((size_t)nt);
+    std::vector<std::string> errs((size_t)nt);
+    std::vector<char> ok((size_t)nt, 1);
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; ++t)
+      th.emplace_back([&, t]() { ok[(size_t)t] = parse_chunk(cut[(size_t)t], cut[(size_t)t + 1], parts[(size_t)t], errs[(size_t)t]) ? 1 : 0; });
+    for (auto& x : th) x.join();
+    for (int t = 0; t < nt; ++t)
+      if (!ok[(size_t)t]) {
+        qf::set_error("qf_runs_parse: %s: %s", paths[fi], errs[(size_t)t].c_str());
+        if (sz) munmap((void*)base, sz);
+        close(fd);
+        delete R;
+        return QF_E_INVALID;
+      }
+    size_t n = 0;
+    for (auto& v : parts) n += v.size();
+    FileRows& F = R->files[(size_t)fi];
+    F.qid.reserve(n); F.doc.reserve(n); F.rank.reserve(n); F.micro.reserve(n); F.score.reserve(n);
+    Tok last_q{nullptr, 0};
+    int32_t last_qi = -1;
+    for (auto& v : parts)
+      for (size_t ri = 0; ri < v.size(); ++ri) {        // dictionary encoding in file order (serial: shared dictionaries)
+        const Row& r = v[ri];
+        if (ri + 8 < v.size()) R->docs.prefetch(v[ri + 8].doc_hash);
+        if (last_qi < 0 || r.qid.len != last_q.len || memcmp(r.qid.p, last_q.p, (size_t)r.qid.len) != 0) {
+          last_qi = R->qids.get(r.qid.p, r.qid.len);
+          last_q = r.qid;
+        }
+        F.qid.push_back(last_qi);
+        F.doc.push_back(R->docs.get_hashed(r.doc.p, r.doc.len, r.doc_hash));
+        F.rank.push_back(r.rank);
+        F.micro.push_back(r.micro);
+        F.score.push_back(r.score);
+        if (!r.micro_ok) R->all_micro = false;
+      }
+    if (sz) munmap((void*)base, sz);
+    close(fd);
+  }
+  *out = R;
+  return QF_OK;
+}
+
+extern "C" void qf_runs_free(qf_runs* r) { delete r; }
+
+extern "C" int qf_runs_info(const qf_runs* r, int64_t* rows_per_file, int32_t* n_qids, int32_t* n_docs, int32_t* all_micro,
+                            int64_t* qid_arena_bytes, int64_t* doc_arena_bytes) {
+  QF_REQUIRE(r, QF_E_INVALID, "qf_runs_info: null handle");
+  if (rows_per_file)
+    for (size_t i = 0; i < r->files.size(); ++i) rows_per_file[i] = (int64_t)r->files[i].qid.size();
+  if (n_qids) *n_qids = r->qids.size();
+  if (n_docs) *n_docs = r->docs.size();
+  if (all_micro) *all_micro = r->all_micro ? 1 : 0;
+  if (qid_arena_bytes) *qid_arena_bytes = (int64_t)r->qids.arena.size();
+  if (doc_arena_bytes) *doc_arena_bytes = (int64_t)r->docs.arena.size();
+  return QF_OK;
+}
+
+// copy one file's columns into caller buffers (each nullable), rows_per_file[file] elements
+extern "C" int qf_runs_rows(const qf_runs* r, int file, int32_t* qid_idx, int32_t* doc_idx, int32_t* rank, int32_t* micro,
+                            double* score) {
+  QF_REQUIRE(r && file >= 0 && (size_t)file < r->files.size(), QF_E_INVALID, "qf_runs_rows: bad arguments");
+  const FileRows& F = r->files[(size_t)file];
+  const size_t n = F.qid.size();
+  if (qid_idx) memcpy(qid_idx, F.qid.data(), n * 4);
+  if (doc_idx) memcpy(doc_idx, F.doc.data(), n * 4);
+  if (rank) memcpy(rank, F.rank.data(), n * 4);
+  if (micro) memcpy(micro, F.micro.data(), n * 4);
+  if (score) memcpy(score, F.score.data(), n * 8);
+  return QF_OK;
+}
+
+// which = 0: qid dictionary, 1: docno dictionary.  arena: concatenated strings, offsets: n+1 entries.
+extern "C" int qf_runs_dict(const qf_runs* r, int which, char* arena, int64_t* offsets) {
+  QF_REQUIRE(r && (which == 0 || which == 1), QF_E_INVALID, "qf_runs_dict: bad arguments");
+  const Dict& d = which == 0 ? r->qids : r->docs;
+  if (arena) memcpy(arena, d.arena.data(), d.arena.size());
+  if (offsets) memcpy(offsets, d.off.data(), d.off.size() * 8);
+  return QF_OK;
+}
+
+// Write a TREC run file from CSR results.  Query j (output order) = rows [offsets[qsel[j]], offsets[qsel[j]+1]) of
+// ids/scores, already ranked; lines "{qid} Q0 {docno} {rank} {score:.6f} {tag}\n" (reference src/fusion.py:488-490;
+// glibc's %.6f is correctly rounded, like Python's).
+extern "C" int qf_runfile_write(const char* path, const char* qid_arena, const int64_t* qid_off, const int32_t* qsel,
+                                int n_queries, const char* doc_arena, const int64_t* doc_off, const int64_t* offsets,
+                                const int32_t* ids, const double* scores, const char* tag, int n_threads) {
+  QF_REQUIRE(path && qid_arena && qid_off && qsel && doc_arena && doc_off && offsets && ids && scores && tag && n_queries >= 0,
+             QF_E_INVALID, "qf_runfile_write: bad arguments");
+  if (n_threads < 1) n_threads = 1;
+  if (n_threads > n_queries) n_threads = n_queries > 0 ? n_queries : 1;
+  std::vector<std::string> bufs((size_t)n_threads);
+  std::vector<std::thread> th;
+  const size_t tag_len = strlen(tag);
+  for (int t = 0; t < n_threads; ++t)
+    th.emplace_back([&, t]() {
+      const int j0 = (int)((long long)n_queries * t / n_threads), j1 = (int)((long long)n_queries * (t + 1) / n_threads);
+      std::string& out = bufs[(size_t)t];
+      char num[64];
+      for (int j = j0; j < j1; ++j) {
+        const int q = qsel[j];
+        const char* qs = qid_arena + qid_off[q];
+        const size_t ql = (size_t)(qid_off[q + 1] - qid_off[q]);
+        int rank = 1;
+        for (int64_t e = offsets[q]; e < offsets[q + 1]; ++e, ++rank) {
+          const int32_t d = ids[e];
+          out.append(qs, ql);
+          out.append(" Q0 ", 4);
+          out.append(doc_arena + doc_off[d], (size_t)(doc_off[d + 1] - doc_off[d]));
+          const int nl = snprintf(num, sizeof(num), " %d %.6f ", rank, scores[e]);
+          out.append(num, (size_t)nl);
+          out.append(tag, tag_len);
+          out.push_back('\n');
+        }
+      }
+    });
+  for (auto& x : th) x.join();
+  FILE* f = fopen(path, "wb");
+  if (!f) { qf::set_error("qf_runfile_write: cannot open %s", path); return QF_E_INVALID; }
+  for (auto& b : bufs)
+    if (!b.empty() && fwrite(b.data(), 1, b.size(), f) != b.size()) { fclose(f); qf::set_error("qf_runfile_write: short write"); return QF_E_INVALID; }
+  fclose(f);
+  return QF_OK;
+}

@@ -50,6 +50,12 @@ PROTOTYPES = {
     "qf_profile_read": (_i, [_i, ctypes.POINTER(ctypes.c_float)]),
     "qf_fuse_max_postings": (_i, []),
     "qf_fuse": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _d, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "qf_runs_parse": (_i, [_vp, _i, _i, _vp]),
+    "qf_runs_free": (None, [_vp]),
+    "qf_runs_info": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "qf_runs_rows": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp]),
+    "qf_runs_dict": (_i, [_vp, _i, _vp, _vp]),
+    "qf_runfile_write": (_i, [ctypes.c_char_p, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, ctypes.c_char_p, _i]),
     "qf_compact_workspace_bytes": (_sz, [_i]),
     "qf_compact_fused": (_i, [_vp, _vp, _vp, _i, ctypes.c_longlong, _vp, _vp, _vp, _vp, _sz, _vp]),
     "qf_qpp_stats": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),

@@ -283,43 +283,88 @@ def write_runfile(fused: Fused, output_path: str, tag: str = "fusion"):
     print(f"Wrote fused run to {output_path}")
 
 
+def _fused_dict_from_out(packed: PackedRuns, docnos: np.ndarray, out: ops.FuseOut, first_seen_order: bool) -> Fused:
+    """Kernel outputs (ranked) -> the reference's return value; weighted_* lists come back in first-seen order."""
+    ids, scores, lens = out.ids.cpu().numpy(), out.scores.cpu().numpy(), out.lens.cpu().numpy()
+    pos = out.pos.cpu().numpy() if first_seen_order else None
+    fused = {}
+    for qi, qid in enumerate(packed.qids):
+        n = int(lens[qi])
+        if n == 0:
+            continue
+        d, s_ = docnos[ids[qi, :n]], scores[qi, :n]
+        if pos is not None:
+            inv = np.empty(n, dtype=np.int64)
+            inv[pos[qi, :n].astype(np.int64)] = np.arange(n)
+            d, s_ = d[inv], s_[inv]
+        fused[qid] = list(zip(d.tolist(), s_.tolist()))
+    return fused
+
+
 def run_fusion(method: str, runs_dir: str, qpp_dir: Optional[str] = None, qpp_model: str = None,
-               model_path: Optional[str] = None, output_path: Optional[str] = None, rrf_k: int = None) -> Fused:
-    """Dispatcher with the reference's method names, aliases, tags and errors (src/fusion.py:495-579)."""
+               model_path: Optional[str] = None, output_path: Optional[str] = None, rrf_k: int = None,
+               return_fused: bool = True) -> Fused:
+    """Dispatcher with the reference's method names, aliases, tags and errors (src/fusion.py:495-579).
+
+    File-to-file fast path: the run files are parsed and dictionary-encoded by the native reader
+    (native_io.parse_runs), fused in one qf_fuse launch, CSR-compacted on the device and written by the native
+    writer; the Python dict the reference returns is still built (return_fused=False skips it, the CLI does)."""
+    from . import native_io as nio
     qpp_model = qpp_model or config.qpp.default_method
     rrf_k = rrf_k if rrf_k is not None else config.fusion.rrf_k
-    runs = load_runs(runs_dir, use_normalized=True)
-    print(f"Loaded {len(runs)} rankers: {list(runs.keys())}")
     method = method.lower()
-    if method == "combsum":
-        fused, tag = combsum(runs), "combsum"
-    elif method == "combmnz":
-        fused, tag = combmnz(runs), "combmnz"
-    elif method == "rrf":
-        fused, tag = rrf(runs, k=rrf_k), f"rrf-k{rrf_k}"
-    elif method in ["wcombsum", "w-combsum", "wcombmnz", "w-combmnz", "wrrf", "w-rrf"]:
-        if not qpp_dir:
-            raise ValueError("--qpp_dir required for weighted methods")
-        qpp_data = load_qpp_scores(qpp_dir)
-        qpp_index = get_qpp_index(qpp_model)
-        base = method.replace("-", "")
-        if base == "wcombsum":
-            fused = weighted_combsum(runs, qpp_data, qpp_index)
-        elif base == "wcombmnz":
-            fused = weighted_combmnz(runs, qpp_data, qpp_index)
-        else:
-            fused = weighted_rrf(runs, qpp_data, qpp_index, k=rrf_k)
-        tag = f"{base}-{qpp_model.lower()}"
-    elif method == "learned":
+    if method == "learned":
         if not model_path:
             raise ValueError("--model_path required for learned fusion")
         if not qpp_dir:
             raise ValueError("--qpp_dir required for learned fusion")
-        fused, tag = learned_fusion(runs, load_qpp_scores(qpp_dir), model_path), "learned"
-    else:
+        runs = load_runs(runs_dir, use_normalized=True)
+        print(f"Loaded {len(runs)} rankers: {list(runs.keys())}")
+        fused = learned_fusion(runs, load_qpp_scores(qpp_dir), model_path)
+        if output_path:
+            write_runfile(fused, output_path, "learned")
+        return fused
+    weighted_names = {"wcombsum": N.METHOD_SUM, "wcombmnz": N.METHOD_MNZ, "wrrf": N.METHOD_RRF}
+    plain_names = {"combsum": N.METHOD_SUM, "combmnz": N.METHOD_MNZ, "rrf": N.METHOD_RRF}
+    base = method.replace("-", "")
+    if base not in weighted_names and method not in plain_names:
+        files, _ = _run_files(runs_dir, True)          # FileNotFoundError first, as the reference (load_runs runs first)
         raise ValueError(f"Unknown method '{method}'. Valid: {config.fusion.methods}")
+    files, suffix = _run_files(runs_dir, True)
+    names = [f.replace(suffix, "") for f in files]
+    if base in weighted_names and method not in plain_names and not qpp_dir:
+        print(f"Loaded {len(names)} rankers: {names}")
+        raise ValueError("--qpp_dir required for weighted methods")
+    parsed = nio.parse_runs([os.path.join(runs_dir, f) for f in files], names)
+    print(f"Loaded {len(names)} rankers: {names}")
+    if method in plain_names:
+        m = plain_names[method]
+        packed, qorder = nio.pack_parsed(parsed, "ranx")
+        flags = N.FLAG_REQUIRE_SORTED | (N.FLAG_MNZ_SKIP_ZERO if (m == N.METHOD_MNZ and not config.fusion.ranx_mnz_counts_zero_scores) else 0)
+        print(f"[fusion] Running {method} (qf_fuse)...")
+        out = fuse_packed(packed, m, None, N.NORM_NONE if m == N.METHOD_RRF else N.NORM_MINMAX, float(rrf_k), flags)
+        tag = f"rrf-k{rrf_k}" if method == "rrf" else method
+        first_seen = False
+    else:
+        m = weighted_names[base]
+        qpp_data = load_qpp_scores(qpp_dir)
+        qpp_index = get_qpp_index(qpp_model)
+        packed, qorder = nio.pack_parsed(parsed, "weighted_rrf" if m == N.METHOD_RRF else "weighted", need_ranks=(m == N.METHOD_RRF))
+        w = _weights_matrix(packed, qpp_data, qpp_index)
+        print(f"[fusion] Running {base} (QPP index={qpp_index}, qf_fuse)...")
+        out = fuse_packed(packed, m, w, N.NORM_NONE, float(rrf_k), 0, want_pos=return_fused)
+        tag = f"{base}-{qpp_model.lower()}"
+        first_seen = True
     if output_path:
-        write_runfile(fused, output_path, tag)
+        off, cids, csc = ops.compact_fused(out)
+        off = off.cpu().numpy()
+        total = int(off[-1])
+        nio.write_runfile_csr(output_path, parsed, qorder, off, cids[:total].cpu().numpy(), csc[:total].cpu().numpy(), tag)
+        print(f"Wrote fused run to {output_path}")
+    if not return_fused:
+        return {}
+    fused = _fused_dict_from_out(packed, parsed.doc_strings(), out, first_seen)
+    print(f"[fusion] {method} done: {len(fused)} queries")
     return fused
 
 
@@ -336,4 +381,4 @@ if __name__ == "__main__":
     parser.add_argument("--rrf_k", type=int, default=config.fusion.rrf_k, help="RRF k constant")
     a = parser.parse_args()
     run_fusion(method=a.method, runs_dir=a.runs_dir, qpp_dir=a.qpp_dir, qpp_model=a.qpp_model,
-               model_path=a.model_path, output_path=a.output, rrf_k=a.rrf_k)
+               model_path=a.model_path, output_path=a.output, rrf_k=a.rrf_k, return_fused=False)

@@ -132,3 +132,80 @@ def test_retriever_result_and_normalize_scores():
     assert BaseRetriever.normalize_scores(r.results) == [("d1", 1.0, 1), ("d2", 0.0, 2)]
     assert BaseRetriever.normalize_scores([("d", 2.0, 1)]) == [("d", 0.0, 1)]
     assert BaseRetriever.normalize_scores([]) == []
+
+
+def _write_runs(tmp_path, seed=3, n_q=9, k=30, adversarial=True):
+    rng = np.random.default_rng(seed)
+    d = tmp_path / "runs"
+    d.mkdir()
+    for rk in ("BGE", "BM25", "Splade"):
+        lines = []
+        for q in range(n_q):
+            docs = rng.choice(200, size=k, replace=False)
+            sc = np.sort(rng.random(k) * (25 if rk == "BM25" else 1))[::-1]
+            if adversarial and q == 2 and rk == "BM25":
+                docs[5] = docs[1]                                  # duplicate docno
+            if adversarial and q == 3:
+                sc[4:8] = sc[4]                                    # ties
+            order = rng.permutation(k) if (adversarial and q == 4 and rk == "Splade") else np.arange(k)
+            for i in order:
+                lines.append(f"test{q}\tQ0  doc{docs[i]} {i + 1} {sc[i]:.6f} {rk}")
+        (d / f"{rk}.norm.res").write_text("\n".join(lines) + "\n")
+    return d
+
+
+@pytest.mark.parametrize("mode", ["weighted", "weighted_rrf", "ranx"])
+def test_native_parser_and_packing_equal_the_pandas_path(tmp_path, mode):
+    from qppfusion import native_io as nio
+    d = _write_runs(tmp_path)
+    runs = fusion.load_runs(str(d))
+    ref = pack_runs(runs, mode=mode, need_ranks=True)
+    files = sorted(f for f in os.listdir(d))
+    parsed = nio.parse_runs([str(d / f) for f in files], [f.replace(".norm.res", "") for f in files], n_threads=3)
+    got, qorder = nio.pack_parsed(parsed, mode, need_ranks=True)
+    assert parsed.all_micro and got.scores.dtype == np.int32
+    assert got.qids == ref.qids and got.rankers == ref.rankers
+    assert np.array_equal(got.lens, ref.lens) and np.array_equal(got.scores, ref.scores) and np.array_equal(got.ranks, ref.ranks)
+    docs = parsed.doc_strings()
+    valid = got.doc_ids >= 0
+    assert np.array_equal(valid, ref.doc_ids >= 0)
+    assert (docs[got.doc_ids[valid]] == ref.docnos[ref.doc_ids[valid]]).all()
+
+
+def test_native_parser_f64_fallback_and_errors(tmp_path):
+    from qppfusion import _native as N_
+    from qppfusion import native_io as nio
+    p = tmp_path / "a.res"
+    p.write_text("q1 Q0 d1 1 0.1234567 A\nq1 Q0 d2 2 1e-3 A\n\nq2 Q0 d1 1 -7 A\n")
+    parsed = nio.parse_runs([str(p)])
+    assert not parsed.all_micro
+    assert parsed.cols[0]["score"].tolist() == [0.1234567, 1e-3, -7.0]
+    assert parsed.qid_strings() == ["q1", "q2"] and parsed.doc_strings().tolist() == ["d1", "d2"]
+    bad = tmp_path / "b.res"
+    bad.write_text("q1 Q0 d1\n")
+    with pytest.raises(N_.NativeError, match="fields"):
+        nio.parse_runs([str(bad)])
+    with pytest.raises(N_.NativeError, match="cannot open"):
+        nio.parse_runs([str(tmp_path / "missing.res")])
+
+
+def test_native_writer_matches_python_write_runfile(tmp_path):
+    from qppfusion import native_io as nio
+    d = _write_runs(tmp_path, adversarial=False)
+    files = sorted(os.listdir(d))
+    parsed = nio.parse_runs([str(d / f) for f in files])
+    packed, qorder = nio.pack_parsed(parsed, "weighted")
+    docs = parsed.doc_strings()
+    rng = np.random.default_rng(1)
+    fused, offs, ids, scs = {}, [0], [], []
+    for qi, qid in enumerate(packed.qids):
+        n = int(rng.integers(0, 40))
+        di = rng.choice(len(docs), size=n, replace=False).astype(np.int32)
+        sc = np.sort(rng.normal(size=n))[::-1]
+        if n:
+            fused[qid] = list(zip(docs[di].tolist(), sc.tolist()))
+        ids.append(di); scs.append(sc); offs.append(offs[-1] + n)
+    out_py, out_c = tmp_path / "py.res", tmp_path / "c.res"
+    fusion.write_runfile(fused, str(out_py), "tag-x")
+    nio.write_runfile_csr(str(out_c), parsed, qorder, np.array(offs), np.concatenate(ids), np.concatenate(scs), "tag-x", n_threads=3)
+    assert out_c.read_bytes() == out_py.read_bytes()
