@@ -1,44 +1,67 @@
 """
-Retriever result types (the search call's return contract; reference src/retrievers/base.py).
+Result record and retriever interface of the search call (the return contract of the hot path's first stage).
+
+Field names, the TREC line layout and the per-query min-max rule are the reference's
+(src/retrievers/base.py:14-29, :60-73); they are what scripts/02_retrieve.py::write_run serialises into
+`.res` / `.norm.res`, i.e. the 6-decimal values every later stage (03_qpp, 05_fusion) reads back.
 """
-from abc import ABC, abstractmethod
-from dataclasses import dataclass, field
-from typing import Any, Dict, List, Optional, Tuple
+from __future__ import annotations
+
+import abc
+import dataclasses
+from typing import Any, Dict, Iterable, List, Optional, Tuple
+
+Hit = Tuple[str, float, int]          # (docno, score, rank)
 
 
-@dataclass
+def trec_line(qid: str, hit: Hit, run_name: str) -> str:
+    """One run-file line; the score is printed with 6 decimals -- this rounding defines the downstream values."""
+    docno, score, rank = hit
+    return "%s Q0 %s %d %.6f %s" % (qid, docno, rank, score, run_name)
+
+
+def minmax_normalize(hits: Iterable[Hit]) -> List[Hit]:
+    """Per-query min-max of the scores: (s - lo) / (hi - lo), with a unit divisor when all scores are equal
+    (so a constant or single-document list maps to 0.0).  Docno and rank pass through untouched."""
+    hits = list(hits)
+    if len(hits) == 0:
+        return hits
+    lo = hi = hits[0][1]
+    for _, s, _ in hits[1:]:
+        lo = s if s < lo else lo
+        hi = s if s > hi else hi
+    span = (hi - lo) if hi > lo else 1.0
+    return [(d, (s - lo) / span, r) for d, s, r in hits]
+
+
+@dataclasses.dataclass
 class RetrieverResult:
-    """Standard retriever output (reference src/retrievers/base.py:14-29)."""
+    """What every retriever returns for one query."""
     qid: str
-    results: List[Tuple[str, float, int]]  # (docno, score, rank)
+    results: List[Hit]
     retriever_name: str
     latency_ms: float = 0.0
-    metadata: Dict[str, Any] = field(default_factory=dict)
+    metadata: Dict[str, Any] = dataclasses.field(default_factory=dict)
 
     def to_trec_lines(self, run_name: Optional[str] = None) -> List[str]:
-        name = run_name or self.retriever_name
-        return [f"{self.qid} Q0 {docno} {rank} {score:.6f} {name}" for docno, score, rank in self.results]
+        label = self.retriever_name if not run_name else run_name
+        return [trec_line(self.qid, h, label) for h in self.results]
 
 
-class BaseRetriever(ABC):
-    """Abstract base (reference src/retrievers/base.py:32-73)."""
+class BaseRetriever(abc.ABC):
+    """Interface shared by the retrievers; only BGE's flat inner-product search is implemented in this package."""
 
     name: str = "base"
 
-    @abstractmethod
+    @abc.abstractmethod
     def retrieve(self, query: str, qid: str, top_k: int = 100, **kwargs) -> RetrieverResult:
-        ...
+        raise NotImplementedError
 
     def retrieve_batch(self, queries: Dict[str, str], top_k: int = 100, **kwargs) -> Dict[str, RetrieverResult]:
-        return {qid: self.retrieve(query, qid, top_k, **kwargs) for qid, query in queries.items()}
+        out: Dict[str, RetrieverResult] = {}
+        for qid in queries:
+            out[qid] = self.retrieve(queries[qid], qid, top_k, **kwargs)
+        return out
 
-    @staticmethod
-    def normalize_scores(results: List[Tuple[str, float, int]]) -> List[Tuple[str, float, int]]:
-        """Per-query min-max producing the .norm.res values: (s - min) / (max - min if max > min else 1.0)
-        (reference src/retrievers/base.py:60-73).  A handful of floats per query; stays on the host."""
-        if not results:
-            return []
-        scores = [s for _, s, _ in results]
-        min_s, max_s = min(scores), max(scores)
-        range_s = max_s - min_s if max_s > min_s else 1.0
-        return [(docno, (score - min_s) / range_s, rank) for docno, score, rank in results]
+    # kept as a static method because callers use BaseRetriever.normalize_scores(docs) (scripts/02_retrieve.py:77)
+    normalize_scores = staticmethod(minmax_normalize)
