@@ -104,6 +104,7 @@ struct Misc {
   int flag_long;
   int flag_single;
   int wl_cnt;
+  int vec_ok;
   int n_u;
   int warp_tot[32];
   u64 red_min[32];
@@ -154,11 +155,12 @@ __global__ void __launch_bounds__(NT) fuse_kernel(const FuseParams p) {
   for (int q = blockIdx.x; q < p.Q; q += gridDim.x) {
     // ---------------------------------------------------------------- P0: stage the query's lists
     if (tid == 0) {
-      int acc = 0, bad = 0;
+      int acc = 0, bad = 0, vec = (K % 4 == 0) ? 1 : 0;
       for (int r = 0; r < R; ++r) {
         m.start[r] = acc;
         const int len = p.lens[(size_t)q * R + r];
         if (len < 0 || len > K) bad = 1;
+        if (len & 3) vec = 0;
         acc += bad ? 0 : len;
         m.w[r] = p.weights ? p.weights[(size_t)q * R + r] : 1.0;
       }
@@ -167,6 +169,7 @@ __global__ void __launch_bounds__(NT) fuse_kernel(const FuseParams p) {
       m.flag_long = 0;
       m.wl_cnt = 0;
       m.flag_status = bad ? QF_QSTAT_BAD_LEN : 0;
+      m.vec_ok = vec;
     }
     {
       u32* t32 = reinterpret_cast<u32*>(s_table);
@@ -185,11 +188,39 @@ __global__ void __launch_bounds__(NT) fuse_kernel(const FuseParams p) {
     {
       const int32_t* gid = p.doc_ids + (size_t)q * R * K;
       const raw_t* gsc = reinterpret_cast<const raw_t*>(p.scores) + (size_t)q * R * K;
-      for (int r = 0; r < R; ++r) {
-        const int s0 = m.start[r], len = m.start[r + 1] - s0;
-        for (int i = tid; i < len; i += NT) {
-          s_ids[s0 + i] = __ldg(gid + (size_t)r * K + i);
-          s_sc[s0 + i] = __ldg(gsc + (size_t)r * K + i);
+      const bool vec = m.vec_ok && ((reinterpret_cast<uintptr_t>(gid) | reinterpret_cast<uintptr_t>(gsc)) & 15) == 0;
+      if (vec) {
+        // every list length is a multiple of 4: 16-byte loads, all of a thread's loads in flight together
+        for (int c4 = tid * 4; c4 < n; c4 += NT * 4) {
+          const int r = list_of(m.start, R, c4);
+          const int i = c4 - m.start[r];
+          *reinterpret_cast<int4*>(s_ids + c4) = __ldg(reinterpret_cast<const int4*>(gid + (size_t)r * K + i));
+          if (sizeof(raw_t) == 4) {
+            *reinterpret_cast<int4*>(s_sc + c4) = __ldg(reinterpret_cast<const int4*>(gsc + (size_t)r * K + i));
+          } else {
+            const int4* src = reinterpret_cast<const int4*>(gsc + (size_t)r * K + i);
+            reinterpret_cast<int4*>(s_sc + c4)[0] = __ldg(src);
+            reinterpret_cast<int4*>(s_sc + c4)[1] = __ldg(src + 1);
+          }
+        }
+      } else {
+        for (int r = 0; r < R; ++r) {
+          const int s0 = m.start[r], len = m.start[r + 1] - s0;
+          for (int i = tid; i < len; i += NT) {
+            s_ids[s0 + i] = __ldg(gid + (size_t)r * K + i);
+            s_sc[s0 + i] = __ldg(gsc + (size_t)r * K + i);
+          }
+        }
+      }
+      // pull the NEXT query of this CTA into L2 while this one is being fused (one 128-byte line per thread)
+      const long long qn = (long long)q + gridDim.x;
+      if (qn < p.Q) {
+        const char* nid = reinterpret_cast<const char*>(p.doc_ids + (size_t)qn * R * K);
+        const char* nsc = reinterpret_cast<const char*>(reinterpret_cast<const raw_t*>(p.scores) + (size_t)qn * R * K);
+        const int id_lines = (R * K * 4 + 127) / 128, sc_lines = (R * K * (int)sizeof(raw_t) + 127) / 128;
+        for (int l = tid; l < id_lines + sc_lines; l += NT) {
+          const char* a = l < id_lines ? nid + (size_t)l * 128 : nsc + (size_t)(l - id_lines) * 128;
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
         }
       }
     }
