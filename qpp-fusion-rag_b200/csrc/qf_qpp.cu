@@ -76,6 +76,7 @@ __global__ void __launch_bounds__(NT) qpp_kernel(const QppParams p) {
                                                         // (a depth bucket holds at most 2 sample entries)
   __shared__ unsigned short s_samp[WARPS][MAXK];
   __shared__ double s_pw[MAXLIST];             // p^(d-1)
+  __shared__ double s_uefw[20];                // UEF rank weights 1 / log2(i + 2)
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool research = p.perms != nullptr;
@@ -83,6 +84,7 @@ __global__ void __launch_bounds__(NT) qpp_kernel(const QppParams p) {
   if (research) {
     for (int d = tid; d < p.K && d < MAXLIST; d += NT) s_pw[d] = pow(p09, (double)d);
   }
+  if (tid < 20) s_uefw[tid] = 1.0 / (log((double)(tid + 2)) / log(2.0));
   __syncthreads();
 
   const long long n_lists = (long long)p.Q * p.R;
@@ -128,16 +130,15 @@ __global__ void __launch_bounds__(NT) qpp_kernel(const QppParams p) {
       col[0] = var;                                                      // nqc          :202-216
       {                                                                  // smv          :223-239
         const double mu = mean <= 0 ? 1.0 : mean;
-        double a = 0.0, ar = 0.0;
+        double a = 0.0;
         for (int j = lane; j < k; j += 32) {
           const double s = x[j];
-          if (s > 0) {
-            a += s * fabs(log(s / mu));
-            if (mean > 0) ar += s * fabs(log(s / mean));
-          }
+          if (s > 0) a += s * fabs(log(s / mu));
         }
         col[1] = qf::warp_sum(a) / kk;
-        col[14] = (qf::warp_sum(ar) / kk) * 1.0;                         // smv_research SMVSpecificity.java:22-45
+        // smv_research (SMVSpecificity.java:22-45) skips every term when the mean is <= 0 instead of falling
+        // back to mu = 1; for a positive mean the two definitions coincide (avgIDF = 1 without an index)
+        col[14] = mean > 0 ? col[1] : 0.0;
       }
       {                                                                  // wig          :247-262
         const double base = 1.0 / fmax(0.01, mean);
@@ -205,7 +206,7 @@ __global__ void __launch_bounds__(NT) qpp_kernel(const QppParams p) {
         const int kk20 = min(20, k);
         double u = 0.0, ws = 0.0;
         for (int i = lane; i < kk20; i += 32) {
-          const double w = 1.0 / (log((double)(i + 2)) / log(2.0));
+          const double w = s_uefw[i];
           u += x[i] * w;
           ws += w;
         }
@@ -218,7 +219,9 @@ __global__ void __launch_bounds__(NT) qpp_kernel(const QppParams p) {
             const double r = x[j];
             if (r > 0) {
               const double f2 = ((r - mean) * (r - mean)) / r;
-              a += pow(pow(1.0, 0.33) * pow(f2, 0.33), 0.33);
+              // pow(pow(1, a) * pow(f2, b), g) with a = b = g = 0.33: pow(1, a) == 1 exactly; the nested power is
+              // evaluated as one pow with exponent b*g (differs from the nested form by <= 2 ulp; tolerance 1e-5)
+              a += pow(f2, 0.33 * 0.33);
             }
           }
           col[10] = qf::warp_sum(a) / kk;

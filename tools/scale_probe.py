@@ -1,0 +1,52 @@
+#!/usr/bin/env python3
+"""Larger BASELINE.json shapes on one GPU (dev probe, not the bench):
+   C4  HotpotQA-shaped dense search: 7,405 queries x 5,233,329 docs, top-1000
+   C5' query sweep for fusion: QPP + W-CombSUM over 200,000 queries x 5 x top-1000 (1/5 of the 1M-query config)"""
+import os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "qpp-fusion-rag_b200"))
+import torch
+import bench
+from qppfusion import ops
+
+dev = torch.device("cuda:0")
+if "dense" in sys.argv[1:] or len(sys.argv) == 1:
+    Q, N, D, k = 7405, 5_233_329, 768, 1000
+    q32, corpus = bench.synth_dense(Q, N, D, 7, dev)
+    qb = q32.to(torch.bfloat16)
+    for _ in range(2):
+        sc, ids, st = torch.ops.qppfusion.dense_topk(qb, corpus, k, 0)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        sc, ids, st = torch.ops.qppfusion.dense_topk(qb, corpus, k, 0)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 3
+    print(f"C4 dense 7405 x 5.23M: {ms:.2f} ms  {Q / ms * 1e3:.0f} QPS  {2.0 * Q * N * D / ms / 1e9:.0f} TFLOP/s whole call; "
+          f"threshold failures {int((st != 0).sum())}")
+    del corpus
+    torch.cuda.empty_cache()
+if "fuse" in sys.argv[1:] or len(sys.argv) == 1:
+    Qs = 200_000
+    parts = [bench.synth_device(50_000, 5, 1000, 100 + i, dev) for i in range(Qs // 50_000)]
+    ids = torch.cat([p[0] for p in parts]); micro = torch.cat([p[1] for p in parts])
+    lens = torch.cat([p[2] for p in parts]); feats = torch.cat([p[3] for p in parts])
+    del parts
+    def step():
+        qpp, _ = ops.qpp_stats(micro, lens, feats, None, None, top_k=100, k_cut=50)
+        ops.qpp_colnorm_(qpp, "minmax", round6=True)
+        w = ops.qpp_select_weight(qpp, 5)
+        return ops.fuse(ids, micro, lens, w, None, 0, 0, 60.0, 0, want_counts=False, want_pos=False)
+    out = step(); torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+    ev[0].record(); qpp, _ = ops.qpp_stats(micro, lens, feats, None, None, top_k=100, k_cut=50)
+    ev[1].record(); ops.qpp_colnorm_(qpp, "minmax", round6=True)
+    ev[2].record(); w = ops.qpp_select_weight(qpp, 5)
+    ev[3].record(); o2 = ops.fuse(ids, micro, lens, w, None, 0, 0, 60.0, 0, want_counts=False, want_pos=False)
+    ev[4].record(); torch.cuda.synchronize()
+    print("   per-op ms: qpp %.2f colnorm %.2f select %.2f fuse %.2f" % tuple(ev[i].elapsed_time(ev[i + 1]) for i in range(4)))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); out = step(); e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    print(f"C5' fusion sweep {Qs} queries: {ms:.1f} ms  {Qs / ms * 1e3:.0f} fused queries/s; status max {int(out.status.max())}")
