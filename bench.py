@@ -243,7 +243,7 @@ def dense_leg(args, dev, world, rank):
             "whole_call_tflops": 2.0 * Q * N_DENSE * D / (ms * 1e-3) / 1e12,
             "e2e": {"value": Q / (e2e_ms * 1e-3), "unit": "queries/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": Q * D * 4, "d2h_bytes_per_step": Q * k * 8},
-            "threshold_failures": status_bad, "parity": parity, "gpu_launches": 5 * steps, "clocks": clocks}
+            "threshold_failures": status_bad, "parity": parity, "gpu_launches": (4 + (1 if world > 1 else 0)) * (2 * steps + 4), "clocks": clocks}
 
 
 def run_ours(args):
