@@ -15,8 +15,10 @@
 //   P5  ranking: stable LSD radix sort (8-bit digits, warp match ranking, no atomics) on the top
 //       32 bits of a range-normalised descending key, then an exact fix-up of equal-prefix runs by
 //       full float64 comparison (long runs fall back to a full 64-bit sort)
-#include "qf_common.cuh"
+#include "qf_fuse_shared.cuh"
 #include "qf_radix.cuh"
+
+#include <stdlib.h>
 
 namespace {
 
@@ -25,38 +27,16 @@ using u32 = unsigned int;
 using u64 = unsigned long long;
 
 constexpr u16 EMPTY16 = 0xFFFFu;
-constexpr int MAX_R = 32;
+constexpr int MAX_R = qf::FUSE_MAX_R;
 #ifndef QF_FUSE_NT
 #define QF_FUSE_NT 512
 #endif
-constexpr u32 QF_FLAG_DEBUG_FULLSORT = 0x100u;   // test hook: force the 64-bit sort path
+constexpr u32 QF_FLAG_DEBUG_FULLSORT = qf::FUSE_FLAG_DEBUG_FULLSORT;
+constexpr int FIXLIST = 1024;                    // fix-up mode: deferred queries collected per scan window
 
-struct FuseParams {
-  const int32_t* doc_ids;
-  const void* scores;
-  const int32_t* ranks;
-  const int32_t* lens;
-  const double* weights;
-  int Q, R, K;
-  int method, norm;
-  double rrf_k;
-  u32 flags;
-  int32_t* out_ids;
-  double* out_scores;
-  u16* out_counts;
-  u16* out_pos;
-  int32_t* out_lens;
-  int32_t* out_status;
-};
-
-template <int ST> struct ScoreT;
-template <> struct ScoreT<QF_SCORE_F64>   { using type = double; };
-template <> struct ScoreT<QF_SCORE_F32>   { using type = float; };
-template <> struct ScoreT<QF_SCORE_MICRO> { using type = int; };
-
-__device__ __forceinline__ double raw_to_f64(double v) { return v; }
-__device__ __forceinline__ double raw_to_f64(float v) { return (double)v; }
-__device__ __forceinline__ double raw_to_f64(int v) { return qf::micro_to_f64(v); }
+using qf::FuseParams;
+using qf::ScoreT;
+using qf::raw_to_f64;
 
 // Shared-memory carve-up.  Region X (scores/table/slot_of/tag) is dead once P2 is done and is reused
 // by the sort buffers.
@@ -91,7 +71,8 @@ struct Layout {
   static constexpr size_t off_uslot = align16(off_acc + sizeof(double) * H);
   static constexpr size_t off_whist = align16(off_uslot + sizeof(u16) * CAP);
   static constexpr size_t off_misc = align16(off_whist + sizeof(u16) * NW * 256);
-  static constexpr size_t total = off_misc + 2048;
+  static constexpr size_t off_fix = off_misc + 2048;           // fix-up mode work list
+  static constexpr size_t total = off_fix + sizeof(int) * FIXLIST;
 };
 
 struct Misc {
@@ -104,6 +85,7 @@ struct Misc {
   int flag_long;
   int flag_single;
   int wl_cnt;
+  int fix_n;
   int vec_ok;
   int n_u;
   int warp_tot[32];
@@ -152,7 +134,34 @@ __global__ void __launch_bounds__(NT) fuse_kernel(const FuseParams p) {
   const int R = p.R, K = p.K;
   const size_t out_stride = (size_t)R * K;
 
-  for (int q = blockIdx.x; q < p.Q; q += gridDim.x) {
+  // Normal mode: grid-stride over all queries.  Fix-up mode (p.fixup): this CTA owns a contiguous span of queries,
+  // scans their out_lens in windows of FIXLIST and fuses only the ones the streaming kernel deferred.
+  int* s_fix = reinterpret_cast<int*>(smem + L::off_fix);
+  const int span = p.fixup ? (p.Q + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  int fix_win = 0, fix_k = 0, fix_n = 0;
+  for (int it = 0;; ++it) {
+    int q;
+    if (!p.fixup) {
+      q = blockIdx.x + it * gridDim.x;
+      if (q >= p.Q) break;
+    } else {
+      while (fix_k >= fix_n && fix_win < span) {
+        __syncthreads();
+        if (tid == 0) m.fix_n = 0;
+        __syncthreads();
+        const int wend = min(span, fix_win + FIXLIST);
+        for (int j = fix_win + tid; j < wend; j += NT) {
+          const long long qq = (long long)blockIdx.x * span + j;
+          if (qq < p.Q && p.out_lens[qq] == qf::FUSE_DEFERRED) s_fix[atomicAdd(&m.fix_n, 1)] = (int)qq;
+        }
+        __syncthreads();
+        fix_n = m.fix_n;
+        fix_k = 0;
+        fix_win = wend;
+      }
+      if (fix_k >= fix_n) break;
+      q = s_fix[fix_k++];
+    }
     // ---------------------------------------------------------------- P0: stage the query's lists
     if (tid == 0) {
       int acc = 0, bad = 0, vec = (K % 4 == 0) ? 1 : 0;
@@ -213,7 +222,7 @@ __global__ void __launch_bounds__(NT) fuse_kernel(const FuseParams p) {
         }
       }
       // pull the NEXT query of this CTA into L2 while this one is being fused (one 128-byte line per thread)
-      const long long qn = (long long)q + gridDim.x;
+      const long long qn = p.fixup ? (long long)p.Q : (long long)q + gridDim.x;
       if (qn < p.Q) {
         const char* nid = reinterpret_cast<const char*>(p.doc_ids + (size_t)qn * R * K);
         const char* nsc = reinterpret_cast<const char*>(reinterpret_cast<const raw_t*>(p.scores) + (size_t)qn * R * K);
@@ -612,8 +621,16 @@ extern "C" int qf_fuse(const int32_t* doc_ids, const void* scores, int score_typ
   int rc = qf::check_device();
   if (rc != QF_OK) return rc;
   FuseParams p{doc_ids, scores, ranks, lens, weights, Q, R, K, method, norm, rrf_k, flags,
-               out_ids, out_scores, out_counts, out_pos, out_lens, out_status};
+               out_ids, out_scores, out_counts, out_pos, out_lens, out_status, 0};
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (qf::fuse_stream_supported(p)) {
+    // common case: streaming kernel; the general kernel then finishes whatever it deferred (usually nothing)
+    rc = qf::fuse_stream_launch(p, score_type, st);
+    if (rc != QF_OK) return rc;
+    p.fixup = 1;
+    static const bool no_fixup = getenv("QF_STREAM_NOFIXUP") != nullptr;   // debug hook: leave deferred queries marked
+    if (no_fixup) return QF_OK;
+  }
   switch (score_type) {
     case QF_SCORE_F64: return dispatch_cap<QF_SCORE_F64>(p, st);
     case QF_SCORE_F32: return dispatch_cap<QF_SCORE_F32>(p, st);

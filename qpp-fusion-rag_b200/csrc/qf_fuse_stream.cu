@@ -1,0 +1,631 @@
+// qf_fuse_stream: rank fusion without staging -- every posting is read from HBM exactly once, straight into the
+// hash-accumulate step; several CTAs per SM (one query each) so one query's barriers hide behind another's work.
+//
+// Replaces ranx.fuse (reference src/fusion.py:182,201,226) and the weighted_* Python dict loops
+// (src/fusion.py:266-278, 309-327, 361-377); semantics in include/qppfusion.h.  Per query:
+//   A  lists are visited in ranker order, one barrier per list.  Each posting (16-byte loads, next chunk
+//      prefetched into registers) claims / finds its doc's slot of an open-addressing table with one shared-memory
+//      atomicCAS on the 32-bit doc id, marks list r in the slot's bit mask with one atomicOr (a second posting of the
+//      same doc in the same list sees the bit -> the query is deferred to the general kernel's exact sequential
+//      path) and adds its contribution to the slot's float64 accumulator with a plain read-modify-write: doc ids
+//      are distinct inside a list and lists are separated by barriers, so the additions happen in exactly the
+//      reference's order ((w0*s0 + w1*s1) + ...), no FMA contraction.  The claiming posting is the doc's FIRST-SEEN
+//      posting; its sequence number goes into the upper half of the mask word (tie-break key).
+//   B  final score (MNZ multiply by popcount, -0.0 -> +0.0), min/max over the union.
+//   C  ranking by ONE bucket pass instead of a multi-pass radix sort: a 64-bin histogram of a 1-in-16 sample
+//      gives a monotone piecewise-linear map score -> bucket (histogram equalisation, so skewed score
+//      distributions still spread evenly over the 2048 buckets); shared-memory atomicAdd assigns a slot in the
+//      bucket, a block scan turns counts into bases, and each doc's exact rank is its bucket base plus the number
+//      of bucket mates that precede it under the exact comparison (score desc as float64, first-seen asc).
+//      Buckets longer than LONGB (long runs of exactly tied scores) defer the query.
+//   D  (id, score[, count, first-seen index]) written straight to the ranked position (bucket order makes the
+//      stores nearly coalesced).
+// Deferred queries (out_lens = FUSE_DEFERRED) are finished by qf_fuse.cu's general kernel in the same stream.
+#include "qf_fuse_shared.cuh"
+
+#include <stdlib.h>
+
+namespace {
+
+using namespace qf;
+using u16 = unsigned short;
+using u32 = unsigned int;
+using u64 = unsigned long long;
+
+constexpr u32 EMPTY = 0xFFFFFFFFu;
+constexpr int SMAX_R = 16;       // list bit mask is the low half of the meta word
+constexpr int CB = 64;           // coarse bins of the equalisation histogram
+constexpr int MAXPROBE = 192;
+constexpr int LONGB = 160;       // longest bucket ranked by pairwise comparison
+
+struct SMisc {
+  int start[SMAX_R + 1];
+  int len[SMAX_R];
+  int ins[SMAX_R];
+  double w[SMAX_R], mn[SMAX_R], den[SMAX_R];
+  double red_mn[16], red_mx[16];
+  int red_cnt[16];
+  int warp_tot[16];
+  int status;
+};
+
+template <int HBITS, int UCAP, int NBBITS, int NMAX, int NT>
+struct SLayout {
+  static constexpr int H = 1 << HBITS;
+  static constexpr int NB = 1 << NBBITS;
+  static constexpr int BW = NMAX / 32;                         // first-seen bitmap words
+  static constexpr size_t a16(size_t x) { return (x + 15) & ~size_t(15); }
+  static constexpr size_t off_keys = 0;
+  static constexpr size_t off_meta = off_keys + 4 * H;
+  static constexpr size_t off_acc = off_meta + 4 * H;
+  static constexpr size_t off_cnt = off_acc + 8 * H;
+  static constexpr size_t off_order = off_cnt + 2 * NB;        // u16 order[UCAP]; aliases bitmap + prefix (dead before S4)
+  static constexpr size_t order_bytes = (2 * UCAP > 6 * BW) ? 2 * UCAP : 6 * BW;
+  static constexpr size_t off_coarse = a16(off_order + order_bytes);
+  static constexpr size_t off_misc = a16(off_coarse + 4 * CB * 3);
+  static constexpr size_t total = a16(off_misc + sizeof(SMisc));
+  static_assert(NB / 8 <= NT, "bucket scan: 8 counters per thread");
+  static_assert(UCAP < H && NMAX % 32 == 0 && NMAX <= 65536 && UCAP < 65536, "layout");
+  static_assert(NT / 32 <= 16 && NT / 32 >= 2, "warps");
+};
+
+__device__ __forceinline__ int warp_sum_int(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <typename raw_t> struct Chunk {
+  int id[4];
+  raw_t sc[4];
+  int rk[4];
+};
+
+template <int HBITS, int UCAP, int NBBITS, int NMAX, int NT, int MINB, int ST>
+__global__ void __launch_bounds__(NT, MINB) fuse_stream_kernel(const FuseParams p) {
+  using L = SLayout<HBITS, UCAP, NBBITS, NMAX, NT>;
+  using raw_t = typename ScoreT<ST>::type;
+  constexpr int H = L::H, NB = L::NB, NW = NT / 32, SPT = (H + NT - 1) / NT, CH = NT * 4, BW = L::BW;
+
+  extern __shared__ __align__(16) unsigned char smem[];
+  u32* s_keys = reinterpret_cast<u32*>(smem + L::off_keys);
+  u32* s_meta = reinterpret_cast<u32*>(smem + L::off_meta);
+  double* s_acc = reinterpret_cast<double*>(smem + L::off_acc);
+  u32* s_cnt32 = reinterpret_cast<u32*>(smem + L::off_cnt);
+  u16* s_base16 = reinterpret_cast<u16*>(smem + L::off_cnt);
+  u16* s_order = reinterpret_cast<u16*>(smem + L::off_order);
+  u32* s_bitmap = reinterpret_cast<u32*>(smem + L::off_order);
+  u16* s_bpre = reinterpret_cast<u16*>(smem + L::off_order + 4 * BW);
+  int* s_chist = reinterpret_cast<int*>(smem + L::off_coarse);
+  float* s_ccum = reinterpret_cast<float*>(smem + L::off_coarse + 4 * CB);
+  float* s_cw = reinterpret_cast<float*>(smem + L::off_coarse + 8 * CB);
+  SMisc& m = *reinterpret_cast<SMisc*>(smem + L::off_misc);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int R = p.R, K = p.K;
+  const size_t out_stride = (size_t)R * K;
+  const bool is_rrf = (p.method == QF_METHOD_RRF);
+  const bool is_mnz = (p.method == QF_METHOD_MNZ);
+  const bool weighted = (p.weights != nullptr);
+  const bool skip_zero = (p.flags & QF_FLAG_MNZ_SKIP_ZERO) != 0;
+  const bool check_sorted = (p.flags & QF_FLAG_REQUIRE_SORTED) != 0;
+  const bool unranked = (p.flags & QF_FLAG_UNRANKED_OUTPUT) != 0;
+  const bool minmax = (p.norm == QF_NORM_MINMAX) && !is_rrf;
+  const bool need_scores = !is_rrf || check_sorted;
+  const bool want_pos = (p.out_pos != nullptr);
+
+  for (int q = blockIdx.x; q < p.Q; q += gridDim.x) {
+    __syncthreads();                       // previous query's shared state is dead
+    // ------------------------------------------------------------ header + table reset
+    if (warp == 0) {
+      int len = 0;
+      if (lane < R) len = __ldg(p.lens + (size_t)q * R + lane);
+      const unsigned badm = __ballot_sync(0xffffffffu, lane < R && (len < 0 || len > K));
+      const int l = badm ? 0 : len;
+      int incl = l;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      if (lane < R) {
+        m.start[lane] = incl - l;
+        m.len[lane] = l;
+        m.ins[lane] = 0;
+        m.w[lane] = weighted ? __ldg(p.weights + (size_t)q * R + lane) : 1.0;
+      }
+      if (lane == R - 1) m.start[R] = incl;
+      if (lane == 0) m.status = badm ? QF_QSTAT_BAD_LEN : 0;
+    }
+    {
+      uint4* k4 = reinterpret_cast<uint4*>(s_keys);
+      uint4* m4 = reinterpret_cast<uint4*>(s_meta);
+      for (int i = tid; i < H / 4; i += NT) {
+        k4[i] = make_uint4(EMPTY, EMPTY, EMPTY, EMPTY);
+        m4[i] = make_uint4(0u, 0u, 0u, 0u);
+      }
+      for (int i = tid; i < NB / 2; i += NT) s_cnt32[i] = 0u;
+      for (int i = tid; i < BW; i += NT) s_bitmap[i] = 0u;
+      for (int i = tid; i < CB; i += NT) s_chist[i] = 0;
+    }
+    __syncthreads();
+    const int n = m.start[R];
+    if ((m.status & QF_QSTAT_BAD_LEN) || n == 0) {
+      if (tid == 0) {
+        p.out_lens[q] = 0;
+        if (p.out_status) p.out_status[q] = m.status;
+      }
+      continue;
+    }
+    const int32_t* gid = p.doc_ids + (size_t)q * R * K;
+    const raw_t* gsc = reinterpret_cast<const raw_t*>(p.scores) + (size_t)q * R * K;
+    const int32_t* grk = (is_rrf && p.ranks) ? p.ranks + (size_t)q * R * K : nullptr;
+    {   // pull the NEXT query of this CTA into L2 while this one is being fused
+      const long long qn = (long long)q + gridDim.x;
+      if (qn < p.Q) {
+        const char* nid = reinterpret_cast<const char*>(p.doc_ids + (size_t)qn * R * K);
+        const char* nsc = reinterpret_cast<const char*>(reinterpret_cast<const raw_t*>(p.scores) + (size_t)qn * R * K);
+        const int id_lines = (R * K * 4 + 127) / 128;
+        const int sc_lines = need_scores ? (R * K * (int)sizeof(raw_t) + 127) / 128 : 0;
+        for (int l = tid; l < id_lines + sc_lines; l += NT) {
+          const char* a = l < id_lines ? nid + (size_t)l * 128 : nsc + (size_t)(l - id_lines) * 128;
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+        }
+      }
+    }
+    // ------------------------------------------------------------ ranx min-max: per-list min and range
+    if (minmax) {
+      for (int r = warp; r < R; r += NW) {
+        const raw_t* gs = gsc + (size_t)r * K;
+        const int len = m.len[r];
+        double mn = INFINITY, mx = -INFINITY;
+        for (int i = lane; i < len; i += 32) {
+          const double v = raw_to_f64(__ldg(gs + i));
+          mn = fmin(mn, v);
+          mx = fmax(mx, v);
+        }
+        mn = warp_min(mn);
+        mx = warp_max(mx);
+        if (lane == 0) {
+          m.mn[r] = mn;
+          const double d = __dsub_rn(mx, mn);
+          m.den[r] = d > 1e-9 ? d : 1e-9;     // ranx: max(max - min, 1e-9)
+        }
+      }
+      __syncthreads();
+    }
+
+    // ------------------------------------------------------------ A: hash-accumulate, list by list
+    const bool vec = (K % 4 == 0) &&
+                     ((reinterpret_cast<uintptr_t>(gid) | reinterpret_cast<uintptr_t>(gsc) |
+                       reinterpret_cast<uintptr_t>(grk)) & 15) == 0;
+    auto load = [&](Chunk<raw_t>& c, int r, int base) {
+      const int len = m.len[r];
+      const int32_t* gi = gid + (size_t)r * K;
+      const raw_t* gs = gsc + (size_t)r * K;
+      if (vec) {
+        const int i0 = base + tid * 4;
+        if (i0 < len) {                       // K % 4 == 0 and len <= K: the 4-wide load stays inside the row
+          const int4 v = __ldg(reinterpret_cast<const int4*>(gi + i0));
+          c.id[0] = v.x; c.id[1] = v.y; c.id[2] = v.z; c.id[3] = v.w;
+          if (need_scores) {
+            if constexpr (sizeof(raw_t) == 4) {
+              const int4 s = __ldg(reinterpret_cast<const int4*>(gs + i0));
+              c.sc[0] = *reinterpret_cast<const raw_t*>(&s.x);
+              c.sc[1] = *reinterpret_cast<const raw_t*>(&s.y);
+              c.sc[2] = *reinterpret_cast<const raw_t*>(&s.z);
+              c.sc[3] = *reinterpret_cast<const raw_t*>(&s.w);
+            } else {
+              const double2 s0 = __ldg(reinterpret_cast<const double2*>(gs + i0));
+              const double2 s1 = __ldg(reinterpret_cast<const double2*>(gs + i0) + 1);
+              c.sc[0] = (raw_t)s0.x; c.sc[1] = (raw_t)s0.y; c.sc[2] = (raw_t)s1.x; c.sc[3] = (raw_t)s1.y;
+            }
+          }
+          if (grk) {
+            const int4 k4 = __ldg(reinterpret_cast<const int4*>(grk + (size_t)r * K + i0));
+            c.rk[0] = k4.x; c.rk[1] = k4.y; c.rk[2] = k4.z; c.rk[3] = k4.w;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int i = base + j * NT + tid;
+          if (i < len) {
+            c.id[j] = __ldg(gi + i);
+            if (need_scores) c.sc[j] = __ldg(gs + i);
+            if (grk) c.rk[j] = __ldg(grk + (size_t)r * K + i);
+          }
+        }
+      }
+    };
+
+    bool defer = false, bad_order = false;
+    int ins = 0;
+    auto process = [&](const Chunk<raw_t>& c, int r, int base) {
+      const int len = m.len[r], s0 = m.start[r];
+      const double w = m.w[r];
+      const double lmn = minmax ? m.mn[r] : 0.0, lden = minmax ? m.den[r] : 1.0;
+      int idx[4];
+      bool valid[4];
+      u32 h[4], old[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        idx[j] = vec ? base + tid * 4 + j : base + j * NT + tid;
+        valid[j] = idx[j] < len;
+      }
+      if (check_sorted) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (valid[j] && idx[j] > 0) {
+            const raw_t prev = (vec && j > 0) ? c.sc[j > 0 ? j - 1 : 0] : __ldg(gsc + (size_t)r * K + idx[j] - 1);
+            if (prev < c.sc[j]) bad_order = true;
+          }
+      }
+      if (grk) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (valid[j] && idx[j] > 0) {
+            const int prev = (vec && j > 0) ? c.rk[j > 0 ? j - 1 : 0] : __ldg(grk + (size_t)r * K + idx[j] - 1);
+            if (prev > c.rk[j]) bad_order = true;
+          }
+      }
+      // first probe of all four postings back to back, then resolve
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (valid[j]) {
+          if ((u32)c.id[j] == EMPTY) {
+            defer = true;
+            valid[j] = false;
+          } else {
+            h[j] = ((u32)c.id[j] * 2654435761u) >> (32 - HBITS);
+            old[j] = atomicCAS(&s_keys[h[j]], EMPTY, (u32)c.id[j]);
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (!valid[j]) continue;
+        const u32 id = (u32)c.id[j];
+        u32 hh = h[j], o = old[j];
+        int probes = 0;
+        while (o != EMPTY && o != id) {
+          if (++probes > MAXPROBE) break;
+          hh = (hh + 1) & (H - 1);
+          o = atomicCAS(&s_keys[hh], EMPTY, id);
+        }
+        if (o != EMPTY && o != id) {
+          defer = true;
+          continue;
+        }
+        double v;
+        bool counts = true;
+        if (is_rrf) {
+          const double rank = grk ? (double)c.rk[j] : (double)(idx[j] + 1);
+          v = __ddiv_rn(w, __dadd_rn(p.rrf_k, rank));
+        } else {
+          double s = raw_to_f64(c.sc[j]);
+          if (minmax) s = __ddiv_rn(__dsub_rn(s, lmn), lden);
+          if (skip_zero && s == 0.0) counts = false;
+          v = weighted ? __dmul_rn(w, s) : s;
+        }
+        u32 bits = 1u << r;
+        if (skip_zero && counts) bits |= 1u << (8 + r);
+        if (o == EMPTY) {
+          ++ins;
+          bits |= (u32)(s0 + idx[j]) << 16;
+        }
+        const u32 om = atomicOr(&s_meta[hh], bits);
+        if (om & (1u << r)) {
+          defer = true;                                  // the doc id occurs twice inside list r
+        } else if (o == EMPTY) {
+          s_acc[hh] = __dadd_rn(0.0, v);                 // the reference starts from 0.0 (src/fusion.py:275)
+        } else {
+          s_acc[hh] = __dadd_rn(s_acc[hh], v);
+        }
+      }
+    };
+
+    bool deferred = false;
+    {
+      int r = 0, base = 0, total_ins = 0;
+      while (r < R && m.len[r] == 0) ++r;
+      Chunk<raw_t> cur, nxt;
+      load(cur, r, base);
+      while (r < R) {
+        int r2 = r, b2 = base + CH;
+        if (b2 >= m.len[r2]) {
+          b2 = 0;
+          do { ++r2; } while (r2 < R && m.len[r2] == 0);
+        }
+        if (r2 < R) load(nxt, r2, b2);
+        process(cur, r, base);
+        if (r2 != r) {                                   // list boundary
+          const int wi = warp_sum_int(ins);
+          ins = 0;
+          if (lane == 0 && wi) atomicAdd(&m.ins[r], wi);
+          const int stop = __syncthreads_or(defer ? 1 : 0);
+          total_ins += m.ins[r];
+          if (stop || total_ins > UCAP) {
+            deferred = true;
+            break;
+          }
+        }
+        cur = nxt;
+        r = r2;
+        base = b2;
+      }
+    }
+    if (bad_order) atomicOr(&m.status, QF_QSTAT_UNSORTED);
+    if (deferred) {
+      if (tid == 0) p.out_lens[q] = FUSE_DEFERRED;
+      continue;
+    }
+
+    // ------------------------------------------------------------ B: final scores, range, sample
+    auto cntbits = [&](u32 mt) -> int { return __popc(skip_zero ? ((mt >> 8) & 0xFFu) : (mt & 0xFFFFu)); };
+    double fmn = INFINITY, fmx = -INFINITY, samp = 0.0;
+    int n_u = 0;
+    bool has = false;
+#pragma unroll
+    for (int k = 0; k < SPT; ++k) {
+      const int slot = tid + k * NT;
+      if (slot < H && s_keys[slot] != EMPTY) {
+        const u32 mt = s_meta[slot];
+        double a = s_acc[slot];
+        if (is_mnz) a = __dmul_rn(a, (double)cntbits(mt));
+        a = __dadd_rn(a, 0.0);               // -0.0 -> +0.0 (Python: -0.0 == 0.0 is a tie)
+        s_acc[slot] = a;
+        fmn = a < fmn ? a : fmn;
+        fmx = a > fmx ? a : fmx;
+        if (!has) {
+          samp = a;
+          has = true;
+        }
+        ++n_u;
+        if (want_pos) atomicOr(&s_bitmap[mt >> 21], 1u << ((mt >> 16) & 31u));
+      }
+    }
+    fmn = warp_min(fmn);
+    fmx = warp_max(fmx);
+    n_u = warp_sum_int(n_u);
+    if (lane == 0) {
+      m.red_mn[warp] = fmn;
+      m.red_mx[warp] = fmx;
+      m.red_cnt[warp] = n_u;
+    }
+    __syncthreads();
+    fmn = INFINITY;
+    fmx = -INFINITY;
+    n_u = 0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+      fmn = m.red_mn[w] < fmn ? m.red_mn[w] : fmn;
+      fmx = m.red_mx[w] > fmx ? m.red_mx[w] : fmx;
+      n_u += m.red_cnt[w];
+    }
+    if (n_u > UCAP) {                         // cannot happen after the per-list check; kept as a guard
+      if (tid == 0) p.out_lens[q] = FUSE_DEFERRED;
+      continue;
+    }
+    const bool score_mode = !unranked && (fmx > fmn);
+    double cscale = 0.0;
+    if (score_mode) {
+      cscale = (double)CB / __dsub_rn(fmx, fmn);
+      if (!(cscale > 0.0) || isinf(cscale)) cscale = 0.0;
+    }
+    auto coarse = [&](double fs, float& frac) -> int {
+      const float tf = (float)__dmul_rn(__dsub_rn(fmx, fs), cscale);     // monotone in fs
+      int c = (int)tf;
+      c = c < 0 ? 0 : (c > CB - 1 ? CB - 1 : c);
+      frac = tf - (float)c;
+      return c;
+    };
+    if (score_mode && has) {
+      float fr;
+      atomicAdd(&s_chist[coarse(samp, fr)], 1);
+    }
+    __syncthreads();
+    // ------------------------------------------------------------ C: equalisation map, first-seen prefix
+    if (warp == 0 && score_mode) {
+      const int h0 = s_chist[2 * lane] + 1, h1 = s_chist[2 * lane + 1] + 1;
+      const int tot = warp_sum_int(h0 + h1);
+      const int w0 = (h0 * NB) / tot, w1 = (h1 * NB) / tot;
+      int incl = w0 + w1;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      const int excl = incl - (w0 + w1);
+      s_ccum[2 * lane] = (float)excl;
+      s_cw[2 * lane] = (float)w0;
+      s_ccum[2 * lane + 1] = (float)(excl + w0);
+      s_cw[2 * lane + 1] = (float)w1;
+    }
+    if (warp == 1 && want_pos) {
+      int carry = 0;
+      for (int b0 = 0; b0 < BW; b0 += 32) {
+        const int wd = (b0 + lane < BW) ? __popc(s_bitmap[b0 + lane]) : 0;
+        int incl = wd;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int t = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += t;
+        }
+        if (b0 + lane < BW) s_bpre[b0 + lane] = (u16)(carry + incl - wd);
+        carry += __shfl_sync(0xffffffffu, incl, 31);
+      }
+    }
+    __syncthreads();
+    const u32 tie_div = (u32)(want_pos ? n_u : n);       // range of the tie-break key in the meta word
+    auto bucket = [&](double fs, u32 tie) -> int {
+      int b;
+      if (score_mode) {
+        float frac;
+        const int c = coarse(fs, frac);
+        b = (int)fmaf(frac, s_cw[c], s_ccum[c]);          // monotone: cum[c] + frac*w[c] <= cum[c+1]
+      } else {
+        b = (int)((tie * (u32)NB) / tie_div);             // first-seen order only
+      }
+      return b < 0 ? 0 : (b > NB - 1 ? NB - 1 : b);
+    };
+    // bucket counts; the atomicAdd's old value is the doc's offset inside its bucket
+    u32 packed[SPT];
+#pragma unroll
+    for (int k = 0; k < SPT; ++k) {
+      const int slot = tid + k * NT;
+      packed[k] = 0xFFFFFFFFu;
+      if (slot < H && s_keys[slot] != EMPTY) {
+        const u32 mt = s_meta[slot];
+        u32 tie = mt >> 16;
+        if (want_pos) {      // first-seen sequence number -> first-seen index (same order, dense)
+          tie = (u32)s_bpre[tie >> 5] + (u32)__popc(s_bitmap[tie >> 5] & ((1u << (tie & 31u)) - 1u));
+          s_meta[slot] = (tie << 16) | (mt & 0xFFFFu);
+        }
+        const int b = bucket(s_acc[slot], tie);
+        const int sh = (b & 1) * 16;
+        const u32 oldc = atomicAdd(&s_cnt32[b >> 1], 1u << sh);
+        packed[k] = ((u32)b << 16) | ((oldc >> sh) & 0xFFFFu);
+      }
+    }
+    __syncthreads();
+    // exclusive scan of the NB 16-bit counters (8 per thread), in place
+    {
+      const bool active = tid < NB / 8;
+      int c[8];
+      int tsum = 0, tmax = 0;
+      if (active) {
+        const uint4 cv = reinterpret_cast<const uint4*>(s_cnt32)[tid];
+        const u32 wds[4] = {cv.x, cv.y, cv.z, cv.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          c[2 * i] = (int)(wds[i] & 0xFFFFu);
+          c[2 * i + 1] = (int)(wds[i] >> 16);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int t = c[i];
+          tmax = t > tmax ? t : tmax;
+          c[i] = tsum;
+          tsum += t;
+        }
+      }
+      int incl = tsum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      if (lane == 31) m.warp_tot[warp] = incl;
+      const int lng = __syncthreads_or(tmax > LONGB ? 1 : 0);
+      if (lng) {                                // long run of (nearly) tied scores: general kernel
+        if (tid == 0) p.out_lens[q] = FUSE_DEFERRED;
+        continue;
+      }
+      int wbase = 0;
+      for (int w = 0; w < warp; ++w) wbase += m.warp_tot[w];
+      const int base = wbase + incl - tsum;
+      if (active) {
+        uint4 ov;
+        ov.x = (u32)(base + c[0]) | ((u32)(base + c[1]) << 16);
+        ov.y = (u32)(base + c[2]) | ((u32)(base + c[3]) << 16);
+        ov.z = (u32)(base + c[4]) | ((u32)(base + c[5]) << 16);
+        ov.w = (u32)(base + c[6]) | ((u32)(base + c[7]) << 16);
+        reinterpret_cast<uint4*>(s_cnt32)[tid] = ov;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < SPT; ++k) {
+      if (packed[k] != 0xFFFFFFFFu) s_order[s_base16[packed[k] >> 16] + (packed[k] & 0xFFFFu)] = (u16)(tid + k * NT);
+    }
+    __syncthreads();
+    // ------------------------------------------------------------ D: exact rank inside the bucket, output
+    {
+      int32_t* oid = p.out_ids + (size_t)q * out_stride;
+      double* osc = p.out_scores + (size_t)q * out_stride;
+      for (int j = tid; j < n_u; j += NT) {
+        const int slot = s_order[j];
+        const double fs = s_acc[slot];
+        const u32 mt = s_meta[slot];
+        const u32 tie = mt >> 16;
+        const int b = bucket(fs, tie);
+        const int lo = s_base16[b];
+        const int hi = (b + 1 < NB) ? (int)s_base16[b + 1] : n_u;
+        int rank = lo;
+        if (score_mode) {
+          for (int k = lo; k < hi; ++k) {
+            const int s2 = s_order[k];
+            const double f2 = s_acc[s2];
+            rank += (f2 > fs || (f2 == fs && (s_meta[s2] >> 16) < tie)) ? 1 : 0;
+          }
+        } else {
+          for (int k = lo; k < hi; ++k) rank += ((s_meta[s_order[k]] >> 16) < tie) ? 1 : 0;
+        }
+        oid[rank] = (int32_t)s_keys[slot];
+        osc[rank] = fs;
+        if (p.out_counts) p.out_counts[(size_t)q * out_stride + rank] = (u16)cntbits(mt);
+        if (want_pos) p.out_pos[(size_t)q * out_stride + rank] = (u16)tie;
+      }
+      if (tid == 0) {
+        p.out_lens[q] = n_u;
+        if (p.out_status) p.out_status[q] = m.status;
+      }
+    }
+  }
+}
+
+template <int HBITS, int UCAP, int NBBITS, int NMAX, int NT, int MINB, int ST>
+int launch_stream(const FuseParams& p, cudaStream_t stream) {
+  using L = SLayout<HBITS, UCAP, NBBITS, NMAX, NT>;
+  auto kern = fuse_stream_kernel<HBITS, UCAP, NBBITS, NMAX, NT, MINB, ST>;
+  static bool configured = false;   // per instantiation; attribute set is idempotent
+  static int per_sm = 1;
+  if (!configured) {
+    QF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::total));
+    QF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    QF_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, L::total));
+    if (per_sm < 1) per_sm = 1;
+    configured = true;
+  }
+  long long grid = (long long)qf::sm_count() * per_sm;
+  if (grid > p.Q) grid = p.Q;
+  kern<<<(unsigned)grid, NT, L::total, stream>>>(p);
+  QF_CUDA_TRY(cudaGetLastError());
+  return QF_OK;
+}
+
+template <int ST>
+int dispatch_stream(const FuseParams& p, cudaStream_t stream) {
+  const long long n_max = (long long)p.R * p.K;
+  if (n_max <= 1024) return launch_stream<11, 1024, 9, 1024, 128, 5, ST>(p, stream);
+  // QF_STREAM_VARIANT (debug/tuning hook, read once): 0 = 3 CTAs x 256 threads per SM (default), 1 = 2 x 384
+  static const int variant = [] {
+    const char* e = getenv("QF_STREAM_VARIANT");
+    return e ? atoi(e) : 0;
+  }();
+  if (variant == 1) return launch_stream<12, 3200, 11, 5120, 384, 2, ST>(p, stream);
+  return launch_stream<12, 2560, 11, 5120, 256, 3, ST>(p, stream);
+}
+
+}  // namespace
+
+namespace qf {
+
+bool fuse_stream_supported(const FuseParams& p) {
+  if (p.flags & (FUSE_FLAG_DEBUG_FULLSORT | FUSE_FLAG_DEBUG_GENERAL)) return false;
+  if (p.R > SMAX_R) return false;
+  if ((p.flags & QF_FLAG_MNZ_SKIP_ZERO) && p.R > 8) return false;
+  if ((long long)p.R * p.K > 5120) return false;
+  return true;
+}
+
+int fuse_stream_launch(const FuseParams& p, int score_type, cudaStream_t stream) {
+  switch (score_type) {
+    case QF_SCORE_F64: return dispatch_stream<QF_SCORE_F64>(p, stream);
+    case QF_SCORE_F32: return dispatch_stream<QF_SCORE_F32>(p, stream);
+    default: return dispatch_stream<QF_SCORE_MICRO>(p, stream);
+  }
+}
+
+}  // namespace qf

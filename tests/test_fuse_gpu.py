@@ -13,6 +13,16 @@ from oracle import fusion_oracle as fo
 pytestmark = pytest.mark.gpu
 
 METHODS = {"sum": 0, "mnz": 1, "rrf": 2}
+EXTRA_FLAGS = [0]
+
+
+@pytest.fixture(autouse=True, params=["stream", "general"])
+def fuse_kernel_path(request):
+    """Every test runs twice: through the streaming kernel (+ general-kernel fix-up of deferred queries, the product
+    path) and with the streaming kernel disabled (debug flag 0x200), so both kernels keep full parity coverage."""
+    EXTRA_FLAGS[0] = 0x200 if request.param == "general" else 0
+    yield
+    EXTRA_FLAGS[0] = 0
 
 
 def run_gpu(lists, method, weights=None, norm=0, rrf_k=60.0, flags=0, score_type="f64", explicit_ranks=False, k=None):
@@ -21,7 +31,8 @@ def run_gpu(lists, method, weights=None, norm=0, rrf_k=60.0, flags=0, score_type
     dev = torch.device("cuda:0")
     t = lambda a: torch.from_numpy(a).to(dev)
     w = None if weights is None else t(np.asarray(weights, dtype=np.float64))
-    out = ops.fuse(t(ids), t(sc), t(lens), w, t(ranks) if explicit_ranks else None, METHODS[method], norm, rrf_k, flags)
+    out = ops.fuse(t(ids), t(sc), t(lens), w, t(ranks) if explicit_ranks else None, METHODS[method], norm, rrf_k,
+                   flags | EXTRA_FLAGS[0])
     torch.cuda.synchronize()
     return [o.cpu().numpy() for o in out]
 
@@ -133,6 +144,68 @@ def test_ranx_semantics(method):
     if method == "mnz":
         out = run_gpu(lists, method, None, norm=1, flags=2 | 1, k=100)
         check_against_oracle(lists, method, None, out, ranx=True, mnz_skip_zero=True)
+
+
+def test_stream_kernel_envelope_edges():
+    """Conditions the streaming kernel defers or handles specially: doc id -1 (its empty-slot sentinel), R = 16 / 17
+    (list bit mask width), float32 scores, lists shorter than one 16-byte vector, an all-equal-score query (ranking by
+    first-seen order only) and a K that is not a multiple of 4 (scalar loads)."""
+    rng = np.random.default_rng(21)
+    lists = synth_lists(20, n_q=6, n_r=3, k=64, pool=150, ragged=True, ties=True)
+    r_long = max(range(3), key=lambda r: len(lists[2][r]))
+    d, s, rk = lists[2][r_long][5]
+    lists[2][r_long][5] = (-1, s, rk)                              # sentinel id
+    lists[3] = [[(int(x), 0.5, i + 1) for i, x in enumerate(rng.choice(10**6, 40, replace=False))] for _ in range(3)]
+    lists[4] = [rows[:3] for rows in lists[4]]
+    w = np.round(rng.random((6, 3)), 6)
+    w[3] = 0.5                                                     # query 3: every fused score equal
+    for method in ("sum", "mnz", "rrf"):
+        for st in ("f64", "f32", "micro"):
+            ll = lists
+            if st == "f32":     # values exactly representable in float32
+                ll = [[[(d_, float(np.float32(s_)), r_) for (d_, s_, r_) in rows] for rows in per_r] for per_r in lists]
+            out = run_gpu(ll, method, w, score_type=st, k=64)
+            check_against_oracle(ll, method, w, out)
+    out = run_gpu(lists, "sum", w, k=67)
+    check_against_oracle(lists, "sum", w, out)
+    for n_r in (16, 17):
+        ll = synth_lists(22 + n_r, n_q=3, n_r=n_r, k=40, pool=200, ragged=True)
+        ww = np.round(rng.random((3, n_r)), 6)
+        for method in ("sum", "mnz"):
+            out = run_gpu(ll, method, ww, k=40)
+            check_against_oracle(ll, method, ww, out)
+
+
+def test_unranked_output_is_first_seen_order():
+    lists = synth_lists(23, n_q=5, n_r=5, k=200, pool=450, ragged=True, ties=True)
+    w = np.round(np.random.default_rng(24).random((5, 5)), 6)
+    oid, osc, ocnt, opos, olen, ostat = run_gpu(lists, "mnz", w, k=200, flags=4)
+    for q, per_r in enumerate(lists):
+        docs, scores, counts = fo.fuse_weighted_query(per_r, w[q], 1, 60.0)
+        n = len(docs)
+        assert olen[q] == n
+        assert np.array_equal(oid[q, :n].astype(np.int64), np.array(docs, dtype=np.int64))
+        assert np.array_equal(osc[q, :n].view(np.int64), (np.array(scores, dtype=np.float64) + 0.0).view(np.int64))
+        assert np.array_equal(ocnt[q, :n].astype(np.int64), np.array(counts))
+        assert np.array_equal(opos[q, :n].astype(np.int64), np.arange(n))
+
+
+def test_long_tie_runs_and_skewed_scores():
+    """Hundreds of exactly tied fused scores (order = first-seen) next to a heavy-tailed score distribution: the
+    streaming kernel's bucket ranking must either resolve them exactly or defer to the general kernel."""
+    rng = np.random.default_rng(25)
+    lists = []
+    for q in range(4):
+        n = [100, 150, 400, 900][q]
+        docs = rng.choice(10**6, size=n, replace=False)
+        tied = [(int(d), 0.125, i + 1) for i, d in enumerate(docs)]
+        hs = np.sort(np.round(1e3 * rng.pareto(1.5, size=500), 6))[::-1]
+        heavy = [(int(d), float(s_), i + 1) for i, (d, s_) in enumerate(zip(rng.choice(10**6, size=500, replace=False), hs))]
+        lists.append([tied, heavy, tied[: n // 2]])
+    w = np.ones((4, 3))
+    for method in ("sum", "mnz", "rrf"):
+        out = run_gpu(lists, method, w, k=1000)
+        check_against_oracle(lists, method, w, out)
 
 
 def test_empty_queries_and_bad_lens():
