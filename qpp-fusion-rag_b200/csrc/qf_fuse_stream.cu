@@ -4,8 +4,11 @@
 // Replaces ranx.fuse (reference src/fusion.py:182,201,226) and the weighted_* Python dict loops
 // (src/fusion.py:266-278, 309-327, 361-377); semantics in include/qppfusion.h.  Per query:
 //   A  lists are visited in ranker order, one barrier per list.  Each posting (16-byte loads, next chunk
-//      prefetched into registers) claims / finds its doc's slot of an open-addressing table with one shared-memory
-//      atomicCAS on the 32-bit doc id, marks list r in the slot's bit mask with one atomicOr (a second posting of the
+//      prefetched into registers) finds / claims its doc's slot of a bucketised open-addressing table: one 16-byte
+//      shared-memory load fetches the 4 keys of its home group, a match needs no atomic at all, a miss claims the
+//      first empty key with one atomicCAS (the table may run at ~80 % load with ~1.2 probes per posting, and every
+//      probe step ends in __syncwarp so diverged lanes reconverge).  It then marks list r in the slot's bit mask
+//      with one atomicOr (a second posting of the
 //      same doc in the same list sees the bit -> the query is deferred to the general kernel's exact sequential
 //      path) and adds its contribution to the slot's float64 accumulator with a plain read-modify-write: doc ids
 //      are distinct inside a list and lists are separated by barriers, so the additions happen in exactly the
@@ -35,8 +38,15 @@ using u64 = unsigned long long;
 constexpr u32 EMPTY = 0xFFFFFFFFu;
 constexpr int SMAX_R = 16;       // list bit mask is the low half of the meta word
 constexpr int CB = 64;           // coarse bins of the equalisation histogram
-constexpr int MAXPROBE = 192;
+constexpr int MAXPROBE = 64;     // key groups (of 4) visited before the query is deferred
 constexpr int LONGB = 160;       // longest bucket ranked by pairwise comparison
+
+__device__ __forceinline__ uint4 lds128_volatile(const void* ptr) {
+  uint4 v;
+  const unsigned a = (unsigned)__cvta_generic_to_shared(ptr);
+  asm volatile("ld.volatile.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
 
 struct SMisc {
   int start[SMAX_R + 1];
@@ -49,23 +59,44 @@ struct SMisc {
   int status;
 };
 
-template <int HBITS, int UCAP, int NBBITS, int NMAX, int NT>
+// Classify one group of 4 keys with a single select chain: 0..3 = position of `id`, 4..7 = 4 + position of the
+// first empty key (no match), -1 = four foreign keys.
+__device__ __forceinline__ int probe4(const uint4& k, u32 id) {
+  int pos;
+  asm("{\n\t.reg .pred p;\n\t"
+      "mov.s32 %0, -1;\n\t"
+      "setp.eq.u32 p, %4, 0xffffffff;\n\tselp.s32 %0, 7, %0, p;\n\t"
+      "setp.eq.u32 p, %3, 0xffffffff;\n\tselp.s32 %0, 6, %0, p;\n\t"
+      "setp.eq.u32 p, %2, 0xffffffff;\n\tselp.s32 %0, 5, %0, p;\n\t"
+      "setp.eq.u32 p, %1, 0xffffffff;\n\tselp.s32 %0, 4, %0, p;\n\t"
+      "setp.eq.u32 p, %4, %5;\n\tselp.s32 %0, 3, %0, p;\n\t"
+      "setp.eq.u32 p, %3, %5;\n\tselp.s32 %0, 2, %0, p;\n\t"
+      "setp.eq.u32 p, %2, %5;\n\tselp.s32 %0, 1, %0, p;\n\t"
+      "setp.eq.u32 p, %1, %5;\n\tselp.s32 %0, 0, %0, p;\n\t"
+      "}"
+      : "=r"(pos)
+      : "r"(k.x), "r"(k.y), "r"(k.z), "r"(k.w), "r"(id));
+  return pos;
+}
+
+template <int G, int UCAP, int NB, int NMAX, int NT>
 struct SLayout {
-  static constexpr int H = 1 << HBITS;
-  static constexpr int NB = 1 << NBBITS;
+  static constexpr int H = 4 * G;                              // slots: G groups of 4 keys (one 16-byte load per probe)
   static constexpr int BW = NMAX / 32;                         // first-seen bitmap words
+  static constexpr int CPT = NB / NT;                          // bucket counters scanned per thread
   static constexpr size_t a16(size_t x) { return (x + 15) & ~size_t(15); }
   static constexpr size_t off_keys = 0;
   static constexpr size_t off_meta = off_keys + 4 * H;
   static constexpr size_t off_acc = off_meta + 4 * H;
-  static constexpr size_t off_cnt = off_acc + 8 * H;
-  static constexpr size_t off_order = off_cnt + 2 * NB;        // u16 order[UCAP]; aliases bitmap + prefix (dead before S4)
-  static constexpr size_t order_bytes = (2 * UCAP > 6 * BW) ? 2 * UCAP : 6 * BW;
-  static constexpr size_t off_coarse = a16(off_order + order_bytes);
+  static constexpr size_t off_cnt = off_acc + 8 * H;           // u16 bucket counters -> bases
+  static constexpr size_t off_order = a16(off_cnt + 2 * NB);   // u16 order[UCAP]: slots in bucket order
+  static constexpr size_t off_bcache = a16(off_order + 2 * UCAP);   // u16 bucket id per slot
+  static constexpr size_t off_bitmap = a16(off_bcache + 2 * H);     // first-seen bitmap + word prefix (out_pos)
+  static constexpr size_t off_coarse = a16(off_bitmap + 6 * BW);
   static constexpr size_t off_misc = a16(off_coarse + 4 * CB * 3);
   static constexpr size_t total = a16(off_misc + sizeof(SMisc));
-  static_assert(NB / 8 <= NT, "bucket scan: 8 counters per thread");
-  static_assert(UCAP < H && NMAX % 32 == 0 && NMAX <= 65536 && UCAP < 65536, "layout");
+  static_assert(NB % NT == 0 && CPT % 8 == 0 && NB < 65536, "bucket scan: CPT counters per thread, 8 per 16-byte load");
+  static_assert(UCAP < H && NMAX % 32 == 0 && NMAX <= 65536 && UCAP < 65536 && H < 65536, "layout");
   static_assert(NT / 32 <= 16 && NT / 32 >= 2, "warps");
 };
 
@@ -81,11 +112,13 @@ template <typename raw_t> struct Chunk {
   int rk[4];
 };
 
-template <int HBITS, int UCAP, int NBBITS, int NMAX, int NT, int MINB, int ST>
+// MODE 0: CombSUM / CombMNZ (weighted or not) on raw scores -- no min-max norm, no zero-skipping, no order checks
+//         (the weighted_* path and the benchmark step); MODE 1: every option decided at run time.
+template <int G, int UCAP, int NB, int NMAX, int NT, int MINB, int ST, int MODE>
 __global__ void __launch_bounds__(NT, MINB) fuse_stream_kernel(const FuseParams p) {
-  using L = SLayout<HBITS, UCAP, NBBITS, NMAX, NT>;
+  using L = SLayout<G, UCAP, NB, NMAX, NT>;
   using raw_t = typename ScoreT<ST>::type;
-  constexpr int H = L::H, NB = L::NB, NW = NT / 32, SPT = (H + NT - 1) / NT, CH = NT * 4, BW = L::BW;
+  constexpr int H = L::H, NW = NT / 32, SPT = (H + NT - 1) / NT, CH = NT * 4, BW = L::BW, CPT = L::CPT;
 
   extern __shared__ __align__(16) unsigned char smem[];
   u32* s_keys = reinterpret_cast<u32*>(smem + L::off_keys);
@@ -94,8 +127,9 @@ __global__ void __launch_bounds__(NT, MINB) fuse_stream_kernel(const FuseParams 
   u32* s_cnt32 = reinterpret_cast<u32*>(smem + L::off_cnt);
   u16* s_base16 = reinterpret_cast<u16*>(smem + L::off_cnt);
   u16* s_order = reinterpret_cast<u16*>(smem + L::off_order);
-  u32* s_bitmap = reinterpret_cast<u32*>(smem + L::off_order);
-  u16* s_bpre = reinterpret_cast<u16*>(smem + L::off_order + 4 * BW);
+  u16* s_bcache = reinterpret_cast<u16*>(smem + L::off_bcache);
+  u32* s_bitmap = reinterpret_cast<u32*>(smem + L::off_bitmap);
+  u16* s_bpre = reinterpret_cast<u16*>(smem + L::off_bitmap + 4 * BW);
   int* s_chist = reinterpret_cast<int*>(smem + L::off_coarse);
   float* s_ccum = reinterpret_cast<float*>(smem + L::off_coarse + 4 * CB);
   float* s_cw = reinterpret_cast<float*>(smem + L::off_coarse + 8 * CB);
@@ -104,13 +138,13 @@ __global__ void __launch_bounds__(NT, MINB) fuse_stream_kernel(const FuseParams 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int R = p.R, K = p.K;
   const size_t out_stride = (size_t)R * K;
-  const bool is_rrf = (p.method == QF_METHOD_RRF);
+  const bool is_rrf = MODE ? (p.method == QF_METHOD_RRF) : false;
   const bool is_mnz = (p.method == QF_METHOD_MNZ);
   const bool weighted = (p.weights != nullptr);
-  const bool skip_zero = (p.flags & QF_FLAG_MNZ_SKIP_ZERO) != 0;
-  const bool check_sorted = (p.flags & QF_FLAG_REQUIRE_SORTED) != 0;
+  const bool skip_zero = MODE ? (p.flags & QF_FLAG_MNZ_SKIP_ZERO) != 0 : false;
+  const bool check_sorted = MODE ? (p.flags & QF_FLAG_REQUIRE_SORTED) != 0 : false;
   const bool unranked = (p.flags & QF_FLAG_UNRANKED_OUTPUT) != 0;
-  const bool minmax = (p.norm == QF_NORM_MINMAX) && !is_rrf;
+  const bool minmax = MODE ? ((p.norm == QF_NORM_MINMAX) && !is_rrf) : false;
   const bool need_scores = !is_rrf || check_sorted;
   const bool want_pos = (p.out_pos != nullptr);
 
@@ -145,7 +179,8 @@ __global__ void __launch_bounds__(NT, MINB) fuse_stream_kernel(const FuseParams 
         m4[i] = make_uint4(0u, 0u, 0u, 0u);
       }
       for (int i = tid; i < NB / 2; i += NT) s_cnt32[i] = 0u;
-      for (int i = tid; i < BW; i += NT) s_bitmap[i] = 0u;
+      if (want_pos)
+        for (int i = tid; i < BW; i += NT) s_bitmap[i] = 0u;
       for (int i = tid; i < CB; i += NT) s_chist[i] = 0;
     }
     __syncthreads();
@@ -247,7 +282,8 @@ __global__ void __launch_bounds__(NT, MINB) fuse_stream_kernel(const FuseParams 
       const double lmn = minmax ? m.mn[r] : 0.0, lden = minmax ? m.den[r] : 1.0;
       int idx[4];
       bool valid[4];
-      u32 h[4], old[4];
+      u32 g[4];
+      uint4 kk[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         idx[j] = vec ? base + tid * 4 + j : base + j * NT + tid;
@@ -269,7 +305,7 @@ __global__ void __launch_bounds__(NT, MINB) fuse_stream_kernel(const FuseParams 
             if (prev > c.rk[j]) bad_order = true;
           }
       }
-      // first probe of all four postings back to back, then resolve
+      // home groups of all four postings fetched back to back
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         if (valid[j]) {
@@ -277,51 +313,78 @@ __global__ void __launch_bounds__(NT, MINB) fuse_stream_kernel(const FuseParams 
             defer = true;
             valid[j] = false;
           } else {
-            h[j] = ((u32)c.id[j] * 2654435761u) >> (32 - HBITS);
-            old[j] = atomicCAS(&s_keys[h[j]], EMPTY, (u32)c.id[j]);
+            g[j] = __umulhi((u32)c.id[j] * 2654435761u, (u32)G);
+            kk[j] = lds128_volatile(s_keys + 4 * g[j]);
           }
         }
       }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        if (!valid[j]) continue;
-        const u32 id = (u32)c.id[j];
-        u32 hh = h[j], o = old[j];
-        int probes = 0;
-        while (o != EMPTY && o != id) {
-          if (++probes > MAXPROBE) break;
-          hh = (hh + 1) & (H - 1);
-          o = atomicCAS(&s_keys[hh], EMPTY, id);
+        // Probe loop, uniform over the warp (lanes that are done idle, nobody runs a private code path): one
+        // select chain classifies the group -- doc found / first empty key / four foreign keys.  Probe order is
+        // group by group, keys 0..3; a doc always sits before the first empty key of its probe order, so
+        // "match, else claim the first empty key with one CAS, else next group" is exact.
+        int slot = -1;
+        bool inserted = false;
+        {
+          const u32 id = (u32)c.id[j];
+          u32 gq = g[j];
+          uint4 k4 = kk[j];
+          int probes = 0;
+          bool active = valid[j];
+          while (__any_sync(0xffffffffu, active)) {
+            if (active) {
+              const int pos = probe4(k4, id);
+              if (pos < 0) {                                   // four foreign keys: next group
+                if (++probes > MAXPROBE) {
+                  defer = true;
+                  active = false;
+                } else {
+                  gq = gq + 1 == (u32)G ? 0u : gq + 1;
+                  k4 = lds128_volatile(s_keys + 4 * gq);
+                }
+              } else {
+                const int cand = (int)(4 * gq) + (pos & 3);
+                u32 o = id;
+                if (pos >= 4) {
+                  o = atomicCAS(&s_keys[cand], EMPTY, id);
+                  inserted = (o == EMPTY);
+                  o = inserted ? id : o;
+                }
+                if (o == id) {
+                  slot = cand;
+                  active = false;
+                } else {
+                  k4 = lds128_volatile(s_keys + 4 * gq);       // lost the key to another doc: look again
+                }
+              }
+            }
+          }
         }
-        if (o != EMPTY && o != id) {
-          defer = true;
-          continue;
+        if (slot >= 0) {
+          double v;
+          bool counts = true;
+          if (is_rrf) {
+            const double rank = grk ? (double)c.rk[j] : (double)(idx[j] + 1);
+            v = __ddiv_rn(w, __dadd_rn(p.rrf_k, rank));
+          } else {
+            double s = raw_to_f64(c.sc[j]);
+            if (minmax) s = __ddiv_rn(__dsub_rn(s, lmn), lden);
+            if (skip_zero && s == 0.0) counts = false;
+            v = __dmul_rn(w, s);                           // w == 1.0 when unweighted: exact
+          }
+          u32 bits = 1u << r;
+          if (skip_zero && counts) bits |= 1u << (8 + r);
+          if (inserted) {
+            ++ins;
+            bits |= (u32)(s0 + idx[j]) << 16;
+          }
+          const u32 om = atomicOr(&s_meta[slot], bits);
+          const double prev = inserted ? 0.0 : s_acc[slot];     // the reference starts from 0.0 (src/fusion.py:275)
+          if (om & (1u << r)) defer = true;                     // the doc id occurs twice inside list r
+          else s_acc[slot] = __dadd_rn(prev, v);
         }
-        double v;
-        bool counts = true;
-        if (is_rrf) {
-          const double rank = grk ? (double)c.rk[j] : (double)(idx[j] + 1);
-          v = __ddiv_rn(w, __dadd_rn(p.rrf_k, rank));
-        } else {
-          double s = raw_to_f64(c.sc[j]);
-          if (minmax) s = __ddiv_rn(__dsub_rn(s, lmn), lden);
-          if (skip_zero && s == 0.0) counts = false;
-          v = weighted ? __dmul_rn(w, s) : s;
-        }
-        u32 bits = 1u << r;
-        if (skip_zero && counts) bits |= 1u << (8 + r);
-        if (o == EMPTY) {
-          ++ins;
-          bits |= (u32)(s0 + idx[j]) << 16;
-        }
-        const u32 om = atomicOr(&s_meta[hh], bits);
-        if (om & (1u << r)) {
-          defer = true;                                  // the doc id occurs twice inside list r
-        } else if (o == EMPTY) {
-          s_acc[hh] = __dadd_rn(0.0, v);                 // the reference starts from 0.0 (src/fusion.py:275)
-        } else {
-          s_acc[hh] = __dadd_rn(s_acc[hh], v);
-        }
+        __syncwarp();
       }
     };
 
@@ -470,11 +533,11 @@ __global__ void __launch_bounds__(NT, MINB) fuse_stream_kernel(const FuseParams 
       return b < 0 ? 0 : (b > NB - 1 ? NB - 1 : b);
     };
     // bucket counts; the atomicAdd's old value is the doc's offset inside its bucket
-    u32 packed[SPT];
+    u16 offs[SPT];
 #pragma unroll
     for (int k = 0; k < SPT; ++k) {
       const int slot = tid + k * NT;
-      packed[k] = 0xFFFFFFFFu;
+      offs[k] = 0xFFFFu;
       if (slot < H && s_keys[slot] != EMPTY) {
         const u32 mt = s_meta[slot];
         u32 tie = mt >> 16;
@@ -485,30 +548,28 @@ __global__ void __launch_bounds__(NT, MINB) fuse_stream_kernel(const FuseParams 
         const int b = bucket(s_acc[slot], tie);
         const int sh = (b & 1) * 16;
         const u32 oldc = atomicAdd(&s_cnt32[b >> 1], 1u << sh);
-        packed[k] = ((u32)b << 16) | ((oldc >> sh) & 0xFFFFu);
+        s_bcache[slot] = (u16)b;
+        offs[k] = (u16)((oldc >> sh) & 0xFFFFu);
       }
     }
     __syncthreads();
-    // exclusive scan of the NB 16-bit counters (8 per thread), in place
+    // exclusive scan of the NB 16-bit counters (CPT consecutive counters per thread), in place
     {
-      const bool active = tid < NB / 8;
-      int c[8];
       int tsum = 0, tmax = 0;
-      if (active) {
-        const uint4 cv = reinterpret_cast<const uint4*>(s_cnt32)[tid];
-        const u32 wds[4] = {cv.x, cv.y, cv.z, cv.w};
+      uint4 cv[CPT / 8];
+#pragma unroll
+      for (int v = 0; v < CPT / 8; ++v) {
+        cv[v] = reinterpret_cast<const uint4*>(s_cnt32)[tid * (CPT / 8) + v];
+        u32 wds[4] = {cv[v].x, cv[v].y, cv[v].z, cv[v].w};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          c[2 * i] = (int)(wds[i] & 0xFFFFu);
-          c[2 * i + 1] = (int)(wds[i] >> 16);
+          const int c0 = (int)(wds[i] & 0xFFFFu), c1 = (int)(wds[i] >> 16);
+          tmax = c0 > tmax ? c0 : tmax;
+          tmax = c1 > tmax ? c1 : tmax;
+          wds[i] = (u32)tsum | ((u32)(tsum + c0) << 16);       // exclusive prefixes inside the thread
+          tsum += c0 + c1;
         }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int t = c[i];
-          tmax = t > tmax ? t : tmax;
-          c[i] = tsum;
-          tsum += t;
-        }
+        cv[v] = make_uint4(wds[0], wds[1], wds[2], wds[3]);
       }
       int incl = tsum;
 #pragma unroll
@@ -524,20 +585,18 @@ __global__ void __launch_bounds__(NT, MINB) fuse_stream_kernel(const FuseParams 
       }
       int wbase = 0;
       for (int w = 0; w < warp; ++w) wbase += m.warp_tot[w];
-      const int base = wbase + incl - tsum;
-      if (active) {
-        uint4 ov;
-        ov.x = (u32)(base + c[0]) | ((u32)(base + c[1]) << 16);
-        ov.y = (u32)(base + c[2]) | ((u32)(base + c[3]) << 16);
-        ov.z = (u32)(base + c[4]) | ((u32)(base + c[5]) << 16);
-        ov.w = (u32)(base + c[6]) | ((u32)(base + c[7]) << 16);
-        reinterpret_cast<uint4*>(s_cnt32)[tid] = ov;
+      const u32 base2 = (u32)(wbase + incl - tsum) * 0x00010001u;     // added to both 16-bit halves (no carry: < 65536)
+#pragma unroll
+      for (int v = 0; v < CPT / 8; ++v) {
+        cv[v].x += base2; cv[v].y += base2; cv[v].z += base2; cv[v].w += base2;
+        reinterpret_cast<uint4*>(s_cnt32)[tid * (CPT / 8) + v] = cv[v];
       }
     }
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < SPT; ++k) {
-      if (packed[k] != 0xFFFFFFFFu) s_order[s_base16[packed[k] >> 16] + (packed[k] & 0xFFFFu)] = (u16)(tid + k * NT);
+      const int slot = tid + k * NT;
+      if (offs[k] != 0xFFFFu) s_order[s_base16[s_bcache[slot]] + offs[k]] = (u16)slot;
     }
     __syncthreads();
     // ------------------------------------------------------------ D: exact rank inside the bucket, output
@@ -549,7 +608,7 @@ __global__ void __launch_bounds__(NT, MINB) fuse_stream_kernel(const FuseParams 
         const double fs = s_acc[slot];
         const u32 mt = s_meta[slot];
         const u32 tie = mt >> 16;
-        const int b = bucket(fs, tie);
+        const int b = s_bcache[slot];
         const int lo = s_base16[b];
         const int hi = (b + 1 < NB) ? (int)s_base16[b + 1] : n_u;
         int rank = lo;
@@ -575,10 +634,10 @@ __global__ void __launch_bounds__(NT, MINB) fuse_stream_kernel(const FuseParams 
   }
 }
 
-template <int HBITS, int UCAP, int NBBITS, int NMAX, int NT, int MINB, int ST>
+template <int G, int UCAP, int NB, int NMAX, int NT, int MINB, int ST, int MODE>
 int launch_stream(const FuseParams& p, cudaStream_t stream) {
-  using L = SLayout<HBITS, UCAP, NBBITS, NMAX, NT>;
-  auto kern = fuse_stream_kernel<HBITS, UCAP, NBBITS, NMAX, NT, MINB, ST>;
+  using L = SLayout<G, UCAP, NB, NMAX, NT>;
+  auto kern = fuse_stream_kernel<G, UCAP, NB, NMAX, NT, MINB, ST, MODE>;
   static bool configured = false;   // per instantiation; attribute set is idempotent
   static int per_sm = 1;
   if (!configured) {
@@ -595,17 +654,24 @@ int launch_stream(const FuseParams& p, cudaStream_t stream) {
   return QF_OK;
 }
 
-template <int ST>
+template <int ST, int MODE>
 int dispatch_stream(const FuseParams& p, cudaStream_t stream) {
   const long long n_max = (long long)p.R * p.K;
-  if (n_max <= 1024) return launch_stream<11, 1024, 9, 1024, 128, 5, ST>(p, stream);
+  if (n_max <= 1024) return launch_stream<384, 1024, 1024, 1024, 128, 5, ST, MODE>(p, stream);
   // QF_STREAM_VARIANT (debug/tuning hook, read once): 0 = 3 CTAs x 256 threads per SM (default), 1 = 2 x 384
   static const int variant = [] {
     const char* e = getenv("QF_STREAM_VARIANT");
     return e ? atoi(e) : 0;
   }();
-  if (variant == 1) return launch_stream<12, 3200, 11, 5120, 384, 2, ST>(p, stream);
-  return launch_stream<12, 2560, 11, 5120, 256, 3, ST>(p, stream);
+  if (variant == 1) return launch_stream<1024, 3328, 3072, 5120, 384, 2, ST, MODE>(p, stream);
+  return launch_stream<768, 2560, 4096, 5120, 256, 3, ST, MODE>(p, stream);
+}
+
+template <int ST>
+int dispatch_mode(const FuseParams& p, cudaStream_t stream) {
+  const bool plain = p.method != QF_METHOD_RRF && p.norm == QF_NORM_NONE &&
+                     !(p.flags & (QF_FLAG_MNZ_SKIP_ZERO | QF_FLAG_REQUIRE_SORTED));
+  return plain ? dispatch_stream<ST, 0>(p, stream) : dispatch_stream<ST, 1>(p, stream);
 }
 
 }  // namespace
@@ -622,9 +688,9 @@ bool fuse_stream_supported(const FuseParams& p) {
 
 int fuse_stream_launch(const FuseParams& p, int score_type, cudaStream_t stream) {
   switch (score_type) {
-    case QF_SCORE_F64: return dispatch_stream<QF_SCORE_F64>(p, stream);
-    case QF_SCORE_F32: return dispatch_stream<QF_SCORE_F32>(p, stream);
-    default: return dispatch_stream<QF_SCORE_MICRO>(p, stream);
+    case QF_SCORE_F64: return dispatch_mode<QF_SCORE_F64>(p, stream);
+    case QF_SCORE_F32: return dispatch_mode<QF_SCORE_F32>(p, stream);
+    default: return dispatch_mode<QF_SCORE_MICRO>(p, stream);
   }
 }
 
