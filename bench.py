@@ -72,18 +72,53 @@ def synth_device(Q, R, K, seed, device):
 
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons sampled every 200 ms while the timed region runs."""
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-              "clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons sampled WHILE the timed region runs: NVML polled every ~2 ms from a thread (the
+    timed regions here last 10-150 ms, far below nvidia-smi's sampling period); falls back to `nvidia-smi -lms` when
+    NVML is not importable."""
+    REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.thread, self.stop_flag = index, [], None, None, False
+        self.nvml = None
+        try:
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            uuid = str(torch.cuda.get_device_properties(index).uuid)
+            try:
+                self.handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
+            except Exception:
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _poll(self):
+        nv = self.nvml
+        while not self.stop_flag:
+            try:
+                mhz = float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM))
+                try:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                except Exception:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                self.rows.append((mhz, mask))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
+        if self.nvml is not None:
+            self.stop_flag = False
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+            fields = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                      "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={fields}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
@@ -94,6 +129,16 @@ class ClockSampler:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=1.0)
+            sm = sorted(r[0] for r in self.rows)
+            mask = 0
+            for r in self.rows:
+                mask |= r[1]
+            reasons = sorted(n for n, bit in self.REASONS.items() if mask & bit)
+            return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz, "samples": len(sm),
+                    "reasons": reasons, "source": "nvml polled during the timed region"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.25)
@@ -106,15 +151,23 @@ class ClockSampler:
                 mx.append(float(row[1]))
             except (ValueError, IndexError):
                 continue
-            for n, v in zip(names, row[3:7]):
+            for n, v in zip(names, row[2:6]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "source": "nvidia-smi -lms 100"}
 
 
 # ------------------------------------------------------------------------------------------------ ours
+def fuse_traffic():
+    """DRAM bytes per launch of the fusion kernel from the committed ncu --set full capture (profiles/)."""
+    p = os.path.join(ROOT, "profiles", "fuse_traffic.json")
+    if os.path.isfile(p):
+        return json.load(open(p)).get("dram_bytes_per_launch")
+    return None
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(p):
@@ -170,10 +223,10 @@ def dense_leg(args, dev, world, rank):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    N_.profile_enable(True)
     for _ in range(3):
         sc, ids, st = step()
     barrier()
+    N_.profile_enable(True)          # averages the in-library event pairs of the calls from here on
     status_bad = int((st != 0).sum().item())
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler = ClockSampler(dev.index)
@@ -264,6 +317,7 @@ def run_ours(args):
     NSETS = 3     # rotating input sets: 138 MB each, so no step finds its inputs in the 126 MB L2
     sets = [synth_device(Q, R, K, 20250101 + 2 + 17 * rank + 1000 * i, dev) for i in range(NSETS)]
     stream = torch.cuda.current_stream(dev)
+    from qppfusion.pipeline import FusionStepGraph
 
     def step(i, ev=None):
         ids, micro, lens, feats = sets[i % NSETS]
@@ -283,14 +337,22 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    # The product path replays the step as ONE CUDA graph per input set (qppfusion.pipeline.FusionStepGraph): the
+    # kernels are 10-400 us long and issuing seven of them from Python per step leaves the GPU waiting for the host.
+    graphs = [FusionStepGraph(*sets[i], qpp_index=5, top_k=100, k_cut=50, colnorm="minmax", round6=True,
+                              method=0, norm=0, rrf_k=60.0, flags=0, want_counts=False, want_pos=False, compact=True)
+              for i in range(NSETS)]
     for i in range(args.warmup):
-        out = step(i)
+        out = graphs[i % NSETS].replay()
     barrier()
     union_total = int(out.lens.sum().item())
     assert int(out.status.max().item()) == 0
+    eager = step(0)
+    barrier()
+    assert torch.equal(eager.lens, graphs[0].replay().lens)
+    barrier()
 
-    # ---- timed region: K steps, device-timed, max over ranks
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+    # ---- timed region: K steps (graph replays), device-timed, max over ranks
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler = ClockSampler(local)
     if rank == 0:
@@ -298,18 +360,35 @@ def run_ours(args):
     barrier()
     t0.record(stream)
     for i in range(args.steps):
-        out = step(i, evs[i])
+        graphs[i % NSETS].replay()
     t1.record(stream)
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     ms_total = t0.elapsed_time(t1)
-    fuse_ms = sum(e[2].elapsed_time(e[3]) for e in evs) / args.steps
-    qpp_ms = sum(e[0].elapsed_time(e[1]) for e in evs) / args.steps
-    norm_ms = sum(e[1].elapsed_time(e[2]) for e in evs) / args.steps
 
-    # ---- end to end: pinned host buffers -> H2D -> step -> CSR compaction -> D2H of the fused run.
-    # Three streams (H2D / compute / D2H) so step i+1's upload and step i-1's download overlap step i's kernels;
-    # every step's copies are inside the timed region.
+    # ---- per-kernel durations: the same K steps issued kernel by kernel with CUDA events between them (events cannot
+    # be read back from inside a graph replay); the fusion kernel's average is the roofline denominator
+    from qppfusion import _native as N_
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+    for i in range(3):
+        step(i)
+    barrier()
+    N_.profile_enable(True)           # in-library event pairs right around the fusion / QPP kernel launches
+    for i in range(args.steps):
+        step(i, evs[i])
+    barrier()
+    fuse_ms = N_.profile_read(N_.PROF_FUSE_STREAM)            # streaming fusion kernel alone (average of K launches)
+    fixup_ms = N_.profile_read(N_.PROF_FUSE_GENERAL)          # general kernel's fix-up pass over deferred queries
+    qpp_ms = N_.profile_read(N_.PROF_QPP_STATS)
+    N_.profile_enable(False)
+    fuse_op_ms = sum(e[2].elapsed_time(e[3]) for e in evs) / args.steps
+    norm_ms = sum(e[1].elapsed_time(e[2]) for e in evs) / args.steps
+    deferred = int((graphs[0].replay().lens < 0).sum().item())
+    assert deferred == 0
+
+    # ---- end to end: pinned host buffers -> H2D into the graph's input tensors -> graph replay (step + CSR
+    # compaction) -> D2H of the fused run.  Three streams (H2D / compute / D2H) so step i+1's upload and step i-1's
+    # download overlap step i's kernels; every step's copies are inside the timed region.
     h_sets = [[x.cpu().pin_memory() for x in st_] for st_ in sets]
     n_post = Q * R * K
     NB = 2
@@ -322,14 +401,15 @@ def run_ours(args):
     def e2e_run(n_steps):
         ev_h2d = [torch.cuda.Event() for _ in range(n_steps)]
         ev_cmp = [torch.cuda.Event() for _ in range(n_steps)]
+        ev_d2h = [torch.cuda.Event() for _ in range(n_steps)]
         ev_off = torch.cuda.Event()
-        pending = {}
 
         def upload(i):
             with torch.cuda.stream(s_h2d):
                 if i >= NB:
-                    s_h2d.wait_event(ev_cmp[i - NB])            # at most NB uploads ahead of the kernels
-                pending[i] = [x.to(dev, non_blocking=True) for x in h_sets[i % NSETS]]
+                    s_h2d.wait_event(ev_cmp[i - NB])            # that set's previous step has consumed its inputs
+                for dst, src in zip(sets[i % NSETS], h_sets[i % NSETS]):
+                    dst.copy_(src, non_blocking=True)
                 ev_h2d[i].record(s_h2d)
 
         upload(0)
@@ -337,21 +417,16 @@ def run_ours(args):
             if i + 1 < n_steps:
                 upload(i + 1)
             b = i % NB
+            g = graphs[i % NSETS]
             with torch.cuda.stream(s_cmp):
                 s_cmp.wait_event(ev_h2d[i])
-                d = pending.pop(i)
-                for t_ in d:
-                    t_.record_stream(s_cmp)
-                qpp, _ = ops.qpp_stats(d[1], d[2], d[3], None, None, top_k=100, k_cut=50)
-                ops.qpp_colnorm_(qpp, "minmax", round6=True)
-                w = ops.qpp_select_weight(qpp, 5)
-                o = ops.fuse(d[0], d[1], d[2], w, None, 0, 0, 60.0, 0, want_counts=False, want_pos=False)
-                off, cids, csc = ops.compact_fused(o)
+                if i >= NSETS:
+                    s_cmp.wait_event(ev_d2h[i - NSETS])         # that graph's previous outputs have been downloaded
+                g.replay()
                 ev_cmp[i].record(s_cmp)
+            off, cids, csc = g.csr
             with torch.cuda.stream(s_d2h):
                 s_d2h.wait_event(ev_cmp[i])
-                for t_ in (off, cids, csc):
-                    t_.record_stream(s_d2h)
                 h_off[b].copy_(off, non_blocking=True)
                 ev_off.record(s_d2h)
             ev_off.synchronize()                                 # host needs the total before sizing the copy
@@ -359,6 +434,7 @@ def run_ours(args):
             with torch.cuda.stream(s_d2h):
                 h_ids[b][:total].copy_(cids[:total], non_blocking=True)
                 h_sc[b][:total].copy_(csc[:total], non_blocking=True)
+                ev_d2h[i].record(s_d2h)
             d2h_bytes[0] = total * 12 + (Q + 1) * 8
 
     e2e_steps = max(4, min(args.steps, 12))
@@ -377,6 +453,7 @@ def run_ours(args):
     h2d = sum(x.numel() * x.element_size() for x in h_sets[0])
     d2h = d2h_bytes[0]
     h_in, h_out = h_sets, (h_off, h_ids, h_sc)
+    del graphs
 
     del sets, h_in, h_out
     torch.cuda.empty_cache()
@@ -397,18 +474,26 @@ def run_ours(args):
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "NQ-shaped 3452 queries x 5 retrievers x top-1000: 13 QPP predictors + "
-                                   "cross-query min-max + W-CombSUM(RSD) per step (BASELINE configs[1])",
+                                   "cross-query min-max + W-CombSUM(RSD) per step (BASELINE configs[1]); each step is "
+                                   "one CUDA-graph replay of the 7 kernels",
                        "queries_per_gpu": Q, "retrievers": R, "depth": K, "score_format": "int32 micro-units",
                        "union_ratio": union_total / n_post, "sharding": f"query-sharded x{world}, no collective",
                        "l2": "3 rotating input sets of 138 MB (> 126 MB L2)"},
-            "kernel_ms": {"qpp_stats": qpp_ms, "colnorm+select": norm_ms, "fuse": fuse_ms},
-            "roofline": {"kernel": "fuse_kernel<5120,13,512,micro>", "bound": "hbm", "achieved": achieved,
-                         "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "peak_source": which,
-                         "algorithmic_bytes": alg_bytes, "traffic": None},
+            "kernel_ms": {"qpp_stats": qpp_ms, "colnorm+select": norm_ms, "fuse_stream": fuse_ms,
+                          "fuse_fixup": fixup_ms, "fuse_op_eager": fuse_op_ms,
+                          "note": "per-kernel times from a second K-step loop issued kernel by kernel (in-library "
+                                  "CUDA events around the launches); the timed region itself replays CUDA graphs"},
+            "roofline": {"kernel": "fuse_stream_kernel<768,2560,4096,5120,256,3,micro,plain>", "bound": "hbm",
+                         "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                         "peak_source": which, "algorithmic_bytes": alg_bytes, "traffic": fuse_traffic(),
+                         "frac_of_nominal_8TBs": achieved / 8000.0},
             "e2e": {"value": world * Q / (e2e_ms * 1e-3), "unit": "fused queries/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "note": "pinned host buffers; H2D / kernels / CSR-compacted D2H of consecutive steps overlap on 3 streams"},
-            "gpu_launches": 6 * args.steps + 10 * (e2e_steps + 3) + (dense["gpu_launches"] if dense else 0),
+                    "note": "pinned host buffers -> H2D into the graph's inputs -> graph replay (step + CSR compaction) -> "
+                            "D2H; consecutive steps overlap on 3 streams"},
+            # per step: qpp 1 + colnorm 3 + select 1 + fuse 2 (streaming + fix-up) = 7; CSR compaction adds 4
+            "gpu_launches": (11 * (args.steps + args.warmup + 1) + 7 * (args.steps + 4) + 11 * (e2e_steps + 3)
+                             + (dense["gpu_launches"] if dense else 0)),
             "clocks": clocks,
             "dense": dense,
         }

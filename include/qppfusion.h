@@ -49,16 +49,19 @@ QF_API int         qf_abi_version(void);
 QF_API int         qf_device_check(int device);
 
 /*
- * Optional device-side timing of the kernels a multi-kernel entry point launches (used by bench.py for
- * the per-kernel roofline): when enabled, CUDA events are recorded on the caller's stream around the
- * named phase; qf_profile_read synchronises on the closing event and returns the elapsed milliseconds
- * of the most recent call.
+ * Optional device-side timing of individual kernels (used by bench.py for the per-kernel roofline): while enabled,
+ * CUDA events are recorded on the caller's stream around the named phase of every call (up to 512 calls);
+ * qf_profile_read synchronises on the last closing event and returns the AVERAGE elapsed milliseconds of the calls
+ * recorded since the last qf_profile_enable(1).  Not for use during CUDA-graph capture.
  */
 #define QF_PROF_DENSE_SAMPLE 0   /* strided-sample scoring pass of qf_dense_topk            */
 #define QF_PROF_DENSE_TAU    1   /* per-query threshold selection                           */
 #define QF_PROF_DENSE_MAIN   2   /* tcgen05 GEMM + fused threshold filter over the corpus   */
 #define QF_PROF_DENSE_SELECT 3   /* per-query candidate ranking                             */
-#define QF_PROF_PHASES       4
+#define QF_PROF_FUSE_STREAM  4   /* qf_fuse: streaming fusion kernel                        */
+#define QF_PROF_FUSE_GENERAL 5   /* qf_fuse: general kernel (whole launch, or the fix-up pass after the streaming one) */
+#define QF_PROF_QPP_STATS    6   /* qf_qpp_stats kernel                                     */
+#define QF_PROF_PHASES       7
 QF_API int qf_profile_enable(int on);
 QF_API int qf_profile_read(int phase, float* ms);
 

@@ -22,30 +22,49 @@ int check_device() {
     set_error("no CUDA device: %s (libqppfusion has no CPU fallback)", cudaGetErrorString(e));
     return QF_E_NO_DEVICE;
   }
-  return qf_device_check(dev);
+  static bool ok[64] = {};                  // devices already verified (the answer cannot change)
+  if (dev >= 0 && dev < 64 && ok[dev]) return QF_OK;
+  const int rc = qf_device_check(dev);
+  if (rc == QF_OK && dev >= 0 && dev < 64) ok[dev] = true;
+  return rc;
 }
 
+// Optional device-side timing (qf_profile_*): up to PROF_MAX event pairs per phase since the last enable; the read
+// returns their average.
+constexpr int PROF_MAX = 512;
+struct ProfPhase {
+  cudaEvent_t ev[PROF_MAX][2];
+  int created = 0, n = 0;
+  bool open = false;
+};
 static bool g_prof_on = false;
-static cudaEvent_t g_prof_ev[QF_PROF_PHASES][2];
-static bool g_prof_init = false, g_prof_rec[QF_PROF_PHASES];
+static ProfPhase g_prof[QF_PROF_PHASES];
 
 void prof_mark(int phase, int which, cudaStream_t st) {
   if (!g_prof_on || phase < 0 || phase >= QF_PROF_PHASES) return;
-  if (!g_prof_init) {
-    for (int i = 0; i < QF_PROF_PHASES; ++i) {
-      cudaEventCreate(&g_prof_ev[i][0]);
-      cudaEventCreate(&g_prof_ev[i][1]);
-      g_prof_rec[i] = false;
+  ProfPhase& ph = g_prof[phase];
+  if (ph.n >= PROF_MAX) return;
+  if (which == 0) {
+    if (ph.n >= ph.created) {
+      if (cudaEventCreate(&ph.ev[ph.n][0]) != cudaSuccess || cudaEventCreate(&ph.ev[ph.n][1]) != cudaSuccess) return;
+      ph.created = ph.n + 1;
     }
-    g_prof_init = true;
+    cudaEventRecord(ph.ev[ph.n][0], st);
+    ph.open = true;
+  } else if (ph.open) {
+    cudaEventRecord(ph.ev[ph.n][1], st);
+    ph.open = false;
+    ++ph.n;
   }
-  cudaEventRecord(g_prof_ev[phase][which], st);
-  if (which == 1) g_prof_rec[phase] = true;
 }
 
 int sm_count() {
+  static int cached[64] = {};
   int dev = 0, n = 148;
-  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  if (cudaGetDevice(&dev) != cudaSuccess) return n;
+  if (dev >= 0 && dev < 64 && cached[dev] > 0) return cached[dev];
+  cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  if (dev >= 0 && dev < 64) cached[dev] = n;
   return n;
 }
 
@@ -78,13 +97,25 @@ extern "C" int qf_device_check(int device) {
 
 extern "C" int qf_profile_enable(int on) {
   qf::g_prof_on = on != 0;
+  if (on)
+    for (int i = 0; i < QF_PROF_PHASES; ++i) {
+      qf::g_prof[i].n = 0;
+      qf::g_prof[i].open = false;
+    }
   return QF_OK;
 }
 
 extern "C" int qf_profile_read(int phase, float* ms) {
   QF_REQUIRE(ms != nullptr && phase >= 0 && phase < QF_PROF_PHASES, QF_E_INVALID, "qf_profile_read: bad argument");
-  QF_REQUIRE(qf::g_prof_init && qf::g_prof_rec[phase], QF_E_INVALID, "qf_profile_read: phase %d was not recorded", phase);
-  QF_CUDA_TRY(cudaEventSynchronize(qf::g_prof_ev[phase][1]));
-  QF_CUDA_TRY(cudaEventElapsedTime(ms, qf::g_prof_ev[phase][0], qf::g_prof_ev[phase][1]));
+  qf::ProfPhase& ph = qf::g_prof[phase];
+  QF_REQUIRE(ph.n > 0, QF_E_INVALID, "qf_profile_read: phase %d was not recorded", phase);
+  QF_CUDA_TRY(cudaEventSynchronize(ph.ev[ph.n - 1][1]));
+  double sum = 0.0;
+  for (int i = 0; i < ph.n; ++i) {
+    float t = 0.f;
+    QF_CUDA_TRY(cudaEventElapsedTime(&t, ph.ev[i][0], ph.ev[i][1]));
+    sum += t;
+  }
+  *ms = (float)(sum / ph.n);
   return QF_OK;
 }

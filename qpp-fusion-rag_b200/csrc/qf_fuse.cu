@@ -625,15 +625,20 @@ extern "C" int qf_fuse(const int32_t* doc_ids, const void* scores, int score_typ
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (qf::fuse_stream_supported(p)) {
     // common case: streaming kernel; the general kernel then finishes whatever it deferred (usually nothing)
+    qf::prof_mark(QF_PROF_FUSE_STREAM, 0, st);
     rc = qf::fuse_stream_launch(p, score_type, st);
+    qf::prof_mark(QF_PROF_FUSE_STREAM, 1, st);
     if (rc != QF_OK) return rc;
     p.fixup = 1;
     static const bool no_fixup = getenv("QF_STREAM_NOFIXUP") != nullptr;   // debug hook: leave deferred queries marked
     if (no_fixup) return QF_OK;
   }
+  qf::prof_mark(QF_PROF_FUSE_GENERAL, 0, st);
   switch (score_type) {
-    case QF_SCORE_F64: return dispatch_cap<QF_SCORE_F64>(p, st);
-    case QF_SCORE_F32: return dispatch_cap<QF_SCORE_F32>(p, st);
-    default: return dispatch_cap<QF_SCORE_MICRO>(p, st);
+    case QF_SCORE_F64: rc = dispatch_cap<QF_SCORE_F64>(p, st); break;
+    case QF_SCORE_F32: rc = dispatch_cap<QF_SCORE_F32>(p, st); break;
+    default: rc = dispatch_cap<QF_SCORE_MICRO>(p, st); break;
   }
+  qf::prof_mark(QF_PROF_FUSE_GENERAL, 1, st);
+  return rc;
 }

@@ -41,11 +41,21 @@ constexpr int CB = 64;           // coarse bins of the equalisation histogram
 constexpr int MAXPROBE = 64;     // key groups (of 4) visited before the query is deferred
 constexpr int LONGB = 160;       // longest bucket ranked by pairwise comparison
 
-__device__ __forceinline__ uint4 lds128_volatile(const void* ptr) {
+// Shared-memory accesses by 32-bit shared-window address (no generic->shared conversion per access).
+__device__ __forceinline__ uint4 lds128_volatile(u32 sa) {
   uint4 v;
-  const unsigned a = (unsigned)__cvta_generic_to_shared(ptr);
-  asm volatile("ld.volatile.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  asm volatile("ld.volatile.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(sa));
   return v;
+}
+__device__ __forceinline__ u32 atoms_cas(u32 sa, u32 cmp, u32 val) {
+  u32 old;
+  asm volatile("atom.shared.cas.b32 %0, [%1], %2, %3;" : "=r"(old) : "r"(sa), "r"(cmp), "r"(val) : "memory");
+  return old;
+}
+__device__ __forceinline__ u32 atoms_or(u32 sa, u32 val) {
+  u32 old;
+  asm volatile("atom.shared.or.b32 %0, [%1], %2;" : "=r"(old) : "r"(sa), "r"(val) : "memory");
+  return old;
 }
 
 struct SMisc {
@@ -59,16 +69,11 @@ struct SMisc {
   int status;
 };
 
-// Classify one group of 4 keys with a single select chain: 0..3 = position of `id`, 4..7 = 4 + position of the
-// first empty key (no match), -1 = four foreign keys.
-__device__ __forceinline__ int probe4(const uint4& k, u32 id) {
+// Position of `id` among the 4 keys of a group (0..3) or -1: one select chain, no branches.
+__device__ __forceinline__ int hit4(const uint4& k, u32 id) {
   int pos;
   asm("{\n\t.reg .pred p;\n\t"
       "mov.s32 %0, -1;\n\t"
-      "setp.eq.u32 p, %4, 0xffffffff;\n\tselp.s32 %0, 7, %0, p;\n\t"
-      "setp.eq.u32 p, %3, 0xffffffff;\n\tselp.s32 %0, 6, %0, p;\n\t"
-      "setp.eq.u32 p, %2, 0xffffffff;\n\tselp.s32 %0, 5, %0, p;\n\t"
-      "setp.eq.u32 p, %1, 0xffffffff;\n\tselp.s32 %0, 4, %0, p;\n\t"
       "setp.eq.u32 p, %4, %5;\n\tselp.s32 %0, 3, %0, p;\n\t"
       "setp.eq.u32 p, %3, %5;\n\tselp.s32 %0, 2, %0, p;\n\t"
       "setp.eq.u32 p, %2, %5;\n\tselp.s32 %0, 1, %0, p;\n\t"
@@ -77,6 +82,19 @@ __device__ __forceinline__ int probe4(const uint4& k, u32 id) {
       : "=r"(pos)
       : "r"(k.x), "r"(k.y), "r"(k.z), "r"(k.w), "r"(id));
   return pos;
+}
+// Bit i set when key i of the group is still empty.
+__device__ __forceinline__ u32 empty4(const uint4& k) {
+  u32 a, b, c, d;
+  asm("{\n\t.reg .pred p;\n\t"
+      "setp.eq.u32 p, %4, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t"
+      "setp.eq.u32 p, %5, 0xffffffff;\n\tselp.u32 %1, 2, 0, p;\n\t"
+      "setp.eq.u32 p, %6, 0xffffffff;\n\tselp.u32 %2, 4, 0, p;\n\t"
+      "setp.eq.u32 p, %7, 0xffffffff;\n\tselp.u32 %3, 8, 0, p;\n\t"
+      "}"
+      : "=r"(a), "=r"(b), "=r"(c), "=r"(d)
+      : "r"(k.x), "r"(k.y), "r"(k.z), "r"(k.w));
+  return a | b | c | d;
 }
 
 template <int G, int UCAP, int NB, int NMAX, int NT>
@@ -100,11 +118,7 @@ struct SLayout {
   static_assert(NT / 32 <= 16 && NT / 32 >= 2, "warps");
 };
 
-__device__ __forceinline__ int warp_sum_int(int v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
+__device__ __forceinline__ int warp_sum_int(int v) { return __reduce_add_sync(0xffffffffu, v); }
 
 template <typename raw_t> struct Chunk {
   int id[4];
@@ -138,6 +152,8 @@ __global__ void __launch_bounds__(NT, MINB) fuse_stream_kernel(const FuseParams 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int R = p.R, K = p.K;
   const size_t out_stride = (size_t)R * K;
+  const u32 keys_sa = (u32)__cvta_generic_to_shared(s_keys);
+  const u32 meta_sa = (u32)__cvta_generic_to_shared(s_meta);
   const bool is_rrf = MODE ? (p.method == QF_METHOD_RRF) : false;
   const bool is_mnz = (p.method == QF_METHOD_MNZ);
   const bool weighted = (p.weights != nullptr);
@@ -283,7 +299,7 @@ __global__ void __launch_bounds__(NT, MINB) fuse_stream_kernel(const FuseParams 
       int idx[4];
       bool valid[4];
       u32 g[4];
-      uint4 kk[4];
+      uint4 kk[2];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         idx[j] = vec ? base + tid * 4 + j : base + j * NT + tid;
@@ -305,57 +321,63 @@ __global__ void __launch_bounds__(NT, MINB) fuse_stream_kernel(const FuseParams 
             if (prev > c.rk[j]) bad_order = true;
           }
       }
-      // home groups of all four postings fetched back to back
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      // Home group of posting j+1 is fetched while posting j is resolved (a longer look-ahead only makes the
+      // fetched keys staler and the claims below fail more often).
+      auto fetch = [&](int j) {
         if (valid[j]) {
           if ((u32)c.id[j] == EMPTY) {
             defer = true;
             valid[j] = false;
           } else {
             g[j] = __umulhi((u32)c.id[j] * 2654435761u, (u32)G);
-            kk[j] = lds128_volatile(s_keys + 4 * g[j]);
+            kk[j & 1] = lds128_volatile(keys_sa + 16u * g[j]);
           }
         }
-      }
+      };
+      fetch(0);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        // Probe loop, uniform over the warp (lanes that are done idle, nobody runs a private code path): one
-        // select chain classifies the group -- doc found / first empty key / four foreign keys.  Probe order is
-        // group by group, keys 0..3; a doc always sits before the first empty key of its probe order, so
-        // "match, else claim the first empty key with one CAS, else next group" is exact.
+        if (j + 1 < 4) fetch(j + 1);
+        // Probe loop, uniform over the warp (lanes that are done idle, nobody runs a private code path).  Probe
+        // order is group by group, keys 0..3; a doc always sits before the first empty key of its probe order, so
+        // "match, else claim the first empty key with one CAS, else next group" is exact.  A claim lost to another
+        // doc moves on to the next empty key of the same (possibly stale) view -- stale views only ever show too
+        // many empty keys, and a CAS on a key that meanwhile holds this very doc returns it (= found).
         int slot = -1;
         bool inserted = false;
         {
           const u32 id = (u32)c.id[j];
           u32 gq = g[j];
-          uint4 k4 = kk[j];
+          uint4 k4 = kk[j & 1];
           int probes = 0;
           bool active = valid[j];
           while (__any_sync(0xffffffffu, active)) {
             if (active) {
-              const int pos = probe4(k4, id);
-              if (pos < 0) {                                   // four foreign keys: next group
-                if (++probes > MAXPROBE) {
-                  defer = true;
-                  active = false;
-                } else {
-                  gq = gq + 1 == (u32)G ? 0u : gq + 1;
-                  k4 = lds128_volatile(s_keys + 4 * gq);
-                }
+              const int hit = hit4(k4, id);
+              u32 em = empty4(k4);
+              if (hit >= 0) {
+                slot = (int)(4 * gq) + hit;
+                active = false;
               } else {
-                const int cand = (int)(4 * gq) + (pos & 3);
-                u32 o = id;
-                if (pos >= 4) {
-                  o = atomicCAS(&s_keys[cand], EMPTY, id);
-                  inserted = (o == EMPTY);
-                  o = inserted ? id : o;
+                while (em) {
+                  const int e = __ffs((int)em) - 1;
+                  const u32 o = atoms_cas(keys_sa + 16u * gq + 4u * (u32)e, EMPTY, id);
+                  if (o == EMPTY || o == id) {
+                    slot = (int)(4 * gq) + e;
+                    inserted = (o == EMPTY);
+                    active = false;
+                    break;
+                  }
+                  em &= em - 1;
                 }
-                if (o == id) {
-                  slot = cand;
-                  active = false;
-                } else {
-                  k4 = lds128_volatile(s_keys + 4 * gq);       // lost the key to another doc: look again
+                if (active) {                                  // group full of foreign keys: next group
+                  if (++probes > MAXPROBE) {
+                    defer = true;
+                    active = false;
+                  } else {
+                    gq = gq + 1 == (u32)G ? 0u : gq + 1;
+                    k4 = lds128_volatile(keys_sa + 16u * gq);
+                  }
                 }
               }
             }
@@ -379,7 +401,7 @@ __global__ void __launch_bounds__(NT, MINB) fuse_stream_kernel(const FuseParams 
             ++ins;
             bits |= (u32)(s0 + idx[j]) << 16;
           }
-          const u32 om = atomicOr(&s_meta[slot], bits);
+          const u32 om = atoms_or(meta_sa + 4u * (u32)slot, bits);
           const double prev = inserted ? 0.0 : s_acc[slot];     // the reference starts from 0.0 (src/fusion.py:275)
           if (om & (1u << r)) defer = true;                     // the doc id occurs twice inside list r
           else s_acc[slot] = __dadd_rn(prev, v);
@@ -434,10 +456,13 @@ __global__ void __launch_bounds__(NT, MINB) fuse_stream_kernel(const FuseParams 
       const int slot = tid + k * NT;
       if (slot < H && s_keys[slot] != EMPTY) {
         const u32 mt = s_meta[slot];
+        // the accumulator started from +0.0 and x + (-x) rounds to +0.0, so it is never -0.0 (Python treats
+        // -0.0 == 0.0 as a tie; nothing to canonicalise) and only CombMNZ rewrites it
         double a = s_acc[slot];
-        if (is_mnz) a = __dmul_rn(a, (double)cntbits(mt));
-        a = __dadd_rn(a, 0.0);               // -0.0 -> +0.0 (Python: -0.0 == 0.0 is a tie)
-        s_acc[slot] = a;
+        if (is_mnz) {
+          a = __dmul_rn(a, (double)cntbits(mt));
+          s_acc[slot] = a;
+        }
         fmn = a < fmn ? a : fmn;
         fmx = a > fmx ? a : fmx;
         if (!has) {

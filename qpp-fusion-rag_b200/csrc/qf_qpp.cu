@@ -66,20 +66,21 @@ __device__ __forceinline__ double warp_var(F get, int cnt, int lane, double* mea
   return v / (double)cnt;
 }
 
-template <int ST>
+// RESEARCH = false: the 13 QPPBridge columns only (the pipeline's step 03); no bootstrap buffers, so more warps per SM.
+template <int ST, bool RESEARCH>
 __global__ void __launch_bounds__(NT) qpp_kernel(const QppParams p) {
   using raw_t = typename Raw<ST>::type;
+  constexpr int ML = RESEARCH ? MAXLIST : 4;
   __shared__ double s_x[WARPS][MAXK];          // first k scores (float32-rounded, widened)
-  __shared__ double s_win[WARPS][MAXK];        // var of x[0:i]
-  __shared__ float s_all[WARPS][MAXLIST];      // whole list as float32 (bootstrap)
-  __shared__ unsigned s_cnt[WARPS][MAXLIST / 4 + 1];   // RBO depth histogram, 4 x 8-bit counters per word
+  __shared__ float s_all[WARPS][ML];           // whole list as float32 (bootstrap)
+  __shared__ unsigned s_cnt[WARPS][ML / 4 + 1];        // RBO depth histogram, 4 x 8-bit counters per word
                                                         // (a depth bucket holds at most 2 sample entries)
-  __shared__ unsigned short s_samp[WARPS][MAXK];
-  __shared__ double s_pw[MAXLIST];             // p^(d-1)
+  __shared__ unsigned short s_samp[WARPS][RESEARCH ? MAXK : 4];
+  __shared__ double s_pw[ML];                  // p^(d-1)
   __shared__ double s_uefw[20];                // UEF rank weights 1 / log2(i + 2)
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const bool research = p.perms != nullptr;
+  constexpr bool research = RESEARCH;
   const double p09 = (double)0.9f;              // RBO p is a Java float
   if (research) {
     for (int d = tid; d < p.K && d < MAXLIST; d += NT) s_pw[d] = pow(p09, (double)d);
@@ -147,23 +148,32 @@ __global__ void __launch_bounds__(NT) qpp_kernel(const QppParams p) {
         col[2] = qf::warp_sum(a) / ((double)nT * kk);
       }
       {                                                                  // SigmaMax :269-293, cumnqc :400-410
-        double* win = s_win[warp];
-        for (int i = 2 + lane; i <= k; i += 32) {
-          double s = 0.0;
-          for (int j = 0; j < i; ++j) s += x[j];
-          const double mu = s / (double)i;
-          double v = 0.0;
-          for (int j = 0; j < i; ++j) {
-            const double d = x[j] - mu;
-            v += d * d;
+        // Population variance of every prefix x[0:i], i = 2..k.  The Java recomputes each window from scratch
+        // (O(k^2)); here one warp scan of y = x - x[0] and y^2 gives var_i = (S2_i - S_i^2 / i) / i.  Every window
+        // contains x[0] (y = 0), so the window's spread is at least its largest |y| and the subtraction loses at
+        // most a factor ~2i of precision: relative error ~1e-14 (parity tolerance 1e-9); all-equal prefixes give an
+        // exact 0 as the two-pass formula does.
+        const double x0 = x[0];
+        double mx = 0.0, sm = 0.0, cs = 0.0, cs2 = 0.0;
+        for (int base = 0; base < k; base += 32) {
+          const int j = base + lane;
+          const double y = j < k ? x[j] - x0 : 0.0;
+          double a = y, b = y * y;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const double ta = __shfl_up_sync(0xffffffffu, a, o), tb = __shfl_up_sync(0xffffffffu, b, o);
+            if (lane >= o) { a += ta; b += tb; }
           }
-          win[i - 2] = v / (double)i;
-        }
-        __syncwarp();
-        double mx = 0.0, sm = 0.0;
-        for (int i = lane; i < k - 1; i += 32) {
-          mx = fmax(mx, win[i]);
-          sm += win[i];
+          a += cs;
+          b += cs2;
+          if (j >= 1 && j < k) {                                         // window i = j + 1
+            const double n_i = (double)(j + 1);
+            const double v = fmax((b - a * a / n_i) / n_i, 0.0);
+            mx = fmax(mx, v);
+            sm += v;
+          }
+          cs = __shfl_sync(0xffffffffu, a, 31);
+          cs2 = __shfl_sync(0xffffffffu, b, 31);
         }
         mx = qf::warp_max(mx);
         sm = qf::warp_sum(sm);
@@ -339,35 +349,62 @@ __global__ void colnorm_init(ColStat* st, int n) {
   if (i < n) { st[i].omin = ~0ull; st[i].omax = 0ull; st[i].sum = 0.0; st[i].sumsq = 0.0; }
 }
 
-// pass 1: min / max / sum per (r, col); pass 2: sum of squared deviations
+// pass 1: min / max / sum per (r, col); pass 2: sum of squared deviations.
+// A CTA owns a contiguous range of rows; thread (row group, column) keeps its column's statistics in registers while
+// it walks the rows (loads coalesced across columns), so shared and global atomics are per (row group, column), not
+// per element.
 template <int PASS>
 __global__ void __launch_bounds__(256) colnorm_reduce(const double* vals, long long Q, int RC, ColStat* st) {
   extern __shared__ unsigned char sm_raw[];
   ColStat* loc = reinterpret_cast<ColStat*>(sm_raw);
   for (int i = threadIdx.x; i < RC; i += blockDim.x) { loc[i].omin = ~0ull; loc[i].omax = 0ull; loc[i].sum = 0.0; loc[i].sumsq = 0.0; }
   __syncthreads();
-  const long long total = Q * RC;
-  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(e % RC);
-    const double v = vals[e];
-    if (PASS == 1) {
-      const unsigned long long o = qf::ord_f64(v + 0.0);
-      atomicMin(&loc[c].omin, o);
-      atomicMax(&loc[c].omax, o);
-      atomicAdd(&loc[c].sum, v);
-    } else {
-      const double d = v - st[c].sum / (double)Q;
-      atomicAdd(&loc[c].sumsq, d * d);
+  const int cpt = RC < (int)blockDim.x ? RC : (int)blockDim.x;     // columns per sweep
+  const int n_rg = (int)blockDim.x / cpt;                           // row groups
+  const int c_in = (int)threadIdx.x % cpt, rg = (int)threadIdx.x / cpt;
+  const long long rows_per = (Q + gridDim.x - 1) / gridDim.x;
+  const long long q0 = (long long)blockIdx.x * rows_per;
+  const long long q1 = q0 + rows_per < Q ? q0 + rows_per : Q;
+  if (rg < n_rg) {
+    for (int c = c_in; c < RC; c += cpt) {
+      unsigned long long omin = ~0ull, omax = 0ull;
+      double sum = 0.0;
+      const double mean = PASS == 2 ? st[c].sum / (double)Q : 0.0;
+      bool any = false;
+      for (long long q = q0 + rg; q < q1; q += n_rg) {
+        const double v = vals[q * RC + c];
+        any = true;
+        if (PASS == 1) {
+          const unsigned long long o = qf::ord_f64(v + 0.0);
+          omin = o < omin ? o : omin;
+          omax = o > omax ? o : omax;
+          sum += v;
+        } else {
+          const double d = v - mean;
+          sum += d * d;
+        }
+      }
+      if (any) {
+        if (PASS == 1) {
+          atomicMin(&loc[c].omin, omin);
+          atomicMax(&loc[c].omax, omax);
+          atomicAdd(&loc[c].sum, sum);
+        } else {
+          atomicAdd(&loc[c].sumsq, sum);
+        }
+      }
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < RC; i += blockDim.x) {
-    if (PASS == 1) {
-      atomicMin(&st[i].omin, loc[i].omin);
-      atomicMax(&st[i].omax, loc[i].omax);
-      atomicAdd(&st[i].sum, loc[i].sum);
-    } else {
-      atomicAdd(&st[i].sumsq, loc[i].sumsq);
+  if (q0 < q1) {
+    for (int i = threadIdx.x; i < RC; i += blockDim.x) {
+      if (PASS == 1) {
+        atomicMin(&st[i].omin, loc[i].omin);
+        atomicMax(&st[i].omax, loc[i].omax);
+        atomicAdd(&st[i].sum, loc[i].sum);
+      } else {
+        atomicAdd(&st[i].sumsq, loc[i].sumsq);
+      }
     }
   }
 }
@@ -493,11 +530,22 @@ extern "C" int qf_qpp_stats(const void* scores, int score_type, const int32_t* l
   const long long cap = (long long)qf::sm_count() * 16;
   if (blocks > cap) blocks = cap;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  switch (score_type) {
-    case QF_SCORE_F64: qpp_kernel<QF_SCORE_F64><<<(unsigned)blocks, NT, 0, st>>>(p); break;
-    case QF_SCORE_F32: qpp_kernel<QF_SCORE_F32><<<(unsigned)blocks, NT, 0, st>>>(p); break;
-    default: qpp_kernel<QF_SCORE_MICRO><<<(unsigned)blocks, NT, 0, st>>>(p); break;
+  const unsigned nb = (unsigned)blocks;
+  qf::prof_mark(QF_PROF_QPP_STATS, 0, st);
+  if (perms) {
+    switch (score_type) {
+      case QF_SCORE_F64: qpp_kernel<QF_SCORE_F64, true><<<nb, NT, 0, st>>>(p); break;
+      case QF_SCORE_F32: qpp_kernel<QF_SCORE_F32, true><<<nb, NT, 0, st>>>(p); break;
+      default: qpp_kernel<QF_SCORE_MICRO, true><<<nb, NT, 0, st>>>(p); break;
+    }
+  } else {
+    switch (score_type) {
+      case QF_SCORE_F64: qpp_kernel<QF_SCORE_F64, false><<<nb, NT, 0, st>>>(p); break;
+      case QF_SCORE_F32: qpp_kernel<QF_SCORE_F32, false><<<nb, NT, 0, st>>>(p); break;
+      default: qpp_kernel<QF_SCORE_MICRO, false><<<nb, NT, 0, st>>>(p); break;
+    }
   }
+  qf::prof_mark(QF_PROF_QPP_STATS, 1, st);
   QF_CUDA_TRY(cudaGetLastError());
   return QF_OK;
 }
@@ -525,11 +573,13 @@ extern "C" int qf_qpp_colnorm(double* vals, int Q, int R, int ncols, int mode, i
   long long blocks = (total + 255) / 256;
   const long long cap = (long long)qf::sm_count() * 8;
   if (blocks > cap) blocks = cap;
+  long long rblocks = ((long long)Q + 15) / 16;          // reduce: a contiguous row range per CTA
+  if (rblocks > qf::sm_count()) rblocks = qf::sm_count();
   if (mode != 0) {
     colnorm_init<<<(RC + 255) / 256, 256, 0, st>>>(cs, RC);
-    colnorm_reduce<1><<<(unsigned)blocks, 256, sizeof(ColStat) * RC, st>>>(vals, Q, RC, cs);
+    colnorm_reduce<1><<<(unsigned)rblocks, 256, sizeof(ColStat) * RC, st>>>(vals, Q, RC, cs);
     if (mode == QF_COLNORM_ZSCORE)
-      colnorm_reduce<2><<<(unsigned)blocks, 256, sizeof(ColStat) * RC, st>>>(vals, Q, RC, cs);
+      colnorm_reduce<2><<<(unsigned)rblocks, 256, sizeof(ColStat) * RC, st>>>(vals, Q, RC, cs);
   }
   if (mode != 0 || round6_flag)
     colnorm_apply<<<(unsigned)blocks, 256, 0, st>>>(vals, Q, RC, cs, mode, round6_flag);
@@ -572,7 +622,9 @@ extern "C" int qf_qpp_colstats(const double* vals, int Q, int R, int ncols, cons
   if (blocks < 1) blocks = 1;
   colnorm_init<<<(RC + 255) / 256, 256, 0, st>>>(cs, RC);
   if (Q > 0) {
-    colnorm_reduce<1><<<(unsigned)blocks, 256, sizeof(ColStat) * RC, st>>>(vals, Q, RC, cs);
+    long long rblocks = ((long long)Q + 15) / 16;
+    if (rblocks > qf::sm_count()) rblocks = qf::sm_count();
+    colnorm_reduce<1><<<(unsigned)rblocks, 256, sizeof(ColStat) * RC, st>>>(vals, Q, RC, cs);
     if (mean) colstats_sumsq<1><<<(unsigned)blocks, 256, sizeof(double) * RC, st>>>(vals, Q, RC, mean, cs);
   }
   colstats_export<<<(RC + 255) / 256, 256, 0, st>>>(cs, RC, stats);

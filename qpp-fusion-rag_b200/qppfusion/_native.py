@@ -125,6 +125,7 @@ def require_cuda(*tensors: Optional[torch.Tensor]) -> torch.device:
 
 
 PROF_DENSE_SAMPLE, PROF_DENSE_TAU, PROF_DENSE_MAIN, PROF_DENSE_SELECT = 0, 1, 2, 3
+PROF_FUSE_STREAM, PROF_FUSE_GENERAL, PROF_QPP_STATS = 4, 5, 6
 
 
 def profile_enable(on: bool) -> None:

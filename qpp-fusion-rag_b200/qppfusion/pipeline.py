@@ -1,0 +1,60 @@
+"""
+Device-side step of the reference's 03_qpp -> 05_fusion pipeline, captured as a CUDA graph.
+
+One step = qf_qpp_stats (13 QPPBridge predictors per run list, scripts/03_qpp.py -> src/qpp.py:245-337)
+         -> qf_qpp_colnorm (cross-query min-max / z-score + "%.6f", src/qpp.py:340-374, :331-334)
+         -> qf_qpp_select_weight (get_qpp_weight, src/fusion.py:116-158)
+         -> qf_fuse (weighted_combsum / weighted_combmnz / weighted_rrf, src/fusion.py:237-380).
+The kernels are short (tens to hundreds of microseconds), so issuing them one by one from Python leaves the GPU
+waiting for the host; the graph replays the whole step with one launch.  Inputs live in caller-owned device tensors
+whose storage the graph reads on every replay (refill them in place, e.g. with copy_ from pinned host memory).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _native as N
+from . import ops
+
+
+class FusionStepGraph:
+    def __init__(self, doc_ids: torch.Tensor, scores: torch.Tensor, lens: torch.Tensor, text_feats: torch.Tensor, *,
+                 qpp_index: int = 5, top_k: int = 100, k_cut: int = 50, colnorm: Optional[str] = "minmax",
+                 round6: bool = True, method: int = N.METHOD_SUM, norm: int = N.NORM_NONE, rrf_k: float = 60.0,
+                 flags: int = 0, want_counts: bool = False, want_pos: bool = False, compact: bool = False,
+                 ranks: Optional[torch.Tensor] = None, warmup: int = 2):
+        self.dev = N.require_cuda(doc_ids, scores, lens, text_feats, ranks)
+        self.inputs = (doc_ids, scores, lens, text_feats, ranks)
+        self._cfg = dict(qpp_index=int(qpp_index), top_k=int(top_k), k_cut=int(k_cut), colnorm=colnorm,
+                         round6=bool(round6), method=int(method), norm=int(norm), rrf_k=float(rrf_k), flags=int(flags),
+                         want_counts=bool(want_counts), want_pos=bool(want_pos), compact=bool(compact))
+        cur = torch.cuda.current_stream(self.dev)
+        side = torch.cuda.Stream(self.dev)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):          # warm-up outside capture: one-time kernel attribute setup, allocator
+            for _ in range(max(1, warmup)):
+                self._body()
+        cur.wait_stream(side)
+        torch.cuda.synchronize(self.dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.qpp, self.weights, self.out, self.csr = self._body()
+
+    def _body(self):
+        ids, sc, lens, feats, ranks = self.inputs
+        c = self._cfg
+        qpp, _status = ops.qpp_stats(sc, lens, feats, None, None, top_k=c["top_k"], k_cut=c["k_cut"])
+        if c["colnorm"] or c["round6"]:
+            ops.qpp_colnorm_(qpp, c["colnorm"] or "none", round6=c["round6"])
+        w = ops.qpp_select_weight(qpp, c["qpp_index"])
+        out = ops.fuse(ids, sc, lens, w, ranks, c["method"], c["norm"], c["rrf_k"], c["flags"],
+                       want_counts=c["want_counts"], want_pos=c["want_pos"])
+        csr = ops.compact_fused(out) if c["compact"] else None
+        return qpp, w, out, csr
+
+    def replay(self):
+        """Run the captured step on the current stream; returns the (static) FuseOut."""
+        self.graph.replay()
+        return self.out
