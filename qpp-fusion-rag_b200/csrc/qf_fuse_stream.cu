@@ -399,7 +399,9 @@ __global__ void __launch_bounds__(NT, MINB) fuse_stream_kernel(const FuseParams 
           if (skip_zero && counts) bits |= 1u << (8 + r);
           if (inserted) {
             ++ins;
-            bits |= (u32)(s0 + idx[j]) << 16;
+            const u32 seq = (u32)(s0 + idx[j]);
+            bits |= seq << 16;
+            if (want_pos) atomicOr(&s_bitmap[seq >> 5], 1u << (seq & 31u));   // first-seen bitmap (out_pos)
           }
           const u32 om = atoms_or(meta_sa + 4u * (u32)slot, bits);
           const double prev = inserted ? 0.0 : s_acc[slot];     // the reference starts from 0.0 (src/fusion.py:275)
@@ -411,8 +413,9 @@ __global__ void __launch_bounds__(NT, MINB) fuse_stream_kernel(const FuseParams 
     };
 
     bool deferred = false;
+    int total_ins = 0;
     {
-      int r = 0, base = 0, total_ins = 0;
+      int r = 0, base = 0;
       while (r < R && m.len[r] == 0) ++r;
       Chunk<raw_t> cur, nxt;
       load(cur, r, base);
@@ -446,54 +449,60 @@ __global__ void __launch_bounds__(NT, MINB) fuse_stream_kernel(const FuseParams 
       continue;
     }
 
-    // ------------------------------------------------------------ B: final scores, range, sample
+    // ------------------------------------------------------------ B: score range and histogram from a sample
+    // The union size is the number of claimed keys.  Final score of a slot = accumulator (x popcount for CombMNZ).
+    // The accumulator started from +0.0 and x + (-x) rounds to +0.0, so it is never -0.0 (Python treats
+    // -0.0 == 0.0 as a tie): nothing to canonicalise.
+    // The bucket map only has to be MONOTONE in the score, so its range and its equalisation histogram come from a
+    // sample (each thread's first occupied slot); scores outside the sampled range are clamped into the end buckets
+    // and ordered there by the exact comparison like everything else.
     auto cntbits = [&](u32 mt) -> int { return __popc(skip_zero ? ((mt >> 8) & 0xFFu) : (mt & 0xFFFFu)); };
+    auto final_score = [&](int slot, u32 mt) -> double {
+      const double a = s_acc[slot];
+      return is_mnz ? __dmul_rn(a, (double)cntbits(mt)) : a;
+    };
+    const int n_u = total_ins;
     double fmn = INFINITY, fmx = -INFINITY, samp = 0.0;
-    int n_u = 0;
     bool has = false;
-#pragma unroll
-    for (int k = 0; k < SPT; ++k) {
+#pragma unroll 1
+    for (int k = 0; k < SPT && !has; ++k) {
       const int slot = tid + k * NT;
       if (slot < H && s_keys[slot] != EMPTY) {
-        const u32 mt = s_meta[slot];
-        // the accumulator started from +0.0 and x + (-x) rounds to +0.0, so it is never -0.0 (Python treats
-        // -0.0 == 0.0 as a tie; nothing to canonicalise) and only CombMNZ rewrites it
-        double a = s_acc[slot];
-        if (is_mnz) {
-          a = __dmul_rn(a, (double)cntbits(mt));
-          s_acc[slot] = a;
-        }
-        fmn = a < fmn ? a : fmn;
-        fmx = a > fmx ? a : fmx;
-        if (!has) {
-          samp = a;
-          has = true;
-        }
-        ++n_u;
-        if (want_pos) atomicOr(&s_bitmap[mt >> 21], 1u << ((mt >> 16) & 31u));
+        samp = final_score(slot, s_meta[slot]);
+        has = true;
       }
     }
-    fmn = warp_min(fmn);
-    fmx = warp_max(fmx);
-    n_u = warp_sum_int(n_u);
-    if (lane == 0) {
-      m.red_mn[warp] = fmn;
-      m.red_mx[warp] = fmx;
-      m.red_cnt[warp] = n_u;
-    }
-    __syncthreads();
-    fmn = INFINITY;
-    fmx = -INFINITY;
-    n_u = 0;
+    auto block_range = [&](double lo, double hi) {          // -> fmn / fmx over the block (one barrier)
+      lo = warp_min(lo);
+      hi = warp_max(hi);
+      if (lane == 0) {
+        m.red_mn[warp] = lo;
+        m.red_mx[warp] = hi;
+      }
+      __syncthreads();
+      fmn = INFINITY;
+      fmx = -INFINITY;
 #pragma unroll
-    for (int w = 0; w < NW; ++w) {
-      fmn = m.red_mn[w] < fmn ? m.red_mn[w] : fmn;
-      fmx = m.red_mx[w] > fmx ? m.red_mx[w] : fmx;
-      n_u += m.red_cnt[w];
-    }
-    if (n_u > UCAP) {                         // cannot happen after the per-list check; kept as a guard
-      if (tid == 0) p.out_lens[q] = FUSE_DEFERRED;
-      continue;
+      for (int w = 0; w < NW; ++w) {
+        fmn = m.red_mn[w] < fmn ? m.red_mn[w] : fmn;
+        fmx = m.red_mx[w] > fmx ? m.red_mx[w] : fmx;
+      }
+    };
+    block_range(has ? samp : INFINITY, has ? samp : -INFINITY);
+    if (!unranked && !(fmx > fmn)) {
+      // every sampled score equal: find out whether ALL scores are equal (then only first-seen order matters)
+      double lo = INFINITY, hi = -INFINITY;
+#pragma unroll 1
+      for (int k = 0; k < SPT; ++k) {
+        const int slot = tid + k * NT;
+        if (slot < H && s_keys[slot] != EMPTY) {
+          const double a = final_score(slot, s_meta[slot]);
+          lo = a < lo ? a : lo;
+          hi = a > hi ? a : hi;
+        }
+      }
+      __syncthreads();                                       // red_mn / red_mx are being re-used
+      block_range(lo, hi);
     }
     const bool score_mode = !unranked && (fmx > fmn);
     double cscale = 0.0;
@@ -502,9 +511,10 @@ __global__ void __launch_bounds__(NT, MINB) fuse_stream_kernel(const FuseParams 
       if (!(cscale > 0.0) || isinf(cscale)) cscale = 0.0;
     }
     auto coarse = [&](double fs, float& frac) -> int {
-      const float tf = (float)__dmul_rn(__dsub_rn(fmx, fs), cscale);     // monotone in fs
+      float tf = (float)__dmul_rn(__dsub_rn(fmx, fs), cscale);           // monotone in fs
+      tf = fminf(fmaxf(tf, 0.0f), (float)CB);                            // scores outside the sampled range
       int c = (int)tf;
-      c = c < 0 ? 0 : (c > CB - 1 ? CB - 1 : c);
+      c = c > CB - 1 ? CB - 1 : c;
       frac = tf - (float)c;
       return c;
     };
@@ -570,7 +580,12 @@ __global__ void __launch_bounds__(NT, MINB) fuse_stream_kernel(const FuseParams 
           tie = (u32)s_bpre[tie >> 5] + (u32)__popc(s_bitmap[tie >> 5] & ((1u << (tie & 31u)) - 1u));
           s_meta[slot] = (tie << 16) | (mt & 0xFFFFu);
         }
-        const int b = bucket(s_acc[slot], tie);
+        double fs = s_acc[slot];
+        if (is_mnz) {
+          fs = __dmul_rn(fs, (double)cntbits(mt));
+          s_acc[slot] = fs;
+        }
+        const int b = bucket(fs, tie);
         const int sh = (b & 1) * 16;
         const u32 oldc = atomicAdd(&s_cnt32[b >> 1], 1u << sh);
         s_bcache[slot] = (u16)b;

@@ -208,6 +208,30 @@ def test_long_tie_runs_and_skewed_scores():
         check_against_oracle(lists, method, w, out)
 
 
+def test_outliers_outside_the_sampled_score_range():
+    """The streaming kernel takes the bucket map's range from a sample of the scores: queries whose sample is
+    constant while a few unsampled scores differ, and scores far outside the sampled range, must still rank exactly."""
+    rng = np.random.default_rng(26)
+    lists = []
+    for q in range(12):
+        n = int(rng.integers(100, 155))
+        docs = rng.choice(10**6, size=n + 3, replace=False)
+        rows = [(int(docs[0]), 7.5, 1), (int(docs[1]), 0.9, 2)]
+        rows += [(int(d), 0.5, i + 3) for i, d in enumerate(docs[3:])]
+        rows.append((int(docs[2]), -4.0, n + 3))
+        lists.append([rows, rows[:1] + rows[-1:]])
+    for q in range(4):
+        n = 1500 + 100 * q
+        docs = rng.choice(10**6, size=n, replace=False)
+        sc = np.sort(np.concatenate([[1e6, 5e5, -1e6], np.round(rng.random(n - 3), 6)]))[::-1]
+        rows = [(int(d), float(s_), i + 1) for i, (d, s_) in enumerate(zip(docs, sc))]
+        lists.append([rows, rows[::7]])
+    w = np.ones((len(lists), 2))
+    for method in ("sum", "mnz"):
+        out = run_gpu(lists, method, w, k=2000)
+        check_against_oracle(lists, method, w, out)
+
+
 def test_empty_queries_and_bad_lens():
     lists = synth_lists(13, n_q=3, n_r=3, k=10, pool=30)
     lists[1] = [[], [], []]
