@@ -34,12 +34,18 @@ def launches(path, out, cmd):
         a = agg.setdefault(name, [0, 0.0])
         a[0] += 1
         a[1] += float(r[vi].replace(",", ""))
-    tot = sum(v[1] for v in agg.values())
+    is_torch = lambda k: "native::" in k or "kernelPointwiseApply" in k or k.startswith("void at::") or "elementwise_kernel" in k or "cub::" in k
+    ours = {k: v for k, v in agg.items() if not is_torch(k)}
+    tot = sum(v[1] for v in ours.values())
     with open(out, "w") as f:
         f.write(f"# ncu --metrics gpu__time_duration.sum --clock-control none  {cmd}\n")
-        f.write("# libqppfusion kernels only; per-launch times are cold-cache and serialised: compare SHARES, not absolutes\n")
-        for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        f.write("# libqppfusion kernels; per-launch times are cold-cache and serialised: compare SHARES, not absolutes\n")
+        for k, v in sorted(ours.items(), key=lambda kv: -kv[1][1]):
             f.write(f"{v[1] / v[0] / 1e3:10.1f} us/launch  share {100 * v[1] / tot:5.1f}%  launches={v[0]:3d}  {k}\n")
+        t_n = sum(v[0] for k, v in agg.items() if is_torch(k))
+        t_t = sum(v[1] for k, v in agg.items() if is_torch(k))
+        f.write(f"# PyTorch kernels in the same capture (synthetic data generation, dtype casts, parity spot check; outside "
+                f"the timed regions): {t_n} launches, {t_t / 1e6:.2f} ms in total\n")
 
 
 def kernel(rep, out, title, src=None):
