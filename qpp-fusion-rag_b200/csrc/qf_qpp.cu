@@ -32,7 +32,7 @@ struct QppParams {
 // double quotient is correctly rounded; if it sits exactly on a float32 rounding boundary the sign of
 // the exact residual decides.
 __device__ __forceinline__ float micro_to_f32(int v) {
-  const double d = __ddiv_rn((double)v, 1.0e6);
+  const double d = qf::micro_to_f64(v);       // == v / 1e6 correctly rounded (exhaustively verified), no division
   const float fu = __double2float_ru(d), fd = __double2float_rd(d);
   if (fu == fd) return fu;
   const double mid = 0.5 * ((double)fu + (double)fd);
@@ -337,6 +337,189 @@ __global__ void __launch_bounds__(NT) qpp_kernel(const QppParams p) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Bridge-only kernel (the pipeline's step 03: the 13 QPPBridge columns; research columns are written as 0).
+// EIGHT lanes per list, four lists per warp: k_cut = 50 scores are 7 per lane, and every reduction is 3 shuffle
+// steps inside the 8-lane group instead of 5 across a warp that is 36 % idle in its second pass.  Groups are
+// independent (shuffles and syncs use the group's lane mask), so lists of different length may diverge freely.
+// Same formulas as qpp_kernel above (QPPBridge.java:134-453); only the summation grouping differs (tolerance 1e-9).
+// ------------------------------------------------------------------------------------------------
+constexpr int LPL = 8;                 // lanes per list
+constexpr int GPW = 32 / LPL;          // lists per warp
+
+__device__ __forceinline__ double gsum(unsigned m, double v) {
+#pragma unroll
+  for (int o = LPL / 2; o > 0; o >>= 1) v += __shfl_xor_sync(m, v, o);
+  return v;
+}
+__device__ __forceinline__ double gmax(unsigned m, double v) {
+#pragma unroll
+  for (int o = LPL / 2; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(m, v, o));
+  return v;
+}
+__device__ __forceinline__ double gmin(unsigned m, double v) {
+#pragma unroll
+  for (int o = LPL / 2; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(m, v, o));
+  return v;
+}
+
+template <int ST>
+__global__ void __launch_bounds__(NT) qpp_bridge_kernel(const QppParams p) {
+  using raw_t = typename Raw<ST>::type;
+  __shared__ double s_x[WARPS * GPW][MAXK];    // first k scores of each list in flight (float32-rounded, widened)
+  __shared__ double s_uefw[20];                // UEF rank weights 1 / log2(i + 2)
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int sl = lane & (LPL - 1), gi = lane / LPL;
+  const unsigned gm = ((1u << LPL) - 1u) << (gi * LPL);
+  if (tid < 20) s_uefw[tid] = 1.0 / (log((double)(tid + 2)) / log(2.0));
+  __syncthreads();
+
+  double* x = s_x[warp * GPW + gi];
+  const long long n_lists = (long long)p.Q * p.R;
+  const long long stride = (long long)gridDim.x * WARPS * GPW;
+  for (long long li = ((long long)blockIdx.x * WARPS + warp) * GPW + gi; li < n_lists; li += stride) {
+    const int q = (int)(li / p.R);
+    const raw_t* g = reinterpret_cast<const raw_t*>(p.scores) + li * p.K;
+    double* out = p.out + li * QF_QPP_COLS;
+    int len = p.lens[li];
+    int status = 0;
+    if (len < 0 || len > p.K) { status |= QF_QSTAT_BAD_LEN; len = 0; }
+    const int k = min(p.k_cut, min(len, p.top_k));
+
+    __syncwarp(gm);                             // previous list's x is dead
+    for (int j = sl; j < k; j += LPL) x[j] = (double)Raw<ST>::f32(__ldg(g + j));
+    __syncwarp(gm);
+    int unsorted = 0;
+    for (int j = sl + 1; j < k; j += LPL) unsorted |= (x[j - 1] < x[j]);
+    if (__any_sync(gm, unsorted)) status |= QF_QSTAT_UNSORTED;
+
+    const int* tf = p.text_feats + (size_t)q * 4;
+    const int n_terms = tf[0], n_unique = tf[1], max_len = tf[2], sum_len = tf[3];
+    const int nT = max(1, n_terms);
+
+    double col[QF_QPP_BRIDGE_COLS];
+#pragma unroll
+    for (int c = 0; c < QF_QPP_BRIDGE_COLS; ++c) col[c] = 0.0;
+
+    if (k > 0) {
+      const double kk = (double)k;
+      // one pass: sum, min, max, count/sum above half of the top score
+      const double thr = x[0] * 0.5;
+      double s1 = 0.0, mn = INFINITY, mx = -INFINITY, sx = 0.0;
+      int cx = 0;
+      for (int j = sl; j < k; j += LPL) {
+        const double v = x[j];
+        s1 += v;
+        mn = fmin(mn, v);
+        mx = fmax(mx, v);
+        if (v >= thr) { ++cx; sx += v; }
+      }
+      s1 = gsum(gm, s1);
+      mn = gmin(gm, mn);
+      mx = gmax(gm, mx);
+      sx = gsum(gm, sx);
+      cx = __reduce_add_sync(gm, cx);
+      const double mean = s1 / kk;
+      const double mu_smv = mean <= 0 ? 1.0 : mean;
+      const double wig_base = 1.0 / fmax(0.01, mean);
+      const double mu_x = cx >= 1 ? sx / (double)cx : 0.0;
+      // second pass: everything that needs the mean(s)
+      double vsum = 0.0, smv = 0.0, wig = 0.0, vx = 0.0, snqc = 0.0;
+      for (int j = sl; j < k; j += LPL) {
+        const double v = x[j];
+        const double d = v - mean;
+        vsum += d * d;
+        if (v > 0) smv += v * fabs(log(v / mu_smv));
+        wig += v - wig_base;
+        if (v >= thr) { const double dx = v - mu_x; vx += dx * dx; }
+        if (mean > 0 && v > 0) snqc += pow((d * d) / v, 0.33 * 0.33);     // see qpp_kernel: one pow, <= 2 ulp
+      }
+      vsum = gsum(gm, vsum);
+      smv = gsum(gm, smv);
+      wig = gsum(gm, wig);
+      vx = gsum(gm, vx);
+      snqc = gsum(gm, snqc);
+      const double var = vsum / kk;
+      col[0] = var;                                                      // nqc          :202-216
+      col[1] = smv / kk;                                                 // smv          :223-239
+      col[2] = wig / ((double)nT * kk);                                  // wig          :247-262
+      {                                                                  // SigmaMax :269-293, cumnqc :400-410
+        const double x0 = x[0];
+        double wmx = 0.0, wsm = 0.0, cs = 0.0, cs2 = 0.0;
+        for (int base = 0; base < k; base += LPL) {
+          const int j = base + sl;
+          const double y = j < k ? x[j] - x0 : 0.0;
+          double a = y, b = y * y;
+#pragma unroll
+          for (int o = 1; o < LPL; o <<= 1) {
+            const double ta = __shfl_up_sync(gm, a, o, LPL), tb = __shfl_up_sync(gm, b, o, LPL);
+            if (sl >= o) { a += ta; b += tb; }
+          }
+          a += cs;
+          b += cs2;
+          if (j >= 1 && j < k) {                                         // window i = j + 1
+            const double n_i = (double)(j + 1);
+            const double v = fmax((b - a * a / n_i) / n_i, 0.0);
+            wmx = fmax(wmx, v);
+            wsm += v;
+          }
+          cs = __shfl_sync(gm, a, LPL - 1, LPL);
+          cs2 = __shfl_sync(gm, b, LPL - 1, LPL);
+        }
+        wmx = gmax(gm, wmx);
+        wsm = gsum(gm, wsm);
+        if (k >= 2) {
+          col[3] = sqrt(wmx) / sqrt((double)max(1, nT));
+          col[9] = wsm / (double)(k - 1);
+        }
+      }
+      {                                                                  // SigmaX       :299-319
+        const double sig = cx >= 1 ? sqrt(vx / (double)cx) : 0.0;
+        col[4] = (k >= 2 && cx >= 2) ? sig : 0.0;
+      }
+      {                                                                  // RSD skew     :324-342
+        const double sd = sqrt(var);
+        if (k >= 3 && !(sd < 1e-10)) {
+          double a = 0.0;
+          for (int j = sl; j < k; j += LPL) {
+            const double z = (x[j] - mean) / sd;
+            a += z * z * z;
+          }
+          col[5] = gsum(gm, a) / kk;
+        }
+      }
+      {                                                                  // UEF          :349-363
+        const int kk20 = min(20, k);
+        double u = 0.0, ws = 0.0;
+        for (int i = sl; i < kk20; i += LPL) {
+          const double w = s_uefw[i];
+          u += x[i] * w;
+          ws += w;
+        }
+        col[6] = gsum(gm, u) / gsum(gm, ws);
+      }
+      if (mean > 0) col[10] = snqc / kk;                                 // snqc         :417-438
+      {                                                                  // dense-qpp(-m) :444-453
+        const double range = mx - mn;
+        col[11] = col[12] = (k >= 2 && range > 0) ? log(1.0 + 1.0 / range) : 0.0;
+      }
+      // text-only proxies                                                :368-393
+      col[7] = log(1.0 + (double)n_unique) + log(1.0 + (double)max_len) * 0.5;
+      {
+        const double avg_len = n_terms > 0 ? (double)sum_len / (double)n_terms : 3.0;
+        const double diversity = n_terms > 0 ? (double)n_unique / (double)n_terms : __longlong_as_double(0x7ff8000000000000ll);
+        col[8] = log(1.0 + avg_len) * diversity;
+      }
+    }
+    // every lane of the group holds identical col[]: spread the stores over its lanes
+#pragma unroll
+    for (int c = 0; c < QF_QPP_COLS; ++c)
+      if (sl == (c & (LPL - 1))) out[c] = c < QF_QPP_BRIDGE_COLS ? col[c < QF_QPP_BRIDGE_COLS ? c : 0] : 0.0;
+    if (p.out_status && sl == LPL - 1) p.out_status[li] = status;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // column normalisation
 // ------------------------------------------------------------------------------------------------
 struct ColStat {
@@ -539,10 +722,12 @@ extern "C" int qf_qpp_stats(const void* scores, int score_type, const int32_t* l
       default: qpp_kernel<QF_SCORE_MICRO, true><<<nb, NT, 0, st>>>(p); break;
     }
   } else {
+    long long gb = (n_lists + WARPS * GPW - 1) / (WARPS * GPW);
+    if (gb > cap) gb = cap;
     switch (score_type) {
-      case QF_SCORE_F64: qpp_kernel<QF_SCORE_F64, false><<<nb, NT, 0, st>>>(p); break;
-      case QF_SCORE_F32: qpp_kernel<QF_SCORE_F32, false><<<nb, NT, 0, st>>>(p); break;
-      default: qpp_kernel<QF_SCORE_MICRO, false><<<nb, NT, 0, st>>>(p); break;
+      case QF_SCORE_F64: qpp_bridge_kernel<QF_SCORE_F64><<<(unsigned)gb, NT, 0, st>>>(p); break;
+      case QF_SCORE_F32: qpp_bridge_kernel<QF_SCORE_F32><<<(unsigned)gb, NT, 0, st>>>(p); break;
+      default: qpp_bridge_kernel<QF_SCORE_MICRO><<<(unsigned)gb, NT, 0, st>>>(p); break;
     }
   }
   qf::prof_mark(QF_PROF_QPP_STATS, 1, st);

@@ -86,7 +86,9 @@ def test_bridge_and_research_columns(score_type):
     # without permutations the research columns are zero and the bridge columns unchanged
     out2, _ = ops.qpp_stats(t(dev_sc), t(lens), t(feats), None, None)
     out2 = out2.cpu().numpy()
-    assert np.array_equal(out2[..., :13], out[..., :13]) and (out2[..., 13:] == 0).all()
+    # (the bridge-only call runs the 8-lanes-per-list kernel: same formulas, different summation grouping)
+    assert close(out2[..., :13], exp[..., :13]).all() and (out2[..., 13:] == 0).all()
+    assert np.allclose(out2[..., :13], out[..., :13], rtol=1e-11, atol=1e-13, equal_nan=True)
 
 
 def test_reference_smoke_vector_and_k1000():
