@@ -110,7 +110,8 @@ struct SLayout {
   static constexpr size_t off_order = a16(off_cnt + 2 * NB);   // u16 order[UCAP]: slots in bucket order
   static constexpr size_t off_bcache = a16(off_order + 2 * UCAP);   // u16 bucket id per slot
   static constexpr size_t off_bitmap = a16(off_bcache + 2 * H);     // first-seen bitmap + word prefix (out_pos)
-  static constexpr size_t off_coarse = a16(off_bitmap + 6 * BW);
+  static constexpr size_t off_queue = a16(off_bitmap + 6 * BW);     // u16 straggler queue, 128 entries per warp
+  static constexpr size_t off_coarse = a16(off_queue + 2 * 128 * (NT / 32));
   static constexpr size_t off_misc = a16(off_coarse + 4 * CB * 3);
   static constexpr size_t total = a16(off_misc + sizeof(SMisc));
   static_assert(NB % NT == 0 && CPT % 8 == 0 && NB < 65536, "bucket scan: CPT counters per thread, 8 per 16-byte load");
@@ -144,6 +145,7 @@ __global__ void __launch_bounds__(NT, MINB) fuse_stream_kernel(const FuseParams 
   u16* s_bcache = reinterpret_cast<u16*>(smem + L::off_bcache);
   u32* s_bitmap = reinterpret_cast<u32*>(smem + L::off_bitmap);
   u16* s_bpre = reinterpret_cast<u16*>(smem + L::off_bitmap + 4 * BW);
+  u16* s_queue = reinterpret_cast<u16*>(smem + L::off_queue) + 128 * (threadIdx.x >> 5);   // this warp's queue
   int* s_chist = reinterpret_cast<int*>(smem + L::off_coarse);
   float* s_ccum = reinterpret_cast<float*>(smem + L::off_coarse + 4 * CB);
   float* s_cw = reinterpret_cast<float*>(smem + L::off_coarse + 8 * CB);
@@ -321,8 +323,57 @@ __global__ void __launch_bounds__(NT, MINB) fuse_stream_kernel(const FuseParams 
             if (prev > c.rk[j]) bad_order = true;
           }
       }
+      // One probe step: classify the group with a select chain -- doc found (no atomic) / claim the first empty key
+      // with one CAS (a claim lost to another doc moves on to the next empty key of the same, possibly stale, view:
+      // stale views only ever show too many empty keys, and a CAS on a key that meanwhile holds this very doc
+      // returns it = found) / four foreign keys (-> false).  Probe order is group by group, keys 0..3; a doc always
+      // sits before the first empty key of its probe order, so this is exact.
+      auto probe_once = [&](u32 id, u32 gq, const uint4& k4, int& slot, bool& inserted) -> bool {
+        const int hit = hit4(k4, id);
+        u32 em = empty4(k4);
+        if (hit >= 0) {
+          slot = (int)(4 * gq) + hit;
+          return true;
+        }
+        while (em) {
+          const int e = __ffs((int)em) - 1;
+          const u32 o = atoms_cas(keys_sa + 16u * gq + 4u * (u32)e, EMPTY, id);
+          if (o == EMPTY || o == id) {
+            slot = (int)(4 * gq) + e;
+            inserted = (o == EMPTY);
+            return true;
+          }
+          em &= em - 1;
+        }
+        return false;
+      };
+      auto accumulate = [&](int slot, bool inserted, raw_t sc, int rk, int i) {
+        double v;
+        bool counts = true;
+        if (is_rrf) {
+          const double rank = grk ? (double)rk : (double)(i + 1);
+          v = __ddiv_rn(w, __dadd_rn(p.rrf_k, rank));
+        } else {
+          double s = raw_to_f64(sc);
+          if (minmax) s = __ddiv_rn(__dsub_rn(s, lmn), lden);
+          if (skip_zero && s == 0.0) counts = false;
+          v = __dmul_rn(w, s);                           // w == 1.0 when unweighted: exact
+        }
+        u32 bits = 1u << r;
+        if (skip_zero && counts) bits |= 1u << (8 + r);
+        if (inserted) {
+          ++ins;
+          const u32 seq = (u32)(s0 + i);
+          bits |= seq << 16;
+          if (want_pos) atomicOr(&s_bitmap[seq >> 5], 1u << (seq & 31u));   // first-seen bitmap (out_pos)
+        }
+        const u32 om = atoms_or(meta_sa + 4u * (u32)slot, bits);
+        const double prev = inserted ? 0.0 : s_acc[slot];     // the reference starts from 0.0 (src/fusion.py:275)
+        if (om & (1u << r)) defer = true;                     // the doc id occurs twice inside list r
+        else s_acc[slot] = __dadd_rn(prev, v);
+      };
       // Home group of posting j+1 is fetched while posting j is resolved (a longer look-ahead only makes the
-      // fetched keys staler and the claims below fail more often).
+      // fetched keys staler and the claims fail more often).
       auto fetch = [&](int j) {
         if (valid[j]) {
           if ((u32)c.id[j] == EMPTY) {
@@ -334,80 +385,58 @@ __global__ void __launch_bounds__(NT, MINB) fuse_stream_kernel(const FuseParams 
           }
         }
       };
+      // First pass: ONE probe step per posting, all lanes together.  The ~10 % of postings whose home group holds four
+      // foreign keys are not chased here (every extra loop iteration would run for the whole warp with 2-3 live
+      // lanes): they go to this warp's queue and are resolved below on densely packed lanes.
+      int qn = 0;
       fetch(0);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         if (j + 1 < 4) fetch(j + 1);
-        // Probe loop, uniform over the warp (lanes that are done idle, nobody runs a private code path).  Probe
-        // order is group by group, keys 0..3; a doc always sits before the first empty key of its probe order, so
-        // "match, else claim the first empty key with one CAS, else next group" is exact.  A claim lost to another
-        // doc moves on to the next empty key of the same (possibly stale) view -- stale views only ever show too
-        // many empty keys, and a CAS on a key that meanwhile holds this very doc returns it (= found).
         int slot = -1;
         bool inserted = false;
-        {
-          const u32 id = (u32)c.id[j];
-          u32 gq = g[j];
-          uint4 k4 = kk[j & 1];
-          int probes = 0;
-          bool active = valid[j];
-          while (__any_sync(0xffffffffu, active)) {
-            if (active) {
-              const int hit = hit4(k4, id);
-              u32 em = empty4(k4);
-              if (hit >= 0) {
-                slot = (int)(4 * gq) + hit;
-                active = false;
-              } else {
-                while (em) {
-                  const int e = __ffs((int)em) - 1;
-                  const u32 o = atoms_cas(keys_sa + 16u * gq + 4u * (u32)e, EMPTY, id);
-                  if (o == EMPTY || o == id) {
-                    slot = (int)(4 * gq) + e;
-                    inserted = (o == EMPTY);
-                    active = false;
-                    break;
-                  }
-                  em &= em - 1;
-                }
-                if (active) {                                  // group full of foreign keys: next group
-                  if (++probes > MAXPROBE) {
-                    defer = true;
-                    active = false;
-                  } else {
-                    gq = gq + 1 == (u32)G ? 0u : gq + 1;
-                    k4 = lds128_volatile(keys_sa + 16u * gq);
-                  }
-                }
-              }
+        bool resolved = false;
+        if (valid[j]) resolved = probe_once((u32)c.id[j], g[j], kk[j & 1], slot, inserted);
+        const bool strag = valid[j] && !resolved;
+        const unsigned bal = __ballot_sync(0xffffffffu, strag);
+        if (strag) s_queue[qn + __popc(bal & ((1u << lane) - 1u))] = (u16)idx[j];
+        qn += __popc(bal);
+        if (resolved) accumulate(slot, inserted, need_scores ? c.sc[j] : raw_t(0), grk ? c.rk[j] : 0, idx[j]);
+        __syncwarp();
+      }
+      // Drain: up to 32 stragglers at a time, full probe loop (uniform over the warp) from the home group.
+      while (qn > 0) {
+        const int take = qn < 32 ? qn : 32;
+        qn -= take;
+        const bool mine = lane < take;
+        int i = 0, rk = 0, slot = -1;
+        u32 id = 0, gq = 0;
+        raw_t sc = raw_t(0);
+        uint4 k4 = make_uint4(0u, 0u, 0u, 0u);
+        if (mine) {
+          i = s_queue[qn + lane];
+          id = (u32)__ldg(gid + (size_t)r * K + i);
+          if (need_scores) sc = __ldg(gsc + (size_t)r * K + i);
+          if (grk) rk = __ldg(grk + (size_t)r * K + i);
+          gq = __umulhi(id * 2654435761u, (u32)G);
+          k4 = lds128_volatile(keys_sa + 16u * gq);
+        }
+        bool inserted = false, active = mine;
+        int probes = 0;
+        while (__any_sync(0xffffffffu, active)) {
+          if (active) {
+            if (probe_once(id, gq, k4, slot, inserted)) {
+              active = false;
+            } else if (++probes > MAXPROBE) {
+              defer = true;
+              active = false;
+            } else {
+              gq = gq + 1 == (u32)G ? 0u : gq + 1;
+              k4 = lds128_volatile(keys_sa + 16u * gq);
             }
           }
         }
-        if (slot >= 0) {
-          double v;
-          bool counts = true;
-          if (is_rrf) {
-            const double rank = grk ? (double)c.rk[j] : (double)(idx[j] + 1);
-            v = __ddiv_rn(w, __dadd_rn(p.rrf_k, rank));
-          } else {
-            double s = raw_to_f64(c.sc[j]);
-            if (minmax) s = __ddiv_rn(__dsub_rn(s, lmn), lden);
-            if (skip_zero && s == 0.0) counts = false;
-            v = __dmul_rn(w, s);                           // w == 1.0 when unweighted: exact
-          }
-          u32 bits = 1u << r;
-          if (skip_zero && counts) bits |= 1u << (8 + r);
-          if (inserted) {
-            ++ins;
-            const u32 seq = (u32)(s0 + idx[j]);
-            bits |= seq << 16;
-            if (want_pos) atomicOr(&s_bitmap[seq >> 5], 1u << (seq & 31u));   // first-seen bitmap (out_pos)
-          }
-          const u32 om = atoms_or(meta_sa + 4u * (u32)slot, bits);
-          const double prev = inserted ? 0.0 : s_acc[slot];     // the reference starts from 0.0 (src/fusion.py:275)
-          if (om & (1u << r)) defer = true;                     // the doc id occurs twice inside list r
-          else s_acc[slot] = __dadd_rn(prev, v);
-        }
+        if (slot >= 0) accumulate(slot, inserted, sc, rk, i);
         __syncwarp();
       }
     };
