@@ -168,6 +168,14 @@ def fuse_traffic():
     return None
 
 
+def dense_traffic():
+    """DRAM bytes of the dense main pass (NQ shape, one GPU) from the committed ncu --set full capture."""
+    p = os.path.join(ROOT, "profiles", "dense_traffic.json")
+    if os.path.isfile(p):
+        return json.load(open(p)).get("dram_bytes_per_launch")
+    return None
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(p):
@@ -194,12 +202,14 @@ def synth_dense(Q, N, D, seed, device):
     return q32, corpus
 
 
-def dense_leg(args, dev, world, rank):
-    """BGE-shaped flat inner-product top-1000 (BASELINE configs[2]); corpus row-sharded when world > 1."""
+def dense_leg(args, dev, world, rank, Q=Q_NQ, n_docs=None, label="BASELINE configs[2]", max_steps=10):
+    """BGE-shaped flat inner-product top-1000 (BASELINE configs[2] by default; configs[3] = HotpotQA shape with
+    Q=7405, n_docs=5,233,329); corpus row-sharded when world > 1."""
     import torch
     import torch.distributed as dist
     from qppfusion import _native as N_, ops
-    Q, D, k = Q_NQ, D_DENSE, K_DENSE
+    N_DENSE = n_docs or globals()["N_DENSE"]
+    D, k = D_DENSE, K_DENSE
     n_local = (N_DENSE + world - 1) // world
     lo = rank * n_local
     n_local = max(0, min(n_local, N_DENSE - lo))
@@ -208,7 +218,7 @@ def dense_leg(args, dev, world, rank):
         dist.broadcast(q32, src=0)
     qb = q32.to(torch.bfloat16)
     stream = torch.cuda.current_stream(dev)
-    steps = max(3, min(args.steps, 10))
+    steps = max(3, min(args.steps, max_steps))
 
     from qppfusion import distributed as qd
 
@@ -286,13 +296,14 @@ def dense_leg(args, dev, world, rank):
     ach = flops_main / (main_ms * 1e-3) / 1e12
     return {"metric": "BGE top-1000 QPS", "value": Q / (ms * 1e-3), "unit": "queries/s", "ms_per_step": ms,
             "scaling": "strong" if world > 1 else "n/a",
-            "config": {"workload": "BGE-base-shaped flat IP top-1000 (BASELINE configs[2])", "queries": Q,
+            "config": {"workload": f"BGE-base-shaped flat IP top-1000 ({label})", "queries": Q,
                        "docs": N_DENSE, "docs_per_gpu": n_local, "dim": D, "k": k, "dtype": "bf16 in, fp32 accumulate",
                        "sharding": f"corpus rows x{world}" + (", all_to_all + qf_topk_merge(Q/G) + all_gather" if world > 1 else "")},
             "kernel_ms": phases,
             "roofline": {"kernel": "dense_kernel (tcgen05 main pass)", "bound": "tensor", "achieved": ach, "peak": tf_peak,
                          "unit": "TFLOP/s", "frac": ach / tf_peak, "peak_source": which,
-                         "algorithmic_flops": flops_main, "traffic": None},
+                         "algorithmic_flops": flops_main,
+                         "traffic": dense_traffic() if (world == 1 and n_docs is None) else None},
             "whole_call_tflops": 2.0 * Q * N_DENSE * D / (ms * 1e-3) / 1e12,
             "e2e": {"value": Q / (e2e_ms * 1e-3), "unit": "queries/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": Q * D * 4, "d2h_bytes_per_step": Q * k * 8},
@@ -363,8 +374,9 @@ def run_ours(args):
         graphs[i % NSETS].replay()
     t1.record(stream)
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
     ms_total = t0.elapsed_time(t1)
+    # (the clock sampler keeps running through the per-kernel loop below: same kernels, same load, and the K-step timed
+    # region alone lasts only ~10 ms)
 
     # ---- per-kernel durations: the same K steps issued kernel by kernel with CUDA events between them (events cannot
     # be read back from inside a graph replay); the fusion kernel's average is the roofline denominator
@@ -381,6 +393,9 @@ def run_ours(args):
     fixup_ms = N_.profile_read(N_.PROF_FUSE_GENERAL)          # general kernel's fix-up pass over deferred queries
     qpp_ms = N_.profile_read(N_.PROF_QPP_STATS)
     N_.profile_enable(False)
+    clocks = sampler.stop() if rank == 0 else None
+    if clocks is not None:
+        clocks["window"] = "timed region + the per-kernel loop that follows it"
     fuse_op_ms = sum(e[2].elapsed_time(e[3]) for e in evs) / args.steps
     norm_ms = sum(e[1].elapsed_time(e[2]) for e in evs) / args.steps
     deferred = int((graphs[0].replay().lens < 0).sum().item())
@@ -458,6 +473,10 @@ def run_ours(args):
     del sets, h_in, h_out
     torch.cuda.empty_cache()
     dense = None if args.no_dense else dense_leg(args, dev, world, rank)
+    torch.cuda.empty_cache()
+    # HotpotQA-shaped dense search (BASELINE configs[3]: the corpus-sharded multi-GPU config), fewer steps
+    dense_c4 = None if args.no_dense else dense_leg(args, dev, world, rank, Q=7405, n_docs=5_233_329,
+                                                    label="BASELINE configs[3], HotpotQA shape", max_steps=4)
 
     times = torch.tensor([ms_total, e2e_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -493,9 +512,10 @@ def run_ours(args):
                             "D2H; consecutive steps overlap on 3 streams"},
             # per step: qpp 1 + colnorm 3 + select 1 + fuse 2 (streaming + fix-up) = 7; CSR compaction adds 4
             "gpu_launches": (11 * (args.steps + args.warmup + 1) + 7 * (args.steps + 4) + 11 * (e2e_steps + 3)
-                             + (dense["gpu_launches"] if dense else 0)),
+                             + (dense["gpu_launches"] if dense else 0) + (dense_c4["gpu_launches"] if dense_c4 else 0)),
             "clocks": clocks,
             "dense": dense,
+            "dense_hotpotqa": dense_c4,
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(seconds=10.0)
