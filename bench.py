@@ -325,7 +325,8 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
 
     Q, R, K = Q_NQ, R_NQ, K_NQ
-    NSETS = 3     # rotating input sets: 138 MB each, so no step finds its inputs in the 126 MB L2
+    NSETS = 4     # rotating input sets: 138 MB each, so no step finds its inputs in the 126 MB L2
+    INFLIGHT = 2  # steps in flight (one stream each); step i and step i + NSETS share a graph AND a stream
     sets = [synth_device(Q, R, K, 20250101 + 2 + 17 * rank + 1000 * i, dev) for i in range(NSETS)]
     stream = torch.cuda.current_stream(dev)
     from qppfusion.pipeline import FusionStepGraph
@@ -350,17 +351,33 @@ def run_ours(args):
 
     # The product path replays the step as ONE CUDA graph per input set (qppfusion.pipeline.FusionStepGraph): the
     # kernels are 10-400 us long and issuing seven of them from Python per step leaves the GPU waiting for the host.
-    graphs = [FusionStepGraph(*sets[i], qpp_index=5, top_k=100, k_cut=50, colnorm="minmax", round6=True,
-                              method=0, norm=0, rrf_k=60.0, flags=0, want_counts=False, want_pos=False, compact=True)
-              for i in range(NSETS)]
-    for i in range(args.warmup):
-        out = graphs[i % NSETS].replay()
+    def make_graph(i, compact):
+        return FusionStepGraph(*sets[i], qpp_index=5, top_k=100, k_cut=50, colnorm="minmax", round6=True, method=0,
+                               norm=0, rrf_k=60.0, flags=0, want_counts=False, want_pos=False, compact=compact)
+
+    graphs = [make_graph(i, False) for i in range(NSETS)]
+    run_streams = [torch.cuda.Stream(dev) for _ in range(INFLIGHT)]
+
+    def run_steps(n):
+        """n consecutive steps, INFLIGHT of them in flight: queries of different steps are independent, so step i+1's
+        short QPP / normalisation kernels and the tail of step i's fusion kernel share the SMs."""
+        for s_ in run_streams:
+            s_.wait_stream(stream)
+        out_ = None
+        for i in range(n):
+            with torch.cuda.stream(run_streams[i % INFLIGHT]):
+                out_ = graphs[i % NSETS].replay()
+        for s_ in run_streams:
+            stream.wait_stream(s_)
+        return out_
+
+    out = run_steps(max(args.warmup, NSETS))
     barrier()
-    union_total = int(out.lens.sum().item())
-    assert int(out.status.max().item()) == 0
+    union_total = int(graphs[0].out.lens.sum().item())
+    assert all(int(g.out.status.max().item()) == 0 for g in graphs)
     eager = step(0)
     barrier()
-    assert torch.equal(eager.lens, graphs[0].replay().lens)
+    assert torch.equal(eager.lens, graphs[0].out.lens) and torch.equal(eager.scores[0, :16], graphs[0].out.scores[0, :16])
     barrier()
 
     # ---- timed region: K steps (graph replays), device-timed, max over ranks
@@ -370,8 +387,7 @@ def run_ours(args):
         sampler.start()
     barrier()
     t0.record(stream)
-    for i in range(args.steps):
-        graphs[i % NSETS].replay()
+    run_steps(args.steps)
     t1.record(stream)
     barrier()
     ms_total = t0.elapsed_time(t1)
@@ -398,13 +414,16 @@ def run_ours(args):
         clocks["window"] = "timed region + the per-kernel loop that follows it"
     fuse_op_ms = sum(e[2].elapsed_time(e[3]) for e in evs) / args.steps
     norm_ms = sum(e[1].elapsed_time(e[2]) for e in evs) / args.steps
-    deferred = int((graphs[0].replay().lens < 0).sum().item())
-    assert deferred == 0
+    assert int((graphs[0].out.lens < 0).sum().item()) == 0       # nothing left deferred
 
     # ---- end to end: pinned host buffers -> H2D into the graph's input tensors -> graph replay (step + CSR
     # compaction) -> D2H of the fused run.  Three streams (H2D / compute / D2H) so step i+1's upload and step i-1's
     # download overlap step i's kernels; every step's copies are inside the timed region.
-    h_sets = [[x.cpu().pin_memory() for x in st_] for st_ in sets]
+    del graphs
+    torch.cuda.empty_cache()
+    graphs = [make_graph(i, True) for i in range(3)]       # e2e: step + CSR compaction in one graph
+    NSETS = 3
+    h_sets = [[x.cpu().pin_memory() for x in st_] for st_ in sets[:NSETS]]
     n_post = Q * R * K
     NB = 2
     h_off = [torch.empty((Q + 1,), dtype=torch.int64).pin_memory() for _ in range(NB)]
@@ -497,7 +516,8 @@ def run_ours(args):
                                    "one CUDA-graph replay of the 7 kernels",
                        "queries_per_gpu": Q, "retrievers": R, "depth": K, "score_format": "int32 micro-units",
                        "union_ratio": union_total / n_post, "sharding": f"query-sharded x{world}, no collective",
-                       "l2": "3 rotating input sets of 138 MB (> 126 MB L2)"},
+                       "l2": "4 rotating input sets of 138 MB (> 126 MB L2)",
+                       "steps_in_flight": INFLIGHT},
             "kernel_ms": {"qpp_stats": qpp_ms, "colnorm+select": norm_ms, "fuse_stream": fuse_ms,
                           "fuse_fixup": fixup_ms, "fuse_op_eager": fuse_op_ms,
                           "note": "per-kernel times from a second K-step loop issued kernel by kernel (in-library "
@@ -511,7 +531,7 @@ def run_ours(args):
                     "note": "pinned host buffers -> H2D into the graph's inputs -> graph replay (step + CSR compaction) -> "
                             "D2H; consecutive steps overlap on 3 streams"},
             # per step: qpp 1 + colnorm 3 + select 1 + fuse 2 (streaming + fix-up) = 7; CSR compaction adds 4
-            "gpu_launches": (11 * (args.steps + args.warmup + 1) + 7 * (args.steps + 4) + 11 * (e2e_steps + 3)
+            "gpu_launches": (7 * (args.steps + max(args.warmup, 4)) + 7 * (args.steps + 4) + 11 * (e2e_steps + 3 + 6)
                              + (dense["gpu_launches"] if dense else 0) + (dense_c4["gpu_launches"] if dense_c4 else 0)),
             "clocks": clocks,
             "dense": dense,
