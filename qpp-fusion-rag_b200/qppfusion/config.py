@@ -61,7 +61,10 @@ config = _Config(
     ),
     processing=SimpleNamespace(
         retrieval=SimpleNamespace(top_k=100, first_stage_k=100),      # :152-154
-        batch_sizes=SimpleNamespace(bge_encoding=64, bge_mini=100),   # :141,145
+        batch_sizes=SimpleNamespace(bge_encoding=64, bge_mini=100,    # :141,145
+                                    tct_encoding=64, tct_mini=100),   # :140,146
     ),
-    models=SimpleNamespace(bge=SimpleNamespace(name="BAAI/bge-base-en-v1.5", embedding_dim=768)),   # :102-104
+    models=SimpleNamespace(bge=SimpleNamespace(name="BAAI/bge-base-en-v1.5", embedding_dim=768),    # :102-104
+                           tct_colbert=SimpleNamespace(name="castorini/tct_colbert-v2-hnp-msmarco",  # :106-108
+                                                       embedding_dim=768)),
 )

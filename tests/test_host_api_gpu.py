@@ -174,3 +174,40 @@ def test_bge_retriever_search_calls(tmp_path):
     assert len(res2) == 3 and res2["q1"].results[0][0] == res["q1"].results[0][0]
     one = ret.retrieve("alpha", "q1", top_k=5)
     assert [d for d, _, _ in one.results] == [d for d, _, _ in res["q1"].results]
+
+
+def test_tct_colbert_retriever_uses_the_same_flat_ip_search(tmp_path):
+    """TCT-ColBERT's faiss.IndexFlatIP search (reference src/retrievers/tct_colbert.py:139-151,163,194) through the
+    dense kernel: embedding cache files in the reference's format, result tuples, checkpoint."""
+    from qppfusion.retrievers import TCTColBERTRetriever
+    rng = np.random.default_rng(12)
+    N, D = 5000, 768
+    c = rng.standard_normal((N, D)).astype(np.float32)
+    c /= np.linalg.norm(c, axis=1, keepdims=True)
+    corpus = {f"d{i}": {"text": "x", "title": ""} for i in range(N)}
+    np.save(str(tmp_path / f"tct_colbert_{N}_fp16.npy"), c.astype(np.float16))
+    np.save(str(tmp_path / f"tct_colbert_{N}_ids.npy"), np.array(list(corpus.keys()), dtype=object))
+
+    def encoder(texts):
+        out = []
+        for t in texts:
+            r = np.random.default_rng(abs(hash(t)) % (2 ** 32)).standard_normal(D).astype(np.float32)
+            out.append(r / np.linalg.norm(r))
+        return np.stack(out)
+
+    ret = TCTColBERTRetriever(corpus, cache_dir=str(tmp_path), encoder=encoder)
+    assert ret.name == "TCT-ColBERT"
+    q = encoder(["alpha", "beta"])
+    res = ret._process_mini_batch([("q1", "alpha"), ("q2", "beta")], 50)
+    c16 = torch.from_numpy(c.astype(np.float16).astype(np.float32)).to(torch.bfloat16).float().numpy()
+    qb = torch.from_numpy(q).to(torch.bfloat16).float().numpy()
+    oi, os_ = do.flat_ip_topk(qb, c16, 50)
+    got_ids = [[int(d[1:]) for d, _, _ in r.results] for r in res]
+    assert np.mean(np.array(got_ids) == oi) > 0.98
+    assert np.abs(np.array([[s for _, s, _ in r.results] for r in res]) - os_).max() <= 2e-5
+    assert [rk for _, _, rk in res[0].results] == list(range(1, 51))
+    ck = tmp_path / "TCT.checkpoint.jsonl"
+    out = ret.retrieve_batch({"q1": "alpha", "q2": "beta"}, top_k=5, checkpoint_path=str(ck))
+    assert [d for d, _, _ in out["q1"].results] == [d for d, _, _ in res[0].results[:5]]
+    with pytest.raises(FileNotFoundError):
+        TCTColBERTRetriever(corpus, cache_dir=str(tmp_path / "missing"), encoder=encoder)
