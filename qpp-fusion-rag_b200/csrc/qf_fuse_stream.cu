@@ -69,11 +69,16 @@ struct SMisc {
   int status;
 };
 
-// Position of `id` among the 4 keys of a group (0..3) or -1: one select chain, no branches.
-__device__ __forceinline__ int hit4(const uint4& k, u32 id) {
+// Classify one group of 4 keys with a single select chain: 0..3 = position of `id`, 4..7 = 4 + position of the
+// first empty key (no match), -1 = four foreign keys.
+__device__ __forceinline__ int probe4(const uint4& k, u32 id) {
   int pos;
   asm("{\n\t.reg .pred p;\n\t"
       "mov.s32 %0, -1;\n\t"
+      "setp.eq.u32 p, %4, 0xffffffff;\n\tselp.s32 %0, 7, %0, p;\n\t"
+      "setp.eq.u32 p, %3, 0xffffffff;\n\tselp.s32 %0, 6, %0, p;\n\t"
+      "setp.eq.u32 p, %2, 0xffffffff;\n\tselp.s32 %0, 5, %0, p;\n\t"
+      "setp.eq.u32 p, %1, 0xffffffff;\n\tselp.s32 %0, 4, %0, p;\n\t"
       "setp.eq.u32 p, %4, %5;\n\tselp.s32 %0, 3, %0, p;\n\t"
       "setp.eq.u32 p, %3, %5;\n\tselp.s32 %0, 2, %0, p;\n\t"
       "setp.eq.u32 p, %2, %5;\n\tselp.s32 %0, 1, %0, p;\n\t"
@@ -82,19 +87,6 @@ __device__ __forceinline__ int hit4(const uint4& k, u32 id) {
       : "=r"(pos)
       : "r"(k.x), "r"(k.y), "r"(k.z), "r"(k.w), "r"(id));
   return pos;
-}
-// Bit i set when key i of the group is still empty.
-__device__ __forceinline__ u32 empty4(const uint4& k) {
-  u32 a, b, c, d;
-  asm("{\n\t.reg .pred p;\n\t"
-      "setp.eq.u32 p, %4, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t"
-      "setp.eq.u32 p, %5, 0xffffffff;\n\tselp.u32 %1, 2, 0, p;\n\t"
-      "setp.eq.u32 p, %6, 0xffffffff;\n\tselp.u32 %2, 4, 0, p;\n\t"
-      "setp.eq.u32 p, %7, 0xffffffff;\n\tselp.u32 %3, 8, 0, p;\n\t"
-      "}"
-      : "=r"(a), "=r"(b), "=r"(c), "=r"(d)
-      : "r"(k.x), "r"(k.y), "r"(k.z), "r"(k.w));
-  return a | b | c | d;
 }
 
 template <int G, int UCAP, int NB, int NMAX, int NT>
@@ -323,29 +315,23 @@ __global__ void __launch_bounds__(NT, MINB) fuse_stream_kernel(const FuseParams 
             if (prev > c.rk[j]) bad_order = true;
           }
       }
-      // One probe step: classify the group with a select chain -- doc found (no atomic) / claim the first empty key
-      // with one CAS (a claim lost to another doc moves on to the next empty key of the same, possibly stale, view:
-      // stale views only ever show too many empty keys, and a CAS on a key that meanwhile holds this very doc
-      // returns it = found) / four foreign keys (-> false).  Probe order is group by group, keys 0..3; a doc always
-      // sits before the first empty key of its probe order, so this is exact.
-      auto probe_once = [&](u32 id, u32 gq, const uint4& k4, int& slot, bool& inserted) -> bool {
-        const int hit = hit4(k4, id);
-        u32 em = empty4(k4);
-        if (hit >= 0) {
-          slot = (int)(4 * gq) + hit;
-          return true;
+      // One probe step: classify the group with one select chain -- doc found (no atomic) / first empty key, claimed
+      // with one CAS (a CAS on a key that meanwhile holds this very doc returns it = found) / four foreign keys or a
+      // claim lost to another doc (-> false: look at the group again, or move on, later).  Probe order is group by
+      // group, keys 0..3; a doc always sits before the first empty key of its probe order (views can only be stale
+      // towards "too empty", and then the CAS fails), so this is exact.
+      auto probe_once = [&](u32 id, u32 gq, const uint4& k4, int& slot, bool& inserted, bool& full) -> bool {
+        const int pos = probe4(k4, id);
+        full = pos < 0;
+        if (pos < 0) return false;
+        const int cand = (int)(4 * gq) + (pos & 3);
+        if (pos >= 4) {
+          const u32 o = atoms_cas(keys_sa + 4u * (u32)cand, EMPTY, id);
+          inserted = (o == EMPTY);
+          if (!inserted && o != id) return false;
         }
-        while (em) {
-          const int e = __ffs((int)em) - 1;
-          const u32 o = atoms_cas(keys_sa + 16u * gq + 4u * (u32)e, EMPTY, id);
-          if (o == EMPTY || o == id) {
-            slot = (int)(4 * gq) + e;
-            inserted = (o == EMPTY);
-            return true;
-          }
-          em &= em - 1;
-        }
-        return false;
+        slot = cand;
+        return true;
       };
       auto accumulate = [&](int slot, bool inserted, raw_t sc, int rk, int i) {
         double v;
@@ -395,8 +381,8 @@ __global__ void __launch_bounds__(NT, MINB) fuse_stream_kernel(const FuseParams 
         if (j + 1 < 4) fetch(j + 1);
         int slot = -1;
         bool inserted = false;
-        bool resolved = false;
-        if (valid[j]) resolved = probe_once((u32)c.id[j], g[j], kk[j & 1], slot, inserted);
+        bool resolved = false, full;
+        if (valid[j]) resolved = probe_once((u32)c.id[j], g[j], kk[j & 1], slot, inserted, full);
         const bool strag = valid[j] && !resolved;
         const unsigned bal = __ballot_sync(0xffffffffu, strag);
         if (strag) s_queue[qn + __popc(bal & ((1u << lane) - 1u))] = (u16)idx[j];
@@ -425,13 +411,17 @@ __global__ void __launch_bounds__(NT, MINB) fuse_stream_kernel(const FuseParams 
         int probes = 0;
         while (__any_sync(0xffffffffu, active)) {
           if (active) {
-            if (probe_once(id, gq, k4, slot, inserted)) {
-              active = false;
-            } else if (++probes > MAXPROBE) {
-              defer = true;
+            bool full;
+            if (probe_once(id, gq, k4, slot, inserted, full)) {
               active = false;
             } else {
-              gq = gq + 1 == (u32)G ? 0u : gq + 1;
+              if (full) {                                       // four foreign keys: next group
+                if (++probes > MAXPROBE) {
+                  defer = true;
+                  active = false;
+                }
+                gq = gq + 1 == (u32)G ? 0u : gq + 1;
+              }                                                 // else: lost the key to another doc, same group again
               k4 = lds128_volatile(keys_sa + 16u * gq);
             }
           }
@@ -672,6 +662,7 @@ __global__ void __launch_bounds__(NT, MINB) fuse_stream_kernel(const FuseParams 
     {
       int32_t* oid = p.out_ids + (size_t)q * out_stride;
       double* osc = p.out_scores + (size_t)q * out_stride;
+      asm volatile("" : "+l"(oid), "+l"(osc));           // keep the row pointers in registers (no per-element rebuild)
       for (int j = tid; j < n_u; j += NT) {
         const int slot = s_order[j];
         const double fs = s_acc[slot];
