@@ -539,7 +539,7 @@ def run_ours(args):
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(seconds=10.0)
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -632,10 +632,16 @@ def run_reference(args):
                                        "QPPBridge.java + src/fusion.py weighted_combsum + write_runfile ranking "
                                        "(the reference's engines -- JVM, ranx, faiss -- are not installable offline)"},
             "e2e": {"value": value, "unit": "fused queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
 
 
 def main():
+    # stdout carries exactly ONE JSON line: everything else written to fd 1 while the benchmark runs (NCCL prints its
+    # version banner there from C) is sent to stderr; the line itself goes to the saved descriptor.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w")
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
