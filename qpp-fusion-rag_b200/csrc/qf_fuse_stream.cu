@@ -724,7 +724,7 @@ int dispatch_stream(const FuseParams& p, cudaStream_t stream) {
     return e ? atoi(e) : 0;
   }();
   if (variant == 1) return launch_stream<1024, 3328, 3072, 5120, 384, 2, ST, MODE>(p, stream);
-  return launch_stream<768, 2560, 4096, 5120, 256, 3, ST, MODE>(p, stream);
+  return launch_stream<768, 2816, 4096, 5120, 256, 3, ST, MODE>(p, stream);
 }
 
 template <int ST>

@@ -78,8 +78,9 @@ def test_weighted_nq_shape_k1000(method):
 
 
 def test_full_union_and_full_overlap_k1000():
-    # pool == k: every list holds the same 1000 docs (union 1000); pool = 5k: almost disjoint (union ~5000)
-    for pool in (1000, 5000):
+    # pool == k: every list holds the same 1000 docs (union 1000); pool = 3200: union ~2700, the top of the streaming
+    # kernel's envelope (table ~90 % full); pool = 4000 / 5000: union ~3050 / ~3400, deferred to the general kernel
+    for pool in (1000, 3200, 4000, 5000):
         lists = synth_lists(5, n_q=4, n_r=5, k=1000, pool=pool)
         w = np.round(np.random.default_rng(6).random((4, 5)), 6)
         out = run_gpu(lists, "sum", w, score_type="f64", k=1000)
