@@ -87,6 +87,9 @@ QF_API int qf_profile_read(int phase, float* ms);
                                       /* and duplicate-free (the packer guarantees it); violations    */
                                       /* are reported in out_status, never silently repaired          */
 #define QF_FLAG_UNRANKED_OUTPUT   4u  /* skip the final ranking: outputs stay in first-seen order     */
+#define QF_FLAG_LARGE_UNION       8u  /* performance hint, results unchanged: most queries merge to   */
+                                      /* more than ~45 % of R*K distinct docs (little overlap between  */
+                                      /* the runs) -> use the larger shared-memory table configuration */
 
 /* per-query status bits written to out_status[Q] */
 #define QF_QSTAT_DUPLICATES   1   /* a doc id occurs twice inside one list (handled exactly; info)    */

@@ -718,12 +718,16 @@ template <int ST, int MODE>
 int dispatch_stream(const FuseParams& p, cudaStream_t stream) {
   const long long n_max = (long long)p.R * p.K;
   if (n_max <= 1024) return launch_stream<384, 1024, 1024, 1024, 128, 5, ST, MODE>(p, stream);
-  // QF_STREAM_VARIANT (debug/tuning hook, read once): 0 = 3 CTAs x 256 threads per SM (default), 1 = 2 x 384
-  static const int variant = [] {
+  // Two table sizes.  Default: 3072 slots, 3 CTAs x 256 threads per SM -- fastest while a query's union stays below
+  // ~2300 docs (table <= 75 % full), degrading quickly above.  QF_FLAG_LARGE_UNION: 5120 slots, 2 CTAs x 384 threads
+  // -- ~10 % slower on small unions, 1.7-2.4x faster from ~2700 docs up, and nothing is deferred for size up to 4352.
+  // QF_STREAM_VARIANT=0/1 (debug/tuning hook, read once) overrides the flag.
+  static const int forced = [] {
     const char* e = getenv("QF_STREAM_VARIANT");
-    return e ? atoi(e) : 0;
+    return e ? atoi(e) : -1;
   }();
-  if (variant == 1) return launch_stream<1024, 3328, 3072, 5120, 384, 2, ST, MODE>(p, stream);
+  const bool large = forced >= 0 ? forced == 1 : (p.flags & QF_FLAG_LARGE_UNION) != 0;
+  if (large) return launch_stream<1280, 4352, 3072, 5120, 384, 2, ST, MODE>(p, stream);
   return launch_stream<768, 2816, 4096, 5120, 256, 3, ST, MODE>(p, stream);
 }
 

@@ -119,14 +119,32 @@ def _weights_matrix(packed: PackedRuns, qpp_data, qpp_index: int) -> np.ndarray:
     return w
 
 
+# Table-size hint for qf_fuse (results never depend on it): the mean union ratio seen by the previous call with the same
+# [R, K] shape decides whether the next one asks for the larger-table configuration (N.FLAG_LARGE_UNION).
+_UNION_RATIO: Dict[tuple, float] = {}
+LARGE_UNION_RATIO = 0.46
+
+
+def union_hint_flags(shape_key: tuple) -> int:
+    return N.FLAG_LARGE_UNION if _UNION_RATIO.get(shape_key, 0.0) > LARGE_UNION_RATIO else 0
+
+
+def remember_union(shape_key: tuple, out_lens: torch.Tensor) -> None:
+    r, k = shape_key
+    if out_lens.numel():
+        _UNION_RATIO[shape_key] = float(out_lens.clamp(min=0).float().mean().item()) / float(max(1, r * k))
+
+
 def fuse_packed(packed: PackedRuns, method: int, weights: Optional[np.ndarray] = None, norm: int = N.NORM_NONE,
                 rrf_k: float = 60.0, flags: int = 0, want_counts: bool = False, want_pos: bool = False) -> ops.FuseOut:
     """Array-level entry point: PackedRuns -> kernel outputs on the device (no Python objects built)."""
     dev = _device()
     t = lambda a: None if a is None else torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    shape_key = tuple(packed.doc_ids.shape[1:])
     out = ops.fuse(t(packed.doc_ids), t(packed.scores), t(packed.lens), t(weights), t(packed.ranks), method, norm,
-                   rrf_k, flags, want_counts, want_pos)
+                   rrf_k, flags | union_hint_flags(shape_key), want_counts, want_pos)
     status = out.status.cpu().numpy()
+    remember_union(shape_key, out.lens)
     if (status & N.QSTAT_BAD_LEN).any():
         raise ValueError("qf_fuse: invalid list length")
     if (status & N.QSTAT_UNSORTED).any():

@@ -35,9 +35,19 @@ class FusionStepGraph:
         side.wait_stream(cur)
         with torch.cuda.stream(side):          # warm-up outside capture: one-time kernel attribute setup, allocator
             for _ in range(max(1, warmup)):
-                self._body()
+                warm = self._body()
         cur.wait_stream(side)
         torch.cuda.synchronize(self.dev)
+        # table-size hint from the warm-up batch (a performance choice only; see N.FLAG_LARGE_UNION)
+        r, k = doc_ids.shape[1], doc_ids.shape[2]
+        ratio = float(warm[2].lens.clamp(min=0).float().mean().item()) / float(max(1, r * k))
+        if ratio > 0.46 and not (self._cfg["flags"] & N.FLAG_LARGE_UNION):
+            self._cfg["flags"] |= N.FLAG_LARGE_UNION
+            with torch.cuda.stream(side):
+                self._body()                   # configure that kernel variant outside capture too
+            cur.wait_stream(side)
+            torch.cuda.synchronize(self.dev)
+        del warm
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.qpp, self.weights, self.out, self.csr = self._body()

@@ -16,11 +16,12 @@ METHODS = {"sum": 0, "mnz": 1, "rrf": 2}
 EXTRA_FLAGS = [0]
 
 
-@pytest.fixture(autouse=True, params=["stream", "general"])
+@pytest.fixture(autouse=True, params=["stream", "stream-large", "general"])
 def fuse_kernel_path(request):
-    """Every test runs twice: through the streaming kernel (+ general-kernel fix-up of deferred queries, the product
-    path) and with the streaming kernel disabled (debug flag 0x200), so both kernels keep full parity coverage."""
-    EXTRA_FLAGS[0] = 0x200 if request.param == "general" else 0
+    """Every test runs three times: through the streaming kernel (+ general-kernel fix-up of deferred queries, the
+    product path), through its larger-table configuration (QF_FLAG_LARGE_UNION, a performance hint that must not change
+    any result) and with the streaming kernel disabled (debug flag 0x200), so all kernels keep full parity coverage."""
+    EXTRA_FLAGS[0] = {"stream": 0, "stream-large": 8, "general": 0x200}[request.param]
     yield
     EXTRA_FLAGS[0] = 0
 
