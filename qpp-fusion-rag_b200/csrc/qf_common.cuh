@@ -13,6 +13,7 @@ namespace qf {
 void set_error(const char* fmt, ...);
 int  check_device();                       // QF_OK or QF_E_NO_DEVICE (message set)
 int  sm_count();
+int  device_index();                    // current CUDA device, clamped to [0, 63] (index of per-device one-time state)
 void prof_mark(int phase, int which, cudaStream_t st);   // CUDA-event pair around a kernel (qf_profile_*)
 
 #define QF_CUDA_TRY(expr)                                                                 \

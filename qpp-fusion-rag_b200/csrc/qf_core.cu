@@ -58,6 +58,12 @@ void prof_mark(int phase, int which, cudaStream_t st) {
   }
 }
 
+int device_index() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  return dev < 0 ? 0 : (dev > 63 ? 63 : dev);
+}
+
 int sm_count() {
   static int cached[64] = {};
   int dev = 0, n = 148;

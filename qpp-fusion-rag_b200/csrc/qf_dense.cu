@@ -1050,7 +1050,8 @@ int launch_dense(const DenseMaps& maps, const DenseParams& p_in, cudaStream_t st
   if (!dbg) cudaMalloc(&dbg, sizeof(long long) * 8 * 256);
   p.dbg = dbg;
 #endif
-  static bool configured = false;
+  static bool configured_dev[64] = {};
+  bool& configured = configured_dev[qf::device_index()];   // kernel attributes are per device
   if (!configured) {
     QF_CUDA_TRY(cudaFuncSetAttribute(dense_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DENSE_SMEM_BYTES));
     QF_CUDA_TRY(cudaFuncSetAttribute(dense_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DENSE_SMEM_BYTES));
@@ -1175,7 +1176,8 @@ extern "C" int qf_dense_topk(const void* queries_bf16, const void* corpus_bf16, 
   if (rc != QF_OK) return rc;
   rc = make_corpus_tmap(corpus_bf16, N, D, BN / 2, &maps.pair);
   if (rc != QF_OK) return rc;
-  static bool configured = false;
+  static bool configured_dev[64] = {};
+  bool& configured = configured_dev[qf::device_index()];   // kernel attributes are per device
   if (!configured) {
     QF_CUDA_TRY(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SEL_SMEM));
     configured = true;
@@ -1311,7 +1313,8 @@ extern "C" int qf_topk_merge(const float* scores, const int32_t* ids, int G, int
   QF_REQUIRE(scores && ids && out_scores && out_ids, QF_E_INVALID, "qf_topk_merge: null pointer argument");
   int rc = qf::check_device();
   if (rc != QF_OK) return rc;
-  static bool configured = false;
+  static bool configured_dev[64] = {};
+  bool& configured = configured_dev[qf::device_index()];   // kernel attributes are per device
   if (!configured) {
     QF_CUDA_TRY(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SEL_SMEM));
     configured = true;

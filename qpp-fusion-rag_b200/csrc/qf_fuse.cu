@@ -574,7 +574,8 @@ template <int CAP, int HBITS, int NT, int ST>
 int launch(const FuseParams& p, cudaStream_t stream) {
   using L = Layout<CAP, HBITS, NT, ST>;
   auto kern = fuse_kernel<CAP, HBITS, NT, ST>;
-  static bool configured = false;   // per instantiation; attribute set is idempotent
+  static bool configured_dev[64] = {};   // per instantiation; attribute set is idempotent
+  bool& configured = configured_dev[qf::device_index()];   // kernel attributes are per device
   if (!configured) {
     QF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::total));
     configured = true;

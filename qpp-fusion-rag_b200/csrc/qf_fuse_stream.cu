@@ -698,8 +698,10 @@ template <int G, int UCAP, int NB, int NMAX, int NT, int MINB, int ST, int MODE>
 int launch_stream(const FuseParams& p, cudaStream_t stream) {
   using L = SLayout<G, UCAP, NB, NMAX, NT>;
   auto kern = fuse_stream_kernel<G, UCAP, NB, NMAX, NT, MINB, ST, MODE>;
-  static bool configured = false;   // per instantiation; attribute set is idempotent
-  static int per_sm = 1;
+  static bool configured_dev[64] = {};   // per instantiation; attribute set is idempotent
+  bool& configured = configured_dev[qf::device_index()];   // kernel attributes are per device
+  static int per_sm_dev[64] = {};
+  int& per_sm = per_sm_dev[qf::device_index()];
   if (!configured) {
     QF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::total));
     QF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
