@@ -21,6 +21,8 @@
 #include <algorithm>
 
 #include "qf_common.cuh"
+
+#include <stdlib.h>
 #include "qf_radix.cuh"
 
 namespace {
@@ -653,7 +655,9 @@ struct SelectParams {
   float* out_scores;       // [Q, k]
   int* out_ids;            // [Q, k]  (-1 padded)
   int* out_status;         // [Q] nullable: 1 = candidate underflow, 2 = overflow
+  int fixup;               // select_kernel only: process just the queries select2_kernel deferred
 };
+constexpr int SEL_DEFERRED = -2;   // out_ids[q][0] marker: query left to select_kernel by select2_kernel
 
 struct SelSmem {
   float* score;
@@ -816,6 +820,7 @@ __global__ void __launch_bounds__(SEL_NT, 1) select_kernel(const SelectParams p)
   __shared__ int s_n, s_flag;
   __shared__ int s_pref[260];
   for (int q = blockIdx.x; q < p.Q; q += gridDim.x) {
+    if (p.fixup && p.out_ids[(size_t)q * p.k] != SEL_DEFERRED) continue;      // uniform: same word for every thread
     int status = 0;
     int n = 0;
     const int want = min(p.k, p.N_total);
@@ -908,6 +913,260 @@ __global__ void __launch_bounds__(SEL_NT, 1) select_kernel(const SelectParams p)
     }
     if (p.out_status && tid == 0) p.out_status[q] = status;
     __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// select2_kernel: the common-case candidate ranking after the FILTER pass -- several queries in flight per SM and ONE
+// bucket pass instead of a 4-pass radix select followed by a 4-pass radix sort (same idea as the fusion kernel's
+// ranking, csrc/qf_fuse_stream.cu).  Per query (one CTA of 256 threads, ~75 KB of shared memory, 3 CTAs per SM):
+//   1. scan the per-(unit, thread) segment counts, copy the ~4k (score, id) pairs into shared memory
+//      (thread per segment; neighbouring threads read neighbouring segments, L1 absorbs the sector re-use);
+//   2. a 256-candidate sample gives min / max and a 64-bin histogram -> monotone piecewise-linear map
+//      score -> one of 4096 buckets (histogram equalisation), higher score = lower bucket;
+//   3. one pass counts the buckets (packed 16-bit shared-memory atomics); a block scan finds the first bucket b*
+//      whose cumulative count reaches k: only candidates in buckets <= b* can be in the top k;
+//   4. those (k .. k + one bucket) candidates are scattered into bucket order and each one's exact rank is its
+//      bucket's start plus the number of bucket mates that precede it under (score desc, id asc).
+// Anything unusual -- more than S2_CAP candidates, a segment overflow, > 1024 segments, a bucket longer than
+// S2_LONGB inside the cut (long runs of equal scores) -- marks the query SEL_DEFERRED for select_kernel (fix-up mode).
+constexpr int S2_NT = 256;
+constexpr int S2_CAP = 6144;        // candidates held per query
+constexpr int S2_NB = 4096;         // buckets
+constexpr int S2_KEEP = 2048;       // candidates that survive the bucket cut (k + one bucket)
+constexpr int S2_MAXSEG = 1024;
+constexpr int S2_LONGB = 128;
+constexpr int S2_CB = 64;
+constexpr size_t S2_OFF_ID = 4 * S2_CAP;
+constexpr size_t S2_OFF_BC = 8 * S2_CAP;
+constexpr size_t S2_OFF_CNT = 10 * S2_CAP;
+constexpr size_t S2_OFF_ORDER = S2_OFF_CNT + 2 * S2_NB;          // u16 order[S2_KEEP]; aliases u16 seg_off[S2_MAXSEG + 1]
+constexpr size_t S2_OFF_COARSE = S2_OFF_ORDER + 2 * S2_KEEP;
+constexpr size_t S2_SMEM = S2_OFF_COARSE + 4 * S2_CB * 3;
+static_assert(2 * (S2_MAXSEG + 1) <= 2 * S2_KEEP && S2_NB % (S2_NT * 8) == 0 && S2_CAP < 65536, "select2 layout");
+
+__global__ void __launch_bounds__(S2_NT, 3) select2_kernel(const SelectParams p) {
+  extern __shared__ __align__(16) unsigned char sm[];
+  float* s_score = reinterpret_cast<float*>(sm);
+  int* s_id = reinterpret_cast<int*>(sm + S2_OFF_ID);
+  u16* s_bc = reinterpret_cast<u16*>(sm + S2_OFF_BC);
+  u32* s_cnt32 = reinterpret_cast<u32*>(sm + S2_OFF_CNT);
+  u16* s_cur16 = reinterpret_cast<u16*>(sm + S2_OFF_CNT);
+  u16* s_order = reinterpret_cast<u16*>(sm + S2_OFF_ORDER);
+  u16* s_segoff = reinterpret_cast<u16*>(sm + S2_OFF_ORDER);
+  int* s_chist = reinterpret_cast<int*>(sm + S2_OFF_COARSE);
+  float* s_ccum = reinterpret_cast<float*>(sm + S2_OFF_COARSE + 4 * S2_CB);
+  float* s_cw = reinterpret_cast<float*>(sm + S2_OFF_COARSE + 8 * S2_CB);
+  __shared__ int warp_tot[S2_NT / 32];
+  __shared__ float red_mn[S2_NT / 32], red_mx[S2_NT / 32];
+  __shared__ int s_bstar, s_kept;
+  constexpr int NW = S2_NT / 32, CPT = S2_NB / S2_NT;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  for (int q = blockIdx.x; q < p.Q; q += gridDim.x) {
+    __syncthreads();                               // previous query's shared state is dead
+    const int want_k = min(p.k, p.N_total);
+    const size_t seg0 = (size_t)q * p.n_segs;
+    if (tid == 0) { s_bstar = S2_NB - 1; s_kept = 0; }
+    for (int i = tid; i < S2_NB / 2; i += S2_NT) s_cnt32[i] = 0u;
+    for (int i = tid; i < S2_CB; i += S2_NT) s_chist[i] = 0;
+    // ---- 1. segment counts -> offsets
+    int my_c[S2_MAXSEG / S2_NT];
+    int carry = 0;
+    bool bad = p.n_segs > S2_MAXSEG;
+#pragma unroll
+    for (int r = 0; r < S2_MAXSEG / S2_NT; ++r) {
+      const int sg = r * S2_NT + tid;
+      int c = (!bad && sg < p.n_segs) ? __ldg(p.seg_cnt + seg0 + sg) : 0;
+      if (c > SEG_T) { bad = true; c = SEG_T; }      // a unit overflowed its private segment: select_kernel reports it
+      my_c[r] = c;
+      int incl = c;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t_ = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t_;
+      }
+      if (lane == 31) warp_tot[warp] = incl;
+      __syncthreads();
+      int wb = 0, tot = 0;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) {
+        if (w < warp) wb += warp_tot[w];
+        tot += warp_tot[w];
+      }
+      if (sg <= S2_MAXSEG) s_segoff[sg] = (u16)min(carry + wb + incl - c, 65535);
+      carry += tot;
+      __syncthreads();
+    }
+    const int n = carry;
+    if (__syncthreads_or((bad || n > S2_CAP) ? 1 : 0)) {
+      if (tid == 0) p.out_ids[(size_t)q * p.k] = SEL_DEFERRED;
+      continue;
+    }
+    // ---- copy the candidates (thread per segment)
+#pragma unroll
+    for (int r = 0; r < S2_MAXSEG / S2_NT; ++r) {
+      const int sg = r * S2_NT + tid;
+      const int c = my_c[r];
+      if (c > 0) {
+        const uint2* src = p.seg_pairs + (seg0 + sg) * SEG_T;
+        const int off = s_segoff[sg];
+        for (int e = 0; e < c; ++e) {
+          const uint2 pr = __ldg(src + e);
+          s_score[off + e] = __uint_as_float(pr.x);
+          s_id[off + e] = (int)pr.y;
+        }
+      }
+    }
+    __syncthreads();
+    const int want = min(want_k, n);
+    // ---- 2. sample -> range, equalisation map
+    float mn = INFINITY, mx = -INFINITY, samp = 0.f;
+    const bool has = tid < n;
+    if (has) {
+      samp = s_score[(int)(((long long)tid * n) / S2_NT)];     // spread over the whole candidate array
+      mn = mx = samp;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if (lane == 0) { red_mn[warp] = mn; red_mx[warp] = mx; }
+    __syncthreads();
+    mn = INFINITY; mx = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) { mn = fminf(mn, red_mn[w]); mx = fmaxf(mx, red_mx[w]); }
+    float cscale = (mx > mn) ? (float)S2_CB / (mx - mn) : 0.f;
+    if (!(cscale > 0.f) || isinf(cscale)) cscale = 0.f;
+    auto coarse = [&](float v, float& frac) -> int {
+      float tf = (mx - v) * cscale;                              // monotone: higher score -> smaller tf
+      tf = fminf(fmaxf(tf, 0.f), (float)S2_CB);
+      int c = (int)tf;
+      c = c > S2_CB - 1 ? S2_CB - 1 : c;
+      frac = tf - (float)c;
+      return c;
+    };
+    if (has) { float fr; atomicAdd(&s_chist[coarse(samp, fr)], 1); }
+    __syncthreads();
+    if (warp == 0) {
+      const int h0 = s_chist[2 * lane] + 1, h1 = s_chist[2 * lane + 1] + 1;
+      const int tot = __reduce_add_sync(0xffffffffu, h0 + h1);
+      const int w0 = (h0 * S2_NB) / tot, w1 = (h1 * S2_NB) / tot;
+      int incl = w0 + w1;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t_ = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t_;
+      }
+      const int excl = incl - (w0 + w1);
+      s_ccum[2 * lane] = (float)excl;
+      s_cw[2 * lane] = (float)w0;
+      s_ccum[2 * lane + 1] = (float)(excl + w0);
+      s_cw[2 * lane + 1] = (float)w1;
+    }
+    __syncthreads();
+    // ---- 3. bucket counts
+    for (int i = tid; i < n; i += S2_NT) {
+      float frac;
+      const int c = coarse(s_score[i], frac);
+      int b = (int)fmaf(frac, s_cw[c], s_ccum[c]);
+      b = b < 0 ? 0 : (b > S2_NB - 1 ? S2_NB - 1 : b);
+      s_bc[i] = (u16)b;
+      atomicAdd(&s_cnt32[b >> 1], 1u << ((b & 1) * 16));
+    }
+    __syncthreads();
+    {   // exclusive scan of the 16-bit counters (CPT consecutive per thread), in place; cut bucket b*
+      int tsum = 0;
+      uint4 cv[CPT / 8];
+      int cnts[CPT];
+#pragma unroll
+      for (int v = 0; v < CPT / 8; ++v) {
+        cv[v] = reinterpret_cast<const uint4*>(s_cnt32)[tid * (CPT / 8) + v];
+        u32 wds[4] = {cv[v].x, cv[v].y, cv[v].z, cv[v].w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int c0 = (int)(wds[i] & 0xFFFFu), c1 = (int)(wds[i] >> 16);
+          cnts[v * 8 + 2 * i] = c0;
+          cnts[v * 8 + 2 * i + 1] = c1;
+          wds[i] = (u32)tsum | ((u32)(tsum + c0) << 16);
+          tsum += c0 + c1;
+        }
+        cv[v] = make_uint4(wds[0], wds[1], wds[2], wds[3]);
+      }
+      int incl = tsum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t_ = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t_;
+      }
+      if (lane == 31) warp_tot[warp] = incl;
+      __syncthreads();
+      int wbase = 0;
+      for (int w = 0; w < warp; ++w) wbase += warp_tot[w];
+      const int base = wbase + incl - tsum;
+      // buckets of this thread: the cut, and long buckets inside the cut
+      int run = base, tmax = 0;
+#pragma unroll
+      for (int i = 0; i < CPT; ++i) {
+        if (run < want) {                              // bucket starts inside the top `want`
+          tmax = cnts[i] > tmax ? cnts[i] : tmax;
+          if (run + cnts[i] >= want) { s_bstar = tid * CPT + i; s_kept = run + cnts[i]; }
+        }
+        run += cnts[i];
+      }
+      const u32 base2 = (u32)base * 0x00010001u;
+#pragma unroll
+      for (int v = 0; v < CPT / 8; ++v) {
+        cv[v].x += base2; cv[v].y += base2; cv[v].z += base2; cv[v].w += base2;
+        reinterpret_cast<uint4*>(s_cnt32)[tid * (CPT / 8) + v] = cv[v];
+      }
+      if (__syncthreads_or(tmax > S2_LONGB ? 1 : 0)) {
+        if (tid == 0) p.out_ids[(size_t)q * p.k] = SEL_DEFERRED;
+        continue;
+      }
+    }
+    const int bstar = s_bstar, kept = want > 0 ? s_kept : 0;
+    if (kept > S2_KEEP) {                               // uniform; cannot happen with S2_LONGB < S2_KEEP - k_max... guard
+      if (tid == 0) p.out_ids[(size_t)q * p.k] = SEL_DEFERRED;
+      continue;
+    }
+    // ---- 4. scatter the survivors into bucket order (cursor = bucket base, advanced atomically)
+    for (int i = tid; i < n; i += S2_NT) {
+      const int b = s_bc[i];
+      if (b <= bstar && want > 0) {
+        const int sh = (b & 1) * 16;
+        const u32 old = atomicAdd(&s_cnt32[b >> 1], 1u << sh);
+        s_order[(old >> sh) & 0xFFFFu] = (u16)i;
+      }
+    }
+    __syncthreads();
+    // ---- exact rank inside the bucket, output
+    float* osc = p.out_scores + (size_t)q * p.k;
+    int* oid = p.out_ids + (size_t)q * p.k;
+    for (int j = tid; j < kept; j += S2_NT) {
+      const int i = s_order[j];
+      const float v = s_score[i];
+      const int id = s_id[i];
+      const int b = s_bc[i];
+      const int hi = s_cur16[b];                        // after the scatter: end of bucket b = start of bucket b + 1
+      const int lo = b > 0 ? (int)s_cur16[b - 1] : 0;
+      int rank = lo;
+      for (int m = lo; m < hi; ++m) {
+        const int i2 = s_order[m];
+        const float v2 = s_score[i2];
+        rank += (v2 > v || (v2 == v && s_id[i2] < id)) ? 1 : 0;
+      }
+      if (rank < want) {
+        osc[rank] = v;
+        oid[rank] = (int)(id + p.id_offset);
+      }
+    }
+    for (int j = want + tid; j < p.k; j += S2_NT) {
+      osc[j] = -INFINITY;
+      oid[j] = -1;
+    }
+    if (p.out_status && tid == 0) p.out_status[q] = n < want_k ? 1 : 0;
   }
 }
 
@@ -1254,6 +1513,23 @@ extern "C" int qf_dense_topk(const void* queries_bf16, const void* corpus_bf16, 
   sp.Q = Q; sp.k = k; sp.N_total = N; sp.id_offset = id_offset;
   sp.out_scores = out_scores; sp.out_ids = out_ids; sp.out_status = out_status;
   qf::prof_mark(QF_PROF_DENSE_SELECT, 0, st);
+  {
+    // common case: select2_kernel (3 queries in flight per SM); select_kernel then finishes what it deferred
+    static bool s2_dev[64] = {};
+    bool& s2_ready = s2_dev[qf::device_index()];
+    if (!s2_ready) {
+      QF_CUDA_TRY(cudaFuncSetAttribute(select2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S2_SMEM));
+      QF_CUDA_TRY(cudaFuncSetAttribute(select2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+      s2_ready = true;
+    }
+    static const bool no_s2 = getenv("QF_DENSE_NO_SELECT2") != nullptr;     // debug hook: old ranking kernel only
+    if (!no_s2 && w.n_chunks * 2 <= S2_MAXSEG && k >= 1) {
+      const int g2 = Q < 3 * sms ? Q : 3 * sms;
+      select2_kernel<<<g2, S2_NT, S2_SMEM, st>>>(sp);
+      QF_CUDA_TRY(cudaGetLastError());
+      sp.fixup = 1;
+    }
+  }
   select_kernel<<<Q < sms ? Q : sms, SEL_NT, SEL_SMEM, st>>>(sp);
   qf::prof_mark(QF_PROF_DENSE_SELECT, 1, st);
   QF_CUDA_TRY(cudaGetLastError());
