@@ -98,6 +98,33 @@ def test_smaller_embedding_dim():
     check(Q=33, N=5000, D=256, k=50, seed=6)
 
 
+def test_duplicate_documents_are_ordered_by_id():
+    """Runs of exactly equal scores inside the top k: 40 copies of one document (ranked inside select2_kernel's bucket)
+    and 300 copies of another, spread over the corpus (longer than its in-bucket limit -> finished by select_kernel);
+    ties go by id.  (Copies in CONSECUTIVE rows overflow a private candidate segment instead: that is the status-2 /
+    exact-fallback case of the next test.)"""
+    rng = np.random.default_rng(41)
+    Q, N, D, k = 40, 60_000, 768, 1000
+    c = unit_rows(rng, N, D)
+    c[1000:1040] = c[7]
+    spread = 5000 + 97 * np.arange(300)
+    c[spread] = c[9]
+    qv = unit_rows(rng, Q, D)
+    qv[0], qv[1] = c[7], c[9]
+    qb, cb = to_bf16(qv), to_bf16(c)
+    dev = torch.device("cuda:0")
+    scores, ids, status = torch.ops.qppfusion.dense_topk(qb.to(dev), cb.to(dev), k, 0)
+    torch.cuda.synchronize()
+    assert int(status.max()) == 0
+    oi, os_ = do.flat_ip_topk(qb.float().numpy(), cb.float().numpy(), k)
+    ids, scores = ids.cpu().numpy(), scores.cpu().numpy()
+    assert np.array_equal(ids[0, :41], oi[0, :41]) and np.array_equal(ids[1, :301], oi[1, :301])
+    assert np.abs(scores - os_).max() <= TOL_SAME_INPUT
+    for q in range(Q):
+        eq = np.flatnonzero(scores[q, 1:] == scores[q, :-1])
+        assert np.all(ids[q, eq + 1] > ids[q, eq])
+
+
 def test_topk_merge_matches_oracle():
     from qppfusion import ops
     rng = np.random.default_rng(7)
