@@ -931,32 +931,38 @@ __global__ void __launch_bounds__(SEL_NT, 1) select_kernel(const SelectParams p)
 // Anything unusual -- more than S2_CAP candidates, a segment overflow, > 1024 segments, a bucket longer than
 // S2_LONGB inside the cut (long runs of equal scores) -- marks the query SEL_DEFERRED for select_kernel (fix-up mode).
 constexpr int S2_NT = 256;
-constexpr int S2_CAP = 6144;        // candidates held per query
+constexpr int S2_CAP = 6144;        // candidates held per query after the FILTER pass (3 CTAs per SM)
+constexpr int S2_CAP_MERGE = 8192;  // candidates held per query in the k-way merge of qf_topk_merge (2 CTAs per SM)
 constexpr int S2_NB = 4096;         // buckets
 constexpr int S2_KEEP = 2048;       // candidates that survive the bucket cut (k + one bucket)
 constexpr int S2_MAXSEG = 1024;
 constexpr int S2_LONGB = 128;
 constexpr int S2_CB = 64;
-constexpr size_t S2_OFF_ID = 4 * S2_CAP;
-constexpr size_t S2_OFF_BC = 8 * S2_CAP;
-constexpr size_t S2_OFF_CNT = 10 * S2_CAP;
-constexpr size_t S2_OFF_ORDER = S2_OFF_CNT + 2 * S2_NB;          // u16 order[S2_KEEP]; aliases u16 seg_off[S2_MAXSEG + 1]
-constexpr size_t S2_OFF_COARSE = S2_OFF_ORDER + 2 * S2_KEEP;
-constexpr size_t S2_SMEM = S2_OFF_COARSE + 4 * S2_CB * 3;
-static_assert(2 * (S2_MAXSEG + 1) <= 2 * S2_KEEP && S2_NB % (S2_NT * 8) == 0 && S2_CAP < 65536, "select2 layout");
+template <int CAP>
+struct S2Layout {
+  static constexpr size_t off_id = 4 * (size_t)CAP;
+  static constexpr size_t off_bc = 8 * (size_t)CAP;
+  static constexpr size_t off_cnt = 10 * (size_t)CAP;
+  static constexpr size_t off_order = off_cnt + 2 * S2_NB;        // u16 order[S2_KEEP]; aliases u16 seg_off[S2_MAXSEG + 1]
+  static constexpr size_t off_coarse = off_order + 2 * S2_KEEP;
+  static constexpr size_t total = off_coarse + 4 * S2_CB * 3;
+};
+static_assert(2 * (S2_MAXSEG + 1) <= 2 * S2_KEEP && S2_NB % (S2_NT * 8) == 0 && S2_CAP_MERGE < 65536, "select2 layout");
 
-__global__ void __launch_bounds__(S2_NT, 3) select2_kernel(const SelectParams p) {
+template <int CAP, int MINB>
+__global__ void __launch_bounds__(S2_NT, MINB) select2_kernel(const SelectParams p) {
+  using L2 = S2Layout<CAP>;
   extern __shared__ __align__(16) unsigned char sm[];
   float* s_score = reinterpret_cast<float*>(sm);
-  int* s_id = reinterpret_cast<int*>(sm + S2_OFF_ID);
-  u16* s_bc = reinterpret_cast<u16*>(sm + S2_OFF_BC);
-  u32* s_cnt32 = reinterpret_cast<u32*>(sm + S2_OFF_CNT);
-  u16* s_cur16 = reinterpret_cast<u16*>(sm + S2_OFF_CNT);
-  u16* s_order = reinterpret_cast<u16*>(sm + S2_OFF_ORDER);
-  u16* s_segoff = reinterpret_cast<u16*>(sm + S2_OFF_ORDER);
-  int* s_chist = reinterpret_cast<int*>(sm + S2_OFF_COARSE);
-  float* s_ccum = reinterpret_cast<float*>(sm + S2_OFF_COARSE + 4 * S2_CB);
-  float* s_cw = reinterpret_cast<float*>(sm + S2_OFF_COARSE + 8 * S2_CB);
+  int* s_id = reinterpret_cast<int*>(sm + L2::off_id);
+  u16* s_bc = reinterpret_cast<u16*>(sm + L2::off_bc);
+  u32* s_cnt32 = reinterpret_cast<u32*>(sm + L2::off_cnt);
+  u16* s_cur16 = reinterpret_cast<u16*>(sm + L2::off_cnt);
+  u16* s_order = reinterpret_cast<u16*>(sm + L2::off_order);
+  u16* s_segoff = reinterpret_cast<u16*>(sm + L2::off_order);
+  int* s_chist = reinterpret_cast<int*>(sm + L2::off_coarse);
+  float* s_ccum = reinterpret_cast<float*>(sm + L2::off_coarse + 4 * S2_CB);
+  float* s_cw = reinterpret_cast<float*>(sm + L2::off_coarse + 8 * S2_CB);
   __shared__ int warp_tot[S2_NT / 32];
   __shared__ float red_mn[S2_NT / 32], red_mx[S2_NT / 32];
   __shared__ int s_bstar, s_kept;
@@ -970,62 +976,88 @@ __global__ void __launch_bounds__(S2_NT, 3) select2_kernel(const SelectParams p)
     if (tid == 0) { s_bstar = S2_NB - 1; s_kept = 0; }
     for (int i = tid; i < S2_NB / 2; i += S2_NT) s_cnt32[i] = 0u;
     for (int i = tid; i < S2_CB; i += S2_NT) s_chist[i] = 0;
-    // ---- 1. segment counts -> offsets
-    int my_c[S2_MAXSEG / S2_NT];
-    int carry = 0;
-    bool bad = p.n_segs > S2_MAXSEG;
+    int n = 0, n_valid = 0;
+    if (p.seg_pairs) {
+      // ---- 1. segment counts -> offsets
+      int my_c[S2_MAXSEG / S2_NT];
+      int carry = 0;
+      bool bad = p.n_segs > S2_MAXSEG;
 #pragma unroll
-    for (int r = 0; r < S2_MAXSEG / S2_NT; ++r) {
-      const int sg = r * S2_NT + tid;
-      int c = (!bad && sg < p.n_segs) ? __ldg(p.seg_cnt + seg0 + sg) : 0;
-      if (c > SEG_T) { bad = true; c = SEG_T; }      // a unit overflowed its private segment: select_kernel reports it
-      my_c[r] = c;
-      int incl = c;
+      for (int r = 0; r < S2_MAXSEG / S2_NT; ++r) {
+        const int sg = r * S2_NT + tid;
+        int c = (!bad && sg < p.n_segs) ? __ldg(p.seg_cnt + seg0 + sg) : 0;
+        if (c > SEG_T) { bad = true; c = SEG_T; }    // a unit overflowed its private segment: select_kernel reports it
+        my_c[r] = c;
+        int incl = c;
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int t_ = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t_;
+        for (int o = 1; o < 32; o <<= 1) {
+          const int t_ = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += t_;
+        }
+        if (lane == 31) warp_tot[warp] = incl;
+        __syncthreads();
+        int wb = 0, tot = 0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+          if (w < warp) wb += warp_tot[w];
+          tot += warp_tot[w];
+        }
+        s_segoff[sg] = (u16)min(carry + wb + incl - c, 65535);
+        carry += tot;
+        __syncthreads();
       }
-      if (lane == 31) warp_tot[warp] = incl;
-      __syncthreads();
-      int wb = 0, tot = 0;
-#pragma unroll
-      for (int w = 0; w < NW; ++w) {
-        if (w < warp) wb += warp_tot[w];
-        tot += warp_tot[w];
+      n = n_valid = carry;
+      if (__syncthreads_or((bad || n > CAP) ? 1 : 0)) {
+        if (tid == 0) p.out_ids[(size_t)q * p.k] = SEL_DEFERRED;
+        continue;
       }
-      if (sg <= S2_MAXSEG) s_segoff[sg] = (u16)min(carry + wb + incl - c, 65535);
-      carry += tot;
-      __syncthreads();
-    }
-    const int n = carry;
-    if (__syncthreads_or((bad || n > S2_CAP) ? 1 : 0)) {
-      if (tid == 0) p.out_ids[(size_t)q * p.k] = SEL_DEFERRED;
-      continue;
-    }
-    // ---- copy the candidates (thread per segment)
+      // ---- copy the candidates (thread per segment)
 #pragma unroll
-    for (int r = 0; r < S2_MAXSEG / S2_NT; ++r) {
-      const int sg = r * S2_NT + tid;
-      const int c = my_c[r];
-      if (c > 0) {
-        const uint2* src = p.seg_pairs + (seg0 + sg) * SEG_T;
-        const int off = s_segoff[sg];
-        for (int e = 0; e < c; ++e) {
-          const uint2 pr = __ldg(src + e);
-          s_score[off + e] = __uint_as_float(pr.x);
-          s_id[off + e] = (int)pr.y;
+      for (int r = 0; r < S2_MAXSEG / S2_NT; ++r) {
+        const int sg = r * S2_NT + tid;
+        const int c = my_c[r];
+        if (c > 0) {
+          const uint2* src = p.seg_pairs + (seg0 + sg) * SEG_T;
+          const int off = s_segoff[sg];
+          for (int e = 0; e < c; ++e) {
+            const uint2 pr = __ldg(src + e);
+            s_score[off + e] = __uint_as_float(pr.x);
+            s_id[off + e] = (int)pr.y;
+          }
         }
       }
+    } else {
+      // ---- k-way merge input: nseg ranked lists of seg_len entries (id < 0 = padding of a short list)
+      n = p.nseg * p.seg_len;
+      if (n > CAP) {                                   // uniform
+        if (tid == 0) p.out_ids[(size_t)q * p.k] = SEL_DEFERRED;
+        continue;
+      }
+      int valid = 0;
+      for (int i = tid; i < n; i += S2_NT) {
+        const size_t a = (size_t)q * p.q_stride + (size_t)(i / p.seg_len) * p.seg_stride + (i % p.seg_len);
+        float v = __ldg(p.cand_score + a);
+        int id = __ldg(p.cand_id + a);
+        if (id < 0 || v == -INFINITY) { v = -INFINITY; id = 0x7fffffff; } else ++valid;
+        s_score[i] = v;
+        s_id[i] = id;
+      }
+      valid = __reduce_add_sync(0xffffffffu, valid);
+      if (lane == 0) warp_tot[warp] = valid;
+      __syncthreads();
+      n_valid = 0;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) n_valid += warp_tot[w];
     }
     __syncthreads();
-    const int want = min(want_k, n);
-    // ---- 2. sample -> range, equalisation map
+    const int want = min(want_k, n_valid);
+    // ---- 2. sample -> range, equalisation map (padding entries, score -inf, always go to the last bucket)
     float mn = INFINITY, mx = -INFINITY, samp = 0.f;
-    const bool has = tid < n;
+    bool has = tid < n;
     if (has) {
       samp = s_score[(int)(((long long)tid * n) / S2_NT)];     // spread over the whole candidate array
-      mn = mx = samp;
+      has = samp != -INFINITY;
+      if (has) mn = mx = samp;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -1069,9 +1101,11 @@ __global__ void __launch_bounds__(S2_NT, 3) select2_kernel(const SelectParams p)
     // ---- 3. bucket counts
     for (int i = tid; i < n; i += S2_NT) {
       float frac;
-      const int c = coarse(s_score[i], frac);
+      const float v = s_score[i];
+      const int c = coarse(v, frac);
       int b = (int)fmaf(frac, s_cw[c], s_ccum[c]);
-      b = b < 0 ? 0 : (b > S2_NB - 1 ? S2_NB - 1 : b);
+      b = (b < 0 ? 0 : (b > S2_NB - 1 ? S2_NB - 1 : b));
+      if (v == -INFINITY) b = S2_NB - 1;
       s_bc[i] = (u16)b;
       atomicAdd(&s_cnt32[b >> 1], 1u << ((b & 1) * 16));
     }
@@ -1159,14 +1193,14 @@ __global__ void __launch_bounds__(S2_NT, 3) select2_kernel(const SelectParams p)
       }
       if (rank < want) {
         osc[rank] = v;
-        oid[rank] = (int)(id + p.id_offset);
+        oid[rank] = (int)(id + p.id_offset);           // rank < want <= n_valid: never a padding entry
       }
     }
     for (int j = want + tid; j < p.k; j += S2_NT) {
       osc[j] = -INFINITY;
       oid[j] = -1;
     }
-    if (p.out_status && tid == 0) p.out_status[q] = n < want_k ? 1 : 0;
+    if (p.out_status && tid == 0) p.out_status[q] = n_valid < want_k ? 1 : 0;
   }
 }
 
@@ -1518,14 +1552,15 @@ extern "C" int qf_dense_topk(const void* queries_bf16, const void* corpus_bf16, 
     static bool s2_dev[64] = {};
     bool& s2_ready = s2_dev[qf::device_index()];
     if (!s2_ready) {
-      QF_CUDA_TRY(cudaFuncSetAttribute(select2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S2_SMEM));
-      QF_CUDA_TRY(cudaFuncSetAttribute(select2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+      QF_CUDA_TRY(cudaFuncSetAttribute(select2_kernel<S2_CAP, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)S2Layout<S2_CAP>::total));
+      QF_CUDA_TRY(cudaFuncSetAttribute(select2_kernel<S2_CAP, 3>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
       s2_ready = true;
     }
     static const bool no_s2 = getenv("QF_DENSE_NO_SELECT2") != nullptr;     // debug hook: old ranking kernel only
     if (!no_s2 && w.n_chunks * 2 <= S2_MAXSEG && k >= 1) {
       const int g2 = Q < 3 * sms ? Q : 3 * sms;
-      select2_kernel<<<g2, S2_NT, S2_SMEM, st>>>(sp);
+      select2_kernel<S2_CAP, 3><<<g2, S2_NT, S2Layout<S2_CAP>::total, st>>>(sp);
       QF_CUDA_TRY(cudaGetLastError());
       sp.fixup = 1;
     }
@@ -1593,6 +1628,9 @@ extern "C" int qf_topk_merge(const float* scores, const int32_t* ids, int G, int
   bool& configured = configured_dev[qf::device_index()];   // kernel attributes are per device
   if (!configured) {
     QF_CUDA_TRY(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SEL_SMEM));
+    QF_CUDA_TRY(cudaFuncSetAttribute(select2_kernel<S2_CAP_MERGE, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)S2Layout<S2_CAP_MERGE>::total));
+    QF_CUDA_TRY(cudaFuncSetAttribute(select2_kernel<S2_CAP_MERGE, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     configured = true;
   }
   SelectParams sp{};
@@ -1601,7 +1639,16 @@ extern "C" int qf_topk_merge(const float* scores, const int32_t* ids, int G, int
   sp.Q = Q; sp.k = k; sp.N_total = 0x7fffffff; sp.id_offset = 0;
   sp.out_scores = out_scores; sp.out_ids = out_ids; sp.out_status = nullptr;
   const int sms = qf::sm_count();
-  select_kernel<<<Q < sms ? Q : sms, SEL_NT, SEL_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(sp);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  static const bool no_s2 = getenv("QF_DENSE_NO_SELECT2") != nullptr;     // debug hook: old ranking kernel only
+  if (!no_s2) {
+    // common case: bucket-cut kernel, two queries in flight per SM; select_kernel then finishes what it deferred
+    const int g2 = Q < 2 * sms ? Q : 2 * sms;
+    select2_kernel<S2_CAP_MERGE, 2><<<g2, S2_NT, S2Layout<S2_CAP_MERGE>::total, st>>>(sp);
+    QF_CUDA_TRY(cudaGetLastError());
+    sp.fixup = 1;
+  }
+  select_kernel<<<Q < sms ? Q : sms, SEL_NT, SEL_SMEM, st>>>(sp);
   QF_CUDA_TRY(cudaGetLastError());
   return QF_OK;
 }
