@@ -209,3 +209,58 @@ def test_native_writer_matches_python_write_runfile(tmp_path):
     fusion.write_runfile(fused, str(out_py), "tag-x")
     nio.write_runfile_csr(str(out_c), parsed, qorder, np.array(offs), np.concatenate(ids), np.concatenate(scs), "tag-x", n_threads=3)
     assert out_c.read_bytes() == out_py.read_bytes()
+
+
+def test_native_parser_multithreaded_shards_equal_single_thread(tmp_path):
+    """A file large enough (> 1 MiB) for the chunk-parallel tokeniser and the shard-parallel docno dictionary: every
+    thread count yields the same rows; docno codes may be numbered differently but must name the same strings."""
+    from qppfusion import native_io as nio
+    rng = np.random.default_rng(5)
+    lines = []
+    for q in range(120):
+        docs = rng.choice(30_000, size=400, replace=False)
+        sc = np.sort(rng.normal(size=400) * 3)[::-1]
+        for i, (dno, s_) in enumerate(zip(docs, sc)):
+            lines.append(f"q{q} Q0 D-{dno:07d} {i + 1} {s_:.6f} runA")
+    p = tmp_path / "big.res"
+    p.write_text("\n".join(lines) + "\n")
+    assert p.stat().st_size > (1 << 20)
+    ref = nio.parse_runs([str(p)], n_threads=1)
+    ref_docs = ref.doc_strings()
+    df = pd.read_csv(p, sep=r"\s+", names=["qid", "iter", "docno", "rank", "score", "runid"], dtype={"qid": str, "docno": str})
+    assert (ref_docs[ref.cols[0]["doc"]] == df["docno"].to_numpy()).all()
+    assert np.array_equal(ref.cols[0]["score"], df["score"].to_numpy()) and np.array_equal(ref.cols[0]["rank"], df["rank"].to_numpy())
+    assert np.array_equal(ref.cols[0]["micro"], np.round(df["score"].to_numpy() * 1e6).astype(np.int32))
+    for nt in (2, 5, 8):
+        got = nio.parse_runs([str(p)], n_threads=nt)
+        assert got.all_micro and got.qid_strings() == ref.qid_strings()
+        for col in ("qid", "rank", "micro", "score"):
+            assert np.array_equal(got.cols[0][col], ref.cols[0][col]), (nt, col)
+        gd = got.doc_strings()
+        assert sorted(gd.tolist()) == sorted(ref_docs.tolist())
+        assert (gd[got.cols[0]["doc"]] == ref_docs[ref.cols[0]["doc"]]).all()
+
+
+def test_native_writer_fixed6_is_python_format(tmp_path):
+    """The printf-free "%.6f" of qf_runfile_write against Python's formatting: random magnitudes, exact ties of the
+    seventh decimal (k + 0.5) * 1e-6 representable in binary, negative zero, values at and beyond the 1e9 fallback."""
+    from qppfusion import native_io as nio
+    rng = np.random.default_rng(6)
+    vals = np.concatenate([
+        rng.normal(size=20000) * 10.0 ** rng.integers(-8, 9, size=20000),
+        (rng.integers(-2_000_000, 2_000_000, size=20000) + 0.5) / 1e6,            # decimal ties (inexact in binary)
+        rng.integers(-4096, 4096, size=4000) / 64.0 + 2.0 ** -21 * rng.integers(-3, 4, size=4000),   # binary ties region
+        np.array([0.0, -0.0, 1e-7, -1e-7, 4.9999995e-7, 5e-7, 5.0000005e-7, 0.9999995, 0.99999949999,
+                  123456789.1234565, 999999999.9999995, 1e9, -1e9, 1.5e12, 2147.4836475, -2147.4836475]),
+    ])
+    p = tmp_path / "one.res"
+    p.write_text("q1 Q0 d0 1 0.5 A\n")
+    parsed = nio.parse_runs([str(p)])
+    _, qorder = nio.pack_parsed(parsed)
+    n = len(vals)
+    out = tmp_path / "out.res"
+    nio.write_runfile_csr(str(out), parsed, qorder, np.array([0, n]), np.zeros(n, dtype=np.int32), vals, "t", n_threads=4)
+    got = [ln.split(" ")[4] for ln in out.read_text().splitlines()]
+    exp = ["%.6f" % v for v in vals]
+    bad = [(g, e, float(v).hex()) for g, e, v in zip(got, exp, vals) if g != e]
+    assert not bad, bad[:10]
