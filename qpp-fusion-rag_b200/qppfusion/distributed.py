@@ -97,17 +97,33 @@ def dense_search_sharded(queries_bf16: torch.Tensor, corpus_shard_bf16: torch.Te
     ranks.  merge="all_to_all" (default): each rank merges Q/G queries and the merged slices are all-gathered;
     merge="all_gather": every rank gathers all [G, Q, k] lists and merges all Q queries itself."""
     from . import ops
-    scores, ids, status = ops.dense_topk(queries_bf16, corpus_shard_bf16, k, id_offset)
     world = dist.get_world_size(group)
-    Q = scores.shape[0]
-    if merge == "all_gather" or world == 1:
-        gs, gi = gather_topk(scores, ids, group)
-        ms, mi = ops.topk_merge(gs, gi)
-        return ms, mi, status
-    rs, ri, qs = exchange_topk(scores, ids, group)
-    ms, mi = ops.topk_merge(rs.contiguous(), ri.contiguous())                       # [qs, k] for this rank's query slice
-    fs = torch.empty((world * qs, k), dtype=ms.dtype, device=ms.device)
-    fi = torch.empty((world * qs, k), dtype=mi.dtype, device=mi.device)
-    dist.all_gather_into_tensor(fs, ms.contiguous(), group=group)
-    dist.all_gather_into_tensor(fi, mi.contiguous(), group=group)
-    return fs[:Q], fi[:Q], status
+
+    def run(exact: bool):
+        if exact:     # local search with the status-driven exact repair (reads the status back: a host sync)
+            scores, ids, status = ops.dense_topk(queries_bf16, corpus_shard_bf16, k, id_offset)
+        else:         # raw op: nothing waits for the host, the whole call is enqueued back to back
+            scores, ids, status = torch.ops.qppfusion.dense_topk(queries_bf16, corpus_shard_bf16, int(k), int(id_offset))
+        Q = scores.shape[0]
+        if merge == "all_gather" or world == 1:
+            gs, gi = gather_topk(scores, ids, group)
+            ms, mi = ops.topk_merge(gs, gi)
+            return ms, mi, status
+        rs, ri, qs = exchange_topk(scores, ids, group)
+        ms, mi = ops.topk_merge(rs.contiguous(), ri.contiguous())                   # [qs, k] for this rank's query slice
+        fs = torch.empty((world * qs, k), dtype=ms.dtype, device=ms.device)
+        fi = torch.empty((world * qs, k), dtype=mi.dtype, device=mi.device)
+        dist.all_gather_into_tensor(fs, ms.contiguous(), group=group)
+        dist.all_gather_into_tensor(fi, mi.contiguous(), group=group)
+        return fs[:Q], fi[:Q], status
+
+    # Optimistic pass without any host synchronisation; ONE check at the end (the flag is MAX-reduced so that every
+    # rank takes the same branch).  A failed sampled threshold anywhere -- rare -- repeats the call on all ranks with
+    # the exact repair path.
+    out_s, out_i, status = run(False)
+    flag = (status != 0).any().to(torch.int32).reshape(1)
+    if world > 1:
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
+    if int(flag.item()) != 0:
+        out_s, out_i, status = run(True)
+    return out_s, out_i, status
