@@ -73,17 +73,39 @@ __global__ void __launch_bounds__(NT) qpp_kernel(const QppParams p) {
   constexpr int ML = RESEARCH ? MAXLIST : 4;
   __shared__ double s_x[WARPS][MAXK];          // first k scores (float32-rounded, widened)
   __shared__ float s_all[WARPS][ML];           // whole list as float32 (bootstrap)
-  __shared__ unsigned s_cnt[WARPS][ML / 4 + 1];        // RBO depth histogram, 4 x 8-bit counters per word
-                                                        // (a depth bucket holds at most 2 sample entries)
   __shared__ unsigned short s_samp[WARPS][RESEARCH ? MAXK : 4];
-  __shared__ double s_pw[ML];                  // p^(d-1)
+  __shared__ double s_S[ML + 1];               // RBO suffix sums S[t] = sum_{d = t+1 .. Kd} p^(d-1) / d
   __shared__ double s_uefw[20];                // UEF rank weights 1 / log2(i + 2)
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr bool research = RESEARCH;
   const double p09 = (double)0.9f;              // RBO p is a Java float
+  // RBO(original, sample; depth n, p) = (1 - p) * sum_{d=1..n} overlap(d)/d * p^(d-1) with
+  // overlap(d) = #{j < m : max(j, b_j) < d}  (OverlapStats.java:77-99).  Exchanging the sums, every sample entry j
+  // contributes sum_{d = t_j+1 .. n} p^(d-1)/d with t_j = max(j, b_j): a difference of two suffix sums of a series
+  // that depends on nothing but p -- S[t_j] - S[n].  The table is built once per CTA; a sample then costs m look-ups
+  // instead of a scan over all n depths (same value up to summation order, ~1e-15 relative).
   if (research) {
-    for (int d = tid; d < p.K && d < MAXLIST; d += NT) s_pw[d] = pow(p09, (double)d);
+    const int Kd = p.K < MAXLIST ? p.K : MAXLIST;
+    const double lp = log(p09);
+    for (int d = tid; d < Kd; d += NT) s_S[d] = exp((double)d * lp) / (double)(d + 1);     // term of depth d + 1
+    if (tid == 0) s_S[Kd] = 0.0;
+    __syncthreads();
+    if (tid < 32) {                       // in-place suffix sums, 32 entries at a time from the tail
+      double carry = 0.0;
+      for (int hi = Kd; hi > 0; hi -= 32) {
+        const int idx = hi - 1 - (int)tid;                // lane 0 = last entry of the window
+        double v = idx >= 0 ? s_S[idx] : 0.0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const double t_ = __shfl_up_sync(0xffffffffu, v, o);
+          if ((int)tid >= o) v += t_;
+        }
+        v += carry;
+        if (idx >= 0) s_S[idx] = v;
+        carry = __shfl_sync(0xffffffffu, v, 31);
+      }
+    }
   }
   if (tid < 20) s_uefw[tid] = 1.0 / (log((double)(tid + 2)) / log(2.0));
   __syncthreads();
@@ -275,7 +297,6 @@ __global__ void __launch_bounds__(NT) qpp_kernel(const QppParams p) {
         }
         {                                                                // rsd_bootstrap  RSDSpecificity.java:22-52
           const int mS = min(len, p.k_cut);
-          unsigned* cnt = s_cnt[warp];
           unsigned short* samp = s_samp[warp];
           double acc = 0.0;
           for (int s = 0; s < p.n_samples; ++s) {
@@ -293,26 +314,12 @@ __global__ void __launch_bounds__(NT) qpp_kernel(const QppParams p) {
             __syncwarp();
             auto gets = [&](int j) { return (double)all[samp[j]]; };
             const double est = warp_var(gets, mS, lane, nullptr);       // NQC of the sample
-            // RBO(original, sample; depth len, p = 0.9f): overlap(d) = #{j < mS : max(j, b_j) < d}
-            for (int d = lane; d <= (len >> 2); d += 32) cnt[d] = 0u;
-            __syncwarp();
+            // RBO(original, sample; depth len, p = 0.9f) through the suffix table (see the kernel prologue)
+            const double s_len = s_S[len];
+            double aggr = 0.0;
             for (int j = lane; j < mS; j += 32) {
               const int t = max(j, (int)samp[j]);
-              atomicAdd(&cnt[t >> 2], 1u << (8 * (t & 3)));
-            }
-            __syncwarp();
-            double aggr = 0.0;
-            int carry = 0;
-            for (int base = 0; base < len; base += 32) {
-              const int t = base + lane;                                  // depth d = t + 1 uses cnt[0..t]
-              int c = t < len ? (int)((cnt[t >> 2] >> (8 * (t & 3))) & 0xffu) : 0;
-#pragma unroll
-              for (int o = 1; o < 32; o <<= 1) {
-                const int v = __shfl_up_sync(0xffffffffu, c, o);
-                if (lane >= o) c += v;
-              }
-              if (t < len) aggr += ((double)(carry + c) / (double)(t + 1)) * s_pw[t];
-              carry += __shfl_sync(0xffffffffu, c, 31);
+              aggr += s_S[t] - s_len;
             }
             aggr = qf::warp_sum(aggr);
             const double one_minus_p = (double)(1.0f - 0.9f);
