@@ -47,26 +47,31 @@ __device__ __forceinline__ uint4 lds128_volatile(u32 sa) {
   asm volatile("ld.volatile.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(sa));
   return v;
 }
-__device__ __forceinline__ u32 atoms_cas(u32 sa, u32 cmp, u32 val) {
-  u32 old;
-  asm volatile("atom.shared.cas.b32 %0, [%1], %2, %3;" : "=r"(old) : "r"(sa), "r"(cmp), "r"(val) : "memory");
+// CAS executed only where `pred` holds; elsewhere the result is `dflt` (no branch around the atomic).
+__device__ __forceinline__ u32 atoms_cas_if(bool pred, u32 sa, u32 cmp, u32 val, u32 dflt) {
+  u32 old = dflt;
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %4, 0;\n\t@p atom.shared.cas.b32 %0, [%1], %2, %3;\n\t}"
+               : "+r"(old) : "r"(sa), "r"(cmp), "r"(val), "r"((u32)pred) : "memory");
   return old;
 }
-__device__ __forceinline__ u32 atoms_or(u32 sa, u32 val) {
+__device__ __forceinline__ u32 atoms_add(u32 sa, u32 val) {
   u32 old;
-  asm volatile("atom.shared.or.b32 %0, [%1], %2;" : "=r"(old) : "r"(sa), "r"(val) : "memory");
+  asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(sa), "r"(val) : "memory");
   return old;
 }
-
 struct SMisc {
   int start[SMAX_R + 1];
   int len[SMAX_R];
-  int ins[SMAX_R];
+  int next[SMAX_R];  // next non-empty list after r (R if none)
+  int first;         // first non-empty list
   double w[SMAX_R], mn[SMAX_R], den[SMAX_R];
   double red_mn[16], red_mx[16];
   int red_cnt[16];
   int warp_tot[16];
   int status;
+  int qn;           // queued (unresolved) postings of the join pass
+  int ins_total;    // claimed keys = size of the union
+  int pc;           // sum of the list-mask popcounts (== number of postings unless a list holds a doc id twice)
 };
 
 // Classify one group of 4 keys with a single select chain: 0..3 = position of `id`, 4..7 = 4 + position of the
@@ -100,24 +105,20 @@ struct SLayout {
   static constexpr size_t off_acc = off_meta + 4 * H;
   static constexpr size_t off_cnt = off_acc + 8 * H;           // u16 bucket counters -> bases
   static constexpr size_t off_order = a16(off_cnt + 2 * NB);   // u16 order[UCAP]: slots in bucket order
+  static constexpr size_t off_slot = off_cnt;                  // phase A only: u16 slot of posting r*K+i [NMAX]
   static constexpr size_t off_bcache = a16(off_order + 2 * UCAP);   // u16 bucket id per slot
+  static constexpr size_t off_queue = off_bcache;                   // phase A only: u16 queue of unresolved postings [H]
   static constexpr size_t off_bitmap = a16(off_bcache + 2 * H);     // first-seen bitmap + word prefix (out_pos)
-  static constexpr size_t off_queue = a16(off_bitmap + 6 * BW);     // u16 straggler queue, 128 entries per warp
-  static constexpr size_t off_coarse = a16(off_queue + 2 * 128 * (NT / 32));
+  static constexpr size_t off_coarse = a16(off_bitmap + 6 * BW);
   static constexpr size_t off_misc = a16(off_coarse + 4 * CB * 3);
   static constexpr size_t total = a16(off_misc + sizeof(SMisc));
   static_assert(NB % NT == 0 && CPT % 8 == 0 && NB < 65536, "bucket scan: CPT counters per thread, 8 per 16-byte load");
   static_assert(UCAP < H && NMAX % 32 == 0 && NMAX <= 65536 && UCAP < 65536 && H < 65536, "layout");
   static_assert(NT / 32 <= 16 && NT / 32 >= 2, "warps");
+  static_assert(off_slot + 2 * NMAX <= off_bcache, "s_slot must fit into the bucket counter + order arrays");
 };
 
 __device__ __forceinline__ int warp_sum_int(int v) { return __reduce_add_sync(0xffffffffu, v); }
-
-template <typename raw_t> struct Chunk {
-  int id[4];
-  raw_t sc[4];
-  int rk[4];
-};
 
 // MODE 0: CombSUM / CombMNZ (weighted or not) on raw scores -- no min-max norm, no zero-skipping, no order checks
 //         (the weighted_* path and the benchmark step); MODE 1: every option decided at run time.
@@ -125,7 +126,7 @@ template <int G, int UCAP, int NB, int NMAX, int NT, int MINB, int ST, int MODE>
 __global__ void __launch_bounds__(NT, MINB) fuse_stream_kernel(const FuseParams p) {
   using L = SLayout<G, UCAP, NB, NMAX, NT>;
   using raw_t = typename ScoreT<ST>::type;
-  constexpr int H = L::H, NW = NT / 32, SPT = (H + NT - 1) / NT, CH = NT * 4, BW = L::BW, CPT = L::CPT;
+  constexpr int H = L::H, NW = NT / 32, SPT = (H + NT - 1) / NT, CH = NT * 4, BW = L::BW, CPT = L::CPT, QCAP = H;
 
   extern __shared__ __align__(16) unsigned char smem[];
   u32* s_keys = reinterpret_cast<u32*>(smem + L::off_keys);
@@ -137,7 +138,8 @@ __global__ void __launch_bounds__(NT, MINB) fuse_stream_kernel(const FuseParams 
   u16* s_bcache = reinterpret_cast<u16*>(smem + L::off_bcache);
   u32* s_bitmap = reinterpret_cast<u32*>(smem + L::off_bitmap);
   u16* s_bpre = reinterpret_cast<u16*>(smem + L::off_bitmap + 4 * BW);
-  u16* s_queue = reinterpret_cast<u16*>(smem + L::off_queue) + 128 * (threadIdx.x >> 5);   // this warp's queue
+  u16* s_queue = reinterpret_cast<u16*>(smem + L::off_queue);   // phase A: postings still to be resolved
+  u16* s_slot = reinterpret_cast<u16*>(smem + L::off_slot);     // phase A: table slot of every posting
   int* s_chist = reinterpret_cast<int*>(smem + L::off_coarse);
   float* s_ccum = reinterpret_cast<float*>(smem + L::off_coarse + 4 * CB);
   float* s_cw = reinterpret_cast<float*>(smem + L::off_coarse + 8 * CB);
@@ -158,12 +160,28 @@ __global__ void __launch_bounds__(NT, MINB) fuse_stream_kernel(const FuseParams 
   const bool need_scores = !is_rrf || check_sorted;
   const bool want_pos = (p.out_pos != nullptr);
 
+  // warp 0 keeps the NEXT query's list lengths and weights in registers (loaded while the current one is fused)
+  int pre_len = 0;
+  double pre_w = 1.0;
+  if (warp == 0 && lane < R && (int)blockIdx.x < p.Q) {
+    pre_len = __ldg(p.lens + (size_t)blockIdx.x * R + lane);
+    if (weighted) pre_w = __ldg(p.weights + (size_t)blockIdx.x * R + lane);
+  }
+  const u32 qn_sa = (u32)__cvta_generic_to_shared(&m.qn);
+
   for (int q = blockIdx.x; q < p.Q; q += gridDim.x) {
     __syncthreads();                       // previous query's shared state is dead
     // ------------------------------------------------------------ header + table reset
     if (warp == 0) {
-      int len = 0;
-      if (lane < R) len = __ldg(p.lens + (size_t)q * R + lane);
+      const int len = pre_len;
+      const double wq = pre_w;
+      {
+        const long long qx = (long long)q + gridDim.x;
+        if (lane < R && qx < p.Q) {
+          pre_len = __ldg(p.lens + (size_t)qx * R + lane);
+          if (weighted) pre_w = __ldg(p.weights + (size_t)qx * R + lane);
+        }
+      }
       const unsigned badm = __ballot_sync(0xffffffffu, lane < R && (len < 0 || len > K));
       const int l = badm ? 0 : len;
       int incl = l;
@@ -175,11 +193,21 @@ __global__ void __launch_bounds__(NT, MINB) fuse_stream_kernel(const FuseParams 
       if (lane < R) {
         m.start[lane] = incl - l;
         m.len[lane] = l;
-        m.ins[lane] = 0;
-        m.w[lane] = weighted ? __ldg(p.weights + (size_t)q * R + lane) : 1.0;
+        m.w[lane] = wq;
+      }
+      const unsigned nz = __ballot_sync(0xffffffffu, lane < R && l > 0);
+      if (lane < R) {
+        const unsigned rest = lane < 31 ? nz >> (lane + 1) : 0u;
+        m.next[lane] = rest ? lane + __ffs(rest) : R;
       }
       if (lane == R - 1) m.start[R] = incl;
-      if (lane == 0) m.status = badm ? QF_QSTAT_BAD_LEN : 0;
+      if (lane == 0) {
+        m.first = nz ? __ffs(nz) - 1 : R;
+        m.status = badm ? QF_QSTAT_BAD_LEN : 0;
+        m.qn = 0;
+        m.ins_total = 0;
+        m.pc = 0;
+      }
     }
     {
       uint4* k4 = reinterpret_cast<uint4*>(s_keys);
@@ -188,7 +216,6 @@ __global__ void __launch_bounds__(NT, MINB) fuse_stream_kernel(const FuseParams 
         k4[i] = make_uint4(EMPTY, EMPTY, EMPTY, EMPTY);
         m4[i] = make_uint4(0u, 0u, 0u, 0u);
       }
-      for (int i = tid; i < NB / 2; i += NT) s_cnt32[i] = 0u;
       if (want_pos)
         for (int i = tid; i < BW; i += NT) s_bitmap[i] = 0u;
       for (int i = tid; i < CB; i += NT) s_chist[i] = 0;
@@ -240,19 +267,120 @@ __global__ void __launch_bounds__(NT, MINB) fuse_stream_kernel(const FuseParams 
       __syncthreads();
     }
 
-    // ------------------------------------------------------------ A: hash-accumulate, list by list
+    // ------------------------------------------------------------ A1: join -- doc ids only, no ordering constraint
+    // Every posting of every list finds / claims its doc's slot and records it in s_slot[r*K + i].  Nothing here
+    // depends on the order in which postings arrive (the first-seen posting and the additions are settled in A2), so
+    // there is no barrier between lists, the four postings of a thread are resolved side by side (straight-line
+    // code, four independent dependency chains), and the postings whose home group holds four foreign keys or whose
+    // claim was lost are only queued: they are resolved once per query on densely packed lanes.
     const bool vec = (K % 4 == 0) &&
                      ((reinterpret_cast<uintptr_t>(gid) | reinterpret_cast<uintptr_t>(gsc) |
                        reinterpret_cast<uintptr_t>(grk)) & 15) == 0;
-    auto load = [&](Chunk<raw_t>& c, int r, int base) {
-      const int len = m.len[r];
+    auto load_ids = [&](int (&id)[4], int r, int base, int len) {
       const int32_t* gi = gid + (size_t)r * K;
+      if (vec) {
+        const int i0 = base + tid * 4;
+        if (i0 < len) {                         // K % 4 == 0 and len <= K: the 4-wide load stays inside the row
+          const int4 v = __ldg(reinterpret_cast<const int4*>(gi + i0));
+          id[0] = v.x; id[1] = v.y; id[2] = v.z; id[3] = v.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int i = base + j * NT + tid;
+          if (i < len) id[j] = __ldg(gi + i);
+        }
+      }
+    };
+    // One probe step: classify the group with one select chain -- doc found (no atomic) / first empty key, claimed
+    // with one CAS (a CAS on a key that meanwhile holds this very doc returns it = found) / four foreign keys or a
+    // claim lost to another doc (-> not resolved: queued).  Keys only ever change from EMPTY to a doc id, and a doc
+    // always sits before the first empty key of its probe order (home group, then groups at the doc's own stride;
+    // views can only be stale towards "too empty", and then the CAS fails), so concurrent postings of the same doc
+    // from different lists end up in the same slot.
+    bool defer = false;
+    int ins = 0;
+    auto join4 = [&](const int (&id)[4], int r, int base, int len) {
+      const u32 rowoff = (u32)r * (u32)K;
+      const int i0 = vec ? base + tid * 4 : base + tid;
+      bool valid[4], fail[4];
+      u32 g[4], sl[4];
+      uint4 kk[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        valid[j] = (vec ? i0 + j : i0 + j * NT) < len;
+        defer |= valid[j] && (u32)id[j] == EMPTY;          // doc id -1 is the empty-key sentinel: general kernel
+        g[j] = __umulhi((u32)id[j] * 2654435761u, (u32)G);
+        kk[j] = lds128_volatile(keys_sa + 16u * g[j]);     // (a dead lane reads some group: harmless)
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int pos = probe4(kk[j], (u32)id[j]);
+        const bool claim = valid[j] && pos >= 4;
+        const u32 cand = 4u * g[j] + (u32)(pos & 3);
+        const u32 o = atoms_cas_if(claim, keys_sa + 4u * cand, EMPTY, (u32)id[j], (u32)id[j]);
+        const bool ok = pos >= 0 && (o == EMPTY || o == (u32)id[j]);
+        ins += (claim && o == EMPTY) ? 1 : 0;
+        fail[j] = valid[j] && !ok;
+        sl[j] = ok ? cand : 0xFFFFu;
+      }
+      if (vec) {                                           // 4 consecutive u16 entries, 8-byte aligned
+        if (valid[0])
+          *reinterpret_cast<uint2*>(s_slot + rowoff + (u32)i0) = make_uint2(sl[0] | (sl[1] << 16), sl[2] | (sl[3] << 16));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (valid[j]) s_slot[rowoff + (u32)(i0 + j * NT)] = (u16)sl[j];
+      }
+      // unresolved postings -> CTA queue (one shared-memory atomic per warp and chunk)
+      unsigned bal[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bal[j] = __ballot_sync(0xffffffffu, fail[j]);
+      if (bal[0] | bal[1] | bal[2] | bal[3]) {
+        const int c0 = __popc(bal[0]), c1 = __popc(bal[1]), c2 = __popc(bal[2]), c3 = __popc(bal[3]);
+        u32 qb = 0;
+        if (lane == 0) qb = atoms_add(qn_sa, (u32)(c0 + c1 + c2 + c3));
+        qb = __shfl_sync(0xffffffffu, qb, 0);
+        const unsigned lt = (1u << lane) - 1u;
+        const u32 pre[4] = {qb, qb + (u32)c0, qb + (u32)(c0 + c1), qb + (u32)(c0 + c1 + c2)};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const u32 qp = pre[j] + (u32)__popc(bal[j] & lt);
+          if (fail[j] && qp < (u32)QCAP) s_queue[qp] = (u16)(rowoff + (u32)(vec ? i0 + j : i0 + j * NT));
+        }
+      }
+    };
+    {
+      int r = m.first, base = 0, len_r = m.len[r];        // n > 0: there is a non-empty list
+      int cur[4] = {0, 0, 0, 0}, nxt[4] = {0, 0, 0, 0};
+      load_ids(cur, r, base, len_r);
+      while (r < R) {
+        int r2 = r, b2 = base + CH, len2 = len_r;
+        if (b2 >= len_r) {
+          b2 = 0;
+          r2 = m.next[r];
+          len2 = r2 < R ? m.len[r2] : 0;
+        }
+        if (r2 < R) load_ids(nxt, r2, b2, len2);
+        join4(cur, r, base, len_r);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) cur[j] = nxt[j];
+        r = r2;
+        base = b2;
+        len_r = len2;
+      }
+    }
+
+    // ------------------------------------------------------------ A2 prologue: first chunk of scores in flight
+    struct SC {
+      raw_t sc[4];
+      int rk[4];
+    };
+    auto load_sc = [&](SC& c, int r, int base, int len) {
       const raw_t* gs = gsc + (size_t)r * K;
       if (vec) {
         const int i0 = base + tid * 4;
-        if (i0 < len) {                       // K % 4 == 0 and len <= K: the 4-wide load stays inside the row
-          const int4 v = __ldg(reinterpret_cast<const int4*>(gi + i0));
-          c.id[0] = v.x; c.id[1] = v.y; c.id[2] = v.z; c.id[3] = v.w;
+        if (i0 < len) {
           if (need_scores) {
             if constexpr (sizeof(raw_t) == 4) {
               const int4 s = __ldg(reinterpret_cast<const int4*>(gs + i0));
@@ -276,28 +404,105 @@ __global__ void __launch_bounds__(NT, MINB) fuse_stream_kernel(const FuseParams 
         for (int j = 0; j < 4; ++j) {
           const int i = base + j * NT + tid;
           if (i < len) {
-            c.id[j] = __ldg(gi + i);
             if (need_scores) c.sc[j] = __ldg(gs + i);
             if (grk) c.rk[j] = __ldg(grk + (size_t)r * K + i);
           }
         }
       }
     };
+    const int r_first = m.first;
+    SC cur_sc, nxt_sc;
+    load_sc(cur_sc, r_first, 0, m.len[r_first]);
 
-    bool defer = false, bad_order = false;
-    int ins = 0;
-    auto process = [&](const Chunk<raw_t>& c, int r, int base) {
-      const int len = m.len[r], s0 = m.start[r];
+    // ------------------------------------------------------------ A1 drain: the queued postings, 32 per warp round
+    __syncthreads();                                           // queue complete
+    {
+      const int qn = m.qn;
+      if (qn > QCAP) {
+        defer = true;                                          // (never at sane table loads) general kernel
+      } else {
+        for (int b = warp * 32; b < qn; b += NT) {
+          const bool mine = b + lane < qn;
+          u32 off = 0, id = 0, gq = 0, step = 1;
+          int slot = -1;
+          if (mine) {
+            off = s_queue[b + lane];
+            id = (u32)__ldg(gid + off);
+            const u32 h = id * 2654435761u;
+            gq = __umulhi(h, (u32)G);
+            step = ((h >> 4) & 0xFEu) | 1u;                    // odd stride < 256 <= G: no primary clustering
+          }
+          uint4 k4 = lds128_volatile(keys_sa + 16u * gq);
+          bool inserted = false, active = mine;
+          int probes = 0;
+          while (__any_sync(0xffffffffu, active)) {            // probe loop uniform over the warp
+            if (active) {
+              const int pos = probe4(k4, id);
+              const u32 cand = 4u * gq + (u32)(pos & 3);
+              const u32 o = atoms_cas_if(pos >= 4, keys_sa + 4u * cand, EMPTY, id, id);
+              if (pos >= 0 && (o == EMPTY || o == id)) {
+                inserted = (pos >= 4) && (o == EMPTY);
+                slot = (int)cand;
+                active = false;
+              } else if (pos < 0) {                            // four foreign keys: next group of this doc's sequence
+                if (++probes > MAXPROBE) {
+                  defer = true;
+                  active = false;
+                }
+                gq += step;
+                gq = gq >= (u32)G ? gq - (u32)G : gq;
+              }                                                // else: lost the key to another doc, same group again
+              k4 = lds128_volatile(keys_sa + 16u * gq);
+            }
+          }
+          if (slot >= 0) {
+            s_slot[off] = (u16)slot;
+            ins += inserted ? 1 : 0;
+          }
+        }
+      }
+    }
+    {
+      const int wi = warp_sum_int(ins);
+      if (lane == 0 && wi) atomicAdd(&m.ins_total, wi);
+    }
+    const int stop = __syncthreads_or(defer ? 1 : 0);
+    const int total_ins = m.ins_total;
+    if (stop || total_ins > UCAP) {
+      if (tid == 0) p.out_lens[q] = FUSE_DEFERRED;
+      continue;
+    }
+
+    // ------------------------------------------------------------ A2: accumulate, list by list (one barrier per list)
+    // Posting i of list r adds fl(w_r * s_i) to its doc's float64 accumulator with a plain read-modify-write: doc ids
+    // are distinct inside a list and lists are separated by barriers, so the additions happen in exactly the
+    // reference's order ((w0*s0 + w1*s1) + ...), no FMA contraction.  The posting that finds the slot's list mask
+    // empty is the doc's FIRST-SEEN posting; its sequence number goes into the upper half of the meta word (tie-break
+    // key).  No atomics: a doc id that occurs twice inside one list makes two postings set the same mask bit, so the
+    // mask popcounts no longer add up to the number of postings -- checked in phase C, query deferred.
+    bool bad_order = false;
+    auto acc4 = [&](const SC& c, int r, int base, int len) {
+      const int s0 = m.start[r];
       const double w = m.w[r];
       const double lmn = minmax ? m.mn[r] : 0.0, lden = minmax ? m.den[r] : 1.0;
+      const u32 rowoff = (u32)r * (u32)K;
       int idx[4];
       bool valid[4];
-      u32 g[4];
-      uint4 kk[2];
+      u32 slot[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         idx[j] = vec ? base + tid * 4 + j : base + j * NT + tid;
         valid[j] = idx[j] < len;
+      }
+      if (vec) {
+        if (valid[0]) {                                        // 4 consecutive u16 slots, 8-byte aligned
+          const uint2 s2 = *reinterpret_cast<const uint2*>(s_slot + rowoff + (u32)idx[0]);
+          slot[0] = s2.x & 0xFFFFu; slot[1] = s2.x >> 16; slot[2] = s2.y & 0xFFFFu; slot[3] = s2.y >> 16;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (valid[j]) slot[j] = s_slot[rowoff + (u32)idx[j]];
       }
       if (check_sorted) {
 #pragma unroll
@@ -315,158 +520,55 @@ __global__ void __launch_bounds__(NT, MINB) fuse_stream_kernel(const FuseParams 
             if (prev > c.rk[j]) bad_order = true;
           }
       }
-      // One probe step: classify the group with one select chain -- doc found (no atomic) / first empty key, claimed
-      // with one CAS (a CAS on a key that meanwhile holds this very doc returns it = found) / four foreign keys or a
-      // claim lost to another doc (-> false: look at the group again, or move on, later).  Probe order is group by
-      // group, keys 0..3; a doc always sits before the first empty key of its probe order (views can only be stale
-      // towards "too empty", and then the CAS fails), so this is exact.
-      auto probe_once = [&](u32 id, u32 gq, const uint4& k4, int& slot, bool& inserted, bool& full) -> bool {
-        const int pos = probe4(k4, id);
-        full = pos < 0;
-        if (pos < 0) return false;
-        const int cand = (int)(4 * gq) + (pos & 3);
-        if (pos >= 4) {
-          const u32 o = atoms_cas(keys_sa + 4u * (u32)cand, EMPTY, id);
-          inserted = (o == EMPTY);
-          if (!inserted && o != id) return false;
-        }
-        slot = cand;
-        return true;
-      };
-      auto accumulate = [&](int slot, bool inserted, raw_t sc, int rk, int i) {
-        double v;
-        bool counts = true;
-        if (is_rrf) {
-          const double rank = grk ? (double)rk : (double)(i + 1);
-          v = __ddiv_rn(w, __dadd_rn(p.rrf_k, rank));
-        } else {
-          double s = raw_to_f64(sc);
-          if (minmax) s = __ddiv_rn(__dsub_rn(s, lmn), lden);
-          if (skip_zero && s == 0.0) counts = false;
-          v = __dmul_rn(w, s);                           // w == 1.0 when unweighted: exact
-        }
-        u32 bits = 1u << r;
-        if (skip_zero && counts) bits |= 1u << (8 + r);
-        if (inserted) {
-          ++ins;
-          const u32 seq = (u32)(s0 + i);
-          bits |= seq << 16;
-          if (want_pos) atomicOr(&s_bitmap[seq >> 5], 1u << (seq & 31u));   // first-seen bitmap (out_pos)
-        }
-        const u32 om = atoms_or(meta_sa + 4u * (u32)slot, bits);
-        const double prev = inserted ? 0.0 : s_acc[slot];     // the reference starts from 0.0 (src/fusion.py:275)
-        if (om & (1u << r)) defer = true;                     // the doc id occurs twice inside list r
-        else s_acc[slot] = __dadd_rn(prev, v);
-      };
-      // Home group of posting j+1 is fetched while posting j is resolved (a longer look-ahead only makes the
-      // fetched keys staler and the claims fail more often).
-      auto fetch = [&](int j) {
-        if (valid[j]) {
-          if ((u32)c.id[j] == EMPTY) {
-            defer = true;
-            valid[j] = false;
-          } else {
-            g[j] = __umulhi((u32)c.id[j] * 2654435761u, (u32)G);
-            kk[j & 1] = lds128_volatile(keys_sa + 16u * g[j]);
-          }
-        }
-      };
-      // First pass: ONE probe step per posting, all lanes together.  The ~10 % of postings whose home group holds four
-      // foreign keys are not chased here (every extra loop iteration would run for the whole warp with 2-3 live
-      // lanes): they go to this warp's queue and are resolved below on densely packed lanes.
-      int qn = 0;
-      fetch(0);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        if (j + 1 < 4) fetch(j + 1);
-        int slot = -1;
-        bool inserted = false;
-        bool resolved = false, full;
-        if (valid[j]) resolved = probe_once((u32)c.id[j], g[j], kk[j & 1], slot, inserted, full);
-        const bool strag = valid[j] && !resolved;
-        const unsigned bal = __ballot_sync(0xffffffffu, strag);
-        if (strag) s_queue[qn + __popc(bal & ((1u << lane) - 1u))] = (u16)idx[j];
-        qn += __popc(bal);
-        if (resolved) accumulate(slot, inserted, need_scores ? c.sc[j] : raw_t(0), grk ? c.rk[j] : 0, idx[j]);
-        __syncwarp();
-      }
-      // Drain: up to 32 stragglers at a time, full probe loop (uniform over the warp) from the home group.
-      while (qn > 0) {
-        const int take = qn < 32 ? qn : 32;
-        qn -= take;
-        const bool mine = lane < take;
-        int i = 0, rk = 0, slot = -1;
-        u32 id = 0, gq = 0;
-        raw_t sc = raw_t(0);
-        uint4 k4 = make_uint4(0u, 0u, 0u, 0u);
-        if (mine) {
-          i = s_queue[qn + lane];
-          id = (u32)__ldg(gid + (size_t)r * K + i);
-          if (need_scores) sc = __ldg(gsc + (size_t)r * K + i);
-          if (grk) rk = __ldg(grk + (size_t)r * K + i);
-          gq = __umulhi(id * 2654435761u, (u32)G);
-          k4 = lds128_volatile(keys_sa + 16u * gq);
-        }
-        bool inserted = false, active = mine;
-        int probes = 0;
-        while (__any_sync(0xffffffffu, active)) {
-          if (active) {
-            bool full;
-            if (probe_once(id, gq, k4, slot, inserted, full)) {
-              active = false;
-            } else {
-              if (full) {                                       // four foreign keys: next group
-                if (++probes > MAXPROBE) {
-                  defer = true;
-                  active = false;
-                }
-                gq = gq + 1 == (u32)G ? 0u : gq + 1;
-              }                                                 // else: lost the key to another doc, same group again
-              k4 = lds128_volatile(keys_sa + 16u * gq);
-            }
+        if (valid[j]) {
+          double v;
+          bool counts = true;
+          if (is_rrf) {
+            const double rank = grk ? (double)c.rk[j] : (double)(idx[j] + 1);
+            v = __ddiv_rn(w, __dadd_rn(p.rrf_k, rank));
+          } else {
+            double s = raw_to_f64(c.sc[j]);
+            if (minmax) s = __ddiv_rn(__dsub_rn(s, lmn), lden);
+            if (skip_zero && s == 0.0) counts = false;
+            v = __dmul_rn(w, s);                             // w == 1.0 when unweighted: exact
           }
+          u32 bits = 1u << r;
+          if (skip_zero && counts) bits |= 1u << (8 + r);
+          const u32 mt = s_meta[slot[j]];
+          const bool first = (mt & 0xFFFFu) == 0u;           // no list has touched this doc yet
+          if (first) {
+            const u32 seq = (u32)(s0 + idx[j]);
+            bits |= seq << 16;
+            if (want_pos) atomicOr(&s_bitmap[seq >> 5], 1u << (seq & 31u));   // first-seen bitmap (out_pos)
+          }
+          s_meta[slot[j]] = mt | bits;
+          const double prev = first ? 0.0 : s_acc[slot[j]];    // the reference starts from 0.0 (src/fusion.py:275)
+          s_acc[slot[j]] = __dadd_rn(prev, v);
         }
-        if (slot >= 0) accumulate(slot, inserted, sc, rk, i);
-        __syncwarp();
       }
     };
-
-    bool deferred = false;
-    int total_ins = 0;
     {
-      int r = 0, base = 0;
-      while (r < R && m.len[r] == 0) ++r;
-      Chunk<raw_t> cur, nxt;
-      load(cur, r, base);
+      int r = r_first, base = 0, len_r = m.len[r];
       while (r < R) {
-        int r2 = r, b2 = base + CH;
-        if (b2 >= m.len[r2]) {
+        int r2 = r, b2 = base + CH, len2 = len_r;
+        if (b2 >= len_r) {
           b2 = 0;
-          do { ++r2; } while (r2 < R && m.len[r2] == 0);
+          r2 = m.next[r];
+          len2 = r2 < R ? m.len[r2] : 0;
         }
-        if (r2 < R) load(nxt, r2, b2);
-        process(cur, r, base);
-        if (r2 != r) {                                   // list boundary
-          const int wi = warp_sum_int(ins);
-          ins = 0;
-          if (lane == 0 && wi) atomicAdd(&m.ins[r], wi);
-          const int stop = __syncthreads_or(defer ? 1 : 0);
-          total_ins += m.ins[r];
-          if (stop || total_ins > UCAP) {
-            deferred = true;
-            break;
-          }
-        }
-        cur = nxt;
+        if (r2 < R) load_sc(nxt_sc, r2, b2, len2);
+        acc4(cur_sc, r, base, len_r);
+        if (r2 != r) __syncthreads();                         // list boundary
+        cur_sc = nxt_sc;
         r = r2;
         base = b2;
+        len_r = len2;
       }
     }
     if (bad_order) atomicOr(&m.status, QF_QSTAT_UNSORTED);
-    if (deferred) {
-      if (tid == 0) p.out_lens[q] = FUSE_DEFERRED;
-      continue;
-    }
+    for (int i = tid; i < NB / 2; i += NT) s_cnt32[i] = 0u;    // the bucket counters share memory with s_slot
 
     // ------------------------------------------------------------ B: score range and histogram from a sample
     // The union size is the number of claimed keys.  Final score of a slot = accumulator (x popcount for CombMNZ).
@@ -588,12 +690,14 @@ __global__ void __launch_bounds__(NT, MINB) fuse_stream_kernel(const FuseParams 
     };
     // bucket counts; the atomicAdd's old value is the doc's offset inside its bucket
     u16 offs[SPT];
+    int pc = 0;
 #pragma unroll
     for (int k = 0; k < SPT; ++k) {
       const int slot = tid + k * NT;
       offs[k] = 0xFFFFu;
       if (slot < H && s_keys[slot] != EMPTY) {
         const u32 mt = s_meta[slot];
+        pc += __popc(mt & (skip_zero ? 0xFFu : 0xFFFFu));
         u32 tie = mt >> 16;
         if (want_pos) {      // first-seen sequence number -> first-seen index (same order, dense)
           tie = (u32)s_bpre[tie >> 5] + (u32)__popc(s_bitmap[tie >> 5] & ((1u << (tie & 31u)) - 1u));
@@ -610,6 +714,10 @@ __global__ void __launch_bounds__(NT, MINB) fuse_stream_kernel(const FuseParams 
         s_bcache[slot] = (u16)b;
         offs[k] = (u16)((oldc >> sh) & 0xFFFFu);
       }
+    }
+    {
+      const int wp = warp_sum_int(pc);
+      if (lane == 0) atomicAdd(&m.pc, wp);
     }
     __syncthreads();
     // exclusive scan of the NB 16-bit counters (CPT consecutive counters per thread), in place
@@ -637,8 +745,8 @@ __global__ void __launch_bounds__(NT, MINB) fuse_stream_kernel(const FuseParams 
         if (lane >= o) incl += t;
       }
       if (lane == 31) m.warp_tot[warp] = incl;
-      const int lng = __syncthreads_or(tmax > LONGB ? 1 : 0);
-      if (lng) {                                // long run of (nearly) tied scores: general kernel
+      const int lng = __syncthreads_or((tmax > LONGB || m.pc != n) ? 1 : 0);
+      if (lng) {                                // long run of (nearly) tied scores, or a doc id twice inside a list
         if (tid == 0) p.out_lens[q] = FUSE_DEFERRED;
         continue;
       }
