@@ -54,6 +54,13 @@ __device__ __forceinline__ u32 atoms_cas_if(bool pred, u32 sa, u32 cmp, u32 val,
                : "+r"(old) : "r"(sa), "r"(cmp), "r"(val), "r"((u32)pred) : "memory");
   return old;
 }
+// shared-memory add executed only where `pred` holds; elsewhere the result is `dflt`
+__device__ __forceinline__ u32 atoms_add_if(bool pred, u32 sa, u32 val, u32 dflt) {
+  u32 old = dflt;
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t@p atom.shared.add.u32 %0, [%1], %2;\n\t}"
+               : "+r"(old) : "r"(sa), "r"(val), "r"((u32)pred) : "memory");
+  return old;
+}
 __device__ __forceinline__ u32 atoms_add(u32 sa, u32 val) {
   u32 old;
   asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(sa), "r"(val) : "memory");
@@ -300,6 +307,60 @@ __global__ void __launch_bounds__(NT, MINB) fuse_stream_kernel(const FuseParams 
     // from different lists end up in the same slot.
     bool defer = false;
     int ins = 0;
+    // unresolved postings -> CTA queue (one shared-memory atomic per warp and chunk)
+    auto push_failed = [&](const bool (&fail)[4], u32 rowoff, int i0) {
+      unsigned bal[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bal[j] = __ballot_sync(0xffffffffu, fail[j]);
+      if (bal[0] | bal[1] | bal[2] | bal[3]) {
+        const int c0 = __popc(bal[0]), c1 = __popc(bal[1]), c2 = __popc(bal[2]), c3 = __popc(bal[3]);
+        u32 qb = 0;
+        if (lane == 0) qb = atoms_add(qn_sa, (u32)(c0 + c1 + c2 + c3));
+        qb = __shfl_sync(0xffffffffu, qb, 0);
+        const unsigned lt = (1u << lane) - 1u;
+        const u32 pre[4] = {qb, qb + (u32)c0, qb + (u32)(c0 + c1), qb + (u32)(c0 + c1 + c2)};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const u32 qp = pre[j] + (u32)__popc(bal[j] & lt);
+          if (fail[j] && qp < (u32)QCAP) s_queue[qp] = (u16)(rowoff + (u32)(vec ? i0 + j : i0 + j * NT));
+        }
+      }
+    };
+    auto store_slots = [&](const bool (&valid)[4], const u32 (&sl)[4], u32 rowoff, int i0) {
+      if (vec) {                                           // 4 consecutive u16 entries, 8-byte aligned
+        if (valid[0])
+          *reinterpret_cast<uint2*>(s_slot + rowoff + (u32)i0) = make_uint2(sl[0] | (sl[1] << 16), sl[2] | (sl[3] << 16));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (valid[j]) s_slot[rowoff + (u32)(i0 + j * NT)] = (u16)sl[j];
+      }
+    };
+    // The FIRST non-empty list meets an empty table and (barring a doc id that occurs twice in it) only new docs:
+    // no probing at all -- a per-group fill counter (kept in the group's first meta word, cleared afterwards) hands
+    // out the key positions 0..3, the rest of the group's postings are queued.  A doc id occurring twice would sit
+    // in its group twice: checked group by group after the list's barrier.
+    auto first4 = [&](const int (&id)[4], int r, int base, int len) {
+      const u32 rowoff = (u32)r * (u32)K;
+      const int i0 = vec ? base + tid * 4 : base + tid;
+      bool valid[4], fail[4];
+      u32 sl[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        valid[j] = (vec ? i0 + j : i0 + j * NT) < len;
+        defer |= valid[j] && (u32)id[j] == EMPTY;
+        const u32 g = __umulhi((u32)id[j] * 2654435761u, (u32)G);
+        const u32 c = atoms_add_if(valid[j], meta_sa + 16u * g, 1u, 4u);
+        const bool ok = c < 4u;
+        const u32 cand = 4u * g + c;
+        if (ok) s_keys[cand] = (u32)id[j];
+        ins += ok ? 1 : 0;
+        fail[j] = valid[j] && !ok;
+        sl[j] = ok ? cand : 0xFFFFu;
+      }
+      store_slots(valid, sl, rowoff, i0);
+      push_failed(fail, rowoff, i0);
+    };
     auto join4 = [&](const int (&id)[4], int r, int base, int len) {
       const u32 rowoff = (u32)r * (u32)K;
       const int i0 = vec ? base + tid * 4 : base + tid;
@@ -324,34 +385,12 @@ __global__ void __launch_bounds__(NT, MINB) fuse_stream_kernel(const FuseParams 
         fail[j] = valid[j] && !ok;
         sl[j] = ok ? cand : 0xFFFFu;
       }
-      if (vec) {                                           // 4 consecutive u16 entries, 8-byte aligned
-        if (valid[0])
-          *reinterpret_cast<uint2*>(s_slot + rowoff + (u32)i0) = make_uint2(sl[0] | (sl[1] << 16), sl[2] | (sl[3] << 16));
-      } else {
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (valid[j]) s_slot[rowoff + (u32)(i0 + j * NT)] = (u16)sl[j];
-      }
-      // unresolved postings -> CTA queue (one shared-memory atomic per warp and chunk)
-      unsigned bal[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) bal[j] = __ballot_sync(0xffffffffu, fail[j]);
-      if (bal[0] | bal[1] | bal[2] | bal[3]) {
-        const int c0 = __popc(bal[0]), c1 = __popc(bal[1]), c2 = __popc(bal[2]), c3 = __popc(bal[3]);
-        u32 qb = 0;
-        if (lane == 0) qb = atoms_add(qn_sa, (u32)(c0 + c1 + c2 + c3));
-        qb = __shfl_sync(0xffffffffu, qb, 0);
-        const unsigned lt = (1u << lane) - 1u;
-        const u32 pre[4] = {qb, qb + (u32)c0, qb + (u32)(c0 + c1), qb + (u32)(c0 + c1 + c2)};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const u32 qp = pre[j] + (u32)__popc(bal[j] & lt);
-          if (fail[j] && qp < (u32)QCAP) s_queue[qp] = (u16)(rowoff + (u32)(vec ? i0 + j : i0 + j * NT));
-        }
-      }
+      store_slots(valid, sl, rowoff, i0);
+      push_failed(fail, rowoff, i0);
     };
     {
-      int r = m.first, base = 0, len_r = m.len[r];        // n > 0: there is a non-empty list
+      const int r0 = m.first;
+      int r = r0, base = 0, len_r = m.len[r];             // n > 0: there is a non-empty list
       int cur[4] = {0, 0, 0, 0}, nxt[4] = {0, 0, 0, 0};
       load_ids(cur, r, base, len_r);
       while (r < R) {
@@ -362,7 +401,20 @@ __global__ void __launch_bounds__(NT, MINB) fuse_stream_kernel(const FuseParams 
           len2 = r2 < R ? m.len[r2] : 0;
         }
         if (r2 < R) load_ids(nxt, r2, b2, len2);
-        join4(cur, r, base, len_r);
+        if (r == r0) {
+          first4(cur, r, base, len_r);
+          if (r2 != r0) {                                  // first list complete: keys visible, counters cleared
+            __syncthreads();
+            for (int g = tid; g < G; g += NT) {
+              const uint4 k = reinterpret_cast<const uint4*>(s_keys)[g];
+              defer |= (k.x != EMPTY && (k.x == k.y || k.x == k.z || k.x == k.w)) ||
+                       (k.y != EMPTY && (k.y == k.z || k.y == k.w)) || (k.z != EMPTY && k.z == k.w);
+              s_meta[4 * g] = 0u;
+            }
+          }
+        } else {
+          join4(cur, r, base, len_r);
+        }
 #pragma unroll
         for (int j = 0; j < 4; ++j) cur[j] = nxt[j];
         r = r2;
@@ -781,6 +833,7 @@ __global__ void __launch_bounds__(NT, MINB) fuse_stream_kernel(const FuseParams 
         const int hi = (b + 1 < NB) ? (int)s_base16[b + 1] : n_u;
         int rank = lo;
         if (score_mode) {
+#pragma unroll 1
           for (int k = lo; k < hi; ++k) {
             const int s2 = s_order[k];
             const double f2 = s_acc[s2];
