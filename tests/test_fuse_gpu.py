@@ -301,3 +301,50 @@ def test_compact_fused_csr():
     ci, cs = cids.cpu().numpy(), csc.cpu().numpy()
     for q in range(300):
         assert np.array_equal(ci[off[q]:off[q + 1]], oi[q, :n[q]]) and np.array_equal(cs[off[q]:off[q + 1]], os_[q, :n[q]])
+
+
+def _same_group_ids(G, group, count, start=1):
+    """doc ids whose home group in a streaming-kernel table of G groups is `group` (hash of qf_fuse_stream.cu)."""
+    out, d = [], start
+    while len(out) < count:
+        if ((((d * 2654435761) & 0xFFFFFFFF) * G) >> 32) == group:
+            out.append(d)
+        d += 1
+    return out
+
+
+@pytest.mark.parametrize("k,groups", [(400, (768, 1280)), (100, (384,))])
+def test_duplicate_doc_ids_in_the_first_list(k, groups):
+    """The first non-empty list is inserted without probing (per-group fill counters); a doc id that occurs twice in
+    it must still end in the exact sequential path: both copies inside one group, one inside and one overflowed, both
+    overflowed (7 docs share a home group), and the same with a leading empty list."""
+    rng = np.random.default_rng(77)
+    base = synth_lists(31, n_q=8, n_r=3, k=k, pool=int(2.2 * k))
+    lists = []
+    for q, per_r in enumerate(base):
+        per_r = [list(rows) for rows in per_r]
+        G = groups[q % len(groups)]
+        crowd = _same_group_ids(G, 5 + q, 7, start=2_000_000)
+        rows0 = per_r[0]
+        variant = q % 4
+        if variant == 0:        # dup pair among the first four of the group
+            pick = [crowd[0], crowd[1], crowd[0], crowd[2], crowd[3], crowd[4], crowd[5]]
+        elif variant == 1:      # one copy inside the group, one overflowed
+            pick = [crowd[0], crowd[1], crowd[2], crowd[3], crowd[4], crowd[0], crowd[5]]
+        elif variant == 2:      # both copies overflowed
+            pick = [crowd[0], crowd[1], crowd[2], crowd[3], crowd[4], crowd[5], crowd[4]]
+        else:                   # crowded group without a duplicate, later lists hit the overflowed docs too
+            pick = crowd
+        at = sorted(rng.choice(len(rows0), size=len(pick), replace=False))
+        for i, d in zip(at, pick):
+            rows0[i] = (int(d), rows0[i][1], rows0[i][2])
+        for r in (1, 2):
+            j = int(rng.integers(0, len(per_r[r])))
+            per_r[r][j] = (int(crowd[4 + (r - 1)]), per_r[r][j][1], per_r[r][j][2])
+        if q >= 4:
+            per_r = [[]] + per_r[:2]                    # first list empty: list 1 takes the no-probe path
+        lists.append(per_r)
+    w = np.round(rng.random((len(lists), 3)), 6)
+    for method in ("sum", "mnz"):
+        out = run_gpu(lists, method, w, k=k)
+        check_against_oracle(lists, method, w, out)
