@@ -177,11 +177,14 @@ __global__ void __launch_bounds__(NT, MINB) fuse_stream_kernel(const FuseParams 
   const u32 qn_sa = (u32)__cvta_generic_to_shared(&m.qn);
 
   for (int q = blockIdx.x; q < p.Q; q += gridDim.x) {
-    __syncthreads();                       // previous query's shared state is dead
     // ------------------------------------------------------------ header + table reset
+    // warp 0 works the header out in registers BEFORE the barrier that retires the previous query
+    int h_l = 0, h_incl = 0;
+    double h_w = 1.0;
+    unsigned h_badm = 0u, h_nz = 0u;
     if (warp == 0) {
       const int len = pre_len;
-      const double wq = pre_w;
+      h_w = pre_w;
       {
         const long long qx = (long long)q + gridDim.x;
         if (lane < R && qx < p.Q) {
@@ -189,28 +192,29 @@ __global__ void __launch_bounds__(NT, MINB) fuse_stream_kernel(const FuseParams 
           if (weighted) pre_w = __ldg(p.weights + (size_t)qx * R + lane);
         }
       }
-      const unsigned badm = __ballot_sync(0xffffffffu, lane < R && (len < 0 || len > K));
-      const int l = badm ? 0 : len;
-      int incl = l;
+      h_badm = __ballot_sync(0xffffffffu, lane < R && (len < 0 || len > K));
+      h_l = h_badm ? 0 : len;
+      h_incl = h_l;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
+        const int t = __shfl_up_sync(0xffffffffu, h_incl, o);
+        if (lane >= o) h_incl += t;
       }
+      h_nz = __ballot_sync(0xffffffffu, lane < R && h_l > 0);
+    }
+    __syncthreads();                       // previous query's shared state is dead
+    if (warp == 0) {
       if (lane < R) {
-        m.start[lane] = incl - l;
-        m.len[lane] = l;
-        m.w[lane] = wq;
-      }
-      const unsigned nz = __ballot_sync(0xffffffffu, lane < R && l > 0);
-      if (lane < R) {
-        const unsigned rest = lane < 31 ? nz >> (lane + 1) : 0u;
+        m.start[lane] = h_incl - h_l;
+        m.len[lane] = h_l;
+        m.w[lane] = h_w;
+        const unsigned rest = lane < 31 ? h_nz >> (lane + 1) : 0u;
         m.next[lane] = rest ? lane + __ffs(rest) : R;
       }
-      if (lane == R - 1) m.start[R] = incl;
+      if (lane == R - 1) m.start[R] = h_incl;
       if (lane == 0) {
-        m.first = nz ? __ffs(nz) - 1 : R;
-        m.status = badm ? QF_QSTAT_BAD_LEN : 0;
+        m.first = h_nz ? __ffs(h_nz) - 1 : R;
+        m.status = h_badm ? QF_QSTAT_BAD_LEN : 0;
         m.qn = 0;
         m.ins_total = 0;
         m.pc = 0;
@@ -636,14 +640,13 @@ __global__ void __launch_bounds__(NT, MINB) fuse_stream_kernel(const FuseParams 
     };
     const int n_u = total_ins;
     double fmn = INFINITY, fmx = -INFINITY, samp = 0.0;
-    bool has = false;
-#pragma unroll 1
-    for (int k = 0; k < SPT && !has; ++k) {
-      const int slot = tid + k * NT;
-      if (slot < H && s_keys[slot] != EMPTY) {
-        samp = final_score(slot, s_meta[slot]);
-        has = true;
-      }
+    bool has;
+    {                                                       // sample: this thread's first occupied slot of two
+      static_assert(H >= 2 * NT, "two sample probes per thread");
+      const bool h0 = s_keys[tid] != EMPTY, h1 = s_keys[tid + NT] != EMPTY;
+      const int slot = h0 ? tid : tid + NT;
+      has = h0 | h1;
+      if (has) samp = final_score(slot, s_meta[slot]);
     }
     auto block_range = [&](double lo, double hi) {          // -> fmn / fmx over the block (one barrier)
       lo = warp_min(lo);
@@ -837,7 +840,8 @@ __global__ void __launch_bounds__(NT, MINB) fuse_stream_kernel(const FuseParams 
           for (int k = lo; k < hi; ++k) {
             const int s2 = s_order[k];
             const double f2 = s_acc[s2];
-            rank += (f2 > fs || (f2 == fs && (s_meta[s2] >> 16) < tie)) ? 1 : 0;
+            const u32 t2 = s_meta[s2] >> 16;                 // loaded unconditionally: no branch inside the loop
+            rank += (int)((f2 > fs) | ((f2 == fs) & (t2 < tie)));
           }
         } else {
           for (int k = lo; k < hi; ++k) rank += ((s_meta[s_order[k]] >> 16) < tie) ? 1 : 0;
