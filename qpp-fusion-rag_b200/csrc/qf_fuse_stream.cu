@@ -3,21 +3,25 @@
 //
 // Replaces ranx.fuse (reference src/fusion.py:182,201,226) and the weighted_* Python dict loops
 // (src/fusion.py:266-278, 309-327, 361-377); semantics in include/qppfusion.h.  Per query:
-//   A  lists are visited in ranker order, one barrier per list.  Each posting (16-byte loads, next chunk
-//      prefetched into registers) finds / claims its doc's slot of a bucketised open-addressing table: one 16-byte
-//      shared-memory load fetches the 4 keys of its home group, a match needs no atomic at all, a miss claims the
-//      first empty key with one atomicCAS (the table may run at ~80 % load with ~1.2 probes per posting, and every
-//      probe step ends in __syncwarp so diverged lanes reconverge).  It then marks list r in the slot's bit mask
-//      with one atomicOr (a second posting of the
-//      same doc in the same list sees the bit -> the query is deferred to the general kernel's exact sequential
-//      path) and adds its contribution to the slot's float64 accumulator with a plain read-modify-write: doc ids
-//      are distinct inside a list and lists are separated by barriers, so the additions happen in exactly the
-//      reference's order ((w0*s0 + w1*s1) + ...), no FMA contraction.  The claiming posting is the doc's FIRST-SEEN
-//      posting; its sequence number goes into the upper half of the mask word (tie-break key).
+//   A1 join, doc ids only: finding a doc's slot does not depend on the order of the postings, so every posting of
+//      every list (16-byte loads, next chunk prefetched into registers, no barrier between lists) finds / claims its
+//      doc's slot of a bucketised open-addressing table and records it in s_slot[r*K + i].  One 16-byte shared-memory
+//      load fetches the 4 keys of the home group, a match needs no atomic, a miss claims the first empty key with one
+//      predicated atomicCAS; a thread's four postings are resolved side by side in straight-line code.  Postings whose
+//      home group is full or whose claim was lost are queued and resolved once per query on dense lanes (probe loop
+//      uniform over the warp, per-doc odd stride).  The first non-empty list is inserted without probing through
+//      per-group fill counters.
+//   A2 accumulate, list by list (one barrier per list, no atomics): posting i of list r adds fl(w_r * s_i) to its
+//      slot's float64 accumulator with a plain read-modify-write -- doc ids are distinct inside a list and lists are
+//      separated by barriers, so the additions happen in exactly the reference's order ((w0*s0 + w1*s1) + ...), no
+//      FMA contraction.  The posting that finds the slot's list mask empty is the doc's FIRST-SEEN posting; its
+//      sequence number goes into the upper half of the meta word (tie-break key).  A doc id occurring twice inside a
+//      list shows up as a deficit in the sum of the mask popcounts -> the query is deferred to the general kernel's
+//      exact sequential path.
 //   B  final score (MNZ multiply by popcount, -0.0 -> +0.0), min/max over the union.
-//   C  ranking by ONE bucket pass instead of a multi-pass radix sort: a 64-bin histogram of a 1-in-16 sample
+//   C  ranking by ONE bucket pass instead of a multi-pass radix sort: a 64-bin histogram of a sample
 //      gives a monotone piecewise-linear map score -> bucket (histogram equalisation, so skewed score
-//      distributions still spread evenly over the 2048 buckets); shared-memory atomicAdd assigns a slot in the
+//      distributions still spread evenly over the buckets); shared-memory atomicAdd assigns a slot in the
 //      bucket, a block scan turns counts into bases, and each doc's exact rank is its bucket base plus the number
 //      of bucket mates that precede it under the exact comparison (score desc as float64, first-seen asc).
 //      Buckets longer than LONGB (long runs of exactly tied scores) defer the query.
