@@ -264,6 +264,47 @@ QF_API int    qf_dense_row_topk(const float* scores, long long ld, const int32_t
 QF_API int    qf_topk_merge(const float* scores, const int32_t* ids, int G, int Q, int k,
                             float* out_scores, int32_t* out_ids, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Query encoder  --  replaces SentenceTransformer(model).encode(queries, normalize_embeddings=True) behind
+ *                    BGERetriever._encode_queries (src/retrievers/bge.py:153-170): HF BertModel (post-LN encoder,
+ *                    exact erf GELU, LayerNorm eps in the config) + CLS pooling + L2 normalisation, which is what
+ *                    BAAI/bge-base-en-v1.5 (config/defaults.yaml:60-69) is.  Tokenisation stays on the host.
+ * ---------------------------------------------------------------------------------------------- */
+#define QF_BERT_POOL_CLS  0
+#define QF_BERT_POOL_MEAN 1   /* mean over the unpadded tokens (other sentence-transformers checkpoints) */
+
+typedef struct qf_bert_config {
+  int   n_layers;   /* 12 for bge-base */
+  int   hidden;     /* 768; envelope: 256, 512, 768 or 1024, head dimension 64 */
+  int   heads;      /* hidden / 64 */
+  int   ffn;        /* 3072 */
+  int   vocab;      /* 30522 */
+  int   max_pos;    /* 512 */
+  int   pooling;    /* QF_BERT_POOL_* */
+  float ln_eps;     /* 1e-12 */
+} qf_bert_config;
+
+/*
+ * Weights: ONE packed device blob of bf16 elements, tensors in this order, each row-major as PyTorch stores them:
+ *   word_embeddings [vocab, H], position_embeddings [max_pos, H], token_type_embeddings [2, H],
+ *   embeddings.LayerNorm weight [H], bias [H], then per layer:
+ *   W_qkv [3H, H] (query, key, value weights stacked), b_qkv [3H], W_o [H, H], b_o [H], LN1 weight [H], bias [H],
+ *   W_1 [ffn, H], b_1 [ffn], W_2 [H, ffn], b_2 [H], LN2 weight [H], bias [H].
+ * qf_bert_weight_elems returns the element count (0 for a config outside the envelope).
+ */
+QF_API size_t qf_bert_weight_elems(const qf_bert_config* cfg);
+QF_API size_t qf_bert_workspace_bytes(const qf_bert_config* cfg, int B, int L);
+/*
+ * tokens[B][L] int32 (padded with anything; positions >= lens[b] are masked as keys and never pooled), lens[B]
+ * (nullable = all L; clamped to [1, L]).  Outputs (either may be null): out_bf16[B][H] -- directly the `queries_bf16`
+ * of qf_dense_topk -- and out_f32[B][H], the L2-normalised embedding.  out_status[b] (nullable): bit 0 = a token id
+ * outside [0, vocab) (replaced by id 0, never read out of bounds).  bf16 activations, fp32 accumulation and
+ * statistics; the four Linear layers per block run through cuBLASLt, everything else is in csrc/qf_bert.cu.
+ */
+QF_API int    qf_bert_encode(const qf_bert_config* cfg, const void* weights_bf16, const int32_t* tokens,
+                             const int32_t* lens, int B, int L, void* out_bf16, float* out_f32, int32_t* out_status,
+                             void* ws, size_t ws_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,494 @@
+// qf_bert: BERT-base query encoder on the device -- the step right before the dense search
+// (reference: BGERetriever._encode_queries -> SentenceTransformer("BAAI/bge-base-en-v1.5").encode(...,
+// normalize_embeddings=True), src/retrievers/bge.py:153-170; model = HF BertModel + CLS pooling + L2 normalisation).
+//
+// Activations are bf16 [B*L, H] row-major (one row per token, padded to L tokens per query), statistics and
+// accumulation fp32.  The four Linear layers of a block are plain library GEMMs (cuBLASLt, bf16 in / fp32 accumulate,
+// bias in the epilogue); everything between them is hand-written and fused:
+//   embed_ln      word + position + type embedding -> LayerNorm                       (warp per token, 16-byte loads)
+//   attn          one CTA per (query, head): K/V of the head staged in shared memory, warp per query row,
+//                 masked softmax in registers, P.V through shuffles -- the [L, L] score matrix never leaves the SM
+//   add_ln        residual + LayerNorm                                                (warp per token)
+//   gelu          exact erf GELU in place (cuBLASLt's fused GELU is the tanh approximation, HF BERT uses erf)
+//   pool_norm     CLS (or masked mean) pooling + L2 normalisation -> bf16 queries for qf_dense_topk and/or fp32
+// Weights: ONE packed bf16 blob, layout in include/qppfusion.h (qf_bert_weight_elems).
+#include <cublasLt.h>
+#include <cuda_bf16.h>
+
+#include <mutex>
+#include <vector>
+
+#include "qf_common.cuh"
+
+namespace {
+
+using bf16 = __nv_bfloat16;
+
+struct Offsets {
+  size_t word, pos, type, eg, eb, layer0, per_layer, total;
+  // inside a layer
+  size_t wqkv, bqkv, wo, bo, g1, b1, w1, bi1, w2, bi2, g2, b2;
+};
+
+Offsets offsets(const qf_bert_config& c) {
+  Offsets o{};
+  const size_t H = c.hidden, F = c.ffn;
+  size_t a = 0;
+  o.word = a; a += (size_t)c.vocab * H;
+  o.pos = a;  a += (size_t)c.max_pos * H;
+  o.type = a; a += 2 * H;
+  o.eg = a;   a += H;
+  o.eb = a;   a += H;
+  o.layer0 = a;
+  size_t l = 0;
+  o.wqkv = l; l += 3 * H * H;
+  o.bqkv = l; l += 3 * H;
+  o.wo = l;   l += H * H;
+  o.bo = l;   l += H;
+  o.g1 = l;   l += H;
+  o.b1 = l;   l += H;
+  o.w1 = l;   l += F * H;
+  o.bi1 = l;  l += F;
+  o.w2 = l;   l += H * F;
+  o.bi2 = l;  l += H;
+  o.g2 = l;   l += H;
+  o.b2 = l;   l += H;
+  o.per_layer = l;
+  o.total = a + (size_t)c.n_layers * l;
+  return o;
+}
+
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+  const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __bfloat1622float2(p[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 v;
+  __nv_bfloat162* p = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) p[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return v;
+}
+__device__ __forceinline__ float wsum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float wmax(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// LayerNorm of one token row held as VPL 16-byte vectors per lane (H = 256 * VPL): HF BertLayerNorm = biased variance,
+// y = (x - mean) / sqrt(var + eps) * gamma + beta.
+template <int VPL>
+__device__ __forceinline__ void ln_store(float (&x)[VPL][8], const bf16* gamma, const bf16* beta, float eps, int H,
+                                         bf16* out_row, int lane) {
+  float s = 0.f;
+#pragma unroll
+  for (int v = 0; v < VPL; ++v)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += x[v][i];
+  const float mean = wsum(s) / (float)H;
+  float q = 0.f;
+#pragma unroll
+  for (int v = 0; v < VPL; ++v)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float d = x[v][i] - mean;
+      q += d * d;
+    }
+  const float rstd = rsqrtf(wsum(q) / (float)H + eps);
+#pragma unroll
+  for (int v = 0; v < VPL; ++v) {
+    const int col = (v * 32 + lane) * 8;
+    float g[8], b[8], y[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(gamma + col)), g);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(beta + col)), b);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) y[i] = (x[v][i] - mean) * rstd * g[i] + b[i];
+    *reinterpret_cast<uint4*>(out_row + col) = pack8(y);
+  }
+}
+
+template <int VPL>
+__global__ void __launch_bounds__(256) embed_ln_kernel(const int32_t* tokens, const bf16* word, const bf16* pos,
+                                                       const bf16* type, const bf16* gamma, const bf16* beta, float eps,
+                                                       bf16* out, long long M, int L, int V, int32_t* status) {
+  const int lane = threadIdx.x & 31;
+  const long long m = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (m >= M) return;
+  constexpr int H = 256 * VPL;
+  int tok = __ldg(tokens + m);
+  if (tok < 0 || tok >= V) {                       // never read outside the table; reported, not repaired silently
+    if (lane == 0 && status) atomicOr(status + m / L, 1);
+    tok = 0;
+  }
+  const int p = (int)(m % L);
+  float x[VPL][8];
+#pragma unroll
+  for (int v = 0; v < VPL; ++v) {
+    const int col = (v * 32 + lane) * 8;
+    float a[8], b[8], c[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(word + (size_t)tok * H + col)), a);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(pos + (size_t)p * H + col)), b);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(type + col)), c);      // token_type_ids = 0
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[v][i] = (a[i] + c[i]) + b[i];         // HF: inputs_embeds + token_type, then + position
+  }
+  ln_store<VPL>(x, gamma, beta, eps, H, out + (size_t)m * H, lane);
+}
+
+template <int VPL>
+__global__ void __launch_bounds__(256) add_ln_kernel(const bf16* x_in, const bf16* res, const bf16* gamma,
+                                                     const bf16* beta, float eps, bf16* out, long long M) {
+  const int lane = threadIdx.x & 31;
+  const long long m = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (m >= M) return;
+  constexpr int H = 256 * VPL;
+  float x[VPL][8];
+#pragma unroll
+  for (int v = 0; v < VPL; ++v) {
+    const int col = (v * 32 + lane) * 8;
+    float a[8], b[8];
+    unpack8(*reinterpret_cast<const uint4*>(x_in + (size_t)m * H + col), a);
+    unpack8(*reinterpret_cast<const uint4*>(res + (size_t)m * H + col), b);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[v][i] = a[i] + b[i];
+  }
+  ln_store<VPL>(x, gamma, beta, eps, H, out + (size_t)m * H, lane);
+}
+
+__global__ void __launch_bounds__(256) gelu_kernel(bf16* x, size_t n8) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
+    uint4* p = reinterpret_cast<uint4*>(x) + i;
+    float f[8];
+    unpack8(*p, f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f[k] = 0.5f * f[k] * (1.0f + erff(f[k] * 0.70710678118654752f));
+    *p = pack8(f);
+  }
+}
+
+// One CTA per (head, query): 4 warps, warp w owns query rows w, w+4, ...; lane l owns keys l, l+32, ... (TL per lane).
+constexpr int HD = 64;            // head dimension
+constexpr int KPAD = HD + 2;      // K row stride in bf16: 33 words -> lanes reading different rows hit different banks
+template <int TL>
+__global__ void __launch_bounds__(128) attn_kernel(const bf16* qkv, const int32_t* lens, bf16* ctx, int L, int H) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  bf16* sK = reinterpret_cast<bf16*>(smem_raw);                       // [L][KPAD]
+  bf16* sV = sK + (size_t)L * KPAD;                                    // [L][HD]
+  float* sQ = reinterpret_cast<float*>(sV + (size_t)L * HD);           // [4][HD]
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int len = lens ? __ldg(lens + b) : L;
+  len = len < 1 ? 1 : (len > L ? L : len);
+  const size_t row0 = (size_t)b * L;
+  const int H3 = 3 * H;
+  for (int i = tid; i < L * (HD / 2); i += 128) {                      // bf16 pairs
+    const int j = i / (HD / 2), d2 = i % (HD / 2);
+    const bf16* base = qkv + (row0 + j) * H3 + h * HD + 2 * d2;
+    *reinterpret_cast<__nv_bfloat162*>(sK + (size_t)j * KPAD + 2 * d2) = *reinterpret_cast<const __nv_bfloat162*>(base + H);
+    *reinterpret_cast<__nv_bfloat162*>(sV + (size_t)j * HD + 2 * d2) = *reinterpret_cast<const __nv_bfloat162*>(base + 2 * H);
+  }
+  __syncthreads();
+  float* q = sQ + warp * HD;
+  for (int i = warp; i < L; i += 4) {
+    __syncwarp();
+    {
+      const float2 t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(qkv + (row0 + i) * H3 + h * HD + 2 * lane));
+      q[2 * lane] = t.x * 0.125f;                                      // 1 / sqrt(64), exact in binary
+      q[2 * lane + 1] = t.y * 0.125f;
+    }
+    __syncwarp();
+    float s[TL];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int t = 0; t < TL; ++t) {
+      const int j = lane + 32 * t;
+      float a = -INFINITY;
+      if (j < len) {
+        a = 0.f;
+        const bf16* kr = sK + (size_t)j * KPAD;
+#pragma unroll
+        for (int d2 = 0; d2 < HD / 2; ++d2) {
+          const float2 kv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(kr + 2 * d2));
+          const float2 qv = *reinterpret_cast<const float2*>(q + 2 * d2);
+          a = fmaf(qv.x, kv.x, a);
+          a = fmaf(qv.y, kv.y, a);
+        }
+      }
+      s[t] = a;
+      mx = fmaxf(mx, a);
+    }
+    mx = wmax(mx);
+    float sum = 0.f;
+#pragma unroll
+    for (int t = 0; t < TL; ++t) {
+      s[t] = (lane + 32 * t < len) ? __expf(s[t] - mx) : 0.f;
+      sum += s[t];
+    }
+    const float inv = 1.0f / wsum(sum);
+    float o0 = 0.f, o1 = 0.f;
+#pragma unroll
+    for (int t = 0; t < TL; ++t) {
+      const int jn = min(32, len - 32 * t);                            // keys of this slice that are not masked
+      for (int jj = 0; jj < jn; ++jj) {
+        const float pj = __shfl_sync(0xffffffffu, s[t], jj);
+        const bf16* vr = sV + (size_t)(32 * t + jj) * HD;
+        o0 = fmaf(pj, __bfloat162float(vr[lane]), o0);
+        o1 = fmaf(pj, __bfloat162float(vr[lane + 32]), o1);
+      }
+    }
+    bf16* out = ctx + (row0 + i) * H + h * HD;
+    out[lane] = __float2bfloat16_rn(o0 * inv);
+    out[lane + 32] = __float2bfloat16_rn(o1 * inv);
+  }
+}
+
+template <int VPL>
+__global__ void __launch_bounds__(256) pool_norm_kernel(const bf16* x, const int32_t* lens, int L, int pooling,
+                                                        bf16* out_bf16, float* out_f32, int B) {
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (b >= B) return;
+  constexpr int H = 256 * VPL;
+  int len = lens ? __ldg(lens + b) : L;
+  len = len < 1 ? 1 : (len > L ? L : len);
+  float acc[VPL][8];
+#pragma unroll
+  for (int v = 0; v < VPL; ++v)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[v][i] = 0.f;
+  const int n_tok = pooling == QF_BERT_POOL_MEAN ? len : 1;
+  for (int t = 0; t < n_tok; ++t) {
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+      float f[8];
+      unpack8(*reinterpret_cast<const uint4*>(x + ((size_t)b * L + t) * H + (v * 32 + lane) * 8), f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[v][i] += f[i];
+    }
+  }
+  float ss = 0.f;
+#pragma unroll
+  for (int v = 0; v < VPL; ++v)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      acc[v][i] /= (float)n_tok;
+      ss += acc[v][i] * acc[v][i];
+    }
+  const float inv = 1.0f / fmaxf(sqrtf(wsum(ss)), 1e-12f);              // torch.nn.functional.normalize(eps=1e-12)
+#pragma unroll
+  for (int v = 0; v < VPL; ++v) {
+    const int col = (v * 32 + lane) * 8;
+    float y[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) y[i] = acc[v][i] * inv;
+    if (out_bf16) *reinterpret_cast<uint4*>(out_bf16 + (size_t)b * H + col) = pack8(y);
+    if (out_f32) {
+      float4* o = reinterpret_cast<float4*>(out_f32 + (size_t)b * H + col);
+      o[0] = make_float4(y[0], y[1], y[2], y[3]);
+      o[1] = make_float4(y[4], y[5], y[6], y[7]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ cuBLASLt plumbing
+constexpr size_t LT_WS = 32u << 20;
+
+struct Plan {
+  int dev;
+  long long M;
+  int N, K;
+  cublasLtMatmulDesc_t op;
+  cublasLtMatrixLayout_t a, b, c;
+  cublasLtMatmulAlgo_t algo;
+};
+std::mutex g_mu;
+cublasLtHandle_t g_lt[64] = {};
+std::vector<Plan> g_plans;
+
+#define QF_LT_TRY(expr)                                                                      \
+  do {                                                                                       \
+    cublasStatus_t _s = (expr);                                                              \
+    if (_s != CUBLAS_STATUS_SUCCESS) {                                                       \
+      qf::set_error("%s failed: cuBLASLt status %d (%s:%d)", #expr, (int)_s, __FILE__, __LINE__); \
+      return QF_E_CUDA;                                                                      \
+    }                                                                                        \
+  } while (0)
+
+// Y[M,N] = X[M,K] . W[N,K]^T + bias[N]   (row-major; as column-major: C[N,M] = op_T(A = W as [K,N]) . B = X as [K,M])
+int gemm_bias(const bf16* W, const bf16* X, const bf16* bias, bf16* Y, long long M, int N, int K, void* lt_ws,
+              cudaStream_t st) {
+  const int dev = qf::device_index();
+  Plan plan{};
+  bool found = false;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g_lt[dev]) QF_LT_TRY(cublasLtCreate(&g_lt[dev]));
+    for (const Plan& pl : g_plans)
+      if (pl.dev == dev && pl.M == M && pl.N == N && pl.K == K) {
+        plan = pl;
+        found = true;
+        break;
+      }
+    if (!found) {
+      plan.dev = dev; plan.M = M; plan.N = N; plan.K = K;
+      QF_LT_TRY(cublasLtMatmulDescCreate(&plan.op, CUBLAS_COMPUTE_32F, CUDA_R_32F));
+      const cublasOperation_t T = CUBLAS_OP_T, Nn = CUBLAS_OP_N;
+      QF_LT_TRY(cublasLtMatmulDescSetAttribute(plan.op, CUBLASLT_MATMUL_DESC_TRANSA, &T, sizeof(T)));
+      QF_LT_TRY(cublasLtMatmulDescSetAttribute(plan.op, CUBLASLT_MATMUL_DESC_TRANSB, &Nn, sizeof(Nn)));
+      const cublasLtEpilogue_t ep = CUBLASLT_EPILOGUE_BIAS;
+      QF_LT_TRY(cublasLtMatmulDescSetAttribute(plan.op, CUBLASLT_MATMUL_DESC_EPILOGUE, &ep, sizeof(ep)));
+      const cudaDataType_t bt = CUDA_R_16BF;
+      QF_LT_TRY(cublasLtMatmulDescSetAttribute(plan.op, CUBLASLT_MATMUL_DESC_BIAS_DATA_TYPE, &bt, sizeof(bt)));
+      QF_LT_TRY(cublasLtMatrixLayoutCreate(&plan.a, CUDA_R_16BF, K, N, K));
+      QF_LT_TRY(cublasLtMatrixLayoutCreate(&plan.b, CUDA_R_16BF, K, M, K));
+      QF_LT_TRY(cublasLtMatrixLayoutCreate(&plan.c, CUDA_R_16BF, N, M, N));
+      // the heuristic needs the bias pointer attribute to be set to something non-null for the epilogue it plans
+      QF_LT_TRY(cublasLtMatmulDescSetAttribute(plan.op, CUBLASLT_MATMUL_DESC_BIAS_POINTER, &bias, sizeof(bias)));
+      cublasLtMatmulPreference_t pref;
+      QF_LT_TRY(cublasLtMatmulPreferenceCreate(&pref));
+      QF_LT_TRY(cublasLtMatmulPreferenceSetAttribute(pref, CUBLASLT_MATMUL_PREF_MAX_WORKSPACE_BYTES, &LT_WS, sizeof(LT_WS)));
+      cublasLtMatmulHeuristicResult_t res{};
+      int n_res = 0;
+      const cublasStatus_t hs =
+          cublasLtMatmulAlgoGetHeuristic(g_lt[dev], plan.op, plan.a, plan.b, plan.c, plan.c, pref, 1, &res, &n_res);
+      cublasLtMatmulPreferenceDestroy(pref);
+      if (hs != CUBLAS_STATUS_SUCCESS || n_res == 0) {
+        qf::set_error("qf_bert_encode: no cuBLASLt algorithm for M=%lld N=%d K=%d (status %d)", M, N, K, (int)hs);
+        return QF_E_UNSUPPORTED;
+      }
+      plan.algo = res.algo;
+      g_plans.push_back(plan);
+    }
+    // the descriptor carries the bias pointer: set and launch under the lock (launches are asynchronous and short)
+    QF_LT_TRY(cublasLtMatmulDescSetAttribute(plan.op, CUBLASLT_MATMUL_DESC_BIAS_POINTER, &bias, sizeof(bias)));
+    const float one = 1.0f, zero = 0.0f;
+    QF_LT_TRY(cublasLtMatmul(g_lt[dev], plan.op, &one, W, plan.a, X, plan.b, &zero, Y, plan.c, Y, plan.c, &plan.algo,
+                             lt_ws, LT_WS, st));
+  }
+  return QF_OK;
+}
+
+size_t a256(size_t x) { return (x + 255) & ~size_t(255); }
+
+struct Ws {
+  size_t x, qkv, ctx, t1, ff, lt, total;
+};
+Ws ws_layout(const qf_bert_config& c, long long M) {
+  Ws w{};
+  size_t a = 0;
+  w.x = a;   a += a256((size_t)M * c.hidden * 2);
+  w.qkv = a; a += a256((size_t)M * c.hidden * 3 * 2);
+  w.ctx = a; a += a256((size_t)M * c.hidden * 2);
+  w.t1 = a;  a += a256((size_t)M * c.hidden * 2);
+  w.ff = a;  a += a256((size_t)M * c.ffn * 2);
+  w.lt = a;  a += LT_WS;
+  w.total = a;
+  return w;
+}
+
+int check_config(const qf_bert_config* c) {
+  QF_REQUIRE(c != nullptr, QF_E_INVALID, "qf_bert: null config");
+  QF_REQUIRE(c->n_layers >= 1 && c->vocab >= 1 && c->max_pos >= 1 && c->ffn >= 8 && c->ffn % 8 == 0, QF_E_INVALID,
+             "qf_bert: bad config (layers=%d vocab=%d max_pos=%d ffn=%d)", c->n_layers, c->vocab, c->max_pos, c->ffn);
+  QF_REQUIRE(c->hidden % 256 == 0 && c->hidden >= 256 && c->hidden <= 1024 && c->heads * HD == c->hidden,
+             QF_E_UNSUPPORTED, "qf_bert: hidden=%d heads=%d outside the envelope (hidden in {256,512,768,1024}, head dim 64)",
+             c->hidden, c->heads);
+  QF_REQUIRE(c->pooling == QF_BERT_POOL_CLS || c->pooling == QF_BERT_POOL_MEAN, QF_E_INVALID, "qf_bert: unknown pooling %d",
+             c->pooling);
+  return QF_OK;
+}
+
+template <int VPL>
+int encode_impl(const qf_bert_config& c, const bf16* wts, const int32_t* tokens, const int32_t* lens, int B, int L,
+                bf16* out_bf16, float* out_f32, int32_t* out_status, unsigned char* ws, cudaStream_t st) {
+  const long long M = (long long)B * L;
+  const Offsets o = offsets(c);
+  const Ws w = ws_layout(c, M);
+  bf16* X = reinterpret_cast<bf16*>(ws + w.x);
+  bf16* QKV = reinterpret_cast<bf16*>(ws + w.qkv);
+  bf16* CTX = reinterpret_cast<bf16*>(ws + w.ctx);
+  bf16* T1 = reinterpret_cast<bf16*>(ws + w.t1);
+  bf16* FF = reinterpret_cast<bf16*>(ws + w.ff);
+  void* lt_ws = ws + w.lt;
+  const int H = c.hidden, F = c.ffn;
+  const unsigned tok_blocks = (unsigned)((M + 7) / 8);
+  if (out_status) QF_CUDA_TRY(cudaMemsetAsync(out_status, 0, (size_t)B * sizeof(int32_t), st));
+  embed_ln_kernel<VPL><<<tok_blocks, 256, 0, st>>>(tokens, wts + o.word, wts + o.pos, wts + o.type, wts + o.eg,
+                                                   wts + o.eb, c.ln_eps, X, M, L, c.vocab, out_status);
+  QF_CUDA_TRY(cudaGetLastError());
+  const int tl = (L + 31) / 32;
+  const size_t attn_smem = (size_t)L * KPAD * 2 + (size_t)L * HD * 2 + 4 * HD * sizeof(float);
+  auto attn = tl <= 1 ? attn_kernel<1> : tl <= 2 ? attn_kernel<2> : tl <= 4 ? attn_kernel<4> : tl <= 8 ? attn_kernel<8> : attn_kernel<16>;
+  QF_CUDA_TRY(cudaFuncSetAttribute(attn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem));
+  for (int l = 0; l < c.n_layers; ++l) {
+    const bf16* lw = wts + o.layer0 + (size_t)l * o.per_layer;
+    int rc = gemm_bias(lw + o.wqkv, X, lw + o.bqkv, QKV, M, 3 * H, H, lt_ws, st);
+    if (rc != QF_OK) return rc;
+    attn<<<dim3((unsigned)c.heads, (unsigned)B), 128, attn_smem, st>>>(QKV, lens, CTX, L, H);
+    QF_CUDA_TRY(cudaGetLastError());
+    rc = gemm_bias(lw + o.wo, CTX, lw + o.bo, T1, M, H, H, lt_ws, st);
+    if (rc != QF_OK) return rc;
+    add_ln_kernel<VPL><<<tok_blocks, 256, 0, st>>>(T1, X, lw + o.g1, lw + o.b1, c.ln_eps, X, M);
+    QF_CUDA_TRY(cudaGetLastError());
+    rc = gemm_bias(lw + o.w1, X, lw + o.bi1, FF, M, F, H, lt_ws, st);
+    if (rc != QF_OK) return rc;
+    const size_t n8 = (size_t)M * F / 8;
+    const size_t gelu_cap = (size_t)qf::sm_count() * 16, gelu_need = (n8 + 255) / 256;
+    gelu_kernel<<<(unsigned)(gelu_need < gelu_cap ? gelu_need : gelu_cap), 256, 0, st>>>(FF, n8);
+    QF_CUDA_TRY(cudaGetLastError());
+    rc = gemm_bias(lw + o.w2, FF, lw + o.bi2, T1, M, H, F, lt_ws, st);
+    if (rc != QF_OK) return rc;
+    add_ln_kernel<VPL><<<tok_blocks, 256, 0, st>>>(T1, X, lw + o.g2, lw + o.b2, c.ln_eps, X, M);
+    QF_CUDA_TRY(cudaGetLastError());
+  }
+  pool_norm_kernel<VPL><<<(unsigned)((B + 7) / 8), 256, 0, st>>>(X, lens, L, c.pooling, out_bf16, out_f32, B);
+  QF_CUDA_TRY(cudaGetLastError());
+  return QF_OK;
+}
+
+}  // namespace
+
+extern "C" size_t qf_bert_weight_elems(const qf_bert_config* c) {
+  if (check_config(c) != QF_OK) return 0;
+  return offsets(*c).total;
+}
+
+extern "C" size_t qf_bert_workspace_bytes(const qf_bert_config* c, int B, int L) {
+  if (check_config(c) != QF_OK || B < 0 || L < 1) return 0;
+  return ws_layout(*c, (long long)B * L).total;
+}
+
+extern "C" int qf_bert_encode(const qf_bert_config* c, const void* weights_bf16, const int32_t* tokens,
+                              const int32_t* lens, int B, int L, void* out_bf16, float* out_f32, int32_t* out_status,
+                              void* ws, size_t ws_bytes, void* stream) {
+  int rc = check_config(c);
+  if (rc != QF_OK) return rc;
+  QF_REQUIRE(B >= 0 && L >= 1, QF_E_INVALID, "qf_bert_encode: bad sizes B=%d L=%d", B, L);
+  QF_REQUIRE(L <= c->max_pos && L <= 512, QF_E_UNSUPPORTED, "qf_bert_encode: L=%d exceeds max_pos=%d / 512", L, c->max_pos);
+  if (B == 0) return QF_OK;
+  QF_REQUIRE(weights_bf16 && tokens && ws && (out_bf16 || out_f32), QF_E_INVALID, "qf_bert_encode: null pointer argument");
+  QF_REQUIRE(ws_bytes >= ws_layout(*c, (long long)B * L).total, QF_E_WORKSPACE,
+             "qf_bert_encode: workspace %zu < %zu bytes", ws_bytes, ws_layout(*c, (long long)B * L).total);
+  rc = qf::check_device();
+  if (rc != QF_OK) return rc;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const bf16* w = reinterpret_cast<const bf16*>(weights_bf16);
+  bf16* ob = reinterpret_cast<bf16*>(out_bf16);
+  unsigned char* wsb = reinterpret_cast<unsigned char*>(ws);
+  switch (c->hidden / 256) {
+    case 1: return encode_impl<1>(*c, w, tokens, lens, B, L, ob, out_f32, out_status, wsb, st);
+    case 2: return encode_impl<2>(*c, w, tokens, lens, B, L, ob, out_f32, out_status, wsb, st);
+    case 3: return encode_impl<3>(*c, w, tokens, lens, B, L, ob, out_f32, out_status, wsb, st);
+    default: return encode_impl<4>(*c, w, tokens, lens, B, L, ob, out_f32, out_status, wsb, st);
+  }
+}

@@ -72,7 +72,18 @@ PROTOTYPES = {
     "qf_dense_scores": (_i, [_vp, _vp, _i, _i, _i, _vp, ctypes.c_longlong, _vp]),
     "qf_dense_row_topk": (_i, [_vp, ctypes.c_longlong, _vp, _i, _i, _i, ctypes.c_longlong, _vp, _vp, _vp, _vp]),
     "qf_topk_merge": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
+    "qf_bert_weight_elems": (_sz, [_vp]),
+    "qf_bert_workspace_bytes": (_sz, [_vp, _i, _i]),
+    "qf_bert_encode": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
 }
+
+BERT_POOL_CLS, BERT_POOL_MEAN = 0, 1
+
+
+class BertConfigC(ctypes.Structure):
+    """qf_bert_config (include/qppfusion.h)."""
+    _fields_ = [("n_layers", _i), ("hidden", _i), ("heads", _i), ("ffn", _i), ("vocab", _i), ("max_pos", _i),
+                ("pooling", _i), ("ln_eps", ctypes.c_float)]
 
 
 def lib() -> ctypes.CDLL:

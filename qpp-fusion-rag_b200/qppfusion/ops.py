@@ -302,3 +302,46 @@ def qpp_colnorm_apply_(vals: torch.Tensor, base: Optional[torch.Tensor], scale: 
         N.check(N.lib().qf_qpp_colnorm_apply(N.ptr(vals), Q, R, C, N.ptr(base), N.ptr(scale), 1 if round6 else 0,
                                              N.stream_ptr(dev)))
     return vals
+
+
+# ---------------------------------------------------------------------------------------------- query encoder
+@torch.library.custom_op("qppfusion::bert_encode", mutates_args=())
+def _bert_encode_op(weights: torch.Tensor, tokens: torch.Tensor, lens: torch.Tensor, n_layers: int, hidden: int,
+                    heads: int, ffn: int, vocab: int, max_pos: int, pooling: int, ln_eps: float
+                    ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    dev = N.require_cuda(weights, tokens, lens)
+    if weights.dtype != torch.bfloat16 or weights.dim() != 1:
+        raise TypeError("weights must be the packed bf16 blob (qppfusion.encoder.pack_bert_weights)")
+    if tokens.dtype != torch.int32 or tokens.dim() != 2 or lens.dtype != torch.int32 or lens.shape != (tokens.shape[0],):
+        raise TypeError("tokens int32 [B, L] and lens int32 [B] expected")
+    cfg = N.BertConfigC(n_layers, hidden, heads, ffn, vocab, max_pos, pooling, ln_eps)
+    cp = ctypes.addressof(cfg)
+    need = N.lib().qf_bert_weight_elems(cp)
+    if need == 0:
+        raise N.NativeError(-2, N.lib().qf_last_error().decode("utf-8", "replace"))
+    if weights.numel() != need:
+        raise ValueError(f"weight blob has {weights.numel()} elements, the config needs {need}")
+    B, L = tokens.shape
+    out_b = torch.empty((B, hidden), dtype=torch.bfloat16, device=dev)
+    out_f = torch.empty((B, hidden), dtype=torch.float32, device=dev)
+    status = torch.empty((B,), dtype=torch.int32, device=dev)
+    ws = torch.empty((max(N.lib().qf_bert_workspace_bytes(cp, B, L), 8),), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        N.check(N.lib().qf_bert_encode(cp, N.ptr(weights), N.ptr(tokens), N.ptr(lens), B, L, N.ptr(out_b), N.ptr(out_f),
+                                       N.ptr(status), N.ptr(ws), ws.numel(), N.stream_ptr(dev)))
+    return out_b, out_f, status
+
+
+@_bert_encode_op.register_fake
+def _(weights, tokens, lens, n_layers, hidden, heads, ffn, vocab, max_pos, pooling, ln_eps):
+    B = tokens.shape[0]
+    return (torch.empty((B, hidden), dtype=torch.bfloat16, device=tokens.device),
+            torch.empty((B, hidden), dtype=torch.float32, device=tokens.device),
+            torch.empty((B,), dtype=torch.int32, device=tokens.device))
+
+
+def bert_encode(weights: torch.Tensor, tokens: torch.Tensor, lens: torch.Tensor, *, n_layers: int, hidden: int, heads: int,
+                ffn: int, vocab: int, max_pos: int, pooling: int = N.BERT_POOL_CLS, ln_eps: float = 1e-12):
+    """-> (embeddings bf16 [B, H] -- the query operand of dense_topk, embeddings f32 [B, H], status int32 [B])."""
+    return torch.ops.qppfusion.bert_encode(weights, tokens, lens, int(n_layers), int(hidden), int(heads), int(ffn),
+                                           int(vocab), int(max_pos), int(pooling), float(ln_eps))

@@ -8,8 +8,10 @@ HBM as bf16 [N, 768] and one call scores the whole batch with the tcgen05 kernel
 qf_dense_topk (csrc/qf_dense.cu); per-GPU results are merged with an NCCL all-gather + qf_topk_merge
 when the corpus is row-sharded across ranks.
 
-Out of scope here: the SentenceTransformer query encoder (pass `encoder=`, any
-callable List[str] -> float32 [n, 768] with L2-normalised rows) and the approximate HNSW segments.
+Query encoder: `encoder=` takes any callable List[str] -> float32 [n, 768] with L2-normalised rows; `model_dir=`
+(a local bge-base-en-v1.5 checkpoint directory) builds the on-device BERT encoder (qppfusion.encoder ->
+qf_bert_encode), whose bf16 output feeds the search without a host round trip.  Out of scope:
+the approximate HNSW segments.
 """
 from __future__ import annotations
 
@@ -61,13 +63,14 @@ class BGERetriever(BaseRetriever):
                  use_mps: bool = True, ef_search: Optional[int] = None, *,
                  corpus_embeddings=None, docids: Optional[Sequence[str]] = None,
                  index_dir: Optional[str] = None, encoder: Optional[Callable[[List[str]], np.ndarray]] = None,
-                 id_offset: int = 0, process_group=None, **kwargs):
+                 model_dir: Optional[str] = None, id_offset: int = 0, process_group=None, **kwargs):
         """
         index_name / dataset / encoder_batch_size / use_mps / ef_search: reference signature
         (src/retrievers/bge.py:41-85); use_mps and ef_search have no meaning here.
         corpus_embeddings: float32/bf16 [N, 768] (numpy or torch) -- this rank's corpus rows.
         docids: the docno of each GLOBAL row (reference: the Pyserini `docid` file, one per line).
         index_dir: a Pyserini flat index directory holding `index` (FAISS IndexFlat) and `docid`.
+        encoder / model_dir: the query encoder (see the module docstring); model_dir is used when encoder is None.
         id_offset / process_group: row offset of this rank's shard and the NCCL group to merge over.
         """
         self.model_name = config.models.bge.name
@@ -93,6 +96,9 @@ class BGERetriever(BaseRetriever):
             raise FileNotFoundError("No index found: pass corpus_embeddings=/docids= or index_dir= "
                                     "(Pyserini flat index directory)")
         self.corpus = self.corpus_to_device(corpus_embeddings)
+        if self.encoder is None and model_dir is not None:
+            from ..encoder import BertQueryEncoder
+            self.encoder = BertQueryEncoder.from_pretrained(model_dir, device=self.device)
         self.docids = list(docids) if docids is not None else [str(i) for i in range(self.id_offset + self.corpus.shape[0])]
         print(f"[BGE] Total vectors on {self.device}: {self.corpus.shape[0]:,} (bf16, {self.corpus.numel() * 2 / 1e9:.2f} GB)")
 
@@ -118,6 +124,11 @@ class BGERetriever(BaseRetriever):
                                "BERT forward is outside this package's hot path)")
         return np.asarray(self.encoder(queries), dtype=np.float32)
 
+    def _encode_queries_device(self, queries: List[str]):
+        """bf16 rows on the device when the encoder can produce them (BertQueryEncoder), else the host array."""
+        enc = getattr(self.encoder, "encode_device", None)
+        return enc(queries) if enc is not None else self._encode_queries(queries)
+
     def _search_device(self, query_embs: torch.Tensor, top_k: int):
         if self.process_group is not None:
             from .. import distributed as qd
@@ -132,7 +143,10 @@ class BGERetriever(BaseRetriever):
     def _search_batch(self, query_embs: np.ndarray, top_k: int) -> Tuple[np.ndarray, np.ndarray]:
         """(ids int64 [n, k], scores float32 [n, k]) sorted by score descending, -1 ids when fewer than k hits
         -- note the (ids, scores) order, as the reference (src/retrievers/bge.py:191-194)."""
-        q = torch.from_numpy(np.ascontiguousarray(query_embs, dtype=np.float32)).to(self.device).to(torch.bfloat16)
+        if isinstance(query_embs, torch.Tensor):
+            q = query_embs.to(self.device).to(torch.bfloat16).contiguous()
+        else:
+            q = torch.from_numpy(np.ascontiguousarray(query_embs, dtype=np.float32)).to(self.device).to(torch.bfloat16)
         scores, ids = self._search_device(q, int(top_k))
         return ids.cpu().numpy().astype(np.int64), scores.cpu().numpy()
 
@@ -178,7 +192,7 @@ class BGERetriever(BaseRetriever):
             batch = pending[i:i + mini_batch_size]
             qids = [q[0] for q in batch]
             t0 = time.time()
-            query_embs = self._encode_queries([q[1] for q in batch])
+            query_embs = self._encode_queries_device([q[1] for q in batch])
             encode_time = time.time() - t0
             t0 = time.time()
             all_ids, all_scores = self._search_batch(query_embs, top_k)

@@ -1,0 +1,122 @@
+"""Query encoder on the GPU (qf_bert_encode through torch.ops.qppfusion.bert_encode and BertQueryEncoder) against
+the numpy oracle and the committed transformers.BertModel outputs.
+
+Tolerances (bf16 weights and activations, fp32 accumulation, against an fp32/float64 reference; rows are unit
+vectors): cosine >= 0.9995 and max |diff| <= 4e-3 for the 2-layer fixture, cosine >= 0.999 for the 12-layer
+BGE-base shape -- far below what moves a top-1000 ranking (the corpus itself is held in bf16)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from make_golden_bert import CFG, TEXTS, bert_small_state, synthetic_vocab
+from oracle import bert_oracle
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "bert_small.npz")
+
+
+def _encode(sd, cfg_hf, tokens, lens, pooling="cls"):
+    from qppfusion import ops
+    from qppfusion.encoder import BertConfig, pack_bert_weights
+    cfg = BertConfig.from_hf(cfg_hf, pooling)
+    dev = torch.device("cuda", 0)
+    blob = pack_bert_weights({k: torch.from_numpy(v) for k, v in sd.items()}, cfg).to(dev)
+    return ops.bert_encode(blob, torch.from_numpy(np.ascontiguousarray(tokens, dtype=np.int32)).to(dev),
+                           torch.from_numpy(np.ascontiguousarray(lens, dtype=np.int32)).to(dev), n_layers=cfg.n_layers,
+                           hidden=cfg.hidden, heads=cfg.heads, ffn=cfg.ffn, vocab=cfg.vocab, max_pos=cfg.max_pos,
+                           pooling=cfg.pooling_id, ln_eps=cfg.ln_eps)
+
+
+@pytest.mark.parametrize("pooling", ["cls", "mean"])
+def test_small_model_matches_golden_bertmodel(pooling):
+    g = np.load(GOLD)
+    out_b, out_f, status = _encode(bert_small_state(), CFG, g["tokens"], g["lens"], pooling)
+    got = out_f.double().cpu().numpy()
+    assert int(status.max().item()) == 0
+    assert ((got * g[pooling]).sum(1) >= 0.9995).all()
+    assert np.abs(got - g[pooling]).max() <= 4e-3
+    np.testing.assert_allclose(np.linalg.norm(got, axis=1), 1.0, atol=1e-5)
+    # the bf16 rows handed to the dense search are the rounded fp32 rows
+    assert torch.equal(out_b, out_f.to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("hidden,heads,L", [(256, 4, 8), (512, 8, 40), (768, 12, 64), (1024, 16, 24), (256, 4, 160)])
+def test_shapes_against_oracle(hidden, heads, L):
+    cfg = dict(CFG, hidden_size=hidden, num_attention_heads=heads, intermediate_size=2 * hidden, num_hidden_layers=2,
+               max_position_embeddings=max(64, L))
+    sd = bert_small_state(seed=hidden + L, cfg=cfg)
+    rng = np.random.default_rng(L)
+    B = 9
+    tokens = rng.integers(0, cfg["vocab_size"], size=(B, L))
+    lens = rng.integers(1, L + 1, size=B)
+    lens[0], lens[1] = L, 1
+    sd_bf = {k: bert_oracle._bf16_round(v) for k, v in sd.items()}
+    ref = bert_oracle.bert_encode(sd_bf, tokens, lens, n_layers=2, heads=heads)
+    _, out_f, status = _encode(sd, cfg, tokens, lens)
+    got = out_f.double().cpu().numpy()
+    assert int(status.max().item()) == 0
+    assert ((got * ref).sum(1) >= 0.9995).all()
+    assert np.abs(got - ref).max() <= 4e-3
+
+
+def test_padding_and_batch_independence():
+    g = np.load(GOLD)
+    sd = bert_small_state()
+    _, a, _ = _encode(sd, CFG, g["tokens"], g["lens"])
+    junk = np.pad(g["tokens"], ((0, 0), (0, 16)), constant_values=77)
+    _, b, _ = _encode(sd, CFG, junk, g["lens"])
+    assert (a - b).abs().max().item() <= 2e-3             # masked keys contribute nothing (other L: other GEMM algorithm)
+    _, c, _ = _encode(sd, CFG, g["tokens"][2:3], g["lens"][2:3])
+    assert (a[2:3] - c).abs().max().item() <= 2e-3        # cuBLASLt may pick another algorithm for another M
+
+
+def test_bad_token_is_reported_not_read():
+    g = np.load(GOLD)
+    toks = g["tokens"].copy()
+    toks[3, 2] = CFG["vocab_size"] + 5
+    toks[4, 0] = -1
+    _, _, status = _encode(bert_small_state(), CFG, toks, g["lens"])
+    assert status.cpu().tolist() == [0, 0, 0, 1, 1, 0]
+
+
+def test_bge_base_shape_against_oracle():
+    base = dict(vocab_size=30522, hidden_size=768, num_hidden_layers=12, num_attention_heads=12, intermediate_size=3072,
+                max_position_embeddings=512)
+    sd = bert_small_state(seed=42, cfg=base)
+    rng = np.random.default_rng(1)
+    B, L = 70, 32
+    tokens = rng.integers(0, base["vocab_size"], size=(B, L))
+    lens = np.clip(rng.poisson(11, size=B) + 3, 3, L)
+    _, out_f, status = _encode(sd, base, tokens, lens)
+    n = 6
+    ref = bert_oracle.bert_encode(sd, tokens[:n], lens[:n], n_layers=12, heads=12)     # fp32 weights, float64 math
+    got = out_f[:n].double().cpu().numpy()
+    assert int(status.max().item()) == 0
+    assert ((got * ref).sum(1) >= 0.999).all(), (got * ref).sum(1)
+
+
+def test_query_encoder_end_to_end_into_dense_search():
+    """Strings -> host WordPiece -> device BERT -> bf16 rows -> tcgen05 flat search, through BGERetriever."""
+    from qppfusion.encoder import BertConfig, BertQueryEncoder, WordPieceTokenizer
+    from qppfusion.retrievers.bge import BGERetriever
+    vocab = {t: i for i, t in enumerate(synthetic_vocab())}
+    cfg_hf = dict(CFG, hidden_size=768, num_attention_heads=12, intermediate_size=1024, vocab_size=len(vocab))
+    sd = bert_small_state(seed=9, cfg=cfg_hf)
+    enc = BertQueryEncoder({k: torch.from_numpy(v) for k, v in sd.items()}, BertConfig.from_hf(cfg_hf),
+                           WordPieceTokenizer(vocab, max_length=64), batch_size=3)
+    emb = enc(TEXTS)
+    assert emb.shape == (len(TEXTS), 768) and emb.dtype == np.float32
+    tok = enc.tokenizer
+    toks, lens = tok.batch(TEXTS)
+    ref = bert_oracle.bert_encode({k: bert_oracle._bf16_round(v) for k, v in sd.items()}, toks, lens, n_layers=2, heads=12)
+    assert ((emb.astype(np.float64) * ref).sum(1) >= 0.9995).all()
+    rng = np.random.default_rng(0)
+    corpus = rng.standard_normal((5000, 768)).astype(np.float32)
+    corpus /= np.linalg.norm(corpus, axis=1, keepdims=True)
+    corpus[1234] = emb[0]
+    r = BGERetriever(corpus_embeddings=corpus, encoder=enc)
+    res = r.retrieve_batch({f"q{i}": t for i, t in enumerate(TEXTS)}, top_k=10)
+    assert res["q0"].results[0][0] == "1234" and abs(res["q0"].results[0][1] - 1.0) < 1e-2
+    assert all(len(v.results) == 10 for v in res.values())

@@ -1,0 +1,122 @@
+"""Query encoder, CPU side: the numpy oracle (oracle/bert_oracle.py) against the committed outputs of the real
+transformers.BertModel (tests/golden/bert_small.npz, tools/make_golden_bert.py) and against a live BertModel when
+transformers is importable; the host tokeniser (qppfusion.encoder.WordPieceTokenizer) against the token ids the real
+transformers.BertTokenizer produced; the weight packer's layout and error behaviour."""
+import os
+
+import numpy as np
+import pytest
+
+from make_golden_bert import CFG, TEXTS, bert_small_state, synthetic_vocab
+from oracle import bert_oracle
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "bert_small.npz")
+
+
+def test_oracle_matches_golden_bertmodel_outputs():
+    g = np.load(GOLD)
+    sd = bert_small_state()
+    for pooling in ("cls", "mean"):
+        got = bert_oracle.bert_encode(sd, g["tokens"], g["lens"], n_layers=CFG["num_hidden_layers"],
+                                      heads=CFG["num_attention_heads"], pooling=pooling)
+        # the golden rows are float32 torch outputs: 2e-6 absolute on unit vectors is fp32 round-off over 2 layers
+        np.testing.assert_allclose(got, g[pooling], atol=2e-6, rtol=0)
+        np.testing.assert_allclose(np.linalg.norm(got, axis=1), 1.0, atol=1e-12)
+
+
+def test_oracle_matches_live_bertmodel():
+    torch = pytest.importorskip("torch")
+    tr = pytest.importorskip("transformers")
+    cfg = dict(CFG, num_hidden_layers=3, hidden_size=512, num_attention_heads=8, intermediate_size=1024)
+    sd = bert_small_state(seed=5, cfg=cfg)
+    model = tr.BertModel(tr.BertConfig(**cfg), add_pooling_layer=False).eval()
+    model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=False)
+    rng = np.random.default_rng(11)
+    tokens = rng.integers(0, cfg["vocab_size"], size=(5, 40))
+    lens = np.array([40, 3, 17, 33, 1])
+    mask = torch.from_numpy((np.arange(40)[None, :] < lens[:, None]).astype(np.int64))
+    with torch.no_grad():
+        hid = model(input_ids=torch.from_numpy(tokens), attention_mask=mask).last_hidden_state
+    ref = torch.nn.functional.normalize(hid[:, 0], p=2, dim=1).numpy()
+    got = bert_oracle.bert_encode(sd, tokens, lens, n_layers=3, heads=8)
+    np.testing.assert_allclose(got, ref, atol=3e-6, rtol=0)
+    # padding never leaks: the same rows padded to another length give the same embedding
+    got2 = bert_oracle.bert_encode(sd, np.pad(tokens, ((0, 0), (0, 8))), lens, n_layers=3, heads=8)
+    np.testing.assert_allclose(got2, got, atol=1e-12)
+
+
+def test_bf16_emulation_rounding():
+    x = np.array([1.0, 1.00390625, 1.01171875, -3.1415927, 0.0], dtype=np.float32)
+    torch = pytest.importorskip("torch")
+    want = torch.from_numpy(x).to(torch.bfloat16).to(torch.float32).numpy()
+    np.testing.assert_array_equal(bert_oracle._bf16_round(x), want)
+
+
+def test_tokenizer_matches_real_berttokenizer_ids():
+    from qppfusion.encoder import WordPieceTokenizer
+    g = np.load(GOLD)
+    tok = WordPieceTokenizer({t: i for i, t in enumerate(synthetic_vocab())}, max_length=32)
+    for i, text in enumerate(TEXTS):
+        want = g["tok_flat"][g["tok_offs"][i]:g["tok_offs"][i + 1]].tolist()
+        assert tok.encode(text) == want, text
+    toks, lens = tok.batch(TEXTS)
+    assert toks.shape[1] % 8 == 0 and toks.dtype == np.int32 and lens.tolist() == np.diff(g["tok_offs"]).tolist()
+    assert (toks[5, 2:] == tok.pad_id).all() and toks[5, 0] == tok.cls_id and toks[5, 1] == tok.sep_id
+    long = WordPieceTokenizer(tok.vocab, max_length=16).encode("what is the capital of france " * 10)
+    assert len(long) == 16 and long[0] == tok.cls_id and long[-1] == tok.sep_id
+
+
+def test_tokenizer_matches_live_berttokenizer(tmp_path):
+    tr = pytest.importorskip("transformers")
+    from qppfusion.encoder import WordPieceTokenizer
+    vp = tmp_path / "vocab.txt"
+    vp.write_text("\n".join(synthetic_vocab()) + "\n", encoding="utf-8")
+    real = tr.BertTokenizer(str(vp), do_lower_case=True)
+    mine = WordPieceTokenizer(vp, max_length=48)
+    rng = np.random.default_rng(3)
+    alphabet = list("abcdefghij  \t!?'-.,éÉñ$5京") + ["what", "capital", "unbelievably", "resume", "Hamlet", " "]
+    for _ in range(200):
+        text = "".join(rng.choice(alphabet, size=int(rng.integers(0, 40))))
+        assert mine.encode(text) == real(text, truncation=True, max_length=48)["input_ids"], repr(text)
+
+
+def test_pack_weights_layout_and_errors():
+    torch = pytest.importorskip("torch")
+    from qppfusion.encoder import BertConfig, pack_bert_weights
+    sd = {k: torch.from_numpy(v) for k, v in bert_small_state().items()}
+    cfg = BertConfig.from_hf(dict(CFG, layer_norm_eps=1e-12, hidden_act="gelu"))
+    blob = pack_bert_weights(sd, cfg)
+    H, F, V, P = cfg.hidden, cfg.ffn, cfg.vocab, cfg.max_pos
+    per_layer = 4 * H * H + 2 * F * H + 9 * H + F
+    assert blob.dtype == torch.bfloat16 and blob.numel() == (V + P + 2) * H + 2 * H + cfg.n_layers * per_layer
+    o = (V + P + 2) * H + 2 * H
+    assert torch.equal(blob[o + H * H:o + 2 * H * H].float().reshape(H, H),
+                       sd["encoder.layer.0.attention.self.key.weight"].to(torch.bfloat16).float())
+    assert torch.equal(blob[o + 3 * H * H + H:o + 3 * H * H + 2 * H].float(),
+                       sd["encoder.layer.0.attention.self.key.bias"].to(torch.bfloat16).float())
+    # a 'bert.'-prefixed dict packs the same; a missing or mis-shaped tensor raises
+    assert torch.equal(pack_bert_weights({"bert." + k: v for k, v in sd.items()}, cfg), blob)
+    bad = dict(sd)
+    del bad["encoder.layer.1.output.dense.bias"]
+    with pytest.raises(KeyError):
+        pack_bert_weights(bad, cfg)
+    bad = dict(sd)
+    bad["embeddings.LayerNorm.weight"] = torch.zeros(H + 1)
+    with pytest.raises(ValueError):
+        pack_bert_weights(bad, cfg)
+    with pytest.raises(ValueError):
+        BertConfig.from_hf(dict(CFG, hidden_act="relu"))
+
+
+def test_encoder_fails_loudly_without_gpu():
+    torch = pytest.importorskip("torch")
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from qppfusion import ops
+    from qppfusion.encoder import BertConfig, BertQueryEncoder, WordPieceTokenizer
+    sd = {k: torch.from_numpy(v) for k, v in bert_small_state().items()}
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        BertQueryEncoder(sd, BertConfig.from_hf(CFG), WordPieceTokenizer({t: i for i, t in enumerate(synthetic_vocab())}))
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):
+        ops.bert_encode(torch.zeros(8, dtype=torch.bfloat16), torch.zeros((1, 8), dtype=torch.int32),
+                        torch.ones(1, dtype=torch.int32), n_layers=1, hidden=256, heads=4, ffn=512, vocab=10, max_pos=8)
