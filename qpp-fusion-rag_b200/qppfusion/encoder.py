@@ -195,7 +195,7 @@ class BertQueryEncoder:
     and what the reference's `self.encoder.encode(..., normalize_embeddings=True)` returns."""
 
     def __init__(self, state_dict: Mapping[str, torch.Tensor], cfg: BertConfig, tokenizer: WordPieceTokenizer,
-                 device: Optional[torch.device] = None, batch_size: int = 4096):
+                 device: Optional[torch.device] = None, batch_size: int = 8192):
         if not torch.cuda.is_available():
             raise RuntimeError("BertQueryEncoder needs a CUDA (sm_100) device: there is no CPU fallback")
         self.cfg = cfg
@@ -235,33 +235,57 @@ class BertQueryEncoder:
             raise FileNotFoundError(f"No model.safetensors / pytorch_model.bin under {d}")
         return cls(sd, BertConfig.from_hf(hf, pooling), WordPieceTokenizer(d / "vocab.txt", lower, max_len), **kwargs)
 
-    def encode_tokens(self, tokens: torch.Tensor, lens: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    def encode_tokens(self, tokens: torch.Tensor, lens: torch.Tensor, _status_out: Optional[list] = None
+                      ) -> Tuple[torch.Tensor, torch.Tensor]:
         """tokens int32 [n, L], lens int32 [n] on the device -> (bf16 [n, H], float32 [n, H]); raises on a token id
         outside the vocabulary."""
         c = self.cfg
         out_b, out_f, status = ops.bert_encode(self.weights, tokens, lens, n_layers=c.n_layers, hidden=c.hidden,
                                                heads=c.heads, ffn=c.ffn, vocab=c.vocab, max_pos=c.max_pos,
                                                pooling=c.pooling_id, ln_eps=c.ln_eps)
-        if int(status.max().item()) != 0:
+        if _status_out is not None:                     # the caller checks all its calls with one host sync
+            _status_out.append(status)
+        elif int(status.max().item()) != 0:
             bad = torch.nonzero(status).flatten()[:5].tolist()
             raise ValueError(f"token id outside [0, {c.vocab}) in rows {bad}")
         return out_b, out_f
 
-    def _encode(self, queries: Sequence[str]) -> Tuple[torch.Tensor, torch.Tensor]:
-        queries = list(queries)
-        H = self.cfg.hidden
-        out_b = torch.empty((len(queries), H), dtype=torch.bfloat16, device=self.device)
-        out_f = torch.empty((len(queries), H), dtype=torch.float32, device=self.device)
-        # longest first, as sentence-transformers batches: rows of one batch pad to similar lengths
-        order = sorted(range(len(queries)), key=lambda i: -len(queries[i]))
-        for s in range(0, len(order), self.batch_size):
-            idx = order[s:s + self.batch_size]
-            toks, lens = self.tokenizer.batch([queries[i] for i in idx])
-            b, f = self.encode_tokens(torch.from_numpy(toks).to(self.device), torch.from_numpy(lens).to(self.device))
-            ix = torch.tensor(idx, dtype=torch.long, device=self.device)
-            out_b[ix] = b
-            out_f[ix] = f
+    def encode_token_lists(self, rows: Sequence[Sequence[int]], bucket: int = 8) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Token id rows ([CLS] ... [SEP] included) -> (bf16 [n, H], float32 [n, H]) on the device.
+        Rows are grouped by their length rounded up to `bucket` tokens and each group is one qf_bert_encode call
+        padded only to its own length: a query batch whose lengths spread from 5 to 32 tokens spends its GEMM
+        rows on real tokens instead of on padding up to the longest query (sentence-transformers sorts by length
+        for the same reason).  Groups are further cut at `batch_size` queries."""
+        n, H = len(rows), self.cfg.hidden
+        out_b = torch.empty((n, H), dtype=torch.bfloat16, device=self.device)
+        out_f = torch.empty((n, H), dtype=torch.float32, device=self.device)
+        if n == 0:
+            return out_b, out_f
+        lens = np.fromiter((len(r) for r in rows), dtype=np.int64, count=n)
+        if lens.min() < 1 or lens.max() > self.cfg.max_pos:
+            raise ValueError(f"row lengths must lie in [1, {self.cfg.max_pos}]")
+        padded = np.minimum(-(-lens // bucket) * bucket, self.cfg.max_pos)
+        order = np.argsort(padded, kind="stable")
+        statuses: list = []
+        bounds = np.flatnonzero(np.diff(padded[order])) + 1
+        for grp in np.split(order, bounds):
+            L = int(padded[grp[0]])
+            for s in range(0, len(grp), self.batch_size):
+                idx = grp[s:s + self.batch_size]
+                toks = np.full((len(idx), L), self.tokenizer.pad_id if self.tokenizer is not None else 0, dtype=np.int32)
+                for j, i in enumerate(idx):
+                    toks[j, : lens[i]] = rows[i]
+                b, f = self.encode_tokens(torch.from_numpy(toks).to(self.device, non_blocking=True),
+                                          torch.from_numpy(lens[idx].astype(np.int32)).to(self.device, non_blocking=True), statuses)
+                ix = torch.from_numpy(idx).to(self.device)
+                out_b[ix] = b
+                out_f[ix] = f
+        if int(torch.stack([st.max() for st in statuses]).max().item()) != 0:
+            raise ValueError(f"token id outside [0, {self.cfg.vocab}) in the batch")
         return out_b, out_f
+
+    def _encode(self, queries: Sequence[str]) -> Tuple[torch.Tensor, torch.Tensor]:
+        return self.encode_token_lists([self.tokenizer.encode(q) for q in queries])
 
     def encode_device(self, queries: Sequence[str]) -> torch.Tensor:
         """bf16 [n, H] on the device: the `queries` operand of ops.dense_topk."""

@@ -6,6 +6,7 @@ libqppfusion's hand-written sm_100a kernels) and calls the matching qf_* entry p
 """
 from __future__ import annotations
 
+import ctypes
 from typing import NamedTuple, Optional, Tuple
 
 import torch
