@@ -6,8 +6,10 @@
 // accumulation fp32.  The four Linear layers of a block are plain library GEMMs (cuBLASLt, bf16 in / fp32 accumulate,
 // bias in the epilogue); everything between them is hand-written and fused:
 //   embed_ln      word + position + type embedding -> LayerNorm                       (warp per token, 16-byte loads)
-//   attn          one CTA per (query, head): K/V of the head staged in shared memory, warp per query row,
-//                 masked softmax in registers, P.V through shuffles -- the [L, L] score matrix never leaves the SM
+//   attn          L <= 128: one WARP per (query, head) on mma.sync tiles, K/V staged in the warp's shared-memory slice,
+//                 masked softmax on the accumulator fragments, which then ARE the A operand of P.V;
+//                 longer sequences: one CTA per (query, head), warp per query row, P.V through shuffles.
+//                 Either way the [L, L] score matrix never leaves the SM and padded query rows are not computed
 //   add_ln        residual + LayerNorm                                                (warp per token)
 //   gelu          exact erf GELU in place (cuBLASLt's fused GELU is the tanh approximation, HF BERT uses erf)
 //   pool_norm     CLS (or masked mean) pooling + L2 normalisation -> bf16 queries for qf_dense_topk and/or fp32
@@ -200,6 +202,11 @@ __global__ void __launch_bounds__(128) attn_kernel(const bf16* qkv, const int32_
   __syncthreads();
   float* q = sQ + warp * HD;
   for (int i = warp; i < L; i += 4) {
+    if (i >= len) {                                                    // padding token: never read by a real one
+      bf16* out = ctx + (row0 + i) * H + h * HD;
+      out[lane] = out[lane + 32] = __float2bfloat16_rn(0.f);
+      continue;
+    }
     __syncwarp();
     {
       const float2 t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(qkv + (row0 + i) * H3 + h * HD + 2 * lane));
@@ -250,6 +257,149 @@ __global__ void __launch_bounds__(128) attn_kernel(const bf16* qkv, const int32_
     out[lane] = __float2bfloat16_rn(o0 * inv);
     out[lane + 32] = __float2bfloat16_rn(o1 * inv);
   }
+}
+
+// Tensor-core attention for query-length sequences (L <= 128): ONE WARP per (query, head), no CTA-wide barrier.
+// K and V of the head are staged in the warp's own shared-memory slice (16-byte loads, rows padded to 72 bf16 so both the
+// 32-bit B-fragment reads of K and the transposing ldmatrix of V are bank-conflict free); Q fragments come straight from
+// global memory.  S = Q.K^T and O = P.V run on mma.sync.m16n8k16 (bf16 in, fp32 accumulate): a 32 x 32 x 64 head is far
+// below one tcgen05 tile (M = 128), and the kernel is bound by the QKV read, not by the tensor pipe.  The S accumulators
+// of two adjacent key tiles ARE the A fragment of the P.V product, so the probabilities never leave registers.
+// Query rows >= len (padding) are not computed: their context rows are written as zeros, and V rows >= len are staged
+// as zeros so that 0 x (whatever the padded tokens hold) can never reach a real token.
+constexpr int VSTR = HD + 8;      // staged row stride in bf16 (144 bytes)
+
+__device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
+
+template <int LT>   // L rounded up to 32, 64 or 128
+__global__ void __launch_bounds__(128) attn_mma_kernel(const bf16* __restrict__ qkv, const int32_t* __restrict__ lens,
+                                                       bf16* __restrict__ ctx, int L, int H) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int NT = LT / 8;                                            // key tiles of 8
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int h = blockIdx.x * 4 + warp, b = blockIdx.y;
+  bf16* sK = reinterpret_cast<bf16*>(smem_raw) + (size_t)warp * 2 * LT * VSTR;
+  bf16* sV = sK + (size_t)LT * VSTR;
+  int len = lens ? __ldg(lens + b) : L;
+  len = len < 1 ? 1 : (len > L ? L : len);
+  const size_t row0 = (size_t)b * L;
+  const int H3 = 3 * H;
+  const int kt_n = (len + 7) >> 3;                                      // key tiles that hold a real key
+  const int kt16 = (len + 15) >> 4;                                     // the same in steps of 16 (k steps of P.V)
+  {                                                                     // stage K, V rows [0, 16 * kt16)
+    const int c8 = lane & 7, r4 = lane >> 3;                            // 8 lanes x 16 bytes = one 64-element row
+    for (int j = r4; j < kt16 * 16; j += 4) {
+      uint4 kv = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
+      if (j < len) {
+        const bf16* base = qkv + (row0 + j) * H3 + h * HD + c8 * 8;
+        kv = __ldg(reinterpret_cast<const uint4*>(base + H));
+        vv = __ldg(reinterpret_cast<const uint4*>(base + 2 * H));
+      }
+      *reinterpret_cast<uint4*>(sK + (size_t)j * VSTR + c8 * 8) = kv;
+      *reinterpret_cast<uint4*>(sV + (size_t)j * VSTR + c8 * 8) = vv;
+    }
+  }
+  __syncwarp();
+  const int g = lane >> 2, t4 = lane & 3;                               // fragment row / column-pair of this lane
+  const int mt_n = (len + 15) >> 4;
+  for (int mt = 0; mt < mt_n; ++mt) {
+    const int ra = mt * 16 + g, rb = ra + 8;                            // the two query rows this lane holds
+    const bf16* qa = qkv + (row0 + min(ra, L - 1)) * H3 + h * HD + t4 * 2;
+    const bf16* qb = qkv + (row0 + min(rb, L - 1)) * H3 + h * HD + t4 * 2;
+    uint32_t aq[4][4];
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      aq[ks][0] = __ldg(reinterpret_cast<const uint32_t*>(qa + ks * 16));
+      aq[ks][1] = __ldg(reinterpret_cast<const uint32_t*>(qb + ks * 16));
+      aq[ks][2] = __ldg(reinterpret_cast<const uint32_t*>(qa + ks * 16 + 8));
+      aq[ks][3] = __ldg(reinterpret_cast<const uint32_t*>(qb + ks * 16 + 8));
+    }
+    float sc[NT][4];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.f;
+      if (nt < kt_n) {
+        const bf16* kr = sK + (size_t)(nt * 8 + g) * VSTR + t4 * 2;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          mma_bf16(sc[nt], aq[ks], *reinterpret_cast<const uint32_t*>(kr + ks * 16),
+                   *reinterpret_cast<const uint32_t*>(kr + ks * 16 + 8));
+      }
+    }
+    // masked softmax over the keys; rows ra (elements 0, 1) and rb (elements 2, 3) live in the 4 lanes of a quad
+    float mxa = -INFINITY, mxb = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int j = nt * 8 + t4 * 2 + (e & 1);
+        sc[nt][e] = j < len ? sc[nt][e] * 0.125f : -INFINITY;           // 1 / sqrt(64)
+      }
+      mxa = fmaxf(mxa, fmaxf(sc[nt][0], sc[nt][1]));
+      mxb = fmaxf(mxb, fmaxf(sc[nt][2], sc[nt][3]));
+    }
+    mxa = fmaxf(mxa, __shfl_xor_sync(0xffffffffu, mxa, 1));
+    mxa = fmaxf(mxa, __shfl_xor_sync(0xffffffffu, mxa, 2));
+    mxb = fmaxf(mxb, __shfl_xor_sync(0xffffffffu, mxb, 1));
+    mxb = fmaxf(mxb, __shfl_xor_sync(0xffffffffu, mxb, 2));
+    float sma = 0.f, smb = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      sc[nt][0] = __expf(sc[nt][0] - mxa);                              // exp(-inf) = 0 for the masked keys
+      sc[nt][1] = __expf(sc[nt][1] - mxa);
+      sc[nt][2] = __expf(sc[nt][2] - mxb);
+      sc[nt][3] = __expf(sc[nt][3] - mxb);
+      sma += sc[nt][0] + sc[nt][1];
+      smb += sc[nt][2] + sc[nt][3];
+    }
+    sma += __shfl_xor_sync(0xffffffffu, sma, 1);
+    sma += __shfl_xor_sync(0xffffffffu, sma, 2);
+    smb += __shfl_xor_sync(0xffffffffu, smb, 1);
+    smb += __shfl_xor_sync(0xffffffffu, smb, 2);
+    const float inva = 1.0f / sma, invb = 1.0f / smb;
+    float o[8][4];
+#pragma unroll
+    for (int dt = 0; dt < 8; ++dt) o[dt][0] = o[dt][1] = o[dt][2] = o[dt][3] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < NT / 2; ++kk) {
+      if (kk < kt16) {
+        uint32_t ap[4];
+        ap[0] = pack_bf16x2(sc[2 * kk][0], sc[2 * kk][1]);
+        ap[1] = pack_bf16x2(sc[2 * kk][2], sc[2 * kk][3]);
+        ap[2] = pack_bf16x2(sc[2 * kk + 1][0], sc[2 * kk + 1][1]);
+        ap[3] = pack_bf16x2(sc[2 * kk + 1][2], sc[2 * kk + 1][3]);
+        // lanes 0-15 address the 16 V rows of this k step; .trans hands every lane V[k pair][d = lane / 4]
+        const uint32_t vaddr = (uint32_t)__cvta_generic_to_shared(sV + (size_t)(kk * 16 + (lane & 15)) * VSTR);
+#pragma unroll
+        for (int dt = 0; dt < 8; ++dt) {
+          uint32_t b0, b1;
+          asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];\n"
+                       : "=r"(b0), "=r"(b1) : "r"(vaddr + dt * 16));
+          mma_bf16(o[dt], ap, b0, b1);
+        }
+      }
+    }
+    bf16* oa = ctx + (row0 + ra) * H + h * HD + t4 * 2;
+    bf16* ob = ctx + (row0 + rb) * H + h * HD + t4 * 2;
+    const bool wa = ra < L, wb = rb < L;                                // rows in [len, L) get zeros, rows >= L nothing
+    const float fa = ra < len ? inva : 0.f, fb = rb < len ? invb : 0.f;
+#pragma unroll
+    for (int dt = 0; dt < 8; ++dt) {
+      if (wa) *reinterpret_cast<uint32_t*>(oa + dt * 8) = pack_bf16x2(o[dt][0] * fa, o[dt][1] * fa);
+      if (wb) *reinterpret_cast<uint32_t*>(ob + dt * 8) = pack_bf16x2(o[dt][2] * fb, o[dt][3] * fb);
+    }
+  }
+  // context rows of the remaining padding tokens: zeros (8 lanes x 16 bytes per row)
+  for (int j = mt_n * 16 + (lane >> 3); j < L; j += 4)
+    *reinterpret_cast<uint4*>(ctx + (row0 + j) * H + h * HD + (lane & 7) * 8) = make_uint4(0, 0, 0, 0);
 }
 
 template <int VPL>
@@ -427,14 +577,19 @@ int encode_impl(const qf_bert_config& c, const bf16* wts, const int32_t* tokens,
                                                    wts + o.eb, c.ln_eps, X, M, L, c.vocab, out_status);
   QF_CUDA_TRY(cudaGetLastError());
   const int tl = (L + 31) / 32;
-  const size_t attn_smem = (size_t)L * KPAD * 2 + (size_t)L * HD * 2 + 4 * HD * sizeof(float);
-  auto attn = tl <= 1 ? attn_kernel<1> : tl <= 2 ? attn_kernel<2> : tl <= 4 ? attn_kernel<4> : tl <= 8 ? attn_kernel<8> : attn_kernel<16>;
+  const bool use_mma = L <= 128;                    // query-length sequences: the tensor-core kernel, one warp per head
+  const int lt = L <= 32 ? 32 : L <= 64 ? 64 : 128;
+  const size_t attn_smem = use_mma ? (size_t)4 * 2 * lt * VSTR * sizeof(bf16)
+                                   : (size_t)L * KPAD * 2 + (size_t)L * HD * 2 + 4 * HD * sizeof(float);
+  auto attn = use_mma ? (lt == 32 ? attn_mma_kernel<32> : lt == 64 ? attn_mma_kernel<64> : attn_mma_kernel<128>)
+              : tl <= 8 ? attn_kernel<8> : attn_kernel<16>;
   QF_CUDA_TRY(cudaFuncSetAttribute(attn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem));
+  const dim3 attn_grid(use_mma ? (unsigned)c.heads / 4 : (unsigned)c.heads, (unsigned)B);
   for (int l = 0; l < c.n_layers; ++l) {
     const bf16* lw = wts + o.layer0 + (size_t)l * o.per_layer;
     int rc = gemm_bias(lw + o.wqkv, X, lw + o.bqkv, QKV, M, 3 * H, H, lt_ws, st);
     if (rc != QF_OK) return rc;
-    attn<<<dim3((unsigned)c.heads, (unsigned)B), 128, attn_smem, st>>>(QKV, lens, CTX, L, H);
+    attn<<<attn_grid, 128, attn_smem, st>>>(QKV, lens, CTX, L, H);
     QF_CUDA_TRY(cudaGetLastError());
     rc = gemm_bias(lw + o.wo, CTX, lw + o.bo, T1, M, H, H, lt_ws, st);
     if (rc != QF_OK) return rc;

@@ -189,6 +189,32 @@ class WordPieceTokenizer:
         return toks, lens
 
 
+def bucket_token_rows(rows: Sequence[Sequence[int]], bucket: int, max_len: int, batch_size: int, pad_id: int = 0):
+    """Group token rows by their length rounded up to `bucket` (host side, vectorised): yields
+    (row indices int64 [m], tokens int32 [m, L] padded with pad_id, lens int32 [m]) per group of at most batch_size rows."""
+    n = len(rows)
+    lens = np.fromiter((len(r) for r in rows), dtype=np.int64, count=n)
+    if n and (lens.min() < 1 or lens.max() > max_len):
+        raise ValueError(f"row lengths must lie in [1, {max_len}]")
+    flat = np.fromiter((t for r in rows for t in r), dtype=np.int64, count=int(lens.sum()))
+    if flat.size and (flat.min() < -2**31 or flat.max() >= 2**31):
+        raise ValueError("token id does not fit int32")
+    offs = np.concatenate(([0], np.cumsum(lens)))
+    padded = np.minimum(-(-lens // bucket) * bucket, max_len)
+    order = np.argsort(padded, kind="stable")
+    bounds = np.flatnonzero(np.diff(padded[order])) + 1
+    for grp in np.split(order, bounds) if n else []:
+        L = int(padded[grp[0]])
+        for s in range(0, len(grp), batch_size):
+            idx = grp[s:s + batch_size]
+            ln = lens[idx]
+            toks = np.full((len(idx), L), pad_id, dtype=np.int32)
+            r = np.repeat(np.arange(len(idx)), ln)                         # destination row of every real token
+            c = np.arange(int(ln.sum())) - np.repeat(np.cumsum(ln) - ln, ln)   # and its column
+            toks[r, c] = flat[np.repeat(offs[idx], ln) + c]
+            yield idx, toks, ln.astype(np.int32)
+
+
 # ------------------------------------------------------------------------------------------------ encoder
 class BertQueryEncoder:
     """Callable List[str] -> float32 [n, hidden] with L2-normalised rows: what BGERetriever(encoder=...) expects,
@@ -261,25 +287,14 @@ class BertQueryEncoder:
         out_f = torch.empty((n, H), dtype=torch.float32, device=self.device)
         if n == 0:
             return out_b, out_f
-        lens = np.fromiter((len(r) for r in rows), dtype=np.int64, count=n)
-        if lens.min() < 1 or lens.max() > self.cfg.max_pos:
-            raise ValueError(f"row lengths must lie in [1, {self.cfg.max_pos}]")
-        padded = np.minimum(-(-lens // bucket) * bucket, self.cfg.max_pos)
-        order = np.argsort(padded, kind="stable")
+        pad_id = self.tokenizer.pad_id if self.tokenizer is not None else 0
         statuses: list = []
-        bounds = np.flatnonzero(np.diff(padded[order])) + 1
-        for grp in np.split(order, bounds):
-            L = int(padded[grp[0]])
-            for s in range(0, len(grp), self.batch_size):
-                idx = grp[s:s + self.batch_size]
-                toks = np.full((len(idx), L), self.tokenizer.pad_id if self.tokenizer is not None else 0, dtype=np.int32)
-                for j, i in enumerate(idx):
-                    toks[j, : lens[i]] = rows[i]
-                b, f = self.encode_tokens(torch.from_numpy(toks).to(self.device, non_blocking=True),
-                                          torch.from_numpy(lens[idx].astype(np.int32)).to(self.device, non_blocking=True), statuses)
-                ix = torch.from_numpy(idx).to(self.device)
-                out_b[ix] = b
-                out_f[ix] = f
+        for idx, toks, lens in bucket_token_rows(rows, bucket, self.cfg.max_pos, self.batch_size, pad_id):
+            b, f = self.encode_tokens(torch.from_numpy(toks).to(self.device, non_blocking=True),
+                                      torch.from_numpy(lens).to(self.device, non_blocking=True), statuses)
+            ix = torch.from_numpy(idx).to(self.device, non_blocking=True)
+            out_b[ix] = b
+            out_f[ix] = f
         if int(torch.stack([st.max() for st in statuses]).max().item()) != 0:
             raise ValueError(f"token id outside [0, {self.cfg.vocab}) in the batch")
         return out_b, out_f

@@ -120,3 +120,22 @@ def test_encoder_fails_loudly_without_gpu():
     with pytest.raises(RuntimeError, match="CUDA tensors only"):
         ops.bert_encode(torch.zeros(8, dtype=torch.bfloat16), torch.zeros((1, 8), dtype=torch.int32),
                         torch.ones(1, dtype=torch.int32), n_layers=1, hidden=256, heads=4, ffn=512, vocab=10, max_pos=8)
+
+
+def test_bucket_token_rows_groups_by_padded_length():
+    from qppfusion.encoder import bucket_token_rows
+    rng = np.random.default_rng(2)
+    rows = [rng.integers(0, 1000, size=int(n)).tolist() for n in rng.integers(1, 41, size=300)]
+    seen = []
+    for idx, toks, lens in bucket_token_rows(rows, 8, 40, 64, pad_id=7):
+        assert toks.dtype == np.int32 and lens.dtype == np.int32 and len(idx) <= 64
+        for j, i in enumerate(idx):
+            assert toks[j, :lens[j]].tolist() == rows[i] and (toks[j, lens[j]:] == 7).all()
+            assert toks.shape[1] == -(-len(rows[i]) // 8) * 8
+        seen += idx.tolist()
+    assert sorted(seen) == list(range(300))
+    assert list(bucket_token_rows([], 8, 40, 64)) == []
+    with pytest.raises(ValueError):
+        list(bucket_token_rows([[1] * 41], 8, 40, 64))
+    with pytest.raises(ValueError):
+        list(bucket_token_rows([[1], []], 8, 40, 64))
