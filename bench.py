@@ -310,6 +310,102 @@ def dense_leg(args, dev, world, rank, Q=Q_NQ, n_docs=None, label="BASELINE confi
             "threshold_failures": status_bad, "parity": parity, "gpu_launches": (4 + (1 if world > 1 else 0)) * (2 * steps + 4), "clocks": clocks}
 
 
+def encoder_leg(args, dev, world, rank, Q=Q_NQ):
+    """BGE-base-shaped query encoder (12 x 768, random-init bf16 weights): Q synthetic queries of 5..32 tokens
+    (Poisson(11) + 3, the NQ query length profile), query-sharded across ranks, no collective.  kernel = one padded
+    qf_bert_encode call on resident tokens; e2e = host token rows -> length buckets -> H2D -> encode -> D2H float32."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from qppfusion import ops
+    from qppfusion.encoder import BertConfig, BertQueryEncoder
+    cfg = BertConfig()
+    g = torch.Generator(device=dev).manual_seed(20250105)
+    H, F = cfg.hidden, cfg.ffn
+
+    def rnd(*shape, scale):
+        return torch.randn(shape, generator=g, device=dev) * scale
+
+    def ln(prefix, sd):
+        sd[prefix + ".weight"] = 1.0 + rnd(H, scale=0.1)
+        sd[prefix + ".bias"] = rnd(H, scale=0.1)
+
+    sd = {"embeddings.word_embeddings.weight": rnd(cfg.vocab, H, scale=0.5),
+          "embeddings.position_embeddings.weight": rnd(cfg.max_pos, H, scale=0.2),
+          "embeddings.token_type_embeddings.weight": rnd(2, H, scale=0.2)}
+    ln("embeddings.LayerNorm", sd)
+    for l in range(cfg.n_layers):
+        p = f"encoder.layer.{l}."
+        for n_ in ("query", "key", "value"):
+            sd[p + f"attention.self.{n_}.weight"] = rnd(H, H, scale=0.08)
+            sd[p + f"attention.self.{n_}.bias"] = rnd(H, scale=0.05)
+        sd[p + "attention.output.dense.weight"] = rnd(H, H, scale=0.05)
+        sd[p + "attention.output.dense.bias"] = rnd(H, scale=0.05)
+        ln(p + "attention.output.LayerNorm", sd)
+        sd[p + "intermediate.dense.weight"] = rnd(F, H, scale=0.05)
+        sd[p + "intermediate.dense.bias"] = rnd(F, scale=0.05)
+        sd[p + "output.dense.weight"] = rnd(H, F, scale=0.05)
+        sd[p + "output.dense.bias"] = rnd(H, scale=0.05)
+        ln(p + "output.LayerNorm", sd)
+    enc = BertQueryEncoder(sd, cfg, None, device=dev)
+    del sd
+    q_local = (Q + world - 1) // world
+    q_local = max(0, min(q_local, Q - rank * q_local))
+    rng = np.random.default_rng(20250105 + rank)
+    L = 32
+    lens = np.clip(rng.poisson(11, size=q_local) + 3, 3, L).astype(np.int32)
+    tokens = rng.integers(0, cfg.vocab, size=(q_local, L)).astype(np.int32)
+    rows = [tokens[i, :lens[i]] for i in range(q_local)]
+    t_d, l_d = torch.from_numpy(tokens).to(dev), torch.from_numpy(lens).to(dev)
+    stream = torch.cuda.current_stream(dev)
+    steps = max(3, min(args.steps, 10))
+    kw = dict(n_layers=cfg.n_layers, hidden=H, heads=cfg.heads, ffn=F, vocab=cfg.vocab, max_pos=cfg.max_pos)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(3):
+        ops.bert_encode(enc.weights, t_d, l_d, **kw)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(steps):
+        ops.bert_encode(enc.weights, t_d, l_d, **kw)
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1) / steps
+    h_out = torch.empty((q_local, H), dtype=torch.float32).pin_memory()
+    enc.encode_token_lists(rows)
+    barrier()
+    e0.record(stream)
+    for _ in range(steps):
+        h_out.copy_(enc.encode_token_lists(rows)[1], non_blocking=True)
+    e1.record(stream)
+    barrier()
+    e2e_ms = e0.elapsed_time(e1) / steps
+    t = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, e2e_ms = t.tolist()
+    flop_tok = 2.0 * cfg.n_layers * (4 * H * H + 2 * H * F)
+    return {"metric": "BGE query-encoder QPS", "value": Q / (ms * 1e-3), "unit": "queries/s", "ms_per_step": ms,
+            "config": {"workload": "BERT-base 12 x 768 forward + CLS pooling + L2 norm, random-init bf16 weights, "
+                                   f"{Q} queries padded to {L} tokens (SURVEY 8f item 4)", "queries_per_gpu": q_local,
+                       "real_tokens_per_gpu": int(lens.sum()), "sharding": f"query-sharded x{world}, no collective"},
+            "linear_layer_tflops": flop_tok * q_local * L / (ms * 1e-3) / 1e12,
+            "e2e": {"value": Q / (e2e_ms * 1e-3), "unit": "queries/s", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": int((-(-lens // 8) * 8).sum()) * 4 + q_local * 12,
+                    "d2h_bytes_per_step": q_local * H * 4,
+                    "note": "host token rows -> length buckets of 8 -> one qf_bert_encode call per bucket -> D2H; "
+                            "tokenisation (host WordPiece) not included"},
+            # own kernels per call: embed+LN, pool+norm, and per layer attention, 2 x add+LN, GELU (the 4 Linear layers per
+            # block are cuBLASLt launches and not counted); the e2e path makes one call per length bucket (4 here)
+            "gpu_launches": (2 + 4 * cfg.n_layers) * (steps + 3) + 4 * (2 + 4 * cfg.n_layers) * (steps + 1)}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -497,6 +593,10 @@ def run_ours(args):
     dense_c4 = None if args.no_dense else dense_leg(args, dev, world, rank, Q=7405, n_docs=5_233_329,
                                                     label="BASELINE configs[3], HotpotQA shape", max_steps=4)
 
+    torch.cuda.empty_cache()
+    encoder = None if args.no_dense else encoder_leg(args, dev, world, rank)
+    torch.cuda.empty_cache()
+
     times = torch.tensor([ms_total, e2e_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
@@ -532,10 +632,12 @@ def run_ours(args):
                             "D2H; consecutive steps overlap on 3 streams"},
             # per step: qpp 1 + colnorm 3 + select 1 + fuse 2 (streaming + fix-up) = 7; CSR compaction adds 4
             "gpu_launches": (7 * (args.steps + max(args.warmup, 4)) + 7 * (args.steps + 4) + 11 * (e2e_steps + 3 + 6)
-                             + (dense["gpu_launches"] if dense else 0) + (dense_c4["gpu_launches"] if dense_c4 else 0)),
+                             + (dense["gpu_launches"] if dense else 0) + (dense_c4["gpu_launches"] if dense_c4 else 0)
+                             + (encoder["gpu_launches"] if encoder else 0)),
             "clocks": clocks,
             "dense": dense,
             "dense_hotpotqa": dense_c4,
+            "encoder": encoder,
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(seconds=10.0)

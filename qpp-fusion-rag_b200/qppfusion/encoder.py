@@ -196,7 +196,11 @@ def bucket_token_rows(rows: Sequence[Sequence[int]], bucket: int, max_len: int, 
     lens = np.fromiter((len(r) for r in rows), dtype=np.int64, count=n)
     if n and (lens.min() < 1 or lens.max() > max_len):
         raise ValueError(f"row lengths must lie in [1, {max_len}]")
-    flat = np.fromiter((t for r in rows for t in r), dtype=np.int64, count=int(lens.sum()))
+    if n and isinstance(rows[0], np.ndarray):
+        flat = np.concatenate(rows).astype(np.int64, copy=False)
+    else:
+        import itertools
+        flat = np.fromiter(itertools.chain.from_iterable(rows), dtype=np.int64, count=int(lens.sum()))
     if flat.size and (flat.min() < -2**31 or flat.max() >= 2**31):
         raise ValueError("token id does not fit int32")
     offs = np.concatenate(([0], np.cumsum(lens)))
