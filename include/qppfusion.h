@@ -305,6 +305,20 @@ QF_API int    qf_bert_encode(const qf_bert_config* cfg, const void* weights_bf16
                              const int32_t* lens, int B, int L, void* out_bf16, float* out_f32, int32_t* out_status,
                              void* ws, size_t ws_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * WordPiece tokeniser (host side, multi-threaded, no CUDA)  --  replaces the HF BertTokenizer call inside
+ * SentenceTransformer.encode (BGERetriever._encode_queries, src/retrievers/bge.py:160-170) for 7-bit texts
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct qf_wordpiece qf_wordpiece;
+/* vocab = the bytes of a BERT vocab.txt (one token per line, id = line number); needs [CLS] [SEP] [UNK] [PAD]. */
+QF_API int  qf_wordpiece_create(const char* vocab, size_t vocab_bytes, int do_lower_case, qf_wordpiece** out);
+QF_API void qf_wordpiece_free(qf_wordpiece* wp);
+/* texts: n UTF-8 strings back to back, text i = bytes [offsets[i], offsets[i+1]).  out_tokens[n][row_cap]
+ * ([CLS] pieces [SEP], truncated to max_len <= row_cap tokens, padded with [PAD]), out_lens[n].  out_flags[i] = 1:
+ * the text holds a byte >= 0x80 and was NOT tokenised (out_lens[i] = 0) -- the caller runs its Unicode path for it. */
+QF_API int  qf_wordpiece_encode(const qf_wordpiece* wp, const char* texts, const int64_t* offsets, int n, int max_len,
+                                int row_cap, int n_threads, int32_t* out_tokens, int32_t* out_lens, uint8_t* out_flags);
+
 #ifdef __cplusplus
 }
 #endif

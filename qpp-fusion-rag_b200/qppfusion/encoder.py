@@ -177,6 +177,53 @@ class WordPieceTokenizer:
         ids = [i for w in self.words(text) for i in self.pieces(w)][: self.max_length - 2]
         return [self.cls_id] + ids + [self.sep_id]
 
+    # -- native fast path -------------------------------------------------------------------------------------
+    def _native_handle(self):
+        h = getattr(self, "_wp", None)
+        if h is None:
+            import ctypes
+            by_id = [None] * (max(self.vocab.values()) + 1)
+            for t, i in self.vocab.items():
+                if i < 0 or by_id[i] is not None:
+                    raise ValueError("vocabulary ids must be distinct and non-negative")
+                by_id[i] = t
+            # ids no token maps to (a vocab.txt line shadowed by a later duplicate): a placeholder no word can match
+            blob = "\n".join(t if t is not None else f"\x00unused{i}" for i, t in enumerate(by_id)).encode("utf-8")
+            h = ctypes.c_void_p()
+            N.check(N.lib().qf_wordpiece_create(blob, len(blob), 1 if self.do_lower_case else 0, ctypes.byref(h)))
+            self._wp = h
+        return h
+
+    def __del__(self):
+        h = getattr(self, "_wp", None)
+        if h is not None:
+            try:
+                N.lib().qf_wordpiece_free(h)
+            except Exception:
+                pass
+
+    def encode_batch(self, texts: Sequence[str], n_threads: int = 0) -> List[np.ndarray]:
+        """[CLS] ... [SEP] id rows (int32 arrays) for many texts: 7-bit texts through the multi-threaded C++
+        tokeniser (qf_wordpiece_encode), the rest through `encode` (full Unicode handling) one by one."""
+        n = len(texts)
+        if n == 0:
+            return []
+        enc = [t.encode("utf-8") for t in texts]
+        offs = np.zeros(n + 1, dtype=np.int64)
+        np.cumsum([len(b) for b in enc], out=offs[1:])
+        blob = b"".join(enc)
+        cap = int(min(self.max_length, max(len(b) for b in enc) + 2))
+        cap = max(cap, 2)
+        toks = np.empty((n, cap), dtype=np.int32)
+        lens = np.empty(n, dtype=np.int32)
+        flags = np.empty(n, dtype=np.uint8)
+        N.check(N.lib().qf_wordpiece_encode(self._native_handle(), blob, offs.ctypes.data, n, cap, cap, int(n_threads),
+                                            toks.ctypes.data, lens.ctypes.data, flags.ctypes.data))
+        rows = [toks[i, :lens[i]] for i in range(n)]
+        for i in np.flatnonzero(flags):
+            rows[i] = np.asarray(self.encode(texts[i]), dtype=np.int32)
+        return rows
+
     def batch(self, texts: Sequence[str], pad_multiple: int = 8) -> Tuple[np.ndarray, np.ndarray]:
         """-> (tokens int32 [n, L] padded with [PAD], lens int32 [n]); L = longest row rounded up to pad_multiple."""
         rows = [self.encode(t) for t in texts]
@@ -304,7 +351,7 @@ class BertQueryEncoder:
         return out_b, out_f
 
     def _encode(self, queries: Sequence[str]) -> Tuple[torch.Tensor, torch.Tensor]:
-        return self.encode_token_lists([self.tokenizer.encode(q) for q in queries])
+        return self.encode_token_lists(self.tokenizer.encode_batch(list(queries)))
 
     def encode_device(self, queries: Sequence[str]) -> torch.Tensor:
         """bf16 [n, H] on the device: the `queries` operand of ops.dense_topk."""

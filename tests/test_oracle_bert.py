@@ -139,3 +139,32 @@ def test_bucket_token_rows_groups_by_padded_length():
         list(bucket_token_rows([[1] * 41], 8, 40, 64))
     with pytest.raises(ValueError):
         list(bucket_token_rows([[1], []], 8, 40, 64))
+
+
+def test_native_tokenizer_matches_python_and_real_berttokenizer(tmp_path):
+    """qf_wordpiece_encode (C++, 7-bit fast path) against the Python tokeniser and the live transformers.BertTokenizer;
+    non-ASCII texts take the Python path inside encode_batch."""
+    from qppfusion.encoder import WordPieceTokenizer
+    vocab = synthetic_vocab() + ["x" * 101, "##" + "y" * 30, "hello", "##llo", "he", "world", "##ld", "wor"]
+    tok = WordPieceTokenizer({t: i for i, t in enumerate(vocab)}, max_length=24)
+    rng = np.random.default_rng(8)
+    alphabet = list("abcdefghijxy  \t\n\r!?'-.,;:()[]{}$5Z\x0b\x01\x7f") + ["what", "Capital", "unbelievably", "hello", "world",
+                                                                      "helloworld", " ", "é", "京"]
+    texts = ["".join(rng.choice(alphabet, size=int(rng.integers(0, 60)))) for _ in range(1500)]
+    texts += ["", " ", "x" * 101, "x" * 100, "a" * 300, "hello " * 40, "\x00a\x00", "A.B,C"]
+    rows = tok.encode_batch(texts, n_threads=3)
+    assert len(rows) == len(texts)
+    for t, r in zip(texts, rows):
+        assert r.dtype == np.int32 and r.tolist() == tok.encode(t), repr(t)
+        assert len(r) <= 24 and r[0] == tok.cls_id and r[-1] == tok.sep_id
+    assert [r.tolist() for r in tok.encode_batch(texts[:40], n_threads=1)] == [r.tolist() for r in rows[:40]]
+    assert tok.encode_batch([]) == []
+    tr = pytest.importorskip("transformers")
+    vp = tmp_path / "vocab.txt"
+    vp.write_text("\n".join(vocab) + "\n", encoding="utf-8")
+    real = tr.BertTokenizer(str(vp), do_lower_case=True)
+    for t, r in list(zip(texts, rows))[::7]:
+        assert r.tolist() == real(t, truncation=True, max_length=24)["input_ids"], repr(t)
+    # a vocabulary without the special tokens is rejected by the C side as by the Python side
+    with pytest.raises(ValueError):
+        WordPieceTokenizer({"a": 0, "b": 1})
