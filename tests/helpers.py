@@ -49,3 +49,18 @@ def pack_lists(lists, k=None, score_type="f64"):
                 ranks[q, r, i] = rk
                 sc[q, r, i] = int(round(s * 1e6)) if score_type == "micro" else s
     return ids, sc, ranks, lens
+
+
+class LinearWeightModel:
+    """Stand-in for the reference's pickled fusion-weight model (src/fusion.py:408-429 only needs `.predict(X)` ->
+    [n_queries, n_retrievers]): softmax of a seeded linear map of the QPP feature vector.  Lives here so that the
+    pickle written by tools/make_golden_learned.py resolves (`helpers.LinearWeightModel`) in the tests."""
+
+    def __init__(self, n_features: int, n_retrievers: int, seed: int = 0):
+        self.W = np.random.default_rng(seed).standard_normal((n_features, n_retrievers))
+
+    def predict(self, X):
+        z = np.asarray(X, dtype=np.float64) @ self.W
+        z = z - z.max(axis=1, keepdims=True)
+        e = np.exp(z)
+        return e / e.sum(axis=1, keepdims=True)

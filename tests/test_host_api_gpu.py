@@ -211,3 +211,32 @@ def test_tct_colbert_retriever_uses_the_same_flat_ip_search(tmp_path):
     assert [d for d, _, _ in out["q1"].results] == [d for d, _, _ in res[0].results[:5]]
     with pytest.raises(FileNotFoundError):
         TCTColBERTRetriever(corpus, cache_dir=str(tmp_path / "missing"), encoder=encoder)
+
+
+def test_learned_fusion_equals_the_real_reference_outputs(tmp_path):
+    """qppfusion.fusion.learned_fusion (weights from a pickled model -> qf_fuse W-CombSUM) against the outputs of the
+    REAL reference learned_fusion (tests/golden/fusion_learned.json.gz): same qids, same docno-ascending lists, scores
+    within 2 ulp (the reference sums with pandas' Kahan-compensated groupby, the kernel sequentially in list order)."""
+    import os
+    import pickle
+    import numpy as np
+    from helpers import LinearWeightModel
+    from qppfusion import fusion
+    path = os.path.join(os.path.dirname(GOLD), "fusion_learned.json.gz")
+    with gzip.open(path, "rt") as f:
+        gold = json.load(f)
+    for case in gold["cases"]:
+        frames = gold_frames(case, gold["rankers"])
+        mr = case["model_rankers"]
+        pkl = tmp_path / f"{case['name']}.pkl"
+        with open(pkl, "wb") as f:
+            pickle.dump({"model": LinearWeightModel(13 * len(mr), len(mr), case["model_seed"]),
+                         "model_type": "PerRetrieverLGBM", "retrievers": mr, "n_qpp": 13}, f)
+        fused = fusion.learned_fusion(frames, case["qpp"], str(pkl))
+        ref = case["fused"]
+        assert sorted(fused.keys()) == sorted(ref.keys())
+        for q in ref:
+            assert [d for d, _ in fused[q]] == [d for d, _ in ref[q]], (case["name"], q)
+            a = np.array([s for _, s in fused[q]])
+            b = np.array([float(s) for _, s in ref[q]])
+            assert np.all(np.abs(a - b) <= 2 * np.spacing(np.abs(b))), (case["name"], q)

@@ -80,3 +80,26 @@ def test_ranx_restatement_formulas():
 
 def test_rank_order_is_stable_descending():
     assert fo.rank_order([0.5, 1.0, 0.5, 1.0, -0.0, 0.0]) == [1, 3, 0, 2, 4, 5]
+
+
+GOLD_LEARNED = os.path.join(os.path.dirname(__file__), "golden", "fusion_learned.json.gz")
+
+
+def test_learned_fusion_matches_the_real_reference():
+    """oracle learned_fusion vs the outputs of the REAL reference learned_fusion (tools/make_golden_learned.py):
+    same qids, same docno order, scores within 2 ulp (pandas sums with Kahan compensation, the oracle sequentially)."""
+    import numpy as np
+    from helpers import LinearWeightModel
+    with gzip.open(GOLD_LEARNED, "rt") as f:
+        gold = json.load(f)
+    for case in gold["cases"]:
+        runs = rows_to_runs(case, gold["rankers"])
+        mr = case["model_rankers"]
+        fused = fo.learned_fusion(runs, case["qpp"], LinearWeightModel(13 * len(mr), len(mr), case["model_seed"]), mr)
+        ref = case["fused"]
+        assert sorted(fused.keys()) == sorted(ref.keys())
+        for q in ref:
+            assert [d for d, _ in fused[q]] == [d for d, _ in ref[q]], (case["name"], q)
+            a = np.array([s for _, s in fused[q]])
+            b = np.array([float(s) for _, s in ref[q]])
+            assert np.all(np.abs(a - b) <= 2 * np.spacing(np.abs(b))), (case["name"], q)
