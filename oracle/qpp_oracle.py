@@ -414,21 +414,22 @@ def research_scores(all_scores: Sequence[float], n_query_terms: int, max_idf: fl
 # --------------------------------------------------------------------------------------------------
 
 def normalize_qpp(results: Dict[str, List[float]], method: str) -> Dict[str, List[float]]:
-    """_normalize_qpp (src/qpp.py:340-374).  numpy's mean/std are pairwise-summed; plain summation is
-    used here (difference <= 1e-13 relative, tolerance of this path is 1e-5)."""
+    """_normalize_qpp (src/qpp.py:340-374), with numpy's own min/max/mean/std as the reference calls them (pairwise
+    summation), so the result is bit-equal to the reference's: pinned by tests/golden/qpp_normalize.json.gz, outputs of
+    the REAL function (tools/make_golden_qpp_norm.py)."""
+    import numpy as np
     if not results:
         return {}
     n = len(next(iter(results.values())))
     cols = [[v[i] for v in results.values()] for i in range(n)]
     params = []
     for vals in cols:
+        arr = np.array(vals)
         if method == "minmax":
-            vmin, vmax = min(vals), max(vals)
+            vmin, vmax = arr.min(), arr.max()
             params.append((vmin, vmax - vmin if vmax > vmin else 1.0))
         else:
-            mean = math.fsum(vals) / len(vals)
-            std = math.sqrt(math.fsum((v - mean) * (v - mean) for v in vals) / len(vals))
-            params.append((mean, std if std > 0 else 1.0))
+            params.append((arr.mean(), arr.std() if arr.std() > 0 else 1.0))
     out = {}
     for qid, vals in results.items():
         row = []

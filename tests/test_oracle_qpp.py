@@ -121,3 +121,21 @@ def test_normalize_and_file_format():
     assert z["9"][0] == pytest.approx((3 - 2) / math.sqrt(2 / 3))
     assert z["9"][1] == 0.0
     assert qo.qpp_file_lines(mm) == ["9\t1.000000\t0.000000", "10\t0.000000\t0.000000"]
+
+
+def test_normalize_qpp_bit_equal_to_the_real_reference_function():
+    """oracle normalize_qpp vs outputs of the REAL src/qpp.py::_normalize_qpp (tools/make_golden_qpp_norm.py)."""
+    import gzip
+    import json
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "qpp_normalize.json.gz")
+    with gzip.open(path, "rt") as f:
+        gold = json.load(f)
+    for case in gold["cases"]:
+        table = {q: [float(v) for v in row] for q, row in case["table"].items()}
+        for mode in ("minmax", "zscore"):
+            got = qo.normalize_qpp(table, mode)
+            ref = case[mode]
+            assert list(got.keys()) == list(ref.keys())
+            for q in ref:
+                assert [float(v) for v in got[q]] == [float(v) for v in ref[q]], (case["seed"], mode, q)
