@@ -181,12 +181,15 @@ __global__ void __launch_bounds__(256) gelu_kernel(bf16* x, size_t n8) {
 // One CTA per (head, query): 4 warps, warp w owns query rows w, w+4, ...; lane l owns keys l, l+32, ... (TL per lane).
 constexpr int HD = 64;            // head dimension
 constexpr int KPAD = HD + 2;      // K row stride in bf16: 33 words -> lanes reading different rows hit different banks
+__host__ __device__ inline size_t attn_q_offset(int L) {
+  return (((size_t)L * KPAD + (size_t)L * HD) * sizeof(bf16) + 15) & ~size_t(15);
+}
 template <int TL>
 __global__ void __launch_bounds__(128) attn_kernel(const bf16* qkv, const int32_t* lens, bf16* ctx, int L, int H) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   bf16* sK = reinterpret_cast<bf16*>(smem_raw);                       // [L][KPAD]
   bf16* sV = sK + (size_t)L * KPAD;                                    // [L][HD]
-  float* sQ = reinterpret_cast<float*>(sV + (size_t)L * HD);           // [4][HD]
+  float* sQ = reinterpret_cast<float*>(smem_raw + attn_q_offset(L));   // [4][HD], 16-byte aligned for any L
   const int h = blockIdx.x, b = blockIdx.y;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   int len = lens ? __ldg(lens + b) : L;
@@ -580,7 +583,7 @@ int encode_impl(const qf_bert_config& c, const bf16* wts, const int32_t* tokens,
   const bool use_mma = L <= 128;                    // query-length sequences: the tensor-core kernel, one warp per head
   const int lt = L <= 32 ? 32 : L <= 64 ? 64 : 128;
   const size_t attn_smem = use_mma ? (size_t)4 * 2 * lt * VSTR * sizeof(bf16)
-                                   : (size_t)L * KPAD * 2 + (size_t)L * HD * 2 + 4 * HD * sizeof(float);
+                                   : attn_q_offset(L) + 4 * HD * sizeof(float);
   auto attn = use_mma ? (lt == 32 ? attn_mma_kernel<32> : lt == 64 ? attn_mma_kernel<64> : attn_mma_kernel<128>)
               : tl <= 8 ? attn_kernel<8> : attn_kernel<16>;
   QF_CUDA_TRY(cudaFuncSetAttribute(attn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem));

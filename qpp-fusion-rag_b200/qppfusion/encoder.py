@@ -236,9 +236,11 @@ class WordPieceTokenizer:
         return toks, lens
 
 
-def bucket_token_rows(rows: Sequence[Sequence[int]], bucket: int, max_len: int, batch_size: int, pad_id: int = 0):
+def bucket_token_rows(rows: Sequence[Sequence[int]], bucket: int, max_len: int, batch_size: int, pad_id: int = 0,
+                      max_tokens: int = 1 << 18):
     """Group token rows by their length rounded up to `bucket` (host side, vectorised): yields
-    (row indices int64 [m], tokens int32 [m, L] padded with pad_id, lens int32 [m]) per group of at most batch_size rows."""
+    (row indices int64 [m], tokens int32 [m, L] padded with pad_id, lens int32 [m]) per group of at most batch_size
+    rows and at most max_tokens padded tokens (the encoder's workspace is ~15 kB per token for bert-base)."""
     n = len(rows)
     lens = np.fromiter((len(r) for r in rows), dtype=np.int64, count=n)
     if n and (lens.min() < 1 or lens.max() > max_len):
@@ -256,8 +258,9 @@ def bucket_token_rows(rows: Sequence[Sequence[int]], bucket: int, max_len: int, 
     bounds = np.flatnonzero(np.diff(padded[order])) + 1
     for grp in np.split(order, bounds) if n else []:
         L = int(padded[grp[0]])
-        for s in range(0, len(grp), batch_size):
-            idx = grp[s:s + batch_size]
+        step = max(1, min(batch_size, max_tokens // L))
+        for s in range(0, len(grp), step):
+            idx = grp[s:s + step]
             ln = lens[idx]
             toks = np.full((len(idx), L), pad_id, dtype=np.int32)
             r = np.repeat(np.arange(len(idx)), ln)                         # destination row of every real token
@@ -290,8 +293,11 @@ class BertQueryEncoder:
         if not (d / "config.json").exists():
             raise FileNotFoundError(f"No config.json under {d}")
         hf = json.loads((d / "config.json").read_text())
-        pooling = "cls"
+        # a plain HF checkpoint (no sentence-transformers modules): SentenceTransformer(name) adds MEAN pooling;
+        # bge-base-en-v1.5 ships 1_Pooling/config.json with pooling_mode_cls_token = true
+        pooling = "mean"
         if (d / "1_Pooling" / "config.json").exists():
+            pooling = "cls"
             pc = json.loads((d / "1_Pooling" / "config.json").read_text())
             if pc.get("pooling_mode_mean_tokens"):
                 pooling = "mean"

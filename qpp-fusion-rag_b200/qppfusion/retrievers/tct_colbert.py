@@ -8,8 +8,10 @@ Kept from the reference: the class name and `name = "TCT-ColBERT"`, the construc
 (corpus, cache_dir, batch_size, use_fp16), the embedding cache files it reads
 (`tct_colbert_{n_docs}_{fp16|fp32}.npy` + `tct_colbert_{n_docs}_ids.npy`, :76-103), `retrieve`, `_process_mini_batch`,
 `retrieve_batch` with the JSONL checkpoint format, and the result tuples (docno, score, rank from 1).
-Out of scope: the SentenceTransformer encoder -- pass `encoder=` (List[str] -> float32 [n, 768],
-L2-normalised rows) and, when no cache file exists, `doc_embeddings=`.
+Encoder: `model_dir=` (a local checkpoint directory -> qppfusion.encoder.BertQueryEncoder, mean pooling for a plain
+HF checkpoint as SentenceTransformer(model_name) builds it) or `encoder=` (List[str] -> float32 [n, 768], L2-normalised
+rows).  With an encoder and a cache_dir a missing cache is computed and written like the reference does (:97-134);
+without one a missing cache raises.
 """
 from __future__ import annotations
 
@@ -35,8 +37,17 @@ class TCTColBERTRetriever(BGERetriever):
         self.batch_size = batch_size or config.processing.batch_sizes.tct_encoding
         self.use_fp16 = use_fp16
         self.cache_dir = Path(cache_dir) if cache_dir else None
-        if doc_embeddings is None:
-            doc_embeddings = self._load_cached_embeddings()
+        model_dir = kwargs.pop("model_dir", None)
+        if encoder is None and model_dir is not None:
+            from ..encoder import BertQueryEncoder
+            encoder = BertQueryEncoder.from_pretrained(model_dir)      # plain HF checkpoint -> mean pooling, like
+        if doc_embeddings is None:                                      # SentenceTransformer(model_name)
+            try:
+                doc_embeddings = self._load_cached_embeddings()
+            except FileNotFoundError:
+                if encoder is None or self.cache_dir is None:
+                    raise
+                doc_embeddings = self._encode_corpus_chunked(encoder)
         super().__init__(corpus_embeddings=doc_embeddings, docids=self.doc_ids, encoder=encoder, **kwargs)
         self.model_name = config.models.tct_colbert.name
         self.embedding_dim = config.models.tct_colbert.embedding_dim
@@ -61,6 +72,22 @@ class TCTColBERTRetriever(BGERetriever):
         cached_ids = np.load(str(ids_path), allow_pickle=True)
         if list(cached_ids) != self.doc_ids:
             raise ValueError("[TCT-ColBERT] Cache IDs mismatch")
+        return emb
+
+    def _encode_corpus_chunked(self, encoder) -> np.ndarray:
+        """No cache: encode "title text" of every document in chunks of 8 batches and write the reference's cache
+        files (src/retrievers/tct_colbert.py:97-134: same text construction, dtype, file names and id file)."""
+        dtype = np.float16 if self.use_fp16 else np.float32
+        n_docs = len(self.doc_ids)
+        emb = np.zeros((n_docs, config.models.tct_colbert.embedding_dim), dtype=dtype)
+        chunk = self.batch_size * 8
+        for s0 in range(0, n_docs, chunk):
+            ids = self.doc_ids[s0:s0 + chunk]
+            texts = [(self.corpus_docs[d].get("title", "") + " " + self.corpus_docs[d].get("text", "")).strip() for d in ids]
+            emb[s0:s0 + len(ids)] = np.asarray(encoder(texts), dtype=np.float32).astype(dtype)
+        self.cache_dir.mkdir(parents=True, exist_ok=True)
+        np.save(str(self._get_cache_path()), emb)
+        np.save(str(self.cache_dir / f"tct_colbert_{n_docs}_ids.npy"), np.array(self.doc_ids, dtype=object))
         return emb
 
     def _process_mini_batch(self, queries: List[Tuple[str, str]], top_k: int) -> List[RetrieverResult]:

@@ -43,13 +43,14 @@ def test_small_model_matches_golden_bertmodel(pooling):
     assert torch.equal(out_b, out_f.to(torch.bfloat16))
 
 
-@pytest.mark.parametrize("hidden,heads,L", [(256, 4, 8), (512, 8, 40), (768, 12, 64), (1024, 16, 24), (256, 4, 160)])
+@pytest.mark.parametrize("hidden,heads,L", [(256, 4, 8), (512, 8, 40), (768, 12, 64), (1024, 16, 24), (256, 4, 160),
+                                            (256, 4, 128), (256, 4, 129), (256, 4, 384), (256, 4, 512), (256, 4, 7), (256, 4, 33), (256, 4, 1)])
 def test_shapes_against_oracle(hidden, heads, L):
     cfg = dict(CFG, hidden_size=hidden, num_attention_heads=heads, intermediate_size=2 * hidden, num_hidden_layers=2,
                max_position_embeddings=max(64, L))
+    B = 9 if L <= 160 else 4
     sd = bert_small_state(seed=hidden + L, cfg=cfg)
     rng = np.random.default_rng(L)
-    B = 9
     tokens = rng.integers(0, cfg["vocab_size"], size=(B, L))
     lens = rng.integers(1, L + 1, size=B)
     lens[0], lens[1] = L, 1
@@ -150,3 +151,47 @@ def test_query_encoder_end_to_end_into_dense_search():
     res = r.retrieve_batch({f"q{i}": t for i, t in enumerate(TEXTS)}, top_k=10)
     assert res["q0"].results[0][0] == "1234" and abs(res["q0"].results[0][1] - 1.0) < 1e-2
     assert all(len(v.results) == 10 for v in res.values())
+
+
+def test_from_pretrained_and_tct_colbert_corpus_encoding(tmp_path):
+    """A checkpoint directory (config.json, vocab.txt, model.safetensors) -> BertQueryEncoder.from_pretrained (mean
+    pooling for a plain HF checkpoint, as SentenceTransformer(name) builds it) -> TCTColBERTRetriever encodes the
+    corpus, writes the reference's cache files, a second instance reads them back."""
+    import json
+    from safetensors.torch import save_file
+    from qppfusion.encoder import BertQueryEncoder
+    from qppfusion.retrievers.tct_colbert import TCTColBERTRetriever
+    vocab = synthetic_vocab()
+    cfg_hf = dict(CFG, hidden_size=768, num_attention_heads=12, intermediate_size=1024, vocab_size=len(vocab),
+                  layer_norm_eps=1e-12, hidden_act="gelu", max_position_embeddings=64)
+    sd = bert_small_state(seed=17, cfg=cfg_hf)
+    d = tmp_path / "ckpt"
+    d.mkdir()
+    (d / "config.json").write_text(json.dumps(cfg_hf))
+    (d / "vocab.txt").write_text("\n".join(vocab) + "\n", encoding="utf-8")
+    save_file({"bert." + k: torch.from_numpy(v) for k, v in sd.items()}, str(d / "model.safetensors"))
+    enc = BertQueryEncoder.from_pretrained(str(d))
+    assert enc.cfg.pooling == "mean" and enc.tokenizer.max_length == 64
+    emb = enc(TEXTS)
+    toks, lens = enc.tokenizer.batch(TEXTS)
+    ref = bert_oracle.bert_encode({k: bert_oracle._bf16_round(v) for k, v in sd.items()}, toks, lens, n_layers=2,
+                                  heads=12, pooling="mean")
+    assert ((emb.astype(np.float64) * ref).sum(1) >= 0.9995).all()
+    (d / "1_Pooling").mkdir()
+    (d / "1_Pooling" / "config.json").write_text(json.dumps({"pooling_mode_cls_token": True, "pooling_mode_mean_tokens": False}))
+    assert BertQueryEncoder.from_pretrained(str(d)).cfg.pooling == "cls"
+    corpus = {f"d{i}": {"title": TEXTS[i % len(TEXTS)], "text": "what is the capital of france " * (1 + i % 9)} for i in range(40)}
+    cache = tmp_path / "cache"
+    r = TCTColBERTRetriever(corpus, cache_dir=str(cache), batch_size=4, use_fp16=True, encoder=enc)
+    files = sorted(p.name for p in cache.iterdir())
+    assert files == ["tct_colbert_40_fp16.npy", "tct_colbert_40_ids.npy"]
+    saved = np.load(str(cache / "tct_colbert_40_fp16.npy"))
+    assert saved.dtype == np.float16 and saved.shape == (40, 768)
+    want = enc([(corpus["d7"]["title"] + " " + corpus["d7"]["text"]).strip()])[0]
+    assert np.abs(saved[7].astype(np.float32) - want).max() <= 2e-3
+    hit = r.retrieve((corpus["d7"]["title"] + " " + corpus["d7"]["text"]).strip(), qid="q", top_k=3)
+    assert abs(hit.results[0][1] - 1.0) < 2e-2
+    r2 = TCTColBERTRetriever(corpus, cache_dir=str(cache), batch_size=4, use_fp16=True, encoder=enc)     # from the cache
+    assert torch.equal(r2.corpus, r.corpus)
+    with pytest.raises(FileNotFoundError):
+        TCTColBERTRetriever(corpus, cache_dir=str(tmp_path / "none"), use_fp16=True)                     # no encoder

@@ -209,8 +209,8 @@ def test_tct_colbert_retriever_uses_the_same_flat_ip_search(tmp_path):
     ck = tmp_path / "TCT.checkpoint.jsonl"
     out = ret.retrieve_batch({"q1": "alpha", "q2": "beta"}, top_k=5, checkpoint_path=str(ck))
     assert [d for d, _, _ in out["q1"].results] == [d for d, _, _ in res[0].results[:5]]
-    with pytest.raises(FileNotFoundError):
-        TCTColBERTRetriever(corpus, cache_dir=str(tmp_path / "missing"), encoder=encoder)
+    with pytest.raises(FileNotFoundError):        # no cache and no encoder to compute one with
+        TCTColBERTRetriever(corpus, cache_dir=str(tmp_path / "missing"))
 
 
 def test_learned_fusion_equals_the_real_reference_outputs(tmp_path):
