@@ -355,23 +355,35 @@ def run_fusion(method: str, runs_dir: str, qpp_dir: Optional[str] = None, qpp_mo
         raise ValueError("--qpp_dir required for weighted methods")
     parsed = nio.parse_runs([os.path.join(runs_dir, f) for f in files], names)
     print(f"Loaded {len(names)} rankers: {names}")
-    if method in plain_names:
-        m = plain_names[method]
+    qpp_data = load_qpp_scores(qpp_dir) if method not in plain_names else None
+    return _fuse_parsed(parsed, method, qpp_data, qpp_model, output_path, rrf_k, return_fused)
+
+
+_WEIGHTED = {"wcombsum": N.METHOD_SUM, "wcombmnz": N.METHOD_MNZ, "wrrf": N.METHOD_RRF}
+_PLAIN = {"combsum": N.METHOD_SUM, "combmnz": N.METHOD_MNZ, "rrf": N.METHOD_RRF}
+
+
+def _fuse_parsed(parsed, method: str, qpp_data, qpp_model: str, output_path: Optional[str], rrf_k: int,
+                 return_fused: bool, tag: Optional[str] = None) -> Fused:
+    """One fusion method over already parsed run files: pack -> qf_fuse -> (CSR compaction -> native writer)."""
+    from . import native_io as nio
+    base = method.replace("-", "")
+    if method in _PLAIN:
+        m = _PLAIN[method]
         packed, qorder = nio.pack_parsed(parsed, "ranx")
         flags = N.FLAG_REQUIRE_SORTED | (N.FLAG_MNZ_SKIP_ZERO if (m == N.METHOD_MNZ and not config.fusion.ranx_mnz_counts_zero_scores) else 0)
         print(f"[fusion] Running {method} (qf_fuse)...")
         out = fuse_packed(packed, m, None, N.NORM_NONE if m == N.METHOD_RRF else N.NORM_MINMAX, float(rrf_k), flags)
-        tag = f"rrf-k{rrf_k}" if method == "rrf" else method
+        tag = tag or (f"rrf-k{rrf_k}" if method == "rrf" else method)
         first_seen = False
     else:
-        m = weighted_names[base]
-        qpp_data = load_qpp_scores(qpp_dir)
+        m = _WEIGHTED[base]
         qpp_index = get_qpp_index(qpp_model)
         packed, qorder = nio.pack_parsed(parsed, "weighted_rrf" if m == N.METHOD_RRF else "weighted", need_ranks=(m == N.METHOD_RRF))
         w = _weights_matrix(packed, qpp_data, qpp_index)
         print(f"[fusion] Running {base} (QPP index={qpp_index}, qf_fuse)...")
         out = fuse_packed(packed, m, w, N.NORM_NONE, float(rrf_k), 0, want_pos=return_fused)
-        tag = f"{base}-{qpp_model.lower()}"
+        tag = tag or f"{base}-{qpp_model.lower()}"
         first_seen = True
     if output_path:
         off, cids, csc = ops.compact_fused(out)
@@ -384,6 +396,54 @@ def run_fusion(method: str, runs_dir: str, qpp_dir: Optional[str] = None, qpp_mo
     fused = _fused_dict_from_out(packed, parsed.doc_strings(), out, first_seen)
     print(f"[fusion] {method} done: {len(fused)} queries")
     return fused
+
+
+def run_all_methods(runs_dir, qpp_dir, fused_dir, qpp_model: str = None, rrf_k: int = None) -> Dict[str, "os.PathLike"]:
+    """Every fusion method in one go, with the reference's file names and tags (scripts/05_fusion.py:56-152):
+    combsum.res, combmnz.res, rrf.res (tag "rrf"), then -- if qpp_dir exists -- wcombsum_{model}.res,
+    wcombmnz_{model}.res, wrrf_{model}.res and learned_{name}.res for every model pickle under ../models.
+    The run files are parsed and dictionary-encoded ONCE (native reader); each method is one pack + qf_fuse launch +
+    device-side CSR compaction + native writer.  -> {method: output path}."""
+    from pathlib import Path
+    from . import native_io as nio
+    runs_dir, qpp_dir, fused_dir = Path(runs_dir), Path(qpp_dir), Path(fused_dir)
+    qpp_model = qpp_model or config.qpp.default_method
+    rrf_k = rrf_k if rrf_k is not None else config.fusion.rrf_k
+    print("[05_fusion] Running all fusion methods...")
+    print(f"[05_fusion] QPP model for weighted: {qpp_model}")
+    files, suffix = _run_files(str(runs_dir), True)
+    names = [f.replace(suffix, "") for f in files]
+    parsed = nio.parse_runs([os.path.join(str(runs_dir), f) for f in files], names)
+    print(f"[05_fusion] Loaded {len(names)} rankers: {names}")
+    fused_dir.mkdir(parents=True, exist_ok=True)
+    results: Dict[str, Path] = {}
+    for method in ("combsum", "combmnz", "rrf"):
+        out = fused_dir / f"{method}.res"
+        _fuse_parsed(parsed, method, None, qpp_model, str(out), rrf_k, False, tag=method)
+        results[method] = out
+    if qpp_dir.exists():
+        qpp_data = load_qpp_scores(str(qpp_dir))
+        for method in ("wcombsum", "wcombmnz", "wrrf"):
+            out = fused_dir / f"{method}_{qpp_model.lower()}.res"
+            _fuse_parsed(parsed, method, qpp_data, qpp_model, str(out), rrf_k, False)
+            results[method] = out
+        models_dir = fused_dir.parent / "models"
+        runs = None
+        for model_name in ("per_retriever", "multioutput", "mlp"):
+            model_file = models_dir / f"fusion_{model_name}.pkl"
+            if model_file.exists():
+                runs = runs if runs is not None else load_runs(str(runs_dir), use_normalized=True)
+                out = fused_dir / f"learned_{model_name}.res"
+                write_runfile(learned_fusion(runs, qpp_data, str(model_file)), str(out), f"learned-{model_name}")
+                results[f"learned_{model_name}"] = out
+            else:
+                print(f"[05_fusion] Skipping learned ({model_name}) - model not found")
+    else:
+        print(f"[05_fusion] Skipping weighted methods (no QPP at {qpp_dir})")
+    print(f"\n=== Generated {len(results)} fusion runs ===")
+    for method, path in results.items():
+        print(f"  {method}: {path}")
+    return results
 
 
 if __name__ == "__main__":

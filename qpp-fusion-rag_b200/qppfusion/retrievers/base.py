@@ -65,3 +65,20 @@ class BaseRetriever(abc.ABC):
 
     # kept as a static method because callers use BaseRetriever.normalize_scores(docs) (scripts/02_retrieve.py:77)
     normalize_scores = staticmethod(minmax_normalize)
+
+
+def write_run(results: Dict[str, "RetrieverResult"], output_path: str, retriever_name: str, normalize: bool = False) -> None:
+    """TREC run file of a retriever's results (reference scripts/02_retrieve.py:65-82): queries in the reference's
+    order (numeric for "test<N>" ids, else string order), optional per-query min-max, "%.6f" scores -- the rounding that
+    defines the values every later stage sees."""
+    import os
+    d = os.path.dirname(output_path)
+    if d:
+        os.makedirs(d, exist_ok=True)
+    with open(output_path, "w") as f:
+        for qid in sorted(results.keys(), key=lambda x: int(x.replace("test", "")) if x.startswith("test") else x):
+            docs = results[qid].results
+            if normalize:
+                docs = BaseRetriever.normalize_scores(docs)
+            f.write("".join(f"{qid} Q0 {docno} {rank} {score:.6f} {retriever_name}\n" for docno, score, rank in docs))
+    print(f"[02_retrieve] Wrote {output_path}")

@@ -134,6 +134,24 @@ def test_retriever_result_and_normalize_scores():
     assert BaseRetriever.normalize_scores([]) == []
 
 
+def test_write_run_is_the_reference_format(tmp_path):
+    """retrievers.base.write_run == scripts/02_retrieve.py:65-82: qid order, optional min-max, "%.6f"."""
+    from qppfusion.retrievers.base import write_run
+    results = {"test10": RetrieverResult("test10", [("d1", 3.0, 1), ("d2", 1.0, 2)], "BGE"),
+               "test9": RetrieverResult("test9", [("d7", 0.1234567, 1)], "BGE"),
+               "test2": RetrieverResult("test2", [], "BGE")}
+    out = tmp_path / "sub" / "BGE.res"
+    write_run(results, str(out), "BGE")
+    assert out.read_text().splitlines() == ["test9 Q0 d7 1 0.123457 BGE", "test10 Q0 d1 1 3.000000 BGE",
+                                           "test10 Q0 d2 2 1.000000 BGE"]
+    write_run(results, str(tmp_path / "BGE.norm.res"), "BGE", normalize=True)
+    assert (tmp_path / "BGE.norm.res").read_text().splitlines() == [
+        "test9 Q0 d7 1 0.000000 BGE", "test10 Q0 d1 1 1.000000 BGE", "test10 Q0 d2 2 0.000000 BGE"]
+    plain = {"10": RetrieverResult("10", [("a", 1.0, 1)], "X"), "9": RetrieverResult("9", [("b", 2.0, 1)], "X")}
+    write_run(plain, str(tmp_path / "x.res"), "X")
+    assert [ln.split()[0] for ln in (tmp_path / "x.res").read_text().splitlines()] == ["10", "9"]     # string order
+
+
 def _write_runs(tmp_path, seed=3, n_q=9, k=30, adversarial=True):
     rng = np.random.default_rng(seed)
     d = tmp_path / "runs"

@@ -116,6 +116,22 @@ def test_run_fusion_end_to_end_files(tmp_path):
     for m, tag in (("combsum", "combsum"), ("rrf", "rrf-k60"), ("w-rrf", "wrrf-rsd")):
         fusion.run_fusion(m, str(runs_dir), qpp_dir=str(qpp_dir), output_path=str(out))
         assert out.read_text().splitlines()[0].endswith(tag)
+    # scripts/05_fusion.py::run_all_methods: one parse, six methods, the reference's file names and tags
+    fused_dir = tmp_path / "fused"
+    res = fusion.run_all_methods(runs_dir, qpp_dir, fused_dir, qpp_model="RSD", rrf_k=60)
+    assert list(res.keys()) == ["combsum", "combmnz", "rrf", "wcombsum", "wcombmnz", "wrrf"]
+    assert sorted(p.name for p in fused_dir.iterdir()) == ["combmnz.res", "combsum.res", "rrf.res", "wcombmnz_rsd.res",
+                                                          "wcombsum_rsd.res", "wrrf_rsd.res"]
+    strip = lambda text: [ln.rsplit(" ", 1)[0] for ln in text.splitlines()]
+    for m, name, tag in (("combsum", "combsum.res", "combsum"), ("combmnz", "combmnz.res", "combmnz"), ("rrf", "rrf.res", "rrf"),
+                         ("wcombsum", "wcombsum_rsd.res", "wcombsum-rsd"), ("wcombmnz", "wcombmnz_rsd.res", "wcombmnz-rsd"),
+                         ("wrrf", "wrrf_rsd.res", "wrrf-rsd")):
+        fusion.run_fusion(m, str(runs_dir), qpp_dir=str(qpp_dir), qpp_model="RSD", output_path=str(out), rrf_k=60)
+        got = (fused_dir / name).read_text()
+        assert strip(got) == strip(out.read_text()), m
+        assert all(ln.endswith(" " + tag) for ln in got.splitlines()), m
+    res2 = fusion.run_all_methods(runs_dir, tmp_path / "no_qpp", tmp_path / "fused2")
+    assert list(res2.keys()) == ["combsum", "combmnz", "rrf"]
 
 
 def test_qpp_bridge_api():
