@@ -313,7 +313,7 @@ def dense_leg(args, dev, world, rank, Q=Q_NQ, n_docs=None, label="BASELINE confi
 def encoder_leg(args, dev, world, rank, Q=Q_NQ):
     """BGE-base-shaped query encoder (12 x 768, random-init bf16 weights): Q synthetic queries of 5..32 tokens
     (Poisson(11) + 3, the NQ query length profile), query-sharded across ranks, no collective.  kernel = one padded
-    qf_bert_encode call on resident tokens; e2e = host token rows -> length buckets -> H2D -> encode -> D2H float32."""
+    qf_bert_encode call on resident tokens; e2e = host token rows -> packed tokens -> H2D -> qf_bert_encode_packed -> D2H."""
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -397,13 +397,13 @@ def encoder_leg(args, dev, world, rank, Q=Q_NQ):
                        "real_tokens_per_gpu": int(lens.sum()), "sharding": f"query-sharded x{world}, no collective"},
             "linear_layer_tflops": flop_tok * q_local * L / (ms * 1e-3) / 1e12,
             "e2e": {"value": Q / (e2e_ms * 1e-3), "unit": "queries/s", "ms_per_step": e2e_ms,
-                    "h2d_bytes_per_step": int((-(-lens // 8) * 8).sum()) * 4 + q_local * 12,
+                    "h2d_bytes_per_step": int(lens.sum()) * 4 + (q_local + 1) * 4,
                     "d2h_bytes_per_step": q_local * H * 4,
-                    "note": "host token rows -> length buckets of 8 -> one qf_bert_encode call per bucket -> D2H; "
-                            "tokenisation (host WordPiece) not included"},
+                    "note": "host token rows -> packed tokens + cu_seqlens -> H2D -> qf_bert_encode_packed (no padding "
+                            "rows) -> D2H; tokenisation (host WordPiece) not included"},
             # own kernels per call: embed+LN, pool+norm, and per layer attention, 2 x add+LN, GELU (the 4 Linear layers per
-            # block are cuBLASLt launches and not counted); the e2e path makes one call per length bucket (4 here)
-            "gpu_launches": (2 + 4 * cfg.n_layers) * (steps + 3) + 4 * (2 + 4 * cfg.n_layers) * (steps + 1)}
+            # block are cuBLASLt launches and not counted); the e2e path is one packed call per step
+            "gpu_launches": (2 + 4 * cfg.n_layers) * (steps + 3) + (2 + 4 * cfg.n_layers) * (steps + 1)}
 
 
 def run_ours(args):

@@ -304,6 +304,16 @@ QF_API size_t qf_bert_workspace_bytes(const qf_bert_config* cfg, int B, int L);
 QF_API int    qf_bert_encode(const qf_bert_config* cfg, const void* weights_bf16, const int32_t* tokens,
                              const int32_t* lens, int B, int L, void* out_bf16, float* out_f32, int32_t* out_status,
                              void* ws, size_t ws_bytes, void* stream);
+/*
+ * Packed (variable-length) form: the B sequences lie back to back, tokens[M], sequence b = tokens[cu_seqlens[b] ..
+ * cu_seqlens[b+1]) (cu_seqlens int32 [B+1] on the device, cu_seqlens[0] = 0, cu_seqlens[B] = M), no padding rows at
+ * all -- every GEMM row is a real token.  max_len bounds the sequence lengths (sizes the attention kernel's shared
+ * memory); workspace = qf_bert_workspace_bytes(cfg, 1, M).  out_status[b]: bit 0 as above, bit 1 = the sequence's
+ * length is outside [1, max_len] (tokens beyond max_len are ignored, an empty sequence yields a zero vector).
+ */
+QF_API int    qf_bert_encode_packed(const qf_bert_config* cfg, const void* weights_bf16, const int32_t* tokens,
+                                    const int32_t* cu_seqlens, int B, long long M, int max_len, void* out_bf16,
+                                    float* out_f32, int32_t* out_status, void* ws, size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * WordPiece tokeniser (host side, multi-threaded, no CUDA)  --  replaces the HF BertTokenizer call inside

@@ -87,6 +87,31 @@ __device__ __forceinline__ float wmax(float v) {
   return v;
 }
 
+
+// Where sequence b lives in the [tokens, H] activation matrix.  Padded layout (cu == null): rows [b*L, b*L + L), the
+// first `len` are real.  Packed layout (cu = exclusive prefix sums of the lengths, B + 1 entries): rows
+// [cu[b], cu[b+1]), all real; L is then only the longest admissible sequence (sizes the shared memory).
+struct Seq {
+  size_t row0;
+  int len;    // real tokens taking part in attention / pooling (clamped to [0, L])
+  int rows;   // rows of the matrix that belong to the sequence
+};
+__device__ __forceinline__ Seq seq_of(const int32_t* lens, const int32_t* cu, int b, int L) {
+  Seq q;
+  if (cu) {
+    const int s0 = __ldg(cu + b), n = __ldg(cu + b + 1) - s0;
+    q.row0 = (size_t)s0;
+    q.rows = n < 0 ? 0 : n;
+    q.len = q.rows > L ? L : q.rows;
+  } else {
+    int len = lens ? __ldg(lens + b) : L;
+    q.row0 = (size_t)b * L;
+    q.rows = L;
+    q.len = len < 1 ? 1 : (len > L ? L : len);
+  }
+  return q;
+}
+
 // LayerNorm of one token row held as VPL 16-byte vectors per lane (H = 256 * VPL): HF BertLayerNorm = biased variance,
 // y = (x - mean) / sqrt(var + eps) * gamma + beta.
 template <int VPL>
@@ -122,17 +147,31 @@ __device__ __forceinline__ void ln_store(float (&x)[VPL][8], const bf16* gamma, 
 template <int VPL>
 __global__ void __launch_bounds__(256) embed_ln_kernel(const int32_t* tokens, const bf16* word, const bf16* pos,
                                                        const bf16* type, const bf16* gamma, const bf16* beta, float eps,
-                                                       bf16* out, long long M, int L, int V, int32_t* status) {
+                                                       bf16* out, long long M, int L, int V, int32_t* status,
+                                                       const int32_t* cu, int B, int max_pos) {
   const int lane = threadIdx.x & 31;
   const long long m = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (m >= M) return;
   constexpr int H = 256 * VPL;
+  int b, p;
+  if (cu) {                                        // packed: sequence = last b with cu[b] <= m, position inside it
+    int lo = 0, hi = B - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if ((long long)__ldg(cu + mid) <= m) lo = mid; else hi = mid - 1;
+    }
+    b = lo;
+    p = (int)(m - __ldg(cu + b));
+    p = p < 0 ? 0 : (p >= max_pos ? max_pos - 1 : p);
+  } else {
+    b = (int)(m / L);
+    p = (int)(m % L);
+  }
   int tok = __ldg(tokens + m);
   if (tok < 0 || tok >= V) {                       // never read outside the table; reported, not repaired silently
-    if (lane == 0 && status) atomicOr(status + m / L, 1);
+    if (lane == 0 && status) atomicOr(status + b, 1);
     tok = 0;
   }
-  const int p = (int)(m % L);
   float x[VPL][8];
 #pragma unroll
   for (int v = 0; v < VPL; ++v) {
@@ -185,18 +224,19 @@ __host__ __device__ inline size_t attn_q_offset(int L) {
   return (((size_t)L * KPAD + (size_t)L * HD) * sizeof(bf16) + 15) & ~size_t(15);
 }
 template <int TL>
-__global__ void __launch_bounds__(128) attn_kernel(const bf16* qkv, const int32_t* lens, bf16* ctx, int L, int H) {
+__global__ void __launch_bounds__(128) attn_kernel(const bf16* qkv, const int32_t* lens, const int32_t* cu, bf16* ctx,
+                                                   int L, int H) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   bf16* sK = reinterpret_cast<bf16*>(smem_raw);                       // [L][KPAD]
   bf16* sV = sK + (size_t)L * KPAD;                                    // [L][HD]
   float* sQ = reinterpret_cast<float*>(smem_raw + attn_q_offset(L));   // [4][HD], 16-byte aligned for any L
   const int h = blockIdx.x, b = blockIdx.y;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  int len = lens ? __ldg(lens + b) : L;
-  len = len < 1 ? 1 : (len > L ? L : len);
-  const size_t row0 = (size_t)b * L;
+  const Seq sq = seq_of(lens, cu, b, L);
+  const int len = sq.len, rows = sq.rows;
+  const size_t row0 = sq.row0;
   const int H3 = 3 * H;
-  for (int i = tid; i < L * (HD / 2); i += 128) {                      // bf16 pairs
+  for (int i = tid; i < len * (HD / 2); i += 128) {                    // bf16 pairs of the real keys
     const int j = i / (HD / 2), d2 = i % (HD / 2);
     const bf16* base = qkv + (row0 + j) * H3 + h * HD + 2 * d2;
     *reinterpret_cast<__nv_bfloat162*>(sK + (size_t)j * KPAD + 2 * d2) = *reinterpret_cast<const __nv_bfloat162*>(base + H);
@@ -204,7 +244,7 @@ __global__ void __launch_bounds__(128) attn_kernel(const bf16* qkv, const int32_
   }
   __syncthreads();
   float* q = sQ + warp * HD;
-  for (int i = warp; i < L; i += 4) {
+  for (int i = warp; i < rows; i += 4) {
     if (i >= len) {                                                    // padding token: never read by a real one
       bf16* out = ctx + (row0 + i) * H + h * HD;
       out[lane] = out[lane + 32] = __float2bfloat16_rn(0.f);
@@ -284,16 +324,18 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 
 template <int LT>   // L rounded up to 32, 64 or 128
 __global__ void __launch_bounds__(128) attn_mma_kernel(const bf16* __restrict__ qkv, const int32_t* __restrict__ lens,
-                                                       bf16* __restrict__ ctx, int L, int H) {
+                                                       const int32_t* __restrict__ cu, bf16* __restrict__ ctx, int L,
+                                                       int H) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int NT = LT / 8;                                            // key tiles of 8
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int h = blockIdx.x * 4 + warp, b = blockIdx.y;
   bf16* sK = reinterpret_cast<bf16*>(smem_raw) + (size_t)warp * 2 * LT * VSTR;
   bf16* sV = sK + (size_t)LT * VSTR;
-  int len = lens ? __ldg(lens + b) : L;
-  len = len < 1 ? 1 : (len > L ? L : len);
-  const size_t row0 = (size_t)b * L;
+  const Seq sq = seq_of(lens, cu, b, L);
+  const int len = sq.len, rows = sq.rows;
+  if (rows == 0) return;                                                // (packed layout only) empty sequence
+  const size_t row0 = sq.row0;
   const int H3 = 3 * H;
   const int kt_n = (len + 7) >> 3;                                      // key tiles that hold a real key
   const int kt16 = (len + 15) >> 4;                                     // the same in steps of 16 (k steps of P.V)
@@ -315,8 +357,8 @@ __global__ void __launch_bounds__(128) attn_mma_kernel(const bf16* __restrict__ 
   const int mt_n = (len + 15) >> 4;
   for (int mt = 0; mt < mt_n; ++mt) {
     const int ra = mt * 16 + g, rb = ra + 8;                            // the two query rows this lane holds
-    const bf16* qa = qkv + (row0 + min(ra, L - 1)) * H3 + h * HD + t4 * 2;
-    const bf16* qb = qkv + (row0 + min(rb, L - 1)) * H3 + h * HD + t4 * 2;
+    const bf16* qa = qkv + (row0 + min(ra, rows - 1)) * H3 + h * HD + t4 * 2;
+    const bf16* qb = qkv + (row0 + min(rb, rows - 1)) * H3 + h * HD + t4 * 2;
     uint32_t aq[4][4];
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {
@@ -392,7 +434,7 @@ __global__ void __launch_bounds__(128) attn_mma_kernel(const bf16* __restrict__ 
     }
     bf16* oa = ctx + (row0 + ra) * H + h * HD + t4 * 2;
     bf16* ob = ctx + (row0 + rb) * H + h * HD + t4 * 2;
-    const bool wa = ra < L, wb = rb < L;                                // rows in [len, L) get zeros, rows >= L nothing
+    const bool wa = ra < rows, wb = rb < rows;                          // rows in [len, rows) get zeros, beyond: nothing
     const float fa = ra < len ? inva : 0.f, fb = rb < len ? invb : 0.f;
 #pragma unroll
     for (int dt = 0; dt < 8; ++dt) {
@@ -401,30 +443,32 @@ __global__ void __launch_bounds__(128) attn_mma_kernel(const bf16* __restrict__ 
     }
   }
   // context rows of the remaining padding tokens: zeros (8 lanes x 16 bytes per row)
-  for (int j = mt_n * 16 + (lane >> 3); j < L; j += 4)
+  for (int j = mt_n * 16 + (lane >> 3); j < rows; j += 4)
     *reinterpret_cast<uint4*>(ctx + (row0 + j) * H + h * HD + (lane & 7) * 8) = make_uint4(0, 0, 0, 0);
 }
 
 template <int VPL>
-__global__ void __launch_bounds__(256) pool_norm_kernel(const bf16* x, const int32_t* lens, int L, int pooling,
-                                                        bf16* out_bf16, float* out_f32, int B) {
+__global__ void __launch_bounds__(256) pool_norm_kernel(const bf16* x, const int32_t* lens, const int32_t* cu, int L,
+                                                        int pooling, bf16* out_bf16, float* out_f32, int B,
+                                                        int32_t* status) {
   const int lane = threadIdx.x & 31;
   const int b = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (b >= B) return;
   constexpr int H = 256 * VPL;
-  int len = lens ? __ldg(lens + b) : L;
-  len = len < 1 ? 1 : (len > L ? L : len);
+  const Seq sq = seq_of(lens, cu, b, L);
+  const int len = sq.len;
+  if (cu && lane == 0 && status && (sq.rows < 1 || sq.rows > L)) atomicOr(status + b, 2);   // cu_seqlens vs max_len
   float acc[VPL][8];
 #pragma unroll
   for (int v = 0; v < VPL; ++v)
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[v][i] = 0.f;
-  const int n_tok = pooling == QF_BERT_POOL_MEAN ? len : 1;
+  const int n_tok = len < 1 ? 0 : (pooling == QF_BERT_POOL_MEAN ? len : 1);    // empty sequence: zero vector
   for (int t = 0; t < n_tok; ++t) {
 #pragma unroll
     for (int v = 0; v < VPL; ++v) {
       float f[8];
-      unpack8(*reinterpret_cast<const uint4*>(x + ((size_t)b * L + t) * H + (v * 32 + lane) * 8), f);
+      unpack8(*reinterpret_cast<const uint4*>(x + (sq.row0 + t) * H + (v * 32 + lane) * 8), f);
 #pragma unroll
       for (int i = 0; i < 8; ++i) acc[v][i] += f[i];
     }
@@ -434,7 +478,7 @@ __global__ void __launch_bounds__(256) pool_norm_kernel(const bf16* x, const int
   for (int v = 0; v < VPL; ++v)
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      acc[v][i] /= (float)n_tok;
+      acc[v][i] /= (float)(n_tok > 0 ? n_tok : 1);
       ss += acc[v][i] * acc[v][i];
     }
   const float inv = 1.0f / fmaxf(sqrtf(wsum(ss)), 1e-12f);              // torch.nn.functional.normalize(eps=1e-12)
@@ -562,9 +606,10 @@ int check_config(const qf_bert_config* c) {
 }
 
 template <int VPL>
-int encode_impl(const qf_bert_config& c, const bf16* wts, const int32_t* tokens, const int32_t* lens, int B, int L,
-                bf16* out_bf16, float* out_f32, int32_t* out_status, unsigned char* ws, cudaStream_t st) {
-  const long long M = (long long)B * L;
+int encode_impl(const qf_bert_config& c, const bf16* wts, const int32_t* tokens, const int32_t* lens, const int32_t* cu,
+                long long M_packed, int B, int L, bf16* out_bf16, float* out_f32, int32_t* out_status, unsigned char* ws,
+                cudaStream_t st) {
+  const long long M = cu ? M_packed : (long long)B * L;        // packed: L = longest admissible sequence
   const Offsets o = offsets(c);
   const Ws w = ws_layout(c, M);
   bf16* X = reinterpret_cast<bf16*>(ws + w.x);
@@ -577,7 +622,7 @@ int encode_impl(const qf_bert_config& c, const bf16* wts, const int32_t* tokens,
   const unsigned tok_blocks = (unsigned)((M + 7) / 8);
   if (out_status) QF_CUDA_TRY(cudaMemsetAsync(out_status, 0, (size_t)B * sizeof(int32_t), st));
   embed_ln_kernel<VPL><<<tok_blocks, 256, 0, st>>>(tokens, wts + o.word, wts + o.pos, wts + o.type, wts + o.eg,
-                                                   wts + o.eb, c.ln_eps, X, M, L, c.vocab, out_status);
+                                                   wts + o.eb, c.ln_eps, X, M, L, c.vocab, out_status, cu, B, c.max_pos);
   QF_CUDA_TRY(cudaGetLastError());
   const int tl = (L + 31) / 32;
   const bool use_mma = L <= 128;                    // query-length sequences: the tensor-core kernel, one warp per head
@@ -592,7 +637,7 @@ int encode_impl(const qf_bert_config& c, const bf16* wts, const int32_t* tokens,
     const bf16* lw = wts + o.layer0 + (size_t)l * o.per_layer;
     int rc = gemm_bias(lw + o.wqkv, X, lw + o.bqkv, QKV, M, 3 * H, H, lt_ws, st);
     if (rc != QF_OK) return rc;
-    attn<<<attn_grid, 128, attn_smem, st>>>(QKV, lens, CTX, L, H);
+    attn<<<attn_grid, 128, attn_smem, st>>>(QKV, lens, cu, CTX, L, H);
     QF_CUDA_TRY(cudaGetLastError());
     rc = gemm_bias(lw + o.wo, CTX, lw + o.bo, T1, M, H, H, lt_ws, st);
     if (rc != QF_OK) return rc;
@@ -609,9 +654,21 @@ int encode_impl(const qf_bert_config& c, const bf16* wts, const int32_t* tokens,
     add_ln_kernel<VPL><<<tok_blocks, 256, 0, st>>>(T1, X, lw + o.g2, lw + o.b2, c.ln_eps, X, M);
     QF_CUDA_TRY(cudaGetLastError());
   }
-  pool_norm_kernel<VPL><<<(unsigned)((B + 7) / 8), 256, 0, st>>>(X, lens, L, c.pooling, out_bf16, out_f32, B);
+  pool_norm_kernel<VPL><<<(unsigned)((B + 7) / 8), 256, 0, st>>>(X, lens, cu, L, c.pooling, out_bf16, out_f32, B,
+                                                                 out_status);
   QF_CUDA_TRY(cudaGetLastError());
   return QF_OK;
+}
+
+int encode_dispatch(const qf_bert_config& c, const bf16* w, const int32_t* tokens, const int32_t* lens, const int32_t* cu,
+                    long long M, int B, int L, bf16* ob, float* out_f32, int32_t* out_status, unsigned char* wsb,
+                    cudaStream_t st) {
+  switch (c.hidden / 256) {
+    case 1: return encode_impl<1>(c, w, tokens, lens, cu, M, B, L, ob, out_f32, out_status, wsb, st);
+    case 2: return encode_impl<2>(c, w, tokens, lens, cu, M, B, L, ob, out_f32, out_status, wsb, st);
+    case 3: return encode_impl<3>(c, w, tokens, lens, cu, M, B, L, ob, out_f32, out_status, wsb, st);
+    default: return encode_impl<4>(c, w, tokens, lens, cu, M, B, L, ob, out_f32, out_status, wsb, st);
+  }
 }
 
 }  // namespace
@@ -643,10 +700,28 @@ extern "C" int qf_bert_encode(const qf_bert_config* c, const void* weights_bf16,
   const bf16* w = reinterpret_cast<const bf16*>(weights_bf16);
   bf16* ob = reinterpret_cast<bf16*>(out_bf16);
   unsigned char* wsb = reinterpret_cast<unsigned char*>(ws);
-  switch (c->hidden / 256) {
-    case 1: return encode_impl<1>(*c, w, tokens, lens, B, L, ob, out_f32, out_status, wsb, st);
-    case 2: return encode_impl<2>(*c, w, tokens, lens, B, L, ob, out_f32, out_status, wsb, st);
-    case 3: return encode_impl<3>(*c, w, tokens, lens, B, L, ob, out_f32, out_status, wsb, st);
-    default: return encode_impl<4>(*c, w, tokens, lens, B, L, ob, out_f32, out_status, wsb, st);
-  }
+  return encode_dispatch(*c, w, tokens, lens, nullptr, 0, B, L, ob, out_f32, out_status, wsb, st);
+}
+
+extern "C" int qf_bert_encode_packed(const qf_bert_config* c, const void* weights_bf16, const int32_t* tokens,
+                                     const int32_t* cu_seqlens, int B, long long M, int max_len, void* out_bf16,
+                                     float* out_f32, int32_t* out_status, void* ws, size_t ws_bytes, void* stream) {
+  int rc = check_config(c);
+  if (rc != QF_OK) return rc;
+  QF_REQUIRE(B >= 0 && M >= 0 && max_len >= 1, QF_E_INVALID, "qf_bert_encode_packed: bad sizes B=%d M=%lld max_len=%d", B, M,
+             max_len);
+  QF_REQUIRE(max_len <= c->max_pos && max_len <= 512, QF_E_UNSUPPORTED,
+             "qf_bert_encode_packed: max_len=%d exceeds max_pos=%d / 512", max_len, c->max_pos);
+  if (B == 0) return QF_OK;
+  QF_REQUIRE(M >= 1 && M <= (long long)B * max_len, QF_E_INVALID,
+             "qf_bert_encode_packed: M=%lld outside [1, B * max_len = %lld]", M, (long long)B * max_len);
+  QF_REQUIRE(weights_bf16 && tokens && cu_seqlens && ws && (out_bf16 || out_f32), QF_E_INVALID,
+             "qf_bert_encode_packed: null pointer argument");
+  QF_REQUIRE(ws_bytes >= ws_layout(*c, M).total, QF_E_WORKSPACE, "qf_bert_encode_packed: workspace %zu < %zu bytes",
+             ws_bytes, ws_layout(*c, M).total);
+  rc = qf::check_device();
+  if (rc != QF_OK) return rc;
+  return encode_dispatch(*c, reinterpret_cast<const bf16*>(weights_bf16), tokens, nullptr, cu_seqlens, M, B, max_len,
+                         reinterpret_cast<bf16*>(out_bf16), out_f32, out_status, reinterpret_cast<unsigned char*>(ws),
+                         reinterpret_cast<cudaStream_t>(stream));
 }

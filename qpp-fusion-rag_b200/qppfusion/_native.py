@@ -75,6 +75,7 @@ PROTOTYPES = {
     "qf_bert_weight_elems": (_sz, [_vp]),
     "qf_bert_workspace_bytes": (_sz, [_vp, _i, _i]),
     "qf_bert_encode": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "qf_bert_encode_packed": (_i, [_vp, _vp, _vp, _vp, _i, ctypes.c_longlong, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "qf_wordpiece_create": (_i, [ctypes.c_char_p, _sz, _i, _vp]),
     "qf_wordpiece_free": (None, [_vp]),
     "qf_wordpiece_encode": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),

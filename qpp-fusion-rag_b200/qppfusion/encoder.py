@@ -333,27 +333,52 @@ class BertQueryEncoder:
             raise ValueError(f"token id outside [0, {c.vocab}) in rows {bad}")
         return out_b, out_f
 
-    def encode_token_lists(self, rows: Sequence[Sequence[int]], bucket: int = 8) -> Tuple[torch.Tensor, torch.Tensor]:
+    def encode_token_lists(self, rows: Sequence[Sequence[int]], max_tokens: int = 1 << 18
+                           ) -> Tuple[torch.Tensor, torch.Tensor]:
         """Token id rows ([CLS] ... [SEP] included) -> (bf16 [n, H], float32 [n, H]) on the device.
-        Rows are grouped by their length rounded up to `bucket` tokens and each group is one qf_bert_encode call
-        padded only to its own length: a query batch whose lengths spread from 5 to 32 tokens spends its GEMM
-        rows on real tokens instead of on padding up to the longest query (sentence-transformers sorts by length
-        for the same reason).  Groups are further cut at `batch_size` queries."""
+        The rows go to the device PACKED back to back (qf_bert_encode_packed: tokens [M] + prefix sums of the
+        lengths), so every GEMM row is a real token -- a query batch whose lengths spread from 5 to 32 tokens costs
+        its 14-token average, not the longest query.  Batches are cut at max_tokens tokens (workspace ~15 kB per
+        token for bert-base) and at batch_size rows."""
         n, H = len(rows), self.cfg.hidden
         out_b = torch.empty((n, H), dtype=torch.bfloat16, device=self.device)
         out_f = torch.empty((n, H), dtype=torch.float32, device=self.device)
         if n == 0:
             return out_b, out_f
-        pad_id = self.tokenizer.pad_id if self.tokenizer is not None else 0
-        statuses: list = []
-        for idx, toks, lens in bucket_token_rows(rows, bucket, self.cfg.max_pos, self.batch_size, pad_id):
-            b, f = self.encode_tokens(torch.from_numpy(toks).to(self.device, non_blocking=True),
-                                      torch.from_numpy(lens).to(self.device, non_blocking=True), statuses)
-            ix = torch.from_numpy(idx).to(self.device, non_blocking=True)
-            out_b[ix] = b
-            out_f[ix] = f
-        if int(torch.stack([st.max() for st in statuses]).max().item()) != 0:
+        lens = np.fromiter((len(r) for r in rows), dtype=np.int64, count=n)
+        if lens.min() < 1 or lens.max() > self.cfg.max_pos:
+            raise ValueError(f"row lengths must lie in [1, {self.cfg.max_pos}]")
+        if isinstance(rows[0], np.ndarray):
+            flat = np.concatenate(rows).astype(np.int32, copy=False)
+        else:
+            import itertools
+            flat64 = np.fromiter(itertools.chain.from_iterable(rows), dtype=np.int64, count=int(lens.sum()))
+            if flat64.size and (flat64.min() < -2**31 or flat64.max() >= 2**31):
+                raise ValueError("token id does not fit int32")
+            flat = flat64.astype(np.int32)
+        offs = np.concatenate(([0], np.cumsum(lens)))
+        c = self.cfg
+        kw = dict(n_layers=c.n_layers, hidden=c.hidden, heads=c.heads, ffn=c.ffn, vocab=c.vocab, max_pos=c.max_pos,
+                  pooling=c.pooling_id, ln_eps=c.ln_eps)
+        statuses = []
+        s = 0
+        while s < n:                                   # greedy cut: <= batch_size rows and <= max_tokens tokens
+            e = int(np.searchsorted(offs, offs[s] + max_tokens, side="right")) - 1
+            e = min(max(e, s + 1), s + self.batch_size, n)
+            cu = (offs[s:e + 1] - offs[s]).astype(np.int32)
+            toks = flat[offs[s]:offs[e]]
+            b, f, st = ops.bert_encode_packed(self.weights, torch.from_numpy(toks).to(self.device, non_blocking=True),
+                                              torch.from_numpy(cu).to(self.device, non_blocking=True),
+                                              int(lens[s:e].max()), **kw)
+            out_b[s:e] = b
+            out_f[s:e] = f
+            statuses.append(st.max())
+            s = e
+        worst = int(torch.stack(statuses).max().item())
+        if worst & 1:
             raise ValueError(f"token id outside [0, {self.cfg.vocab}) in the batch")
+        if worst:
+            raise RuntimeError("qf_bert_encode_packed: inconsistent sequence lengths")
         return out_b, out_f
 
     def _encode(self, queries: Sequence[str]) -> Tuple[torch.Tensor, torch.Tensor]:

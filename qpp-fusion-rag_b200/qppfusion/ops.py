@@ -346,3 +346,50 @@ def bert_encode(weights: torch.Tensor, tokens: torch.Tensor, lens: torch.Tensor,
     """-> (embeddings bf16 [B, H] -- the query operand of dense_topk, embeddings f32 [B, H], status int32 [B])."""
     return torch.ops.qppfusion.bert_encode(weights, tokens, lens, int(n_layers), int(hidden), int(heads), int(ffn),
                                            int(vocab), int(max_pos), int(pooling), float(ln_eps))
+
+
+@torch.library.custom_op("qppfusion::bert_encode_packed", mutates_args=())
+def _bert_encode_packed_op(weights: torch.Tensor, tokens: torch.Tensor, cu_seqlens: torch.Tensor, max_len: int,
+                           n_layers: int, hidden: int, heads: int, ffn: int, vocab: int, max_pos: int, pooling: int,
+                           ln_eps: float) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    dev = N.require_cuda(weights, tokens, cu_seqlens)
+    if weights.dtype != torch.bfloat16 or weights.dim() != 1:
+        raise TypeError("weights must be the packed bf16 blob (qppfusion.encoder.pack_bert_weights)")
+    if tokens.dtype != torch.int32 or tokens.dim() != 1 or cu_seqlens.dtype != torch.int32 or cu_seqlens.dim() != 1 \
+            or cu_seqlens.numel() < 1:
+        raise TypeError("tokens int32 [M] and cu_seqlens int32 [B + 1] expected")
+    cfg = N.BertConfigC(n_layers, hidden, heads, ffn, vocab, max_pos, pooling, ln_eps)
+    cp = ctypes.addressof(cfg)
+    need = N.lib().qf_bert_weight_elems(cp)
+    if need == 0:
+        raise N.NativeError(-2, N.lib().qf_last_error().decode("utf-8", "replace"))
+    if weights.numel() != need:
+        raise ValueError(f"weight blob has {weights.numel()} elements, the config needs {need}")
+    B, M = cu_seqlens.numel() - 1, tokens.numel()
+    out_b = torch.empty((B, hidden), dtype=torch.bfloat16, device=dev)
+    out_f = torch.empty((B, hidden), dtype=torch.float32, device=dev)
+    status = torch.empty((B,), dtype=torch.int32, device=dev)
+    ws = torch.empty((max(N.lib().qf_bert_workspace_bytes(cp, 1, max(M, 1)), 8),), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        N.check(N.lib().qf_bert_encode_packed(cp, N.ptr(weights), N.ptr(tokens), N.ptr(cu_seqlens), B, M, max_len,
+                                              N.ptr(out_b), N.ptr(out_f), N.ptr(status), N.ptr(ws), ws.numel(),
+                                              N.stream_ptr(dev)))
+    return out_b, out_f, status
+
+
+@_bert_encode_packed_op.register_fake
+def _(weights, tokens, cu_seqlens, max_len, n_layers, hidden, heads, ffn, vocab, max_pos, pooling, ln_eps):
+    B = cu_seqlens.shape[0] - 1
+    return (torch.empty((B, hidden), dtype=torch.bfloat16, device=tokens.device),
+            torch.empty((B, hidden), dtype=torch.float32, device=tokens.device),
+            torch.empty((B,), dtype=torch.int32, device=tokens.device))
+
+
+def bert_encode_packed(weights: torch.Tensor, tokens: torch.Tensor, cu_seqlens: torch.Tensor, max_len: int, *,
+                       n_layers: int, hidden: int, heads: int, ffn: int, vocab: int, max_pos: int,
+                       pooling: int = N.BERT_POOL_CLS, ln_eps: float = 1e-12):
+    """Variable-length form of bert_encode: tokens int32 [M] back to back, cu_seqlens int32 [B + 1] (prefix sums of the
+    lengths), max_len >= the longest sequence.  -> (bf16 [B, H], f32 [B, H], status int32 [B])."""
+    return torch.ops.qppfusion.bert_encode_packed(weights, tokens, cu_seqlens, int(max_len), int(n_layers), int(hidden),
+                                                  int(heads), int(ffn), int(vocab), int(max_pos), int(pooling),
+                                                  float(ln_eps))

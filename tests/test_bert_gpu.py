@@ -102,6 +102,47 @@ def test_bge_base_shape_against_oracle():
     assert ((got * ref).sum(1) >= 0.998).all(), (got * ref).sum(1)
 
 
+def test_packed_layout_matches_padded_layout_and_reports_bad_lengths():
+    """qf_bert_encode_packed (tokens back to back + cu_seqlens) against the padded call on the same sequences: the
+    per-token arithmetic is identical, only the GEMM row count differs; length errors are reported per sequence."""
+    from qppfusion import ops
+    from qppfusion.encoder import BertConfig, pack_bert_weights
+    cfg_hf = dict(CFG, max_position_embeddings=256)
+    sd = bert_small_state(seed=4, cfg=cfg_hf)
+    cfg = BertConfig.from_hf(cfg_hf)
+    dev = torch.device("cuda", 0)
+    blob = pack_bert_weights({k: torch.from_numpy(v) for k, v in sd.items()}, cfg).to(dev)
+    kw = dict(n_layers=cfg.n_layers, hidden=cfg.hidden, heads=cfg.heads, ffn=cfg.ffn, vocab=cfg.vocab, max_pos=cfg.max_pos)
+    rng = np.random.default_rng(12)
+    for L, pooling in ((24, 0), (97, 1), (200, 0)):               # mma kernel (32 / 128 wide) and the long-sequence kernel
+        B = 13
+        lens = rng.integers(1, L + 1, size=B).astype(np.int32)
+        lens[0], lens[1] = L, 1
+        tokens = rng.integers(0, cfg.vocab, size=(B, L)).astype(np.int32)
+        _, pad_f, st0 = ops.bert_encode(blob, torch.from_numpy(tokens).to(dev), torch.from_numpy(lens).to(dev), pooling=pooling, **kw)
+        flat = np.concatenate([tokens[i, :lens[i]] for i in range(B)])
+        cu = np.concatenate(([0], np.cumsum(lens))).astype(np.int32)
+        out_b, out_f, st = ops.bert_encode_packed(blob, torch.from_numpy(flat).to(dev), torch.from_numpy(cu).to(dev), L,
+                                                  pooling=pooling, **kw)
+        assert st.cpu().tolist() == [0] * B and st0.cpu().tolist() == [0] * B
+        assert (out_f - pad_f).abs().max().item() <= 2e-3, (L, pooling)
+        assert torch.equal(out_b, out_f.to(torch.bfloat16))
+        ref = bert_oracle.bert_encode({k: bert_oracle._bf16_round(v) for k, v in sd.items()}, tokens, lens, n_layers=2,
+                                      heads=4, pooling="mean" if pooling else "cls")
+        assert ((out_f.double().cpu().numpy() * ref).sum(1) >= 0.9995).all()
+    # a sequence longer than max_len and an empty one: flagged (bit 1), the others unaffected
+    lens = np.array([5, 40, 0, 7], dtype=np.int32)
+    flat = rng.integers(0, cfg.vocab, size=int(lens.sum())).astype(np.int32)
+    flat[2] = cfg.vocab + 9                                        # bad token id in sequence 0 (bit 0)
+    cu = np.concatenate(([0], np.cumsum(lens))).astype(np.int32)
+    _, f, st = ops.bert_encode_packed(blob, torch.from_numpy(flat).to(dev), torch.from_numpy(cu).to(dev), 32, **kw)
+    assert st.cpu().tolist() == [1, 2, 2, 0]
+    assert float(f[2].abs().max()) == 0.0 and torch.isfinite(f).all()
+    solo = ops.bert_encode_packed(blob, torch.from_numpy(flat[45:]).to(dev),
+                                  torch.tensor([0, 7], dtype=torch.int32, device=dev), 32, **kw)[1]
+    assert (solo[0] - f[3]).abs().max().item() <= 2e-3
+
+
 def test_bucketed_token_lists_match_one_padded_call():
     from qppfusion.encoder import BertConfig, BertQueryEncoder, WordPieceTokenizer
     vocab = {t: i for i, t in enumerate(synthetic_vocab())}
