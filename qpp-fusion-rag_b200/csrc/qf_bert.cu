@@ -253,7 +253,7 @@ __global__ void __launch_bounds__(128) attn_kernel(const bf16* qkv, const int32_
   bf16* sK = reinterpret_cast<bf16*>(smem_raw);                       // [L][KPAD]
   bf16* sV = sK + (size_t)L * KPAD;                                    // [L][HD]
   float* sQ = reinterpret_cast<float*>(smem_raw + attn_q_offset(L));   // [4][HD], 16-byte aligned for any L
-  const int h = blockIdx.x, b = blockIdx.y;
+  const int h = blockIdx.y, b = blockIdx.x;                            // sequences on x: no 65535 limit
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const Seq sq = seq_of(lens, cu, b, L);
   const int len = sq.len, rows = sq.rows;
@@ -352,7 +352,7 @@ __global__ void __launch_bounds__(128) attn_mma_kernel(const bf16* __restrict__ 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int NT = LT / 8;                                            // key tiles of 8
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int h = blockIdx.x * 4 + warp, b = blockIdx.y;
+  const int h = blockIdx.y * 4 + warp, b = blockIdx.x;                  // sequences on x: no 65535 limit
   bf16* sK = reinterpret_cast<bf16*>(smem_raw) + (size_t)warp * 2 * LT * VSTR;
   bf16* sV = sK + (size_t)LT * VSTR;
   const Seq sq = seq_of(lens, cu, b, L);
@@ -587,6 +587,14 @@ int gemm_bias(const bf16* W, const bf16* X, const bf16* bias, bf16* Y, long long
         return QF_E_UNSUPPORTED;
       }
       plan.algo = res.algo;
+      if (g_plans.size() >= 256) {                     // bounded cache: drop the oldest shape
+        const Plan& old = g_plans.front();
+        cublasLtMatmulDescDestroy(old.op);
+        cublasLtMatrixLayoutDestroy(old.a);
+        cublasLtMatrixLayoutDestroy(old.b);
+        cublasLtMatrixLayoutDestroy(old.c);
+        g_plans.erase(g_plans.begin());
+      }
       g_plans.push_back(plan);
     }
     // the descriptor carries the bias pointer: set and launch under the lock (launches are asynchronous and short)
@@ -600,10 +608,19 @@ int gemm_bias(const bf16* W, const bf16* X, const bf16* bias, bf16* Y, long long
 
 size_t a256(size_t x) { return (x + 255) & ~size_t(255); }
 
+// Rows the Linear layers run on: M rounded up (128 below 4096 rows, 512 above), so that the packed layout's ever-changing
+// token counts map onto few GEMM shapes (one cuBLASLt plan + heuristic query per shape).  The extra rows hold whatever
+// the workspace held: rows are independent in every kernel of the encoder and nothing reads them back.
+long long gemm_rows(long long M) {
+  const long long g = M < 4096 ? 128 : 512;
+  return (M + g - 1) / g * g;
+}
+
 struct Ws {
   size_t x, qkv, ctx, t1, ff, lt, total;
 };
-Ws ws_layout(const qf_bert_config& c, long long M) {
+Ws ws_layout(const qf_bert_config& c, long long M_tokens) {
+  const long long M = gemm_rows(M_tokens);
   Ws w{};
   size_t a = 0;
   w.x = a;   a += a256((size_t)M * c.hidden * 2);
@@ -642,6 +659,7 @@ int encode_impl(const qf_bert_config& c, const bf16* wts, const int32_t* tokens,
   bf16* FF = reinterpret_cast<bf16*>(ws + w.ff);
   void* lt_ws = ws + w.lt;
   const int H = c.hidden, F = c.ffn;
+  const long long Mg = gemm_rows(M);
   const unsigned tok_blocks = (unsigned)((M + 7) / 8);
   if (out_status) QF_CUDA_TRY(cudaMemsetAsync(out_status, 0, (size_t)B * sizeof(int32_t), st));
   embed_ln_kernel<VPL><<<tok_blocks, 256, 0, st>>>(tokens, wts + o.word, wts + o.pos, wts + o.type, wts + o.eg,
@@ -655,24 +673,24 @@ int encode_impl(const qf_bert_config& c, const bf16* wts, const int32_t* tokens,
   auto attn = use_mma ? (lt == 32 ? attn_mma_kernel<32> : lt == 64 ? attn_mma_kernel<64> : attn_mma_kernel<128>)
               : tl <= 8 ? attn_kernel<8> : attn_kernel<16>;
   QF_CUDA_TRY(cudaFuncSetAttribute(attn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem));
-  const dim3 attn_grid(use_mma ? (unsigned)c.heads / 4 : (unsigned)c.heads, (unsigned)B);
+  const dim3 attn_grid((unsigned)B, use_mma ? (unsigned)c.heads / 4 : (unsigned)c.heads);
   for (int l = 0; l < c.n_layers; ++l) {
     const bf16* lw = wts + o.layer0 + (size_t)l * o.per_layer;
-    int rc = gemm_bias(lw + o.wqkv, X, lw + o.bqkv, QKV, M, 3 * H, H, lt_ws, st);
+    int rc = gemm_bias(lw + o.wqkv, X, lw + o.bqkv, QKV, Mg, 3 * H, H, lt_ws, st);
     if (rc != QF_OK) return rc;
     attn<<<attn_grid, 128, attn_smem, st>>>(QKV, lens, cu, CTX, L, H);
     QF_CUDA_TRY(cudaGetLastError());
-    rc = gemm_bias(lw + o.wo, CTX, lw + o.bo, T1, M, H, H, lt_ws, st);
+    rc = gemm_bias(lw + o.wo, CTX, lw + o.bo, T1, Mg, H, H, lt_ws, st);
     if (rc != QF_OK) return rc;
     add_ln_kernel<VPL><<<tok_blocks, 256, 0, st>>>(T1, X, lw + o.g1, lw + o.b1, c.ln_eps, X, M);
     QF_CUDA_TRY(cudaGetLastError());
-    rc = gemm_bias(lw + o.w1, X, lw + o.bi1, FF, M, F, H, lt_ws, st);
+    rc = gemm_bias(lw + o.w1, X, lw + o.bi1, FF, Mg, F, H, lt_ws, st);
     if (rc != QF_OK) return rc;
     const size_t n8 = (size_t)M * F / 8;
     const size_t gelu_cap = (size_t)qf::sm_count() * 32, gelu_need = (n8 + 255) / 256;
     gelu_kernel<<<(unsigned)(gelu_need < gelu_cap ? gelu_need : gelu_cap), 256, 0, st>>>(FF, n8);
     QF_CUDA_TRY(cudaGetLastError());
-    rc = gemm_bias(lw + o.w2, FF, lw + o.bi2, T1, M, H, F, lt_ws, st);
+    rc = gemm_bias(lw + o.w2, FF, lw + o.bi2, T1, Mg, H, F, lt_ws, st);
     if (rc != QF_OK) return rc;
     add_ln_kernel<VPL><<<tok_blocks, 256, 0, st>>>(T1, X, lw + o.g2, lw + o.b2, c.ln_eps, X, M);
     QF_CUDA_TRY(cudaGetLastError());

@@ -236,3 +236,20 @@ def test_from_pretrained_and_tct_colbert_corpus_encoding(tmp_path):
     assert torch.equal(r2.corpus, r.corpus)
     with pytest.raises(FileNotFoundError):
         TCTColBERTRetriever(corpus, cache_dir=str(tmp_path / "none"), use_fp16=True)                     # no encoder
+
+
+def test_more_than_65535_sequences_in_one_call():
+    """Sequences ride on grid.x: a call with more sequences than gridDim.y allows (65 535) works."""
+    cfg = dict(CFG, num_hidden_layers=1)
+    sd = bert_small_state(seed=8, cfg=cfg)
+    rng = np.random.default_rng(3)
+    B, L = 70000, 2
+    tokens = rng.integers(0, cfg["vocab_size"], size=(B, L))
+    lens = rng.integers(1, L + 1, size=B)
+    _, out_f, status = _encode(sd, cfg, tokens, lens)
+    assert int(status.max().item()) == 0
+    pick = np.array([0, 1, 65535, 65536, B - 1])
+    ref = bert_oracle.bert_encode({k: bert_oracle._bf16_round(v) for k, v in sd.items()}, tokens[pick], lens[pick],
+                                  n_layers=1, heads=4)
+    got = out_f[torch.from_numpy(pick).cuda()].double().cpu().numpy()
+    assert ((got * ref).sum(1) >= 0.9995).all()
