@@ -580,47 +580,32 @@ __global__ void __launch_bounds__(NT, MINB) fuse_stream_kernel(const FuseParams 
             if (prev > c.rk[j]) bad_order = true;
           }
       }
-      // all four read-modify-writes side by side: the slots of one list are distinct (a doc id twice in a list is caught
-      // by the popcount check and the query deferred), so the loads need not wait for the previous posting's stores
-      double v[4];
-      u32 bits[4], mt[4];
-      double prev[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        bool counts = true;
-        v[j] = 0.0;
         if (valid[j]) {
+          double v;
+          bool counts = true;
           if (is_rrf) {
             const double rank = grk ? (double)c.rk[j] : (double)(idx[j] + 1);
-            v[j] = __ddiv_rn(w, __dadd_rn(p.rrf_k, rank));
+            v = __ddiv_rn(w, __dadd_rn(p.rrf_k, rank));
           } else {
             double s = raw_to_f64(c.sc[j]);
             if (minmax) s = __ddiv_rn(__dsub_rn(s, lmn), lden);
             if (skip_zero && s == 0.0) counts = false;
-            v[j] = __dmul_rn(w, s);                          // w == 1.0 when unweighted: exact
+            v = __dmul_rn(w, s);                             // w == 1.0 when unweighted: exact
           }
-        }
-        bits[j] = 1u << r;
-        if (skip_zero && counts) bits[j] |= 1u << (8 + r);
-        slot[j] = valid[j] ? slot[j] : 0u;
-      }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        mt[j] = s_meta[slot[j]];
-        prev[j] = s_acc[slot[j]];
-      }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (valid[j]) {
-          const bool first = (mt[j] & 0xFFFFu) == 0u;        // no list has touched this doc yet
+          u32 bits = 1u << r;
+          if (skip_zero && counts) bits |= 1u << (8 + r);
+          const u32 mt = s_meta[slot[j]];
+          const bool first = (mt & 0xFFFFu) == 0u;           // no list has touched this doc yet
           if (first) {
             const u32 seq = (u32)(s0 + idx[j]);
-            bits[j] |= seq << 16;
+            bits |= seq << 16;
             if (want_pos) atomicOr(&s_bitmap[seq >> 5], 1u << (seq & 31u));   // first-seen bitmap (out_pos)
           }
-          s_meta[slot[j]] = mt[j] | bits[j];
-          // the reference starts from 0.0 (src/fusion.py:275); the accumulator of an untouched slot is stale
-          s_acc[slot[j]] = __dadd_rn(first ? 0.0 : prev[j], v[j]);
+          s_meta[slot[j]] = mt | bits;
+          const double prev = first ? 0.0 : s_acc[slot[j]];    // the reference starts from 0.0 (src/fusion.py:275)
+          s_acc[slot[j]] = __dadd_rn(prev, v);
         }
       }
     };
