@@ -208,6 +208,16 @@ class WordPieceTokenizer:
         n = len(texts)
         if n == 0:
             return []
+        toks, lens, flags = self._native_encode(texts, n_threads)
+        rows = [toks[i, :lens[i]] for i in range(n)]
+        for i in np.flatnonzero(flags):
+            rows[i] = np.asarray(self.encode(texts[i]), dtype=np.int32)
+        return rows
+
+    def _native_encode(self, texts: Sequence[str], n_threads: int = 0):
+        """qf_wordpiece_encode over all texts -> (tokens int32 [n, cap] padded, lens int32 [n], flags uint8 [n];
+        flag 1 = a byte >= 0x80, text not tokenised)."""
+        n = len(texts)
         enc = [t.encode("utf-8") for t in texts]
         offs = np.zeros(n + 1, dtype=np.int64)
         np.cumsum([len(b) for b in enc], out=offs[1:])
@@ -219,10 +229,23 @@ class WordPieceTokenizer:
         flags = np.empty(n, dtype=np.uint8)
         N.check(N.lib().qf_wordpiece_encode(self._native_handle(), blob, offs.ctypes.data, n, cap, cap, int(n_threads),
                                             toks.ctypes.data, lens.ctypes.data, flags.ctypes.data))
+        return toks, lens, flags
+
+    def encode_batch_packed(self, texts: Sequence[str], n_threads: int = 0) -> Tuple[np.ndarray, np.ndarray]:
+        """-> (flat int32 token ids of all texts back to back, lens int64 [n]): the packed layout qf_bert_encode_packed
+        takes, built without a Python object per text (non-ASCII texts go through `encode` one by one)."""
+        n = len(texts)
+        if n == 0:
+            return np.zeros(0, dtype=np.int32), np.zeros(0, dtype=np.int64)
+        toks, lens, flags = self._native_encode(texts, n_threads)
+        slow = np.flatnonzero(flags)
+        if slow.size == 0:
+            keep = np.arange(toks.shape[1])[None, :] < lens[:, None]
+            return toks[keep], lens.astype(np.int64)
         rows = [toks[i, :lens[i]] for i in range(n)]
-        for i in np.flatnonzero(flags):
+        for i in slow:
             rows[i] = np.asarray(self.encode(texts[i]), dtype=np.int32)
-        return rows
+        return np.concatenate(rows), np.fromiter((len(r) for r in rows), dtype=np.int64, count=n)
 
     def batch(self, texts: Sequence[str], pad_multiple: int = 8) -> Tuple[np.ndarray, np.ndarray]:
         """-> (tokens int32 [n, L] padded with [PAD], lens int32 [n]); L = longest row rounded up to pad_multiple."""
@@ -340,11 +363,9 @@ class BertQueryEncoder:
         lengths), so every GEMM row is a real token -- a query batch whose lengths spread from 5 to 32 tokens costs
         its 14-token average, not the longest query.  Batches are cut at max_tokens tokens (workspace ~15 kB per
         token for bert-base) and at batch_size rows."""
-        n, H = len(rows), self.cfg.hidden
-        out_b = torch.empty((n, H), dtype=torch.bfloat16, device=self.device)
-        out_f = torch.empty((n, H), dtype=torch.float32, device=self.device)
+        n = len(rows)
         if n == 0:
-            return out_b, out_f
+            return self.encode_packed(np.zeros(0, dtype=np.int32), np.zeros(0, dtype=np.int64))
         lens = np.fromiter((len(r) for r in rows), dtype=np.int64, count=n)
         if lens.min() < 1 or lens.max() > self.cfg.max_pos:
             raise ValueError(f"row lengths must lie in [1, {self.cfg.max_pos}]")
@@ -356,6 +377,21 @@ class BertQueryEncoder:
             if flat64.size and (flat64.min() < -2**31 or flat64.max() >= 2**31):
                 raise ValueError("token id does not fit int32")
             flat = flat64.astype(np.int32)
+        return self.encode_packed(flat, lens, max_tokens)
+
+    def encode_packed(self, flat: np.ndarray, lens: np.ndarray, max_tokens: int = 1 << 18
+                      ) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Host arrays already in the packed layout -- flat int32 [sum(lens)] token ids back to back, lens [n] --
+        -> (bf16 [n, H], float32 [n, H]) on the device (what WordPieceTokenizer.encode_batch_packed returns)."""
+        lens = np.asarray(lens, dtype=np.int64)
+        flat = np.ascontiguousarray(flat, dtype=np.int32)
+        n, H = len(lens), self.cfg.hidden
+        out_b = torch.empty((n, H), dtype=torch.bfloat16, device=self.device)
+        out_f = torch.empty((n, H), dtype=torch.float32, device=self.device)
+        if n == 0:
+            return out_b, out_f
+        if lens.min() < 1 or lens.max() > self.cfg.max_pos or int(lens.sum()) != flat.size:
+            raise ValueError(f"row lengths must lie in [1, {self.cfg.max_pos}] and add up to the number of tokens")
         offs = np.concatenate(([0], np.cumsum(lens)))
         c = self.cfg
         kw = dict(n_layers=c.n_layers, hidden=c.hidden, heads=c.heads, ffn=c.ffn, vocab=c.vocab, max_pos=c.max_pos,
@@ -382,7 +418,7 @@ class BertQueryEncoder:
         return out_b, out_f
 
     def _encode(self, queries: Sequence[str]) -> Tuple[torch.Tensor, torch.Tensor]:
-        return self.encode_token_lists(self.tokenizer.encode_batch(list(queries)))
+        return self.encode_packed(*self.tokenizer.encode_batch_packed(list(queries)))
 
     def encode_device(self, queries: Sequence[str]) -> torch.Tensor:
         """bf16 [n, H] on the device: the `queries` operand of ops.dense_topk."""

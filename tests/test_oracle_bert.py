@@ -168,3 +168,17 @@ def test_native_tokenizer_matches_python_and_real_berttokenizer(tmp_path):
     # a vocabulary without the special tokens is rejected by the C side as by the Python side
     with pytest.raises(ValueError):
         WordPieceTokenizer({"a": 0, "b": 1})
+
+
+def test_encode_batch_packed_equals_rows():
+    from qppfusion.encoder import WordPieceTokenizer
+    tok = WordPieceTokenizer({t: i for i, t in enumerate(synthetic_vocab())}, max_length=32)
+    texts = TEXTS + ["what is the capital of france", "a b c", "", "who wrote hamlet?"] * 3
+    flat, lens = tok.encode_batch_packed(texts)
+    rows = [tok.encode(t) for t in texts]
+    assert flat.dtype == np.int32 and lens.tolist() == [len(r) for r in rows]
+    assert flat.tolist() == [i for r in rows for i in r]
+    ascii_only = [t for t in texts if t.isascii()]
+    flat2, lens2 = tok.encode_batch_packed(ascii_only)                     # the all-native branch (no Python rows)
+    assert flat2.tolist() == [i for t in ascii_only for i in tok.encode(t)] and lens2.sum() == flat2.size
+    assert tok.encode_batch_packed([])[0].size == 0
