@@ -197,6 +197,50 @@ def compute_qpp_for_res_file(res_path: str, output_path: Optional[str] = None, t
     return results
 
 
+def compute_qpp_for_runs_dir(runs_dir, qpp_dir=None, queries: Optional[str] = None, top_k: int = None,
+                             normalize: str = None, force: bool = False) -> Dict[str, str]:
+    """Step 03 for a whole runs directory (reference scripts/03_qpp.py:38-135): every `<ranker>.res` (not `.norm.res`)
+    -> `<qpp_dir>/<ranker>.res.mmnorm.qpp`; qpp_dir defaults to `<dataset>/qpp` next to the runs directory; the query
+    texts are taken from `queries`, else `<dataset>/BEIR-*/queries.jsonl`, else `<dataset>/queries.jsonl`; existing
+    outputs are skipped unless `force`.  The reference spreads the files over up to 8 processes, each spawning a JVM;
+    here every file is a handful of kernel launches on the one device, so they run one after the other.
+    -> {run file name: output path} of the files computed."""
+    from pathlib import Path
+    runs_dir = Path(runs_dir)
+    dataset_dir = runs_dir.parent
+    qpp_dir = Path(qpp_dir) if qpp_dir else dataset_dir / "qpp"
+    queries_path = queries
+    if not queries_path:
+        for sub in sorted(dataset_dir.iterdir()):
+            if sub.is_dir() and sub.name.startswith("BEIR") and (sub / "queries.jsonl").exists():
+                queries_path = str(sub / "queries.jsonl")
+                break
+        if not queries_path and (dataset_dir / "queries.jsonl").exists():
+            queries_path = str(dataset_dir / "queries.jsonl")
+    if queries_path:
+        print(f"[03_qpp] Using query texts from: {queries_path}")
+    else:
+        print("[03_qpp] WARNING: No queries.jsonl found - IDF-based methods will be inaccurate")
+    os.makedirs(qpp_dir, exist_ok=True)
+    res_files = sorted(f for f in os.listdir(runs_dir) if f.endswith(".res") and not f.endswith(".norm.res"))
+    if not res_files:
+        print(f"[03_qpp] No .res files found in {runs_dir}")
+        return {}
+    done: Dict[str, str] = {}
+    skipped = 0
+    for res_file in res_files:
+        out = qpp_dir / res_file.replace(".res", ".res.mmnorm.qpp")
+        if out.exists() and not force:
+            print(f"[03_qpp] SKIP {res_file} (already exists)")
+            skipped += 1
+            continue
+        print(f"[03_qpp] Processing {res_file}...")
+        compute_qpp_for_res_file(str(runs_dir / res_file), str(out), top_k, normalize, queries_path)
+        done[res_file] = str(out)
+    print(f"\n[03_qpp] Processed: {len(done)}, Skipped: {skipped}")
+    return done
+
+
 def _normalize_qpp(results: Dict[str, List[float]], method: str) -> Dict[str, List[float]]:
     """Normalise QPP scores across queries (reference src/qpp.py:340-374) on the device."""
     if not results:

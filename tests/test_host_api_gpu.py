@@ -101,6 +101,19 @@ def test_run_fusion_end_to_end_files(tmp_path):
             assert np.allclose(res[q], exp[q], rtol=1e-9, atol=1e-12)
         got_lines = (qpp_dir / f"{rk}.res.mmnorm.qpp").read_text().splitlines()
         assert got_lines == qo.qpp_file_lines(exp)
+    # scripts/03_qpp.py: the whole runs directory in one call -- same files, skip / force behaviour, query auto-detection
+    from qppfusion.qpp import compute_qpp_for_runs_dir
+    (tmp_path / "BEIR-x").mkdir()
+    (tmp_path / "BEIR-x" / "queries.jsonl").write_text((tmp_path / "queries.jsonl").read_text())
+    qpp_dir2 = tmp_path / "qpp"                                         # the default location next to runs/
+    before = {rk: (qpp_dir / f"{rk}.res.mmnorm.qpp").read_text() for rk in rankers}
+    assert compute_qpp_for_runs_dir(runs_dir) == {}                     # everything exists already: skipped
+    for rk in rankers:
+        (qpp_dir2 / f"{rk}.res.mmnorm.qpp").unlink()
+    done = compute_qpp_for_runs_dir(runs_dir)
+    assert sorted(done) == [f"{rk}.res" for rk in rankers]
+    assert {rk: (qpp_dir / f"{rk}.res.mmnorm.qpp").read_text() for rk in rankers} == before
+    assert sorted(compute_qpp_for_runs_dir(runs_dir, force=True)) == [f"{rk}.res" for rk in rankers]
     # 05_fusion
     out = tmp_path / "fused.res"
     fused = fusion.run_fusion("wcombsum", str(runs_dir), qpp_dir=str(qpp_dir), qpp_model="RSD", output_path=str(out))
