@@ -82,3 +82,26 @@ def write_run(results: Dict[str, "RetrieverResult"], output_path: str, retriever
                 docs = BaseRetriever.normalize_scores(docs)
             f.write("".join(f"{qid} Q0 {docno} {rank} {score:.6f} {retriever_name}\n" for docno, score, rank in docs))
     print(f"[02_retrieve] Wrote {output_path}")
+
+
+def run_retriever(retriever, queries: Dict[str, str], runs_dir, top_k: int, mini_batch_size: Optional[int] = None,
+                  name: Optional[str] = None) -> Dict[str, "RetrieverResult"]:
+    """One retriever of step 02 (reference scripts/02_retrieve.py run_bge :184-213 / run_tct_colbert :117-150):
+    retrieve_batch with the `<name>.checkpoint.jsonl` resume file, then `<name>.res` and `<name>.norm.res` through
+    write_run, then the checkpoint is removed.  -> the results dict."""
+    import os
+    import time
+    name = name or retriever.name
+    print(f"\n[02_retrieve] === {name} ===")
+    start = time.time()
+    os.makedirs(str(runs_dir), exist_ok=True)
+    checkpoint_path = os.path.join(str(runs_dir), f"{name}.checkpoint.jsonl")
+    results = retriever.retrieve_batch(queries, top_k=top_k, checkpoint_path=checkpoint_path,
+                                       mini_batch_size=mini_batch_size)
+    write_run(results, os.path.join(str(runs_dir), f"{name}.res"), name, normalize=False)
+    write_run(results, os.path.join(str(runs_dir), f"{name}.norm.res"), name, normalize=True)
+    if os.path.exists(checkpoint_path):
+        os.unlink(checkpoint_path)
+        print("[02_retrieve] Removed checkpoint file")
+    print(f"[02_retrieve] {name} completed in {time.time() - start:.1f}s")
+    return results

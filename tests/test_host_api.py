@@ -152,6 +152,33 @@ def test_write_run_is_the_reference_format(tmp_path):
     assert [ln.split()[0] for ln in (tmp_path / "x.res").read_text().splitlines()] == ["10", "9"]     # string order
 
 
+def test_run_retriever_writes_both_run_files_and_clears_the_checkpoint(tmp_path):
+    """retrievers.base.run_retriever == the per-retriever step of scripts/02_retrieve.py (run_bge :184-213)."""
+    from qppfusion.retrievers.base import run_retriever
+
+    class Fake(BaseRetriever):
+        name = "BGE"
+        calls = []
+
+        def retrieve(self, query, qid="", top_k=100, **kw):
+            raise NotImplementedError
+
+        def retrieve_batch(self, queries, top_k=100, checkpoint_path=None, mini_batch_size=None, **kw):
+            Fake.calls.append((top_k, checkpoint_path, mini_batch_size))
+            open(checkpoint_path, "w").write("{}\n")
+            return {q: RetrieverResult(q, [(f"d{i}", float(top_k - i), i + 1) for i in range(top_k)], self.name)
+                    for q in queries}
+
+    runs = tmp_path / "runs"
+    res = run_retriever(Fake(), {"test1": "a", "test0": "b"}, runs, top_k=3, mini_batch_size=7)
+    assert sorted(p.name for p in runs.iterdir()) == ["BGE.norm.res", "BGE.res"]          # checkpoint removed
+    assert Fake.calls == [(3, str(runs / "BGE.checkpoint.jsonl"), 7)] and sorted(res) == ["test0", "test1"]
+    assert (runs / "BGE.res").read_text().splitlines()[:3] == ["test0 Q0 d0 1 3.000000 BGE", "test0 Q0 d1 2 2.000000 BGE",
+                                                               "test0 Q0 d2 3 1.000000 BGE"]
+    assert (runs / "BGE.norm.res").read_text().splitlines()[:3] == ["test0 Q0 d0 1 1.000000 BGE", "test0 Q0 d1 2 0.500000 BGE",
+                                                                    "test0 Q0 d2 3 0.000000 BGE"]
+
+
 def _write_runs(tmp_path, seed=3, n_q=9, k=30, adversarial=True):
     rng = np.random.default_rng(seed)
     d = tmp_path / "runs"
