@@ -317,7 +317,8 @@ QF_API int    qf_bert_encode_packed(const qf_bert_config* cfg, const void* weigh
 
 /* ------------------------------------------------------------------------------------------------
  * WordPiece tokeniser (host side, multi-threaded, no CUDA)  --  replaces the HF BertTokenizer call inside
- * SentenceTransformer.encode (BGERetriever._encode_queries, src/retrievers/bge.py:160-170) for 7-bit texts
+ * SentenceTransformer.encode (BGERetriever._encode_queries, src/retrievers/bge.py:160-170) for texts below U+3000
+ * that NFC leaves alone (ASCII, accented Latin, Greek, Cyrillic, punctuation); other texts are flagged, not tokenised
  * ---------------------------------------------------------------------------------------------- */
 typedef struct qf_wordpiece qf_wordpiece;
 /* vocab = the bytes of a BERT vocab.txt (one token per line, id = line number); needs [CLS] [SEP] [UNK] [PAD]. */
@@ -325,7 +326,8 @@ QF_API int  qf_wordpiece_create(const char* vocab, size_t vocab_bytes, int do_lo
 QF_API void qf_wordpiece_free(qf_wordpiece* wp);
 /* texts: n UTF-8 strings back to back, text i = bytes [offsets[i], offsets[i+1]).  out_tokens[n][row_cap]
  * ([CLS] pieces [SEP], truncated to max_len <= row_cap tokens, padded with [PAD]), out_lens[n].  out_flags[i] = 1:
- * the text holds a byte >= 0x80 and was NOT tokenised (out_lens[i] = 0) -- the caller runs its Unicode path for it. */
+ * the text holds a character outside the native scope (combining mark, CJK, malformed UTF-8 ...) and was NOT tokenised
+ * (out_lens[i] = 0) -- the caller runs its full Unicode path for it. */
 QF_API int  qf_wordpiece_encode(const qf_wordpiece* wp, const char* texts, const int64_t* offsets, int n, int max_len,
                                 int row_cap, int n_threads, int32_t* out_tokens, int32_t* out_lens, uint8_t* out_flags);
 

@@ -2,12 +2,14 @@
 // of qf_bert_encode.  Replaces the HF tokenizer that SentenceTransformer.encode runs inside
 // BGERetriever._encode_queries (reference src/retrievers/bge.py:160-170).
 //
-// Scope: the ASCII fast path.  For a text of 7-bit characters BertTokenizer's pipeline (clean -> whitespace split ->
-// lower-case -> split punctuation -> greedy longest-match-first word pieces) needs no Unicode tables: control
-// characters other than \t \n \r are dropped, \t \n \r and ' ' separate words, the punctuation ranges 33-47, 58-64,
-// 91-96, 123-126 are words of their own, words longer than 100 characters become [UNK].  A text holding any byte
-// >= 0x80 is NOT tokenised here: its flag is set and the host layer (qppfusion.encoder.WordPieceTokenizer) runs the
-// full Unicode path (NFC/NFD, accent stripping, CJK) for that text alone.
+// Scope: text whose characters lie below U+3000 and are stable under NFC -- ASCII, Latin with accents, Greek, Cyrillic,
+// general punctuation.  For those BertTokenizer's pipeline (clean -> [NFC] -> whitespace split -> lower-case -> NFD +
+// strip Mn marks -> split punctuation -> greedy longest-match-first word pieces) is a per-character table lookup
+// (csrc/qf_unicode_table.h, generated from Python's unicodedata by tools/gen_unicode_table.py): class word / space /
+// removed / punctuation and the replacement text NFD(lower(c)) without marks.  A text holding anything else (combining
+// marks, characters NFC rewrites, capital sigma whose lower case depends on context, CJK, malformed UTF-8) is NOT
+// tokenised here: its flag is set and the host layer (qppfusion.encoder.WordPieceTokenizer) runs the full Unicode
+// path for that text alone.  Words longer than 100 characters become [UNK].
 #include <stdint.h>
 #include <string.h>
 
@@ -17,6 +19,7 @@
 #include <vector>
 
 #include "qf_common.cuh"
+#include "qf_unicode_table.h"
 
 struct qf_wordpiece {
   std::unordered_map<std::string, int32_t> start, cont;   // pieces that start a word / continue one (stored without "##")
@@ -26,10 +29,6 @@ struct qf_wordpiece {
 };
 
 namespace {
-
-inline bool is_punct_ascii(unsigned char c) {
-  return (c >= 33 && c <= 47) || (c >= 58 && c <= 64) || (c >= 91 && c <= 96) || (c >= 123 && c <= 126);
-}
 
 // greedy longest-match-first pieces of one word; false = no segmentation ([UNK])
 bool pieces_of(const qf_wordpiece& wp, const char* w, size_t n, std::string& key, std::vector<int32_t>& out) {
@@ -57,42 +56,88 @@ bool pieces_of(const qf_wordpiece& wp, const char* w, size_t n, std::string& key
   return true;
 }
 
+// Decode one UTF-8 sequence at t[j..n); returns the code point and advances j, or 0xFFFFFFFF for malformed input.
+inline uint32_t utf8_next(const unsigned char* t, size_t n, size_t& j) {
+  const unsigned char c = t[j];
+  if (c < 0x80) { ++j; return c; }
+  int len;
+  uint32_t cp;
+  if ((c & 0xE0) == 0xC0) { len = 2; cp = c & 0x1F; }
+  else if ((c & 0xF0) == 0xE0) { len = 3; cp = c & 0x0F; }
+  else if ((c & 0xF8) == 0xF0) { len = 4; cp = c & 0x07; }
+  else return 0xFFFFFFFFu;
+  if (j + len > n) return 0xFFFFFFFFu;
+  for (int k = 1; k < len; ++k) {
+    if ((t[j + k] & 0xC0) != 0x80) return 0xFFFFFFFFu;
+    cp = (cp << 6) | (t[j + k] & 0x3F);
+  }
+  static const uint32_t min_cp[5] = {0, 0, 0x80, 0x800, 0x10000};
+  if (cp < min_cp[len] || cp > 0x10FFFF || (cp >= 0xD800 && cp <= 0xDFFF)) return 0xFFFFFFFFu;   // overlong / surrogate
+  j += len;
+  return cp;
+}
+
 void encode_range(const qf_wordpiece& wp, const char* texts, const int64_t* off, int lo, int hi, int max_len,
                   int row_cap, int32_t* out_tokens, int32_t* out_lens, uint8_t* out_flags) {
   std::vector<int32_t> ids;
   std::string word, key;
   for (int i = lo; i < hi; ++i) {
-    const char* t = texts + off[i];
+    const unsigned char* t = reinterpret_cast<const unsigned char*>(texts + off[i]);
     const size_t n = (size_t)(off[i + 1] - off[i]);
     int32_t* row = out_tokens + (size_t)i * row_cap;
-    bool ascii = true;
-    for (size_t j = 0; j < n; ++j) ascii &= (unsigned char)t[j] < 0x80;
-    out_flags[i] = ascii ? 0 : 1;
-    if (!ascii) {
-      out_lens[i] = 0;
-      continue;
-    }
     ids.clear();
     word.clear();
+    size_t word_chars = 0;                                   // characters (not bytes) of the current word
     const size_t budget = (size_t)max_len - 2;
+    bool handled = true;
     auto flush = [&]() {
       if (word.empty()) return;
-      if (word.size() > 100 || !pieces_of(wp, word.data(), word.size(), key, ids)) ids.push_back(wp.unk);
+      if (word_chars > 100 || !pieces_of(wp, word.data(), word.size(), key, ids)) ids.push_back(wp.unk);
       word.clear();
+      word_chars = 0;
     };
-    for (size_t j = 0; j < n && ids.size() < budget; ++j) {
-      unsigned char c = (unsigned char)t[j];
-      if (c == ' ' || c == '\t' || c == '\n' || c == '\r') {
-        flush();
-      } else if (c < 0x20 || c == 0x7F) {
-        // control character: dropped, does not separate words
-      } else if (is_punct_ascii(c)) {
-        flush();
-        word.assign(1, (char)c);
-        flush();
-      } else {
-        word.push_back(wp.lower && c >= 'A' && c <= 'Z' ? (char)(c + 32) : (char)c);
+    // NOTE: the whole text is scanned even when the token budget is reached: an unhandled character anywhere sends the
+    // text to the Python path, whose truncated result must not depend on where the scan stopped
+    for (size_t j = 0; j < n;) {
+      const uint32_t cp = utf8_next(t, n, j);
+      if (cp >= qf_unicode::kLimit) {                        // includes malformed input (0xFFFFFFFF)
+        handled = false;
+        break;
       }
+      const uint8_t kind = qf_unicode::kKind[cp];
+      const int cls = kind & 15, mlen = kind >> 4;
+      if (cls == 4) {
+        handled = false;
+        break;
+      }
+      if (ids.size() >= budget) continue;                    // only validating the rest of the text
+      if (cls == 1) {
+        flush();
+      } else if (cls == 2) {
+        // removed: does not separate words
+      } else {
+        const char* m = reinterpret_cast<const char*>(qf_unicode::kMapBlob + qf_unicode::kMapOff[cp]);
+        if (cls == 3) {
+          flush();
+          word.assign(m, (size_t)mlen);
+          word_chars = 1;
+          flush();
+        } else if (cp < 0x80) {
+          word.push_back(wp.lower ? m[0] : (char)cp);
+          ++word_chars;
+        } else if (wp.lower) {
+          word.append(m, (size_t)mlen);
+          for (int k = 0; k < mlen; ++k) word_chars += ((unsigned char)m[k] & 0xC0) != 0x80;
+        } else {                                             // cased model: characters kept as they are
+          handled = false;                                   // (accent handling of cased checkpoints: Python path)
+          break;
+        }
+      }
+    }
+    out_flags[i] = handled ? 0 : 1;
+    if (!handled) {
+      out_lens[i] = 0;
+      continue;
     }
     if (ids.size() < budget) flush();
     const size_t m = ids.size() < budget ? ids.size() : budget;

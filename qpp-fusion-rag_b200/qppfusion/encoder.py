@@ -203,7 +203,7 @@ class WordPieceTokenizer:
                 pass
 
     def encode_batch(self, texts: Sequence[str], n_threads: int = 0) -> List[np.ndarray]:
-        """[CLS] ... [SEP] id rows (int32 arrays) for many texts: 7-bit texts through the multi-threaded C++
+        """[CLS] ... [SEP] id rows (int32 arrays) for many texts: texts in the native scope (below U+3000, NFC-stable) through the multi-threaded C++
         tokeniser (qf_wordpiece_encode), the rest through `encode` (full Unicode handling) one by one."""
         n = len(texts)
         if n == 0:

@@ -182,3 +182,54 @@ def test_encode_batch_packed_equals_rows():
     flat2, lens2 = tok.encode_batch_packed(ascii_only)                     # the all-native branch (no Python rows)
     assert flat2.tolist() == [i for t in ascii_only for i in tok.encode(t)] and lens2.sum() == flat2.size
     assert tok.encode_batch_packed([])[0].size == 0
+
+
+def test_native_tokenizer_unicode_scope(tmp_path):
+    """Accented Latin, Greek, Cyrillic, typographic punctuation, NBSP / soft hyphen / line separator go through the C++
+    table-driven path and equal the Python tokeniser and the live transformers.BertTokenizer; combining marks, capital
+    sigma, CJK and malformed input are flagged and take the Python path -- same result either way."""
+    import ctypes
+    from qppfusion import _native as N
+    from qppfusion.encoder import WordPieceTokenizer
+    vocab = synthetic_vocab() + ["e", "##e", "cafe2", "naive2", "##ς", "α", "β", "##β", "αβ", "д", "##а", "да", "—", "“", "”", "¿", "ss",
+                                 "ß", "##ß", "æ", "##æ", "ø", "i", "##i"]
+    vocab = list(dict.fromkeys(vocab))
+    tok = WordPieceTokenizer({t: i for i, t in enumerate(vocab)}, max_length=40)
+    rng = np.random.default_rng(21)
+    alphabet = list("abcdeinoszCAFÉéèêëñÑçÇüÜöïîİıßæøÆØ¿¡—–“”‘’«»…· ­  αβγΑΒΣσςдаДЖж 	!?.,'-") + \
+        ["cafe", "naive", "résumé", " ", "é", "京", "́", "ﬁ", "Å", "Å"]
+    texts = ["".join(rng.choice(alphabet, size=int(rng.integers(0, 30)))) for _ in range(1500)]
+    texts += ["Café au lait — “naïve” résumé…", "¿Qué?", "ΑΒ αβ", "Да", "İstanbul", "straße", "a­b", "a b", "x y"]
+    toks, lens, flags = tok._native_encode(texts)
+    assert flags.sum() > 0 and (flags == 0).sum() > len(texts) // 3          # both branches exercised
+    for i, t in enumerate(texts):
+        want = tok.encode(t)
+        if flags[i] == 0:
+            assert toks[i, :lens[i]].tolist() == want, repr(t)
+        else:
+            assert any(ord(c) >= 0x3000 or c in "́ΣÅ" for c in t), repr(t)      # flagged for a reason
+    special = ["a\u00adb", "a\u00a0b", "a\u2028b", "a\u2029b", "a\u200bb", "x\u0085y", "caf\u00e9", "\u0130i", "\u00bfa?"]
+    t3, l3, f3 = tok._native_encode(special)
+    assert f3.tolist() == [0] * len(special)
+    assert [t3[i, :l3[i]].tolist() for i in range(len(special))] == [tok.encode(t) for t in special]
+    assert tok.encode("a\u00adb") == tok.encode("ab") and tok.encode("a\u2028b") == tok.encode("a b")
+    rows = tok.encode_batch(texts)
+    assert [r.tolist() for r in rows] == [tok.encode(t) for t in texts]
+    flat, ln = tok.encode_batch_packed(texts)
+    assert flat.tolist() == [x for r in rows for x in r.tolist()] and ln.tolist() == [len(r) for r in rows]
+    # malformed UTF-8 straight at the C ABI: flagged, never read past the end
+    bad = [b"ab\xff", b"\xc3", b"\xe2\x82", b"\xc0\xaf", b"\xed\xa0\x80", b"ok"]
+    blob = b"".join(bad)
+    offs = np.zeros(len(bad) + 1, dtype=np.int64)
+    np.cumsum([len(b) for b in bad], out=offs[1:])
+    t2 = np.empty((len(bad), 8), dtype=np.int32); l2 = np.empty(len(bad), dtype=np.int32); f2 = np.empty(len(bad), dtype=np.uint8)
+    N.check(N.lib().qf_wordpiece_encode(tok._native_handle(), blob, offs.ctypes.data, len(bad), 8, 8, 1, t2.ctypes.data,
+                                        l2.ctypes.data, f2.ctypes.data))
+    assert f2.tolist() == [1, 1, 1, 1, 1, 0]
+    tr = pytest.importorskip("transformers")
+    vp = tmp_path / "vocab.txt"
+    vp.write_text("\n".join(vocab) + "\n", encoding="utf-8")
+    real = tr.BertTokenizer(str(vp), do_lower_case=True)
+    for i in range(0, len(texts), 3):
+        if flags[i] == 0:
+            assert toks[i, :lens[i]].tolist() == real(texts[i], truncation=True, max_length=40)["input_ids"], repr(texts[i])
