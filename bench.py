@@ -202,6 +202,31 @@ def synth_dense(Q, N, D, seed, device):
     return q32, corpus
 
 
+def dense_cpu_baseline(q32_cpu, corpus_rows_cpu, n_docs_total, k, seconds=6.0):
+    """Flat inner-product search on the host cores, the way the reference's faiss.IndexFlatIP path computes it
+    (src/retrievers/bge.py:188-194: fp32 GEMM + top-k; faiss itself is not installable offline): torch.mm fp32 +
+    torch.topk on a bounded sample -- `q32_cpu` queries against `corpus_rows_cpu` corpus rows -- extrapolated linearly
+    in the corpus size (a flat search is linear in N).  -> dict for the JSON line."""
+    import time
+    import torch
+    nq, n_sub = q32_cpu.shape[0], corpus_rows_cpu.shape[0]
+    c32 = corpus_rows_cpu.float()
+    kk = min(k, n_sub)
+    torch.topk(q32_cpu[:4] @ c32[:4096].T, min(kk, 4096), dim=1)          # warm the thread pool
+    reps, t0 = 0, time.perf_counter()
+    while True:
+        torch.topk(q32_cpu @ c32.T, kk, dim=1)
+        reps += 1
+        dt = time.perf_counter() - t0
+        if dt >= seconds or reps >= 20:
+            break
+    per_query_full = dt / reps / nq * (n_docs_total / n_sub)
+    return {"value": 1.0 / per_query_full, "unit": "queries/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{nq} queries x {n_sub} of {n_docs_total} corpus rows, torch.mm fp32 + torch.topk on the host "
+                      f"(restated flat search; faiss-cpu is not installable offline), {reps} repetitions, extrapolated "
+                      f"linearly to the full corpus"}
+
+
 def dense_leg(args, dev, world, rank, Q=Q_NQ, n_docs=None, label="BASELINE configs[2]", max_steps=10):
     """BGE-shaped flat inner-product top-1000 (BASELINE configs[2] by default; configs[3] = HotpotQA shape with
     Q=7405, n_docs=5,233,329); corpus row-sharded when world > 1."""
@@ -287,6 +312,13 @@ def dense_leg(args, dev, world, rank, Q=Q_NQ, n_docs=None, label="BASELINE confi
             overlap = sum(len(set(ri[i].tolist()) & set(ids[i].tolist())) for i in range(nq)) / (nq * k)
             parity = {"queries_checked": nq, "top1000_overlap_vs_fp32": overlap,
                       "max_abs_score_diff_vs_fp32": float((rs - sc[:nq]).abs().max().item())}
+    dense_cpu = None
+    if world == 1 and n_docs is None and not args.no_cpu_baseline:      # configs[2] only, rank 0, bounded (~6 s)
+        try:
+            n_sub = min(n_local, 1 << 18)
+            dense_cpu = dense_cpu_baseline(q32[:64].cpu(), corpus[:n_sub].cpu(), N_DENSE, k)
+        except Exception as e:                                             # never let the side measurement sink the run
+            dense_cpu = {"error": f"{type(e).__name__}: {e}"}
     t = torch.tensor([ms, e2e_ms, main_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -307,6 +339,7 @@ def dense_leg(args, dev, world, rank, Q=Q_NQ, n_docs=None, label="BASELINE confi
             "whole_call_tflops": 2.0 * Q * N_DENSE * D / (ms * 1e-3) / 1e12,
             "e2e": {"value": Q / (e2e_ms * 1e-3), "unit": "queries/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": Q * D * 4, "d2h_bytes_per_step": Q * k * 8},
+            "cpu_baseline": dense_cpu,
             "threshold_failures": status_bad, "parity": parity, "gpu_launches": (4 + (1 if world > 1 else 0)) * (2 * steps + 4), "clocks": clocks}
 
 
