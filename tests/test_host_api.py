@@ -309,3 +309,38 @@ def test_native_writer_fixed6_is_python_format(tmp_path):
     exp = ["%.6f" % v for v in vals]
     bad = [(g, e, float(v).hex()) for g, e, v in zip(got, exp, vals) if g != e]
     assert not bad, bad[:10]
+
+
+def test_run_all_methods_orchestration_without_gpu(tmp_path, monkeypatch):
+    """File names, tags, the qpp_dir switch and the learned-model discovery of run_all_methods (scripts/05_fusion.py:56-152),
+    with the device work stubbed out (the GPU test runs the real thing)."""
+    from qppfusion import fusion
+    runs_dir = _write_runs(tmp_path, n_q=3, k=5, adversarial=False)
+    qpp_dir, fused_dir = tmp_path / "qpp", tmp_path / "data" / "fused"
+    qpp_dir.mkdir()
+    for rk in ("BGE", "BM25", "Splade"):
+        (qpp_dir / f"{rk}.res.mmnorm.qpp").write_text("".join(f"test{q}\t" + "\t".join(["0.500000"] * 13) + "\n" for q in range(3)))
+    (tmp_path / "data" / "models").mkdir(parents=True)
+    (tmp_path / "data" / "models" / "fusion_mlp.pkl").write_bytes(b"stub")
+    calls = []
+
+    def fake_fuse_parsed(parsed, method, qpp_data, qpp_model, output_path, rrf_k, return_fused, tag=None):
+        calls.append((method, qpp_data is not None, qpp_model, rrf_k, tag))
+        open(output_path, "w").write("x\n")
+        return {}
+
+    monkeypatch.setattr(fusion, "_fuse_parsed", fake_fuse_parsed)
+    monkeypatch.setattr(fusion, "learned_fusion", lambda runs, qpp, path: {"test0": [("d1", 1.0)]})
+    res = fusion.run_all_methods(runs_dir, qpp_dir, fused_dir, qpp_model="NQC", rrf_k=10)
+    assert list(res) == ["combsum", "combmnz", "rrf", "wcombsum", "wcombmnz", "wrrf", "learned_mlp"]
+    assert sorted(p.name for p in fused_dir.iterdir()) == ["combmnz.res", "combsum.res", "learned_mlp.res", "rrf.res",
+                                                          "wcombmnz_nqc.res", "wcombsum_nqc.res", "wrrf_nqc.res"]
+    assert calls[:3] == [("combsum", False, "NQC", 10, "combsum"), ("combmnz", False, "NQC", 10, "combmnz"),
+                         ("rrf", False, "NQC", 10, "rrf")]
+    assert [c[0] for c in calls[3:]] == ["wcombsum", "wcombmnz", "wrrf"] and all(c[1] and c[4] is None for c in calls[3:])
+    assert (fused_dir / "learned_mlp.res").read_text() == "test0 Q0 d1 1 1.000000 learned-mlp\n"
+    calls.clear()
+    res = fusion.run_all_methods(runs_dir, tmp_path / "absent", tmp_path / "f2")
+    assert list(res) == ["combsum", "combmnz", "rrf"] and len(calls) == 3
+    with pytest.raises(FileNotFoundError):
+        fusion.run_all_methods(tmp_path / "no_runs", qpp_dir, tmp_path / "f3")
