@@ -624,10 +624,12 @@ extern "C" int qf_fuse(const int32_t* doc_ids, const void* scores, int score_typ
   FuseParams p{doc_ids, scores, ranks, lens, weights, Q, R, K, method, norm, rrf_k, flags,
                out_ids, out_scores, out_counts, out_pos, out_lens, out_status, 0};
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (qf::fuse_stream_supported(p)) {
-    // common case: streaming kernel; the general kernel then finishes whatever it deferred (usually nothing)
+  const bool gather = qf::fuse_gather_supported(p, score_type);
+  if (gather || qf::fuse_stream_supported(p)) {
+    // common case: gather kernel (or the r1h streaming kernel outside its envelope); the general kernel then
+    // finishes whatever it deferred (usually nothing)
     qf::prof_mark(QF_PROF_FUSE_STREAM, 0, st);
-    rc = qf::fuse_stream_launch(p, score_type, st);
+    rc = gather ? qf::fuse_gather_launch(p, score_type, st) : qf::fuse_stream_launch(p, score_type, st);
     qf::prof_mark(QF_PROF_FUSE_STREAM, 1, st);
     if (rc != QF_OK) return rc;
     p.fixup = 1;

@@ -7,7 +7,8 @@ namespace qf {
 
 constexpr int FUSE_MAX_R = 32;
 constexpr uint32_t FUSE_FLAG_DEBUG_FULLSORT = 0x100u;   // test hook: general kernel, force the 64-bit sort path
-constexpr uint32_t FUSE_FLAG_DEBUG_GENERAL = 0x200u;    // test hook: skip the streaming kernel
+constexpr uint32_t FUSE_FLAG_DEBUG_GENERAL = 0x200u;    // test hook: skip the streaming kernels
+constexpr uint32_t FUSE_FLAG_DEBUG_NOGATHER = 0x400u;   // test hook: skip the gather kernel (r1h streaming kernel instead)
 constexpr int FUSE_DEFERRED = -1;                       // out_lens marker: query left to the general kernel
 
 struct FuseParams {
@@ -43,5 +44,10 @@ __device__ __forceinline__ double raw_to_f64(int v) { return micro_to_f64(v); }
 // long runs of exactly tied scores, hash-probe overflow) get out_lens[q] = FUSE_DEFERRED.
 bool fuse_stream_supported(const FuseParams& p);
 int fuse_stream_launch(const FuseParams& p, int score_type, cudaStream_t stream);
+
+// Gather kernel (qf_fuse_gather.cu, round 2): same contract as the streaming kernel, smaller envelope (R <= 8,
+// K <= 1024, 4-byte scores); preferred whenever it applies.
+bool fuse_gather_supported(const FuseParams& p, int score_type);
+int fuse_gather_launch(const FuseParams& p, int score_type, cudaStream_t stream);
 
 }  // namespace qf

@@ -1,4 +1,4 @@
-"""GPU fuzz: random shapes / options through the three qf_fuse kernel paths (streaming, streaming with the larger table,
+"""GPU fuzz: random shapes / options through the qf_fuse kernel paths (gather, streaming, each with the larger table;
 general) must agree bit for bit; a sample of the queries is also checked against the Python oracle."""
 import numpy as np
 import pytest
@@ -8,7 +8,7 @@ from oracle import fusion_oracle as fo
 
 pytestmark = pytest.mark.gpu
 
-PATHS = {"stream": 0, "stream-large": 8, "general": 0x200}
+PATHS = {"gather": 0, "gather-large": 8, "stream": 0x400, "stream-large": 0x408, "general": 0x200}
 
 
 def _random_case(rng):
@@ -59,7 +59,7 @@ def _random_case(rng):
 
 
 @pytest.mark.parametrize("seed", range(6))
-def test_three_kernel_paths_agree_and_match_the_oracle(seed):
+def test_kernel_paths_agree_and_match_the_oracle(seed):
     from qppfusion import ops
     rng = np.random.default_rng(1000 + seed)
     dev = torch.device("cuda:0")
@@ -76,7 +76,7 @@ def test_three_kernel_paths_agree_and_match_the_oracle(seed):
         n = ref[4]
         assert (n >= 0).all()
         m = np.arange(c["R"] * c["K"])[None, :] < n[:, None]
-        for name in ("stream", "stream-large"):
+        for name in ("gather", "gather-large", "stream", "stream-large"):
             got = outs[name]
             desc = (name, {k: c[k] for k in ("R", "K", "Q", "method", "norm", "flags")})
             assert np.array_equal(got[4], n) and np.array_equal(got[5], ref[5]), desc

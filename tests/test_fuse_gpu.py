@@ -16,12 +16,17 @@ METHODS = {"sum": 0, "mnz": 1, "rrf": 2}
 EXTRA_FLAGS = [0]
 
 
-@pytest.fixture(autouse=True, params=["stream", "stream-large", "general"])
+KERNEL_PATHS = {"gather": 0, "gather-large": 8, "stream": 0x400, "stream-large": 0x408, "general": 0x200}
+
+
+@pytest.fixture(autouse=True, params=list(KERNEL_PATHS))
 def fuse_kernel_path(request):
-    """Every test runs three times: through the streaming kernel (+ general-kernel fix-up of deferred queries, the
-    product path), through its larger-table configuration (QF_FLAG_LARGE_UNION, a performance hint that must not change
-    any result) and with the streaming kernel disabled (debug flag 0x200), so all kernels keep full parity coverage."""
-    EXTRA_FLAGS[0] = {"stream": 0, "stream-large": 8, "general": 0x200}[request.param]
+    """Every test runs five times: through the gather kernel (round 2; + general-kernel fix-up of deferred queries, the
+    product path) and its larger-table configuration (QF_FLAG_LARGE_UNION, a performance hint that must not change any
+    result), through the r1h streaming kernel (debug flag 0x400 skips the gather kernel; still the product path
+    outside the gather kernel's envelope) in both table sizes, and with both disabled (debug flag 0x200), so all
+    kernels keep full parity coverage."""
+    EXTRA_FLAGS[0] = KERNEL_PATHS[request.param]
     yield
     EXTRA_FLAGS[0] = 0
 
