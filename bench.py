@@ -70,6 +70,33 @@ def synth_device(Q, R, K, seed, device):
     return ids.contiguous(), micro.contiguous(), lens, feats
 
 
+def write_synth_run_files(root, nq, seed=1, R=R_NQ, K=K_NQ):
+    """Synthetic run / QPP files in the reference's wire formats (BASELINE configs[1] shape, a sample of `nq` queries):
+    <root>/runs/<Ranker>.norm.res  "{qid} Q0 {docno} {rank} {score:.6f} {tag}"  (scripts/02_retrieve.py:80)
+    <root>/qpp/<Ranker>.res.mmnorm.qpp  "qid\t13 x %.6f"                         (src/qpp.py:331-334)
+    -> (runs_dir, qpp_dir).  Written with numpy/pandas on the host, outside every timed region."""
+    import numpy as np
+    import pandas as pd
+    names = ["BGE", "BM25", "BM25_MonoT5", "BM25_TCT", "Splade"][:R]
+    runs_dir, qpp_dir = os.path.join(root, "runs"), os.path.join(root, "qpp")
+    os.makedirs(runs_dir, exist_ok=True)
+    os.makedirs(qpp_dir, exist_ok=True)
+    ids, micro, _lens, _feats = _cpu_sample_arrays(nq, seed)
+    rng = np.random.default_rng(seed + 77)
+    qid = np.repeat(np.arange(nq), K)
+    rank = np.tile(np.arange(1, K + 1), nq)
+    for r, name in enumerate(names):
+        df = pd.DataFrame({"qid": np.char.add("test", qid.astype(str)), "q0": "Q0",
+                           "docno": np.char.add("doc", ids[:, r].reshape(-1).astype(str)), "rank": rank,
+                           "score": micro[:, r].reshape(-1) / 1e6, "tag": name})
+        df.to_csv(os.path.join(runs_dir, f"{name}.norm.res"), sep=" ", header=False, index=False, float_format="%.6f")
+        q = np.round(rng.random((nq, 13)), 6)
+        with open(os.path.join(qpp_dir, f"{name}.res.mmnorm.qpp"), "w") as f:
+            for i in range(nq):
+                f.write(f"test{i}\t" + "\t".join(f"{v:.6f}" for v in q[i]) + "\n")
+    return runs_dir, qpp_dir
+
+
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
     """SM clock + throttle reasons sampled WHILE the timed region runs: NVML polled every ~2 ms from a thread (the
@@ -439,6 +466,252 @@ def encoder_leg(args, dev, world, rank, Q=Q_NQ):
             "gpu_launches": (2 + 4 * cfg.n_layers) * (steps + 3) + (2 + 4 * cfg.n_layers) * (steps + 1)}
 
 
+
+# ------------------------------------------------------------------------------------------------ extra legs (round 2)
+def _oracle_check_weighted(ids, micro, lens, w, out, method, ranks=None, n=32, seed=0):
+    """In-run parity sample, OUTSIDE every timed region: `n` queries of a device batch against the C restatement of
+    the reference's weighted_* loops + write_runfile ranking (oracle/qf_oracle.c): ranked ids and float64 score bits."""
+    import numpy as np
+    import torch
+    from oracle import c_oracle as co
+    Q = ids.shape[0]
+    rng = np.random.default_rng(seed)
+    pick = torch.from_numpy(np.sort(rng.choice(Q, size=min(n, Q), replace=False))).to(ids.device)
+    h = lambda t: t.index_select(0, pick).cpu().numpy()
+    o_ids, o_sc, _c, _p, o_len = co.fuse_weighted(h(ids), h(micro), h(lens), h(w), method, 60.0,
+                                                  None if ranks is None else h(ranks), n_threads=os.cpu_count() or 1)
+    g_ids, g_sc, g_len = h(out.ids), h(out.scores), h(out.lens)
+    ok = bool(np.array_equal(g_len, o_len))
+    if ok:
+        m = np.arange(g_ids.shape[1])[None, :] < o_len[:, None]
+        ok = bool(np.array_equal(g_ids[m], o_ids[m]) and np.array_equal(g_sc[m].view(np.int64), o_sc[m].view(np.int64)))
+    return {"queries_checked": int(len(pick)), "bit_exact_vs_oracle": ok}
+
+
+def _time_replays(fn, steps, stream, dev, warm=3):
+    import torch
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(steps):
+        fn(i) if fn.__code__.co_argcount else fn()
+    e1.record(stream)
+    torch.cuda.synchronize(dev)
+    return e0.elapsed_time(e1) / steps
+
+
+def wrrf_leg(args, dev, sets):
+    """BASELINE configs[1] names W-CombSUM / W-RRF: the same step with weighted_rrf (src/fusion.py:333-380), i.e. the
+    FILE's rank column (explicit int32 ranks, one more 69 MB array per input set) and one float64 division per posting."""
+    import torch
+    from qppfusion import _native as N_, ops
+    from qppfusion.pipeline import FusionStepGraph
+    Q, R, K = sets[0][0].shape
+    stream = torch.cuda.current_stream(dev)
+    ranks = [torch.arange(1, K + 1, dtype=torch.int32, device=dev).expand(Q, R, K).contiguous() for _ in sets]
+    graphs = [FusionStepGraph(*st, qpp_index=5, top_k=100, k_cut=50, colnorm="minmax", round6=True, method=2, norm=0,
+                              rrf_k=60.0, flags=0, want_counts=False, want_pos=False, compact=False, ranks=rk)
+              for st, rk in zip(sets, ranks)]
+    steps = max(4, min(args.steps, 20))
+    ms = _time_replays(lambda i=0: graphs[i % len(graphs)].replay(), steps, stream, dev, warm=len(graphs))
+    N_.profile_enable(True)
+    for i in range(steps):
+        ids, micro, lens, _f = sets[i % len(sets)]
+        ops.fuse(ids, micro, lens, graphs[i % len(sets)].weights, ranks[i % len(sets)], 2, 0, 60.0, 0, want_counts=False, want_pos=False)
+    torch.cuda.synchronize(dev)
+    fuse_ms = N_.profile_read(N_.PROF_FUSE_STREAM)
+    N_.profile_enable(False)
+    g = graphs[0]
+    g.replay()
+    torch.cuda.synchronize(dev)
+    check = _oracle_check_weighted(sets[0][0], sets[0][1], sets[0][2], g.weights, g.out, 2, ranks[0], seed=1)
+    union = int(g.out.lens.sum().item())
+    alg = 12 * Q * R * K + Q * R * 12 + 12 * union + 8 * Q           # ids + micro + ranks in
+    hbm, _tf, _w = load_peaks()
+    return {"value": Q / (ms * 1e-3), "unit": "fused queries/s", "ms_per_step": ms, "fuse_kernel_ms": fuse_ms,
+            "hbm_frac": alg / (fuse_ms * 1e-3) / 1e9 / hbm, "algorithmic_bytes": alg, "parity": check,
+            "workload": "configs[1] step with W-RRF on the file's rank column (one graph replay per step, one step in flight)"}
+
+
+def c1_leg(args, dev):
+    """BASELINE configs[0]: SciFact-shaped 300 queries x 5 retrievers x top-100, CombSUM / CombMNZ / RRF with ranx
+    semantics (min-max per list, sorted-run positions), the three methods as ONE CUDA graph over one batch."""
+    import numpy as np
+    import torch
+    from oracle import fusion_oracle as fo
+    from qppfusion import ops
+    global N_DOCS, POOL
+    keep = (N_DOCS, POOL)
+    N_DOCS, POOL = 5183, 230
+    try:
+        sets = [synth_device(300, 5, 100, 11 + i, dev) for i in range(4)]
+    finally:
+        N_DOCS, POOL = keep
+    stream = torch.cuda.current_stream(dev)
+    cfg = (("combsum", 0, 1), ("combmnz", 1, 1), ("rrf", 2, 0))
+
+    def body(st):
+        ids, micro, lens, _f = st
+        return [ops.fuse(ids, micro, lens, None, None, m, norm, 60.0, 2, want_counts=False, want_pos=False) for _n, m, norm in cfg]
+
+    side = torch.cuda.Stream(dev)
+    side.wait_stream(stream)
+    with torch.cuda.stream(side):
+        for st in sets:
+            body(st)
+    stream.wait_stream(side)
+    torch.cuda.synchronize(dev)
+    graphs, outs = [], []
+    for st in sets:
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            outs.append(body(st))
+        graphs.append(g)
+    steps = 200
+    ms = _time_replays(lambda i=0: graphs[i % 4].replay(), steps, stream, dev, warm=8)
+    # parity sample against the ranx restatement (oracle/fusion_oracle.py), 6 queries x 3 methods
+    ids, micro, lens, _f = [t.cpu().numpy() for t in sets[0]]
+    ok = True
+    for (name, m, norm), out in zip(cfg, outs[0]):
+        o_ids, o_sc, o_len = out.ids.cpu().numpy(), out.scores.cpu().numpy(), out.lens.cpu().numpy()
+        for q in range(0, 300, 50):
+            per_r = [[(int(ids[q, r, i]), micro[q, r, i] / 1e6, i + 1) for i in range(lens[q, r])] for r in range(5)]
+            docs, sc, _c = fo.fuse_ranx_query(per_r, m, 60.0, "min-max", False)
+            order = fo.rank_order(sc)
+            n = len(docs)
+            ok &= bool(o_len[q] == n and [int(x) for x in o_ids[q, :n]] == [docs[i] for i in order]
+                       and np.array_equal(o_sc[q, :n], np.array([sc[i] for i in order]) + 0.0))
+    return {"value": 300 / (ms * 1e-3), "unit": "queries/s (each fused by CombSUM, CombMNZ and RRF)", "ms_per_step": ms,
+            "parity": {"queries_checked": 6, "methods": 3, "bit_exact_vs_oracle": ok},
+            "workload": "configs[0]: 300 q x 5 x top-100, ranx-semantics CombSUM + CombMNZ + RRF as one CUDA graph of 6 "
+                        "launches; 4 rotating input sets (1.2 MB each: L2-resident, launch-bound shape)"}
+
+
+def c5_leg(args, dev, world, rank):
+    """BASELINE configs[4]: throughput sweep, QPP-weighted fusion of 5 x top-1000 lists, query-sharded, no collective.
+    200 000 synthetic queries per GPU (8 GB of postings + 12 GB of padded outputs), fused by ONE qf_fuse launch per
+    step after qf_qpp_stats / colnorm / select_weight; inputs are 64x the L2."""
+    import torch
+    import torch.distributed as dist
+    from qppfusion import _native as N_, ops
+    Qc, chunk = 200_000, 25_000
+    parts = [synth_device(chunk, R_NQ, K_NQ, 20250105 + 31 * rank + 1000 * i, dev) for i in range(Qc // chunk)]
+    ids, micro, lens, feats = [torch.cat([p_[j] for p_ in parts]) for j in range(4)]
+    del parts
+    stream = torch.cuda.current_stream(dev)
+
+    def step():
+        qpp, _st = ops.qpp_stats(micro, lens, feats, None, None, top_k=100, k_cut=50)
+        ops.qpp_colnorm_(qpp, "minmax", round6=True)
+        w = ops.qpp_select_weight(qpp, 5)
+        return w, ops.fuse(ids, micro, lens, w, None, 0, 0, 60.0, 0, want_counts=False, want_pos=False)
+
+    w, out = step()
+    torch.cuda.synchronize(dev)
+    N_.profile_enable(True)
+    steps = 3
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        w, out = step()
+    e1.record(stream)
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / steps
+    fuse_ms = N_.profile_read(N_.PROF_FUSE_STREAM)
+    N_.profile_enable(False)
+    t = torch.tensor([ms, fuse_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, fuse_ms = t.tolist()
+    deferred = int((out.lens < 0).sum().item())
+    union = int(out.lens.clamp(min=0).sum().item())
+    check = _oracle_check_weighted(ids, micro, lens, w, out, 0, None, n=32, seed=2) if rank == 0 else None
+    alg = 8 * Qc * R_NQ * K_NQ + Qc * R_NQ * 12 + 12 * union + 8 * Qc
+    hbm, _tf, _w = load_peaks()
+    return {"value": world * Qc / (ms * 1e-3), "unit": "fused queries/s", "ms_per_step": ms, "fuse_kernel_ms": fuse_ms,
+            "queries_per_gpu": Qc, "n_gpus": world, "hbm_frac": alg / (fuse_ms * 1e-3) / 1e9 / hbm, "deferred": deferred,
+            "parity": check,
+            "workload": "configs[4]: 200 000 queries x 5 x top-1000 per GPU, QPP (13 predictors) + min-max + W-CombSUM(RSD), "
+                        "one launch per kernel per step; 1 M queries = 5 such steps per GPU"}
+
+
+def api_e2e_leg(args, dev):
+    """File to file through the reference-facing call: 5 x <Ranker>.norm.res + 5 x .qpp on disk ->
+    qppfusion.fusion.run_fusion("wcombsum") -> fused .res on disk (native parse + pack + H2D + qf_fuse + CSR compaction
+    + D2H + native writer).  A 512-query sample of the configs[1] shape (2.56 M run-file lines, ~106 MB of text)."""
+    import contextlib
+    import io
+    import shutil
+    import tempfile
+    import torch
+    from qppfusion import fusion
+    nq = 512
+    root = tempfile.mkdtemp(prefix="qf_api_e2e_")
+    try:
+        runs_dir, qpp_dir = write_synth_run_files(root, nq, seed=21)
+        in_bytes = sum(os.path.getsize(os.path.join(runs_dir, f)) for f in os.listdir(runs_dir))
+        out_path = os.path.join(root, "wcombsum_rsd.res")
+        times = []
+        for _ in range(4):
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            with contextlib.redirect_stdout(io.StringIO()):
+                fusion.run_fusion("wcombsum", runs_dir, qpp_dir=qpp_dir, qpp_model="RSD", output_path=out_path, return_fused=False)
+            torch.cuda.synchronize(dev)
+            times.append(time.perf_counter() - t0)
+        best = min(times[1:])
+        out_bytes = os.path.getsize(out_path)
+        return {"value": nq / best, "unit": "fused queries/s", "seconds": best, "queries": nq, "input_text_bytes": in_bytes,
+                "output_text_bytes": out_bytes, "host_threads": os.cpu_count(),
+                "workload": "run_fusion('wcombsum', runs_dir, qpp_dir, output_path): .norm.res + .qpp files -> fused .res "
+                            "file, wall clock, best of 3 after one warm-up (page cache warm)"}
+    finally:
+        shutil.rmtree(root, ignore_errors=True)
+
+
+def pcie_probe(dev, up_bytes, down_bytes):
+    """Pinned-memory copy bandwidth with both directions active (the e2e step's pattern): the ceiling of `e2e`."""
+    import torch
+    h_up = torch.empty(up_bytes, dtype=torch.uint8).pin_memory()
+    h_dn = torch.empty(down_bytes, dtype=torch.uint8).pin_memory()
+    d_up = torch.empty(up_bytes, dtype=torch.uint8, device=dev)
+    d_dn = torch.empty(down_bytes, dtype=torch.uint8, device=dev)
+    s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 6
+    cur = torch.cuda.current_stream(dev)
+    for it in range(2):
+        e0.record(cur)
+        s1.wait_stream(cur)
+        s2.wait_stream(cur)
+        for _ in range(reps):
+            with torch.cuda.stream(s1):
+                d_up.copy_(h_up, non_blocking=True)
+            with torch.cuda.stream(s2):
+                h_dn.copy_(d_dn, non_blocking=True)
+        cur.wait_stream(s1)
+        cur.wait_stream(s2)
+        e1.record(cur)
+        torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / reps
+    return {"ms_per_step_copies_only": ms, "h2d_gbs": up_bytes / ms / 1e6, "d2h_gbs": down_bytes / ms / 1e6}
+
+
+def recorded_reference():
+    """The REAL reference (src/fusion.py weighted_combsum etc.) cannot travel to the GPU box (/root/reference exists
+    only in the build container): its timing is recorded there by `python bench.py --impl reference` and committed."""
+    p = os.path.join(ROOT, "profiles", "ref_real_fusion_cpu.json")
+    if os.path.isfile(p):
+        return json.load(open(p))
+    return None
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -480,7 +753,13 @@ def run_ours(args):
 
     # The product path replays the step as ONE CUDA graph per input set (qppfusion.pipeline.FusionStepGraph): the
     # kernels are 10-400 us long and issuing seven of them from Python per step leaves the GPU waiting for the host.
+    # N > 1: the ranks' shards form ONE logical run file of world x 3 452 queries, so the cross-query min / max of
+    # _normalize_qpp (src/qpp.py:340-374) is all-reduced over the ranks inside every step (ShardedFusionStep).
     def make_graph(i, compact):
+        if world > 1:
+            from qppfusion.pipeline import ShardedFusionStep
+            return ShardedFusionStep(*sets[i], qpp_index=5, top_k=100, k_cut=50, round6=True, method=0, rrf_k=60.0,
+                                     flags=0, want_counts=False, want_pos=False, compact=compact)
         return FusionStepGraph(*sets[i], qpp_index=5, top_k=100, k_cut=50, colnorm="minmax", round6=True, method=0,
                                norm=0, rrf_k=60.0, flags=0, want_counts=False, want_pos=False, compact=compact)
 
@@ -504,9 +783,32 @@ def run_ours(args):
     barrier()
     union_total = int(graphs[0].out.lens.sum().item())
     assert all(int(g.out.status.max().item()) == 0 for g in graphs)
-    eager = step(0)
-    barrier()
-    assert torch.equal(eager.lens, graphs[0].out.lens) and torch.equal(eager.scores[0, :16], graphs[0].out.scores[0, :16])
+    sharded_check = None
+    if world == 1:
+        eager = step(0)
+        barrier()
+        assert torch.equal(eager.lens, graphs[0].out.lens) and torch.equal(eager.scores[0, :16], graphs[0].out.scores[0, :16])
+    else:
+        # sharded == single GPU, bit for bit: every rank's QPP weights of input set 0 are gathered on all ranks and
+        # rank 0 recomputes the WHOLE world x Q-query file alone (it regenerates the other ranks' seeded shards)
+        graphs[0].replay()
+        mine = graphs[0].weights.contiguous()
+        allw = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allw, mine)
+        if rank == 0:
+            ok = True
+            qpp_all = []
+            for r_ in range(world):
+                ids_r, micro_r, lens_r, feats_r = sets[0] if r_ == 0 else synth_device(Q, R, K, 20250101 + 2 + 17 * r_, dev)
+                qpp_all.append(ops.qpp_stats(micro_r, lens_r, feats_r, None, None, top_k=100, k_cut=50)[0])
+                del ids_r, micro_r, lens_r, feats_r
+            qpp_all = torch.cat(qpp_all)
+            ops.qpp_colnorm_(qpp_all, "minmax", round6=True)
+            w_all = ops.qpp_select_weight(qpp_all, 5)
+            for r_ in range(world):
+                ok &= bool(torch.equal(w_all[r_ * Q:(r_ + 1) * Q].view(torch.int64), allw[r_].view(torch.int64)))
+            sharded_check = {"queries": world * Q, "weights_bit_equal_to_single_gpu": ok}
+            del qpp_all, w_all
     barrier()
 
     # ---- timed region: K steps (graph replays), device-timed, max over ranks
@@ -544,6 +846,10 @@ def run_ours(args):
     fuse_op_ms = sum(e[2].elapsed_time(e[3]) for e in evs) / args.steps
     norm_ms = sum(e[1].elapsed_time(e[2]) for e in evs) / args.steps
     assert int((graphs[0].out.lens < 0).sum().item()) == 0       # nothing left deferred
+    main_check = _oracle_check_weighted(sets[0][0], sets[0][1], sets[0][2], graphs[0].weights, graphs[0].out, 0, None,
+                                        n=32, seed=0) if rank == 0 else None
+    wrrf = wrrf_leg(args, dev, sets) if (rank == 0 and world == 1) else None
+    torch.cuda.empty_cache()
 
     # ---- end to end: pinned host buffers -> H2D into the graph's input tensors -> graph replay (step + CSR
     # compaction) -> D2H of the fused run.  Three streams (H2D / compute / D2H) so step i+1's upload and step i-1's
@@ -617,6 +923,8 @@ def run_ours(args):
     d2h = d2h_bytes[0]
     h_in, h_out = h_sets, (h_off, h_ids, h_sc)
     del graphs
+    barrier()
+    pcie = pcie_probe(dev, h2d, max(d2h, 1 << 20))       # the same bytes per step, copies only: the ceiling of e2e
 
     del sets, h_in, h_out
     torch.cuda.empty_cache()
@@ -629,6 +937,11 @@ def run_ours(args):
     torch.cuda.empty_cache()
     encoder = None if args.no_dense else encoder_leg(args, dev, world, rank)
     torch.cuda.empty_cache()
+    c1 = c1_leg(args, dev) if (rank == 0 and not args.no_extra) else None
+    torch.cuda.empty_cache()
+    c5 = None if args.no_extra else c5_leg(args, dev, world, rank)
+    torch.cuda.empty_cache()
+    api = api_e2e_leg(args, dev) if (rank == 0 and world == 1 and not args.no_extra) else None
 
     times = torch.tensor([ms_total, e2e_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -640,6 +953,24 @@ def run_ours(args):
         n_post = Q * R * K
         alg_bytes = 8 * n_post + Q * R * 12 + 12 * union_total + 8 * Q   # ids+micro in, lens+weights, ids+f64 out
         achieved = alg_bytes / (fuse_ms * 1e-3) / 1e9
+        # second roofline: instruction issue.  The fusion kernel is bound by the warp schedulers, not by HBM or the
+        # shared-memory pipe: warp-instructions per query from the committed ncu capture x
+        # queries per launch / measured kernel time, against 4 schedulers x 148 SMs x the SM clock seen under load.
+        ft = {}
+        try:
+            ft = json.load(open(os.path.join(ROOT, "profiles", "fuse_traffic.json")))
+        except Exception:
+            pass
+        issue = None
+        if ft.get("warp_inst_per_query") and clocks and clocks.get("sm_mhz"):
+            peak_i = 4 * 148 * clocks["sm_mhz"] * 1e6
+            ach_i = ft["warp_inst_per_query"] * Q / (fuse_ms * 1e-3)
+            issue = {"kernel": "fuse_stream_kernel", "bound": "issue", "achieved": ach_i / 1e9, "peak": peak_i / 1e9,
+                     "unit": "G warp-instructions/s", "frac": ach_i / peak_i,
+                     "warp_inst_per_query": ft["warp_inst_per_query"],
+                     "smem_wavefronts_per_query": ft.get("smem_wavefronts_per_query"),
+                     "lsu_frac": (ft.get("smem_wavefronts_per_query") or 0) * Q / (fuse_ms * 1e-3) / (148 * clocks["sm_mhz"] * 1e6),
+                     "source": "profiles/fuse_traffic.json (ncu --set full of the same kernel) x in-run kernel time"}
         line = {
             "metric": METRIC, "value": world * Q * args.steps / (ms_total * 1e-3), "unit": "fused queries/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
@@ -648,7 +979,9 @@ def run_ours(args):
                                    "cross-query min-max + W-CombSUM(RSD) per step (BASELINE configs[1]); each step is "
                                    "one CUDA-graph replay of the 7 kernels",
                        "queries_per_gpu": Q, "retrievers": R, "depth": K, "score_format": "int32 micro-units",
-                       "union_ratio": union_total / n_post, "sharding": f"query-sharded x{world}, no collective",
+                       "union_ratio": union_total / n_post,
+                       "sharding": (f"query-sharded x{world}; one all-reduce(MAX) of 2x5x13 doubles per step for the "
+                                    "cross-query min/max of _normalize_qpp (ShardedFusionStep)") if world > 1 else "1 GPU",
                        "l2": "4 rotating input sets of 138 MB (> 126 MB L2)",
                        "steps_in_flight": INFLIGHT},
             "kernel_ms": {"qpp_stats": qpp_ms, "colnorm+select": norm_ms, "fuse_stream": fuse_ms,
@@ -661,8 +994,16 @@ def run_ours(args):
                          "frac_of_nominal_8TBs": achieved / 8000.0},
             "e2e": {"value": world * Q / (e2e_ms * 1e-3), "unit": "fused queries/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "pcie_ceiling": dict(pcie, queries_per_s=world * Q / (pcie["ms_per_step_copies_only"] * 1e-3),
+                                         note="the same H2D + D2H bytes per step, copies only, both directions at once "
+                                              "(this rank; measured while the other ranks do the same at N > 1)"),
                     "note": "pinned host buffers -> H2D into the graph's inputs -> graph replay (step + CSR compaction) -> "
                             "D2H; consecutive steps overlap on 3 streams"},
+            "roofline_issue": issue,
+            "parity": main_check,
+            "sharded_colnorm": sharded_check,
+            "wrrf": wrrf, "c1": c1, "c5": c5, "api_e2e": api,
+            "cpu_reference_recorded": recorded_reference(),
             # per step: qpp 1 + colnorm 3 + select 1 + fuse 2 (streaming + fix-up) = 7; CSR compaction adds 4
             "gpu_launches": (7 * (args.steps + max(args.warmup, 4)) + 7 * (args.steps + 4) + 11 * (e2e_steps + 3 + 6)
                              + (dense["gpu_launches"] if dense else 0) + (dense_c4["gpu_launches"] if dense_c4 else 0)
@@ -740,11 +1081,59 @@ def cpu_baseline(seconds=10.0):
                       f"(pandas iterrows, ~5 q/s measured at survey time)"}
 
 
+def run_reference_real(args):
+    """The REAL reference: /root/reference/src/fusion.py weighted_combsum / weighted_rrf (single-threaded pandas
+    loops, src/fusion.py:237-380) + write_runfile on a bounded subsample of the configs[1] shape, and its file-to-file
+    run_fusion on the same files.  Build container only (no GPU needed); the result is committed under profiles/ and
+    quoted by the GPU arm as `cpu_reference_recorded`."""
+    import shutil
+    import tempfile
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import ref_import
+    import contextlib
+    import io
+    rf = ref_import.import_reference_fusion()
+    nq = 40
+    root = tempfile.mkdtemp(prefix="qf_ref_real_")
+    try:
+        runs_dir, qpp_dir = write_synth_run_files(root, nq, seed=21)
+        out = {}
+        with contextlib.redirect_stdout(io.StringIO()):
+            t0 = time.perf_counter()
+            runs = rf.load_runs(runs_dir, use_normalized=True)
+            qpp = rf.load_qpp_scores(qpp_dir)
+            t_load = time.perf_counter() - t0
+            for name, fn in (("weighted_combsum", rf.weighted_combsum), ("weighted_rrf", rf.weighted_rrf)):
+                t0 = time.perf_counter()
+                fused = fn(runs, qpp, 5)
+                dt = time.perf_counter() - t0
+                t0 = time.perf_counter()
+                rf.write_runfile(fused, os.path.join(root, name + ".res"), name)
+                out[name] = {"queries_per_s": nq / dt, "seconds": dt, "write_runfile_seconds": time.perf_counter() - t0}
+            t0 = time.perf_counter()
+            rf.run_fusion("wcombsum", runs_dir, qpp_dir=qpp_dir, qpp_model="RSD", output_path=os.path.join(root, "f.res"))
+            t_api = time.perf_counter() - t0
+        rec = {"kind": "reference", "what": "REAL /root/reference/src/fusion.py (ranx stubbed, src/__init__ bypassed: "
+                                            "tools/ref_import.py), single-threaded by construction",
+               "sample": f"{nq} queries x 5 retrievers x top-1000 (configs[1] shape), synthetic .norm.res / .qpp files",
+               "cores": 1, "host_cpus": os.cpu_count(), "load_runs_and_qpp_seconds": t_load, "functions": out,
+               "run_fusion_wcombsum_file_to_file": {"queries_per_s": nq / t_api, "seconds": t_api},
+               "where": "build container (no GPU); /root/reference does not exist on the GPU box"}
+        os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
+        json.dump(rec, open(os.path.join(ROOT, "profiles", "ref_real_fusion_cpu.json"), "w"), indent=1)
+        print(json.dumps(dict(rec, impl="reference", metric=METRIC, value=out["weighted_combsum"]["queries_per_s"],
+                              unit="fused queries/s")), flush=True)
+    finally:
+        shutil.rmtree(root, ignore_errors=True)
+
+
 def run_reference(args):
     """Reference arm: the CPU implementation of the step (oracle port, all host threads) on a bounded sample."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if args.real:
+        return run_reference_real(args)
     threads = os.cpu_count() or 1
     nq_step = 1024
     ids, micro, lens, feats = _cpu_sample_arrays(nq_step, 9)
@@ -784,6 +1173,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-dense", action="store_true", help="skip the BGE dense-retrieval leg")
+    ap.add_argument("--no-extra", action="store_true", help="skip the configs[0] / configs[4] / file-to-file legs")
+    ap.add_argument("--real", action="store_true", help="--impl reference: time the REAL /root/reference/src/fusion.py "
+                    "(build container only) and write profiles/ref_real_fusion_cpu.json")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

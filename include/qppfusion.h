@@ -75,6 +75,10 @@ QF_API int qf_profile_read(int phase, float* ms);
 
 #define QF_NORM_NONE   0   /* weighted_* path: scores used as given (src/fusion.py:275)               */
 #define QF_NORM_MINMAX 1   /* ranx default norm="min-max": (s-min)/max(max-min,1e-9) per (q, r) list  */
+#define QF_NORM_ZSCORE 2   /* ranx norm="zscore": (s-mean)/max(std,1e-9) per (q, r) list; mean and the   */
+                           /* population variance are SEQUENTIAL float64 sums in list order (what numba's */
+                           /* np.mean / np.std compile to): mean = (((0+s0)+s1)+...)/n,                   */
+                           /* var = (((0+d0*d0)+d1*d1)+...)/n with d = s-mean, std = sqrt(var)            */
 
 #define QF_SCORE_F64   0   /* double scores[Q][R][K]                                                  */
 #define QF_SCORE_F32   1   /* float  scores[Q][R][K]  (widened exactly to double)                     */

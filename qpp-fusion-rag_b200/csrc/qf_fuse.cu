@@ -253,6 +253,24 @@ __global__ void __launch_bounds__(NT) fuse_kernel(const FuseParams p) {
           m.den[r] = d > 1e-9 ? d : 1e-9;     // ranx: max(max - min, 1e-9)
         }
       }
+    } else if (p.norm == QF_NORM_ZSCORE) {
+      // sequential float64 sums in list order (one lane per list: the order of the additions is the definition)
+      for (int r = warp; r < R; r += NW) {
+        const int s0 = m.start[r], s1 = m.start[r + 1];
+        if (lane == 0 && s1 > s0) {
+          double c = 0.0;
+          for (int i = s0; i < s1; ++i) c = __dadd_rn(c, raw_to_f64(s_sc[i]));
+          const double mean = __ddiv_rn(c, (double)(s1 - s0));
+          double ssd = 0.0;
+          for (int i = s0; i < s1; ++i) {
+            const double d = __dsub_rn(raw_to_f64(s_sc[i]), mean);
+            ssd = __dadd_rn(ssd, __dmul_rn(d, d));
+          }
+          const double sd = __dsqrt_rn(__ddiv_rn(ssd, (double)(s1 - s0)));
+          m.mn[r] = mean;
+          m.den[r] = sd > 1e-9 ? sd : 1e-9;
+        }
+      }
     }
     {
       int bad = 0;
@@ -357,7 +375,7 @@ __global__ void __launch_bounds__(NT) fuse_kernel(const FuseParams p) {
         return __ddiv_rn(m.w[r], __dadd_rn(p.rrf_k, rank));
       }
       double s = raw_to_f64(s_sc[seq]);
-      if (p.norm == QF_NORM_MINMAX) s = __ddiv_rn(__dsub_rn(s, m.mn[r]), m.den[r]);
+      if (p.norm != QF_NORM_NONE) s = __ddiv_rn(__dsub_rn(s, m.mn[r]), m.den[r]);   // min-max: mn = min; z-score: mn = mean
       if (skip_zero && s == 0.0) counts = false;
       return weighted ? __dmul_rn(m.w[r], s) : s;
     };
@@ -613,7 +631,8 @@ extern "C" int qf_fuse(const int32_t* doc_ids, const void* scores, int score_typ
              qf_fuse_max_postings());
   QF_REQUIRE(method == QF_METHOD_SUM || method == QF_METHOD_MNZ || method == QF_METHOD_RRF, QF_E_INVALID,
              "qf_fuse: unknown method %d", method);
-  QF_REQUIRE(norm == QF_NORM_NONE || norm == QF_NORM_MINMAX, QF_E_INVALID, "qf_fuse: unknown norm %d", norm);
+  QF_REQUIRE(norm == QF_NORM_NONE || norm == QF_NORM_MINMAX || norm == QF_NORM_ZSCORE, QF_E_INVALID,
+             "qf_fuse: unknown norm %d", norm);
   QF_REQUIRE(score_type >= QF_SCORE_F64 && score_type <= QF_SCORE_MICRO, QF_E_INVALID,
              "qf_fuse: unknown score_type %d", score_type);
   if (Q == 0) return QF_OK;

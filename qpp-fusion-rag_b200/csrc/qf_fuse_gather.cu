@@ -409,30 +409,29 @@ __global__ void __launch_bounds__(NT, MINB) fuse_gather_kernel(const FuseParams 
       push_failed(fail, (u32)r << 10, i0);
     };
     {
+      // all lists' doc ids in flight at once (RM x 4 registers; one 16-byte load per list and thread)
       const int r0 = m.first;
-      int r = r0, len_r = m.len[r];                        // n > 0: there is a non-empty list
-      int cur[4] = {0, 0, 0, 0}, nxt[4] = {0, 0, 0, 0};
-      load_ids(cur, r, len_r);
-      while (r < R) {
-        const int r2 = m.next[r];
-        const int len2 = r2 < R ? m.len[r2] : 0;
-        if (r2 < R) load_ids(nxt, r2, len2);
-        if (r == r0) {
-          first4(cur, r, len_r);
-          __syncthreads();                                 // first list complete: keys visible
-          for (int g = tid; g < G; g += NT) {              // a doc id twice in the first list sits in its group twice
-            const uint4 k = reinterpret_cast<const uint4*>(s_keys)[g];
-            defer |= (k.x != EMPTY && (k.x == k.y || k.x == k.z || k.x == k.w)) ||
-                     (k.y != EMPTY && (k.y == k.z || k.y == k.w)) || (k.z != EMPTY && k.z == k.w);
-          }
-        } else {
-          join4(cur, r, len_r);
-        }
+      int idv[RM][4];
+      int lenr[RM];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) cur[j] = nxt[j];
-        r = r2;
-        len_r = len2;
+      for (int r = 0; r < RM; ++r) {
+        lenr[r] = r < R ? m.len[r] : 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) idv[r][j] = 0;
+        if (lenr[r] > 0) load_ids(idv[r], r, lenr[r]);
       }
+#pragma unroll
+      for (int r = 0; r < RM; ++r)
+        if (r == r0) first4(idv[r], r, lenr[r]);
+      __syncthreads();                                     // first list complete: keys visible
+      for (int g = tid; g < G; g += NT) {                  // a doc id twice in the first list sits in its group twice
+        const uint4 k = reinterpret_cast<const uint4*>(s_keys)[g];
+        defer |= (k.x != EMPTY && (k.x == k.y || k.x == k.z || k.x == k.w)) ||
+                 (k.y != EMPTY && (k.y == k.z || k.y == k.w)) || (k.z != EMPTY && k.z == k.w);
+      }
+#pragma unroll
+      for (int r = 0; r < RM; ++r)
+        if (r != r0 && lenr[r] > 0) join4(idv[r], r, lenr[r]);
     }
 
     // ------------------------------------------------------------ drain: the queued postings, 32 per warp round
@@ -547,12 +546,16 @@ __global__ void __launch_bounds__(NT, MINB) fuse_gather_kernel(const FuseParams 
     double fmn = INFINITY, fmx = -INFINITY, samp = 0.0;
     bool has = false;
     {
+      // An absent (slot, list) pair must cost as little as a present one saves: two thirds of the pairs are absent,
+      // and every warp-level instruction below is issued for them too.  Per pair: halfword extract, compare, address,
+      // predicated 4-byte gather, conversion, multiply, predicated add, predicated mask update.
       double wr[RM], lmn[RM], lden[RM];
-      int st[RM];
+      u32 st[RM], rowS[RM];
 #pragma unroll
       for (int r = 0; r < RM; ++r) {
         wr[r] = r < R ? m.w[r] : 0.0;
-        st[r] = r < R ? m.start[r] : 0;
+        st[r] = r < R ? (u32)m.start[r] : 0u;
+        rowS[r] = S_sa + 4u * (u32)(r * Kp);
         lmn[r] = (MODE && minmax && r < R) ? m.mn[r] : 0.0;
         lden[r] = (MODE && minmax && r < R) ? m.den[r] : 1.0;
       }
@@ -573,51 +576,55 @@ __global__ void __launch_bounds__(NT, MINB) fuse_gather_kernel(const FuseParams 
         const u32 kj[4] = {k4.x, k4.y, k4.z, k4.w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
+          // (an empty slot has no P entries: nobody ever resolved a posting to it)
           double acc = 0.0;                                // the reference starts from 0.0 (src/fusion.py:275)
-          u32 seq = 0;
-          int cnt = 0, cntz = 0;
-          const bool occ = kj[j] != EMPTY;
+          u32 pm = 0u, pz = 0u;                            // lists holding the doc / with a non-zero score
+          u32 ev[RM];
 #pragma unroll
           for (int r = 0; r < RM; ++r) {
+            ev[r] = PNONE;
             if (r < R) {
-              const u32 w2 = (j < 2) ? pr[r].x : pr[r].y;
-              const u32 e = (j & 1) ? (w2 >> 16) : (w2 & 0xFFFFu);
-              const bool pres = occ && e != PNONE;
+              const u32 e = __byte_perm((j < 2) ? pr[r].x : pr[r].y, 0u, (j & 1) ? 0x4432u : 0x4410u);
+              ev[r] = e;
+              const bool pres = e != PNONE;
               u32 raw = 0u;
-              if (pres && (MODE == 0 || stage)) raw = s_S[r * Kp + (int)e];
+              if (MODE == 0 || stage) {
+                if (pres) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(raw) : "r"(rowS[r] + 4u * e));
+              }
               double v;
-              bool counts = true;
               if (MODE && is_rrf) {
                 const double rank = has_rk ? (double)(int)raw : (double)((int)e + 1);
                 v = __ddiv_rn(wr[r], __dadd_rn(p.rrf_k, rank));
               } else {
-                double s = raw_to_f64(*reinterpret_cast<const raw_t*>(&raw));
-                if (MODE && minmax) s = __ddiv_rn(__dsub_rn(s, lmn[r]), lden[r]);
-                if (MODE && skip_zero && s == 0.0) counts = false;
-                v = __dmul_rn(wr[r], s);                   // w == 1.0 when unweighted: exact
+                double sc = raw_to_f64(*reinterpret_cast<const raw_t*>(&raw));
+                if (MODE && minmax) sc = __ddiv_rn(__dsub_rn(sc, lmn[r]), lden[r]);
+                if (MODE && skip_zero && pres && sc != 0.0) pz |= 1u << r;
+                v = __dmul_rn(wr[r], sc);                  // w == 1.0 when unweighted: exact
               }
-              const double a2 = __dadd_rn(acc, v);
-              acc = pres ? a2 : acc;
-              seq = (pres && cnt == 0) ? (u32)st[r] + e : seq;
-              cnt += pres ? 1 : 0;
-              if (MODE) cntz += (pres && counts) ? 1 : 0;
+              if (pres) {
+                acc = __dadd_rn(acc, v);
+                pm |= 1u << r;
+              }
             }
           }
-          const int c_out = (MODE && skip_zero) ? cntz : cnt;
+          u32 seq = 0u;                                    // first list that holds the doc: descending, last write wins
+#pragma unroll
+          for (int r = RM - 1; r >= 0; --r)
+            if (r < R && ev[r] != PNONE) seq = st[r] + ev[r];
+          const int cnt = __popc(pm);
+          const int c_out = (MODE && skip_zero) ? __popc(pz) : cnt;
           const double fs = is_mnz ? __dmul_rn(acc, (double)c_out) : acc;
           // the accumulator started from +0.0 and x + (-x) rounds to +0.0, so it is never -0.0 (Python treats
           // -0.0 == 0.0 as a tie, and so do the comparisons below)
+          const bool occ = kj[j] != EMPTY;
           fsv[gi * 4 + j] = fs;
           mtv[gi * 4 + j] = occ ? (seq | ((u32)c_out << 13)) : 0xFFFFFFFFu;
           pc += cnt;
           if (occ) {
-            const double f = fsv[gi * 4 + j];
-            fmn = f < fmn ? f : fmn;
-            fmx = f > fmx ? f : fmx;
-            if (!has) {
-              samp = f;
-              has = true;
-            }
+            fmn = fmin(fmn, fs);
+            fmx = fmax(fmx, fs);
+            samp = fs;
+            has = true;
             if (want_pos) atomicOr(&s_bitmap[seq >> 5], 1u << (seq & 31u));   // first-seen bitmap (out_pos)
           }
         }
@@ -875,9 +882,9 @@ int dispatch_gmode(const FuseParams& p, cudaStream_t stream) {
 namespace qf {
 
 bool fuse_gather_supported(const FuseParams& p, int score_type) {
-  static const bool off = getenv("QF_FUSE_NOGATHER") != nullptr;     // A/B hook: r1h streaming kernel instead
-  if (off) return false;
-  if (p.flags & (FUSE_FLAG_DEBUG_FULLSORT | FUSE_FLAG_DEBUG_GENERAL | FUSE_FLAG_DEBUG_NOGATHER)) return false;
+  static const bool on = getenv("QF_FUSE_GATHER") != nullptr;        // A/B hook: gather kernel wherever it applies
+  if (!on && !(p.flags & FUSE_FLAG_GATHER)) return false;
+  if (p.flags & (FUSE_FLAG_DEBUG_FULLSORT | FUSE_FLAG_DEBUG_GENERAL)) return false;
   if (score_type != QF_SCORE_F32 && score_type != QF_SCORE_MICRO) return false;
   if (p.R > GR || p.K > KMAX) return false;
   if ((long long)p.R * p.K > 5120) return false;

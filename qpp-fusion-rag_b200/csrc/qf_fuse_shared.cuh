@@ -8,7 +8,7 @@ namespace qf {
 constexpr int FUSE_MAX_R = 32;
 constexpr uint32_t FUSE_FLAG_DEBUG_FULLSORT = 0x100u;   // test hook: general kernel, force the 64-bit sort path
 constexpr uint32_t FUSE_FLAG_DEBUG_GENERAL = 0x200u;    // test hook: skip the streaming kernels
-constexpr uint32_t FUSE_FLAG_DEBUG_NOGATHER = 0x400u;   // test hook: skip the gather kernel (r1h streaming kernel instead)
+constexpr uint32_t FUSE_FLAG_GATHER = 0x400u;           // opt-in: the deposit + gather kernel (qf_fuse_gather.cu) instead of the streaming one
 constexpr int FUSE_DEFERRED = -1;                       // out_lens marker: query left to the general kernel
 
 struct FuseParams {
@@ -46,7 +46,10 @@ bool fuse_stream_supported(const FuseParams& p);
 int fuse_stream_launch(const FuseParams& p, int score_type, cudaStream_t stream);
 
 // Gather kernel (qf_fuse_gather.cu, round 2): same contract as the streaming kernel, smaller envelope (R <= 8,
-// K <= 1024, 4-byte scores); preferred whenever it applies.
+// K <= 1024, 4-byte scores).  Measured on B200 (profiles/r2c_fuse_gather_ncu_summary.txt): 20 % fewer shared-memory
+// wavefronts but 12 % more instructions than the streaming kernel and 10 % SLOWER -- the fusion kernels are bound by
+// instruction issue, not by the LSU pipe -- so it is opt-in (FUSE_FLAG_GATHER / QF_FUSE_GATHER=1), kept with full
+// parity coverage as the measured alternative.
 bool fuse_gather_supported(const FuseParams& p, int score_type);
 int fuse_gather_launch(const FuseParams& p, int score_type, cudaStream_t stream);
 

@@ -167,7 +167,8 @@ __global__ void __launch_bounds__(NT, MINB) fuse_stream_kernel(const FuseParams 
   const bool skip_zero = MODE ? (p.flags & QF_FLAG_MNZ_SKIP_ZERO) != 0 : false;
   const bool check_sorted = MODE ? (p.flags & QF_FLAG_REQUIRE_SORTED) != 0 : false;
   const bool unranked = (p.flags & QF_FLAG_UNRANKED_OUTPUT) != 0;
-  const bool minmax = MODE ? ((p.norm == QF_NORM_MINMAX) && !is_rrf) : false;
+  const bool zscore = MODE ? ((p.norm == QF_NORM_ZSCORE) && !is_rrf) : false;
+  const bool minmax = MODE ? ((p.norm != QF_NORM_NONE) && !is_rrf) : false;     // any per-list (sub, den) normalisation
   const bool need_scores = !is_rrf || check_sorted;
   const bool want_pos = (p.out_pos != nullptr);
 
@@ -265,6 +266,22 @@ __global__ void __launch_bounds__(NT, MINB) fuse_stream_kernel(const FuseParams 
       for (int r = warp; r < R; r += NW) {
         const raw_t* gs = gsc + (size_t)r * K;
         const int len = m.len[r];
+        if (zscore) {          // sequential float64 sums in list order: one lane per list (include/qppfusion.h)
+          if (lane == 0 && len > 0) {
+            double c = 0.0;
+            for (int i = 0; i < len; ++i) c = __dadd_rn(c, raw_to_f64(__ldg(gs + i)));
+            const double mean = __ddiv_rn(c, (double)len);
+            double ssd = 0.0;
+            for (int i = 0; i < len; ++i) {
+              const double d = __dsub_rn(raw_to_f64(__ldg(gs + i)), mean);
+              ssd = __dadd_rn(ssd, __dmul_rn(d, d));
+            }
+            const double sd = __dsqrt_rn(__ddiv_rn(ssd, (double)len));
+            m.mn[r] = mean;
+            m.den[r] = sd > 1e-9 ? sd : 1e-9;
+          }
+          continue;
+        }
         double mn = INFINITY, mx = -INFINITY;
         for (int i = lane; i < len; i += 32) {
           const double v = raw_to_f64(__ldg(gs + i));

@@ -21,13 +21,13 @@ QF_OK = 0
 _ERR_NAMES = {-1: "QF_E_INVALID", -2: "QF_E_UNSUPPORTED", -3: "QF_E_CUDA", -4: "QF_E_NO_DEVICE", -5: "QF_E_WORKSPACE"}
 
 METHOD_SUM, METHOD_MNZ, METHOD_RRF = 0, 1, 2
-NORM_NONE, NORM_MINMAX = 0, 1
+NORM_NONE, NORM_MINMAX, NORM_ZSCORE = 0, 1, 2
 SCORE_F64, SCORE_F32, SCORE_MICRO = 0, 1, 2
 FLAG_MNZ_SKIP_ZERO, FLAG_REQUIRE_SORTED, FLAG_UNRANKED_OUTPUT = 1, 2, 4
 FLAG_LARGE_UNION = 8              # performance hint: little overlap between the runs (larger hash table)
 FLAG_DEBUG_FULLSORT = 0x100      # general kernel, 64-bit sort path (test hook)
 FLAG_DEBUG_GENERAL = 0x200       # skip the gather / streaming fusion kernels (test hook)
-FLAG_DEBUG_NOGATHER = 0x400      # skip the gather kernel: r1h streaming kernel instead (test hook)
+FLAG_GATHER = 0x400              # opt-in: deposit + gather fusion kernel instead of the streaming one (same results)
 QSTAT_DUPLICATES, QSTAT_UNSORTED, QSTAT_BAD_LEN = 1, 2, 4
 QPP_BRIDGE_COLS, QPP_RESEARCH_COLS = 13, 5
 QPP_COLS = QPP_BRIDGE_COLS + QPP_RESEARCH_COLS

@@ -141,6 +141,15 @@ def fuse_packed(packed: PackedRuns, method: int, weights: Optional[np.ndarray] =
     dev = _device()
     t = lambda a: None if a is None else torch.from_numpy(np.ascontiguousarray(a)).to(dev)
     shape_key = tuple(packed.doc_ids.shape[1:])
+    r_, k_ = shape_key
+    if r_ * k_ > N.fuse_max_postings() or r_ > 32:
+        # K is the deepest (qid, ranker) list of the whole call (every list is padded to it): name it
+        qi, ri = np.unravel_index(int(np.argmax(packed.lens)), packed.lens.shape)
+        raise ValueError(
+            f"qf_fuse keeps one query's run lists in shared memory: rankers x depth = {r_} x {k_} = {r_ * k_} exceeds "
+            f"the envelope of {N.fuse_max_postings()} postings per query (and 32 rankers). The deepest list is "
+            f"ranker '{packed.rankers[ri]}' on query '{packed.qids[qi]}' with {int(packed.lens[qi, ri])} rows; cut the "
+            f"runs to depth <= {N.fuse_max_postings() // max(1, r_)} (e.g. top_k at retrieval time) or fuse fewer runs.")
     out = ops.fuse(t(packed.doc_ids), t(packed.scores), t(packed.lens), t(weights), t(packed.ranks), method, norm,
                    rrf_k, flags | union_hint_flags(shape_key), want_counts, want_pos)
     status = out.status.cpu().numpy()
@@ -161,28 +170,35 @@ def _to_dict(packed: PackedRuns, out: ops.FuseOut) -> Fused:
 # Unweighted fusion (reference: ranx.fuse with its default norm="min-max")
 # =============================================================================
 
-def _ranx_fuse(runs: Dict[str, pd.DataFrame], method: int, rrf_k: float = 60.0) -> Fused:
+_RUN_NORMS = {"min-max": N.NORM_MINMAX, "minmax": N.NORM_MINMAX, "zscore": N.NORM_ZSCORE, "z-score": N.NORM_ZSCORE,
+              None: N.NORM_NONE, "none": N.NORM_NONE}
+
+
+def _ranx_fuse(runs: Dict[str, pd.DataFrame], method: int, rrf_k: float = 60.0, norm="min-max") -> Fused:
+    if norm not in _RUN_NORMS:
+        raise ValueError(f"Unknown run normalisation '{norm}'. Valid: min-max, zscore, none")
     packed = pack_runs(runs, mode="ranx")
     flags = N.FLAG_REQUIRE_SORTED
     if method == N.METHOD_MNZ and not config.fusion.ranx_mnz_counts_zero_scores:
         flags |= N.FLAG_MNZ_SKIP_ZERO
-    norm = N.NORM_NONE if method == N.METHOD_RRF else N.NORM_MINMAX
+    norm = N.NORM_NONE if method == N.METHOD_RRF else _RUN_NORMS[norm]
     out = fuse_packed(packed, method, None, norm, rrf_k, flags)
     return _to_dict(packed, out)      # ranked: score descending (as _ranx_to_dict, src/fusion.py:469-477)
 
 
-def combsum(runs: Dict[str, pd.DataFrame]) -> Fused:
-    """CombSUM(d,q) = sum_i S_i(d,q) over min-max normalised runs (reference src/fusion.py:170-186)."""
+def combsum(runs: Dict[str, pd.DataFrame], norm="min-max") -> Fused:
+    """CombSUM(d,q) = sum_i S_i(d,q) over min-max normalised runs (reference src/fusion.py:170-186).
+    `norm` (extension; the reference always takes ranx's default "min-max"): "min-max", "zscore" or None."""
     print("[fusion] Running CombSUM (qf_fuse)...")
-    result = _ranx_fuse(runs, N.METHOD_SUM)
+    result = _ranx_fuse(runs, N.METHOD_SUM, norm=norm)
     print(f"[fusion] CombSUM done: {len(result)} queries")
     return result
 
 
-def combmnz(runs: Dict[str, pd.DataFrame]) -> Fused:
-    """CombMNZ(d,q) = |{i: d in R_i}| x sum_i S_i(d,q) (reference src/fusion.py:189-205)."""
+def combmnz(runs: Dict[str, pd.DataFrame], norm="min-max") -> Fused:
+    """CombMNZ(d,q) = |{i: d in R_i}| x sum_i S_i(d,q) (reference src/fusion.py:189-205).  `norm`: see combsum."""
     print("[fusion] Running CombMNZ (qf_fuse)...")
-    result = _ranx_fuse(runs, N.METHOD_MNZ)
+    result = _ranx_fuse(runs, N.METHOD_MNZ, norm=norm)
     print(f"[fusion] CombMNZ done: {len(result)} queries")
     return result
 

@@ -68,3 +68,61 @@ class FusionStepGraph:
         """Run the captured step on the current stream; returns the (static) FuseOut."""
         self.graph.replay()
         return self.out
+
+
+class ShardedFusionStep:
+    """The same step on a QUERY-SHARDED run file (one rank per GPU): _normalize_qpp's per-column min / max run over ALL
+    queries of the file (src/qpp.py:340-374), so the ranks exchange them -- the one collective of the QPP + fusion path:
+
+        graph A  qf_qpp_stats -> qf_qpp_colstats (this rank's rows) -> [-min | max]
+        NCCL     ONE all-reduce(MAX) of 2 x R x 13 doubles, enqueued on the same stream between the two replays
+        graph B  (v - min) / (max - min or 1) + "%.6f" -> qf_qpp_select_weight -> qf_fuse
+
+    min / max are exact under any reduction order, so the sharded result equals the single-GPU one bit for bit
+    (checked by bench.py at N > 1 and by tools/dist_gpu_check.py).  Only colnorm="minmax" is offered here: the z-score
+    variant's sums depend on the reduction order (use distributed.qpp_colnorm_sharded_ and a tolerance)."""
+
+    def __init__(self, doc_ids, scores, lens, text_feats, *, group=None, qpp_index: int = 5, top_k: int = 100,
+                 k_cut: int = 50, round6: bool = True, method: int = N.METHOD_SUM, rrf_k: float = 60.0, flags: int = 0,
+                 ranks: Optional[torch.Tensor] = None, want_counts: bool = False, want_pos: bool = False,
+                 compact: bool = False):
+        import torch.distributed as dist
+        self.dev = N.require_cuda(doc_ids, scores, lens, text_feats, ranks)
+        self.group, self._dist = group, dist
+        ids, sc, ln, feats = doc_ids, scores, lens, text_feats
+        cur = torch.cuda.current_stream(self.dev)
+        side = torch.cuda.Stream(self.dev)
+
+        def part_a():
+            qpp, _st = ops.qpp_stats(sc, ln, feats, None, None, top_k=top_k, k_cut=k_cut)
+            st = ops.qpp_colstats(qpp)                                   # [R, C, 4] = min, max, sum, sumsq
+            return qpp, torch.stack([-st[..., 0], st[..., 1]]).contiguous()
+
+        def part_b(qpp, mm):
+            mn, mx = -mm[0], mm[1]
+            scale = torch.where(mx > mn, mx - mn, torch.ones_like(mx))
+            ops.qpp_colnorm_apply_(qpp, mn.contiguous(), scale.contiguous(), round6)
+            w = ops.qpp_select_weight(qpp, qpp_index)
+            out = ops.fuse(ids, sc, ln, w, ranks, method, N.NORM_NONE, rrf_k, flags, want_counts=want_counts,
+                           want_pos=want_pos)
+            return w, out, (ops.compact_fused(out) if compact else None)
+
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):                   # warm-up outside capture (kernel attributes, allocator, NCCL)
+            for _ in range(2):
+                qpp, mm = part_a()
+                dist.all_reduce(mm, op=dist.ReduceOp.MAX, group=group)
+                part_b(qpp, mm)
+        cur.wait_stream(side)
+        torch.cuda.synchronize(self.dev)
+        self.graph_a, self.graph_b = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph_a):
+            self.qpp, self.mm = part_a()
+        with torch.cuda.graph(self.graph_b):
+            self.weights, self.out, self.csr = part_b(self.qpp, self.mm)
+
+    def replay(self):
+        self.graph_a.replay()
+        self._dist.all_reduce(self.mm, op=self._dist.ReduceOp.MAX, group=self.group)
+        self.graph_b.replay()
+        return self.out

@@ -8,7 +8,7 @@ from oracle import fusion_oracle as fo
 
 pytestmark = pytest.mark.gpu
 
-PATHS = {"gather": 0, "gather-large": 8, "stream": 0x400, "stream-large": 0x408, "general": 0x200}
+PATHS = {"stream": 0, "stream-large": 8, "gather": 0x400, "gather-large": 0x408, "general": 0x200}
 
 
 def _random_case(rng):

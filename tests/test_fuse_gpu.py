@@ -16,16 +16,16 @@ METHODS = {"sum": 0, "mnz": 1, "rrf": 2}
 EXTRA_FLAGS = [0]
 
 
-KERNEL_PATHS = {"gather": 0, "gather-large": 8, "stream": 0x400, "stream-large": 0x408, "general": 0x200}
+KERNEL_PATHS = {"stream": 0, "stream-large": 8, "gather": 0x400, "gather-large": 0x408, "general": 0x200}
 
 
 @pytest.fixture(autouse=True, params=list(KERNEL_PATHS))
 def fuse_kernel_path(request):
-    """Every test runs five times: through the gather kernel (round 2; + general-kernel fix-up of deferred queries, the
+    """Every test runs five times: through the streaming kernel (+ general-kernel fix-up of deferred queries, the
     product path) and its larger-table configuration (QF_FLAG_LARGE_UNION, a performance hint that must not change any
-    result), through the r1h streaming kernel (debug flag 0x400 skips the gather kernel; still the product path
-    outside the gather kernel's envelope) in both table sizes, and with both disabled (debug flag 0x200), so all
-    kernels keep full parity coverage."""
+    result), through the opt-in deposit + gather kernel (flag 0x400, round 2's measured alternative) in both table
+    sizes, and with both disabled (debug flag 0x200: general kernel alone), so all kernels keep full parity
+    coverage."""
     EXTRA_FLAGS[0] = KERNEL_PATHS[request.param]
     yield
     EXTRA_FLAGS[0] = 0
@@ -43,11 +43,11 @@ def run_gpu(lists, method, weights=None, norm=0, rrf_k=60.0, flags=0, score_type
     return [o.cpu().numpy() for o in out]
 
 
-def check_against_oracle(lists, method, weights, gpu_out, ranx=False, rrf_k=60.0, mnz_skip_zero=False):
+def check_against_oracle(lists, method, weights, gpu_out, ranx=False, rrf_k=60.0, mnz_skip_zero=False, norm="min-max"):
     oid, osc, ocnt, opos, olen, ostat = gpu_out
     for q, per_r in enumerate(lists):
         if ranx:
-            docs, scores, counts = fo.fuse_ranx_query(per_r, METHODS[method], rrf_k, "min-max", mnz_skip_zero)
+            docs, scores, counts = fo.fuse_ranx_query(per_r, METHODS[method], rrf_k, norm, mnz_skip_zero)
         else:
             docs, scores, counts = fo.fuse_weighted_query(per_r, weights[q], METHODS[method], rrf_k)
         n = len(docs)
@@ -151,6 +151,22 @@ def test_ranx_semantics(method):
     if method == "mnz":
         out = run_gpu(lists, method, None, norm=1, flags=2 | 1, k=100)
         check_against_oracle(lists, method, None, out, ranx=True, mnz_skip_zero=True)
+
+
+@pytest.mark.parametrize("method", ["sum", "mnz"])
+@pytest.mark.parametrize("score_type", ["f64", "micro"])
+def test_zscore_run_normalisation(method, score_type):
+    """QF_NORM_ZSCORE (north star: "min-max/z-normalise each run"): per (query, run) zero mean / unit population
+    variance with sequential float64 sums, max(std, 1e-9) guard; bit-exact against the oracle restatement."""
+    lists = synth_lists(14, n_q=16, n_r=5, k=100, pool=230, ragged=True, ties=True, neg_ranker=2)
+    lists[0][1] = [(d, 0.7, rk) for (d, s, rk) in lists[0][1]]          # constant list -> std 0 -> 1e-9 guard
+    lists[1][0] = lists[1][0][:1]                                        # single-doc list
+    lists[2][3] = []                                                     # empty list
+    out = run_gpu(lists, method, None, norm=2, flags=2, k=100, score_type=score_type)
+    check_against_oracle(lists, method, None, out, ranx=True, norm="zscore")
+    if method == "mnz":
+        out = run_gpu(lists, method, None, norm=2, flags=2 | 1, k=100, score_type=score_type)
+        check_against_oracle(lists, method, None, out, ranx=True, mnz_skip_zero=True, norm="zscore")
 
 
 def test_stream_kernel_envelope_edges():

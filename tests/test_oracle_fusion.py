@@ -103,3 +103,21 @@ def test_learned_fusion_matches_the_real_reference():
             a = np.array([s for _, s in fused[q]])
             b = np.array([float(s) for _, s in ref[q]])
             assert np.all(np.abs(a - b) <= 2 * np.spacing(np.abs(b))), (case["name"], q)
+
+
+def test_zscore_norm_restatement():
+    """QF_NORM_ZSCORE contract: sequential sums, population variance, max(std, 1e-9) guard."""
+    import numpy as np
+    from oracle import fusion_oracle as fo
+    rng = np.random.default_rng(5)
+    v = np.sort(rng.normal(3.0, 2.0, 257))[::-1].tolist()
+    z = np.array(fo._zscore_norm(v))
+    assert abs(z.mean()) < 1e-12 and abs(z.std() - 1.0) < 1e-12
+    assert np.allclose(z, (np.array(v) - np.mean(v)) / np.std(v), rtol=1e-12, atol=1e-12)
+    assert fo._zscore_norm([0.5] * 8) == [0.0] * 8                # constant list: std 0 -> 1e-9 guard
+    assert max(abs(x) for x in fo._zscore_norm([0.7] * 9)) < 1e-6    # (the mean of nine 0.7s is not exactly 0.7)
+    assert fo._zscore_norm([2.5]) == [0.0] and fo._zscore_norm([]) == []
+    # through the ranx-path restatement: a doc absent from a run contributes nothing
+    lists = [[(1, 3.0, 1), (2, 1.0, 2)], [(2, 5.0, 1), (3, 1.0, 2)]]
+    docs, scores, counts = fo.fuse_ranx_query(lists, fo.SUM, 60, "zscore")
+    assert docs == [1, 2, 3] and scores == [1.0, 0.0, -1.0] and counts == [1, 2, 1]
