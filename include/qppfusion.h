@@ -268,6 +268,23 @@ QF_API int    qf_dense_row_topk(const float* scores, long long ld, const int32_t
 QF_API int    qf_topk_merge(const float* scores, const int32_t* ids, int G, int Q, int k,
                             float* out_scores, int32_t* out_ids, void* stream);
 
+/*
+ * Packed variants for the ONE-exchange multi-GPU search (qppfusion/distributed.py): a query's result is a pair of
+ * adjacent rows, k float32 score bits followed by k int32 ids ("[2][k] int32"), so scores and ids travel in one
+ * all-to-all and one all-gather instead of two each.
+ *   qf_dense_topk_packed : as qf_dense_topk, query q written at
+ *                          out_pairs + (q / chunk_rows) * chunk_stride + (q % chunk_rows) * 2k      (int32 elements)
+ *                          (chunk_rows = 0: plain [Q][2][k]).  chunk_rows = ceil(Q / G) with chunk_stride =
+ *                          (chunk_rows + 1) * 2k leaves one spare row per destination rank, which the host layer
+ *                          uses to ship the rank's status flag inside the same all-to-all.
+ *   qf_topk_merge_packed : segment g, query j read at in_pairs + g * seg_stride + j * 2k; output [Q][2][k].
+ */
+QF_API int    qf_dense_topk_packed(const void* queries_bf16, const void* corpus_bf16, int Q, int N, int D, int k,
+                                   long long id_offset, int32_t* out_pairs, int chunk_rows, long long chunk_stride,
+                                   int32_t* out_status, void* ws, size_t ws_bytes, void* stream);
+QF_API int    qf_topk_merge_packed(const int32_t* in_pairs, int G, int Q, int k, long long seg_stride,
+                                   int32_t* out_pairs, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Query encoder  --  replaces SentenceTransformer(model).encode(queries, normalize_embeddings=True) behind
  *                    BGERetriever._encode_queries (src/retrievers/bge.py:153-170): HF BertModel (post-LN encoder,

@@ -656,7 +656,17 @@ struct SelectParams {
   int* out_ids;            // [Q, k]  (-1 padded)
   int* out_status;         // [Q] nullable: 1 = candidate underflow, 2 = overflow
   int fixup;               // select_kernel only: process just the queries select2_kernel deferred
+  // output addressing: row(q) = (q / chunk_rows) * chunk_stride + (q % chunk_rows) * out_stride  (elements); the
+  // plain layout is out_stride = k, chunk_rows = 0.  The packed layout of the multi-GPU exchange interleaves score
+  // and id rows (out_stride = 2k, out_ids = out_scores + k) and leaves one spare row per destination chunk.
+  long long out_stride;
+  int chunk_rows;
+  long long chunk_stride;
 };
+__device__ __forceinline__ size_t out_row(const SelectParams& p, int q) {
+  if (p.chunk_rows > 0) return (size_t)(q / p.chunk_rows) * (size_t)p.chunk_stride + (size_t)(q % p.chunk_rows) * (size_t)p.out_stride;
+  return (size_t)q * (size_t)p.out_stride;
+}
 constexpr int SEL_DEFERRED = -2;   // out_ids[q][0] marker: query left to select_kernel by select2_kernel
 
 struct SelSmem {
@@ -820,7 +830,7 @@ __global__ void __launch_bounds__(SEL_NT, 1) select_kernel(const SelectParams p)
   __shared__ int s_n, s_flag;
   __shared__ int s_pref[260];
   for (int q = blockIdx.x; q < p.Q; q += gridDim.x) {
-    if (p.fixup && p.out_ids[(size_t)q * p.k] != SEL_DEFERRED) continue;      // uniform: same word for every thread
+    if (p.fixup && p.out_ids[out_row(p, q)] != SEL_DEFERRED) continue;      // uniform: same word for every thread
     int status = 0;
     int n = 0;
     const int want = min(p.k, p.N_total);
@@ -908,8 +918,8 @@ __global__ void __launch_bounds__(SEL_NT, 1) select_kernel(const SelectParams p)
           id = (int)(S.id[e] + p.id_offset);
         }
       }
-      p.out_scores[(size_t)q * p.k + j] = s;
-      p.out_ids[(size_t)q * p.k + j] = id;
+      p.out_scores[out_row(p, q) + j] = s;
+      p.out_ids[out_row(p, q) + j] = id;
     }
     if (p.out_status && tid == 0) p.out_status[q] = status;
     __syncthreads();
@@ -1008,7 +1018,7 @@ __global__ void __launch_bounds__(S2_NT, MINB) select2_kernel(const SelectParams
       }
       n = n_valid = carry;
       if (__syncthreads_or((bad || n > CAP) ? 1 : 0)) {
-        if (tid == 0) p.out_ids[(size_t)q * p.k] = SEL_DEFERRED;
+        if (tid == 0) p.out_ids[out_row(p, q)] = SEL_DEFERRED;
         continue;
       }
       // ---- copy the candidates (thread per segment)
@@ -1030,7 +1040,7 @@ __global__ void __launch_bounds__(S2_NT, MINB) select2_kernel(const SelectParams
       // ---- k-way merge input: nseg ranked lists of seg_len entries (id < 0 = padding of a short list)
       n = p.nseg * p.seg_len;
       if (n > CAP) {                                   // uniform
-        if (tid == 0) p.out_ids[(size_t)q * p.k] = SEL_DEFERRED;
+        if (tid == 0) p.out_ids[out_row(p, q)] = SEL_DEFERRED;
         continue;
       }
       int valid = 0;
@@ -1156,13 +1166,13 @@ __global__ void __launch_bounds__(S2_NT, MINB) select2_kernel(const SelectParams
         reinterpret_cast<uint4*>(s_cnt32)[tid * (CPT / 8) + v] = cv[v];
       }
       if (__syncthreads_or(tmax > S2_LONGB ? 1 : 0)) {
-        if (tid == 0) p.out_ids[(size_t)q * p.k] = SEL_DEFERRED;
+        if (tid == 0) p.out_ids[out_row(p, q)] = SEL_DEFERRED;
         continue;
       }
     }
     const int bstar = s_bstar, kept = want > 0 ? s_kept : 0;
     if (kept > S2_KEEP) {                               // uniform; cannot happen with S2_LONGB < S2_KEEP - k_max... guard
-      if (tid == 0) p.out_ids[(size_t)q * p.k] = SEL_DEFERRED;
+      if (tid == 0) p.out_ids[out_row(p, q)] = SEL_DEFERRED;
       continue;
     }
     // ---- 4. scatter the survivors into bucket order (cursor = bucket base, advanced atomically)
@@ -1176,8 +1186,8 @@ __global__ void __launch_bounds__(S2_NT, MINB) select2_kernel(const SelectParams
     }
     __syncthreads();
     // ---- exact rank inside the bucket, output
-    float* osc = p.out_scores + (size_t)q * p.k;
-    int* oid = p.out_ids + (size_t)q * p.k;
+    float* osc = p.out_scores + out_row(p, q);
+    int* oid = p.out_ids + out_row(p, q);
     for (int j = tid; j < kept; j += S2_NT) {
       const int i = s_order[j];
       const float v = s_score[i];
@@ -1445,9 +1455,17 @@ extern "C" size_t qf_dense_workspace_bytes(int Q, int N, int k) {
 
 extern "C" int qf_dense_max_k(void) { return 1024; }
 
-extern "C" int qf_dense_topk(const void* queries_bf16, const void* corpus_bf16, int Q, int N, int D, int k,
-                             long long id_offset, float* out_scores, int32_t* out_ids, int32_t* out_status, void* ws,
-                             size_t ws_bytes, void* stream) {
+namespace {
+struct OutLayout {           // see SelectParams: row(q) = (q / chunk_rows) * chunk_stride + (q % chunk_rows) * out_stride
+  long long out_stride;
+  int chunk_rows;
+  long long chunk_stride;
+};
+}  // namespace
+
+static int dense_topk_impl(const void* queries_bf16, const void* corpus_bf16, int Q, int N, int D, int k,
+                           long long id_offset, float* out_scores, int32_t* out_ids, const OutLayout& ol,
+                           int32_t* out_status, void* ws, size_t ws_bytes, void* stream) {
   QF_REQUIRE(Q >= 0 && N >= 1 && k >= 1, QF_E_INVALID, "qf_dense_topk: bad sizes Q=%d N=%d k=%d", Q, N, k);
   QF_REQUIRE(D >= BK && D % BK == 0 && D <= MAX_D, QF_E_UNSUPPORTED,
              "qf_dense_topk: D=%d must be a multiple of %d and <= %d (query tile lives in tensor memory)", D, BK, MAX_D);
@@ -1546,6 +1564,7 @@ extern "C" int qf_dense_topk(const void* queries_bf16, const void* corpus_bf16, 
   sp.seg_pairs = p.seg_pairs; sp.seg_cnt = p.seg_cnt; sp.n_segs = w.n_chunks * 2;
   sp.Q = Q; sp.k = k; sp.N_total = N; sp.id_offset = id_offset;
   sp.out_scores = out_scores; sp.out_ids = out_ids; sp.out_status = out_status;
+  sp.out_stride = ol.out_stride; sp.chunk_rows = ol.chunk_rows; sp.chunk_stride = ol.chunk_stride;
   qf::prof_mark(QF_PROF_DENSE_SELECT, 0, st);
   {
     // common case: select2_kernel (3 queries in flight per SM); select_kernel then finishes what it deferred
@@ -1616,8 +1635,41 @@ extern "C" int qf_dense_row_topk(const float* scores, long long ld, const int32_
   return QF_OK;
 }
 
+extern "C" int qf_dense_topk(const void* queries_bf16, const void* corpus_bf16, int Q, int N, int D, int k,
+                             long long id_offset, float* out_scores, int32_t* out_ids, int32_t* out_status, void* ws,
+                             size_t ws_bytes, void* stream) {
+  return dense_topk_impl(queries_bf16, corpus_bf16, Q, N, D, k, id_offset, out_scores, out_ids, OutLayout{k, 0, 0},
+                         out_status, ws, ws_bytes, stream);
+}
+
+extern "C" int qf_dense_topk_packed(const void* queries_bf16, const void* corpus_bf16, int Q, int N, int D, int k,
+                                    long long id_offset, int32_t* out_pairs, int chunk_rows, long long chunk_stride,
+                                    int32_t* out_status, void* ws, size_t ws_bytes, void* stream) {
+  QF_REQUIRE(out_pairs != nullptr && chunk_rows >= 0 && (chunk_rows == 0 || chunk_stride >= 2LL * k * chunk_rows),
+             QF_E_INVALID, "qf_dense_topk_packed: bad output layout (chunk_rows=%d chunk_stride=%lld)", chunk_rows,
+             chunk_stride);
+  return dense_topk_impl(queries_bf16, corpus_bf16, Q, N, D, k, id_offset, reinterpret_cast<float*>(out_pairs),
+                         out_pairs + k, OutLayout{2LL * k, chunk_rows, chunk_stride}, out_status, ws, ws_bytes, stream);
+}
+
+static int topk_merge_impl(const float* scores, const int32_t* ids, int G, int Q, int k, long long q_stride,
+                           long long seg_stride, float* out_scores, int32_t* out_ids, long long out_stride, void* stream);
+
 extern "C" int qf_topk_merge(const float* scores, const int32_t* ids, int G, int Q, int k, float* out_scores,
                              int32_t* out_ids, void* stream) {
+  return topk_merge_impl(scores, ids, G, Q, k, k, (long long)Q * k, out_scores, out_ids, k, stream);
+}
+
+extern "C" int qf_topk_merge_packed(const int32_t* in_pairs, int G, int Q, int k, long long seg_stride,
+                                    int32_t* out_pairs, void* stream) {
+  QF_REQUIRE(in_pairs != nullptr && out_pairs != nullptr && seg_stride >= 2LL * k * Q, QF_E_INVALID,
+             "qf_topk_merge_packed: bad argument (seg_stride=%lld)", seg_stride);
+  return topk_merge_impl(reinterpret_cast<const float*>(in_pairs), in_pairs + k, G, Q, k, 2LL * k, seg_stride,
+                         reinterpret_cast<float*>(out_pairs), out_pairs + k, 2LL * k, stream);
+}
+
+static int topk_merge_impl(const float* scores, const int32_t* ids, int G, int Q, int k, long long q_stride,
+                           long long seg_stride, float* out_scores, int32_t* out_ids, long long out_stride, void* stream) {
   QF_REQUIRE(G >= 1 && Q >= 0 && k >= 1, QF_E_INVALID, "qf_topk_merge: bad sizes G=%d Q=%d k=%d", G, Q, k);
   QF_REQUIRE((long long)G * k <= SEL_CAP, QF_E_UNSUPPORTED, "qf_topk_merge: G*k=%lld exceeds %d", (long long)G * k, SEL_CAP);
   if (Q == 0) return QF_OK;
@@ -1635,9 +1687,10 @@ extern "C" int qf_topk_merge(const float* scores, const int32_t* ids, int G, int
   }
   SelectParams sp{};
   sp.seg_pairs = nullptr; sp.seg_cnt = nullptr; sp.cand_score = scores; sp.cand_id = ids;
-  sp.q_stride = k; sp.seg_stride = (long long)Q * k; sp.nseg = G; sp.seg_len = k;
+  sp.q_stride = q_stride; sp.seg_stride = seg_stride; sp.nseg = G; sp.seg_len = k;
   sp.Q = Q; sp.k = k; sp.N_total = 0x7fffffff; sp.id_offset = 0;
   sp.out_scores = out_scores; sp.out_ids = out_ids; sp.out_status = nullptr;
+  sp.out_stride = out_stride; sp.chunk_rows = 0; sp.chunk_stride = 0;
   const int sms = qf::sm_count();
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   static const bool no_s2 = getenv("QF_DENSE_NO_SELECT2") != nullptr;     // debug hook: old ranking kernel only

@@ -91,39 +91,84 @@ def exchange_topk(scores: torch.Tensor, ids: torch.Tensor, group=None):
     return rs.view(world, qs, k), ri.view(world, qs, k), qs
 
 
-def dense_search_sharded(queries_bf16: torch.Tensor, corpus_shard_bf16: torch.Tensor, k: int, id_offset: int, group=None,
-                         merge: str = "all_to_all"):
-    """Every rank: local top-k over its corpus rows (global ids), exchange, k-way merge -> identical [Q, k] on all
-    ranks.  merge="all_to_all" (default): each rank merges Q/G queries and the merged slices are all-gathered;
-    merge="all_gather": every rank gathers all [G, Q, k] lists and merges all Q queries itself."""
+class ShardedSearchResult:
+    """Result of dense_search_packed: everything stays on the device and NOTHING has been synchronised with the host.
+    `pairs` is int32 [rows, 2, k] (this rank's merged query slice [lo, hi)) or, after the all-gather, [Q, 2, k];
+    `flags` int32 [G] holds every rank's threshold-failure flag (they travelled inside the all-to-all).  Read
+    `ok()` when the result is consumed (one tiny D2H, e.g. together with the result copy); a False means some shard's
+    sampled threshold failed -- rare -- and the caller repeats the search with the exact path on all ranks."""
+
+    def __init__(self, pairs, flags, lo, hi, gathered):
+        self.pairs, self.flags, self.lo, self.hi, self.gathered = pairs, flags, lo, hi, gathered
+
+    @property
+    def scores(self):
+        return self.pairs[: (self.hi - self.lo), 0, :].view(torch.float32)
+
+    @property
+    def ids(self):
+        return self.pairs[: (self.hi - self.lo), 1, :]
+
+    def ok(self) -> bool:
+        return int(self.flags.max().item()) == 0
+
+
+def dense_search_packed(queries_bf16: torch.Tensor, corpus_shard_bf16: torch.Tensor, k: int, id_offset: int, group=None,
+                        gather: bool = True) -> ShardedSearchResult:
+    """Sharded exact search with ONE exchange and no host synchronisation:
+        local top-k written as packed (score, id) rows per destination rank (qf_dense_topk_packed)
+        -> ONE all-to-all (each rank receives all shards' lists for ITS Q/G queries, plus every rank's status flag in
+           the spare row of its chunk)
+        -> k-way merge of the slice (qf_topk_merge_packed)
+        -> gather=True: ONE all-gather of the merged slices ([Q, 2, k] on every rank);
+           gather=False: the rank keeps only its slice (a serving front end reads the G slices: Q*k*8 bytes in total
+           leave the GPUs instead of G times that).
+    Round 1 used five collectives (scores and ids separately, twice, plus a MAX all-reduce read back with .item())."""
     from . import ops
     world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    Q = queries_bf16.shape[0]
+    send, _status = ops.dense_topk_packed(queries_bf16, corpus_shard_bf16, k, id_offset, chunks=world)
+    rows = send.shape[1] - 1
+    recv = torch.empty_like(send)
+    dist.all_to_all_single(recv, send, group=group)                    # chunk g of the send buffer goes to rank g
+    flags = recv[:, rows, 0, 0].contiguous()                           # every rank's flag, identical on all ranks
+    merged = ops.topk_merge_packed(recv, rows)                         # [rows, 2, k]
+    lo = min(Q, rank * rows)
+    hi = min(Q, lo + rows)
+    if not gather:
+        return ShardedSearchResult(merged, flags, lo, hi, False)
+    full = torch.empty((world * rows, 2, k), dtype=torch.int32, device=merged.device)
+    dist.all_gather_into_tensor(full, merged, group=group)
+    return ShardedSearchResult(full, flags, 0, Q, True)
 
-    def run(exact: bool):
-        if exact:     # local search with the status-driven exact repair (reads the status back: a host sync)
-            scores, ids, status = ops.dense_topk(queries_bf16, corpus_shard_bf16, k, id_offset)
-        else:         # raw op: nothing waits for the host, the whole call is enqueued back to back
-            scores, ids, status = torch.ops.qppfusion.dense_topk(queries_bf16, corpus_shard_bf16, int(k), int(id_offset))
-        Q = scores.shape[0]
-        if merge == "all_gather" or world == 1:
-            gs, gi = gather_topk(scores, ids, group)
-            ms, mi = ops.topk_merge(gs, gi)
-            return ms, mi, status
-        rs, ri, qs = exchange_topk(scores, ids, group)
-        ms, mi = ops.topk_merge(rs.contiguous(), ri.contiguous())                   # [qs, k] for this rank's query slice
-        fs = torch.empty((world * qs, k), dtype=ms.dtype, device=ms.device)
-        fi = torch.empty((world * qs, k), dtype=mi.dtype, device=mi.device)
-        dist.all_gather_into_tensor(fs, ms.contiguous(), group=group)
-        dist.all_gather_into_tensor(fi, mi.contiguous(), group=group)
-        return fs[:Q], fi[:Q], status
 
-    # Optimistic pass without any host synchronisation; ONE check at the end (the flag is MAX-reduced so that every
-    # rank takes the same branch).  A failed sampled threshold anywhere -- rare -- repeats the call on all ranks with
-    # the exact repair path.
-    out_s, out_i, status = run(False)
-    flag = (status != 0).any().to(torch.int32).reshape(1)
-    if world > 1:
-        dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
-    if int(flag.item()) != 0:
-        out_s, out_i, status = run(True)
-    return out_s, out_i, status
+def dense_search_sharded(queries_bf16: torch.Tensor, corpus_shard_bf16: torch.Tensor, k: int, id_offset: int, group=None,
+                         merge: str = "all_to_all", exact: bool = False):
+    """Every rank: local top-k over its corpus rows (global ids), exchange, k-way merge -> identical [Q, k] on all
+    ranks.  -> (scores, ids, status).
+
+    merge="all_to_all" (default): the packed ONE-exchange path (dense_search_packed) -- one all-to-all, one
+    all-gather, nothing waits for the host.  `status` is then the int32 [G] vector of every rank's threshold-failure
+    flag (identical on all ranks); the CALLER reads it when it consumes the result and, if any flag is set -- rare --
+    repeats the call with exact=True on all ranks.
+    exact=True or merge="all_gather": local search with the status-driven exact repair (reads the status back: a host
+    synchronisation), scores and ids exchanged separately; `status` is the per-query vector (all zero)."""
+    from . import ops
+    world = dist.get_world_size(group)
+    if merge == "all_to_all" and world > 1 and not exact:
+        res = dense_search_packed(queries_bf16, corpus_shard_bf16, k, id_offset, group, gather=True)
+        return res.scores, res.ids, res.flags
+    scores, ids, status = ops.dense_topk(queries_bf16, corpus_shard_bf16, k, id_offset)
+    Q = scores.shape[0]
+    if merge == "all_gather" or world == 1:
+        gs, gi = gather_topk(scores, ids, group)
+        ms, mi = ops.topk_merge(gs, gi)
+        return ms, mi, status
+    rs, ri, qs = exchange_topk(scores, ids, group)
+    ms, mi = ops.topk_merge(rs.contiguous(), ri.contiguous())                   # [qs, k] for this rank's query slice
+    fs = torch.empty((world * qs, k), dtype=ms.dtype, device=ms.device)
+    fi = torch.empty((world * qs, k), dtype=mi.dtype, device=mi.device)
+    dist.all_gather_into_tensor(fs, ms.contiguous(), group=group)
+    dist.all_gather_into_tensor(fi, mi.contiguous(), group=group)
+    return fs[:Q], fi[:Q], status

@@ -214,6 +214,47 @@ def _(queries, corpus, k, id_offset):
             torch.empty((Q,), dtype=torch.int32, device=queries.device))
 
 
+def dense_topk_packed(queries: torch.Tensor, corpus: torch.Tensor, k: int, id_offset: int = 0, chunks: int = 1):
+    """Local search written straight into the layout the ONE-exchange multi-GPU search sends: int32
+    [chunks, rows + 1, 2, k] with rows = ceil(Q / chunks); query q lives in chunk q // rows, row q % rows as
+    (k float32 score bits, k int32 ids); padding rows hold (-inf, -1); row `rows` of every chunk is the spare row whose
+    first word carries this rank's status flag (1 = some query's sampled threshold failed).  -> (pairs, status [Q])."""
+    dev = N.require_cuda(queries, corpus)
+    if queries.dtype != torch.bfloat16 or corpus.dtype != torch.bfloat16:
+        raise TypeError("queries and corpus must be bfloat16 (convert the fp32 index once with corpus_to_device)")
+    Q, D = queries.shape
+    Nn = corpus.shape[0]
+    rows = (Q + chunks - 1) // chunks
+    pairs = torch.empty((chunks, rows + 1, 2, k), dtype=torch.int32, device=dev)
+    pad = chunks * rows - Q
+    flat = pairs.view(chunks * (rows + 1), 2, k)
+    if pad:                                           # trailing padding rows of the last chunk(s): (-inf, -1)
+        for c in range(chunks):
+            lo = max(0, min(rows, Q - c * rows))
+            if lo < rows:
+                pairs[c, lo:rows, 0, :] = -8388608    # 0xFF800000 = float32 -inf
+                pairs[c, lo:rows, 1, :] = -1
+    status = torch.zeros((Q,), dtype=torch.int32, device=dev)
+    nbytes = N.lib().qf_dense_workspace_bytes(Q, Nn, k)
+    ws = torch.empty((max(nbytes, 16),), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        N.check(N.lib().qf_dense_topk_packed(N.ptr(queries), N.ptr(corpus), Q, Nn, D, k, id_offset, N.ptr(pairs), rows,
+                                             (rows + 1) * 2 * k, N.ptr(status), N.ptr(ws), nbytes, N.stream_ptr(dev)))
+    pairs[:, rows, 0, 0] = (status != 0).any().to(torch.int32)        # the rank's flag rides in every chunk's spare row
+    del flat
+    return pairs, status
+
+
+def topk_merge_packed(pairs: torch.Tensor, rows: int) -> torch.Tensor:
+    """pairs int32 [G, rows(+spare), 2, k] (as the all-to-all leaves them) -> merged int32 [rows, 2, k]."""
+    dev = N.require_cuda(pairs)
+    G, rr, two, k = pairs.shape
+    out = torch.empty((rows, 2, k), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        N.check(N.lib().qf_topk_merge_packed(N.ptr(pairs), G, rows, k, rr * 2 * k, N.ptr(out), N.stream_ptr(dev)))
+    return out
+
+
 def dense_scores(queries: torch.Tensor, corpus: torch.Tensor) -> torch.Tensor:
     """Full fp32 score rows [ceil128(Q), 64*ceil(N/64)] (tcgen05 kernel, STORE epilogue); for small Q."""
     dev = N.require_cuda(queries, corpus)

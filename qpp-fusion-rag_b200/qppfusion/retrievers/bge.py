@@ -133,6 +133,9 @@ class BGERetriever(BaseRetriever):
         if self.process_group is not None:
             from .. import distributed as qd
             scores, ids, status = qd.dense_search_sharded(query_embs, self.corpus, top_k, self.id_offset, self.process_group)
+            if int(status.max().item()) != 0:      # some shard's sampled threshold failed (flags are identical on all
+                scores, ids, status = qd.dense_search_sharded(query_embs, self.corpus, top_k, self.id_offset,   # ranks)
+                                                              self.process_group, exact=True)
         else:
             scores, ids, status = ops.dense_topk(query_embs, self.corpus, top_k, self.id_offset)
         if int(status.max().item()) != 0:      # cannot happen with the exact fallback enabled; never silently accept

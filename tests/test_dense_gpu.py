@@ -207,3 +207,63 @@ def test_dense_scores_matches_fp32_matmul():
     ref = qb.float() @ cb.float().T
     assert full.shape == (128, 1024)
     assert float((full[:Q, :N] - ref).abs().max()) <= TOL_SAME_INPUT
+
+
+def test_packed_one_exchange_layout_on_one_gpu():
+    """qf_dense_topk_packed + qf_topk_merge_packed (the ONE-exchange multi-GPU search, qppfusion/distributed.py) with the
+    all-to-all emulated by indexing: G corpus shards searched on one device, each shard's packed output [G, rows+1, 2, k]
+    'sent' chunk by chunk, every destination merges its query slice, the slices concatenated == the single search."""
+    from qppfusion import ops
+    rng = np.random.default_rng(31)
+    Q, N, D, k, G = 301, 30011, 768, 100, 4
+    dev = torch.device("cuda:0")
+    qb, cb = to_bf16(unit_rows(rng, Q, D)).to(dev), to_bf16(unit_rows(rng, N, D)).to(dev)
+    fs, fi, st = ops.dense_topk(qb, cb, k, 0)
+    per = (N + G - 1) // G
+    sends = []
+    for g in range(G):
+        lo = g * per
+        pairs, status = ops.dense_topk_packed(qb, cb[lo:lo + per].contiguous(), k, lo, chunks=G)
+        assert int(status.max()) == 0 and pairs.shape == (G, (Q + G - 1) // G + 1, 2, k)
+        assert int(pairs[:, -1, 0, 0].max()) == 0                  # the flag row
+        sends.append(pairs)
+    rows = sends[0].shape[1] - 1
+    merged = []
+    for dst in range(G):
+        recv = torch.stack([sends[src][dst] for src in range(G)]).contiguous()      # what rank dst receives
+        merged.append(ops.topk_merge_packed(recv, rows))
+    full = torch.cat(merged)[:Q]
+    assert torch.equal(full[:, 1, :], fi)
+    assert torch.equal(full[:, 0, :].contiguous().view(torch.float32), fs)
+
+
+def test_c3_size_same_input_parity_against_fp32_matmul():
+    """BASELINE configs[2] at FULL size (3 452 queries x 2 681 468 docs x 768, top-1000): 64 queries of the search
+    checked against an on-device fp32 matmul of the SAME bf16-rounded inputs + torch.topk.  Tolerance: fp32
+    accumulation order only (2e-5); ids may differ only where scores tie within it at the rank-k boundary."""
+    import bench
+    from qppfusion import ops
+    dev = torch.device("cuda:0")
+    q32, corpus = bench.synth_dense(bench.Q_NQ, bench.N_DENSE, bench.D_DENSE, 20250103, dev)
+    qb = q32.to(torch.bfloat16)
+    sc, ids, st = ops.dense_topk(qb, corpus, bench.K_DENSE, 0)
+    assert int(st.max()) == 0
+    k = bench.K_DENSE
+    pick = torch.arange(0, bench.Q_NQ, bench.Q_NQ // 64, device=dev)[:64]
+    ref = torch.empty((64, bench.N_DENSE), dtype=torch.float32, device=dev)
+    qf = qb[pick].float()
+    for s in range(0, bench.N_DENSE, 1 << 19):
+        ref[:, s:s + (1 << 19)] = qf @ corpus[s:s + (1 << 19)].float().T
+    rs, ri = torch.topk(ref, k, dim=1)
+    got_s, got_i = sc[pick], ids[pick].long()
+    assert float((got_s - rs).abs().max()) <= TOL_SAME_INPUT
+    assert bool((got_s[:, 1:] <= got_s[:, :-1]).all())
+    # every returned score is the true score of the returned id
+    assert float((torch.gather(ref, 1, got_i) - got_s).abs().max()) <= TOL_SAME_INPUT
+    same = 0
+    for j in range(64):
+        a, b = set(got_i[j].tolist()), set(ri[j].tolist())
+        same += len(a & b)
+        for d in a ^ b:                     # only boundary near-ties may differ
+            assert abs(float(ref[j, d]) - float(rs[j, k - 1])) <= 2 * TOL_SAME_INPUT
+    assert same / (64 * k) > 0.999

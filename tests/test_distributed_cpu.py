@@ -45,6 +45,27 @@ def _worker(rank, world, port, ret):
         q0 = rank * qs
         n_mine = max(0, min(qs, Q - q0))
         assert np.array_equal(mi2[:n_mine], fi[q0:q0 + n_mine]) and np.array_equal(ms2[:n_mine], fs[q0:q0 + n_mine])
+        # ---- packed ONE-exchange layout (dense_search_packed): [G, rows + 1, 2, k] int32, (score bits | ids) rows per
+        # destination rank, padding rows (-inf, -1), every rank's status flag in the spare row of each chunk
+        rows = (Q + world - 1) // world
+        send = np.empty((world, rows + 1, 2, k), dtype=np.int32)
+        send[:, :, 0, :] = np.float32(-np.inf).view(np.int32)
+        send[:, :, 1, :] = -1
+        for q in range(Q):
+            send[q // rows, q % rows, 0] = sc[q].view(np.int32)
+            send[q // rows, q % rows, 1] = ids[q].astype(np.int32)
+        send[:, rows, 0, 0] = rank + 10                              # "flag" of this rank
+        recv = torch.empty((world, rows + 1, 2, k), dtype=torch.int32)
+        dist.all_to_all_single(recv, torch.from_numpy(send))
+        recv = recv.numpy()
+        assert recv[:, rows, 0, 0].tolist() == [10 + g for g in range(world)]      # everyone sees every flag
+        ms3, mi3 = do.merge_topk(recv[:, :rows, 0, :].copy().view(np.float32), recv[:, :rows, 1, :].copy(), k)
+        assert np.array_equal(mi3[:n_mine], fi[q0:q0 + n_mine]) and np.array_equal(ms3[:n_mine], fs[q0:q0 + n_mine])
+        full = torch.empty((world * rows, 2, k), dtype=torch.int32)
+        mine = np.stack([ms3.view(np.int32), mi3.astype(np.int32)], axis=1)
+        dist.all_gather_into_tensor(full, torch.from_numpy(np.ascontiguousarray(mine)))
+        full = full.numpy()[:Q]
+        assert np.array_equal(full[:, 1, :], fi) and np.array_equal(full[:, 0, :].copy().view(np.float32), fs)
         # ---- QPP colnorm: query-sharded table, stats all-reduced, params as _normalize_qpp
         Qq, R, C = 53, 3, 13
         table = rng.normal(size=(Qq, R, C))
