@@ -260,6 +260,16 @@ QF_API int    qf_dense_row_topk(const float* scores, long long ld, const int32_t
                                 void* stream);
 
 /*
+ * float32 re-scoring of an over-fetched candidate list (closes the bf16-vs-fp32 gap to the reference's float32
+ * faiss.IndexFlatIP, src/retrievers/bge.py:188-194): out_scores[q][j] = <queries_f32[q], corpus_f32[cand_ids[q][j] -
+ * id_offset]> with float32 FMAs (fixed summation order), -inf for padding ids (< 0) or ids outside [id_offset,
+ * id_offset + N).  The host layer searches top (k + margin) in bf16, re-scores, and keeps the exact top k
+ * (qf_dense_row_topk over the re-scored rows).
+ */
+QF_API int    qf_dense_rescore_f32(const float* queries_f32, const float* corpus_f32, int Q, long long N, int D,
+                                   const int32_t* cand_ids, int kc, long long id_offset, float* out_scores, void* stream);
+
+/*
  * k-way merge after the all-gather of per-shard results (multi-GPU dense retrieval; precedent: the
  * reference's HNSW segment merge, src/retrievers/bge.py:216-237): scores/ids are [G][Q][k] as
  * ncclAllGather leaves them, ids global, -1 = padding.  Output [Q][k], (score desc, id asc).

@@ -73,6 +73,7 @@ PROTOTYPES = {
     "qf_dense_scores": (_i, [_vp, _vp, _i, _i, _i, _vp, ctypes.c_longlong, _vp]),
     "qf_dense_row_topk": (_i, [_vp, ctypes.c_longlong, _vp, _i, _i, _i, ctypes.c_longlong, _vp, _vp, _vp, _vp]),
     "qf_topk_merge": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
+    "qf_dense_rescore_f32": (_i, [_vp, _vp, _i, ctypes.c_longlong, _i, _vp, _i, ctypes.c_longlong, _vp, _vp]),
     "qf_dense_topk_packed": (_i, [_vp, _vp, _i, _i, _i, _i, ctypes.c_longlong, _vp, _i, ctypes.c_longlong, _vp, _vp, _sz, _vp]),
     "qf_topk_merge_packed": (_i, [_vp, _i, _i, _i, ctypes.c_longlong, _vp, _vp]),
     "qf_bert_weight_elems": (_sz, [_vp]),

@@ -214,6 +214,33 @@ def _(queries, corpus, k, id_offset):
             torch.empty((Q,), dtype=torch.int32, device=queries.device))
 
 
+def dense_rescore_topk(queries_f32: torch.Tensor, corpus_f32: torch.Tensor, cand_ids: torch.Tensor, k: int,
+                       id_offset: int = 0):
+    """float32 re-scoring of over-fetched candidates + exact top-k of the re-scored lists.
+    queries_f32 [Q, D], corpus_f32 [N, D] (this shard's rows), cand_ids int32 [Q, kc] (global ids, -1 padding)
+    -> (scores f32 [Q, k] desc, ids int32 [Q, k]); ties by candidate position (= the bf16 ranking)."""
+    dev = N.require_cuda(queries_f32, corpus_f32, cand_ids)
+    if queries_f32.dtype != torch.float32 or corpus_f32.dtype != torch.float32 or cand_ids.dtype != torch.int32:
+        raise TypeError("queries/corpus must be float32 and cand_ids int32")
+    Q, D = queries_f32.shape
+    kc = cand_ids.shape[1]
+    k = min(int(k), kc)
+    queries_f32, corpus_f32, cand_ids = queries_f32.contiguous(), corpus_f32.contiguous(), cand_ids.contiguous()
+    rs = torch.empty((Q, kc), dtype=torch.float32, device=dev)
+    out_s = torch.empty((Q, k), dtype=torch.float32, device=dev)
+    out_c = torch.empty((Q, k), dtype=torch.int32, device=dev)
+    status = torch.zeros((Q,), dtype=torch.int32, device=dev)
+    rows = torch.arange(Q, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        N.check(N.lib().qf_dense_rescore_f32(N.ptr(queries_f32), N.ptr(corpus_f32), Q, corpus_f32.shape[0], D,
+                                             N.ptr(cand_ids), kc, id_offset, N.ptr(rs), N.stream_ptr(dev)))
+        N.check(N.lib().qf_dense_row_topk(N.ptr(rs), kc, N.ptr(rows), Q, kc, k, 0, N.ptr(out_s), N.ptr(out_c),
+                                          N.ptr(status), N.stream_ptr(dev)))
+    ids = torch.gather(cand_ids, 1, out_c.clamp(min=0).long())
+    ids = torch.where((out_c >= 0) & torch.isfinite(out_s), ids, torch.full_like(ids, -1))
+    return out_s, ids
+
+
 def dense_topk_packed(queries: torch.Tensor, corpus: torch.Tensor, k: int, id_offset: int = 0, chunks: int = 1):
     """Local search written straight into the layout the ONE-exchange multi-GPU search sends: int32
     [chunks, rows + 1, 2, k] with rows = ceil(Q / chunks); query q lives in chunk q // rows, row q % rows as

@@ -63,7 +63,8 @@ class BGERetriever(BaseRetriever):
                  use_mps: bool = True, ef_search: Optional[int] = None, *,
                  corpus_embeddings=None, docids: Optional[Sequence[str]] = None,
                  index_dir: Optional[str] = None, encoder: Optional[Callable[[List[str]], np.ndarray]] = None,
-                 model_dir: Optional[str] = None, id_offset: int = 0, process_group=None, **kwargs):
+                 model_dir: Optional[str] = None, id_offset: int = 0, process_group=None,
+                 rescore_fp32: int = 0, **kwargs):
         """
         index_name / dataset / encoder_batch_size / use_mps / ef_search: reference signature
         (src/retrievers/bge.py:41-85); use_mps and ef_search have no meaning here.
@@ -72,6 +73,11 @@ class BGERetriever(BaseRetriever):
         index_dir: a Pyserini flat index directory holding `index` (FAISS IndexFlat) and `docid`.
         encoder / model_dir: the query encoder (see the module docstring); model_dir is used when encoder is None.
         id_offset / process_group: row offset of this rank's shard and the NCCL group to merge over.
+        rescore_fp32: margin m > 0 keeps a float32 copy of the corpus rows in HBM (4 bytes x N x 768) and re-scores
+                      the bf16 top (k + m) candidates in float32 (qf_dense_rescore_f32), so the returned scores are
+                      float32 inner products of the float32 inputs -- what the reference's faiss.IndexFlatIP computes --
+                      and bf16 rounding can no longer change membership or order unless a true top-k document falls
+                      outside the bf16 top (k + m).  k + m is capped at qf_dense_max_k() = 1024.  Single-GPU only.
         """
         self.model_name = config.models.bge.name
         self.embedding_dim = config.models.bge.embedding_dim
@@ -96,6 +102,17 @@ class BGERetriever(BaseRetriever):
             raise FileNotFoundError("No index found: pass corpus_embeddings=/docids= or index_dir= "
                                     "(Pyserini flat index directory)")
         self.corpus = self.corpus_to_device(corpus_embeddings)
+        self.rescore_margin = int(rescore_fp32)
+        self.corpus_f32 = None
+        if self.rescore_margin > 0:
+            if process_group is not None:
+                raise ValueError("rescore_fp32 is not offered for the sharded search")
+            if isinstance(corpus_embeddings, torch.Tensor):
+                if corpus_embeddings.dtype != torch.float32:
+                    raise TypeError("rescore_fp32 needs the float32 corpus embeddings")
+                self.corpus_f32 = corpus_embeddings.to(self.device).contiguous()
+            else:
+                self.corpus_f32 = torch.from_numpy(np.ascontiguousarray(corpus_embeddings, dtype=np.float32)).to(self.device)
         if self.encoder is None and model_dir is not None:
             from ..encoder import BertQueryEncoder
             self.encoder = BertQueryEncoder.from_pretrained(model_dir, device=self.device)
@@ -150,7 +167,14 @@ class BGERetriever(BaseRetriever):
             q = query_embs.to(self.device).to(torch.bfloat16).contiguous()
         else:
             q = torch.from_numpy(np.ascontiguousarray(query_embs, dtype=np.float32)).to(self.device).to(torch.bfloat16)
-        scores, ids = self._search_device(q, int(top_k))
+        if self.corpus_f32 is not None:
+            q32 = (query_embs.to(self.device).float() if isinstance(query_embs, torch.Tensor)
+                   else torch.from_numpy(np.ascontiguousarray(query_embs, dtype=np.float32)).to(self.device))
+            k2 = min(int(N.lib().qf_dense_max_k()), int(top_k) + self.rescore_margin)
+            _s, cand = self._search_device(q, k2)
+            scores, ids = ops.dense_rescore_topk(q32.contiguous(), self.corpus_f32, cand, int(top_k), self.id_offset)
+        else:
+            scores, ids = self._search_device(q, int(top_k))
         return ids.cpu().numpy().astype(np.int64), scores.cpu().numpy()
 
     _search_faiss_batch = _search_batch

@@ -267,3 +267,28 @@ def test_c3_size_same_input_parity_against_fp32_matmul():
         for d in a ^ b:                     # only boundary near-ties may differ
             assert abs(float(ref[j, d]) - float(rs[j, k - 1])) <= 2 * TOL_SAME_INPUT
     assert same / (64 * k) > 0.999
+
+
+def test_fp32_rescoring_closes_the_bf16_gap_to_the_fp32_oracle():
+    """BGERetriever(rescore_fp32=m): bf16 top (k + m) re-scored against the float32 corpus (qf_dense_rescore_f32) vs
+    the float32 flat-IP oracle (= what the reference's faiss.IndexFlatIP computes).  Reports and gates recall@k and the
+    largest score error, with and without re-scoring."""
+    from qppfusion.retrievers.bge import BGERetriever
+    rng = np.random.default_rng(41)
+    Q, N, D, k = 96, 60000, 768, 100
+    qf32, cf32 = unit_rows(rng, Q, D), unit_rows(rng, N, D)
+    oi, os_ = do.flat_ip_topk(qf32, cf32, k)
+
+    def run(margin):
+        r = BGERetriever(corpus_embeddings=cf32, docids=None, rescore_fp32=margin)
+        ids, sc = r._search_batch(qf32, k)
+        recall = np.mean([len(set(a.tolist()) & set(b.tolist())) / k for a, b in zip(ids, oi)])
+        same_order = np.mean(ids == oi)
+        return recall, same_order, float(np.abs(sc - os_).max())
+
+    r0, o0, e0 = run(0)
+    r1, o1, e1 = run(128)
+    print(f"bf16 only: recall@{k} {r0:.5f}, identical positions {o0:.4f}, max |score diff| {e0:.2e}; "
+          f"fp32 re-scored (margin 128): recall {r1:.5f}, identical positions {o1:.4f}, max |score diff| {e1:.2e}")
+    assert r0 > 0.97 and e0 <= TOL_BF16
+    assert r1 == 1.0 and e1 <= 2e-6 and o1 > 0.999           # fp32 summation order only
