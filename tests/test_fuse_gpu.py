@@ -369,3 +369,30 @@ def test_duplicate_doc_ids_in_the_first_list(k, groups):
     for method in ("sum", "mnz"):
         out = run_gpu(lists, method, w, k=k)
         check_against_oracle(lists, method, w, out)
+
+
+def test_repeated_launches_are_bitwise_identical():
+    """The join claims table keys with racy-by-design shared-memory CAS (stale volatile views, lost claims re-queued):
+    the ARRIVAL order of postings differs from launch to launch, the result must not.  40 launches of the same
+    NQ-shaped batch (1 024 queries x 5 x top-1000, ~44 % union, ties included) through the current kernel path must
+    reproduce the first launch bit for bit (compute-sanitizer is closed on this pool; this is the stand-in for a
+    racecheck run: a hazard that matters shows up as run-to-run differences)."""
+    from qppfusion import ops
+    import bench
+    dev = torch.device("cuda:0")
+    ids, micro, lens, _f = bench.synth_device(1024, 5, 1000, 77, dev)
+    micro = (micro // 1000) * 1000                                      # 3-decimal scores: many exact ties
+    w = (torch.rand((1024, 5), generator=torch.Generator().manual_seed(3), dtype=torch.float64) * 1e6).round() / 1e6
+    w = w.to(dev)
+    for method in (0, 1):
+        first = None
+        for it in range(40):
+            out = ops.fuse(ids, micro, lens, w, None, method, 0, 60.0, EXTRA_FLAGS[0])
+            cur = [out.ids.clone(), out.scores.clone().view(torch.int64), out.counts.clone(), out.pos.clone(), out.lens.clone()]
+            n = out.lens.long()
+            m = torch.arange(out.ids.shape[1], device=dev)[None, :] < n[:, None]
+            cur = [c[m] if c.dim() == 2 else c for c in cur]
+            if first is None:
+                first = cur
+            else:
+                assert all(torch.equal(a, b) for a, b in zip(first, cur)), f"launch {it} differs (method {method})"
