@@ -45,7 +45,8 @@ constexpr int EPI_THREADS = 256;        // 2 threads per query row (32 accumulat
 
 constexpr int MODE_FILTER = 0;
 constexpr int MODE_STORE = 1;
-constexpr int MODE_TILEMAX = 2;   // store only max over each thread's 32 columns: store[row][vtile*2 + half]
+constexpr int MODE_TILEMAX = 2;   // store only maxima over groups of each thread's 32 columns:
+                                  // store[row][(vtile*2 + half) * tm_parts + part]
 
 struct DenseParams {
   const __nv_bfloat16* queries;   // [Q, D]
@@ -55,6 +56,7 @@ struct DenseParams {
   int tile_step;                  // real tile = vtile * tile_step (1 = whole corpus, >1 = strided sample)
   int chunk_tiles;                // vtiles per work unit
   int mode;
+  int tm_parts;                   // TILEMAX: maxima stored per epilogue thread and tile (1, 2 or 4 groups of 32 / 16 / 8 docs)
   const float* tau;               // [Q]            (FILTER)
   // FILTER output: every epilogue thread owns a private segment per work unit, so survivors are written with
   // plain stores (no atomics, no round trips): segment s = q*n_segs + chunk*2 + half holds seg_cnt[s]
@@ -443,10 +445,25 @@ __global__ void __launch_bounds__(NT, 1) dense_kernel(const __grid_constant__ CU
           }
         } else if (p.mode == MODE_TILEMAX) {
           const int nvalid = p.N - doc0;
-          float mx = -INFINITY;
+          float mq[4];                                    // maxima over the four groups of 8 columns
 #pragma unroll
-          for (int j = 0; j < 32; ++j) mx = (j < nvalid) ? fmaxf(mx, __uint_as_float(v[j])) : mx;
-          if (m < p.n_mtiles) p.store[(size_t)(m * BM + row) * p.store_ld + (size_t)t * 2 + half] = mx;
+          for (int g = 0; g < 4; ++g) {
+            float mx = -INFINITY;
+#pragma unroll
+            for (int j = 8 * g; j < 8 * g + 8; ++j) mx = (j < nvalid) ? fmaxf(mx, __uint_as_float(v[j])) : mx;
+            mq[g] = mx;
+          }
+          if (m < p.n_mtiles) {
+            float* dst = p.store + (size_t)(m * BM + row) * p.store_ld + ((size_t)t * 2 + half) * p.tm_parts;
+            if (p.tm_parts == 1) {
+              dst[0] = fmaxf(fmaxf(mq[0], mq[1]), fmaxf(mq[2], mq[3]));
+            } else if (p.tm_parts == 2) {
+              dst[0] = fmaxf(mq[0], mq[1]);
+              dst[1] = fmaxf(mq[2], mq[3]);
+            } else {
+              dst[0] = mq[0]; dst[1] = mq[1]; dst[2] = mq[2]; dst[3] = mq[3];
+            }
+          }
         } else if (m < p.n_mtiles) {
           float4* dst = reinterpret_cast<float4*>(p.store + (size_t)(m * BM + row) * p.store_ld + (size_t)t * BN + half * 32);
 #pragma unroll
@@ -612,9 +629,9 @@ __device__ __forceinline__ void bitonic1024_desc(float* v, int tid) {
   }
 }
 
-// tau[q] = the jj-th largest of the per-(sample tile, column half) maxima written by MODE_TILEMAX: a lower bound
-// of the jj-th largest sample score (equal unless two of the top jj fall into the same 32-document bucket), so
-// the threshold errs towards admitting a few more candidates.  n_vals = 2 * n_sample_tiles <= 1024.
+// tau[q] = the jj-th largest of the per-(sample tile, column group) maxima written by MODE_TILEMAX: a lower bound
+// of the jj-th largest sample score (equal unless two of the top jj fall into the same 32 / 16 / 8-document group), so
+// the threshold errs towards admitting a few more candidates.  n_vals = 2 * tm_parts * n_sample_tiles <= 1024.
 __global__ void __launch_bounds__(512) tau_kernel_tilemax(const float* vals, long long ld, int n_vals, int jj, int Q, float* tau) {
   __shared__ float buf[1024];
   const int q = blockIdx.x, tid = threadIdx.x;
@@ -1525,9 +1542,17 @@ static int dense_topk_impl(const void* queries_bf16, const void* corpus_bf16, in
     long long jj = ((long long)target * s_valid + N - 1) / N;
     if (jj < 1) jj = 1;
     if (jj > s_valid) jj = s_valid;
-    const bool tilemax = jj <= 64 && p.n_vtiles * 2 <= 1024 && p.n_vtiles * 2 >= 4 * jj;
+    // groups of 32 documents (one maximum per epilogue thread and tile) when the sample is large; small corpora --
+    // e.g. one of 8 shards of the NQ corpus, 335 k rows -- get 16- or 8-document groups so that the cheap estimator
+    // still has >= 4 jj values to choose from (round 1 fell back to the exact select over stored scores there: the
+    // "tau" phase took 0.18 ms instead of 0.07 ms at N = 8)
+    int parts = 1;
+    while (parts < 4 && (long long)p.n_vtiles * 2 * parts < 4 * jj) parts *= 2;
+    const long long n_vals = (long long)p.n_vtiles * 2 * parts;
+    const bool tilemax = jj <= 64 && n_vals <= 1024 && n_vals >= 4 * jj;
     p.mode = tilemax ? MODE_TILEMAX : MODE_STORE;
-    if (tilemax) p.store_ld = (long long)p.n_vtiles * 2;
+    p.tm_parts = parts;
+    if (tilemax) p.store_ld = n_vals;
     const int units = ((p.n_vtiles + p.chunk_tiles - 1) / p.chunk_tiles) * n_mtiles;
     qf::prof_mark(QF_PROF_DENSE_SAMPLE, 0, st);
     rc = launch_dense(maps, p, st);
@@ -1537,7 +1562,7 @@ static int dense_topk_impl(const void* queries_bf16, const void* corpus_bf16, in
     const bool small_j = ((long long)target * s_cols + N - 1) / N <= 128;
     qf::prof_mark(QF_PROF_DENSE_TAU, 0, st);
     if (tilemax) {
-      tau_kernel_tilemax<<<Q, 512, 0, st>>>(p.store, p.store_ld, p.n_vtiles * 2, (int)jj, Q, tau);
+      tau_kernel_tilemax<<<Q, 512, 0, st>>>(p.store, p.store_ld, (int)n_vals, (int)jj, Q, tau);
     } else {
       if (small_j) tau_kernel_small<<<Q, 512, 0, st>>>(p.store, p.store_ld, p.n_vtiles, p.tile_step, N, Q, target, tau);
       tau_kernel<<<Q, 512, 0, st>>>(p.store, p.store_ld, p.n_vtiles, p.tile_step, N, Q, target, tau, small_j ? 1 : 0);

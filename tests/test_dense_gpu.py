@@ -94,6 +94,14 @@ def test_sampled_threshold_path_large_corpus():
     assert overlap >= 0.95
 
 
+def test_sampled_threshold_path_shard_sized_corpus():
+    """335 k rows = one of 8 shards of the NQ corpus: the tile-max threshold estimator runs on 16-document groups."""
+    overlap, _ = check(Q=130, N=335_184, D=768, k=1000, seed=8)
+    assert overlap >= 0.95
+    overlap, _ = check(Q=40, N=150_000, D=768, k=1000, seed=9)           # 8-document groups
+    assert overlap >= 0.95
+
+
 def test_smaller_embedding_dim():
     check(Q=33, N=5000, D=256, k=50, seed=6)
 

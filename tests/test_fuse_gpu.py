@@ -388,7 +388,7 @@ def test_repeated_launches_are_bitwise_identical():
         first = None
         for it in range(40):
             out = ops.fuse(ids, micro, lens, w, None, method, 0, 60.0, EXTRA_FLAGS[0])
-            cur = [out.ids.clone(), out.scores.clone().view(torch.int64), out.counts.clone(), out.pos.clone(), out.lens.clone()]
+            cur = [out.ids.clone(), out.scores.clone().view(torch.int64), out.counts.to(torch.int32), out.pos.to(torch.int32), out.lens.clone()]
             n = out.lens.long()
             m = torch.arange(out.ids.shape[1], device=dev)[None, :] < n[:, None]
             cur = [c[m] if c.dim() == 2 else c for c in cur]
