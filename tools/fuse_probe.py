@@ -19,7 +19,7 @@ sets = [bench.synth_device(Q, 5, 1000, 20250103 + 1000 * i, dev) for i in range(
 g = torch.Generator(device=dev)
 g.manual_seed(5)
 w = (torch.rand((Q, 5), generator=g, device=dev, dtype=torch.float64) * 1e6).round() / 1e6
-flags = 0x200 if "general" in sys.argv else 0
+flags = (0x200 if "general" in sys.argv else 0) | int(os.environ.get("PROBE_FLAGS", "0"), 0)
 method = int(os.environ.get("PROBE_METHOD", "0"))
 
 
