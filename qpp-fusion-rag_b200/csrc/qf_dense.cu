@@ -165,7 +165,9 @@ struct Idesc {
   static constexpr u32 value = (1u << 4) | (1u << 7) | (1u << 10) | ((u32)(BN >> 3) << 17) | ((u32)((BM * CG) >> 4) << 24);
 };
 
-constexpr int SEG_T = 48;                 // private candidate segment per (work unit, epilogue thread)
+constexpr int SEG_T = 96;                 // private candidate segment per (work unit, epilogue thread); round 2: 48 -> 96,
+                                          // i.e. twice as long work units on shard-sized corpora (the query tile is
+                                          // reloaded into tensor memory once per unit: 31-tile units cost 8 % at 335 k rows)
 constexpr int MAX_SLOTS = 24;
 constexpr u32 PEER_BIT_MASK = 0xFEFFFFFFu;   // clears the CTA-pair peer bit of a shared::cluster address -> CTA rank 0
 
@@ -1423,8 +1425,8 @@ struct DenseWs {
   long long sample_ld;
 };
 
-// main-pass chunking: with a sampled threshold a thread sees ~12 survivors per 256-tile unit (SEG_T = 48 leaves
-// 4x head-room; overflow is flagged and repaired exactly); without a threshold (tiny corpora, tau = -inf) every
+// main-pass chunking: with a sampled threshold a thread sees ~12 survivors per 256-tile unit (units are sized for
+// SEG_T / 4 expected survivors, i.e. 4x head-room; overflow is flagged and repaired exactly); without a threshold (tiny corpora, tau = -inf) every
 // document survives, so units are single tiles (32 documents per epilogue thread <= SEG_T).
 int cand_target(int k) { return 3 * k + 1000; }   // candidates the sampled threshold aims to admit per query
 
