@@ -741,7 +741,7 @@ def run_ours(args):
 
     Q, R, K = Q_NQ, R_NQ, K_NQ
     NSETS = 4     # rotating input sets: 138 MB each, so no step finds its inputs in the 126 MB L2
-    INFLIGHT = 2 if world == 1 else 4  # steps in flight (one stream each; NSETS % INFLIGHT == 0 keeps a graph on one stream);
+    INFLIGHT = int(os.environ.get("BENCH_INFLIGHT", "0")) or 4  # steps in flight (2 -> 4 in round 2: +1.5 % at N = 1) (one stream each; NSETS % INFLIGHT == 0 keeps a graph on one stream);
     # at N > 1 more steps in flight cover the all-reduce of the cross-query min/max (it waits for the slowest rank)
     sets = [synth_device(Q, R, K, 20250101 + 2 + 17 * rank + 1000 * i, dev) for i in range(NSETS)]
     stream = torch.cuda.current_stream(dev)
