@@ -275,8 +275,9 @@ def dense_leg(args, dev, world, rank, Q=Q_NQ, n_docs=None, label="BASELINE confi
     from qppfusion import distributed as qd
 
     def step():
-        if world > 1:        # local top-k -> all-to-all -> merge Q/G queries per rank -> all-gather
-            return qd.dense_search_sharded(qb, corpus, k, lo)
+        if world > 1:        # local top-k_in -> ONE all-to-all -> merge Q/G queries per rank -> ONE all-gather
+            res = qd.dense_search_packed(qb, corpus, k, lo, gather=True)
+            return res, res.pairs, res.flags
         return ops.dense_topk(qb, corpus, k, lo)
 
     def barrier():
@@ -290,6 +291,8 @@ def dense_leg(args, dev, world, rank, Q=Q_NQ, n_docs=None, label="BASELINE confi
     barrier()
     N_.profile_enable(True)          # averages the in-library event pairs of the calls from here on
     status_bad = int((st != 0).sum().item())
+    if world > 1:
+        status_bad += int((sc.incomplete != 0).sum().item())      # the truncated exchange flagged a possibly lost document
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler = ClockSampler(dev.index)
     if rank == 0:
@@ -312,7 +315,7 @@ def dense_leg(args, dev, world, rank, Q=Q_NQ, n_docs=None, label="BASELINE confi
     h_i = torch.empty((Q, k), dtype=torch.int32).pin_memory()
 
     rows_slice = (Q + world - 1) // world
-    h_pairs = torch.empty((rows_slice, 2, k), dtype=torch.int32).pin_memory()
+    h_pairs = torch.empty((rows_slice + 1, 2, k), dtype=torch.int32).pin_memory()
     h_flags = torch.empty((world,), dtype=torch.int32).pin_memory()
 
     def e2e_step():
@@ -321,7 +324,7 @@ def dense_leg(args, dev, world, rank, Q=Q_NQ, n_docs=None, label="BASELINE confi
             # one exchange, and every rank downloads only ITS merged query slice (+ the G status flags): Q*k*8 bytes
             # leave the GPUs in total instead of G times that
             res = qd.dense_search_packed(dq, corpus, k, lo, gather=False)
-            h_pairs.copy_(res.pairs, non_blocking=True)
+            h_pairs.copy_(res.pairs, non_blocking=True)                # merged slice + its spare row (truncation flag)
             h_flags.copy_(res.flags, non_blocking=True)
         else:
             s_, i_, _ = ops.dense_topk(dq, corpus, k, lo)
@@ -338,6 +341,7 @@ def dense_leg(args, dev, world, rank, Q=Q_NQ, n_docs=None, label="BASELINE confi
     e2e_ms = e0.elapsed_time(e1) / steps
     if world > 1:
         assert int(h_flags.max()) == 0, "a shard's sampled threshold failed during the e2e steps"
+        assert int(h_pairs[rows_slice, 0, 0]) == 0, "the truncated exchange flagged a possibly lost document"
 
     # parity spot check on the device copy (torch fp32 matmul as an independent reference; world == 1 only)
     parity = None
@@ -367,7 +371,8 @@ def dense_leg(args, dev, world, rank, Q=Q_NQ, n_docs=None, label="BASELINE confi
             "scaling": "strong" if world > 1 else "n/a",
             "config": {"workload": f"BGE-base-shaped flat IP top-1000 ({label})", "queries": Q,
                        "docs": N_DENSE, "docs_per_gpu": n_local, "dim": D, "k": k, "dtype": "bf16 in, fp32 accumulate",
-                       "sharding": f"corpus rows x{world}" + (", packed (score,id) rows: ONE all_to_all + qf_topk_merge_packed(Q/G) "
+                       "sharding": f"corpus rows x{world}" + (f", packed (score,id) rows truncated to the shard's top {qd.send_depth(k, world)}"
+                                                              ": ONE all_to_all + qf_topk_merge_packed(Q/G) + completeness check "
                                                               "+ ONE all_gather, no host sync" if world > 1 else "")},
             "kernel_ms": phases,
             "roofline": {"kernel": "dense_kernel (tcgen05 main pass)", "bound": "tensor", "achieved": ach, "peak": tf_peak,

@@ -121,7 +121,9 @@ QF_API int qf_profile_read(int phase, float* ms);
  *                                     unsorted return value)
  *   out_status[q]    (nullable)     : QF_QSTAT_* bits
  *
- * Envelope: R*K <= qf_fuse_max_postings() (shared-memory resident per query), R <= 32.
+ * Envelope: R*K <= qf_fuse_max_postings() = 6144 postings per query (shared-memory resident; 5120 for
+ * QF_SCORE_F64), R <= 32.  Up to 5120 the streaming kernel runs; 5121..6144 (e.g. 6 runs x depth 1000) take the
+ * general kernel alone (about 3x slower per query).
  */
 QF_API int qf_fuse_max_postings(void);
 QF_API int qf_fuse(const int32_t* doc_ids, const void* scores, int score_type, const int32_t* ranks,
@@ -287,13 +289,21 @@ QF_API int    qf_topk_merge(const float* scores, const int32_t* ids, int G, int 
  *                          (chunk_rows = 0: plain [Q][2][k]).  chunk_rows = ceil(Q / G) with chunk_stride =
  *                          (chunk_rows + 1) * 2k leaves one spare row per destination rank, which the host layer
  *                          uses to ship the rank's status flag inside the same all-to-all.
- *   qf_topk_merge_packed : segment g, query j read at in_pairs + g * seg_stride + j * 2k; output [Q][2][k].
+ *   qf_topk_merge_packed : segment g, query j read at in_pairs + g * seg_stride + j * 2 k_in (k_in entries per shard
+ *                          list); output [Q][2][k_out].  k_in < k_out is the TRUNCATED exchange: with G shards a
+ *                          shard holds about k_out / G of the global top k_out, so it sends only its top
+ *                          k_in ~ 2 k_out / G + 64 (4x fewer bytes and a cheaper local search at G = 8).
+ *   qf_topk_merge_check  : sets *flag (device int32) when that truncation may have lost a document: some shard's
+ *                          list is full and its last score reaches the merged k_out-th score.  The host layer then
+ *                          repeats the search with full-length lists (exactness is never traded).
  */
 QF_API int    qf_dense_topk_packed(const void* queries_bf16, const void* corpus_bf16, int Q, int N, int D, int k,
                                    long long id_offset, int32_t* out_pairs, int chunk_rows, long long chunk_stride,
                                    int32_t* out_status, void* ws, size_t ws_bytes, void* stream);
-QF_API int    qf_topk_merge_packed(const int32_t* in_pairs, int G, int Q, int k, long long seg_stride,
+QF_API int    qf_topk_merge_packed(const int32_t* in_pairs, int G, int Q, int k_in, long long seg_stride, int k_out,
                                    int32_t* out_pairs, void* stream);
+QF_API int    qf_topk_merge_check(const int32_t* in_pairs, int G, int Q, int k_in, long long seg_stride,
+                                  const int32_t* merged_pairs, int k_out, int32_t* flag, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Query encoder  --  replaces SentenceTransformer(model).encode(queries, normalize_embeddings=True) behind

@@ -1680,25 +1680,59 @@ extern "C" int qf_dense_topk_packed(const void* queries_bf16, const void* corpus
 }
 
 static int topk_merge_impl(const float* scores, const int32_t* ids, int G, int Q, int k, long long q_stride,
-                           long long seg_stride, float* out_scores, int32_t* out_ids, long long out_stride, void* stream);
+                           long long seg_stride, float* out_scores, int32_t* out_ids, long long out_stride, int k_out,
+                           void* stream);
 
 extern "C" int qf_topk_merge(const float* scores, const int32_t* ids, int G, int Q, int k, float* out_scores,
                              int32_t* out_ids, void* stream) {
-  return topk_merge_impl(scores, ids, G, Q, k, k, (long long)Q * k, out_scores, out_ids, k, stream);
+  return topk_merge_impl(scores, ids, G, Q, k, k, (long long)Q * k, out_scores, out_ids, k, k, stream);
 }
 
-extern "C" int qf_topk_merge_packed(const int32_t* in_pairs, int G, int Q, int k, long long seg_stride,
+extern "C" int qf_topk_merge_packed(const int32_t* in_pairs, int G, int Q, int k_in, long long seg_stride, int k_out,
                                     int32_t* out_pairs, void* stream) {
-  QF_REQUIRE(in_pairs != nullptr && out_pairs != nullptr && seg_stride >= 2LL * k * Q, QF_E_INVALID,
-             "qf_topk_merge_packed: bad argument (seg_stride=%lld)", seg_stride);
-  return topk_merge_impl(reinterpret_cast<const float*>(in_pairs), in_pairs + k, G, Q, k, 2LL * k, seg_stride,
-                         reinterpret_cast<float*>(out_pairs), out_pairs + k, 2LL * k, stream);
+  QF_REQUIRE(in_pairs != nullptr && out_pairs != nullptr && seg_stride >= 2LL * k_in * Q && k_out >= 1, QF_E_INVALID,
+             "qf_topk_merge_packed: bad argument (seg_stride=%lld k_out=%d)", seg_stride, k_out);
+  return topk_merge_impl(reinterpret_cast<const float*>(in_pairs), in_pairs + k_in, G, Q, k_in, 2LL * k_in, seg_stride,
+                         reinterpret_cast<float*>(out_pairs), out_pairs + k_out, 2LL * k_out, k_out, stream);
+}
+
+// Completeness check of a merge over TRUNCATED shard lists (k_in < k_out entries per shard): the merged top k_out is
+// exact unless some shard's list is full and its last score reaches the merged k_out-th score (that shard may hold
+// further documents at or above it), or the merged list itself is not full while a shard's list is.
+__global__ void merge_check_kernel(const int32_t* in_pairs, int G, int Q, int k_in, long long seg_stride,
+                                   const int32_t* merged, int k_out, int32_t* flag) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)G * Q) return;
+  const int g = (int)(i / Q), q = (int)(i % Q);
+  const int32_t* row = in_pairs + (size_t)g * seg_stride + (size_t)q * 2 * k_in;
+  const int last_id = row[k_in + k_in - 1];
+  if (last_id < 0) return;                                   // the shard sent everything it has for this query
+  const float last = __int_as_float(row[k_in - 1]);
+  const int32_t* mr = merged + (size_t)q * 2 * k_out;
+  const bool full = mr[k_out + k_out - 1] >= 0;
+  if (!full || last >= __int_as_float(mr[k_out - 1])) atomicOr(flag, 1);
+}
+
+extern "C" int qf_topk_merge_check(const int32_t* in_pairs, int G, int Q, int k_in, long long seg_stride,
+                                   const int32_t* merged_pairs, int k_out, int32_t* flag, void* stream) {
+  QF_REQUIRE(in_pairs && merged_pairs && flag && G >= 1 && Q >= 0 && k_in >= 1 && k_out >= 1, QF_E_INVALID,
+             "qf_topk_merge_check: bad argument");
+  if (Q == 0) return QF_OK;
+  int rc = qf::check_device();
+  if (rc != QF_OK) return rc;
+  const long long n = (long long)G * Q;
+  merge_check_kernel<<<(unsigned)((n + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      in_pairs, G, Q, k_in, seg_stride, merged_pairs, k_out, flag);
+  QF_CUDA_TRY(cudaGetLastError());
+  return QF_OK;
 }
 
 static int topk_merge_impl(const float* scores, const int32_t* ids, int G, int Q, int k, long long q_stride,
-                           long long seg_stride, float* out_scores, int32_t* out_ids, long long out_stride, void* stream) {
+                           long long seg_stride, float* out_scores, int32_t* out_ids, long long out_stride, int k_out,
+                           void* stream) {
   QF_REQUIRE(G >= 1 && Q >= 0 && k >= 1, QF_E_INVALID, "qf_topk_merge: bad sizes G=%d Q=%d k=%d", G, Q, k);
   QF_REQUIRE((long long)G * k <= SEL_CAP, QF_E_UNSUPPORTED, "qf_topk_merge: G*k=%lld exceeds %d", (long long)G * k, SEL_CAP);
+  QF_REQUIRE(k_out <= qf_dense_max_k(), QF_E_UNSUPPORTED, "qf_topk_merge: k_out=%d exceeds %d", k_out, qf_dense_max_k());
   if (Q == 0) return QF_OK;
   QF_REQUIRE(scores && ids && out_scores && out_ids, QF_E_INVALID, "qf_topk_merge: null pointer argument");
   int rc = qf::check_device();
@@ -1715,7 +1749,7 @@ static int topk_merge_impl(const float* scores, const int32_t* ids, int G, int Q
   SelectParams sp{};
   sp.seg_pairs = nullptr; sp.seg_cnt = nullptr; sp.cand_score = scores; sp.cand_id = ids;
   sp.q_stride = q_stride; sp.seg_stride = seg_stride; sp.nseg = G; sp.seg_len = k;
-  sp.Q = Q; sp.k = k; sp.N_total = 0x7fffffff; sp.id_offset = 0;
+  sp.Q = Q; sp.k = k_out; sp.N_total = 0x7fffffff; sp.id_offset = 0;
   sp.out_scores = out_scores; sp.out_ids = out_ids; sp.out_status = nullptr;
   sp.out_stride = out_stride; sp.chunk_rows = 0; sp.chunk_stride = 0;
   const int sms = qf::sm_count();

@@ -609,16 +609,28 @@ int launch(const FuseParams& p, cudaStream_t stream) {
   return QF_OK;
 }
 
+// 6 144 postings per query (e.g. 6 retrievers x TREC depth 1000) fit the 227 KB of shared memory only with 4-byte
+// scores (micro-units / float32): the float64 instantiation stops at 5 120.
+constexpr int CAP_WIDE = 6144;
+static_assert(Layout<CAP_WIDE, 13, QF_FUSE_NT, QF_SCORE_MICRO>::total <= 232448, "wide general kernel must fit in shared memory");
+
 template <int ST>
 int dispatch_cap(const FuseParams& p, cudaStream_t stream) {
   const long long n_max = (long long)p.R * p.K;
   if (n_max <= 1024) return launch<1024, 11, 128, ST>(p, stream);
-  return launch<5120, 13, QF_FUSE_NT, ST>(p, stream);
+  if (n_max <= 5120) return launch<5120, 13, QF_FUSE_NT, ST>(p, stream);
+  if constexpr (ST == QF_SCORE_F64) {
+    qf::set_error("qf_fuse: R*K=%lld exceeds 5120 postings per query for float64 scores (6144 with QF_SCORE_MICRO / "
+                  "QF_SCORE_F32)", n_max);
+    return QF_E_UNSUPPORTED;
+  } else {
+    return launch<CAP_WIDE, 13, QF_FUSE_NT, ST>(p, stream);
+  }
 }
 
 }  // namespace
 
-extern "C" int qf_fuse_max_postings(void) { return 5120; }
+extern "C" int qf_fuse_max_postings(void) { return CAP_WIDE; }
 
 extern "C" int qf_fuse(const int32_t* doc_ids, const void* scores, int score_type, const int32_t* ranks,
                        const int32_t* lens, const double* weights, int Q, int R, int K, int method, int norm,

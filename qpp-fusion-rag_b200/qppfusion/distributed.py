@@ -91,36 +91,59 @@ def exchange_topk(scores: torch.Tensor, ids: torch.Tensor, group=None):
     return rs.view(world, qs, k), ri.view(world, qs, k), qs
 
 
+def send_depth(k: int, world: int) -> int:
+    """Entries per shard list in the TRUNCATED exchange: a shard holds about k / G of the global top k (rows are
+    sharded contiguously, documents are not sorted by topic), so twice that plus 64 is sent; the merge checks that
+    nothing was lost (qf_topk_merge_check) and the search is repeated with full lists otherwise."""
+    kk = 2 * ((k + world - 1) // world) + 64
+    kk = (kk + 15) // 16 * 16
+    return min(k, kk)
+
+
 class ShardedSearchResult:
     """Result of dense_search_packed: everything stays on the device and NOTHING has been synchronised with the host.
-    `pairs` is int32 [rows, 2, k] (this rank's merged query slice [lo, hi)) or, after the all-gather, [Q, 2, k];
-    `flags` int32 [G] holds every rank's threshold-failure flag (they travelled inside the all-to-all).  Read
-    `ok()` when the result is consumed (one tiny D2H, e.g. together with the result copy); a False means some shard's
-    sampled threshold failed -- rare -- and the caller repeats the search with the exact path on all ranks."""
+    `pairs` is int32 [G, rows + 1, 2, k] after the all-gather (query q lives at [q // rows, q % rows]; [..., 0, :] are
+    float32 score bits, [..., 1, :] int32 ids) or [rows + 1, 2, k] (this rank's merged query slice [lo, hi)) with
+    gather=False; the spare row of every slice carries the merging rank's "truncation may have lost a document" flag.
+    `flags` int32 [G] holds every rank's local-search threshold-failure flag (they travelled inside the all-to-all).
+    Read `ok()` when the result is consumed (one tiny D2H, e.g. together with the result copy); False -- rare -- means
+    the caller repeats the search on all ranks with exact=True (full-length lists, exact repair)."""
 
-    def __init__(self, pairs, flags, lo, hi, gathered):
-        self.pairs, self.flags, self.lo, self.hi, self.gathered = pairs, flags, lo, hi, gathered
+    def __init__(self, pairs, flags, rows, lo, hi, n_queries, gathered):
+        self.pairs, self.flags, self.rows, self.lo, self.hi, self.Q, self.gathered = pairs, flags, rows, lo, hi, n_queries, gathered
+
+    def _part(self, which):
+        if self.gathered:
+            v = self.pairs[:, :self.rows, which, :]
+            return v.reshape(-1, v.shape[-1])[:self.Q]          # (a copy: the slices are separated by their spare rows)
+        return self.pairs[:self.hi - self.lo, which, :]
 
     @property
     def scores(self):
-        return self.pairs[: (self.hi - self.lo), 0, :].view(torch.float32)
+        return self._part(0).view(torch.float32)
 
     @property
     def ids(self):
-        return self.pairs[: (self.hi - self.lo), 1, :]
+        return self._part(1)
+
+    @property
+    def incomplete(self):
+        return self.pairs[:, self.rows, 0, 0] if self.gathered else self.pairs[self.rows, 0, :1]
 
     def ok(self) -> bool:
-        return int(self.flags.max().item()) == 0
+        return int(self.flags.max().item()) == 0 and int(self.incomplete.max().item()) == 0
 
 
 def dense_search_packed(queries_bf16: torch.Tensor, corpus_shard_bf16: torch.Tensor, k: int, id_offset: int, group=None,
-                        gather: bool = True) -> ShardedSearchResult:
+                        gather: bool = True, truncate: bool = True) -> ShardedSearchResult:
     """Sharded exact search with ONE exchange and no host synchronisation:
-        local top-k written as packed (score, id) rows per destination rank (qf_dense_topk_packed)
+        local top-k_in written as packed (score, id) rows per destination rank (qf_dense_topk_packed); k_in =
+        send_depth(k, G) < k when truncate (G >= 3): a cheaper local search and 2-4x fewer bytes on the wire
         -> ONE all-to-all (each rank receives all shards' lists for ITS Q/G queries, plus every rank's status flag in
            the spare row of its chunk)
-        -> k-way merge of the slice (qf_topk_merge_packed)
-        -> gather=True: ONE all-gather of the merged slices ([Q, 2, k] on every rank);
+        -> k-way merge of the slice to the top k (qf_topk_merge_packed) + completeness check of the truncation
+           (qf_topk_merge_check -> flag in the slice's spare row)
+        -> gather=True: ONE all-gather of the merged slices (every rank holds all Q results and all flags);
            gather=False: the rank keeps only its slice (a serving front end reads the G slices: Q*k*8 bytes in total
            leave the GPUs instead of G times that).
     Round 1 used five collectives (scores and ids separately, twice, plus a MAX all-reduce read back with .item())."""
@@ -128,19 +151,22 @@ def dense_search_packed(queries_bf16: torch.Tensor, corpus_shard_bf16: torch.Ten
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     Q = queries_bf16.shape[0]
-    send, _status = ops.dense_topk_packed(queries_bf16, corpus_shard_bf16, k, id_offset, chunks=world)
+    k_in = send_depth(k, world) if truncate else k
+    send, _status = ops.dense_topk_packed(queries_bf16, corpus_shard_bf16, k_in, id_offset, chunks=world)
     rows = send.shape[1] - 1
     recv = torch.empty_like(send)
     dist.all_to_all_single(recv, send, group=group)                    # chunk g of the send buffer goes to rank g
     flags = recv[:, rows, 0, 0].contiguous()                           # every rank's flag, identical on all ranks
-    merged = ops.topk_merge_packed(recv, rows)                         # [rows, 2, k]
+    merged = torch.empty((rows + 1, 2, k), dtype=torch.int32, device=send.device)
+    merged[rows, 0, :1] = 0                                            # this slice's "incomplete" flag
+    ops.topk_merge_packed(recv, rows, k_out=k, out=merged, flag=merged[rows, 0, :1])
     lo = min(Q, rank * rows)
     hi = min(Q, lo + rows)
     if not gather:
-        return ShardedSearchResult(merged, flags, lo, hi, False)
-    full = torch.empty((world * rows, 2, k), dtype=torch.int32, device=merged.device)
+        return ShardedSearchResult(merged, flags, rows, lo, hi, Q, False)
+    full = torch.empty((world, rows + 1, 2, k), dtype=torch.int32, device=merged.device)
     dist.all_gather_into_tensor(full, merged, group=group)
-    return ShardedSearchResult(full, flags, 0, Q, True)
+    return ShardedSearchResult(full, flags, rows, 0, Q, Q, True)
 
 
 def dense_search_sharded(queries_bf16: torch.Tensor, corpus_shard_bf16: torch.Tensor, k: int, id_offset: int, group=None,
@@ -158,7 +184,7 @@ def dense_search_sharded(queries_bf16: torch.Tensor, corpus_shard_bf16: torch.Te
     world = dist.get_world_size(group)
     if merge == "all_to_all" and world > 1 and not exact:
         res = dense_search_packed(queries_bf16, corpus_shard_bf16, k, id_offset, group, gather=True)
-        return res.scores, res.ids, res.flags
+        return res.scores, res.ids, torch.maximum(res.flags, res.incomplete.to(res.flags.dtype))
     scores, ids, status = ops.dense_topk(queries_bf16, corpus_shard_bf16, k, id_offset)
     Q = scores.shape[0]
     if merge == "all_gather" or world == 1:

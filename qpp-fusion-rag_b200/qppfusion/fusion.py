@@ -143,6 +143,8 @@ def fuse_packed(packed: PackedRuns, method: int, weights: Optional[np.ndarray] =
     shape_key = tuple(packed.doc_ids.shape[1:])
     r_, k_ = shape_key
     max_post = int(N.lib().qf_fuse_max_postings())
+    if packed.scores.dtype == np.float64:
+        max_post = min(max_post, 5120)          # 8-byte scores: the wide (6 144-posting) kernel needs 4-byte scores
     if r_ * k_ > max_post or r_ > 32:
         # K is the deepest (qid, ranker) list of the whole call (every list is padded to it): name it
         qi, ri = np.unravel_index(int(np.argmax(packed.lens)), packed.lens.shape)

@@ -272,13 +272,21 @@ def dense_topk_packed(queries: torch.Tensor, corpus: torch.Tensor, k: int, id_of
     return pairs, status
 
 
-def topk_merge_packed(pairs: torch.Tensor, rows: int) -> torch.Tensor:
-    """pairs int32 [G, rows(+spare), 2, k] (as the all-to-all leaves them) -> merged int32 [rows, 2, k]."""
+def topk_merge_packed(pairs: torch.Tensor, rows: int, k_out: Optional[int] = None, out: Optional[torch.Tensor] = None,
+                      flag: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """pairs int32 [G, rows(+spare), 2, k_in] (as the all-to-all leaves them) -> merged int32 [rows, 2, k_out]
+    (written into `out[:rows]` when given).  With `flag` (device int32 [1]) and k_in < k_out the completeness check of
+    the truncated exchange runs too (qf_topk_merge_check)."""
     dev = N.require_cuda(pairs)
-    G, rr, two, k = pairs.shape
-    out = torch.empty((rows, 2, k), dtype=torch.int32, device=dev)
+    G, rr, two, k_in = pairs.shape
+    k_out = int(k_out or k_in)
+    if out is None:
+        out = torch.empty((rows, 2, k_out), dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
-        N.check(N.lib().qf_topk_merge_packed(N.ptr(pairs), G, rows, k, rr * 2 * k, N.ptr(out), N.stream_ptr(dev)))
+        N.check(N.lib().qf_topk_merge_packed(N.ptr(pairs), G, rows, k_in, rr * 2 * k_in, k_out, N.ptr(out), N.stream_ptr(dev)))
+        if flag is not None and k_in < k_out:
+            N.check(N.lib().qf_topk_merge_check(N.ptr(pairs), G, rows, k_in, rr * 2 * k_in, N.ptr(out), k_out, N.ptr(flag),
+                                                N.stream_ptr(dev)))
     return out
 
 

@@ -217,32 +217,56 @@ def test_dense_scores_matches_fp32_matmul():
     assert float((full[:Q, :N] - ref).abs().max()) <= TOL_SAME_INPUT
 
 
-def test_packed_one_exchange_layout_on_one_gpu():
-    """qf_dense_topk_packed + qf_topk_merge_packed (the ONE-exchange multi-GPU search, qppfusion/distributed.py) with the
-    all-to-all emulated by indexing: G corpus shards searched on one device, each shard's packed output [G, rows+1, 2, k]
-    'sent' chunk by chunk, every destination merges its query slice, the slices concatenated == the single search."""
+def _emulated_exchange(qb, cb, k, G, k_in):
+    """G corpus shards searched on one device, the all-to-all emulated by indexing -> (merged [Q,2,k], flag)."""
     from qppfusion import ops
+    Q, N = qb.shape[0], cb.shape[0]
+    per = (N + G - 1) // G
+    sends = []
+    for g in range(G):
+        lo = g * per
+        pairs, status = ops.dense_topk_packed(qb, cb[lo:lo + per].contiguous(), k_in, lo, chunks=G)
+        assert int(status.max()) == 0 and pairs.shape == (G, (Q + G - 1) // G + 1, 2, k_in)
+        assert int(pairs[:, -1, 0, 0].max()) == 0                  # the flag row
+        sends.append(pairs)
+    rows = sends[0].shape[1] - 1
+    flag = torch.zeros((1,), dtype=torch.int32, device=qb.device)
+    merged = []
+    for dst in range(G):
+        recv = torch.stack([sends[src][dst] for src in range(G)]).contiguous()      # what rank dst receives
+        merged.append(ops.topk_merge_packed(recv, rows, k_out=k, flag=flag))
+    return torch.cat(merged)[:Q], int(flag.item())
+
+
+def test_packed_one_exchange_layout_on_one_gpu():
+    """qf_dense_topk_packed + qf_topk_merge_packed (+ qf_topk_merge_check) -- the ONE-exchange multi-GPU search of
+    qppfusion/distributed.py -- with the all-to-all emulated by indexing: every destination merges its query slice, the
+    slices concatenated == the single search.  Full-length lists, then the TRUNCATED exchange (each shard sends its top
+    2k/G + 64): equal on a shuffled corpus with the completeness flag clear; on a corpus whose best documents all sit in
+    one shard the flag must be SET (the host layer then repeats the search with full lists)."""
+    from qppfusion import ops
+    from qppfusion.distributed import send_depth
     rng = np.random.default_rng(31)
     Q, N, D, k, G = 301, 30011, 768, 100, 4
     dev = torch.device("cuda:0")
     qb, cb = to_bf16(unit_rows(rng, Q, D)).to(dev), to_bf16(unit_rows(rng, N, D)).to(dev)
     fs, fi, st = ops.dense_topk(qb, cb, k, 0)
-    per = (N + G - 1) // G
-    sends = []
-    for g in range(G):
-        lo = g * per
-        pairs, status = ops.dense_topk_packed(qb, cb[lo:lo + per].contiguous(), k, lo, chunks=G)
-        assert int(status.max()) == 0 and pairs.shape == (G, (Q + G - 1) // G + 1, 2, k)
-        assert int(pairs[:, -1, 0, 0].max()) == 0                  # the flag row
-        sends.append(pairs)
-    rows = sends[0].shape[1] - 1
-    merged = []
-    for dst in range(G):
-        recv = torch.stack([sends[src][dst] for src in range(G)]).contiguous()      # what rank dst receives
-        merged.append(ops.topk_merge_packed(recv, rows))
-    full = torch.cat(merged)[:Q]
-    assert torch.equal(full[:, 1, :], fi)
-    assert torch.equal(full[:, 0, :].contiguous().view(torch.float32), fs)
+    full, flag = _emulated_exchange(qb, cb, k, G, k)
+    assert flag == 0 and torch.equal(full[:, 1, :], fi) and torch.equal(full[:, 0, :].contiguous().view(torch.float32), fs)
+    k_in = send_depth(k, G)
+    assert k_in == 128 and send_depth(1000, 8) == 320 and send_depth(1000, 2) == 1000
+    full, flag = _emulated_exchange(qb, cb, k, G, k_in)
+    assert flag == 0 and torch.equal(full[:, 1, :], fi) and torch.equal(full[:, 0, :].contiguous().view(torch.float32), fs)
+    # every query's best documents in shard 0: the truncated lists lose documents and the check says so
+    cb2 = cb.clone()
+    n0 = N // G
+    noise = torch.from_numpy(rng.standard_normal((n0, D)).astype(np.float32)).to(dev)
+    cb2[:n0] = (qb.float()[torch.arange(n0, device=dev) % Q] + 0.02 * noise).to(torch.bfloat16)
+    _full2, flag2 = _emulated_exchange(qb, cb2, k, G, k_in)
+    assert flag2 == 1
+    fs2, fi2, _ = ops.dense_topk(qb, cb2, k, 0)
+    full3, flag3 = _emulated_exchange(qb, cb2, k, G, k)              # the repeat with full lists is exact
+    assert flag3 == 0 and torch.equal(full3[:, 1, :], fi2)
 
 
 def test_c3_size_same_input_parity_against_fp32_matmul():

@@ -396,3 +396,17 @@ def test_repeated_launches_are_bitwise_identical():
                 first = cur
             else:
                 assert all(torch.equal(a, b) for a, b in zip(first, cur)), f"launch {it} differs (method {method})"
+
+
+def test_six_runs_of_depth_1000_fit_the_wide_general_kernel():
+    """6 retrievers x TREC depth 1000 = 6 000 postings per query worked in the reference and failed here.
+    4-byte scores now go up to 6 144 postings per query (general kernel alone); float64 scores stop at 5 120 with a
+    message that says so."""
+    from qppfusion import _native as N
+    lists = synth_lists(51, n_q=6, n_r=6, k=1000, pool=2600, ties=True)
+    w = np.round(np.random.default_rng(2).random((6, 6)), 6)
+    for method in ("sum", "mnz", "rrf"):
+        out = run_gpu(lists, method, w, k=1000, score_type="micro")
+        check_against_oracle(lists, method, w, out)
+    with pytest.raises(N.NativeError, match="5120"):
+        run_gpu(lists, "sum", w, k=1000, score_type="f64")

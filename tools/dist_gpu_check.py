@@ -19,14 +19,25 @@ c = torch.randn((N, D), generator=g); c = (c / c.norm(dim=1, keepdim=True)).to(t
 q = torch.randn((Q, D), generator=g); q = (q / q.norm(dim=1, keepdim=True)).to(torch.bfloat16).to(dev)
 lo, hi = qd.shard_range(N, world, rank)
 shard = c[lo:hi].to(dev).contiguous()
-ms, mi, st = qd.dense_search_sharded(q, shard, k, lo)              # packed one-exchange path
-assert st.shape == (world,) and int(st.max()) == 0
+ms, mi, st = qd.dense_search_sharded(q, shard, k, lo)              # packed one-exchange path (truncated lists at G >= 3)
+assert st.shape == (world,) and int(st.max()) == 0, st
 ms2, mi2, _ = qd.dense_search_sharded(q, shard, k, lo, merge="all_gather")
 assert torch.equal(ms, ms2) and torch.equal(mi, mi2), "packed exchange and all_gather merges differ"
 ms3, mi3, _ = qd.dense_search_sharded(q, shard, k, lo, exact=True)
 assert torch.equal(ms, ms3) and torch.equal(mi, mi3), "packed exchange and the exact all_to_all path differ"
 res = qd.dense_search_packed(q, shard, k, lo, gather=False)          # rank-local slice only
 assert res.ok() and torch.equal(res.scores, ms[res.lo:res.hi]) and torch.equal(res.ids, mi[res.lo:res.hi])
+# a corpus whose best documents all sit in ONE shard: the truncated exchange must notice and say so
+if world >= 3:
+    c2 = c.clone()
+    c2[: N // world] = (q.cpu().float()[torch.arange(N // world) % Q] + 0.05 * torch.randn((N // world, D), generator=g)).to(torch.bfloat16)
+    shard2 = c2[lo:hi].to(dev).contiguous()
+    res2 = qd.dense_search_packed(q, shard2, k, lo, gather=True)
+    assert int(res2.flags.max()) == 0 and int(res2.incomplete.max()) != 0, "truncation loss was not detected"
+    ms4, mi4, st4 = qd.dense_search_sharded(q, shard2, k, lo, exact=True)
+    if rank == 0:
+        fs2, fi2, _ = ops.dense_topk(q, c2.to(dev), k, 0)
+        assert torch.equal(fs2, ms4) and torch.equal(fi2, mi4), "exact path differs from single-GPU search"
 if rank == 0:
     fs, fi, st0 = ops.dense_topk(q, c.to(dev), k, 0)
     assert torch.equal(fs, ms) and torch.equal(fi, mi), "sharded dense search differs from single-GPU search"
