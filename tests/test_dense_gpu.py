@@ -247,25 +247,27 @@ def test_packed_one_exchange_layout_on_one_gpu():
     from qppfusion import ops
     from qppfusion.distributed import send_depth
     rng = np.random.default_rng(31)
-    Q, N, D, k, G = 301, 30011, 768, 100, 4
+    Q, N, D, k, G = 301, 30011, 768, 400, 4
     dev = torch.device("cuda:0")
     qb, cb = to_bf16(unit_rows(rng, Q, D)).to(dev), to_bf16(unit_rows(rng, N, D)).to(dev)
     fs, fi, st = ops.dense_topk(qb, cb, k, 0)
     full, flag = _emulated_exchange(qb, cb, k, G, k)
     assert flag == 0 and torch.equal(full[:, 1, :], fi) and torch.equal(full[:, 0, :].contiguous().view(torch.float32), fs)
     k_in = send_depth(k, G)
-    assert k_in == 128 and send_depth(1000, 8) == 320 and send_depth(1000, 2) == 1000
+    assert k_in == 272 and send_depth(1000, 8) == 320 and send_depth(1000, 2) == 1000 and send_depth(100, 4) == 100
     full, flag = _emulated_exchange(qb, cb, k, G, k_in)
     assert flag == 0 and torch.equal(full[:, 1, :], fi) and torch.equal(full[:, 0, :].contiguous().view(torch.float32), fs)
-    # every query's best documents in shard 0: the truncated lists lose documents and the check says so
+    # 16 queries whose 400 best documents all sit in shard 0: the truncated lists lose documents and the check says so
+    q2 = qb[:16].contiguous()
     cb2 = cb.clone()
-    n0 = N // G
+    n0 = 16 * 400
+    assert n0 <= N // G
     noise = torch.from_numpy(rng.standard_normal((n0, D)).astype(np.float32)).to(dev)
-    cb2[:n0] = (qb.float()[torch.arange(n0, device=dev) % Q] + 0.02 * noise).to(torch.bfloat16)
-    _full2, flag2 = _emulated_exchange(qb, cb2, k, G, k_in)
+    cb2[:n0] = (q2.float()[torch.arange(n0, device=dev) % 16] + 0.02 * noise).to(torch.bfloat16)
+    _full2, flag2 = _emulated_exchange(q2, cb2, k, G, k_in)
     assert flag2 == 1
-    fs2, fi2, _ = ops.dense_topk(qb, cb2, k, 0)
-    full3, flag3 = _emulated_exchange(qb, cb2, k, G, k)              # the repeat with full lists is exact
+    fs2, fi2, _ = ops.dense_topk(q2, cb2, k, 0)
+    full3, flag3 = _emulated_exchange(q2, cb2, k, G, k)              # the repeat with full lists is exact
     assert flag3 == 0 and torch.equal(full3[:, 1, :], fi2)
 
 

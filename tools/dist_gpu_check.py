@@ -30,8 +30,11 @@ assert res.ok() and torch.equal(res.scores, ms[res.lo:res.hi]) and torch.equal(r
 # a corpus whose best documents all sit in ONE shard: the truncated exchange must notice and say so
 if world >= 3:
     c2 = c.clone()
-    c2[: N // world] = (q.cpu().float()[torch.arange(N // world) % Q] + 0.05 * torch.randn((N // world, D), generator=g)).to(torch.bfloat16)
+    nq2 = min(Q, (N // world) // k)                       # queries whose k best documents all fit into shard 0
+    q2 = q[:nq2].contiguous()
+    c2[: nq2 * k] = (q2.cpu().float()[torch.arange(nq2 * k) % nq2] + 0.02 * torch.randn((nq2 * k, D), generator=g)).to(torch.bfloat16)
     shard2 = c2[lo:hi].to(dev).contiguous()
+    q = q2
     res2 = qd.dense_search_packed(q, shard2, k, lo, gather=True)
     assert int(res2.flags.max()) == 0 and int(res2.incomplete.max()) != 0, "truncation loss was not detected"
     ms4, mi4, st4 = qd.dense_search_sharded(q, shard2, k, lo, exact=True)
