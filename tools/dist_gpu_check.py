@@ -34,12 +34,11 @@ if world >= 3:
     q2 = q[:nq2].contiguous()
     c2[: nq2 * k] = (q2.cpu().float()[torch.arange(nq2 * k) % nq2] + 0.02 * torch.randn((nq2 * k, D), generator=g)).to(torch.bfloat16)
     shard2 = c2[lo:hi].to(dev).contiguous()
-    q = q2
-    res2 = qd.dense_search_packed(q, shard2, k, lo, gather=True)
+    res2 = qd.dense_search_packed(q2, shard2, k, lo, gather=True)
     assert int(res2.flags.max()) == 0 and int(res2.incomplete.max()) != 0, "truncation loss was not detected"
-    ms4, mi4, st4 = qd.dense_search_sharded(q, shard2, k, lo, exact=True)
+    ms4, mi4, st4 = qd.dense_search_sharded(q2, shard2, k, lo, exact=True)
     if rank == 0:
-        fs2, fi2, _ = ops.dense_topk(q, c2.to(dev), k, 0)
+        fs2, fi2, _ = ops.dense_topk(q2, c2.to(dev), k, 0)
         assert torch.equal(fs2, ms4) and torch.equal(fi2, mi4), "exact path differs from single-GPU search"
 if rank == 0:
     fs, fi, st0 = ops.dense_topk(q, c.to(dev), k, 0)
