@@ -336,6 +336,16 @@ typedef struct qf_bert_config {
 QF_API size_t qf_bert_weight_elems(const qf_bert_config* cfg);
 QF_API size_t qf_bert_workspace_bytes(const qf_bert_config* cfg, int B, int L);
 /*
+ * One Linear layer of the encoder on the tensor cores (own tcgen05 kernel, csrc/qf_gemm.cu; round 1 called cuBLASLt):
+ *   Y[M][N] (bf16) = act( X[M][K] (bf16) . W[N][K]^T (bf16, the nn.Linear weight) + bias[N] (bf16) ),
+ *   act: 0 = identity, 1 = erf-GELU (HF BERT's "gelu").  fp32 accumulation in tensor memory.
+ * Envelope: M % 128 == 0, N % 128 == 0, K % 64 == 0, operands 16-byte aligned.  qf_bert_encode uses it for every
+ * Linear layer (the FFN-1 GELU is fused into its epilogue).
+ */
+QF_API int    qf_linear_bf16(const void* W, const void* X, const void* bias, void* Y, long long M, int N, int K, int act,
+                             void* stream);
+
+/*
  * tokens[B][L] int32 (padded with anything; positions >= lens[b] are masked as keys and never pooled), lens[B]
  * (nullable = all L; clamped to [1, L]).  Outputs (either may be null): out_bf16[B][H] -- directly the `queries_bf16`
  * of qf_dense_topk -- and out_f32[B][H], the L2-normalised embedding.  out_status[b] (nullable): bit 0 = a token id

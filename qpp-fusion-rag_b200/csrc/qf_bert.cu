@@ -21,6 +21,7 @@
 #include <vector>
 
 #include "qf_common.cuh"
+#include "qf_gemm.cuh"
 
 namespace {
 
@@ -674,23 +675,35 @@ int encode_impl(const qf_bert_config& c, const bf16* wts, const int32_t* tokens,
               : tl <= 8 ? attn_kernel<8> : attn_kernel<16>;
   QF_CUDA_TRY(cudaFuncSetAttribute(attn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem));
   const dim3 attn_grid((unsigned)B, use_mma ? (unsigned)c.heads / 4 : (unsigned)c.heads);
+  // Linear layers: the own tcgen05 GEMM (csrc/qf_gemm.cu; FFN-1 with the erf-GELU fused into its epilogue) whenever the
+  // shape fits its envelope (every BERT-base / -large shape does); cuBLASLt + the separate GELU pass otherwise, or with
+  // QF_BERT_CUBLASLT=1 (A/B hook, read once).
+  static const bool force_lt = getenv("QF_BERT_CUBLASLT") != nullptr;
+  const bool own = !force_lt && qf::gemm_supported(Mg, 3 * H, H) && qf::gemm_supported(Mg, H, H) &&
+                   qf::gemm_supported(Mg, F, H) && qf::gemm_supported(Mg, H, F);
+  auto linear = [&](const bf16* W, const bf16* Xin, const bf16* b, bf16* Y, int N_, int K_, int act) -> int {
+    if (own) return qf::gemm_bias_act(W, Xin, b, Y, Mg, N_, K_, act, st);
+    return gemm_bias(W, Xin, b, Y, Mg, N_, K_, lt_ws, st);
+  };
   for (int l = 0; l < c.n_layers; ++l) {
     const bf16* lw = wts + o.layer0 + (size_t)l * o.per_layer;
-    int rc = gemm_bias(lw + o.wqkv, X, lw + o.bqkv, QKV, Mg, 3 * H, H, lt_ws, st);
+    int rc = linear(lw + o.wqkv, X, lw + o.bqkv, QKV, 3 * H, H, 0);
     if (rc != QF_OK) return rc;
     attn<<<attn_grid, 128, attn_smem, st>>>(QKV, lens, cu, CTX, L, H);
     QF_CUDA_TRY(cudaGetLastError());
-    rc = gemm_bias(lw + o.wo, CTX, lw + o.bo, T1, Mg, H, H, lt_ws, st);
+    rc = linear(lw + o.wo, CTX, lw + o.bo, T1, H, H, 0);
     if (rc != QF_OK) return rc;
     add_ln_kernel<VPL><<<tok_blocks, 256, 0, st>>>(T1, X, lw + o.g1, lw + o.b1, c.ln_eps, X, M);
     QF_CUDA_TRY(cudaGetLastError());
-    rc = gemm_bias(lw + o.w1, X, lw + o.bi1, FF, Mg, F, H, lt_ws, st);
+    rc = linear(lw + o.w1, X, lw + o.bi1, FF, F, H, 1);            // own GEMM: GELU fused
     if (rc != QF_OK) return rc;
-    const size_t n8 = (size_t)M * F / 8;
-    const size_t gelu_cap = (size_t)qf::sm_count() * 32, gelu_need = (n8 + 255) / 256;
-    gelu_kernel<<<(unsigned)(gelu_need < gelu_cap ? gelu_need : gelu_cap), 256, 0, st>>>(FF, n8);
-    QF_CUDA_TRY(cudaGetLastError());
-    rc = gemm_bias(lw + o.w2, FF, lw + o.bi2, T1, Mg, H, F, lt_ws, st);
+    if (!own) {
+      const size_t n8 = (size_t)M * F / 8;
+      const size_t gelu_cap = (size_t)qf::sm_count() * 32, gelu_need = (n8 + 255) / 256;
+      gelu_kernel<<<(unsigned)(gelu_need < gelu_cap ? gelu_need : gelu_cap), 256, 0, st>>>(FF, n8);
+      QF_CUDA_TRY(cudaGetLastError());
+    }
+    rc = linear(lw + o.w2, FF, lw + o.bi2, T1, H, F, 0);
     if (rc != QF_OK) return rc;
     add_ln_kernel<VPL><<<tok_blocks, 256, 0, st>>>(T1, X, lw + o.g2, lw + o.b2, c.ln_eps, X, M);
     QF_CUDA_TRY(cudaGetLastError());

@@ -77,6 +77,7 @@ PROTOTYPES = {
     "qf_dense_topk_packed": (_i, [_vp, _vp, _i, _i, _i, _i, ctypes.c_longlong, _vp, _i, ctypes.c_longlong, _vp, _vp, _sz, _vp]),
     "qf_topk_merge_packed": (_i, [_vp, _i, _i, _i, ctypes.c_longlong, _i, _vp, _vp]),
     "qf_topk_merge_check": (_i, [_vp, _i, _i, _i, ctypes.c_longlong, _vp, _i, _vp, _vp]),
+    "qf_linear_bf16": (_i, [_vp, _vp, _vp, _vp, ctypes.c_longlong, _i, _i, _i, _vp]),
     "qf_bert_weight_elems": (_sz, [_vp]),
     "qf_bert_workspace_bytes": (_sz, [_vp, _i, _i]),
     "qf_bert_encode": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
