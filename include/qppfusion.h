@@ -159,6 +159,13 @@ QF_API int  qf_runs_info(const qf_runs* runs, int64_t* rows_per_file, int32_t* n
 QF_API int  qf_runs_rows(const qf_runs* runs, int file, int32_t* qid_idx, int32_t* doc_idx, int32_t* rank, int32_t* micro,
                          double* score);
 QF_API int  qf_runs_dict(const qf_runs* runs, int which /*0 qid, 1 docno*/, char* arena, int64_t* offsets);
+/* Host-side packing of the parsed columns into the dense [Q][R][K] layout qf_fuse reads, "weighted" semantics (every
+ * row kept, file order inside a query: the per-query groupby of src/fusion.py:260-275).  qid_rank[code] = row of that
+ * query in the packed arrays; outputs pre-initialised by the caller (doc_ids -1, the rest 0); pass micro OR scores. */
+QF_API int  qf_pack_weighted(const int32_t* const* qid_cols, const int32_t* const* doc_cols, const int32_t* const* micro_cols,
+                             const double* const* score_cols, const int32_t* const* rank_cols, const int64_t* n_rows, int R,
+                             const int64_t* qid_rank, int n_qid_codes, int Q, int K, int32_t* doc_ids, int32_t* micro,
+                             double* scores, int32_t* ranks);
 /* Write "{qid} Q0 {docno} {rank} {score:.6f} {tag}" lines from CSR results (query j of the file = CSR row qsel[j],
  * already ranked); strings come from the dictionaries (arena + offsets). */
 QF_API int  qf_runfile_write(const char* path, const char* qid_arena, const int64_t* qid_off, const int32_t* qsel,

@@ -401,6 +401,43 @@ extern "C" int qf_runs_dict(const qf_runs* r, int which, char* arena, int64_t* o
   return QF_OK;
 }
 
+// Dense packing of parsed run files for qf_fuse, "weighted" semantics (rows kept as they are, in file order, grouped
+// by query: src/fusion.py:260-275): file r's row i goes to [q][r][w] with q = qid_rank[qid[i]] and w = the number of
+// earlier rows of that file with the same query.  One thread per file; outputs are pre-initialised by the caller
+// (doc ids -1, scores / ranks 0).  Replaces a numpy argsort + fancy-index scatter that cost 75 ns per row.
+extern "C" int qf_pack_weighted(const int32_t* const* qid_cols, const int32_t* const* doc_cols, const int32_t* const* micro_cols,
+                                const double* const* score_cols, const int32_t* const* rank_cols, const int64_t* n_rows, int R,
+                                const int64_t* qid_rank, int n_qid_codes, int Q, int K, int32_t* doc_ids, int32_t* micro,
+                                double* scores, int32_t* ranks) {
+  QF_REQUIRE(qid_cols && doc_cols && n_rows && qid_rank && doc_ids && R >= 1 && Q >= 0 && K >= 1 && (micro || scores),
+             QF_E_INVALID, "qf_pack_weighted: bad arguments");
+  std::vector<std::thread> th;
+  std::vector<int> bad((size_t)R, 0);
+  for (int r = 0; r < R; ++r)
+    th.emplace_back([&, r]() {
+      std::vector<int32_t> cursor((size_t)Q, 0);
+      const int32_t* qc = qid_cols[r];
+      const int32_t* dc = doc_cols[r];
+      const int64_t n = n_rows[r];
+      for (int64_t i = 0; i < n; ++i) {
+        const int32_t code = qc[i];
+        if (code < 0 || code >= n_qid_codes) { bad[(size_t)r] = 1; return; }
+        const int64_t q = qid_rank[code];
+        const int32_t w = cursor[(size_t)q]++;
+        if (w >= K) { bad[(size_t)r] = 1; return; }
+        const size_t at = ((size_t)q * (size_t)R + (size_t)r) * (size_t)K + (size_t)w;
+        doc_ids[at] = dc[i];
+        if (micro) micro[at] = micro_cols[r][i];
+        else scores[at] = score_cols[r][i];
+        if (ranks) ranks[at] = rank_cols[r][i];
+      }
+    });
+  for (auto& t : th) t.join();
+  for (int r = 0; r < R; ++r)
+    QF_REQUIRE(!bad[(size_t)r], QF_E_INVALID, "qf_pack_weighted: file %d has a row outside the packed shape", r);
+  return QF_OK;
+}
+
 // "%d" / "%.6f" without printf.  fmt_fixed6 reproduces glibc's (= Python's) correctly rounded "%.6f" for
 // |x| < 1e9: x * 10^6 is rounded to the nearest integer (ties to even) EXACTLY -- pr = fl(x * 1e6) and the FMA
 // residual err = x * 1e6 - pr give the true product as pr + err, so the distance to the rounding boundary is decided

