@@ -870,82 +870,123 @@ def run_ours(args):
     wrrf = wrrf_leg(args, dev, sets) if (rank == 0 and world == 1) else None
     torch.cuda.empty_cache()
 
-    # ---- end to end: pinned host buffers -> H2D into the graph's input tensors -> graph replay (step + CSR
-    # compaction) -> D2H of the fused run.  Three streams (H2D / compute / D2H) so step i+1's upload and step i-1's
-    # download overlap step i's kernels; every step's copies are inside the timed region.
+    # ---- end to end: pinned host buffers -> H2D -> graph replay (wire expansion + step + CSR compaction) -> D2H of the
+    # fused run.  Three streams (H2D / compute / D2H) so step i+1's upload and step i-1's download overlap step i's
+    # kernels; every step's copies are inside the timed region.  The postings travel bit-packed (csrc/qf_wire.cu:
+    # id_bits + sc_bits per posting instead of 2 x int32) and the step's first kernel expands them; the plain int32
+    # upload is measured next to it (`int32_upload`).
+    ref_lens0 = graphs[0].out.lens.clone()
+    ref_row0 = graphs[0].out.ids[0, :64].clone()
     del graphs
     torch.cuda.empty_cache()
-    graphs = [make_graph(i, True) for i in range(3)]       # e2e: step + CSR compaction in one graph
     NSETS = 3
-    h_sets = [[x.cpu().pin_memory() for x in st_] for st_ in sets[:NSETS]]
     n_post = Q * R * K
     NB = 2
     h_off = [torch.empty((Q + 1,), dtype=torch.int64).pin_memory() for _ in range(NB)]
     h_ids = [torch.empty((n_post,), dtype=torch.int32).pin_memory() for _ in range(NB)]
     h_sc = [torch.empty((n_post,), dtype=torch.float64).pin_memory() for _ in range(NB)]
     s_h2d, s_cmp, s_d2h = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-    d2h_bytes = [0]
-
-    def e2e_run(n_steps):
-        ev_h2d = [torch.cuda.Event() for _ in range(n_steps)]
-        ev_cmp = [torch.cuda.Event() for _ in range(n_steps)]
-        ev_d2h = [torch.cuda.Event() for _ in range(n_steps)]
-        ev_off = torch.cuda.Event()
-
-        def upload(i):
-            with torch.cuda.stream(s_h2d):
-                if i >= NB:
-                    s_h2d.wait_event(ev_cmp[i - NB])            # that set's previous step has consumed its inputs
-                for dst, src in zip(sets[i % NSETS], h_sets[i % NSETS]):
-                    dst.copy_(src, non_blocking=True)
-                ev_h2d[i].record(s_h2d)
-
-        upload(0)
-        for i in range(n_steps):
-            if i + 1 < n_steps:
-                upload(i + 1)
-            b = i % NB
-            g = graphs[i % NSETS]
-            with torch.cuda.stream(s_cmp):
-                s_cmp.wait_event(ev_h2d[i])
-                if i >= NSETS:
-                    s_cmp.wait_event(ev_d2h[i - NSETS])         # that graph's previous outputs have been downloaded
-                g.replay()
-                ev_cmp[i].record(s_cmp)
-            off, cids, csc = g.csr
-            with torch.cuda.stream(s_d2h):
-                s_d2h.wait_event(ev_cmp[i])
-                h_off[b].copy_(off, non_blocking=True)
-                ev_off.record(s_d2h)
-            ev_off.synchronize()                                 # host needs the total before sizing the copy
-            total = int(h_off[b][-1])
-            with torch.cuda.stream(s_d2h):
-                h_ids[b][:total].copy_(cids[:total], non_blocking=True)
-                h_sc[b][:total].copy_(csc[:total], non_blocking=True)
-                ev_d2h[i].record(s_d2h)
-            d2h_bytes[0] = total * 12 + (Q + 1) * 8
-
     e2e_steps = max(4, min(args.steps, 12))
-    e2e_run(3)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for s_ in (s_h2d, s_cmp, s_d2h):
-        s_.wait_stream(stream)
-    e2e_run(e2e_steps)
-    for s_ in (s_h2d, s_cmp, s_d2h):
-        stream.wait_stream(s_)
-    e1.record(stream)
-    barrier()
-    e2e_ms = e0.elapsed_time(e1) / e2e_steps
-    h2d = sum(x.numel() * x.element_size() for x in h_sets[0])
-    d2h = d2h_bytes[0]
-    h_in, h_out = h_sets, (h_off, h_ids, h_sc)
-    del graphs
+
+    def e2e_measure(use_wire):
+        if use_wire:
+            h_wire = [ops.wire_pack(st_[0].cpu(), st_[1].cpu(), st_[2].cpu(), pin=True) for st_ in sets[:NSETS]]
+            d_wire = [w_.to(dev) for w_ in h_wire]
+            pairs = [[(d_wire[i].words, h_wire[i].words), (sets[i][2], sets[i][2].cpu().pin_memory()),
+                      (sets[i][3], sets[i][3].cpu().pin_memory())] for i in range(NSETS)]
+            for i in range(NSETS):                       # the graph must rebuild these from the wire on every replay
+                sets[i][0].zero_()
+                sets[i][1].zero_()
+        else:
+            h_wire = d_wire = [None] * NSETS
+            pairs = [[(x, x.cpu().pin_memory()) for x in sets[i]] for i in range(NSETS)]
+        graphs_ = []
+        for i in range(NSETS):
+            if world > 1:
+                from qppfusion.pipeline import ShardedFusionStep
+                graphs_.append(ShardedFusionStep(*sets[i], qpp_index=5, top_k=100, k_cut=50, round6=True, method=0,
+                                                 rrf_k=60.0, flags=0, want_counts=False, want_pos=False, compact=True,
+                                                 wire=d_wire[i]))
+            else:
+                graphs_.append(FusionStepGraph(*sets[i], qpp_index=5, top_k=100, k_cut=50, colnorm="minmax", round6=True,
+                                               method=0, norm=0, rrf_k=60.0, flags=0, want_counts=False, want_pos=False,
+                                               compact=True, wire=d_wire[i]))
+        d2h_bytes = [0]
+
+        def e2e_run(n_steps):
+            ev_h2d = [torch.cuda.Event() for _ in range(n_steps)]
+            ev_cmp = [torch.cuda.Event() for _ in range(n_steps)]
+            ev_d2h = [torch.cuda.Event() for _ in range(n_steps)]
+            ev_off = torch.cuda.Event()
+
+            def upload(i):
+                with torch.cuda.stream(s_h2d):
+                    if i >= NB:
+                        s_h2d.wait_event(ev_cmp[i - NB])        # that set's previous step has consumed its inputs
+                    for dst, src in pairs[i % NSETS]:
+                        dst.copy_(src, non_blocking=True)
+                    ev_h2d[i].record(s_h2d)
+
+            upload(0)
+            for i in range(n_steps):
+                if i + 1 < n_steps:
+                    upload(i + 1)
+                b = i % NB
+                g = graphs_[i % NSETS]
+                with torch.cuda.stream(s_cmp):
+                    s_cmp.wait_event(ev_h2d[i])
+                    if i >= NSETS:
+                        s_cmp.wait_event(ev_d2h[i - NSETS])     # that graph's previous outputs have been downloaded
+                    g.replay()
+                    ev_cmp[i].record(s_cmp)
+                off, cids, csc = g.csr
+                with torch.cuda.stream(s_d2h):
+                    s_d2h.wait_event(ev_cmp[i])
+                    h_off[b].copy_(off, non_blocking=True)
+                    ev_off.record(s_d2h)
+                ev_off.synchronize()                             # host needs the total before sizing the copy
+                total = int(h_off[b][-1])
+                with torch.cuda.stream(s_d2h):
+                    h_ids[b][:total].copy_(cids[:total], non_blocking=True)
+                    h_sc[b][:total].copy_(csc[:total], non_blocking=True)
+                    ev_d2h[i].record(s_d2h)
+                d2h_bytes[0] = total * 12 + (Q + 1) * 8
+
+        e2e_run(3)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for s_ in (s_h2d, s_cmp, s_d2h):
+            s_.wait_stream(stream)
+        e2e_run(e2e_steps)
+        for s_ in (s_h2d, s_cmp, s_d2h):
+            stream.wait_stream(s_)
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1) / e2e_steps
+        up = sum(src.numel() * src.element_size() for _d, src in pairs[0])
+        # the downloaded run of the last step equals the device-resident result of the same input set (bit for bit)
+        last = (e2e_steps - 1) % NSETS
+        tot = int(h_off[(e2e_steps - 1) % NB][-1])
+        same = bool(tot == int(graphs_[last].out.lens.sum().item()) and
+                    torch.equal(h_ids[(e2e_steps - 1) % NB][:tot], graphs_[last].csr[1][:tot].cpu()) and
+                    torch.equal(graphs_[0].out.lens, ref_lens0) and torch.equal(graphs_[0].out.ids[0, :64], ref_row0))
+        wire_info = None
+        if use_wire:
+            wire_info = {"id_bits": h_wire[0].id_bits, "sc_bits": h_wire[0].sc_bits,
+                         "bytes_per_posting": h_wire[0].words.numel() * 8 / n_post}
+        del graphs_
+        return ms, up, d2h_bytes[0], same, wire_info
+
+    ms_plain, h2d_plain, d2h, same_plain, _ = e2e_measure(False)
+    union_plain = d2h
+    e2e_ms, h2d, d2h, same_wire, wire_info = e2e_measure(True)
+    assert same_plain and same_wire and d2h == union_plain, "e2e: downloaded run differs from the device-resident result"
+    h_out = (h_off, h_ids, h_sc)
     barrier()
     pcie = pcie_probe(dev, h2d, max(d2h, 1 << 20))       # the same bytes per step, copies only: the ceiling of e2e
 
-    del sets, h_in, h_out
+    del sets, h_out
     torch.cuda.empty_cache()
     dense = None if args.no_dense else dense_leg(args, dev, world, rank)
     torch.cuda.empty_cache()
@@ -962,10 +1003,10 @@ def run_ours(args):
     torch.cuda.empty_cache()
     api = api_e2e_leg(args, dev) if (rank == 0 and world == 1 and not args.no_extra) else None
 
-    times = torch.tensor([ms_total, e2e_ms], dtype=torch.float64, device=dev)
+    times = torch.tensor([ms_total, e2e_ms, ms_plain], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    ms_total, e2e_ms = times.tolist()
+    ms_total, e2e_ms, ms_plain = times.tolist()
 
     if rank == 0:
         hbm_peak, tf_peak, which = load_peaks()
@@ -1016,15 +1057,22 @@ def run_ours(args):
                     "pcie_ceiling": dict(pcie, queries_per_s=world * Q / (pcie["ms_per_step_copies_only"] * 1e-3),
                                          note="the same H2D + D2H bytes per step, copies only, both directions at once "
                                               "(this rank; measured while the other ranks do the same at N > 1)"),
-                    "note": "pinned host buffers -> H2D into the graph's inputs -> graph replay (step + CSR compaction) -> "
-                            "D2H; consecutive steps overlap on 3 streams"},
+                    "wire": wire_info,
+                    "int32_upload": {"value": world * Q / (ms_plain * 1e-3), "ms_per_step": ms_plain,
+                                     "h2d_bytes_per_step": h2d_plain,
+                                     "note": "the same step fed with the plain int32 [Q,R,K] id / score arrays"},
+                    "note": "pinned host buffers (postings bit-packed by qf_wire_pack: id_bits + sc_bits per posting) -> "
+                            "H2D -> graph replay (qf_wire_unpack + step + CSR compaction) -> D2H of the fused run; "
+                            "consecutive steps overlap on 3 streams; the downloaded run is checked against the "
+                            "device-resident result"},
             "roofline_issue": issue,
             "parity": main_check,
             "sharded_colnorm": sharded_check,
             "wrrf": wrrf, "c1": c1, "c5": c5, "api_e2e": api,
             "cpu_reference_recorded": recorded_reference(),
-            # per step: qpp 1 + colnorm 3 + select 1 + fuse 2 (streaming + fix-up) = 7; CSR compaction adds 4
-            "gpu_launches": (7 * (args.steps + max(args.warmup, 4)) + 7 * (args.steps + 4) + 11 * (e2e_steps + 3 + 6)
+            # per step: qpp 1 + colnorm 3 + select 1 + fuse 2 (streaming + fix-up) = 7; CSR compaction adds 4, the wire
+            # expansion 1 (e2e is measured twice: int32 upload and bit-packed upload)
+            "gpu_launches": (7 * (args.steps + max(args.warmup, 4)) + 7 * (args.steps + 4) + (11 + 12) * (e2e_steps + 3 + 6)
                              + (dense["gpu_launches"] if dense else 0) + (dense_c4["gpu_launches"] if dense_c4 else 0)
                              + (encoder["gpu_launches"] if encoder else 0)),
             "clocks": clocks,

@@ -123,7 +123,7 @@ QF_API int qf_profile_read(int phase, float* ms);
  *
  * Envelope: R*K <= qf_fuse_max_postings() = 6144 postings per query (shared-memory resident; 5120 for
  * QF_SCORE_F64), R <= 32.  Up to 5120 the streaming kernel runs; 5121..6144 (e.g. 6 runs x depth 1000) take the
- * general kernel alone (about 3x slower per query).
+ * general kernel alone (about 3x slower per query).  Deeper requests: qf_fuse_deep below.
  */
 QF_API int qf_fuse_max_postings(void);
 QF_API int qf_fuse(const int32_t* doc_ids, const void* scores, int score_type, const int32_t* ranks,
@@ -131,6 +131,23 @@ QF_API int qf_fuse(const int32_t* doc_ids, const void* scores, int score_type, c
             int Q, int R, int K, int method, int norm, double rrf_k, uint32_t flags,
             int32_t* out_ids, double* out_scores, uint16_t* out_counts, uint16_t* out_pos,
             int32_t* out_lens, int32_t* out_status, void* stream);
+
+/*
+ * The same fusion for run lists deeper than the shared-memory envelope (the reference's dict loops and ranx.fuse take
+ * any depth: src/fusion.py:266-278, 182): R*K <= qf_fuse_deep_max_postings() = 65535 postings per query (the 16-bit
+ * out_counts / out_pos bound), R <= 32, per-query state in `ws` (qf_fuse_deep_workspace_bytes(Q, R, K) bytes of
+ * 256-byte aligned device scratch; a smaller workspace that holds at least one query just runs fewer CTAs).
+ * Arguments, semantics and outputs are exactly qf_fuse's; out_counts saturates at 65535.  Several times slower per
+ * posting than qf_fuse (hash table and sort buffers in L2 instead of shared memory) -- the host layers call it only
+ * above qf_fuse's envelope.
+ */
+QF_API int    qf_fuse_deep_max_postings(void);
+QF_API size_t qf_fuse_deep_workspace_bytes(int Q, int R, int K);
+QF_API int    qf_fuse_deep(const int32_t* doc_ids, const void* scores, int score_type, const int32_t* ranks,
+                           const int32_t* lens, const double* weights,
+                           int Q, int R, int K, int method, int norm, double rrf_k, uint32_t flags,
+                           int32_t* out_ids, double* out_scores, uint16_t* out_counts, uint16_t* out_pos,
+                           int32_t* out_lens, int32_t* out_status, void* ws, size_t ws_bytes, void* stream);
 
 /*
  * Padded fusion outputs -> CSR: offsets[Q+1] (exclusive scan of out_lens, offsets[Q] = total), then the first
@@ -171,6 +188,26 @@ QF_API int  qf_pack_weighted(const int32_t* const* qid_cols, const int32_t* cons
 QF_API int  qf_runfile_write(const char* path, const char* qid_arena, const int64_t* qid_off, const int32_t* qsel,
                              int n_queries, const char* doc_arena, const int64_t* doc_off, const int64_t* offsets,
                              const int32_t* ids, const double* scores, const char* tag, int n_threads);
+
+/* ------------------------------------------------------------------------------------------------
+ * Bit-packed host->device transport of the run postings (csrc/qf_wire.cu).  The end-to-end step is bound by the PCIe
+ * upload of 8 bytes per posting; dictionary-coded doc ids and 6-decimal scores need id_bits + sc_bits bits (22 + 20
+ * for the NQ shape: 5.25 bytes).  Posting i (row-major position in [Q][R][K]) occupies bits [i*W, (i+1)*W) of a
+ * little-endian uint64 stream, W = id_bits + sc_bits; low id_bits = doc id (>= 0), next sc_bits = micro - sc_base;
+ * positions beyond lens[q][r] are zero.  Lossless.  Sits between the packer above and qf_qpp_stats / qf_fuse; the
+ * reference has no counterpart (it reads its run files from disk, src/fusion.py:46-76).
+ *   qf_wire_plan   (host) : smallest id_bits / sc_bits / sc_base for the valid postings
+ *   qf_wire_words         : uint64 words of the stream (0 for a bad width: id_bits in [1,31], sc_bits in [1,32])
+ *   qf_wire_pack   (host, multi-threaded) : QF_E_INVALID if a value does not fit
+ *   qf_wire_unpack (device): expands into int32 doc_ids[n] / micro[n] (n = Q*R*K; 16-byte aligned)
+ * ---------------------------------------------------------------------------------------------- */
+QF_API size_t qf_wire_words(long long n, int id_bits, int sc_bits);
+QF_API int    qf_wire_plan(const int32_t* doc_ids, const int32_t* micro, const int32_t* lens, int Q, int R, int K,
+                           int n_threads, int* id_bits, int* sc_bits, int32_t* sc_base);
+QF_API int    qf_wire_pack(const int32_t* doc_ids, const int32_t* micro, const int32_t* lens, int Q, int R, int K,
+                           int id_bits, int sc_bits, int32_t sc_base, uint64_t* out, size_t out_words, int n_threads);
+QF_API int    qf_wire_unpack(const uint64_t* wire, long long n, int id_bits, int sc_bits, int32_t sc_base,
+                             int32_t* doc_ids, int32_t* micro, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * QPP statistics  --  replaces the JVM round trip QPPBridge.compute_batch -> qpp.QPPBridge

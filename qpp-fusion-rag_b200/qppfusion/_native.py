@@ -27,6 +27,7 @@ FLAG_MNZ_SKIP_ZERO, FLAG_REQUIRE_SORTED, FLAG_UNRANKED_OUTPUT = 1, 2, 4
 FLAG_LARGE_UNION = 8              # performance hint: little overlap between the runs (larger hash table)
 FLAG_DEBUG_FULLSORT = 0x100      # general kernel, 64-bit sort path (test hook)
 FLAG_DEBUG_GENERAL = 0x200       # skip the gather / streaming fusion kernels (test hook)
+FLAG_DEBUG_DEEP = 0x800         # ops.fuse: take qf_fuse_deep whatever the size (test hook; never reaches the library)
 FLAG_GATHER = 0x400              # opt-in: deposit + gather fusion kernel instead of the streaming one (same results)
 QSTAT_DUPLICATES, QSTAT_UNSORTED, QSTAT_BAD_LEN = 1, 2, 4
 QPP_BRIDGE_COLS, QPP_RESEARCH_COLS = 13, 5
@@ -53,6 +54,9 @@ PROTOTYPES = {
     "qf_profile_read": (_i, [_i, ctypes.POINTER(ctypes.c_float)]),
     "qf_fuse_max_postings": (_i, []),
     "qf_fuse": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _d, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "qf_fuse_deep_max_postings": (_i, []),
+    "qf_fuse_deep_workspace_bytes": (_sz, [_i, _i, _i]),
+    "qf_fuse_deep": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _d, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "qf_runs_parse": (_i, [_vp, _i, _i, _vp]),
     "qf_runs_free": (None, [_vp]),
     "qf_runs_info": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
@@ -60,6 +64,10 @@ PROTOTYPES = {
     "qf_runs_dict": (_i, [_vp, _i, _vp, _vp]),
     "qf_pack_weighted": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "qf_runfile_write": (_i, [ctypes.c_char_p, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, ctypes.c_char_p, _i]),
+    "qf_wire_words": (_sz, [ctypes.c_longlong, _i, _i]),
+    "qf_wire_plan": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "qf_wire_pack": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, ctypes.c_int32, _vp, _sz, _i]),
+    "qf_wire_unpack": (_i, [_vp, ctypes.c_longlong, _i, _i, ctypes.c_int32, _vp, _vp, _vp]),
     "qf_compact_workspace_bytes": (_sz, [_i]),
     "qf_compact_fused": (_i, [_vp, _vp, _vp, _i, ctypes.c_longlong, _vp, _vp, _vp, _vp, _sz, _vp]),
     "qf_qpp_stats": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),

@@ -142,17 +142,15 @@ def fuse_packed(packed: PackedRuns, method: int, weights: Optional[np.ndarray] =
     t = lambda a: None if a is None else torch.from_numpy(np.ascontiguousarray(a)).to(dev)
     shape_key = tuple(packed.doc_ids.shape[1:])
     r_, k_ = shape_key
-    max_post = int(N.lib().qf_fuse_max_postings())
-    if packed.scores.dtype == np.float64:
-        max_post = min(max_post, 5120)          # 8-byte scores: the wide (6 144-posting) kernel needs 4-byte scores
+    max_post = int(N.lib().qf_fuse_deep_max_postings())     # above qf_fuse's envelope ops.fuse takes qf_fuse_deep
     if r_ * k_ > max_post or r_ > 32:
         # K is the deepest (qid, ranker) list of the whole call (every list is padded to it): name it
         qi, ri = np.unravel_index(int(np.argmax(packed.lens)), packed.lens.shape)
         raise ValueError(
-            f"qf_fuse keeps one query's run lists in shared memory: rankers x depth = {r_} x {k_} = {r_ * k_} exceeds "
-            f"the envelope of {max_post} postings per query (and 32 rankers). The deepest list is "
-            f"ranker '{packed.rankers[ri]}' on query '{packed.qids[qi]}' with {int(packed.lens[qi, ri])} rows; cut the "
-            f"runs to depth <= {max_post // max(1, r_)} (e.g. top_k at retrieval time) or fuse fewer runs.")
+            f"qf_fuse: rankers x depth = {r_} x {k_} = {r_ * k_} exceeds the envelope of {max_post} postings per "
+            f"query (and 32 rankers). The deepest list is ranker '{packed.rankers[ri]}' on query "
+            f"'{packed.qids[qi]}' with {int(packed.lens[qi, ri])} rows; cut the runs to depth <= "
+            f"{max_post // max(1, r_)} (e.g. top_k at retrieval time) or fuse fewer runs.")
     out = ops.fuse(t(packed.doc_ids), t(packed.scores), t(packed.lens), t(weights), t(packed.ranks), method, norm,
                    rrf_k, flags | union_hint_flags(shape_key), want_counts, want_pos)
     status = out.status.cpu().numpy()

@@ -49,13 +49,30 @@ def _fuse_op(doc_ids: torch.Tensor, scores: torch.Tensor, lens: torch.Tensor,
     out_pos = torch.empty((Q, n) if want_pos else (0, n), dtype=torch.uint16, device=dev)
     out_lens = torch.empty((Q,), dtype=torch.int32, device=dev)
     out_status = torch.empty((Q,), dtype=torch.int32, device=dev)
+    deep = n > fuse_envelope(st) or bool(flags & N.FLAG_DEBUG_DEEP)
+    flags &= ~N.FLAG_DEBUG_DEEP
+    args = (N.ptr(doc_ids), N.ptr(scores), st, N.ptr(ranks), N.ptr(lens), N.ptr(weights),
+            Q, R, K, method, norm, float(rrf_k), flags, N.ptr(out_ids), N.ptr(out_scores),
+            N.ptr(out_counts) if want_counts else None, N.ptr(out_pos) if want_pos else None,
+            N.ptr(out_lens), N.ptr(out_status))
     with torch.cuda.device(dev):
-        N.check(N.lib().qf_fuse(N.ptr(doc_ids), N.ptr(scores), st, N.ptr(ranks), N.ptr(lens), N.ptr(weights),
-                                Q, R, K, method, norm, float(rrf_k), flags,
-                                N.ptr(out_ids), N.ptr(out_scores),
-                                N.ptr(out_counts) if want_counts else None, N.ptr(out_pos) if want_pos else None,
-                                N.ptr(out_lens), N.ptr(out_status), N.stream_ptr(dev)))
+        if deep:
+            # deeper than the shared-memory kernels: per-query state in a device workspace (qf_fuse_deep)
+            nbytes = N.lib().qf_fuse_deep_workspace_bytes(Q, R, K)
+            if nbytes == 0 and Q > 0:
+                raise ValueError(f"qf_fuse_deep: rankers x depth = {R} x {K} = {n} postings per query exceeds "
+                                 f"{N.lib().qf_fuse_deep_max_postings()} (and 32 rankers)")
+            ws = torch.empty((max(nbytes, 256),), dtype=torch.uint8, device=dev)
+            N.check(N.lib().qf_fuse_deep(*args, N.ptr(ws), nbytes, N.stream_ptr(dev)))
+        else:
+            N.check(N.lib().qf_fuse(*args, N.stream_ptr(dev)))
     return out_ids, out_scores, out_counts, out_pos, out_lens, out_status
+
+
+def fuse_envelope(score_type: int) -> int:
+    """Postings per query (R*K) the shared-memory kernels of qf_fuse take; above it ops.fuse calls qf_fuse_deep."""
+    cap = int(N.lib().qf_fuse_max_postings())
+    return min(cap, 5120) if score_type == N.SCORE_F64 else cap
 
 
 @_fuse_op.register_fake
@@ -98,6 +115,58 @@ def compact_fused(out: "FuseOut", cap: Optional[int] = None):
         N.check(N.lib().qf_compact_fused(N.ptr(out.ids), N.ptr(out.scores), N.ptr(out.lens), Q, stride, N.ptr(offsets),
                                          N.ptr(cids), N.ptr(csc), N.ptr(ws), nbytes, N.stream_ptr(dev)))
     return offsets, cids, csc
+
+
+# ---------------------------------------------------------------------------------------------- wire format
+class Wire(NamedTuple):
+    """Bit-packed postings (csrc/qf_wire.cu): `words` int64 [qf_wire_words] (host, optionally pinned, or device)."""
+    words: torch.Tensor
+    shape: Tuple[int, int, int]      # (Q, R, K) of the arrays it expands to
+    id_bits: int
+    sc_bits: int
+    sc_base: int
+
+    def to(self, device, non_blocking: bool = False) -> "Wire":
+        return self._replace(words=self.words.to(device, non_blocking=non_blocking))
+
+
+def wire_pack(doc_ids: torch.Tensor, micro: torch.Tensor, lens: torch.Tensor, pin: bool = False,
+              n_threads: int = 0, widths: Optional[Tuple[int, int, int]] = None) -> Wire:
+    """HOST side: int32 [Q, R, K] doc ids (dictionary codes >= 0) + int32 micro-unit scores + lens -> Wire.
+    widths = (id_bits, sc_bits, sc_base) fixes the layout (e.g. to refill one pinned buffer step after step);
+    default: the smallest that fits (qf_wire_plan)."""
+    import os
+    for t_ in (doc_ids, micro, lens):
+        if t_.is_cuda or t_.dtype != torch.int32 or not t_.is_contiguous():
+            raise TypeError("wire_pack takes contiguous int32 CPU tensors")
+    Q, R, K = doc_ids.shape
+    if micro.shape != doc_ids.shape or lens.shape != (Q, R):
+        raise ValueError("micro must have the shape of doc_ids, lens [Q, R]")
+    nt = n_threads or min(32, os.cpu_count() or 1)
+    if widths is None:
+        ib, sb, base = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_int32(0)
+        N.check(N.lib().qf_wire_plan(N.ptr(doc_ids), N.ptr(micro), N.ptr(lens), Q, R, K, nt, ctypes.addressof(ib),
+                                     ctypes.addressof(sb), ctypes.addressof(base)))
+        widths = (ib.value, sb.value, base.value)
+    ib_, sb_, base_ = (int(x) for x in widths)
+    nw = int(N.lib().qf_wire_words(Q * R * K, ib_, sb_))
+    if nw == 0:
+        raise ValueError(f"wire_pack: bad widths id_bits={ib_} sc_bits={sb_}")
+    words = torch.empty((nw,), dtype=torch.int64, pin_memory=pin)
+    N.check(N.lib().qf_wire_pack(N.ptr(doc_ids), N.ptr(micro), N.ptr(lens), Q, R, K, ib_, sb_, base_, N.ptr(words), nw, nt))
+    return Wire(words, (Q, R, K), ib_, sb_, base_)
+
+
+def wire_unpack_(wire: Wire, doc_ids: torch.Tensor, micro: torch.Tensor) -> None:
+    """DEVICE side: expand `wire` (words on the device) into the int32 [Q, R, K] tensors the kernels read (in place:
+    these are the static inputs of a FusionStepGraph)."""
+    dev = N.require_cuda(wire.words, doc_ids, micro)
+    if tuple(doc_ids.shape) != tuple(wire.shape) or micro.shape != doc_ids.shape or \
+            doc_ids.dtype != torch.int32 or micro.dtype != torch.int32:
+        raise TypeError("wire_unpack_: outputs must be int32 tensors of the wire's [Q, R, K] shape")
+    with torch.cuda.device(dev):
+        N.check(N.lib().qf_wire_unpack(N.ptr(wire.words), doc_ids.numel(), wire.id_bits, wire.sc_bits, wire.sc_base,
+                                       N.ptr(doc_ids), N.ptr(micro), N.stream_ptr(dev)))
 
 
 # ---------------------------------------------------------------------------------------------- qpp

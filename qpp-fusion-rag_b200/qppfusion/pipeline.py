@@ -24,9 +24,13 @@ class FusionStepGraph:
                  qpp_index: int = 5, top_k: int = 100, k_cut: int = 50, colnorm: Optional[str] = "minmax",
                  round6: bool = True, method: int = N.METHOD_SUM, norm: int = N.NORM_NONE, rrf_k: float = 60.0,
                  flags: int = 0, want_counts: bool = False, want_pos: bool = False, compact: bool = False,
-                 ranks: Optional[torch.Tensor] = None, warmup: int = 2):
+                 ranks: Optional[torch.Tensor] = None, warmup: int = 2, wire: Optional["ops.Wire"] = None):
+        """wire: a DEVICE ops.Wire whose words the step expands into doc_ids / scores first (qf_wire_unpack): the host
+        then refills `wire.words` (5.25 instead of 8 bytes per posting over PCIe for the NQ shape) instead of the
+        two int32 tensors."""
         self.dev = N.require_cuda(doc_ids, scores, lens, text_feats, ranks)
         self.inputs = (doc_ids, scores, lens, text_feats, ranks)
+        self.wire = wire
         self._cfg = dict(qpp_index=int(qpp_index), top_k=int(top_k), k_cut=int(k_cut), colnorm=colnorm,
                          round6=bool(round6), method=int(method), norm=int(norm), rrf_k=float(rrf_k), flags=int(flags),
                          want_counts=bool(want_counts), want_pos=bool(want_pos), compact=bool(compact))
@@ -55,6 +59,8 @@ class FusionStepGraph:
     def _body(self):
         ids, sc, lens, feats, ranks = self.inputs
         c = self._cfg
+        if self.wire is not None:
+            ops.wire_unpack_(self.wire, ids, sc)
         qpp, _status = ops.qpp_stats(sc, lens, feats, None, None, top_k=c["top_k"], k_cut=c["k_cut"])
         if c["colnorm"] or c["round6"]:
             ops.qpp_colnorm_(qpp, c["colnorm"] or "none", round6=c["round6"])
@@ -85,7 +91,7 @@ class ShardedFusionStep:
     def __init__(self, doc_ids, scores, lens, text_feats, *, group=None, qpp_index: int = 5, top_k: int = 100,
                  k_cut: int = 50, round6: bool = True, method: int = N.METHOD_SUM, rrf_k: float = 60.0, flags: int = 0,
                  ranks: Optional[torch.Tensor] = None, want_counts: bool = False, want_pos: bool = False,
-                 compact: bool = False):
+                 compact: bool = False, wire: Optional["ops.Wire"] = None):
         import torch.distributed as dist
         self.dev = N.require_cuda(doc_ids, scores, lens, text_feats, ranks)
         self.group, self._dist = group, dist
@@ -94,6 +100,8 @@ class ShardedFusionStep:
         side = torch.cuda.Stream(self.dev)
 
         def part_a():
+            if wire is not None:
+                ops.wire_unpack_(wire, ids, sc)
             qpp, _st = ops.qpp_stats(sc, ln, feats, None, None, top_k=top_k, k_cut=k_cut)
             st = ops.qpp_colstats(qpp)                                   # [R, C, 4] = min, max, sum, sumsq
             return qpp, torch.stack([-st[..., 0], st[..., 1]]).contiguous()

@@ -16,16 +16,17 @@ METHODS = {"sum": 0, "mnz": 1, "rrf": 2}
 EXTRA_FLAGS = [0]
 
 
-KERNEL_PATHS = {"stream": 0, "stream-large": 8, "gather": 0x400, "gather-large": 0x408, "general": 0x200}
+KERNEL_PATHS = {"stream": 0, "stream-large": 8, "gather": 0x400, "gather-large": 0x408, "general": 0x200, "deep": 0x800}
 
 
 @pytest.fixture(autouse=True, params=list(KERNEL_PATHS))
 def fuse_kernel_path(request):
-    """Every test runs five times: through the streaming kernel (+ general-kernel fix-up of deferred queries, the
+    """Every test runs six times: through the streaming kernel (+ general-kernel fix-up of deferred queries, the
     product path) and its larger-table configuration (QF_FLAG_LARGE_UNION, a performance hint that must not change any
     result), through the opt-in deposit + gather kernel (flag 0x400, round 2's measured alternative) in both table
-    sizes, and with both disabled (debug flag 0x200: general kernel alone), so all kernels keep full parity
-    coverage."""
+    sizes, with both disabled (debug flag 0x200: general kernel alone), and through qf_fuse_deep (ops-level test flag
+    0x800: the workspace-resident kernel for requests above the shared-memory envelope), so all kernels keep full
+    parity coverage."""
     EXTRA_FLAGS[0] = KERNEL_PATHS[request.param]
     yield
     EXTRA_FLAGS[0] = 0
@@ -400,13 +401,44 @@ def test_repeated_launches_are_bitwise_identical():
 
 def test_six_runs_of_depth_1000_fit_the_wide_general_kernel():
     """6 retrievers x TREC depth 1000 = 6 000 postings per query worked in the reference and failed here.
-    4-byte scores now go up to 6 144 postings per query (general kernel alone); float64 scores stop at 5 120 with a
-    message that says so."""
-    from qppfusion import _native as N
+    4-byte scores go up to 6 144 postings per query in shared memory (general kernel alone); float64 scores above
+    5 120 take qf_fuse_deep (round 2) instead of raising."""
     lists = synth_lists(51, n_q=6, n_r=6, k=1000, pool=2600, ties=True)
     w = np.round(np.random.default_rng(2).random((6, 6)), 6)
     for method in ("sum", "mnz", "rrf"):
         out = run_gpu(lists, method, w, k=1000, score_type="micro")
         check_against_oracle(lists, method, w, out)
-    with pytest.raises(N.NativeError, match="5120"):
-        run_gpu(lists, "sum", w, k=1000, score_type="f64")
+    out = run_gpu(lists, "sum", w, k=1000, score_type="f64")
+    check_against_oracle(lists, "sum", w, out)
+
+
+@pytest.mark.parametrize("n_r,k", [(8, 2000), (20, 1000), (32, 2047)])
+def test_deep_runs_beyond_the_shared_memory_envelope(n_r, k):
+    """the reference fuses arbitrary depth.  16 000 / 20 000 / 65 504 postings per query go through
+    qf_fuse_deep (hash table and sort buffers in a device workspace): weighted sum / mnz / rrf with ties, a duplicate
+    doc id inside a list, ragged and empty lists, and the ranx semantics (min-max, z-score, REQUIRE_SORTED), bit-exact."""
+    if EXTRA_FLAGS[0] not in (0, 0x800):
+        pytest.skip("size-routed: the kernel-path flags do not apply")
+    nq = 3
+    lists = synth_lists(60 + n_r, n_q=nq, n_r=n_r, k=k, pool=int(2.4 * k), ragged=True, ties=True, neg_ranker=1)
+    lists[1][2] = []
+    rl = max(range(n_r), key=lambda r: len(lists[2][r]))
+    d0 = lists[2][rl][3][0]
+    lists[2][rl][40] = (d0, lists[2][rl][40][1], lists[2][rl][40][2])       # duplicate inside one list
+    w = np.round(np.random.default_rng(5).random((nq, n_r)), 6)
+    for method in ("sum", "mnz", "rrf"):
+        out = run_gpu(lists, method, w, k=k, score_type="micro" if method != "mnz" else "f64")
+        check_against_oracle(lists, method, w, out)
+        assert out[5][2] & 1 and not (out[5][0] & 1)
+    clean = synth_lists(90 + n_r, n_q=2, n_r=n_r, k=k, pool=int(2.4 * k), ragged=True, ties=True)
+    for method, norm in (("sum", 1), ("mnz", 2), ("rrf", 0)):
+        out = run_gpu(clean, method, None, norm=norm, flags=2, k=k)
+        check_against_oracle(clean, method, None, out, ranx=True, norm="zscore" if norm == 2 else "min-max")
+
+
+def test_deep_limit_is_reported():
+    from qppfusion import ops
+    dev = torch.device("cuda:0")
+    ids = torch.zeros((1, 33, 2000), dtype=torch.int32, device=dev)
+    with pytest.raises(ValueError, match="65535"):
+        ops.fuse(ids, ids.clone(), torch.zeros((1, 33), dtype=torch.int32, device=dev))
