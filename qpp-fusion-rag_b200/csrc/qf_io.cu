@@ -17,24 +17,21 @@
 #include <cstring>
 #include <string>
 #include <thread>
+#include <utility>
 #include <vector>
+#include <chrono>
 
 #include "qf_common.cuh"
+static double now_ms(){return std::chrono::duration<double,std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();}
+static bool g_trace = getenv("QF_IO_TRACE")!=nullptr;
+#define TR(label) do{ if(g_trace){ double t_=now_ms(); fprintf(stderr,"  [io] %-18s %.1f ms\n", label, t_-t_last); t_last=t_; } }while(0)
+
 
 namespace {
 
 struct Tok {
   const char* p;
   int len;
-};
-
-struct Row {
-  Tok qid, doc;
-  uint64_t doc_hash;
-  int32_t rank;
-  int32_t micro;
-  double score;
-  bool micro_ok;
 };
 
 inline bool is_ws(char c) { return c == ' ' || c == '\t' || c == '\r' || c == '\f' || c == '\v'; }
@@ -68,26 +65,82 @@ inline bool parse_micro(const char* s, int len, int32_t* out) {
   return true;
 }
 
+// Large uninitialised buffers: anonymous mappings with transparent huge pages requested, so that the first touch
+// (by the parser threads, spread over all cores) costs one fault per 2 MB instead of one per 4 KB -- on a cold call the
+// 4 KB faults of the column arrays used to cost more than the parsing itself.
+template <typename T>
+struct Big {
+  T* p = nullptr;
+  size_t n = 0, bytes = 0;
+  bool mapped = false;
+  Big() = default;
+  Big(const Big&) = delete;
+  Big& operator=(const Big&) = delete;
+  Big(Big&& o) noexcept { *this = std::move(o); }
+  Big& operator=(Big&& o) noexcept {
+    if (this != &o) {
+      release();
+      p = o.p; n = o.n; bytes = o.bytes; mapped = o.mapped;
+      o.p = nullptr; o.n = o.bytes = 0;
+    }
+    return *this;
+  }
+  ~Big() { release(); }
+  void release() {
+    if (!p) return;
+    if (mapped) munmap(p, bytes); else free(p);
+    p = nullptr;
+    n = bytes = 0;
+  }
+  bool alloc(size_t count) {
+    release();
+    n = count;
+    bytes = count * sizeof(T);
+    if (bytes == 0) { bytes = sizeof(T); }
+    if (bytes >= (size_t(4) << 20)) {
+      bytes = (bytes + (size_t(2) << 20) - 1) & ~((size_t(2) << 20) - 1);
+      void* m = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+      if (m == MAP_FAILED) { p = nullptr; return false; }
+#ifdef MADV_HUGEPAGE
+      if (!getenv("QF_IO_NOHUGE")) madvise(m, bytes, MADV_HUGEPAGE);
+#endif
+      p = static_cast<T*>(m);
+      mapped = true;
+    } else {
+      p = static_cast<T*>(malloc(bytes));
+      mapped = false;
+    }
+    return p != nullptr;
+  }
+  T* data() { return p; }
+  const T* data() const { return p; }
+  size_t size() const { return n; }
+  T& operator[](size_t i) { return p[i]; }
+  const T& operator[](size_t i) const { return p[i]; }
+};
+
 struct Dict {
-  // open addressing over (hash, arena offset, length); arena stores the strings back to back
+  // open addressing; a slot holds (entry, upper hash half), so a probe touches the table line and, on a tag match,
+  // the arena -- not a third array.  The arena stores the strings back to back.
+  struct Slot { int32_t e; uint32_t tag; };
   std::vector<uint64_t> hashes;
-  std::vector<int32_t> slots;   // index into entries or -1
+  std::vector<Slot> slots;
   std::vector<int64_t> off;     // entry -> arena offset (off.size() == n+1)
   std::string arena;
   size_t mask = 0;
-  Dict() { rehash(1 << 16); off.push_back(0); }
+  Dict() { rehash(1 << 10); off.push_back(0); }
   static uint64_t hash(const char* p, int len) {
     uint64_t h = 1469598103934665603ull;
     for (int i = 0; i < len; ++i) { h ^= (unsigned char)p[i]; h *= 1099511628211ull; }
     return h ^ (h >> 29);
   }
   void rehash(size_t cap) {
-    std::vector<int32_t> ns(cap, -1);
+    std::vector<Slot> ns(cap, Slot{-1, 0u});
     const size_t nm = cap - 1;
     for (size_t e = 0; e < hashes.size(); ++e) {
       size_t i = hashes[e] & nm;
-      while (ns[i] >= 0) i = (i + 1) & nm;
-      ns[i] = (int32_t)e;
+      while (ns[i].e >= 0) i = (i + 1) & nm;
+      ns[i] = Slot{(int32_t)e, (uint32_t)(hashes[e] >> 32)};
     }
     slots.swap(ns);
     mask = nm;
@@ -96,17 +149,18 @@ struct Dict {
   int32_t get(const char* p, int len) { return get_hashed(p, len, hash(p, len)); }
   int32_t get_hashed(const char* p, int len, uint64_t h) {
     size_t i = h & mask;
+    const uint32_t tag = (uint32_t)(h >> 32);
     while (true) {
-      const int32_t e = slots[i];
-      if (e < 0) break;
-      if (hashes[e] == h && off[e + 1] - off[e] == len && memcmp(arena.data() + off[e], p, (size_t)len) == 0) return e;
+      const Slot s = slots[i];
+      if (s.e < 0) break;
+      if (s.tag == tag && off[s.e + 1] - off[s.e] == len && memcmp(arena.data() + off[s.e], p, (size_t)len) == 0) return s.e;
       i = (i + 1) & mask;
     }
     const int32_t e = (int32_t)hashes.size();
     hashes.push_back(h);
     arena.append(p, (size_t)len);
     off.push_back((int64_t)arena.size());
-    slots[i] = e;
+    slots[i] = Slot{e, tag};
     if (hashes.size() * 2 > slots.size()) rehash(slots.size() * 2);
     return e;
   }
@@ -114,8 +168,9 @@ struct Dict {
 };
 
 struct FileRows {
-  std::vector<int32_t> qid, doc, rank, micro;
-  std::vector<double> score;
+  Big<int32_t> qid, doc, rank, micro;
+  Big<double> score;
+  size_t n = 0;
 };
 
 constexpr int DOC_SHARDS = 256;        // docno dictionary shards (top 8 bits of the hash), each owned by one thread
@@ -154,66 +209,108 @@ inline bool parse_int(const char* s, int len, int32_t* out) {
   return true;
 }
 
-// `owned[t]` collects the indices of this chunk's rows whose docno shard belongs to thread t (phase 3 then touches
-// only its own rows instead of scanning everybody's)
-bool parse_chunk(const char* b, const char* e, std::vector<Row>& rows, std::vector<std::vector<uint32_t>>& owned, int nt,
-                 std::string& err) {
-  rows.reserve((size_t)(e - b) / 32 + 16);
-  owned.assign((size_t)nt, std::vector<uint32_t>());
-  for (auto& o : owned) o.reserve((size_t)(e - b) / 32 / (size_t)nt + 16);
+struct QStart {            // first row (chunk-local index) of a run of rows with the same qid token
+  uint32_t row;
+  Tok tok;
+  int32_t code;
+};
+
+// Per-file transient row data the docno phase needs (the numeric columns are written straight into FileRows).
+struct DocTok {
+  const char* p;
+  uint64_t hash;
+  int32_t len;
+};
+
+struct Chunk {
+  const char *b, *e;
+  size_t cap = 0, rows = 0, off = 0;          // line count bound, parsed rows, first row in the file's columns
+  std::vector<QStart> qstarts;
+  std::vector<std::vector<uint32_t>> owned;   // owned[t]: chunk-local rows whose docno shard belongs to thread t
+  bool micro_bad = false;
+  std::string err;
+};
+
+size_t count_lines(const char* b, const char* e) {
+  size_t n = 0;
   const char* p = b;
   while (p < e) {
-    const char* eol = (const char*)memchr(p, '\n', (size_t)(e - p));
-    if (!eol) eol = e;
+    const char* nl = (const char*)memchr(p, '\n', (size_t)(e - p));
+    ++n;
+    if (!nl) break;
+    p = nl + 1;
+  }
+  return n;
+}
+
+// Tokenise + convert one chunk straight into the file's columns at [c.off, c.off + c.cap).
+bool parse_chunk(Chunk& c, FileRows& F, DocTok* dt, int nt) {
+  c.owned.assign((size_t)nt, std::vector<uint32_t>());
+  for (auto& o : c.owned) o.reserve(c.cap / (size_t)nt + c.cap / (size_t)(8 * nt) + 16);
+  int32_t* rank = F.rank.data() + c.off;
+  int32_t* micro = F.micro.data() + c.off;
+  double* score = F.score.data() + c.off;
+  DocTok* d = dt + c.off;
+  Tok last_q{nullptr, 0};
+  size_t n = 0;
+  const char* p = c.b;
+  while (p < c.e) {
+    const char* eol = (const char*)memchr(p, '\n', (size_t)(c.e - p));
+    if (!eol) eol = c.e;
     Tok f[6];
     int nf = 0;
-    const char* c = p;
-    while (c < eol && nf < 6) {
-      while (c < eol && is_ws(*c)) ++c;
-      if (c >= eol) break;
-      const char* s = c;
-      while (c < eol && !is_ws(*c)) ++c;
-      f[nf].p = s;
-      f[nf].len = (int)(c - s);
+    const char* s = p;
+    while (s < eol && nf < 6) {
+      while (s < eol && is_ws(*s)) ++s;
+      if (s >= eol) break;
+      const char* t0 = s;
+      while (s < eol && !is_ws(*s)) ++s;
+      f[nf].p = t0;
+      f[nf].len = (int)(s - t0);
       ++nf;
     }
     if (nf >= 5) {
-      Row r;
-      r.qid = f[0];
-      r.doc = f[2];
-      r.doc_hash = Dict::hash(f[2].p, f[2].len);
+      if (!last_q.p || f[0].len != last_q.len || memcmp(f[0].p, last_q.p, (size_t)f[0].len) != 0) {
+        c.qstarts.push_back(QStart{(uint32_t)n, f[0], -1});
+        last_q = f[0];
+      }
+      const uint64_t h = Dict::hash(f[2].p, f[2].len);
+      d[n] = DocTok{f[2].p, h, f[2].len};
       char buf[64];
       char* endp = nullptr;
-      if (!parse_int(f[3].p, f[3].len, &r.rank)) {
+      if (!parse_int(f[3].p, f[3].len, &rank[n])) {
         const int rl = f[3].len < 63 ? f[3].len : 63;
         memcpy(buf, f[3].p, (size_t)rl);
         buf[rl] = 0;
         const long rk = strtol(buf, &endp, 10);
-        if (*endp != 0 || rk < -2147483647L || rk > 2147483647L) { err = "bad rank field '" + std::string(buf) + "'"; return false; }
-        r.rank = (int32_t)rk;
+        if (*endp != 0 || rk < -2147483647L || rk > 2147483647L) { c.err = "bad rank field '" + std::string(buf) + "'"; return false; }
+        rank[n] = (int32_t)rk;
       }
-      r.micro_ok = parse_micro(f[4].p, f[4].len, &r.micro);
-      if (r.micro_ok) {
+      int32_t mi = 0;
+      if (parse_micro(f[4].p, f[4].len, &mi)) {
         // <= 6 decimals: the value is micro / 10^6 exactly, and the IEEE quotient of two exactly representable
         // numbers is the double nearest to it -- the same double strtod returns (sign of a zero kept)
-        r.score = (double)r.micro / 1.0e6;
-        if (r.micro == 0 && f[4].p[0] == '-') r.score = -0.0;
+        micro[n] = mi;
+        score[n] = (mi == 0 && f[4].p[0] == '-') ? -0.0 : (double)mi / 1.0e6;
       } else {
-        r.micro = 0;
+        c.micro_bad = true;
+        micro[n] = 0;
         const int sl = f[4].len < 63 ? f[4].len : 63;
         memcpy(buf, f[4].p, (size_t)sl);
         buf[sl] = 0;
-        r.score = strtod(buf, &endp);
-        if (*endp != 0) { err = "bad score field '" + std::string(buf) + "'"; return false; }
+        score[n] = strtod(buf, &endp);
+        if (*endp != 0) { c.err = "bad score field '" + std::string(buf) + "'"; return false; }
       }
-      owned[(size_t)(doc_shard(r.doc_hash) % nt)].push_back((uint32_t)rows.size());
-      rows.push_back(r);
+      c.owned[(size_t)(doc_shard(h) % nt)].push_back((uint32_t)n);
+      ++n;
     } else if (nf != 0) {
-      err = "line with " + std::to_string(nf) + " fields (need >= 5)";
+      // a short line is rejected, not padded with NaN as pandas would: a run file with a truncated line is broken
+      c.err = "line with " + std::to_string(nf) + " fields (need >= 5)";
       return false;
     }
     p = eol + 1;
   }
+  c.rows = n;
   return true;
 }
 
@@ -231,95 +328,111 @@ extern "C" int qf_runs_parse(const char* const* paths, int n_files, int n_thread
   QF_REQUIRE(paths && out && n_files >= 1, QF_E_INVALID, "qf_runs_parse: bad arguments");
   if (n_threads < 1) n_threads = 1;
   if (n_threads > DOC_SHARDS) n_threads = DOC_SHARDS;
+  double t_last = now_ms();
   qf_runs* R = new qf_runs();
   R->files.resize((size_t)n_files);
+  TR("ctor");
+  auto fail = [&](int code, const char* fmt, const char* a, const char* b) {
+    qf::set_error(fmt, a, b);
+    delete R;
+    return code;
+  };
   for (int fi = 0; fi < n_files; ++fi) {
     const int fd = open(paths[fi], O_RDONLY);
-    if (fd < 0) { qf::set_error("qf_runs_parse: cannot open %s", paths[fi]); delete R; return QF_E_INVALID; }
+    if (fd < 0) return fail(QF_E_INVALID, "qf_runs_parse: cannot open %s%s", paths[fi], "");
     struct stat st;
-    fstat(fd, &st);
+    if (fstat(fd, &st) != 0) { close(fd); return fail(QF_E_INVALID, "qf_runs_parse: cannot stat %s%s", paths[fi], ""); }
     const size_t sz = (size_t)st.st_size;
-    const char* base = sz ? (const char*)mmap(nullptr, sz, PROT_READ, MAP_PRIVATE, fd, 0) : nullptr;
-    if (sz && base == MAP_FAILED) { close(fd); qf::set_error("qf_runs_parse: mmap failed for %s", paths[fi]); delete R; return QF_E_INVALID; }
-    // 1. split at newline boundaries, tokenise + convert numbers in parallel
+    const char* base = sz ? (const char*)mmap(nullptr, sz, PROT_READ, MAP_PRIVATE | MAP_POPULATE, fd, 0) : nullptr;
+    if (sz && base == MAP_FAILED) { close(fd); return fail(QF_E_INVALID, "qf_runs_parse: mmap failed for %s%s", paths[fi], ""); }
+    auto unmap = [&]() { if (sz) munmap((void*)base, sz); close(fd); };
+    // 1. split at newline boundaries; count the lines of every chunk (bound on its rows) so that the columns can be
+    //    allocated once and written in place
     const int nt = sz < (1u << 20) ? 1 : n_threads;
-    std::vector<const char*> cut((size_t)nt + 1);
-    cut[0] = base;
-    cut[(size_t)nt] = base + sz;
-    for (int t = 1; t < nt; ++t) {
-      const char* p = base + sz * (size_t)t / (size_t)nt;
-      const char* nl = (const char*)memchr(p, '\n', (size_t)(base + sz - p));
-      cut[(size_t)t] = nl ? nl + 1 : base + sz;
+    std::vector<Chunk> chunks((size_t)nt);
+    {
+      std::vector<const char*> cut((size_t)nt + 1);
+      cut[0] = base;
+      cut[(size_t)nt] = base + sz;
+      for (int t = 1; t < nt; ++t) {
+        const char* p = base + sz * (size_t)t / (size_t)nt;
+        const char* nl = (const char*)memchr(p, '\n', (size_t)(base + sz - p));
+        cut[(size_t)t] = nl ? nl + 1 : base + sz;
+      }
+      for (int t = 0; t < nt; ++t) { chunks[(size_t)t].b = cut[(size_t)t]; chunks[(size_t)t].e = cut[(size_t)t + 1]; }
     }
-    std::vector<std::vector<Row>> parts((size_t)nt);
-    std::vector<std::vector<std::vector<uint32_t>>> owned((size_t)nt);
-    std::vector<std::string> errs((size_t)nt);
+    parallel_for(nt, [&](int t) { chunks[(size_t)t].cap = count_lines(chunks[(size_t)t].b, chunks[(size_t)t].e); });
+    TR("mmap+count");
+    size_t cap = 0;
+    for (auto& c : chunks) { c.off = cap; cap += c.cap; }
+    FileRows& F = R->files[(size_t)fi];
+    Big<DocTok> dt;
+    if (!F.qid.alloc(cap) || !F.doc.alloc(cap) || !F.rank.alloc(cap) || !F.micro.alloc(cap) || !F.score.alloc(cap) || !dt.alloc(cap)) {
+      unmap();
+      return fail(QF_E_INVALID, "qf_runs_parse: out of memory for %s%s", paths[fi], "");
+    }
+    TR("alloc");
+    // 2. tokenise + convert numbers in parallel, straight into the columns
     std::vector<char> ok((size_t)nt, 1);
-    parallel_for(nt, [&](int t) {
-      ok[(size_t)t] = parse_chunk(cut[(size_t)t], cut[(size_t)t + 1], parts[(size_t)t], owned[(size_t)t], nt,
-                                  errs[(size_t)t]) ? 1 : 0;
-    });
+    parallel_for(nt, [&](int t) { ok[(size_t)t] = parse_chunk(chunks[(size_t)t], F, dt.data(), nt) ? 1 : 0; });
     for (int t = 0; t < nt; ++t)
       if (!ok[(size_t)t]) {
-        qf::set_error("qf_runs_parse: %s: %s", paths[fi], errs[(size_t)t].c_str());
-        if (sz) munmap((void*)base, sz);
-        close(fd);
-        delete R;
-        return QF_E_INVALID;
+        const std::string e = chunks[(size_t)t].err;
+        unmap();
+        return fail(QF_E_INVALID, "qf_runs_parse: %s: %s", paths[fi], e.c_str());
       }
-    std::vector<size_t> part_off((size_t)nt + 1, 0);
-    for (int t = 0; t < nt; ++t) part_off[(size_t)t + 1] = part_off[(size_t)t] + parts[(size_t)t].size();
-    const size_t n = part_off[(size_t)nt];
-    FileRows& F = R->files[(size_t)fi];
-    F.qid.resize(n); F.doc.resize(n); F.rank.resize(n); F.micro.resize(n); F.score.resize(n);
-    // 2. qid codes: serial, but almost every row repeats the previous row's qid (one memcmp)
-    {
-      Tok last_q{nullptr, 0};
-      int32_t last_qi = -1;
-      for (int t = 0; t < nt; ++t) {
-        const std::vector<Row>& v = parts[(size_t)t];
-        int32_t* dst = F.qid.data() + part_off[(size_t)t];
-        for (size_t ri = 0; ri < v.size(); ++ri) {
-          const Row& r = v[ri];
-          if (last_qi < 0 || r.qid.len != last_q.len || memcmp(r.qid.p, last_q.p, (size_t)r.qid.len) != 0) {
-            last_qi = R->qids.get(r.qid.p, r.qid.len);
-            last_q = r.qid;
-          }
-          dst[ri] = last_qi;
-        }
+    TR("tokenise");
+    // blank lines leave gaps between the chunks' rows: close them (rare; the common file has none)
+    size_t n = 0;
+    for (auto& c : chunks) {
+      if (c.off != n) {
+        memmove(F.rank.data() + n, F.rank.data() + c.off, c.rows * 4);
+        memmove(F.micro.data() + n, F.micro.data() + c.off, c.rows * 4);
+        memmove(F.score.data() + n, F.score.data() + c.off, c.rows * 8);
+        memmove(dt.data() + n, dt.data() + c.off, c.rows * sizeof(DocTok));
+        c.off = n;
       }
+      n += c.rows;
+      if (c.micro_bad) R->all_micro = false;
     }
-    // 3. numeric columns (chunk-parallel) and docno codes (shard-parallel: thread t owns the dictionary shards
-    //    s with s % nt == t and visits the rows in file order, so codes are deterministic)
-    std::vector<char> micro_bad((size_t)nt, 0);
+    F.n = n;
+    // 3. qid codes: only the first row of every run of equal qids goes through the dictionary (serial, in file
+    //    order, so codes are first-seen ordered); the runs are filled in parallel
+    for (auto& c : chunks)
+      for (auto& q : c.qstarts) q.code = R->qids.get(q.tok.p, q.tok.len);
+    TR("qid serial");
+    // 4. qid fill + docno codes (shard-parallel: thread t owns the dictionary shards s with s % nt == t and visits
+    //    the rows in file order, so codes are deterministic)
     parallel_for(nt, [&](int t) {
-      const std::vector<Row>& mine = parts[(size_t)t];
-      const size_t o = part_off[(size_t)t];
-      for (size_t ri = 0; ri < mine.size(); ++ri) {
-        F.rank[o + ri] = mine[ri].rank;
-        F.micro[o + ri] = mine[ri].micro;
-        F.score[o + ri] = mine[ri].score;
-        if (!mine[ri].micro_ok) micro_bad[(size_t)t] = 1;
+      Chunk& c = chunks[(size_t)t];
+      int32_t* qd = F.qid.data() + c.off;
+      for (size_t k = 0; k < c.qstarts.size(); ++k) {
+        const size_t r0 = c.qstarts[k].row, r1 = k + 1 < c.qstarts.size() ? c.qstarts[k + 1].row : c.rows;
+        const int32_t code = c.qstarts[k].code;
+        for (size_t r = r0; r < r1; ++r) qd[r] = code;
       }
       for (int pt = 0; pt < nt; ++pt) {
-        const std::vector<Row>& v = parts[(size_t)pt];
-        const std::vector<uint32_t>& idx = owned[(size_t)pt][(size_t)t];
-        int32_t* dst = F.doc.data() + part_off[(size_t)pt];
+        const Chunk& pc = chunks[(size_t)pt];
+        const std::vector<uint32_t>& idx = pc.owned[(size_t)t];
+        const DocTok* v = dt.data() + pc.off;
+        int32_t* dst = F.doc.data() + pc.off;
         for (size_t k = 0; k < idx.size(); ++k) {
-          const Row& r = v[idx[k]];
-          const int s_ = doc_shard(r.doc_hash);
-          if (k + 8 < idx.size()) R->doc_shards[(size_t)doc_shard(v[idx[k + 8]].doc_hash)].prefetch(v[idx[k + 8]].doc_hash);
-          const int32_t code = R->doc_shards[(size_t)s_].get_hashed(r.doc.p, r.doc.len, r.doc_hash);
+          const DocTok& r = v[idx[k]];
+          const int s_ = doc_shard(r.hash);
+          if (k + 8 < idx.size()) {
+            const DocTok& nx = v[idx[k + 8]];
+            R->doc_shards[(size_t)doc_shard(nx.hash)].prefetch(nx.hash);
+          }
+          const int32_t code = R->doc_shards[(size_t)s_].get_hashed(r.p, r.len, r.hash);
           dst[idx[k]] = (int32_t)(((uint32_t)s_ << LOCAL_BITS) | (uint32_t)code);
         }
       }
     });
-    for (int t = 0; t < nt; ++t)
-      if (micro_bad[(size_t)t]) R->all_micro = false;
-    if (sz) munmap((void*)base, sz);
-    close(fd);
+    TR("docno dict");
+    unmap();
+    TR("unmap");
   }
-  // 4. shard bases, merged dictionary, final codes
+  // 5. shard bases, merged dictionary, final codes
   R->shard_base.assign(DOC_SHARDS + 1, 0);
   for (int s_ = 0; s_ < DOC_SHARDS; ++s_) {
     if (R->doc_shards[(size_t)s_].size() >= (1 << LOCAL_BITS)) {
@@ -330,22 +443,25 @@ extern "C" int qf_runs_parse(const char* const* paths, int n_files, int n_thread
     R->shard_base[(size_t)s_ + 1] = R->shard_base[(size_t)s_] + R->doc_shards[(size_t)s_].size();
   }
   {
-    size_t bytes = 0;
-    for (auto& d : R->doc_shards) bytes += d.arena.size();
-    R->doc_arena.reserve(bytes);
-    R->doc_off.reserve((size_t)R->shard_base[DOC_SHARDS] + 1);
-    R->doc_off.push_back(0);
-    for (auto& d : R->doc_shards) {
-      const int64_t at = (int64_t)R->doc_arena.size();
-      R->doc_arena.append(d.arena);
-      for (size_t e = 1; e < d.off.size(); ++e) R->doc_off.push_back(at + d.off[e]);
-      Dict().hashes.swap(d.hashes);          // the shard tables are no longer needed
-      std::vector<int32_t>().swap(d.slots);
-      std::string().swap(d.arena);
-    }
+    std::vector<size_t> at((size_t)DOC_SHARDS + 1, 0);
+    for (int s_ = 0; s_ < DOC_SHARDS; ++s_) at[(size_t)s_ + 1] = at[(size_t)s_] + R->doc_shards[(size_t)s_].arena.size();
+    R->doc_arena.resize(at[DOC_SHARDS]);
+    R->doc_off.resize((size_t)R->shard_base[DOC_SHARDS] + 1);
+    R->doc_off[0] = 0;
+    parallel_for(n_threads, [&](int t) {
+      for (int s_ = t; s_ < DOC_SHARDS; s_ += n_threads) {
+        Dict& d = R->doc_shards[(size_t)s_];
+        memcpy(&R->doc_arena[at[(size_t)s_]], d.arena.data(), d.arena.size());
+        int64_t* o = R->doc_off.data() + R->shard_base[(size_t)s_];
+        for (size_t e = 1; e < d.off.size(); ++e) o[e] = (int64_t)at[(size_t)s_] + d.off[e];
+        std::vector<uint64_t>().swap(d.hashes);          // the shard tables are no longer needed
+        std::vector<Dict::Slot>().swap(d.slots);
+        std::string().swap(d.arena);
+      }
+    });
   }
   for (auto& F : R->files) {
-    const size_t n = F.doc.size();
+    const size_t n = F.n;
     const int nt = n < (1u << 16) ? 1 : n_threads;
     parallel_for(nt, [&](int t) {
       const size_t i0 = n * (size_t)t / (size_t)nt, i1 = n * (size_t)(t + 1) / (size_t)nt;
@@ -355,6 +471,7 @@ extern "C" int qf_runs_parse(const char* const* paths, int n_files, int n_thread
       }
     });
   }
+  TR("merge+recode");
   *out = R;
   return QF_OK;
 }
@@ -365,7 +482,7 @@ extern "C" int qf_runs_info(const qf_runs* r, int64_t* rows_per_file, int32_t* n
                             int64_t* qid_arena_bytes, int64_t* doc_arena_bytes) {
   QF_REQUIRE(r, QF_E_INVALID, "qf_runs_info: null handle");
   if (rows_per_file)
-    for (size_t i = 0; i < r->files.size(); ++i) rows_per_file[i] = (int64_t)r->files[i].qid.size();
+    for (size_t i = 0; i < r->files.size(); ++i) rows_per_file[i] = (int64_t)r->files[i].n;
   if (n_qids) *n_qids = r->qids.size();
   if (n_docs) *n_docs = (int32_t)(r->doc_off.size() - 1);
   if (all_micro) *all_micro = r->all_micro ? 1 : 0;
@@ -379,7 +496,7 @@ extern "C" int qf_runs_rows(const qf_runs* r, int file, int32_t* qid_idx, int32_
                             double* score) {
   QF_REQUIRE(r && file >= 0 && (size_t)file < r->files.size(), QF_E_INVALID, "qf_runs_rows: bad arguments");
   const FileRows& F = r->files[(size_t)file];
-  const size_t n = F.qid.size();
+  const size_t n = F.n;
   if (qid_idx) memcpy(qid_idx, F.qid.data(), n * 4);
   if (doc_idx) memcpy(doc_idx, F.doc.data(), n * 4);
   if (rank) memcpy(rank, F.rank.data(), n * 4);
@@ -450,7 +567,7 @@ inline int fmt_uint(char* out, unsigned long long v) {
   return n;
 }
 inline int fmt_fixed6(char* out, double x) {
-  if (!(std::fabs(x) < 1.0e9)) return snprintf(out, 48, "%.6f", x);
+  if (!(std::fabs(x) < 1.0e9)) return snprintf(out, 400, "%.6f", x);   // (the writer reserves 400 bytes for each)
   const bool neg = std::signbit(x);
   const double a = std::fabs(x);
   const double pr = a * 1.0e6;
@@ -485,46 +602,78 @@ extern "C" int qf_runfile_write(const char* path, const char* qid_arena, const i
              QF_E_INVALID, "qf_runfile_write: bad arguments");
   if (n_threads < 1) n_threads = 1;
   if (n_threads > n_queries) n_threads = n_queries > 0 ? n_queries : 1;
-  std::vector<std::string> bufs((size_t)n_threads);
-  std::vector<std::thread> th;
   const size_t tag_len = strlen(tag);
+  // Every thread formats a contiguous range of queries into its own buffer (sized by an upper bound per line; the
+  // untouched tail of the anonymous mapping costs nothing) and then writes it at its final file offset with pwrite,
+  // so neither the formatting nor the copy into the page cache is serial.
+  struct Part { Big<char> buf; size_t used = 0; int bad = 0; };
+  std::vector<Part> parts((size_t)n_threads);
+  auto range = [&](int t, int& j0, int& j1) {
+    j0 = (int)((long long)n_queries * t / n_threads);
+    j1 = (int)((long long)n_queries * (t + 1) / n_threads);
+  };
+  parallel_for(n_threads, [&](int t) {
+    int j0, j1;
+    range(t, j0, j1);
+    Part& P = parts[(size_t)t];
+    size_t bound = 0;
+    for (int j = j0; j < j1; ++j) {
+      const int q = qsel[j];
+      const size_t ql = (size_t)(qid_off[q + 1] - qid_off[q]);
+      size_t docs = 0;
+      for (int64_t e = offsets[q]; e < offsets[q + 1]; ++e) {
+        docs += (size_t)(doc_off[ids[e] + 1] - doc_off[ids[e]]);
+        if (!(std::fabs(scores[e]) < 1.0e9)) docs += 400;       // "%.6f" of a huge double is up to ~320 characters
+      }
+      bound += docs + (size_t)(offsets[q + 1] - offsets[q]) * (ql + 4 + 1 + 11 + 1 + 48 + 1 + tag_len + 1);
+    }
+    if (!P.buf.alloc(bound + 64)) { P.bad = 1; return; }
+    char* o = P.buf.data();
+    for (int j = j0; j < j1; ++j) {
+      const int q = qsel[j];
+      const char* qs = qid_arena + qid_off[q];
+      const size_t ql = (size_t)(qid_off[q + 1] - qid_off[q]);
+      unsigned long long rank = 1;
+      for (int64_t e = offsets[q]; e < offsets[q + 1]; ++e, ++rank) {
+        const int32_t d = ids[e];
+        if (e + 4 < offsets[q + 1]) __builtin_prefetch(doc_arena + doc_off[ids[e + 4]]);
+        memcpy(o, qs, ql); o += ql;
+        memcpy(o, " Q0 ", 4); o += 4;
+        const size_t dl = (size_t)(doc_off[d + 1] - doc_off[d]);
+        memcpy(o, doc_arena + doc_off[d], dl); o += dl;
+        *o++ = ' ';
+        o += fmt_uint(o, rank);
+        *o++ = ' ';
+        o += fmt_fixed6(o, scores[e]);
+        *o++ = ' ';
+        memcpy(o, tag, tag_len); o += tag_len;
+        *o++ = '\n';
+      }
+    }
+    P.used = (size_t)(o - P.buf.data());
+  });
+  for (auto& P : parts) QF_REQUIRE(!P.bad, QF_E_INVALID, "qf_runfile_write: out of memory");
+  const int fd = open(path, O_WRONLY | O_CREAT | O_TRUNC, 0644);
+  if (fd < 0) { qf::set_error("qf_runfile_write: cannot open %s", path); return QF_E_INVALID; }
+  std::vector<size_t> at((size_t)n_threads + 1, 0);
+  for (int t = 0; t < n_threads; ++t) at[(size_t)t + 1] = at[(size_t)t] + parts[(size_t)t].used;
+  if (at[(size_t)n_threads] && ftruncate(fd, (off_t)at[(size_t)n_threads]) != 0) {
+    close(fd);
+    qf::set_error("qf_runfile_write: cannot size %s", path);
+    return QF_E_INVALID;
+  }
+  std::vector<int> short_write((size_t)n_threads, 0);
+  parallel_for(n_threads, [&](int t) {
+    const Part& P = parts[(size_t)t];
+    size_t done = 0;
+    while (done < P.used) {
+      const ssize_t w = pwrite(fd, P.buf.data() + done, P.used - done, (off_t)(at[(size_t)t] + done));
+      if (w <= 0) { short_write[(size_t)t] = 1; return; }
+      done += (size_t)w;
+    }
+  });
+  close(fd);
   for (int t = 0; t < n_threads; ++t)
-    th.emplace_back([&, t]() {
-      const int j0 = (int)((long long)n_queries * t / n_threads), j1 = (int)((long long)n_queries * (t + 1) / n_threads);
-      std::string& out = bufs[(size_t)t];
-      char num[96];
-      {
-        size_t lines = 0;
-        for (int j = j0; j < j1; ++j) lines += (size_t)(offsets[qsel[j] + 1] - offsets[qsel[j]]);
-        out.reserve(lines * (48 + tag_len));
-      }
-      for (int j = j0; j < j1; ++j) {
-        const int q = qsel[j];
-        const char* qs = qid_arena + qid_off[q];
-        const size_t ql = (size_t)(qid_off[q + 1] - qid_off[q]);
-        int rank = 1;
-        for (int64_t e = offsets[q]; e < offsets[q + 1]; ++e, ++rank) {
-          const int32_t d = ids[e];
-          out.append(qs, ql);
-          out.append(" Q0 ", 4);
-          out.append(doc_arena + doc_off[d], (size_t)(doc_off[d + 1] - doc_off[d]));
-          int nl = 0;
-          num[nl++] = ' ';
-          nl += fmt_uint(num + nl, (unsigned long long)rank);
-          num[nl++] = ' ';
-          nl += fmt_fixed6(num + nl, scores[e]);
-          num[nl++] = ' ';
-          out.append(num, (size_t)nl);
-          out.append(tag, tag_len);
-          out.push_back('\n');
-        }
-      }
-    });
-  for (auto& x : th) x.join();
-  FILE* f = fopen(path, "wb");
-  if (!f) { qf::set_error("qf_runfile_write: cannot open %s", path); return QF_E_INVALID; }
-  for (auto& b : bufs)
-    if (!b.empty() && fwrite(b.data(), 1, b.size(), f) != b.size()) { fclose(f); qf::set_error("qf_runfile_write: short write"); return QF_E_INVALID; }
-  fclose(f);
+    if (short_write[(size_t)t]) { qf::set_error("qf_runfile_write: short write to %s", path); return QF_E_INVALID; }
   return QF_OK;
 }
