@@ -286,6 +286,47 @@ def test_native_parser_multithreaded_shards_equal_single_thread(tmp_path):
         assert (gd[got.cols[0]["doc"]] == ref_docs[ref.cols[0]["doc"]]).all()
 
 
+def test_native_parser_blank_lines_between_chunks_and_missing_final_newline(tmp_path):
+    """The columns are allocated from a line count and written in place; blank / whitespace-only lines leave gaps between
+    the threads' chunks that must be closed, and the last line may lack its newline."""
+    from qppfusion import native_io as nio
+    rng = np.random.default_rng(9)
+    lines, exp = [], []
+    for q in range(90):
+        docs = rng.choice(50_000, size=500, replace=False)
+        for i, dno in enumerate(docs):
+            lines.append(f"q{q}\tQ0  doc{dno} {i + 1} {1.0 / (i + 1):.6f} runB")
+            exp.append((f"q{q}", f"doc{dno}", i + 1, round(1.0 / (i + 1), 6)))
+            if rng.random() < 0.02:
+                lines.append("" if rng.random() < 0.5 else "   \t ")
+    p = tmp_path / "gaps.res"
+    p.write_text("\n\n" + "\n".join(lines))                     # leading blank lines, no trailing newline
+    assert p.stat().st_size > (1 << 20)
+    for nt in (1, 4, 7):
+        got = nio.parse_runs([str(p)], n_threads=nt)
+        c = got.cols[0]
+        assert len(c["qid"]) == len(exp) and got.all_micro
+        qs, ds = got.qid_strings(), got.doc_strings()
+        assert [qs[i] for i in c["qid"]] == [e[0] for e in exp]
+        assert ds[c["doc"]].tolist() == [e[1] for e in exp]
+        assert c["rank"].tolist() == [e[2] for e in exp]
+        assert np.array_equal(c["score"], np.array([e[3] for e in exp]))
+
+
+def test_native_writer_huge_and_non_finite_scores(tmp_path):
+    """"%.6f" of 1e300 is 308 characters: the writer's per-line bound must hold (reference: Python's f-string)."""
+    from qppfusion import native_io as nio
+    p = tmp_path / "one.res"
+    p.write_text("q1 Q0 d0 1 0.5 A\n")
+    parsed = nio.parse_runs([str(p)])
+    _, qorder = nio.pack_parsed(parsed)
+    vals = np.array([1e300, -1.7976931348623157e308, 1e22, float("inf"), float("-inf"), float("nan"), 3.25, 1e9])
+    out = tmp_path / "out.res"
+    nio.write_runfile_csr(str(out), parsed, qorder, np.array([0, len(vals)]), np.zeros(len(vals), dtype=np.int32), vals, "t")
+    got = [ln.split(" ")[4] for ln in out.read_text().splitlines()]
+    assert got == [f"{v:.6f}" for v in vals]
+
+
 def test_native_writer_fixed6_is_python_format(tmp_path):
     """The printf-free "%.6f" of qf_runfile_write against Python's formatting: random magnitudes, exact ties of the
     seventh decimal (k + 0.5) * 1e-6 representable in binary, negative zero, values at and beyond the 1e9 fallback."""
