@@ -292,21 +292,26 @@ def dense_leg(args, dev, world, rank, Q=Q_NQ, n_docs=None, label="BASELINE confi
     # their own streams, so that step i+1's sample / threshold / main pass runs while step i's exchange, merge and
     # launch gaps drain (the NCCL calls keep their issue order on every rank).  The per-kernel times behind the roofline
     # come from a separate SERIAL loop -- overlapped kernels would time each other's waiting.
-    INFLIGHT = max(1, int(os.environ.get("BENCH_DENSE_INFLIGHT", "2")))
+    # Measured (tools/dense_leg_probe.py, 1 and 2 B200): two searches in flight LOWER the device-resident rate (312 k ->
+    # 307 k, 604 k -> 589 k QPS: the persistent main-pass CTAs lose SMs to the next step's small kernels) and RAISE
+    # the end-to-end rate (295 k -> 301 k, 560 k -> 585 k: query upload and result download overlap the next search),
+    # so `value` runs one search at a time and `e2e` two.
+    INFLIGHT_V = max(1, int(os.environ.get("BENCH_DENSE_INFLIGHT", "1")))
+    INFLIGHT = max(2, INFLIGHT_V)
     run_streams = [torch.cuda.Stream(dev) for _ in range(INFLIGHT)]
 
-    def run_steps(fn, n):
+    def run_steps(fn, n, inflight=INFLIGHT):
         for s_ in run_streams:
             s_.wait_stream(stream)
         last = None
         for i in range(n):
-            with torch.cuda.stream(run_streams[i % INFLIGHT]):
+            with torch.cuda.stream(run_streams[i % inflight]):
                 last = fn()
         for s_ in run_streams:
             stream.wait_stream(s_)
         return last
 
-    sc, ids, st = run_steps(step, 3)
+    sc, ids, st = run_steps(step, 3, INFLIGHT_V)
     barrier()
     status_bad = int((st != 0).sum().item())
     if world > 1:
@@ -317,7 +322,7 @@ def dense_leg(args, dev, world, rank, Q=Q_NQ, n_docs=None, label="BASELINE confi
         sampler.start()
     barrier()
     e0.record(stream)
-    sc, ids, st = run_steps(step, steps)
+    sc, ids, st = run_steps(step, steps, INFLIGHT_V)
     e1.record(stream)
     barrier()
     ms = e0.elapsed_time(e1) / steps
@@ -403,7 +408,7 @@ def dense_leg(args, dev, world, rank, Q=Q_NQ, n_docs=None, label="BASELINE confi
             "scaling": "strong" if world > 1 else "n/a",
             "config": {"workload": f"BGE-base-shaped flat IP top-1000 ({label})", "queries": Q,
                        "docs": N_DENSE, "docs_per_gpu": n_local, "dim": D, "k": k, "dtype": "bf16 in, fp32 accumulate",
-                       "steps_in_flight": INFLIGHT,
+                       "steps_in_flight": INFLIGHT_V, "e2e_steps_in_flight": INFLIGHT,
                        "sharding": f"corpus rows x{world}" + (f", packed (score,id) rows truncated to the shard's top {qd.send_depth(k, world)}"
                                                               ": ONE all_to_all + qf_topk_merge_packed(Q/G) + completeness check "
                                                               "+ ONE all_gather, no host sync" if world > 1 else "")},
