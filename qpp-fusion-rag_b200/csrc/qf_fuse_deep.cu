@@ -189,12 +189,7 @@ __global__ void __launch_bounds__(NT) fuse_deep_kernel(const FuseParams p, unsig
       m.status = bad ? QF_QSTAT_BAD_LEN : 0;
       m.flag_dup = 0;
     }
-    for (u32 i = tid; i < H; i += NT) {
-      w.table[i] = EMPTY;
-      w.first[i] = EMPTY;
-      w.cnt[i] = 0u;
-      w.acc[i] = 0.0;
-    }
+    for (u32 i = tid; i < H; i += NT) w.table[i] = EMPTY;     // the per-slot state is initialised by the claiming posting
     __syncthreads();
     const int n = m.start[R];
     if ((m.status & QF_QSTAT_BAD_LEN) || n == 0) {
@@ -263,7 +258,13 @@ __global__ void __launch_bounds__(NT) fuse_deep_kernel(const FuseParams p, unsig
         u32 h = ((u32)id * 2654435761u) >> 7 & HM;
         while (true) {
           const u32 o = atomicCAS(&w.table[h], EMPTY, off);
-          if (o == EMPTY || gid[o] == id) break;
+          if (o == EMPTY) {                      // claimed: this posting initialises the slot (read after the barrier)
+            w.first[h] = EMPTY;
+            w.cnt[h] = 0u;
+            w.acc[h] = 0.0;
+            break;
+          }
+          if (gid[o] == id) break;
           h = (h + 1) & HM;
         }
         w.slotof[off] = h;
@@ -307,11 +308,12 @@ __global__ void __launch_bounds__(NT) fuse_deep_kernel(const FuseParams p, unsig
     if (m.flag_dup) {
       // exact sequential path: a doc id repeats inside one list (reference: every row accumulates and counts,
       // src/fusion.py:275,323-324)
-      for (u32 i = tid; i < H; i += NT) {
-        w.first[i] = EMPTY;
-        w.cnt[i] = 0u;
-        w.acc[i] = 0.0;
-      }
+      for (u32 i = tid; i < H; i += NT)
+        if (w.table[i] != EMPTY) {
+          w.first[i] = EMPTY;
+          w.cnt[i] = 0u;
+          w.acc[i] = 0.0;
+        }
       __syncthreads();
       if (tid == 0) {
         for (int r = 0; r < R; ++r)
