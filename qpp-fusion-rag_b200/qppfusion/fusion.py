@@ -39,10 +39,8 @@ Fused = Dict[str, List[Tuple[str, float]]]
 
 def _run_files(res_path: str, use_normalized: bool):
     suffix = ".norm.res" if use_normalized else ".res"
-    files = [f for f in os.listdir(res_path) if f.endswith(suffix)]
-    if not use_normalized:
-        files = [f for f in files if not f.endswith(".norm.res")]
-    if not files:
+    files = [f for f in os.listdir(res_path) if f.endswith(suffix)]     # use_normalized=False also picks up
+    if not files:                                                        # "X.norm.res" (as ranker "X.norm"), as the reference does
         raise FileNotFoundError(f"No {suffix} files found in {res_path}")
     # The reference keeps os.listdir order (src/fusion.py:60), i.e. filesystem dependent.  Ranker order
     # decides float64 accumulation order and the tie-break, so this build fixes it: sorted by name.
@@ -176,6 +174,10 @@ _RUN_NORMS = {"min-max": N.NORM_MINMAX, "minmax": N.NORM_MINMAX, "zscore": N.NOR
 
 
 def _ranx_fuse(runs: Dict[str, pd.DataFrame], method: int, rrf_k: float = 60.0, norm="min-max") -> Fused:
+    """ranx.fuse restated (parity unpinned: ranx is not installable offline).  Deliberate
+    differences in edge cases the reference pipeline never produces: queries are fused over the UNION of the runs' qids
+    (a run without rows for a query contributes nothing; ranx walks the first run's queries and fails on a run that
+    lacks one), and a single run is accepted (ranx.fuse wants at least two)."""
     if norm not in _RUN_NORMS:
         raise ValueError(f"Unknown run normalisation '{norm}'. Valid: min-max, zscore, none")
     packed = pack_runs(runs, mode="ranx")

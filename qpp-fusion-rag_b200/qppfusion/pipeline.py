@@ -54,26 +54,40 @@ class FusionStepGraph:
         del warm
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
-            self.qpp, self.weights, self.out, self.csr = self._body()
+            self.qpp, self.weights, self.out, self.csr, self.qpp_status = self._body()
 
     def _body(self):
         ids, sc, lens, feats, ranks = self.inputs
         c = self._cfg
         if self.wire is not None:
             ops.wire_unpack_(self.wire, ids, sc)
-        qpp, _status = ops.qpp_stats(sc, lens, feats, None, None, top_k=c["top_k"], k_cut=c["k_cut"])
+        qpp, qpp_status = ops.qpp_stats(sc, lens, feats, None, None, top_k=c["top_k"], k_cut=c["k_cut"])
         if c["colnorm"] or c["round6"]:
             ops.qpp_colnorm_(qpp, c["colnorm"] or "none", round6=c["round6"])
         w = ops.qpp_select_weight(qpp, c["qpp_index"])
         out = ops.fuse(ids, sc, lens, w, ranks, c["method"], c["norm"], c["rrf_k"], c["flags"],
                        want_counts=c["want_counts"], want_pos=c["want_pos"])
         csr = ops.compact_fused(out) if c["compact"] else None
-        return qpp, w, out, csr
+        return qpp, w, out, csr, qpp_status
 
     def replay(self):
         """Run the captured step on the current stream; returns the (static) FuseOut."""
         self.graph.replay()
         return self.out
+
+    def check(self) -> None:
+        """Raise like fusion.fuse_packed does when the last replay flagged a list (QSTAT_BAD_LEN: the query produced
+        no output; QSTAT_UNSORTED: the ordering contract of ranx semantics / the rank column was violated) or the QPP
+        kernel saw an unsorted list.  One small device->host read: call it when the result is consumed, not per replay."""
+        st = torch.stack([(self.out.status & N.QSTAT_BAD_LEN).max(), (self.out.status & N.QSTAT_UNSORTED).max(),
+                          self.qpp_status.max()]).cpu().tolist()
+        if st[0]:
+            raise ValueError("qf_fuse: invalid list length")
+        if st[1]:
+            bad = torch.nonzero(self.out.status & N.QSTAT_UNSORTED).flatten()[:5].tolist()
+            raise ValueError(f"qf_fuse: run lists violate the ordering contract for query rows {bad}")
+        if st[2]:
+            raise ValueError("qf_qpp_stats: a run list is not sorted by score descending")
 
 
 class ShardedFusionStep:

@@ -94,7 +94,9 @@ def test_loaders_and_errors(tmp_path):
     r = fusion.load_runs(str(runs))
     assert list(r.keys()) == ["A", "B"]                      # fixed, documented order
     assert r["A"]["qid"].tolist() == ["q1", "007"] and r["A"]["score"].dtype == np.float64
-    assert list(fusion.load_runs(str(runs), use_normalized=False).keys()) == ["A"]
+    # use_normalized=False: every "*.res" file, "X.norm.res" included under the ranker name "X.norm" -- what the
+    # reference's endswith(".res") + replace(".res", "") does (src/fusion.py:57-64)
+    assert list(fusion.load_runs(str(runs), use_normalized=False).keys()) == ["A.norm", "A", "B.norm"]
     assert load_run_file(runs / "A.res") == {"q1": [("d2", 12.5, 1)]}
     assert load_run_as_dict(runs / "B.norm.res") == {"q1": {"d1": 1.0, "d2": 0.0}}
     qdir = tmp_path / "qpp"

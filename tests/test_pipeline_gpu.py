@@ -49,3 +49,24 @@ def test_graph_step_matches_eager_and_tracks_input_refills(method):
             assert torch.equal(x[m], y[m])
         off, cids, csc = g.csr
         assert int(off[-1]) == int(n.sum()) and torch.equal(cids[: int(off[-1])], exp.ids[m])
+
+
+def test_graph_check_raises_on_flagged_lists():
+    """a graph replay must not pass QSTAT_BAD_LEN / QSTAT_UNSORTED silently -- FusionStepGraph.check() raises
+    like fusion.fuse_packed does (one small read when the result is consumed)."""
+    from qppfusion.pipeline import FusionStepGraph
+    dev = torch.device("cuda:0")
+    ids, sc, lens, feats = _inputs(33, 16, dev)
+    g = FusionStepGraph(ids, sc, lens, feats, qpp_index=5, method=0)
+    g.replay()
+    g.check()                                           # clean batch: nothing raised
+    keep = sc[3, 1, :2].clone()
+    sc[3, 1, 0], sc[3, 1, 1] = keep[1] - 5, keep[0] + 5  # ascending pair at the top of one list
+    g.replay()
+    with pytest.raises(ValueError, match="not sorted"):
+        g.check()
+    sc[3, 1, :2] = keep
+    lens[5, 2] = 10_000                                 # longer than K
+    g.replay()
+    with pytest.raises(ValueError, match="invalid list length"):
+        g.check()
