@@ -664,7 +664,8 @@ def c5_leg(args, dev, world, rank):
         w = ops.qpp_select_weight(qpp, 5)
         return w, ops.fuse(ids, micro, lens, w, None, 0, 0, 60.0, 0, want_counts=False, want_pos=False)
 
-    w, out = step()
+    for _ in range(2):              # two warm-up steps: both ping-pong sets of the 12 GB padded outputs exist before the
+        w, out = step()             # timed region (a cudaMalloc of that size inside it costs ~100 ms)
     torch.cuda.synchronize(dev)
     N_.profile_enable(True)
     steps = 3
