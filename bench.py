@@ -929,9 +929,11 @@ def run_ours(args):
 
     def e2e_measure(use_wire):
         if use_wire:
-            h_wire = [ops.wire_pack(st_[0].cpu(), st_[1].cpu(), st_[2].cpu(), pin=True) for st_ in sets[:NSETS]]
+            h_wire = [ops.wire_pack(src_[0], src_[1], src_[2], pin=True, coding=use_wire) for src_ in cpu_sets]
             d_wire = [w_.to(dev) for w_ in h_wire]
-            pairs = [[(d_wire[i].words, h_wire[i].words), (sets[i][2], sets[i][2].cpu().pin_memory()),
+            # (coding "for": the payload length depends on the data -- only the used prefix of the buffer travels)
+            pairs = [[(d_wire[i].words[:h_wire[i].used_words], h_wire[i].words[:h_wire[i].used_words]),
+                      (sets[i][2], sets[i][2].cpu().pin_memory()),
                       (sets[i][3], sets[i][3].cpu().pin_memory())] for i in range(NSETS)]
             for i in range(NSETS):                       # the graph must rebuild these from the wire on every replay
                 sets[i][0].zero_()
@@ -1012,15 +1014,20 @@ def run_ours(args):
                     torch.equal(graphs_[0].out.lens, ref_lens0) and torch.equal(graphs_[0].out.ids[0, :64], ref_row0))
         wire_info = None
         if use_wire:
-            wire_info = {"id_bits": h_wire[0].id_bits, "sc_bits": h_wire[0].sc_bits,
-                         "bytes_per_posting": h_wire[0].words.numel() * 8 / n_post}
+            wire_info = {"coding": use_wire, "id_bits": h_wire[0].id_bits,
+                         "sc_bits": h_wire[0].sc_bits if use_wire == "fixed" else "frame of reference per block of 32",
+                         "bytes_per_posting": h_wire[0].used_words * 8 / n_post}
         del graphs_
         return ms, up, d2h_bytes[0], same, wire_info
 
-    ms_plain, h2d_plain, d2h, same_plain, _ = e2e_measure(False)
+    cpu_sets = [[x.cpu() for x in st_[:3]] for st_ in sets[:NSETS]]      # (the wire variants zero the device copies)
+    ms_plain, h2d_plain, d2h, same_plain, _ = e2e_measure(None)
     union_plain = d2h
-    e2e_ms, h2d, d2h, same_wire, wire_info = e2e_measure(True)
-    assert same_plain and same_wire and d2h == union_plain, "e2e: downloaded run differs from the device-resident result"
+    ms_fixed, h2d_fixed, d2h_f, same_fixed, wire_fixed = e2e_measure("fixed")
+    e2e_ms, h2d, d2h, same_wire, wire_info = e2e_measure("for")
+    assert same_plain and same_fixed and same_wire and d2h == union_plain and d2h_f == union_plain, \
+        "e2e: downloaded run differs from the device-resident result"
+    del cpu_sets
     h_out = (h_off, h_ids, h_sc)
     barrier()
     pcie = pcie_probe(dev, h2d, max(d2h, 1 << 20))       # the same bytes per step, copies only: the ceiling of e2e
@@ -1042,10 +1049,10 @@ def run_ours(args):
     torch.cuda.empty_cache()
     api = api_e2e_leg(args, dev) if (rank == 0 and world == 1 and not args.no_extra) else None
 
-    times = torch.tensor([ms_total, e2e_ms, ms_plain], dtype=torch.float64, device=dev)
+    times = torch.tensor([ms_total, e2e_ms, ms_plain, ms_fixed], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    ms_total, e2e_ms, ms_plain = times.tolist()
+    ms_total, e2e_ms, ms_plain, ms_fixed = times.tolist()
 
     if rank == 0:
         hbm_peak, tf_peak, which = load_peaks()
@@ -1100,8 +1107,11 @@ def run_ours(args):
                     "int32_upload": {"value": world * Q / (ms_plain * 1e-3), "ms_per_step": ms_plain,
                                      "h2d_bytes_per_step": h2d_plain,
                                      "note": "the same step fed with the plain int32 [Q,R,K] id / score arrays"},
-                    "note": "pinned host buffers (postings bit-packed by qf_wire_pack: id_bits + sc_bits per posting) -> "
-                            "H2D -> graph replay (qf_wire_unpack + step + CSR compaction) -> D2H of the fused run; "
+                    "fixed_width_upload": {"value": world * Q / (ms_fixed * 1e-3), "ms_per_step": ms_fixed,
+                                           "h2d_bytes_per_step": h2d_fixed, "wire": wire_fixed},
+                    "note": "pinned host buffers (postings bit-packed by qf_wire_pack / qf_wire_for_pack: id_bits per doc id, "
+                            "scores frame-of-reference coded per block of 32) -> "
+                            "H2D -> graph replay (qf_wire_unpack + qf_wire_for_unpack + step + CSR compaction) -> D2H of the fused run; "
                             "consecutive steps overlap on 3 streams; the downloaded run is checked against the "
                             "device-resident result"},
             "roofline_issue": issue,
@@ -1111,7 +1121,7 @@ def run_ours(args):
             "cpu_reference_recorded": recorded_reference(),
             # per step: qpp 1 + colnorm 3 + select 1 + fuse 2 (streaming + fix-up) = 7; CSR compaction adds 4, the wire
             # expansion 1 (e2e is measured twice: int32 upload and bit-packed upload)
-            "gpu_launches": (7 * (args.steps + max(args.warmup, 4)) + 7 * (args.steps + 4) + (11 + 12) * (e2e_steps + 3 + 6)
+            "gpu_launches": (7 * (args.steps + max(args.warmup, 4)) + 7 * (args.steps + 4) + (11 + 12 + 13) * (e2e_steps + 3 + 6)
                              + (dense["gpu_launches"] if dense else 0) + (dense_c4["gpu_launches"] if dense_c4 else 0)
                              + (encoder["gpu_launches"] if encoder else 0)),
             "clocks": clocks,

@@ -200,6 +200,14 @@ QF_API int  qf_runfile_write(const char* path, const char* qid_arena, const int6
  *   qf_wire_words         : uint64 words of the stream (0 for a bad width: id_bits in [1,31], sc_bits in [1,32])
  *   qf_wire_pack   (host, multi-threaded) : QF_E_INVALID if a value does not fit
  *   qf_wire_unpack (device): expands into int32 doc_ids[n] / micro[n] (n = Q*R*K; 16-byte aligned)
+ * sc_bits == 0 carries the doc ids alone (micro may be NULL); the scores then travel frame-of-reference coded:
+ * a run list is sorted by score, so 32 consecutive scores span a small range.  Block b = list * ceil(K/32) + i/32
+ * stores base[b] = its smallest valid score and 32 offsets of w_b = bits(max - min) bits each (0 for a constant or
+ * empty block) as w_b uint32 words at payload[off[b] .. off[b+1]) -- 19 instead of 27 bits per score on bench.py's
+ * synthetic runs, header included.
+ *   qf_wire_for_blocks         : number of blocks = Q*R*ceil(K/32)  (base has that many entries, off one more)
+ *   qf_wire_for_pack   (host)  : payload capacity >= 32 * blocks + 1 words; *words_used = words to upload
+ *   qf_wire_for_unpack (device): expands into int32 micro[Q*R*K]
  * ---------------------------------------------------------------------------------------------- */
 QF_API size_t qf_wire_words(long long n, int id_bits, int sc_bits);
 QF_API int    qf_wire_plan(const int32_t* doc_ids, const int32_t* micro, const int32_t* lens, int Q, int R, int K,
@@ -208,6 +216,12 @@ QF_API int    qf_wire_pack(const int32_t* doc_ids, const int32_t* micro, const i
                            int id_bits, int sc_bits, int32_t sc_base, uint64_t* out, size_t out_words, int n_threads);
 QF_API int    qf_wire_unpack(const uint64_t* wire, long long n, int id_bits, int sc_bits, int32_t sc_base,
                              int32_t* doc_ids, int32_t* micro, void* stream);
+QF_API long long qf_wire_for_blocks(int Q, int R, int K);
+QF_API int    qf_wire_for_pack(const int32_t* micro, const int32_t* lens, int Q, int R, int K, int n_threads,
+                               int32_t* base, uint32_t* off, uint32_t* payload, size_t payload_cap_words,
+                               size_t* words_used);
+QF_API int    qf_wire_for_unpack(const int32_t* base, const uint32_t* off, const uint32_t* payload, int Q, int R, int K,
+                                 int32_t* micro, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * QPP statistics  --  replaces the JVM round trip QPPBridge.compute_batch -> qpp.QPPBridge

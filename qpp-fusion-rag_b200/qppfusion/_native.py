@@ -68,6 +68,9 @@ PROTOTYPES = {
     "qf_wire_plan": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "qf_wire_pack": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, ctypes.c_int32, _vp, _sz, _i]),
     "qf_wire_unpack": (_i, [_vp, ctypes.c_longlong, _i, _i, ctypes.c_int32, _vp, _vp, _vp]),
+    "qf_wire_for_blocks": (ctypes.c_longlong, [_i, _i, _i]),
+    "qf_wire_for_pack": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    "qf_wire_for_unpack": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "qf_compact_workspace_bytes": (_sz, [_i]),
     "qf_compact_fused": (_i, [_vp, _vp, _vp, _i, ctypes.c_longlong, _vp, _vp, _vp, _vp, _sz, _vp]),
     "qf_qpp_stats": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),

@@ -119,22 +119,43 @@ def compact_fused(out: "FuseOut", cap: Optional[int] = None):
 
 # ---------------------------------------------------------------------------------------------- wire format
 class Wire(NamedTuple):
-    """Bit-packed postings (csrc/qf_wire.cu): `words` int64 [qf_wire_words] (host, optionally pinned, or device)."""
+    """Bit-packed postings (csrc/qf_wire.cu).  `words` is ONE int64 buffer (host, optionally pinned, or device):
+    coding "fixed": the stream of (id_bits + sc_bits)-bit postings;
+    coding "for"  : [ doc-id stream (id_bits each) | block bases int32 | block offsets uint32 | payload uint32 ] -- the
+                    scores frame-of-reference coded per block of 32; the payload length depends on the data, `used`
+                    (int64 elements) is what has to be uploaded, the buffer is sized for the worst case."""
     words: torch.Tensor
     shape: Tuple[int, int, int]      # (Q, R, K) of the arrays it expands to
     id_bits: int
-    sc_bits: int
+    sc_bits: int                     # 0 for coding "for"
     sc_base: int
+    coding: str = "fixed"
+    used: int = -1                   # int64 elements in use (-1: all)
 
     def to(self, device, non_blocking: bool = False) -> "Wire":
         return self._replace(words=self.words.to(device, non_blocking=non_blocking))
 
+    @property
+    def used_words(self) -> int:
+        return self.words.numel() if self.used < 0 else self.used
+
+
+def _for_segments(Q: int, R: int, K: int, id_bits: int):
+    """int64-element offsets of the four segments of a coding="for" buffer: (ids, base, off, payload, end)."""
+    n = Q * R * K
+    nb = int(N.lib().qf_wire_for_blocks(Q, R, K))
+    ids_w = int(N.lib().qf_wire_words(n, id_bits, 0))
+    base_w, off_w, pay_w = (nb * 4 + 7) // 8, ((nb + 1) * 4 + 7) // 8, ((nb * 32 + 1) * 4 + 7) // 8
+    a = ids_w
+    return 0, a, a + base_w, a + base_w + off_w, a + base_w + off_w + pay_w
+
 
 def wire_pack(doc_ids: torch.Tensor, micro: torch.Tensor, lens: torch.Tensor, pin: bool = False,
-              n_threads: int = 0, widths: Optional[Tuple[int, int, int]] = None) -> Wire:
+              n_threads: int = 0, widths: Optional[Tuple[int, int, int]] = None, coding: str = "fixed") -> Wire:
     """HOST side: int32 [Q, R, K] doc ids (dictionary codes >= 0) + int32 micro-unit scores + lens -> Wire.
-    widths = (id_bits, sc_bits, sc_base) fixes the layout (e.g. to refill one pinned buffer step after step);
-    default: the smallest that fits (qf_wire_plan)."""
+    coding="fixed": widths = (id_bits, sc_bits, sc_base) fixes the layout (e.g. to refill one pinned buffer step after
+    step); default: the smallest that fits (qf_wire_plan).  coding="for": scores frame-of-reference coded per block of
+    32 (sorted lists: ~8 bits per score fewer); only widths[0] = id_bits is used."""
     import os
     for t_ in (doc_ids, micro, lens):
         if t_.is_cuda or t_.dtype != torch.int32 or not t_.is_contiguous():
@@ -142,6 +163,8 @@ def wire_pack(doc_ids: torch.Tensor, micro: torch.Tensor, lens: torch.Tensor, pi
     Q, R, K = doc_ids.shape
     if micro.shape != doc_ids.shape or lens.shape != (Q, R):
         raise ValueError("micro must have the shape of doc_ids, lens [Q, R]")
+    if coding not in ("fixed", "for"):
+        raise ValueError("coding must be 'fixed' or 'for'")
     nt = n_threads or min(32, os.cpu_count() or 1)
     if widths is None:
         ib, sb, base = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_int32(0)
@@ -149,8 +172,23 @@ def wire_pack(doc_ids: torch.Tensor, micro: torch.Tensor, lens: torch.Tensor, pi
                                      ctypes.addressof(sb), ctypes.addressof(base)))
         widths = (ib.value, sb.value, base.value)
     ib_, sb_, base_ = (int(x) for x in widths)
+    if coding == "for":
+        o_ids, o_base, o_off, o_pay, end = _for_segments(Q, R, K, ib_)
+        if o_base == 0:
+            raise ValueError(f"wire_pack: bad id_bits={ib_}")
+        words = torch.empty((end,), dtype=torch.int64, pin_memory=pin)
+        words[o_off - 1] = 0                      # the segments are padded to 8 bytes: keep the stream deterministic
+        words[o_pay - 1] = 0
+        N.check(N.lib().qf_wire_pack(N.ptr(doc_ids), None, N.ptr(lens), Q, R, K, ib_, 0, 0, N.ptr(words), o_base, nt))
+        used = ctypes.c_size_t(0)
+        p0 = words.data_ptr()
+        N.check(N.lib().qf_wire_for_pack(N.ptr(micro), N.ptr(lens), Q, R, K, nt, p0 + 8 * o_base, p0 + 8 * o_off,
+                                         p0 + 8 * o_pay, (end - o_pay) * 2, ctypes.addressof(used)))
+        if used.value & 1:
+            words.view(torch.int32)[2 * o_pay + int(used.value)] = 0
+        return Wire(words, (Q, R, K), ib_, 0, 0, "for", o_pay + (int(used.value) + 1) // 2)
     nw = int(N.lib().qf_wire_words(Q * R * K, ib_, sb_))
-    if nw == 0:
+    if nw == 0 or sb_ == 0:
         raise ValueError(f"wire_pack: bad widths id_bits={ib_} sc_bits={sb_}")
     words = torch.empty((nw,), dtype=torch.int64, pin_memory=pin)
     N.check(N.lib().qf_wire_pack(N.ptr(doc_ids), N.ptr(micro), N.ptr(lens), Q, R, K, ib_, sb_, base_, N.ptr(words), nw, nt))
@@ -164,9 +202,18 @@ def wire_unpack_(wire: Wire, doc_ids: torch.Tensor, micro: torch.Tensor) -> None
     if tuple(doc_ids.shape) != tuple(wire.shape) or micro.shape != doc_ids.shape or \
             doc_ids.dtype != torch.int32 or micro.dtype != torch.int32:
         raise TypeError("wire_unpack_: outputs must be int32 tensors of the wire's [Q, R, K] shape")
+    Q, R, K = wire.shape
     with torch.cuda.device(dev):
-        N.check(N.lib().qf_wire_unpack(N.ptr(wire.words), doc_ids.numel(), wire.id_bits, wire.sc_bits, wire.sc_base,
-                                       N.ptr(doc_ids), N.ptr(micro), N.stream_ptr(dev)))
+        if wire.coding == "for":
+            _o_ids, o_base, o_off, o_pay, _end = _for_segments(Q, R, K, wire.id_bits)
+            p0 = wire.words.data_ptr()
+            N.check(N.lib().qf_wire_unpack(p0, doc_ids.numel(), wire.id_bits, 0, 0, N.ptr(doc_ids), None,
+                                           N.stream_ptr(dev)))
+            N.check(N.lib().qf_wire_for_unpack(p0 + 8 * o_base, p0 + 8 * o_off, p0 + 8 * o_pay, Q, R, K, N.ptr(micro),
+                                               N.stream_ptr(dev)))
+        else:
+            N.check(N.lib().qf_wire_unpack(N.ptr(wire.words), doc_ids.numel(), wire.id_bits, wire.sc_bits, wire.sc_base,
+                                           N.ptr(doc_ids), N.ptr(micro), N.stream_ptr(dev)))
 
 
 # ---------------------------------------------------------------------------------------------- qpp
