@@ -962,25 +962,34 @@ def run_ours(args):
 
             def upload(i):
                 with torch.cuda.stream(s_h2d):
-                    if i >= NB:
-                        s_h2d.wait_event(ev_cmp[i - NB])        # that set's previous step has consumed its inputs
+                    if i >= NSETS:
+                        s_h2d.wait_event(ev_cmp[i - NSETS])     # that set's previous step has consumed its inputs
                     for dst, src in pairs[i % NSETS]:
                         dst.copy_(src, non_blocking=True)
                     ev_h2d[i].record(s_h2d)
 
-            upload(0)
-            for i in range(n_steps):
-                if i + 1 < n_steps:
-                    upload(i + 1)
-                b = i % NB
-                g = graphs_[i % NSETS]
+            def compute(i):
                 with torch.cuda.stream(s_cmp):
                     s_cmp.wait_event(ev_h2d[i])
                     if i >= NSETS:
                         s_cmp.wait_event(ev_d2h[i - NSETS])     # that graph's previous outputs have been downloaded
-                    g.replay()
+                    graphs_[i % NSETS].replay()
                     ev_cmp[i].record(s_cmp)
-                off, cids, csc = g.csr
+
+            # software pipeline: uploads run two steps ahead and the next step's kernels are queued BEFORE the host
+            # waits for this step's CSR total (it needs the number of fused docs to size the download), so neither the
+            # copy engine nor the SMs idle while the host blocks
+            upload(0)
+            if n_steps > 1:
+                upload(1)
+            compute(0)
+            for i in range(n_steps):
+                if i + 2 < n_steps:
+                    upload(i + 2)
+                if i + 1 < n_steps:
+                    compute(i + 1)
+                b = i % NB
+                off, cids, csc = graphs_[i % NSETS].csr
                 with torch.cuda.stream(s_d2h):
                     s_d2h.wait_event(ev_cmp[i])
                     h_off[b].copy_(off, non_blocking=True)
