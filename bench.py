@@ -924,7 +924,7 @@ def run_ours(args):
     h_off = [torch.empty((Q + 1,), dtype=torch.int64).pin_memory() for _ in range(NB)]
     h_ids = [torch.empty((n_post,), dtype=torch.int32).pin_memory() for _ in range(NB)]
     h_sc = [torch.empty((n_post,), dtype=torch.float64).pin_memory() for _ in range(NB)]
-    s_h2d, s_cmp, s_d2h = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    s_h2d, s_cmp, s_d2h, s_off = (torch.cuda.Stream(dev) for _ in range(4))
     e2e_steps = max(4, min(args.steps, 12))
 
     def e2e_measure(use_wire):
@@ -990,13 +990,14 @@ def run_ours(args):
                     compute(i + 1)
                 b = i % NB
                 off, cids, csc = graphs_[i % NSETS].csr
-                with torch.cuda.stream(s_d2h):
-                    s_d2h.wait_event(ev_cmp[i])
+                with torch.cuda.stream(s_off):                   # own stream: not queued behind step i-1's big download
+                    s_off.wait_event(ev_cmp[i])
                     h_off[b].copy_(off, non_blocking=True)
-                    ev_off.record(s_d2h)
+                    ev_off.record(s_off)
                 ev_off.synchronize()                             # host needs the total before sizing the copy
                 total = int(h_off[b][-1])
                 with torch.cuda.stream(s_d2h):
+                    s_d2h.wait_event(ev_cmp[i])
                     h_ids[b][:total].copy_(cids[:total], non_blocking=True)
                     h_sc[b][:total].copy_(csc[:total], non_blocking=True)
                     ev_d2h[i].record(s_d2h)
@@ -1006,10 +1007,10 @@ def run_ours(args):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        for s_ in (s_h2d, s_cmp, s_d2h):
+        for s_ in (s_h2d, s_cmp, s_d2h, s_off):
             s_.wait_stream(stream)
         e2e_run(e2e_steps)
-        for s_ in (s_h2d, s_cmp, s_d2h):
+        for s_ in (s_h2d, s_cmp, s_d2h, s_off):
             stream.wait_stream(s_)
         e1.record(stream)
         barrier()
