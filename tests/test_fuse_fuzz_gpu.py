@@ -1,5 +1,5 @@
 """GPU fuzz: random shapes / options through the qf_fuse kernel paths (gather, streaming, each with the larger table;
-general) must agree bit for bit; a sample of the queries is also checked against the Python oracle."""
+general; qf_fuse_deep) must agree bit for bit; a sample of the queries is also checked against the Python oracle."""
 import numpy as np
 import pytest
 import torch
@@ -8,7 +8,7 @@ from oracle import fusion_oracle as fo
 
 pytestmark = pytest.mark.gpu
 
-PATHS = {"stream": 0, "stream-large": 8, "gather": 0x400, "gather-large": 0x408, "general": 0x200}
+PATHS = {"stream": 0, "stream-large": 8, "gather": 0x400, "gather-large": 0x408, "general": 0x200, "deep": 0x800}
 
 
 def _random_case(rng):
@@ -76,7 +76,7 @@ def test_kernel_paths_agree_and_match_the_oracle(seed):
         n = ref[4]
         assert (n >= 0).all()
         m = np.arange(c["R"] * c["K"])[None, :] < n[:, None]
-        for name in ("gather", "gather-large", "stream", "stream-large"):
+        for name in ("gather", "gather-large", "stream", "stream-large", "deep"):
             got = outs[name]
             desc = (name, {k: c[k] for k in ("R", "K", "Q", "method", "norm", "flags")})
             assert np.array_equal(got[4], n) and np.array_equal(got[5], ref[5]), desc
