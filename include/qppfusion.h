@@ -408,7 +408,8 @@ QF_API int    qf_linear_bf16(const void* W, const void* X, const void* bias, voi
  * (nullable = all L; clamped to [1, L]).  Outputs (either may be null): out_bf16[B][H] -- directly the `queries_bf16`
  * of qf_dense_topk -- and out_f32[B][H], the L2-normalised embedding.  out_status[b] (nullable): bit 0 = a token id
  * outside [0, vocab) (replaced by id 0, never read out of bounds).  bf16 activations, fp32 accumulation and
- * statistics; the four Linear layers per block run through cuBLASLt, everything else is in csrc/qf_bert.cu.
+ * statistics; the four Linear layers per block run through qf_linear_bf16's tcgen05 kernel (cuBLASLt only for shapes
+ * outside its envelope), everything else is in csrc/qf_bert.cu.
  */
 QF_API int    qf_bert_encode(const qf_bert_config* cfg, const void* weights_bf16, const int32_t* tokens,
                              const int32_t* lens, int B, int L, void* out_bf16, float* out_f32, int32_t* out_status,

@@ -65,7 +65,7 @@ def build(force=False, verbose=False):
                 if r.returncode != 0:
                     raise RuntimeError("nvcc failed for " + cmd[-3])
     if jobs or force or _mtime(LIB) < max(_mtime(o) for o in objs):
-        # cuBLASLt (the encoder's Linear layers) is the one dynamic dependency; inside a PyTorch process the loader
+        # cuBLASLt (the encoder's Linear layers outside the own GEMM's envelope) is the one dynamic dependency; inside a PyTorch process the loader
         # binds it to the libcublasLt.so.12 torch has already loaded, otherwise to the toolkit's copy (rpath)
         cmd = [NVCC] + ARCH + ["-shared", "-o", LIB] + objs + ["-Xcompiler", "-fPIC", "-lcublasLt",
                                                                "-Xlinker", "-rpath=/usr/local/cuda/lib64"]

@@ -3,8 +3,9 @@
 // normalize_embeddings=True), src/retrievers/bge.py:153-170; model = HF BertModel + CLS pooling + L2 normalisation).
 //
 // Activations are bf16 [B*L, H] row-major (one row per token, padded to L tokens per query), statistics and
-// accumulation fp32.  The four Linear layers of a block are plain library GEMMs (cuBLASLt, bf16 in / fp32 accumulate,
-// bias in the epilogue); everything between them is hand-written and fused:
+// accumulation fp32.  The four Linear layers of a block run on the library's own tcgen05 GEMM (csrc/qf_gemm.cu: TMA loads,
+// TMEM accumulators, bias + erf-GELU in the epilogue; since round 2); cuBLASLt is kept only for shapes outside that
+// kernel's envelope (row counts not a multiple of 128 never occur: the token rows are padded).  Between the GEMMs:
 //   embed_ln      word + position + type embedding -> LayerNorm                       (warp per token, 16-byte loads)
 //   attn          L <= 128: one WARP per (query, head) on mma.sync tiles, K/V staged in the warp's shared-memory slice,
 //                 masked softmax on the accumulator fragments, which then ARE the A operand of P.V;
