@@ -315,6 +315,41 @@ def test_native_parser_blank_lines_between_chunks_and_missing_final_newline(tmp_
         assert np.array_equal(c["score"], np.array([e[3] for e in exp]))
 
 
+def test_native_parser_fuzz_separators_blank_lines_and_thread_counts(tmp_path):
+    """Random run files: mixed separators, leading / trailing blanks, CR line ends, blank lines, empty files, missing
+    final newline, small and multi-chunk sizes -- every thread count returns exactly the rows that were written."""
+    import random
+    from qppfusion import native_io as nio
+    rnd = random.Random(7)
+    for trial in range(12):
+        big = trial % 4 == 0
+        n = rnd.randrange(40000, 50000) if big else rnd.randrange(0, 200)
+        lines, exp, q = [], [], 0
+        for _ in range(n):
+            q += rnd.random() < 0.02
+            if rnd.random() < 0.03:
+                lines.append(rnd.choice(["", " ", "\t", "  \t  ", "\r"]))
+                continue
+            sep = rnd.choice([" ", "  ", "\t", " \t "])
+            doc = "d" + str(rnd.randrange(0, 5000 if big else 50)) + rnd.choice(["", "-x", "__"])
+            sc = rnd.choice([f"{rnd.uniform(-50, 50):.6f}", f"{rnd.uniform(0, 1):.3f}", str(rnd.randrange(-5, 5))])
+            rank = rnd.randrange(1, 2000)
+            lines.append(rnd.choice(["", " "]) + sep.join([f"q{q}", "Q0", doc, str(rank), sc, "tag"]) + rnd.choice(["", " ", "\r"]))
+            exp.append((f"q{q}", doc, rank, float(sc)))
+        p = tmp_path / f"f{trial}.res"
+        with open(p, "w", newline="") as f:
+            f.write("\n".join(lines) + rnd.choice(["\n", "", "\n\n"]))
+        for nt in (1, 3, 8):
+            got = nio.parse_runs([str(p)], n_threads=nt)
+            c = got.cols[0]
+            assert len(c["qid"]) == len(exp) and got.all_micro, (trial, nt)
+            qs, ds = got.qid_strings(), got.doc_strings()
+            assert [qs[i] for i in c["qid"]] == [e[0] for e in exp]
+            assert (ds[c["doc"]].tolist() if exp else []) == [e[1] for e in exp]
+            assert c["rank"].tolist() == [e[2] for e in exp]
+            assert np.array_equal(c["score"], np.array([e[3] for e in exp], dtype=np.float64))
+
+
 def test_native_writer_huge_and_non_finite_scores(tmp_path):
     """"%.6f" of 1e300 is 308 characters: the writer's per-line bound must hold (reference: Python's f-string)."""
     from qppfusion import native_io as nio
