@@ -390,6 +390,28 @@ def dense_leg(args, dev, world, rank, Q=Q_NQ, n_docs=None, label="BASELINE confi
             overlap = sum(len(set(ri[i].tolist()) & set(ids[i].tolist())) for i in range(nq)) / (nq * k)
             parity = {"queries_checked": nq, "top1000_overlap_vs_fp32": overlap,
                       "max_abs_score_diff_vs_fp32": float((rs - sc[:nq]).abs().max().item())}
+    if world > 1 and n_local <= 3_000_000:
+        # sharded search vs an independent fp32 reference: every rank scores 8 queries against its shard with a torch
+        # matmul, the per-shard top-k are gathered and merged, and rank 0 compares with the sharded result
+        nq = 8
+        rs, ri = torch.topk(q32[:nq] @ corpus.float().T, min(k, n_local), dim=1)
+        if rs.shape[1] < k:
+            rs = torch.cat([rs, torch.full((nq, k - rs.shape[1]), float("-inf"), device=dev)], dim=1)
+            ri = torch.cat([ri, torch.full((nq, k - ri.shape[1]), -1, device=dev, dtype=ri.dtype)], dim=1)
+        ri = ri + lo
+        all_s = [torch.empty_like(rs) for _ in range(world)]
+        all_i = [torch.empty_like(ri) for _ in range(world)]
+        dist.all_gather(all_s, rs.contiguous())
+        dist.all_gather(all_i, ri.contiguous())
+        if rank == 0:
+            cs, ci = torch.cat(all_s, dim=1), torch.cat(all_i, dim=1)
+            ms_, sel = torch.topk(cs, k, dim=1)
+            mi_ = torch.gather(ci, 1, sel)
+            got_s, got_i = sc.scores[:nq], sc.ids[:nq]
+            overlap = sum(len(set(mi_[i].tolist()) & set(got_i[i].tolist())) for i in range(nq)) / (nq * k)
+            parity = {"queries_checked": nq, "top1000_overlap_vs_fp32": overlap,
+                      "max_abs_score_diff_vs_fp32": float((ms_ - got_s).abs().max().item()),
+                      "reference": "per-shard torch fp32 matmul + top-k, gathered and merged on rank 0"}
     dense_cpu = None
     if world == 1 and n_docs is None and not args.no_cpu_baseline:      # configs[2] only, rank 0, bounded (~6 s)
         try:
